@@ -1,0 +1,189 @@
+/* vtb200.h — C-ABI of libvtb200.so: the sm_100a kernels behind the transformer-block hot path of
+ * rosinality/vision-transformers-pytorch (models/{vit,swin_transformer,pvt,halo_transformer,twins}.py).
+ *
+ * The reference has NO native interface: every op below replaces an ATen call issued from the
+ * reference's nn.Module.forward (and the autograd backward of it).  Each entry point cites the
+ * reference call site it stands in for (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory owned by the caller (the library never
+ *     allocates or frees device memory); all work is enqueued on `stream`, nothing synchronises.
+ *   - return 0 on success, negative on error; vtb_last_error() gives the message (thread-local).
+ *   - "bf16" pointers are `const void*` to raw 16-bit brain-floats; "f32" are float*.
+ *   - re-entrant: no global mutable state except the resolved driver entry point (vtb_init).
+ */
+#ifndef VTB200_H
+#define VTB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vtb_stream_t; /* == cudaStream_t */
+
+const char* vtb_last_error(void);
+int vtb_version(void);
+/* Resolve cuTensorMapEncodeTiled through the runtime, query SM count.  Idempotent. */
+int vtb_init(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM on tcgen05 (TMA -> smem -> UMMA -> TMEM -> epilogue):  C[M,N] = alpha * sum_k A(m,k) B(n,k)
+ * Replaces every nn.Linear / k=s Conv2d-as-GEMM forward, dgrad and wgrad on the path:
+ *   layer.py:191-196 (FFN), vit.py:30,43 / swin:128,155 / pvt:40,52,67 / halo:63,107 / twins:66,77,91,130,150
+ *   (attention projections), vit.py:73,76 / pvt.py:111 / pvt.py:27 / twins.py:54 (patch & reduce convs),
+ *   swin:209,226 / halo:162 / twins:209 (patchify linears), vit.py:200 / swin:377 / pvt:278 / halo:219,278 (heads).
+ * Operand layouts (row-major storage, ld in elements, bf16):
+ *   a_mn_major=0: A stored [M][K] (K contiguous)      a_mn_major=1: A stored [K][M] (M contiguous)
+ *   b_mn_major=0: B stored [N][K] (K contiguous)      b_mn_major=1: B stored [K][N] (N contiguous)
+ *   forward  y = x W^T : A=x (0), B=W (0)     dgrad dx = dy W : A=dy (0), B=W (1)
+ *   wgrad dW = dy^T x  : A=dy (1), B=x (1)
+ * Epilogue, applied in this order to v = alpha*acc:
+ *   v += bias[n]                                   (bias != NULL)
+ *   VTB_EPI_SILU_DUAL : out  = bf16(v) ; v = silu(float(bf16(v))) ; stored to out2   (layer.py:193)
+ *   VTB_EPI_SILU_GRAD : v *= silu'(aux[m,n])                                       (backward of it)
+ *   v *= row_scale[m / rows_per_scale]             (DropPath keep-mask/keep-prob, layer.py:176-178)
+ *   v += rowmod_add[(m % out_group_rows) * ld_rowmod + n]   (positional embedding, vit.py:143)
+ *   v += resid[m_out*ldr + n]                      (residual add, vit.py:60-61 etc.)
+ *   out[m_out*ldo + n] = v (bf16 or f32); with accumulate=1: atomicAdd (f32 only; split-K / grad accumulation)
+ *   m_out = m                               if out_group_rows == 0
+ *         = (m / out_group_rows) * out_group_stride + out_group_off + m % out_group_rows   otherwise
+ * ---------------------------------------------------------------------------------------------- */
+enum { VTB_EPI_NONE = 0, VTB_EPI_SILU_DUAL = 1, VTB_EPI_SILU_GRAD = 2 };
+
+typedef struct {
+  int32_t M, N, K;
+  const void* A; int32_t lda; int32_t a_mn_major;
+  const void* B; int32_t ldb; int32_t b_mn_major;
+  void* out; int32_t ldo; int32_t out_f32;
+  void* out2;                         /* bf16, same ld as out (SILU_DUAL only) */
+  const float* bias;                  /* [N] or NULL */
+  const float* resid; int32_t ldr;    /* f32 or NULL */
+  const float* row_scale; int32_t rows_per_scale;
+  const void* aux; int32_t ldaux;     /* bf16 pre-activation (SILU_GRAD) */
+  int32_t epilogue;
+  int32_t splits;                     /* split-K factor; 0 = auto; >1 requires accumulate=1 */
+  int32_t accumulate;
+  int32_t out_group_rows, out_group_stride, out_group_off;
+  const float* rowmod_add; int32_t ld_rowmod;
+  float alpha;
+} vtb_gemm_params;
+
+int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (nn.LayerNorm: vit.py:13,52,54,113 / swin:12,180,185,206,221,277 / pvt:9,31,86,89,112,202 /
+ * halo:9,133,138,159,215,217 / twins:12,166-178,206,258).  fp32 statistics, affine.
+ * Input rows are fp32 (the residual stream).  Optional patchify gather (swin:15-22, A4 in SURVEY):
+ *   patch_s > 1: x is NHWC [B, Hin, Win, C]; row r = (b, by, bx) gathers features (sy*s+sx)*C + c,
+ *   cols must equal s*s*C.   patch_s <= 1: x is [rows, cols].
+ * y is bf16 (y_f32=0) or f32.  mean/rstd [rows] are saved for backward.
+ * rowmod_add (optional, f32 [group_rows, cols]) is added AFTER normalisation by (r % group_rows)  (pvt.py:140).
+ * ---------------------------------------------------------------------------------------------- */
+int vtb_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps,
+                      int64_t rows, int32_t cols, int32_t patch_s, int32_t Hin, int32_t Win,
+                      void* y, int32_t y_f32, float* mean, float* rstd,
+                      const float* rowmod_add, int32_t group_rows, vtb_stream_t stream);
+
+/* Backward of the above.  dy is bf16 (dy_f32=0) or f32 [rows, cols].
+ *   dx_row = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
+ *   dx_out[r] = (dx_in ? dx_in[r] : 0) + dx_row          (f32; patchify mode scatters back to NHWC)
+ *   if dx_bf16 != NULL: dx_bf16[r] = bf16(dx_out[r] * (row_scale ? row_scale[r / rows_per_scale] : 1))
+ *   partial dgamma/dbeta are accumulated into dgamma/dbeta (f32 [cols], atomicAdd; caller zeroes or
+ *   passes the .grad buffer to accumulate into).
+ */
+int vtb_layernorm_bwd(const void* dy, int32_t dy_f32, const float* x, const float* gamma,
+                      const float* mean, const float* rstd, int64_t rows, int32_t cols,
+                      int32_t patch_s, int32_t Hin, int32_t Win, const float* dx_in, float* dx_out,
+                      void* dx_bf16, const float* row_scale, int32_t rows_per_scale,
+                      float* dgamma, float* dbeta, vtb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head attention, all four variants of the reference through one geometry descriptor:
+ *   VTB_ATTN_GLOBAL  vit.py:27-45, pvt.py:32-69, twins.py:58-93   group g = image b
+ *   VTB_ATTN_WINDOW  swin:103-160 (shift/bias/mask), twins.py:109-152   g = (b, window)
+ *   VTB_ATTN_HALO    halo:57-114   g = (b, block); keys gathered from a (W+2h)^2 zero-padded halo
+ * Q,K,V,O live in token-major buffers: element (token t, head h, d) = base[t*ld + h*dh + d].
+ * S = scale * Q K^T + rel_bias[pos[i,j], h] ; S = -inf where mask[g % n_mask, i, j] ; P = softmax(S) ; O = P V.
+ * Scores and probabilities never leave the SM.  lse [groups, H, Nq] (log-sum-exp) is saved for backward.
+ * ---------------------------------------------------------------------------------------------- */
+enum { VTB_ATTN_GLOBAL = 0, VTB_ATTN_WINDOW = 1, VTB_ATTN_HALO = 2 };
+
+typedef struct {
+  int32_t mode;
+  int32_t batch, heads, dh;
+  int32_t nq, nkv;             /* queries / key slots per group */
+  int32_t Hs, Ws;              /* spatial map (WINDOW/HALO) */
+  int32_t window, shift, halo; /* shift = floor(window/2) on shifted layers else 0 */
+  float scale;                 /* 1/sqrt(dh), applied after QK^T (vit.py:37) */
+  const void* q; int32_t ldq;
+  const void* k; int32_t ldk;
+  const void* v; int32_t ldv;
+  void* o; int32_t ldo;
+  float* lse;
+  const float* rel_bias;       /* [n_pos, heads] f32 (rel_pos.weight) or NULL */
+  const int32_t* pos;          /* [nq, nkv] or NULL */
+  int32_t n_pos;               /* rows of rel_bias (swin 169, halo 253; <= 512) */
+  const uint8_t* mask;         /* [n_mask, nq, nkv], 1 = masked (swin local_mask) or NULL */
+  int32_t n_mask;
+  /* backward only */
+  const void* dout; int32_t lddo;
+  void* dq; int32_t lddq;      /* bf16 */
+  void* dk; int32_t lddk;      /* bf16, or f32 atomics when dkv_f32 (HALO: tokens shared by blocks) */
+  void* dv; int32_t lddv;
+  int32_t dkv_f32;
+  float* delta;                /* workspace [groups, H, Nq] */
+  float* drel_bias;            /* [n_pos, heads] f32, atomicAdd */
+} vtb_attn_params;
+
+int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream);
+int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small memory-bound helpers.
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 -> bf16 cast (autocast's weight cast, torch.cuda.amp.autocast at train.py:273). */
+int vtb_cast_f32_bf16(const float* src, void* dst, int64_t n, vtb_stream_t stream);
+/* bf16 <- f32 with row stride: dst[r, c] = bf16(src[r, c]) for strided views. */
+int vtb_cast_f32_bf16_2d(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows,
+                         int32_t cols, vtb_stream_t stream);
+/* dst[r, c] = bf16(src[r, c] * row_scale[r / rows_per_scale])  (row_scale NULL => 1): the DropPath-scaled
+ * bf16 copy of the residual-stream gradient that feeds the branch's dgrad/wgrad GEMMs (layer.py:178 adjoint). */
+int vtb_scale_cast_bf16(const float* src, const float* row_scale, int32_t rows_per_scale, int64_t rows,
+                        int32_t cols, void* dst, vtb_stream_t stream);
+/* SiLU on f32 (halo_transformer.py:218) and its adjoint. */
+int vtb_silu_fwd(const float* x, float* y, int64_t n, vtb_stream_t stream);
+int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, vtb_stream_t stream);
+/* out[n] += sum_m X[m, n]  (bias gradients).  X bf16 [M, ld]. */
+int vtb_colsum_bf16(const void* X, int64_t M, int32_t N, int32_t ld, float* out,
+                    vtb_stream_t stream);
+/* Patch gather to a bf16 GEMM operand (conv k=s stride=s as GEMM):
+ *   src_nchw=1: src[b, c, y, x] (f32)            src_nchw=0: src[b, y, x, c] (f32 or bf16 by src_bf16)
+ *   c_major=1 : feature = c*p*p + py*p + px (vit.py:73, pvt.py:111)
+ *   c_major=0 : feature = (py*p + px)*C + c (patchify, swin:15-22)
+ * dst bf16 [B*(H/p)*(W/p), p*p*C]. */
+int vtb_patch_gather(const void* src, int32_t src_bf16, int32_t src_nchw, int32_t c_major,
+                     int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, void* dst,
+                     vtb_stream_t stream);
+/* Adjoint of vtb_patch_gather for NHWC/pos-major f32 destinations: dx[b,y,x,c] (+)= dA[row, feat]
+ * (dA bf16 or f32).  accumulate=0 overwrites. */
+int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major, int32_t B, int32_t C,
+                      int32_t H, int32_t W, int32_t p, float* dx, int32_t accumulate,
+                      vtb_stream_t stream);
+/* dst[g*stride + off + r, :] = src[r % src_rows, :] (+ add[...]) helpers for cls tokens:
+ * x[b, 0, :] = cls[:] + pos0[:]   (vit.py:141-143, pvt.py:136-140) */
+int vtb_fill_rows(float* x, int64_t row_stride_groups, int32_t groups, int32_t cols,
+                  const float* a, const float* b, vtb_stream_t stream);
+/* out[c] += sum_g x[g*group_stride, c]  (cls_token / pos gradients), f32 */
+int vtb_rowgroup_sum(const float* x, int64_t group_stride, int32_t groups, int32_t rows,
+                     int32_t cols, float* out, vtb_stream_t stream);
+/* Mean over `n` consecutive rows: out[g, :] = mean_r x[g*n + r, :]  (AdaptiveAvgPool2d(1), swin:281) and
+ * its adjoint dx[g*n + r, :] = dy[g, :]/n. */
+int vtb_mean_rows_fwd(const float* x, int32_t groups, int32_t n, int32_t cols, float* out,
+                      vtb_stream_t stream);
+int vtb_mean_rows_bwd(const float* dy, int32_t groups, int32_t n, int32_t cols, float* dx,
+                      vtb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTB200_H */

@@ -1,0 +1,101 @@
+"""Drop-in boundary: the models package reproduces the reference's state_dict schema
+(keys, shapes, dtypes, parameter order), buffers, parameter counts, and loads reference checkpoints."""
+import hashlib
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+
+import models
+from models.halo_transformer import halo_pos
+from models.swin_transformer import window_tables
+from oracle import restate as R
+
+STRUCT = json.load(open(os.path.join(GOLDEN, "structure.json")))
+
+FULL = {
+    "vit_b16": lambda: models.VisionTransformer(None, 224, 16, 12, 768, 12, 3072, 0., 0., 0., 0.),
+    "vit_tiny16": lambda: models.VisionTransformer(None, 224, 16, 12, 192, 3, 768, 0., 0., 0., 0.),
+    "swin_s": lambda: models.SwinTransformer((224, 224), 1000, (2, 2, 18, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
+                                             (384, 768, 1536, 3072), 7, drop_path=0.3),
+    "pvt_small": lambda: models.PyramidVisionTransformer(224, 1000, 3, (3, 4, 6, 3), (64, 128, 320, 512), (1, 2, 5, 8),
+                                                         (512, 1024, 1280, 2048), (8, 4, 2, 1)),
+    "halo_t": lambda: models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
+                                             (384, 768, 1536, 3072), window_size=7, halo_size=3),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_state_dict_schema_matches_reference(name):
+    with torch.device("meta"):
+        pass
+    model = FULL[name]()
+    want = STRUCT[name]
+    sd = model.state_dict()
+    assert sum(p.numel() for p in model.parameters()) == want["n_params"]
+    assert list(sd.keys()) == list(want["keys"].keys())
+    for k, v in sd.items():
+        assert [list(v.shape), str(v.dtype)] == want["keys"][k], k
+    assert [k for k, _ in model.named_parameters()] == want["param_order"]
+    h = hashlib.sha256()
+    for k, v in model.named_buffers():
+        h.update(k.encode())
+        h.update(v.to(torch.int64).numpy().tobytes())
+    assert h.hexdigest() == want["buffers_sha256"]
+
+
+def test_swin_tables_equal_oracle_tables():
+    for hs, shift in [(56, True), (28, True), (14, True), (7, True), (56, False), (14, False), (7, False)]:
+        pos, mask = window_tables((hs, hs), 7, shift)
+        opos, omask = R.swin_tables(hs, hs, 7, shift)
+        assert torch.equal(pos, opos)
+        assert (mask is None) == (omask is None)
+        if shift:
+            assert torch.equal(mask, omask)
+    pos, max_pos = halo_pos(7, 3)
+    assert torch.equal(pos, R.halo_pos_table(7, 3)) and max_pos + 1 == 253
+
+
+@pytest.mark.parametrize("name,ctor", [
+    ("vit_tiny", models.VisionTransformer), ("swin_w2", models.SwinTransformer), ("swin_w7", models.SwinTransformer),
+    ("pvt_tiny", models.PyramidVisionTransformer), ("halo_w2", models.HaloTransformer), ("halo_w7", models.HaloTransformer),
+])
+def test_reference_checkpoints_load_strictly(name, ctor):
+    fx = load_golden(name)
+    model = ctor(**fx["ctor"])
+    missing, unexpected = model.load_state_dict(fx["state_dict"], strict=True)
+    assert not missing and not unexpected
+
+
+def test_drop_path_schedules():
+    s = FULL["swin_s"]()
+    rates = [l.drop_path.p for st in s.blocks() for l in st if hasattr(l, "drop_path")]
+    assert len(rates) == 24 and rates[0] == 0 and abs(rates[-1] - 0.3 * 23 / 24) < 1e-12
+    v = models.VisionTransformer(None, 224, 16, 12, 192, 3, 768, 0., 0., 0., 0.1)
+    assert abs(v.layers[-1].drop_path.p - 0.1) < 1e-7 and v.layers[0].drop_path.p == 0
+    v.set_drop_path(0.2)
+    assert abs(v.layers[-1].drop_path.p - 0.2) < 1e-7
+    p = FULL["pvt_small"]()
+    p.set_drop_path(0.1)
+    assert abs(p.block4[-1].drop_path.p - 0.1) < 1e-7
+
+
+def test_trainer_name_filters_still_bite():
+    """factory.py:25-39 (wd skip), train_util.py:29-31 ('last'), train.py:259 ('linear') work on names."""
+    d = models.dino(image_size=224, window_size=16, depth=1, dim=64, n_head=2, dim_ff=128, dropout=0., drop_attn=0.,
+                    drop_ff=0., drop_path=0.1, dim_head_out=128)
+    names = [n for n, _ in d.named_parameters()]
+    assert "head.last.weight_g" in names and "head.last.weight_v" in names
+    assert "cls_token" in names and "layers.0.norm_attn.weight" in names and "layers.0.ff.3.bias" in names
+    assert len(d.state_dict()) == 6 + 12 + 6 + 2  # embed/cls/pos/norm + 1 layer + head mlp + weight-normed last (158 at depth 12)
+
+
+def test_forward_on_cpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    v = models.VisionTransformer(None, 32, 8, 1, 64, 2, 128, 0., 0., 0., 0.)
+    with pytest.raises(RuntimeError, match="CUDA device required"):
+        v(torch.randn(1, 3, 32, 32))

@@ -1,0 +1,676 @@
+// Fused multi-head attention for every variant on the path (global / shifted-window / halo / SRA),
+// forward and backward, through one geometry descriptor (include/vtb200.h: vtb_attn_params).
+// Scores and probabilities stay in registers; window partition, cyclic shift, halo gather with zero
+// padding and the relative-position bias / mask are folded into the load addressing, so none of the
+// reference's roll / reshape / unfold / masked_fill / softmax kernels (and their HBM traffic) exist.
+//
+// v1 tensor path: mma.sync m16n8k16 bf16 (fp32 accumulate), 4 warps x 16 rows per CTA, online softmax
+// over 64-key blocks.  (Attention is 4 % of the path's FLOPs — SURVEY §3 — the tcgen05 GEMM carries
+// the rest; a tcgen05/TMEM variant of this kernel is the follow-up.)
+#include "common.cuh"
+#include "../../include/vtb200.h"
+#include <math.h>
+
+namespace {
+
+constexpr int BQ = 64;    // rows per CTA tile (4 warps x 16)
+constexpr int BKV = 64;   // keys per inner block
+constexpr int NTHREADS = 128;
+constexpr int MAX_POS = 512;  // relative-position table rows handled in smem (swin 169, halo 253)
+
+struct Geom {
+  int mode, batch, heads, dh, nq, nkv, Hs, Ws, window, shift, halo;
+  int nwx, nw;  // windows per row / per image
+};
+
+__device__ __forceinline__ long q_token(const Geom& g, int grp, int i) {
+  if (i >= g.nq) return -1;
+  if (g.mode == VTB_ATTN_GLOBAL) return (long)grp * g.nq + i;
+  const int b = grp / g.nw, wi = grp - b * g.nw;
+  const int wy = wi / g.nwx, wx = wi - wy * g.nwx;
+  const int ty = i / g.window, tx = i - ty * g.window;
+  int y = wy * g.window + ty, x = wx * g.window + tx;
+  if (g.mode == VTB_ATTN_WINDOW && g.shift) {
+    y += g.shift; if (y >= g.Hs) y -= g.Hs;
+    x += g.shift; if (x >= g.Ws) x -= g.Ws;
+  }
+  return ((long)b * g.Hs + y) * g.Ws + x;
+}
+__device__ __forceinline__ long kv_token(const Geom& g, int grp, int j) {
+  if (j >= g.nkv) return -1;
+  if (g.mode == VTB_ATTN_GLOBAL) return (long)grp * g.nkv + j;
+  if (g.mode == VTB_ATTN_WINDOW) return q_token(g, grp, j);
+  const int b = grp / g.nw, wi = grp - b * g.nw;
+  const int by = wi / g.nwx, bx = wi - by * g.nwx;
+  const int K = g.window + 2 * g.halo;
+  const int ky = j / K, kx = j - ky * K;
+  const int y = by * g.window - g.halo + ky, x = bx * g.window - g.halo + kx;
+  if (y < 0 || y >= g.Hs || x < 0 || x >= g.Ws) return -1;  // zero-padded slot (halo:75-80)
+  return ((long)b * g.Hs + y) * g.Ws + x;
+}
+
+// cooperative load of `rows` (<=64) token rows of DH bf16 into padded smem; missing rows -> zeros
+template <int DH>
+__device__ __forceinline__ void load_rows(bf16 (*dst)[DH + 8], const bf16* base, int ld, int head_off,
+                                          const long* toks) {
+  constexpr int CH = DH / 8;  // 16-byte chunks per row
+  for (int c = threadIdx.x; c < 64 * CH; c += NTHREADS) {
+    const int r = c / CH, cc = c - r * CH;
+    const long t = toks[r];
+    const bf16* src = base + (t < 0 ? 0 : t) * (long)ld + head_off + cc * 8;
+    cp_async16(smem_u32(&dst[r][cc * 8]), src, t >= 0);
+  }
+}
+
+// score bias for element (i, j) of group grp / head h (clamped indices for padding rows)
+struct BiasCtx {
+  const float* table;   // smem copy of rel_bias[:, h] or null
+  const int* pos;       // global [nq, nkv]
+  const uint8_t* mask;  // global, already offset to this group's [nq, nkv] slice, or null
+  int nq, nkv;
+};
+__device__ __forceinline__ float score_bias(const BiasCtx& c, int i, int j, bool& masked) {
+  masked = false;
+  if (i >= c.nq) i = c.nq - 1;
+  float b = 0.f;
+  if (c.table) b = c.table[__ldg(c.pos + (long)i * c.nkv + j)];
+  if (c.mask && c.mask[(long)i * c.nkv + j]) masked = true;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <int DH>
+__global__ void __launch_bounds__(NTHREADS)
+attn_fwd_kernel(vtb_attn_params p, Geom g, int q_tiles) {
+  __shared__ __align__(16) bf16 sQ[BQ][DH + 8];
+  __shared__ __align__(16) bf16 sK[BKV][DH + 8];
+  __shared__ __align__(16) bf16 sV[BKV][DH + 8];
+  __shared__ long sQtok[BQ], sKtok[BKV];
+  __shared__ float sTab[MAX_POS];
+
+  const int qt = blockIdx.x % q_tiles;
+  const int gh = blockIdx.x / q_tiles;
+  const int h = gh % g.heads;
+  const int grp = gh / g.heads;
+  const int i0 = qt * BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  const bf16* Q = reinterpret_cast<const bf16*>(p.q);
+  const bf16* K = reinterpret_cast<const bf16*>(p.k);
+  const bf16* V = reinterpret_cast<const bf16*>(p.v);
+
+  if (threadIdx.x < BQ) sQtok[threadIdx.x] = q_token(g, grp, i0 + threadIdx.x);
+  if (p.rel_bias) {
+    for (int t = threadIdx.x; t < p.n_pos; t += NTHREADS) sTab[t] = p.rel_bias[(long)t * g.heads + h];
+  }
+  __syncthreads();
+  load_rows<DH>(sQ, Q, p.ldq, h * DH, sQtok);
+  cp_async_commit();
+
+  BiasCtx bc;
+  bc.table = p.rel_bias ? sTab : nullptr;
+  bc.pos = p.pos;
+  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  bc.nq = g.nq; bc.nkv = g.nkv;
+
+  float o[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[DH / 16][4];
+  bool q_loaded = false;
+
+  for (int j0 = 0; j0 < g.nkv; j0 += BKV) {
+    __syncthreads();  // previous block's smem reads done
+    if (threadIdx.x < BKV) sKtok[threadIdx.x] = kv_token(g, grp, j0 + threadIdx.x);
+    __syncthreads();
+    load_rows<DH>(sK, K, p.ldk, h * DH, sKtok);
+    load_rows<DH>(sV, V, p.ldv, h * DH, sKtok);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!q_loaded) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk)
+        ldsm_x4(qf[kk], smem_u32(&sQ[warp * 16 + (lane & 15)][kk * 16 + (lane >> 4) * 8]));
+      q_loaded = true;
+    }
+    // S = Q K^T  (16 x 64 per warp)
+    float s[BKV / 8][4];
+#pragma unroll
+    for (int n = 0; n < BKV / 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+      for (int n2 = 0; n2 < BKV / 16; ++n2) {
+        uint32_t kb[4];
+        ldsm_x4(kb, smem_u32(&sK[n2 * 16 + (lane & 7) + ((lane >> 4) << 3)][kk * 16 + ((lane >> 3) & 1) * 8]));
+        uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+        mma_bf16_16816(s[2 * n2], qf[kk], b0);
+        mma_bf16_16816(s[2 * n2 + 1], qf[kk], b1);
+      }
+    }
+    // scale + bias + mask, online softmax
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < BKV / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + warp * 16 + gq + (e >> 1) * 8;
+        const int j = j0 + n * 8 + 2 * tq + (e & 1);
+        float v = s[n][e] * p.scale;
+        if (j >= g.nkv) v = -INFINITY;
+        else if (bc.table || bc.mask) {
+          bool masked;
+          v += score_bias(bc, i, j, masked);
+          if (masked) v = -INFINITY;
+        }
+        s[n][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2], m_use[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = __expf(m_run[r] - m_use[r]);  // exp(-inf) = 0 on the first block
+      m_run[r] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < BKV / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = __expf(s[n][e] - m_use[e >> 1]);
+        s[n][e] = pv;
+        rs[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      l_run[r] = l_run[r] * corr[r] + rs[r];
+    }
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int k2 = 0; k2 < BKV / 16; ++k2) {
+      uint32_t pa[4] = {pack_bf16(s[2 * k2][0], s[2 * k2][1]), pack_bf16(s[2 * k2][2], s[2 * k2][3]),
+                        pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]),
+                        pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3])};
+#pragma unroll
+      for (int d2 = 0; d2 < DH / 16; ++d2) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, smem_u32(&sV[k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][d2 * 16 + (lane >> 4) * 8]));
+        uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+        mma_bf16_16816(o[2 * d2], pa, b0);
+        mma_bf16_16816(o[2 * d2 + 1], pa, b1);
+      }
+    }
+  }
+
+  // finalise: O / l, write; lse = m + log(l)
+  bf16* O = reinterpret_cast<bf16*>(p.o);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = warp * 16 + gq + r * 8;
+    const long tok = sQtok[row];
+    if (tok < 0) continue;
+    const float inv = 1.f / l_run[r];
+    bf16* dst = O + tok * (long)p.ldo + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) =
+          pack_bf16(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+    }
+    if (tq == 0 && p.lse)
+      p.lse[((long)grp * g.heads + h) * g.nq + i0 + row] = m_run[r] + __logf(l_run[r]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward: dQ
+template <int DH>
+__global__ void __launch_bounds__(NTHREADS)
+attn_bwd_dq_kernel(vtb_attn_params p, Geom g, int q_tiles) {
+  const int n_pos = p.n_pos;
+  __shared__ __align__(16) bf16 sQ[BQ][DH + 8];
+  __shared__ __align__(16) bf16 sdO[BQ][DH + 8];
+  __shared__ __align__(16) bf16 sK[BKV][DH + 8];
+  __shared__ __align__(16) bf16 sV[BKV][DH + 8];
+  __shared__ long sQtok[BQ], sKtok[BKV];
+  __shared__ float sTab[MAX_POS], sdTab[MAX_POS];
+  __shared__ float sDelta[BQ], sLse[BQ];
+
+  const int qt = blockIdx.x % q_tiles;
+  const int gh = blockIdx.x / q_tiles;
+  const int h = gh % g.heads;
+  const int grp = gh / g.heads;
+  const int i0 = qt * BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  const bf16* Q = reinterpret_cast<const bf16*>(p.q);
+  const bf16* K = reinterpret_cast<const bf16*>(p.k);
+  const bf16* V = reinterpret_cast<const bf16*>(p.v);
+  const bf16* O = reinterpret_cast<const bf16*>(p.o);
+  const bf16* dO = reinterpret_cast<const bf16*>(p.dout);
+
+  if (threadIdx.x < BQ) sQtok[threadIdx.x] = q_token(g, grp, i0 + threadIdx.x);
+  if (p.rel_bias) {
+    for (int t = threadIdx.x; t < n_pos; t += NTHREADS) {
+      sTab[t] = p.rel_bias[(long)t * g.heads + h];
+      sdTab[t] = 0.f;
+    }
+  }
+  __syncthreads();
+  load_rows<DH>(sQ, Q, p.ldq, h * DH, sQtok);
+  load_rows<DH>(sdO, dO, p.lddo, h * DH, sQtok);
+  cp_async_commit();
+  // delta_i = sum_d dO[i,d] * O[i,d]; two threads per row
+  {
+    const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const long tok = sQtok[row];
+    float acc = 0.f;
+    if (tok >= 0) {
+      const bf16* a = dO + tok * (long)p.lddo + h * DH + half * (DH / 2);
+      const bf16* b = O + tok * (long)p.ldo + h * DH + half * (DH / 2);
+#pragma unroll
+      for (int d = 0; d < DH / 2; d += 8) {
+        const uint4 ra = *reinterpret_cast<const uint4*>(a + d);
+        const uint4 rb = *reinterpret_cast<const uint4*>(b + d);
+        const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
+          acc += fa.x * fb.x + fa.y * fb.y;
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) {
+      sDelta[row] = acc;
+      const long li = ((long)grp * g.heads + h) * g.nq + i0 + row;
+      if (tok >= 0) {
+        p.delta[li] = acc;
+        sLse[row] = p.lse[li];
+      } else {
+        sLse[row] = 0.f;
+      }
+    }
+  }
+
+  BiasCtx bc;
+  bc.table = p.rel_bias ? sTab : nullptr;
+  bc.pos = p.pos;
+  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  bc.nq = g.nq; bc.nkv = g.nkv;
+
+  float dq[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
+  uint32_t qf[DH / 16][4], dof[DH / 16][4];
+  bool loaded = false;
+  float lse_r[2], dl_r[2];
+
+  for (int j0 = 0; j0 < g.nkv; j0 += BKV) {
+    __syncthreads();
+    if (threadIdx.x < BKV) sKtok[threadIdx.x] = kv_token(g, grp, j0 + threadIdx.x);
+    __syncthreads();
+    load_rows<DH>(sK, K, p.ldk, h * DH, sKtok);
+    load_rows<DH>(sV, V, p.ldv, h * DH, sKtok);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!loaded) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        ldsm_x4(qf[kk], smem_u32(&sQ[warp * 16 + (lane & 15)][kk * 16 + (lane >> 4) * 8]));
+        ldsm_x4(dof[kk], smem_u32(&sdO[warp * 16 + (lane & 15)][kk * 16 + (lane >> 4) * 8]));
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        lse_r[r] = sLse[warp * 16 + gq + r * 8];
+        dl_r[r] = sDelta[warp * 16 + gq + r * 8];
+      }
+      loaded = true;
+    }
+    float s[BKV / 8][4], dp[BKV / 8][4];
+#pragma unroll
+    for (int n = 0; n < BKV / 8; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+      for (int n2 = 0; n2 < BKV / 16; ++n2) {
+        uint32_t kb[4], vb[4];
+        const int rr = n2 * 16 + (lane & 7) + ((lane >> 4) << 3), cc = kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kb, smem_u32(&sK[rr][cc]));
+        ldsm_x4(vb, smem_u32(&sV[rr][cc]));
+        uint32_t k0[2] = {kb[0], kb[1]}, k1[2] = {kb[2], kb[3]};
+        uint32_t v0[2] = {vb[0], vb[1]}, v1[2] = {vb[2], vb[3]};
+        mma_bf16_16816(s[2 * n2], qf[kk], k0);
+        mma_bf16_16816(s[2 * n2 + 1], qf[kk], k1);
+        mma_bf16_16816(dp[2 * n2], dof[kk], v0);
+        mma_bf16_16816(dp[2 * n2 + 1], dof[kk], v1);
+      }
+    }
+    // dS = P * (dP - delta)
+#pragma unroll
+    for (int n = 0; n < BKV / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        const int i = i0 + warp * 16 + gq + r * 8;
+        const int j = j0 + n * 8 + 2 * tq + (e & 1);
+        float ds = 0.f;
+        if (j < g.nkv && i < g.nq) {
+          float v = s[n][e] * p.scale;
+          bool masked = false;
+          if (bc.table || bc.mask) v += score_bias(bc, i, j, masked);
+          if (!masked) {
+            const float pv = __expf(v - lse_r[r]);
+            ds = pv * (dp[n][e] - dl_r[r]);
+            if (p.drel_bias && bc.table) atomicAdd(&sdTab[__ldg(bc.pos + (long)i * g.nkv + j)], ds);
+          }
+        }
+        s[n][e] = ds;
+      }
+    }
+    // dQ += dS K
+#pragma unroll
+    for (int k2 = 0; k2 < BKV / 16; ++k2) {
+      uint32_t pa[4] = {pack_bf16(s[2 * k2][0], s[2 * k2][1]), pack_bf16(s[2 * k2][2], s[2 * k2][3]),
+                        pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]),
+                        pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3])};
+#pragma unroll
+      for (int d2 = 0; d2 < DH / 16; ++d2) {
+        uint32_t kb[4];
+        ldsm_x4_t(kb, smem_u32(&sK[k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][d2 * 16 + (lane >> 4) * 8]));
+        uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+        mma_bf16_16816(dq[2 * d2], pa, b0);
+        mma_bf16_16816(dq[2 * d2 + 1], pa, b1);
+      }
+    }
+  }
+
+  bf16* dQ = reinterpret_cast<bf16*>(p.dq);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = warp * 16 + gq + r * 8;
+    const long tok = sQtok[row];
+    if (tok < 0) continue;
+    bf16* dst = dQ + tok * (long)p.lddq + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n)
+      *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) =
+          pack_bf16(dq[n][2 * r] * p.scale, dq[n][2 * r + 1] * p.scale);
+  }
+  if (p.drel_bias && p.rel_bias) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_pos; t += NTHREADS) {
+      const float v = sdTab[t];
+      if (v != 0.f) atomicAdd(p.drel_bias + (long)t * g.heads + h, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward: dK, dV
+template <int DH>
+__global__ void __launch_bounds__(NTHREADS)
+attn_bwd_dkv_kernel(vtb_attn_params p, Geom g, int kv_tiles) {
+  const int n_pos = p.n_pos;
+  __shared__ __align__(16) bf16 sK[BKV][DH + 8];
+  __shared__ __align__(16) bf16 sV[BKV][DH + 8];
+  __shared__ __align__(16) bf16 sQ[BQ][DH + 8];
+  __shared__ __align__(16) bf16 sdO[BQ][DH + 8];
+  __shared__ long sQtok[BQ], sKtok[BKV];
+  __shared__ float sTab[MAX_POS];
+  __shared__ float sDelta[BQ], sLse[BQ];
+
+  const int kt = blockIdx.x % kv_tiles;
+  const int gh = blockIdx.x / kv_tiles;
+  const int h = gh % g.heads;
+  const int grp = gh / g.heads;
+  const int j0 = kt * BKV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  const bf16* Q = reinterpret_cast<const bf16*>(p.q);
+  const bf16* K = reinterpret_cast<const bf16*>(p.k);
+  const bf16* V = reinterpret_cast<const bf16*>(p.v);
+  const bf16* dO = reinterpret_cast<const bf16*>(p.dout);
+
+  if (threadIdx.x < BKV) sKtok[threadIdx.x] = kv_token(g, grp, j0 + threadIdx.x);
+  if (p.rel_bias)
+    for (int t = threadIdx.x; t < n_pos; t += NTHREADS) sTab[t] = p.rel_bias[(long)t * g.heads + h];
+  __syncthreads();
+  load_rows<DH>(sK, K, p.ldk, h * DH, sKtok);
+  load_rows<DH>(sV, V, p.ldv, h * DH, sKtok);
+  cp_async_commit();
+
+  BiasCtx bc;
+  bc.table = p.rel_bias ? sTab : nullptr;
+  bc.pos = p.pos;
+  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  bc.nq = g.nq; bc.nkv = g.nkv;
+
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) {
+    dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+    dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+  }
+  uint32_t kf[DH / 16][4], vf[DH / 16][4];
+  bool loaded = false;
+
+  for (int i0 = 0; i0 < g.nq; i0 += BQ) {
+    __syncthreads();
+    if (threadIdx.x < BQ) {
+      const long tok = q_token(g, grp, i0 + threadIdx.x);
+      sQtok[threadIdx.x] = tok;
+      const long li = ((long)grp * g.heads + h) * g.nq + i0 + threadIdx.x;
+      sLse[threadIdx.x] = tok >= 0 ? p.lse[li] : 0.f;
+      sDelta[threadIdx.x] = tok >= 0 ? p.delta[li] : 0.f;
+    }
+    __syncthreads();
+    load_rows<DH>(sQ, Q, p.ldq, h * DH, sQtok);
+    load_rows<DH>(sdO, dO, p.lddo, h * DH, sQtok);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!loaded) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        ldsm_x4(kf[kk], smem_u32(&sK[warp * 16 + (lane & 15)][kk * 16 + (lane >> 4) * 8]));
+        ldsm_x4(vf[kk], smem_u32(&sV[warp * 16 + (lane & 15)][kk * 16 + (lane >> 4) * 8]));
+      }
+      loaded = true;
+    }
+    // S^T = K Q^T, dP^T = V dO^T   (16 keys x 64 queries per warp)
+    float s[BQ / 8][4], dp[BQ / 8][4];
+#pragma unroll
+    for (int n = 0; n < BQ / 8; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+      for (int n2 = 0; n2 < BQ / 16; ++n2) {
+        uint32_t qb[4], ob[4];
+        const int rr = n2 * 16 + (lane & 7) + ((lane >> 4) << 3), cc = kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(qb, smem_u32(&sQ[rr][cc]));
+        ldsm_x4(ob, smem_u32(&sdO[rr][cc]));
+        uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+        uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+        mma_bf16_16816(s[2 * n2], kf[kk], q0);
+        mma_bf16_16816(s[2 * n2 + 1], kf[kk], q1);
+        mma_bf16_16816(dp[2 * n2], vf[kk], o0);
+        mma_bf16_16816(dp[2 * n2 + 1], vf[kk], o1);
+      }
+    }
+    // P^T and dS^T; rows = keys (j), cols = queries (i)
+#pragma unroll
+    for (int n = 0; n < BQ / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + warp * 16 + gq + (e >> 1) * 8;
+        const int il = n * 8 + 2 * tq + (e & 1);
+        const int i = i0 + il;
+        float pv = 0.f, ds = 0.f;
+        if (j < g.nkv && i < g.nq) {
+          float v = s[n][e] * p.scale;
+          bool masked = false;
+          if (bc.table || bc.mask) v += score_bias(bc, i, j, masked);
+          if (!masked) {
+            pv = __expf(v - sLse[il]);
+            ds = pv * (dp[n][e] - sDelta[il]);
+          }
+        }
+        s[n][e] = pv;
+        dp[n][e] = ds;
+      }
+    }
+    // dV += P^T dO ; dK += dS^T Q
+#pragma unroll
+    for (int k2 = 0; k2 < BQ / 16; ++k2) {
+      uint32_t pa[4] = {pack_bf16(s[2 * k2][0], s[2 * k2][1]), pack_bf16(s[2 * k2][2], s[2 * k2][3]),
+                        pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]),
+                        pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3])};
+      uint32_t da[4] = {pack_bf16(dp[2 * k2][0], dp[2 * k2][1]), pack_bf16(dp[2 * k2][2], dp[2 * k2][3]),
+                        pack_bf16(dp[2 * k2 + 1][0], dp[2 * k2 + 1][1]),
+                        pack_bf16(dp[2 * k2 + 1][2], dp[2 * k2 + 1][3])};
+#pragma unroll
+      for (int d2 = 0; d2 < DH / 16; ++d2) {
+        uint32_t ob[4], qb[4];
+        const int rr = k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, cc = d2 * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(ob, smem_u32(&sdO[rr][cc]));
+        ldsm_x4_t(qb, smem_u32(&sQ[rr][cc]));
+        uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+        uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+        mma_bf16_16816(dv[2 * d2], pa, o0);
+        mma_bf16_16816(dv[2 * d2 + 1], pa, o1);
+        mma_bf16_16816(dk[2 * d2], da, q0);
+        mma_bf16_16816(dk[2 * d2 + 1], da, q1);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = warp * 16 + gq + r * 8;
+    const long tok = sKtok[row];
+    if (tok < 0) continue;
+    if (p.dkv_f32) {
+      float* dKp = reinterpret_cast<float*>(p.dk) + tok * (long)p.lddk + h * DH;
+      float* dVp = reinterpret_cast<float*>(p.dv) + tok * (long)p.lddv + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        atomicAdd(dKp + n * 8 + 2 * tq, dk[n][2 * r] * p.scale);
+        atomicAdd(dKp + n * 8 + 2 * tq + 1, dk[n][2 * r + 1] * p.scale);
+        atomicAdd(dVp + n * 8 + 2 * tq, dv[n][2 * r]);
+        atomicAdd(dVp + n * 8 + 2 * tq + 1, dv[n][2 * r + 1]);
+      }
+    } else {
+      bf16* dKp = reinterpret_cast<bf16*>(p.dk) + tok * (long)p.lddk + h * DH;
+      bf16* dVp = reinterpret_cast<bf16*>(p.dv) + tok * (long)p.lddv + h * DH;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        *reinterpret_cast<uint32_t*>(dKp + n * 8 + 2 * tq) =
+            pack_bf16(dk[n][2 * r] * p.scale, dk[n][2 * r + 1] * p.scale);
+        *reinterpret_cast<uint32_t*>(dVp + n * 8 + 2 * tq) = pack_bf16(dv[n][2 * r], dv[n][2 * r + 1]);
+      }
+    }
+  }
+}
+
+int make_geom(const vtb_attn_params* p, Geom* g, long* groups, const char* who) {
+  VTB_CHECK(p != nullptr, -1, "%s: null params", who);
+  VTB_CHECK(p->dh == 32 || p->dh == 64, -1, "%s: dh must be 32 or 64 (got %d)", who, p->dh);
+  VTB_CHECK(p->batch > 0 && p->heads > 0 && p->nq > 0 && p->nkv > 0, -1, "%s: bad sizes", who);
+  g->mode = p->mode; g->batch = p->batch; g->heads = p->heads; g->dh = p->dh;
+  g->nq = p->nq; g->nkv = p->nkv; g->Hs = p->Hs; g->Ws = p->Ws;
+  g->window = p->window; g->shift = p->shift; g->halo = p->halo;
+  g->nwx = 1; g->nw = 1;
+  if (p->mode == VTB_ATTN_GLOBAL) {
+    *groups = p->batch;
+  } else {
+    VTB_CHECK(p->mode == VTB_ATTN_WINDOW || p->mode == VTB_ATTN_HALO, -1, "%s: bad mode", who);
+    VTB_CHECK(p->window > 0 && p->Hs % p->window == 0 && p->Ws % p->window == 0, -1,
+              "%s: window %d must divide %dx%d", who, p->window, p->Hs, p->Ws);
+    g->nwx = p->Ws / p->window;
+    g->nw = (p->Hs / p->window) * g->nwx;
+    *groups = (long)p->batch * g->nw;
+    VTB_CHECK(p->nq == p->window * p->window, -1, "%s: nq must be window^2", who);
+    const int kk = p->window + 2 * (p->mode == VTB_ATTN_HALO ? p->halo : 0);
+    VTB_CHECK(p->nkv == kk * kk, -1, "%s: nkv must be %d", who, kk * kk);
+    VTB_CHECK(p->shift >= 0 && p->shift < p->window, -1, "%s: bad shift", who);
+  }
+  VTB_CHECK(p->q && p->k && p->v, -1, "%s: null q/k/v", who);
+  VTB_CHECK(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldv % 8 == 0 &&
+                (((uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v) & 15) == 0,
+            -1, "%s: q/k/v must be 16-byte aligned rows", who);
+  VTB_CHECK((p->rel_bias == nullptr) == (p->pos == nullptr), -1, "%s: rel_bias and pos go together", who);
+  VTB_CHECK(!p->mask || p->n_mask > 0, -1, "%s: n_mask", who);
+  VTB_CHECK(!p->rel_bias || (p->n_pos > 0 && p->n_pos <= MAX_POS), -1,
+            "%s: rel_bias rows n_pos=%d must be in (0, %d]", who, p->n_pos, MAX_POS);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Geom g;
+  long groups;
+  int rc = make_geom(p, &g, &groups, "vtb_attention_fwd");
+  if (rc) return rc;
+  VTB_CHECK(p->o && p->ldo % 2 == 0, -1, "vtb_attention_fwd: o");
+  const int q_tiles = (p->nq + BQ - 1) / BQ;
+  const long blocks = groups * p->heads * q_tiles;
+  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd: grid too large");
+  if (p->dh == 64) attn_fwd_kernel<64><<<(unsigned)blocks, NTHREADS, 0, stream>>>(*p, g, q_tiles);
+  else             attn_fwd_kernel<32><<<(unsigned)blocks, NTHREADS, 0, stream>>>(*p, g, q_tiles);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Geom g;
+  long groups;
+  int rc = make_geom(p, &g, &groups, "vtb_attention_bwd");
+  if (rc) return rc;
+  VTB_CHECK(p->o && p->dout && p->dq && p->dk && p->dv && p->lse && p->delta, -1,
+            "vtb_attention_bwd: null pointer");
+  VTB_CHECK(p->lddo % 8 == 0 && p->ldo % 8 == 0 && (((uintptr_t)p->dout | (uintptr_t)p->o) & 15) == 0,
+            -1, "vtb_attention_bwd: o/dout alignment");
+  VTB_CHECK(p->lddq % 2 == 0 && (p->dkv_f32 || (p->lddk % 2 == 0 && p->lddv % 2 == 0)), -1,
+            "vtb_attention_bwd: dq/dk/dv leading dims");
+  const vtb_attn_params& q = *p;
+  const int q_tiles = (p->nq + BQ - 1) / BQ;
+  const int kv_tiles = (p->nkv + BKV - 1) / BKV;
+  const long b1 = groups * p->heads * q_tiles, b2 = groups * p->heads * kv_tiles;
+  VTB_CHECK(b1 < (1L << 31) && b2 < (1L << 31), -1, "vtb_attention_bwd: grid too large");
+  if (p->dh == 64) {
+    attn_bwd_dq_kernel<64><<<(unsigned)b1, NTHREADS, 0, stream>>>(q, g, q_tiles);
+    VTB_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<64><<<(unsigned)b2, NTHREADS, 0, stream>>>(q, g, kv_tiles);
+  } else {
+    attn_bwd_dq_kernel<32><<<(unsigned)b1, NTHREADS, 0, stream>>>(q, g, q_tiles);
+    VTB_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<32><<<(unsigned)b2, NTHREADS, 0, stream>>>(q, g, kv_tiles);
+  }
+  VTB_LAUNCH_CHECK();
+  return 0;
+}

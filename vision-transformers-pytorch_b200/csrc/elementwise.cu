@@ -1,0 +1,325 @@
+// Memory-bound helpers around the GEMM / attention kernels: casts, bias-gradient column sums,
+// patch gather/scatter (conv k=s as GEMM operand), cls-row fill, row pooling.
+#include "common.cuh"
+#include "../../include/vtb200.h"
+#include <stdarg.h>
+#include <string.h>
+
+// ------------------------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+void vtb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* vtb_last_error(void) { return g_err; }
+extern "C" int vtb_version(void) { return 100; }
+int vtb_gemm_init();
+extern "C" int vtb_init(void) { return vtb_gemm_init(); }
+
+namespace {
+
+inline int grid_for(long n, int threads, int per_thread = 1) {
+  long b = (n + (long)threads * per_thread - 1) / ((long)threads * per_thread);
+  const long cap = (long)(vtb_num_sms() > 0 ? vtb_num_sms() : 148) * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  const long n4 = n >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+__global__ void cast2d_kernel(const float* __restrict__ src, long lds, bf16* __restrict__ dst, long ldd,
+                              long rows, int cols) {
+  const long total = rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ldd + c] = __float2bfloat16(src[r * lds + c]);
+  }
+}
+
+__global__ void scale_cast_kernel(const float* __restrict__ src, const float* __restrict__ row_scale,
+                                  int rows_per_scale, long rows, int cols, bf16* __restrict__ dst) {
+  const int c4 = cols >> 2;
+  const long total = rows * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const float sc = row_scale ? __ldg(row_scale + r / rows_per_scale) : 1.f;
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x * sc, v.y * sc), pack_bf16(v.z * sc, v.w * sc));
+  }
+}
+
+__global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = silu_f(x[i]);
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                float* __restrict__ dx, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * silu_grad_f(x[i]);
+}
+
+// out[n] += sum_m X[m, n]; CTA = 32 column-pairs x 8 row lanes, rows strided by the grid.y
+constexpr int CS_ROWS = 8;
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ X, long M, int N, int ld, float* __restrict__ out,
+              long rows_per_block) {
+  __shared__ float2 part[CS_ROWS][32];
+  const int cp = blockIdx.x * 32 + (threadIdx.x & 31);  // column pair
+  const int rl = threadIdx.x >> 5;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  const long r1 = min(M, r0 + rows_per_block);
+  float2 acc = make_float2(0.f, 0.f);
+  if (2 * cp < N) {
+    for (long r = r0 + rl; r < r1; r += CS_ROWS) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + r * ld + 2 * cp));
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+  part[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && 2 * cp < N) {
+#pragma unroll
+    for (int i = 1; i < CS_ROWS; ++i) { acc.x += part[i][threadIdx.x].x; acc.y += part[i][threadIdx.x].y; }
+    atomicAdd(out + 2 * cp, acc.x);
+    if (2 * cp + 1 < N) atomicAdd(out + 2 * cp + 1, acc.y);
+  }
+}
+
+struct PatchGeom { int B, C, H, W, p, Ho, Wo, F; };
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+// One thread per PAIR of output features (consecutive in the fast source dimension for every mode:
+// c_major+NCHW -> px pairs; pos-major+NHWC -> c pairs), so both reads and writes are coalesced.
+template <typename T>
+__global__ void patch_gather_kernel(const T* __restrict__ src, int src_nchw, int c_major, PatchGeom g,
+                                    bf16* __restrict__ dst) {
+  const long total = (long)g.B * g.Ho * g.Wo * (g.F / 2);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % (g.F / 2)) * 2;
+    const long row = i / (g.F / 2);
+    const int bx = (int)(row % g.Wo);
+    const long t = row / g.Wo;
+    const int by = (int)(t % g.Ho);
+    const int b = (int)(t / g.Ho);
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int ff = f + e;
+      int c, py, px;
+      if (c_major) { c = ff / (g.p * g.p); const int r = ff - c * g.p * g.p; py = r / g.p; px = r - py * g.p; }
+      else { const int s = ff / g.C; c = ff - s * g.C; py = s / g.p; px = s - py * g.p; }
+      const int y = by * g.p + py, x = bx * g.p + px;
+      const long off = src_nchw ? (((long)b * g.C + c) * g.H + y) * g.W + x
+                                : (((long)b * g.H + y) * g.W + x) * g.C + c;
+      v[e] = ldf<T>(src + off);
+    }
+    *reinterpret_cast<uint32_t*>(dst + row * g.F + f) = pack_bf16(v[0], v[1]);
+  }
+}
+
+template <typename T>
+__global__ void patch_scatter_kernel(const T* __restrict__ dA, int c_major, PatchGeom g,
+                                     float* __restrict__ dx, int accumulate) {
+  const long total = (long)g.B * g.Ho * g.Wo * g.F;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ff = (int)(i % g.F);
+    const long row = i / g.F;
+    const int bx = (int)(row % g.Wo);
+    const long t = row / g.Wo;
+    const int by = (int)(t % g.Ho);
+    const int b = (int)(t / g.Ho);
+    int c, py, px;
+    if (c_major) { c = ff / (g.p * g.p); const int r = ff - c * g.p * g.p; py = r / g.p; px = r - py * g.p; }
+    else { const int s = ff / g.C; c = ff - s * g.C; py = s / g.p; px = s - py * g.p; }
+    const int y = by * g.p + py, x = bx * g.p + px;
+    const long off = (((long)b * g.H + y) * g.W + x) * g.C + c;  // NHWC destination
+    const float v = ldf<T>(dA + i);
+    dx[off] = accumulate ? dx[off] + v : v;  // patches do not overlap: no atomics needed
+  }
+}
+
+__global__ void fill_rows_kernel(float* __restrict__ x, long stride, int groups, int cols,
+                                 const float* __restrict__ a, const float* __restrict__ b) {
+  const long total = (long)groups * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long gidx = i / cols;
+    x[gidx * stride + c] = a[c] + (b ? b[c] : 0.f);
+  }
+}
+
+// out[r*cols + c] += sum_g x[g*group_stride + r*cols + c]
+__global__ void rowgroup_sum_kernel(const float* __restrict__ x, long group_stride, int groups, int rows,
+                                    int cols, float* __restrict__ out) {
+  const long total = (long)rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int gi = 0; gi < groups; ++gi) acc += x[(long)gi * group_stride + i];
+    out[i] += acc;
+  }
+}
+
+__global__ void mean_rows_fwd_kernel(const float* __restrict__ x, int groups, int n, int cols,
+                                     float* __restrict__ out) {
+  const long total = (long)groups * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long gi = i / cols;
+    float acc = 0.f;
+    for (int r = 0; r < n; ++r) acc += x[(gi * n + r) * cols + c];
+    out[i] = acc / n;
+  }
+}
+__global__ void mean_rows_bwd_kernel(const float* __restrict__ dy, int groups, int n, int cols,
+                                     float* __restrict__ dx) {
+  const long total = (long)groups * n * cols;
+  const float inv = 1.f / n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long gi = i / ((long)n * cols);
+    dx[i] = dy[gi * cols + c] * inv;
+  }
+}
+
+int patch_geom(const char* who, int B, int C, int H, int W, int p, PatchGeom* g) {
+  VTB_CHECK(B > 0 && C > 0 && H > 0 && W > 0 && p > 0 && H % p == 0 && W % p == 0, -1,
+            "%s: bad geometry B=%d C=%d H=%d W=%d p=%d", who, B, C, H, W, p);
+  g->B = B; g->C = C; g->H = H; g->W = W; g->p = p; g->Ho = H / p; g->Wo = W / p; g->F = p * p * C;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int vtb_cast_f32_bf16(const float* src, void* dst, int64_t n, vtb_stream_t s) {
+  VTB_CHECK(src && dst && n >= 0, -1, "vtb_cast_f32_bf16: bad args");
+  if (n == 0) return 0;
+  VTB_CHECK(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, -1, "vtb_cast_f32_bf16: alignment");
+  cast_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)s>>>(src, (bf16*)dst, n);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_cast_f32_bf16_2d(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows,
+                                    int32_t cols, vtb_stream_t s) {
+  VTB_CHECK(src && dst && rows > 0 && cols > 0, -1, "vtb_cast_f32_bf16_2d: bad args");
+  cast2d_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)s>>>(src, lds, (bf16*)dst, ldd, rows, cols);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_scale_cast_bf16(const float* src, const float* row_scale, int32_t rows_per_scale,
+                                   int64_t rows, int32_t cols, void* dst, vtb_stream_t s) {
+  VTB_CHECK(src && dst && rows > 0 && cols > 0 && cols % 4 == 0, -1, "vtb_scale_cast_bf16: bad args");
+  VTB_CHECK(!row_scale || rows_per_scale > 0, -1, "vtb_scale_cast_bf16: rows_per_scale");
+  VTB_CHECK(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, -1, "vtb_scale_cast_bf16: alignment");
+  scale_cast_kernel<<<grid_for(rows * (cols / 4), 256, 2), 256, 0, (cudaStream_t)s>>>(
+      src, row_scale, rows_per_scale, rows, cols, (bf16*)dst);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_silu_fwd(const float* x, float* y, int64_t n, vtb_stream_t s) {
+  VTB_CHECK(x && y && n > 0, -1, "vtb_silu_fwd: bad args");
+  silu_fwd_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)s>>>(x, y, n);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, vtb_stream_t s) {
+  VTB_CHECK(x && dy && dx && n > 0, -1, "vtb_silu_bwd: bad args");
+  silu_bwd_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)s>>>(x, dy, dx, n);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_colsum_bf16(const void* X, int64_t M, int32_t N, int32_t ld, float* out, vtb_stream_t s) {
+  VTB_CHECK(X && out && M > 0 && N > 0, -1, "vtb_colsum_bf16: bad args");
+  VTB_CHECK(ld % 2 == 0 && ((uintptr_t)X & 3) == 0, -1, "vtb_colsum_bf16: alignment");
+  const int gx = ((N + 1) / 2 + 31) / 32;
+  int gy = (4 * (vtb_num_sms() > 0 ? vtb_num_sms() : 148) + gx - 1) / gx;
+  long rpb = (M + gy - 1) / gy;
+  if (rpb < 64) rpb = 64;
+  gy = (int)((M + rpb - 1) / rpb);
+  colsum_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)s>>>((const bf16*)X, M, N, ld, out, rpb);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_patch_gather(const void* src, int32_t src_bf16, int32_t src_nchw, int32_t c_major,
+                                int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, void* dst,
+                                vtb_stream_t s) {
+  PatchGeom g;
+  int rc = patch_geom("vtb_patch_gather", B, C, H, W, p, &g);
+  if (rc) return rc;
+  VTB_CHECK(src && dst, -1, "vtb_patch_gather: null pointer");
+  VTB_CHECK(g.F % 2 == 0, -1, "vtb_patch_gather: feature count must be even");
+  const long total = (long)B * g.Ho * g.Wo * (g.F / 2);
+  if (src_bf16)
+    patch_gather_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)src, src_nchw, c_major, g, (bf16*)dst);
+  else
+    patch_gather_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const float*)src, src_nchw, c_major, g, (bf16*)dst);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major, int32_t B, int32_t C,
+                                 int32_t H, int32_t W, int32_t p, float* dx, int32_t accumulate,
+                                 vtb_stream_t s) {
+  PatchGeom g;
+  int rc = patch_geom("vtb_patch_scatter", B, C, H, W, p, &g);
+  if (rc) return rc;
+  VTB_CHECK(dA && dx, -1, "vtb_patch_scatter: null pointer");
+  const long total = (long)B * g.Ho * g.Wo * g.F;
+  if (dA_f32)
+    patch_scatter_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const float*)dA, c_major, g, dx, accumulate);
+  else
+    patch_scatter_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dA, c_major, g, dx, accumulate);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_fill_rows(float* x, int64_t row_stride_groups, int32_t groups, int32_t cols,
+                             const float* a, const float* b, vtb_stream_t s) {
+  VTB_CHECK(x && a && groups > 0 && cols > 0, -1, "vtb_fill_rows: bad args");
+  fill_rows_kernel<<<grid_for((long)groups * cols, 256), 256, 0, (cudaStream_t)s>>>(x, row_stride_groups, groups, cols, a, b);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_rowgroup_sum(const float* x, int64_t group_stride, int32_t groups, int32_t rows,
+                                int32_t cols, float* out, vtb_stream_t s) {
+  VTB_CHECK(x && out && groups > 0 && rows > 0 && cols > 0, -1, "vtb_rowgroup_sum: bad args");
+  rowgroup_sum_kernel<<<grid_for((long)rows * cols, 128), 128, 0, (cudaStream_t)s>>>(x, group_stride, groups, rows, cols, out);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_mean_rows_fwd(const float* x, int32_t groups, int32_t n, int32_t cols, float* out,
+                                 vtb_stream_t s) {
+  VTB_CHECK(x && out && groups > 0 && n > 0 && cols > 0, -1, "vtb_mean_rows_fwd: bad args");
+  mean_rows_fwd_kernel<<<grid_for((long)groups * cols, 128), 128, 0, (cudaStream_t)s>>>(x, groups, n, cols, out);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_mean_rows_bwd(const float* dy, int32_t groups, int32_t n, int32_t cols, float* dx,
+                                 vtb_stream_t s) {
+  VTB_CHECK(dy && dx && groups > 0 && n > 0 && cols > 0, -1, "vtb_mean_rows_bwd: bad args");
+  mean_rows_bwd_kernel<<<grid_for((long)groups * n * cols, 256), 256, 0, (cudaStream_t)s>>>(dy, groups, n, cols, dx);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,484 @@
+// tcgen05 GEMM for sm_100a: persistent, warp-specialised.
+//   warp 0      : TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      : UMMA issuer  (tcgen05.mma cta_group::1, M=128, N=BN, K=16; fp32 accumulators in TMEM)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue (tcgen05.ld -> registers -> fused epilogue -> global)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+// Operands may be K-major or MN-major (wgrad / dgrad read the same buffers the forward wrote,
+// no transposes are materialised).  See include/vtb200.h for the contract.
+#include "common.cuh"
+#include "../../include/vtb200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+
+struct EpiParams {
+  int M, N;
+  void* out;
+  int ldo;
+  int out_f32;
+  bf16* out2;
+  const float* bias;
+  const float* resid;
+  int ldr;
+  const float* row_scale;
+  int rows_per_scale;
+  const bf16* aux;
+  int ldaux;
+  int epilogue;
+  int accumulate;
+  int og_rows, og_stride, og_off;
+  const float* rowmod_add;
+  int ld_rowmod;
+  float alpha;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 512 / 256 / 128
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// One 32-column chunk of one accumulator row -> global memory with the fused epilogue.
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_t (&acc)[32],
+                                               int m, int n0) {
+  if (m >= e.M) return;
+  long m_out = m;
+  int m_mod = 0;
+  if (e.og_rows > 0) {
+    int g = m / e.og_rows;
+    m_mod = m - g * e.og_rows;
+    m_out = (long)g * e.og_stride + e.og_off + m_mod;
+  }
+  const float rs = e.row_scale ? __ldg(e.row_scale + m / e.rows_per_scale) : 1.f;
+  const bool full = (n0 + 32 <= e.N);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full || n0 + j < e.N) v[j] += __ldg(e.bias + n0 + j);
+  }
+  if (e.epilogue == VTB_EPI_SILU_DUAL) {
+    // out <- bf16(u); v <- silu(float(bf16(u))) goes to out2  (layer.py:191-193 under autocast)
+    bf16* o1 = reinterpret_cast<bf16*>(e.out) + m_out * e.ldo + n0;
+    bf16* o2 = e.out2 + m_out * e.ldo + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t pu[4], ph[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          pu[q] = pack_bf16(v[j + 2 * q], v[j + 2 * q + 1]);
+          float2 ur = unpack_bf16(pu[q]);
+          ph[q] = pack_bf16(silu_f(ur.x), silu_f(ur.y));
+        }
+        *reinterpret_cast<uint4*>(o1 + j) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
+        *reinterpret_cast<uint4*>(o2 + j) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) {
+        bf16 u = __float2bfloat16(v[j]);
+        o1[j] = u;
+        o2[j] = __float2bfloat16(silu_f(__bfloat162float(u)));
+      }
+    }
+    return;
+  }
+  if (e.epilogue == VTB_EPI_SILU_GRAD) {
+    const bf16* a = e.aux + (long)m * e.ldaux + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 raw = *reinterpret_cast<const uint4*>(a + j);
+        uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 u = unpack_bf16(w[q]);
+          v[j + 2 * q] *= silu_grad_f(u.x);
+          v[j + 2 * q + 1] *= silu_grad_f(u.y);
+        }
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) v[j] *= silu_grad_f(__bfloat162float(a[j]));
+    }
+  }
+  if (e.row_scale) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rs;
+  }
+  if (e.rowmod_add) {
+    const float* pa = e.rowmod_add + (long)m_mod * e.ld_rowmod + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 t = *reinterpret_cast<const float4*>(pa + j);
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) v[j] += pa[j];
+    }
+  }
+  if (e.resid) {
+    const float* pr = e.resid + m_out * e.ldr + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 t = *reinterpret_cast<const float4*>(pr + j);
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) v[j] += pr[j];
+    }
+  }
+  if (e.out_f32) {
+    float* o = reinterpret_cast<float*>(e.out) + m_out * e.ldo + n0;
+    if (e.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (full || n0 + j < e.N) atomicAdd(o + j, v[j]);
+    } else if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) o[j] = v[j];
+    }
+  } else {
+    bf16* o = reinterpret_cast<bf16*>(e.out) + m_out * e.ldo + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        *reinterpret_cast<uint4*>(o + j) =
+            make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                       pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) o[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               int m_tiles, int n_tiles, int k_blocks, int splits, EpiParams epi) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = m_tiles * n_tiles * splits;
+  const int kb_per_split = (k_blocks + splits - 1) / splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile % splits;
+        const int mn = tile / splits;
+        const int n_blk = mn % n_tiles;
+        const int m_blk = mn / n_tiles;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64,
+                          kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(b_dst + i * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + i * 64,
+                          kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile % splits;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(k_blocks, kb0 + kb_per_split);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major : atoms of 8 rows x 128 B, SBO = 1024 B, advance 32 B per UMMA_K inside the row.
+            // MN-major: atoms of 8 k-rows x 64 mn (128 B), SBO = 1024 B between k-groups,
+            //           LBO = BK*128 B between 64-wide mn atoms, advance 16 k-rows = 2048 B.
+            const uint64_t adesc = A_MN ? umma_desc_sw128(a_base + k * (UMMA_K * 128), BK * 128, 1024)
+                                        : umma_desc_sw128(a_base + k * (UMMA_K * 2), 0, 1024);
+            const uint64_t bdesc = B_MN ? umma_desc_sw128(b_base + k * (UMMA_K * 128), BK * 128, 1024)
+                                        : umma_desc_sw128(b_base + k * (UMMA_K * 2), 0, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mn = tile / splits;
+      const int n_blk = mn % n_tiles;
+      const int m_blk = mn / n_tiles;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int m = m_blk * BM + ew * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= epi.N) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld_32x32(t_row + c * 32, acc);
+        tmem_ld_wait();
+        epilogue_chunk(epi, acc, m, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+              uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vtb_set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
+                  (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
+                  (unsigned long long)ld_elems, box_inner, box_outer);
+    return -3;
+  }
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap(&ta, p->A, p->K, p->M, p->lda, BK, BM);
+  else       rc = make_tmap(&ta, p->A, p->M, p->K, p->lda, 64, BK);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap(&tb, p->B, p->K, p->N, p->ldb, BK, BN);
+  else       rc = make_tmap(&tb, p->B, p->N, p->K, p->ldb, 64, BK);
+  if (rc) return rc;
+  const int m_tiles = (p->M + BM - 1) / BM;
+  const int n_tiles = (p->N + BN - 1) / BN;
+  const int k_blocks = (p->K + BK - 1) / BK;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = m_tiles * n_tiles * splits;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, m_tiles, n_tiles, k_blocks, splits, epi);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int dispatch_major(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStream_t s) {
+  if (!p->a_mn_major && !p->b_mn_major) return launch<BN, false, false>(p, epi, splits, s);
+  if (!p->a_mn_major && p->b_mn_major) return launch<BN, false, true>(p, epi, splits, s);
+  if (p->a_mn_major && p->b_mn_major) return launch<BN, true, true>(p, epi, splits, s);
+  return launch<BN, true, false>(p, epi, splits, s);
+}
+
+}  // namespace
+
+int vtb_gemm_init() {
+  if (g_encode) return 0;
+  int dev = 0;
+  VTB_CUDA(cudaGetDevice(&dev));
+  VTB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  VTB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  VTB_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, -2,
+            "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+int vtb_num_sms() { return g_num_sms; }
+
+extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(p != nullptr, -1, "vtb_gemm_bf16: null params");
+  VTB_CHECK(g_encode != nullptr, -2, "vtb_gemm_bf16: call vtb_init() first");
+  VTB_CHECK(p->M > 0 && p->N > 0 && p->K > 0, -1, "vtb_gemm_bf16: bad shape M=%d N=%d K=%d", p->M,
+            p->N, p->K);
+  VTB_CHECK(p->A && p->B && p->out, -1, "vtb_gemm_bf16: null operand");
+  VTB_CHECK(((uintptr_t)p->A & 15) == 0 && ((uintptr_t)p->B & 15) == 0, -1,
+            "vtb_gemm_bf16: operands must be 16-byte aligned");
+  VTB_CHECK(p->lda % 8 == 0 && p->ldb % 8 == 0, -1,
+            "vtb_gemm_bf16: lda/ldb must be multiples of 8 (TMA 16-byte strides), got %d %d",
+            p->lda, p->ldb);
+  VTB_CHECK(!p->accumulate || p->out_f32, -1, "vtb_gemm_bf16: accumulate needs an f32 output");
+  VTB_CHECK(p->splits <= 1 || p->accumulate, -1, "vtb_gemm_bf16: split-K needs accumulate=1");
+  VTB_CHECK(p->epilogue != VTB_EPI_SILU_DUAL || (p->out2 && !p->out_f32), -1,
+            "vtb_gemm_bf16: SILU_DUAL needs bf16 out and out2");
+  VTB_CHECK(p->epilogue != VTB_EPI_SILU_GRAD || p->aux, -1, "vtb_gemm_bf16: SILU_GRAD needs aux");
+  // vector epilogue accesses: full 32-column chunks use 16-byte stores
+  const int oalign = p->out_f32 ? 4 : 8;
+  VTB_CHECK(p->ldo % oalign == 0 && ((uintptr_t)p->out & 15) == 0, -1,
+            "vtb_gemm_bf16: out must be 16-byte aligned with ldo %% %d == 0", oalign);
+  VTB_CHECK(!p->resid || (p->ldr % 4 == 0 && ((uintptr_t)p->resid & 15) == 0), -1,
+            "vtb_gemm_bf16: resid alignment");
+  VTB_CHECK(!p->aux || (p->ldaux % 8 == 0 && ((uintptr_t)p->aux & 15) == 0), -1,
+            "vtb_gemm_bf16: aux alignment");
+  VTB_CHECK(!p->rowmod_add || (p->ld_rowmod % 4 == 0 && ((uintptr_t)p->rowmod_add & 15) == 0 &&
+                               p->out_group_rows > 0),
+            -1, "vtb_gemm_bf16: rowmod_add alignment / needs out_group_rows");
+  VTB_CHECK(!p->row_scale || p->rows_per_scale > 0, -1, "vtb_gemm_bf16: rows_per_scale");
+
+  EpiParams e;
+  e.M = p->M; e.N = p->N;
+  e.out = p->out; e.ldo = p->ldo; e.out_f32 = p->out_f32;
+  e.out2 = reinterpret_cast<bf16*>(p->out2);
+  e.bias = p->bias;
+  e.resid = p->resid; e.ldr = p->ldr;
+  e.row_scale = p->row_scale; e.rows_per_scale = p->rows_per_scale;
+  e.aux = reinterpret_cast<const bf16*>(p->aux); e.ldaux = p->ldaux;
+  e.epilogue = p->epilogue;
+  e.accumulate = p->accumulate;
+  e.og_rows = p->out_group_rows; e.og_stride = p->out_group_stride; e.og_off = p->out_group_off;
+  e.rowmod_add = p->rowmod_add; e.ld_rowmod = p->ld_rowmod;
+  e.alpha = p->alpha;
+
+  // Tile-N choice: widest tile that does not waste more than ~25% of the MMA columns.
+  int bn = 256;
+  if (p->N <= 64) bn = 64;
+  else if (p->N <= 128) bn = 128;
+  else {
+    auto waste = [&](int b) { return (double)(((p->N + b - 1) / b) * b) / p->N; };
+    if (waste(256) > 1.2 * waste(128)) bn = 128;
+    if (bn == 128 && waste(128) > 1.2 * waste(64)) bn = 64;
+  }
+  const int m_tiles = (p->M + BM - 1) / BM;
+  const int n_tiles = (p->N + bn - 1) / bn;
+  const int k_blocks = (p->K + BK - 1) / BK;
+  int splits = p->splits;
+  if (splits <= 0) {
+    splits = 1;
+    if (p->accumulate) {
+      // fill the machine: enough split-K slices for >= 2 waves' worth of tiles, >= 8 k-blocks each
+      const int tiles = m_tiles * n_tiles;
+      int want = (2 * g_num_sms + tiles - 1) / tiles;
+      int maxs = k_blocks / 8;
+      if (maxs < 1) maxs = 1;
+      splits = want < maxs ? want : maxs;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > k_blocks) splits = k_blocks;
+  {  // no empty split
+    int per = (k_blocks + splits - 1) / splits;
+    splits = (k_blocks + per - 1) / per;
+  }
+  switch (bn) {
+    case 256: return dispatch_major<256>(p, e, splits, stream);
+    case 128: return dispatch_major<128>(p, e, splits, stream);
+    default:  return dispatch_major<64>(p, e, splits, stream);
+  }
+}

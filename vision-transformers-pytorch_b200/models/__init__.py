@@ -1,0 +1,10 @@
+"""Drop-in `models` package: same exports as the reference's models/__init__.py:1-7 for the transformer
+families (the hot path).  The CNN zoo (NFNet / EfficientNet / NF-EfficientNetV2: cuDNN conv nets) is outside
+the transformer-block path and is not re-implemented here."""
+from .halo_transformer import HaloTransformer
+from .pvt import PyramidVisionTransformer
+from .swin_transformer import SwinTransformer
+from .vit import DINOHead, FusedLinear, VisionTransformer, dino
+
+__all__ = ["HaloTransformer", "PyramidVisionTransformer", "SwinTransformer", "VisionTransformer",
+           "DINOHead", "FusedLinear", "dino"]

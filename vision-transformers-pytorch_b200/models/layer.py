@@ -1,0 +1,72 @@
+"""Shared layer holders (reference: models/layer.py:25,166-196).
+
+These modules only HOLD parameters / hyper-parameters under the reference's names; the arithmetic of a
+block runs in vtb200.blocks (one autograd.Function per pre-LN branch)."""
+from collections import abc
+from itertools import repeat
+
+import torch
+from torch import nn
+
+
+def ensure_tuple(x, n_item):
+    if isinstance(x, abc.Iterable):
+        try:
+            if len(x) != n_item:
+                raise ValueError(f"length of {x} (length: {len(x)}) does not match n_item={n_item}")
+        except TypeError:
+            pass
+        return x
+    return tuple(repeat(x, n_item))
+
+
+def tuple2(x):
+    return ensure_tuple(x, 2)
+
+
+class DropPath(nn.Module):
+    """Holder of the stochastic-depth rate `p` (layer.py:166-183).  The per-sample keep mask is drawn by
+    vtb200.blocks.make_drop_path_scale and applied inside the residual GEMM epilogue."""
+
+    def __init__(self, p=0):
+        super().__init__()
+        self.p = p
+
+    def scale(self, batch, like=torch.bfloat16):
+        from vtb200.blocks import make_drop_path_scale
+
+        return make_drop_path_scale(self.training, self.p, batch, like)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(p={self.p})"
+
+
+class PositionwiseFeedForward(nn.Sequential):
+    """Linear - SiLU - Dropout - Linear parameter holder (layer.py:186-196); indices 0 and 3 are the
+    Linears, exactly as in the reference state_dict."""
+
+    def __init__(self, in_dim, dim=None, out_dim=None, activation=nn.SiLU, dropout=0):
+        dim = in_dim if dim is None else dim
+        out_dim = in_dim if out_dim is None else out_dim
+        if activation is not nn.SiLU:
+            raise NotImplementedError("vtb200: the fused FFN kernel implements SiLU (the only activation "
+                                      "any reference block uses, layer.py:187)")
+        super().__init__(nn.Linear(in_dim, dim), activation(), nn.Dropout(dropout), nn.Linear(dim, out_dim))
+
+    def params(self):
+        return self[0].weight, self[0].bias, self[3].weight, self[3].bias
+
+
+def check_no_dropout(module, *ps):
+    """nn.Dropout with p > 0 in training mode is not fused (every BASELINE config uses 0)."""
+    if module.training and any(float(p) > 0 for p in ps):
+        raise NotImplementedError("vtb200: element dropout p > 0 is not implemented in the fused blocks "
+                                  "(all reference configs use dropout = drop_attn = drop_ff = 0)")
+
+
+def ffn_branch(x, drop_path, norm, ff, rows_per_sample):
+    from vtb200.blocks import FFNBranchFn
+
+    w1, b1, w2, b2 = ff.params()
+    return FFNBranchFn.apply(x, drop_path.scale(x.shape[0]), norm.eps, rows_per_sample, norm.weight,
+                             norm.bias, w1, b1, w2, b2)

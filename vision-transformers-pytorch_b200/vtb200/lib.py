@@ -1,0 +1,137 @@
+"""ctypes binding of libvtb200.so (C-ABI declared in include/vtb200.h).
+
+The library is the product: there is NO CPU / eager fallback.  Importing this module never needs a GPU
+(so the `-m "not gpu"` suite can check that the library loads and exports every symbol); calling any
+op without CUDA raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvtb200.so")
+
+EPI_NONE, EPI_SILU_DUAL, EPI_SILU_GRAD = 0, 1, 2
+ATTN_GLOBAL, ATTN_WINDOW, ATTN_HALO = 0, 1, 2
+
+# every symbol include/vtb200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "vtb_last_error", "vtb_version", "vtb_init", "vtb_gemm_bf16", "vtb_layernorm_fwd",
+    "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_cast_f32_bf16",
+    "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
+    "vtb_patch_scatter", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
+    "vtb_silu_fwd", "vtb_silu_bwd",
+]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int32), ("a_mn_major", C.c_int32),
+        ("B", C.c_void_p), ("ldb", C.c_int32), ("b_mn_major", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int32), ("out_f32", C.c_int32),
+        ("out2", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p), ("ldr", C.c_int32),
+        ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
+        ("aux", C.c_void_p), ("ldaux", C.c_int32),
+        ("epilogue", C.c_int32), ("splits", C.c_int32), ("accumulate", C.c_int32),
+        ("out_group_rows", C.c_int32), ("out_group_stride", C.c_int32), ("out_group_off", C.c_int32),
+        ("rowmod_add", C.c_void_p), ("ld_rowmod", C.c_int32),
+        ("alpha", C.c_float),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("batch", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32),
+        ("nq", C.c_int32), ("nkv", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
+        ("window", C.c_int32), ("shift", C.c_int32), ("halo", C.c_int32),
+        ("scale", C.c_float),
+        ("q", C.c_void_p), ("ldq", C.c_int32),
+        ("k", C.c_void_p), ("ldk", C.c_int32),
+        ("v", C.c_void_p), ("ldv", C.c_int32),
+        ("o", C.c_void_p), ("ldo", C.c_int32),
+        ("lse", C.c_void_p),
+        ("rel_bias", C.c_void_p),
+        ("pos", C.c_void_p), ("n_pos", C.c_int32),
+        ("mask", C.c_void_p), ("n_mask", C.c_int32),
+        ("dout", C.c_void_p), ("lddo", C.c_int32),
+        ("dq", C.c_void_p), ("lddq", C.c_int32),
+        ("dk", C.c_void_p), ("lddk", C.c_int32),
+        ("dv", C.c_void_p), ("lddv", C.c_int32),
+        ("dkv_f32", C.c_int32),
+        ("delta", C.c_void_p),
+        ("drel_bias", C.c_void_p),
+    ]
+
+
+_lib = None
+_inited = False
+
+
+def load():
+    """dlopen the library (no GPU needed) and set prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"vtb200: {LIB_PATH} is missing — build it with `python __graft_entry__.py build` "
+            "(or `make -C vision-transformers-pytorch_b200/csrc`). There is no fallback path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.vtb_last_error.restype = C.c_char_p
+    lib.vtb_last_error.argtypes = []
+    lib.vtb_version.restype = i32
+    lib.vtb_init.restype = i32
+    lib.vtb_gemm_bf16.argtypes = [C.POINTER(GemmParams), vp]
+    lib.vtb_layernorm_fwd.argtypes = [vp, vp, vp, f32, i64, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp]
+    lib.vtb_layernorm_bwd.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp,
+                                      i32, vp, vp, vp]
+    lib.vtb_attention_fwd.argtypes = [C.POINTER(AttnParams), vp]
+    lib.vtb_attention_bwd.argtypes = [C.POINTER(AttnParams), vp]
+    lib.vtb_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
+    lib.vtb_cast_f32_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+    lib.vtb_scale_cast_bf16.argtypes = [vp, vp, i32, i64, i32, vp, vp]
+    lib.vtb_colsum_bf16.argtypes = [vp, i64, i32, i32, vp, vp]
+    lib.vtb_patch_gather.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.vtb_patch_scatter.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+    lib.vtb_fill_rows.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+    lib.vtb_rowgroup_sum.argtypes = [vp, i64, i32, i32, i32, vp, vp]
+    lib.vtb_mean_rows_fwd.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.vtb_mean_rows_bwd.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.vtb_silu_fwd.argtypes = [vp, vp, i64, vp]
+    lib.vtb_silu_bwd.argtypes = [vp, vp, vp, i64, vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("vtb_last_error",):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def get():
+    """Library handle, initialised for the current CUDA device.  Raises without a GPU."""
+    global _inited
+    lib = load()
+    if not _inited:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "vtb200: CUDA device required — the sm_100a kernels are the only implementation "
+                "(no CPU fallback by design)."
+            )
+        torch.cuda.current_device()  # make sure a context exists
+        torch.zeros(1, device="cuda")
+        check(lib.vtb_init(), lib)
+        _inited = True
+    return lib
+
+
+def check(rc, lib=None):
+    if rc != 0:
+        lib = lib or load()
+        msg = lib.vtb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"vtb200 error {rc}: {msg}")

@@ -1,0 +1,332 @@
+"""Tensor-level wrappers over the C-ABI (include/vtb200.h).
+
+torch is used only for device memory, the current stream and dtype bookkeeping; every FLOP and every
+byte moved on the hot path happens inside libvtb200.so.  LAUNCHES counts the library calls (the
+`gpu_launches` claim in bench.py).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as _l
+
+LAUNCHES = 0
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _chk2d(t, dtype, name):
+    if t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
+        raise ValueError(f"vtb200.{name}: expected 2-D row-major {dtype} CUDA tensor, got "
+                         f"{t.dtype} {tuple(t.shape)} strides {t.stride()} on {t.device}")
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, resid=None,
+         row_scale=None, rows_per_scale=0, epilogue=_l.EPI_NONE, aux=None, out2=None, accumulate=False,
+         splits=0, out_group=None, rowmod_add=None, alpha=1.0):
+    """C[M,N] = alpha * sum_k A(m,k) B(n,k) with the fused epilogue of vtb_gemm_bf16.
+
+    a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] or [K,N] (b_mn=True); both bf16 row-major
+    (leading stride may exceed the row length: views into wider buffers are fine).
+    """
+    lib = _l.get()
+    _chk2d(a, BF16, "gemm(a)")
+    _chk2d(b, BF16, "gemm(b)")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError(f"vtb200.gemm: K mismatch {K} vs {Kb}")
+    rows_out = M
+    if out_group is not None:
+        g_rows, g_stride, g_off = out_group
+        if M % g_rows:
+            raise ValueError("vtb200.gemm: M must be a multiple of out_group rows")
+        rows_out = (M // g_rows) * g_stride
+    if out is None:
+        if out_group is not None:
+            raise ValueError("vtb200.gemm: out_group needs an explicit out tensor")
+        out = (torch.zeros if accumulate else torch.empty)((M, N), dtype=out_dtype, device=a.device)
+    _chk2d(out, out.dtype, "gemm(out)")
+    if out.shape[0] < rows_out or out.shape[1] != N:
+        raise ValueError(f"vtb200.gemm: out shape {tuple(out.shape)} vs ({rows_out},{N})")
+    p = _l.GemmParams()
+    p.M, p.N, p.K = M, N, K
+    p.A, p.lda, p.a_mn_major = a.data_ptr(), a.stride(0), int(a_mn)
+    p.B, p.ldb, p.b_mn_major = b.data_ptr(), b.stride(0), int(b_mn)
+    p.out, p.ldo, p.out_f32 = out.data_ptr(), out.stride(0), int(out.dtype == F32)
+    if out.dtype not in (F32, BF16):
+        raise ValueError("vtb200.gemm: out must be f32 or bf16")
+    if out2 is not None:
+        _chk2d(out2, BF16, "gemm(out2)")
+        if out2.stride(0) != out.stride(0) or out2.shape != out.shape:
+            raise ValueError("vtb200.gemm: out2 must match out")
+        p.out2 = out2.data_ptr()
+    if bias is not None:
+        if bias.dtype != F32 or bias.numel() != N or not bias.is_contiguous():
+            raise ValueError("vtb200.gemm: bias must be contiguous f32 [N]")
+        p.bias = bias.data_ptr()
+    if resid is not None:
+        _chk2d(resid, F32, "gemm(resid)")
+        p.resid, p.ldr = resid.data_ptr(), resid.stride(0)
+    if row_scale is not None:
+        if row_scale.dtype != F32 or not row_scale.is_contiguous() or rows_per_scale <= 0:
+            raise ValueError("vtb200.gemm: row_scale must be contiguous f32 with rows_per_scale > 0")
+        if row_scale.numel() * rows_per_scale < M:
+            raise ValueError("vtb200.gemm: row_scale too short")
+        p.row_scale, p.rows_per_scale = row_scale.data_ptr(), rows_per_scale
+    if aux is not None:
+        _chk2d(aux, BF16, "gemm(aux)")
+        p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
+    p.epilogue, p.splits, p.accumulate = epilogue, splits, int(accumulate)
+    if out_group is not None:
+        p.out_group_rows, p.out_group_stride, p.out_group_off = out_group
+    if rowmod_add is not None:
+        _chk2d(rowmod_add, F32, "gemm(rowmod_add)")
+        p.rowmod_add, p.ld_rowmod = rowmod_add.data_ptr(), rowmod_add.stride(0)
+    p.alpha = alpha
+    _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
+    _count()
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, patchify=None, rowmod_add=None, group_rows=0):
+    """x f32 [rows, cols] (or NHWC [B,H,W,C] with patchify=(s,H,W)) -> y, mean, rstd."""
+    lib = _l.get()
+    if x.dtype != F32 or not x.is_contiguous():
+        raise ValueError("vtb200.layernorm_fwd: x must be contiguous f32")
+    if patchify is None:
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        s, H, W = 0, 0, 0
+    else:
+        s, H, W = patchify
+        Cc = x.shape[-1]
+        cols = s * s * Cc
+        rows = x.numel() // cols
+    y = torch.empty((rows, cols), dtype=out_dtype, device=x.device)
+    mean = torch.empty(rows, dtype=F32, device=x.device)
+    rstd = torch.empty(rows, dtype=F32, device=x.device)
+    _l.check(lib.vtb_layernorm_fwd(_p(x), _p(gamma), _p(beta), float(eps), rows, cols, s, H, W, _p(y),
+                                   int(out_dtype == F32), _p(mean), _p(rstd), _p(rowmod_add),
+                                   group_rows, _stream()), lib)
+    _count()
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_in=None, dx_out=None, patchify=None, want_bf16=False,
+                  row_scale=None, rows_per_scale=0, dgamma=None, dbeta=None):
+    """Returns dx (f32, same shape as x), optional bf16 scaled copy, dgamma, dbeta (accumulated)."""
+    lib = _l.get()
+    cols = dy.shape[-1]
+    rows = dy.numel() // cols
+    if not dy.is_contiguous() or dy.dtype not in (F32, BF16):
+        raise ValueError("vtb200.layernorm_bwd: dy must be contiguous f32/bf16")
+    s, H, W = patchify if patchify is not None else (0, 0, 0)
+    if dx_out is None:
+        dx_out = torch.empty_like(x)
+    dxb = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
+    if dgamma is None:
+        dgamma = torch.zeros(cols, dtype=F32, device=x.device)
+    if dbeta is None:
+        dbeta = torch.zeros(cols, dtype=F32, device=x.device)
+    _l.check(lib.vtb_layernorm_bwd(_p(dy), int(dy.dtype == F32), _p(x), _p(gamma), _p(mean), _p(rstd),
+                                   rows, cols, s, H, W, _p(dx_in), _p(dx_out), _p(dxb), _p(row_scale),
+                                   rows_per_scale, _p(dgamma), _p(dbeta), _stream()), lib)
+    _count()
+    return dx_out, dxb, dgamma, dbeta
+
+
+class AttnSpec:
+    """Geometry of one attention call (mirrors vtb_attn_params)."""
+
+    def __init__(self, mode, batch, heads, dh, nq, nkv, Hs=0, Ws=0, window=0, shift=0, halo=0,
+                 rel_bias=None, pos=None, mask=None):
+        self.mode, self.batch, self.heads, self.dh = mode, batch, heads, dh
+        self.nq, self.nkv, self.Hs, self.Ws = nq, nkv, Hs, Ws
+        self.window, self.shift, self.halo = window, shift, halo
+        self.rel_bias, self.pos, self.mask = rel_bias, pos, mask
+        self.scale = 1.0 / math.sqrt(dh)
+
+    @property
+    def groups(self):
+        if self.mode == _l.ATTN_GLOBAL:
+            return self.batch
+        return self.batch * (self.Hs // self.window) * (self.Ws // self.window)
+
+    def fill(self, p):
+        p.mode, p.batch, p.heads, p.dh = self.mode, self.batch, self.heads, self.dh
+        p.nq, p.nkv, p.Hs, p.Ws = self.nq, self.nkv, self.Hs, self.Ws
+        p.window, p.shift, p.halo = self.window, self.shift, self.halo
+        p.scale = self.scale
+        if self.rel_bias is not None:
+            if self.rel_bias.dtype != F32 or not self.rel_bias.is_contiguous():
+                raise ValueError("vtb200.attention: rel_bias must be contiguous f32 [n_pos, heads]")
+            if self.pos.dtype != torch.int32 or not self.pos.is_contiguous():
+                raise ValueError("vtb200.attention: pos must be contiguous int32 [nq, nkv]")
+            p.rel_bias, p.pos, p.n_pos = self.rel_bias.data_ptr(), self.pos.data_ptr(), self.rel_bias.shape[0]
+        if self.mask is not None:
+            if self.mask.dtype != torch.uint8 or not self.mask.is_contiguous():
+                raise ValueError("vtb200.attention: mask must be contiguous uint8 [n_mask, nq, nkv]")
+            p.mask, p.n_mask = self.mask.data_ptr(), self.mask.shape[0]
+
+
+def _qkv_fill(p, q, k, v):
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk2d(t, BF16, f"attention({nm})")
+    p.q, p.ldq = q.data_ptr(), q.stride(0)
+    p.k, p.ldk = k.data_ptr(), k.stride(0)
+    p.v, p.ldv = v.data_ptr(), v.stride(0)
+
+
+def attention_fwd(spec, q, k, v):
+    """q [Tq, >=H*dh], k/v [Tkv, >=H*dh] bf16 views (row-major). Returns o [Tq, H*dh] bf16, lse."""
+    lib = _l.get()
+    p = _l.AttnParams()
+    spec.fill(p)
+    _qkv_fill(p, q, k, v)
+    o = torch.empty((q.shape[0], spec.heads * spec.dh), dtype=BF16, device=q.device)
+    lse = torch.empty((spec.groups, spec.heads, spec.nq), dtype=F32, device=q.device)
+    p.o, p.ldo, p.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
+    _l.check(lib.vtb_attention_fwd(C.byref(p), _stream()), lib)
+    _count()
+    return o, lse
+
+
+def attention_bwd(spec, q, k, v, o, lse, dout, dq, dk, dv, drel_bias=None, dkv_f32=False):
+    """Writes dq/dk/dv (views with the same layout as q/k/v; dk/dv f32 + pre-zeroed when dkv_f32)."""
+    lib = _l.get()
+    p = _l.AttnParams()
+    spec.fill(p)
+    _qkv_fill(p, q, k, v)
+    _chk2d(o, BF16, "attention_bwd(o)")
+    _chk2d(dout, BF16, "attention_bwd(dout)")
+    delta = torch.empty_like(lse)
+    p.o, p.ldo, p.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
+    p.dout, p.lddo = dout.data_ptr(), dout.stride(0)
+    p.dq, p.lddq = dq.data_ptr(), dq.stride(0)
+    p.dk, p.lddk = dk.data_ptr(), dk.stride(0)
+    p.dv, p.lddv = dv.data_ptr(), dv.stride(0)
+    p.dkv_f32 = int(dkv_f32)
+    p.delta = delta.data_ptr()
+    if drel_bias is not None:
+        p.drel_bias = drel_bias.data_ptr()
+    _l.check(lib.vtb_attention_bwd(C.byref(p), _stream()), lib)
+    _count(2)
+
+
+def cast_bf16(src):
+    lib = _l.get()
+    if src.dtype != F32 or not src.is_contiguous():
+        raise ValueError("vtb200.cast_bf16: contiguous f32 expected")
+    dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+    if src.numel():
+        _l.check(lib.vtb_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), lib)
+        _count()
+    return dst
+
+
+def scale_cast_bf16(src, row_scale=None, rows_per_scale=0):
+    """bf16(src * row_scale[row // rows_per_scale]); src f32 [..., cols] contiguous."""
+    lib = _l.get()
+    if src.dtype != F32 or not src.is_contiguous():
+        raise ValueError("vtb200.scale_cast_bf16: contiguous f32 expected")
+    cols = src.shape[-1]
+    rows = src.numel() // cols
+    dst = torch.empty((rows, cols), dtype=BF16, device=src.device)
+    _l.check(lib.vtb_scale_cast_bf16(_p(src), _p(row_scale), rows_per_scale, rows, cols, _p(dst),
+                                     _stream()), lib)
+    _count()
+    return dst
+
+
+def colsum(x, out=None):
+    lib = _l.get()
+    _chk2d(x, BF16, "colsum")
+    M, N = x.shape
+    if out is None:
+        out = torch.zeros(N, dtype=F32, device=x.device)
+    _l.check(lib.vtb_colsum_bf16(_p(x), M, N, x.stride(0), _p(out), _stream()), lib)
+    _count()
+    return out
+
+
+def patch_gather(src, *, nchw, c_major, B, Cc, H, W, p):
+    lib = _l.get()
+    if not src.is_contiguous() or src.dtype not in (F32, BF16):
+        raise ValueError("vtb200.patch_gather: contiguous f32/bf16 expected")
+    rows = B * (H // p) * (W // p)
+    dst = torch.empty((rows, p * p * Cc), dtype=BF16, device=src.device)
+    _l.check(lib.vtb_patch_gather(_p(src), int(src.dtype == BF16), int(nchw), int(c_major), B, Cc, H, W,
+                                  p, _p(dst), _stream()), lib)
+    _count()
+    return dst
+
+
+def patch_scatter(dA, *, c_major, B, Cc, H, W, p, dx=None, accumulate=False):
+    lib = _l.get()
+    if not dA.is_contiguous() or dA.dtype not in (F32, BF16):
+        raise ValueError("vtb200.patch_scatter: contiguous f32/bf16 expected")
+    if dx is None:
+        dx = torch.empty((B, H, W, Cc), dtype=F32, device=dA.device)
+    _l.check(lib.vtb_patch_scatter(_p(dA), int(dA.dtype == F32), int(c_major), B, Cc, H, W, p, _p(dx),
+                                   int(accumulate), _stream()), lib)
+    _count()
+    return dx
+
+
+def fill_rows(x, group_stride, groups, cols, a, b=None):
+    lib = _l.get()
+    _l.check(lib.vtb_fill_rows(_p(x), group_stride, groups, cols, _p(a), _p(b), _stream()), lib)
+    _count()
+
+
+def rowgroup_sum(x, group_stride, groups, rows, cols, out):
+    lib = _l.get()
+    _l.check(lib.vtb_rowgroup_sum(_p(x), group_stride, groups, rows, cols, _p(out), _stream()), lib)
+    _count()
+
+
+def mean_rows_fwd(x, groups, n, cols):
+    lib = _l.get()
+    out = torch.empty((groups, cols), dtype=F32, device=x.device)
+    _l.check(lib.vtb_mean_rows_fwd(_p(x), groups, n, cols, _p(out), _stream()), lib)
+    _count()
+    return out
+
+
+def mean_rows_bwd(dy, groups, n, cols):
+    lib = _l.get()
+    dx = torch.empty((groups * n, cols), dtype=F32, device=dy.device)
+    _l.check(lib.vtb_mean_rows_bwd(_p(dy), groups, n, cols, _p(dx), _stream()), lib)
+    _count()
+    return dx
+
+
+def silu_fwd(x):
+    lib = _l.get()
+    y = torch.empty_like(x)
+    _l.check(lib.vtb_silu_fwd(_p(x), _p(y), x.numel(), _stream()), lib)
+    _count()
+    return y
+
+
+def silu_bwd(x, dy):
+    lib = _l.get()
+    dx = torch.empty_like(x)
+    _l.check(lib.vtb_silu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _stream()), lib)
+    _count()
+    return dx
