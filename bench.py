@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — images/sec, fwd+bwd, on the BASELINE.json configurations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vit_b16|swin_s|pvt_small|halo_t] [--impl reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1); rank 0 prints ONE JSON line.
+A step = forward + cross-entropy + backward of the whole model on one synthetic batch (256 images/GPU, weak
+scaling), gradients of every parameter produced and (N > 1) all-reduced — the reference's step body
+train.py:265-283 without the optimizer (metric: "images/sec fwd+bwd").  `value` has inputs resident in HBM;
+`e2e` runs the same step from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed region).
+--impl reference times the oracle port of the reference path on the host cores (oracle/restate.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "vision-transformers-pytorch_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec fwd+bwd"
+# fwd+bwd GFLOP per image: matmul+bmm+conv FLOPs of the reference graph (BASELINE.md §2 / SURVEY §8d)
+WORKLOADS = {
+    "vit_b16": dict(gflop=105.147, batch=256, desc="ViT-B/16 224x224 fwd+bwd, batch 256/GPU"),
+    "swin_s": dict(gflop=52.416, batch=256, desc="Swin-S 224x224 fwd+bwd, batch 256/GPU"),
+    "pvt_small": dict(gflop=22.875, batch=128, desc="PVT-Small 224x224 fwd+bwd, batch 128/GPU"),
+    "halo_t": dict(gflop=29.36, batch=128, desc="Halo-T* 224x224 fwd+bwd, batch 128/GPU"),
+    "vit_tiny": dict(gflop=7.463, batch=64, desc="ViT-Tiny/16 224x224 fwd+bwd (plumbing)"),
+}
+
+
+def build_model(workload, drop_path=None):
+    import models
+
+    if workload == "vit_b16":
+        dp = 0.1 if drop_path is None else drop_path
+        return models.VisionTransformer(models.FusedLinear(768, 1000), 224, 16, 12, 768, 12, 3072, 0., 0., 0., dp)
+    if workload == "vit_tiny":
+        return models.VisionTransformer(models.FusedLinear(192, 1000), 224, 16, 12, 192, 3, 768, 0., 0., 0., 0.)
+    if workload == "swin_s":
+        dp = 0.3 if drop_path is None else drop_path
+        return models.SwinTransformer((224, 224), 1000, (2, 2, 18, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
+                                      (384, 768, 1536, 3072), 7, drop_path=dp)
+    if workload == "pvt_small":
+        return models.PyramidVisionTransformer(224, 1000, 3, (3, 4, 6, 3), (64, 128, 320, 512), (1, 2, 5, 8),
+                                               (512, 1024, 1280, 2048), (8, 4, 2, 1), drop_path=0.1)
+    if workload == "halo_t":
+        return models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
+                                      (384, 768, 1536, 3072), window_size=7, halo_size=3, drop_path=0.1)
+    raise KeyError(workload)
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", 1410.6), d.get("hbm_gbs", 6452.5), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_step(workload, batch, threads):
+    """One fwd+bwd of the oracle port on the host: returns a closure and the images per call."""
+    from oracle import restate as R
+    import models
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    model = build_model(workload, drop_path=0.0)
+    sd = {k: (v.detach().clone().requires_grad_(v.is_floating_point())) for k, v in model.state_dict().items()}
+    x = torch.randn(batch, 3, 224, 224)
+    y = torch.randint(0, 1000, (batch,))
+
+    def fwd():
+        if workload in ("vit_b16", "vit_tiny"):
+            heads = 12 if workload == "vit_b16" else 3
+            return R.vit_forward(sd, x, patch=16, depth=12, heads=heads,
+                                 head_fn=lambda f: R.linear(f, sd["head.weight"], sd["head.bias"]))
+        if workload == "swin_s":
+            return R.swin_forward(sd, x, depths=(2, 2, 18, 2), n_heads=(3, 6, 12, 24), dim_head=32, window=7)
+        if workload == "pvt_small":
+            return R.pvt_forward(sd, x, depths=(3, 4, 6, 3), n_heads=(1, 2, 5, 8), reductions=(8, 4, 2, 1))
+        return R.halo_forward(sd, x, depths=(2, 2, 6, 2), n_heads=(3, 6, 12, 24), dim_head=32, window=7, halo=3)
+
+    def step():
+        for v in sd.values():
+            if v.is_floating_point():
+                v.grad = None
+        loss = torch.nn.functional.cross_entropy(fwd(), y)
+        loss.backward()
+        return loss.item()
+
+    return step
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 8
+    step = cpu_reference_step(args.workload, batch, threads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = batch / dt
+    sample = f"{WORKLOADS[args.workload]['desc'].split(',')[0]} fp32, batch {batch} per step, {steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "batch_per_step": batch, "where": "host CPU, oracle port of the reference path"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="vit_b16", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's)")
+    ap.add_argument("--impl", default="vtb200", choices=["vtb200", "reference"])
+    ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from vtb200 import dist as vd
+    from vtb200 import ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: a CUDA device is required (the sm_100a kernels are the only implementation)")
+    rank, local_rank, world = vd.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device("cuda", local_rank)
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    W = max(3, args.warmup)
+
+    torch.manual_seed(1234 + rank)
+    model = build_model(args.workload).to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    net, reducer = model, None
+    if world > 1:
+        if args.reducer == "ddp":
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
+                                                            gradient_as_bucket_view=True, bucket_cap_mb=64)
+        else:
+            reducer = vd.FlatGradReducer(params)
+    x_dev = torch.randn(B, 3, 224, 224, device=dev)
+    y_dev = torch.randint(0, 1000, (B,), device=dev)
+
+    def step(x, y):
+        for p in params:
+            p.grad = None
+        loss = torch.nn.functional.cross_entropy(net(x), y)
+        loss.backward()
+        if reducer is not None:
+            reducer.reduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing (`value`)
+    for _ in range(W):
+        step(x_dev, y_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    ms = vd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    launches = (ops.LAUNCHES - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B / (ms * 1e-3)
+
+    # ---------------------------------------------------------------- live roofline pass (dominant kernel: GEMM)
+    ops.PROFILE = []
+    step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
+    gemm_flops = sum(f for f, _, _ in prof)
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": len(prof), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
+                "model_tflops": value / world * wl["gflop"] / 1e3, "model_frac": value / world * wl["gflop"] / 1e3 / peak_tf}
+
+    # ---------------------------------------------------------------- end-to-end from host buffers (`e2e`)
+    e2e = None
+    if not args.no_e2e:
+        n_host = 3
+        xs = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(n_host)]
+        ys = [torch.randint(0, 1000, (B,)).pin_memory() for _ in range(n_host)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                xd = xs[i % n_host].to(dev, non_blocking=True)
+                yd = ys[i % n_host].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return xd, yd, ev
+
+        def e2e_loop(n):
+            nxt = prefetch(0)
+            tot = 0.0
+            for i in range(n):
+                xd, yd, ev = nxt
+                main_stream.wait_event(ev)
+                xd.record_stream(main_stream)
+                yd.record_stream(main_stream)
+                if i + 1 < n:
+                    nxt = prefetch(i + 1)  # overlaps this step's compute, like a DataLoader worker + .to("cuda")
+                tot += step(xd, yd).item()  # D2H read of the loss every step (train.py:279)
+            return tot
+
+        e2e_loop(2)
+        barrier()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        ms2 = vd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        e2e = {"value": world * B / (ms2 * 1e-3), "unit": "images/s", "ms_per_step": ms2,
+               "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8, "d2h_bytes_per_step": 4}
+
+    # ---------------------------------------------------------------- CPU baseline (oracle port, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = 8
+        cstep = cpu_reference_step(args.workload, cb, threads)
+        cstep()
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            cstep()
+        dt = (time.perf_counter() - t0) / n
+        cpu = {"value": cb / dt, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{args.workload} fp32 fwd+bwd, batch {cb}, mean of {n} steps after 1 warm-up (oracle/restate.py)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "desc": wl["desc"], "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": f"dp{world}", "reducer": args.reducer if world > 1 else "none",
+                           "l2": "inputs_exceed_l2 (154 MB batch + multi-GB activations per step >> 126 MB L2)",
+                           "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,63 @@
+"""world_size-2 gloo test of the data-parallel plumbing (runs on CPU)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from vtb200 import dist as vd
+
+    r, lr, w = vd.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    red = vd.FlatGradReducer(model.parameters(), bucket_mb=1)
+    x = torch.full((2, 8), float(rank + 1))
+    model(x).sum().backward()
+    local = [p.grad.clone() for p in model.parameters()]
+    red.reduce()
+    gathered = [torch.zeros_like(torch.cat([g.flatten() for g in local])) for _ in range(world)]
+    dist.all_gather(gathered, torch.cat([g.flatten() for g in local]))
+    want = sum(gathered) / world
+    got = torch.cat([p.grad.flatten() for p in model.parameters()])
+    ok = torch.allclose(got, want, atol=1e-6)
+    mx = vd.max_over_ranks(rank + 10, "cpu")
+    sm = vd.sum_over_ranks(rank + 1, "cpu")
+    q.put((rank, bool(ok), mx, sm, vd.per_rank_batch(256, world)))
+    dist.destroy_process_group()
+
+
+def test_flat_reducer_and_rank_helpers_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == [(0, True, 11.0, 3.0, 128), (1, True, 11.0, 3.0, 128)]
+
+
+def test_bucketing_covers_every_parameter_once():
+    from vtb200 import dist as vd
+
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (10, 300000, 5, 700000, 1)]
+    red = vd.FlatGradReducer(ps, bucket_mb=1)
+    flat = [id(p) for b in red.buckets for p in b]
+    assert flat == [id(p) for p in ps] and len(red.buckets) >= 3

@@ -1,0 +1,373 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against the oracle (oracle/restate.py) or a plain
+fp32 torch restatement of the same op on identical seeded inputs.  Tolerances (stated per test) are for bf16
+operands with fp32 accumulation: outputs stored as bf16 carry 2^-9 relative rounding."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vtb200 import ops as o
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return o
+
+
+def bf(t):
+    return t.to(BF16)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [(128, 64, 64), (256, 256, 128), (300, 200, 72), (128, 96, 48), (1000, 768, 768), (197 * 4, 2304, 768),
+               (64, 1000, 768), (513, 328, 1096)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("layout", ["nt", "nn", "tt", "tn"])
+def test_gemm_layouts(ops, M, N, K, layout):
+    """C = A B^T for all four operand-major combinations (forward / dgrad / wgrad read layouts)."""
+    if layout != "nt" and (M % 8 or N % 8):
+        pytest.skip("MN-major operands need M, N multiples of 8 (16-byte TMA strides)")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g))
+    want = A.float() @ B.float().t()
+    a_mn, b_mn = layout[0] == "t", layout[1] == "n"
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=F32)
+    torch.cuda.synchronize()
+    assert rel(got, want) < 1e-5, (layout, rel(got, want))
+    got16 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=BF16)
+    assert rel(got16.float(), want) < 4e-3
+
+
+def test_gemm_strided_views(ops):
+    """Operands that are column slices of wider buffers (q/k/v inside the fused qkv buffer)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    big = bf(torch.randn(400, 3 * 128, device="cuda", generator=g))
+    W = bf(torch.randn(96, 128, device="cuda", generator=g))
+    for s in range(3):
+        a = big[:, s * 128:(s + 1) * 128]
+        got = ops.gemm(a, W, out_dtype=F32)
+        assert rel(got, a.float() @ W.float().t()) < 1e-5
+
+
+def test_gemm_epilogue_bias_silu_dual(ops):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 392, 512, 192
+    A, W = bf(torch.randn(M, K, device="cuda", generator=g)), bf(torch.randn(N, K, device="cuda", generator=g) * 0.1)
+    bias = torch.randn(N, device="cuda", generator=g)
+    u = torch.empty(M, N, dtype=BF16, device="cuda")
+    h = torch.empty(M, N, dtype=BF16, device="cuda")
+    from vtb200 import lib
+
+    ops.gemm(A, W, out=u, out2=h, bias=bias, epilogue=lib.EPI_SILU_DUAL)
+    want_u = (A.float() @ W.float().t() + bias)
+    assert rel(u.float(), want_u) < 4e-3
+    want_h = torch.nn.functional.silu(u.float())  # silu of the bf16-rounded pre-activation (layer.py:193 under autocast)
+    assert rel(h.float(), want_h) < 4e-3
+
+
+def test_gemm_epilogue_silu_grad(ops):
+    from vtb200 import lib
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, N, K = 264, 384, 128
+    G, W = bf(torch.randn(M, K, device="cuda", generator=g)), bf(torch.randn(K, N, device="cuda", generator=g) * 0.1)
+    u = bf(torch.randn(M, N, device="cuda", generator=g) * 2)
+    got = ops.gemm(G, W, b_mn=True, epilogue=lib.EPI_SILU_GRAD, aux=u, out_dtype=F32)
+    uf = u.float()
+    s = torch.sigmoid(uf)
+    want = (G.float() @ W.float()) * (s * (1 + uf * (1 - s)))
+    assert rel(got, want) < 2e-4  # __expf in the derivative
+
+
+def test_gemm_epilogue_residual_droppath(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, n, N, K = 6, 50, 256, 320
+    M = B * n
+    A, W = bf(torch.randn(M, K, device="cuda", generator=g)), bf(torch.randn(N, K, device="cuda", generator=g) * 0.1)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    scale = torch.tensor([0., 1.25, 1.25, 0., 1.25, 1.25], device="cuda")
+    got = ops.gemm(A, W, out_dtype=F32, bias=bias, resid=resid, row_scale=scale, rows_per_scale=n)
+    want = resid + (A.float() @ W.float().t() + bias) * scale.repeat_interleave(n)[:, None]
+    assert rel(got, want) < 1e-5
+    assert torch.equal(got[:n], resid[:n])  # dropped sample: the branch contributes exactly zero
+
+
+def test_gemm_splitk_accumulate_and_group_rows(ops):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    T, N, K = 4096 + 72, 256, 192
+    Gd, X = bf(torch.randn(T, N, device="cuda", generator=g)), bf(torch.randn(T, K, device="cuda", generator=g))
+    want = Gd.float().t() @ X.float()
+    got = ops.gemm(Gd, X, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True)  # auto split-K
+    assert rel(got, want) < 1e-5
+    got2 = ops.gemm(Gd, X, a_mn=True, b_mn=True, out=got.clone(), accumulate=True, splits=3)
+    assert rel(got2, 2 * want) < 1e-5
+    # row remap + per-row-in-group add (patch embedding with a cls slot per image)
+    Bn, n, D, Kp = 3, 16, 64, 96
+    A, W = bf(torch.randn(Bn * n, Kp, device="cuda", generator=g)), bf(torch.randn(D, Kp, device="cuda", generator=g))
+    pos = torch.randn(n + 1, D, device="cuda", generator=g)
+    out = torch.full((Bn * (n + 1), D), 7.0, device="cuda")
+    ops.gemm(A, W, out=out, out_group=(n, n + 1, 1), rowmod_add=pos[1:])
+    o3 = out.view(Bn, n + 1, D)
+    assert torch.all(o3[:, 0] == 7.0)
+    want = (A.float() @ W.float().t()).view(Bn, n, D) + pos[1:]
+    assert rel(o3[:, 1:], want) < 1e-5
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    A = torch.zeros(16, 12, dtype=BF16, device="cuda")  # K=12 -> lda not a multiple of 8
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.gemm(A, A)
+    with pytest.raises(ValueError):
+        ops.gemm(A.float(), A)
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,cols", [(197 * 3, 768), (1000, 96), (77, 1536), (64, 32), (5, 384)])
+@pytest.mark.parametrize("eps", [1e-6, 1e-5])
+def test_layernorm_fwd_bwd(ops, rows, cols, eps):
+    from oracle import restate as R
+
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2 + 0.5).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(cols, device="cuda", generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(cols, device="cuda", generator=g)).requires_grad_(True)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), w.detach(), b.detach(), eps, out_dtype=F32)
+    want = R.layer_norm(x, w, b, eps)
+    assert rel(y, want) < 2e-6
+    y16, _, _ = ops.layernorm_fwd(x.detach(), w.detach(), b.detach(), eps)
+    assert rel(y16.float(), want) < 4e-3
+    dy = torch.randn(rows, cols, device="cuda", generator=g)
+    want.backward(dy)
+    dx_in = torch.randn(rows, cols, device="cuda", generator=g)
+    scale = torch.rand(rows, device="cuda", generator=g)
+    dx, dxb, dg, db = ops.layernorm_bwd(dy, x.detach(), w.detach(), mean, rstd, dx_in=dx_in, want_bf16=True,
+                                        row_scale=scale, rows_per_scale=1)
+    assert rel(dx, x.grad + dx_in) < 1e-5
+    assert rel(dxb.float(), (x.grad + dx_in) * scale[:, None]) < 4e-3
+    assert rel(dg, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4  # fp32 atomics: order-dependent
+    dx2, _, _, _ = ops.layernorm_bwd(dy.to(BF16), x.detach(), w.detach(), mean, rstd)
+    assert rel(dx2, x.grad) < 5e-3
+
+
+def test_layernorm_patchify_prologue(ops):
+    """PatchMerge: patchify(2) folded into the LN row addressing (swin:224-229)."""
+    from oracle import restate as R
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, W, C = 3, 8, 12, 32
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(4 * C, device="cuda", generator=g))
+    b = 0.1 * torch.randn(4 * C, device="cuda", generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), w, b, 1e-5, out_dtype=F32, patchify=(2, H, W))
+    want = R.layer_norm(R.patchify(x, 2), w, b, 1e-5)
+    assert rel(y, want.reshape(-1, 4 * C)) < 2e-6
+    dy = torch.randn_like(want)
+    want.backward(dy)
+    dx, _, _, _ = ops.layernorm_bwd(dy.reshape(-1, 4 * C).contiguous(), x.detach(), w, mean, rstd, patchify=(2, H, W))
+    assert rel(dx, x.grad) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _attn_reference(q, k, v, bias, mask, do):
+    """fp32 autograd reference on [G, H, N, dh] tensors."""
+    from oracle import restate as R
+
+    q, k, v = (t.float().requires_grad_(True) for t in (q, k, v))
+    bias = bias.float().requires_grad_(True) if bias is not None else None
+    o = R.softmax_attention(q, k, v, bias, mask)
+    o.backward(do.float())
+    return o.detach(), q.grad, k.grad, v.grad, (bias.grad if bias is not None else None)
+
+
+@pytest.mark.parametrize("B,H,dh,Nq,Nkv", [(2, 3, 64, 197, 197), (3, 2, 32, 37, 37), (2, 1, 64, 300, 49), (2, 5, 64, 50, 50),
+                                            (1, 2, 64, 64, 128)])
+def test_attention_global(ops, B, H, dh, Nq, Nkv):
+    from vtb200 import lib
+
+    g = torch.Generator(device="cuda").manual_seed(Nq * 13 + Nkv)
+    HD = H * dh
+    qbuf = bf(torch.randn(B * Nq, HD, device="cuda", generator=g))
+    kvbuf = bf(torch.randn(B * Nkv, 2 * HD, device="cuda", generator=g))
+    spec = ops.AttnSpec(lib.ATTN_GLOBAL, B, H, dh, Nq, Nkv)
+    o, lse = ops.attention_fwd(spec, qbuf, kvbuf[:, :HD], kvbuf[:, HD:])
+    q4 = qbuf.view(B, Nq, H, dh).permute(0, 2, 1, 3)
+    k4 = kvbuf[:, :HD].reshape(B, Nkv, H, dh).permute(0, 2, 1, 3)
+    v4 = kvbuf[:, HD:].reshape(B, Nkv, H, dh).permute(0, 2, 1, 3)
+    do = bf(torch.randn(B * Nq, HD, device="cuda", generator=g))
+    do4 = do.view(B, Nq, H, dh).permute(0, 2, 1, 3)
+    wo, wdq, wdk, wdv, _ = _attn_reference(q4, k4, v4, None, None, do4)
+    got_o = o.view(B, Nq, H, dh).permute(0, 2, 1, 3).float()
+    assert rel(got_o, wo) < 6e-3, rel(got_o, wo)
+    want_lse = torch.logsumexp((q4.float() @ k4.float().transpose(-1, -2)) / math.sqrt(dh), -1)
+    assert rel(lse, want_lse) < 1e-4
+    dq = torch.empty_like(qbuf)
+    dkv = torch.empty_like(kvbuf)
+    ops.attention_bwd(spec, qbuf, kvbuf[:, :HD], kvbuf[:, HD:], o, lse, do, dq, dkv[:, :HD], dkv[:, HD:])
+    assert rel(dq.view(B, Nq, H, dh).permute(0, 2, 1, 3).float(), wdq) < 1.5e-2
+    assert rel(dkv[:, :HD].reshape(B, Nkv, H, dh).permute(0, 2, 1, 3).float(), wdk) < 1.5e-2
+    assert rel(dkv[:, HD:].reshape(B, Nkv, H, dh).permute(0, 2, 1, 3).float(), wdv) < 1.5e-2
+
+
+def _window_case(ops, Hs, W, shift, H, dh, B, seed, use_bias=True):
+    """Window attention on a fused qkv buffer vs the oracle's gather-form restatement."""
+    from oracle import restate as R
+    from vtb200 import lib
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    HD = H * dh
+    T = B * Hs * Hs
+    qkv = bf(torch.randn(T, 3 * HD, device="cuda", generator=g))
+    pos, mask = R.swin_tables(Hs, Hs, W, shift)
+    table = (0.5 * torch.randn((2 * W - 1) ** 2, H, device="cuda", generator=g)) if use_bias else None
+    spec = ops.AttnSpec(lib.ATTN_WINDOW, B, H, dh, W * W, W * W, Hs=Hs, Ws=Hs, window=W, shift=(W // 2) if shift else 0,
+                        rel_bias=table, pos=pos.to(torch.int32).cuda() if use_bias else None,
+                        mask=mask.to(torch.uint8).cuda() if shift else None)
+    o, lse = ops.attention_fwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:])
+    # oracle: identity projections so that swin_window_attention returns the raw attention output
+    C3 = 3 * HD
+    x = qkv.float().view(B, Hs, Hs, C3).requires_grad_(True)
+    tab = (table.clone() if use_bias else torch.zeros((2 * W - 1) ** 2, H, device="cuda")).requires_grad_(True)
+    sd = {"a.weight.weight": torch.eye(C3, device="cuda"), "a.weight.bias": torch.zeros(C3, device="cuda"),
+          "a.linear.weight": torch.eye(HD, device="cuda"), "a.linear.bias": torch.zeros(HD, device="cuda"),
+          "a.rel_pos.weight": tab, "a.pos": pos.cuda()}
+    if shift:
+        sd["a.local_mask"] = mask.cuda()
+    want = R.swin_window_attention(x, sd, "a.", H, dh, W, shift)
+    assert rel(o.float().view(B, Hs, Hs, HD), want) < 6e-3
+    do = bf(torch.randn(T, HD, device="cuda", generator=g))
+    want.backward(do.float().view(B, Hs, Hs, HD))
+    dqkv = torch.empty_like(qkv)
+    drel = torch.zeros_like(table) if use_bias else None
+    ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, dqkv[:, :HD], dqkv[:, HD:2 * HD],
+                      dqkv[:, 2 * HD:], drel)
+    assert rel(dqkv.float().view(B, Hs, Hs, C3), x.grad) < 1.5e-2
+    if use_bias:
+        assert rel(drel, tab.grad) < 1e-2
+
+
+@pytest.mark.parametrize("Hs,shift", [(14, True), (14, False), (7, True), (28, True)])
+def test_attention_window_swin(ops, Hs, shift):
+    _window_case(ops, Hs, 7, shift, H=3, dh=32, B=2, seed=Hs + int(shift))
+
+
+def test_attention_window_plain_twins(ops):
+    _window_case(ops, 14, 7, False, H=2, dh=64, B=2, seed=77, use_bias=False)
+
+
+@pytest.mark.parametrize("Hs,W,hl", [(14, 7, 3), (7, 7, 3), (8, 2, 1)])
+def test_attention_halo(ops, Hs, W, hl):
+    from oracle import restate as R
+    from vtb200 import lib
+
+    g = torch.Generator(device="cuda").manual_seed(Hs * 31 + W)
+    B, H, dh = 2, 3, 32
+    HD, T, K = H * dh, B * Hs * Hs, W + 2 * hl
+    qkv = bf(torch.randn(T, 3 * HD, device="cuda", generator=g))
+    pos = R.halo_pos_table(W, hl)
+    table = 0.5 * torch.randn(int(pos.max()) + 1, H, device="cuda", generator=g)
+    spec = ops.AttnSpec(lib.ATTN_HALO, B, H, dh, W * W, K * K, Hs=Hs, Ws=Hs, window=W, halo=hl, rel_bias=table,
+                        pos=pos.to(torch.int32).cuda())
+    o, lse = ops.attention_fwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:])
+    C3 = 3 * HD
+    x = qkv.float().view(B, Hs, Hs, C3).requires_grad_(True)
+    tab = table.clone().requires_grad_(True)
+    sd = {"a.weight.weight": torch.eye(C3, device="cuda"), "a.linear.weight": torch.eye(HD, device="cuda"),
+          "a.linear.bias": torch.zeros(HD, device="cuda"), "a.rel_pos.weight": tab, "a.pos": pos.cuda()}
+    want = R.halo_attention(x, sd, "a.", H, dh, W, hl)
+    assert rel(o.float().view(B, Hs, Hs, HD), want) < 6e-3
+    do = bf(torch.randn(T, HD, device="cuda", generator=g))
+    want.backward(do.float().view(B, Hs, Hs, HD))
+    dq = torch.empty(T, HD, dtype=BF16, device="cuda")
+    dkv = torch.zeros(T, 2 * HD, dtype=F32, device="cuda")
+    drel = torch.zeros_like(table)
+    ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, dq, dkv[:, :HD], dkv[:, HD:], drel,
+                      dkv_f32=True)
+    xg = x.grad.view(T, C3)
+    assert rel(dq.float(), xg[:, :HD]) < 1.5e-2
+    assert rel(dkv, xg[:, HD:]) < 1.5e-2
+    assert rel(drel, tab.grad) < 1e-2
+
+
+def test_attention_fully_masked_rows_do_not_nan(ops):
+    """Edge case: key padding beyond nkv and a mask that removes most keys."""
+    from vtb200 import lib
+
+    B, H, dh, N = 1, 1, 32, 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = bf(torch.randn(B * 4, 3 * dh, device="cuda", generator=g))
+    mask = torch.ones(1, N, N, dtype=torch.uint8, device="cuda")
+    mask[0].fill_diagonal_(0)  # each token only sees itself -> output == v
+    pos = torch.zeros(N, N, dtype=torch.int32, device="cuda")
+    table = torch.zeros(9, H, device="cuda")
+    spec = ops.AttnSpec(lib.ATTN_WINDOW, B, H, dh, N, N, Hs=2, Ws=2, window=2, shift=0, rel_bias=table, pos=pos, mask=mask)
+    o, _ = ops.attention_fwd(spec, qkv[:, :dh], qkv[:, dh:2 * dh], qkv[:, 2 * dh:])
+    assert torch.isfinite(o.float()).all()
+    assert rel(o.float(), qkv[:, 2 * dh:].float()) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def test_cast_colsum_scalecast(ops):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(1003, 328, device="cuda", generator=g)
+    assert torch.equal(ops.cast_bf16(x), x.to(BF16))
+    s = torch.rand(17, device="cuda", generator=g)
+    got = ops.scale_cast_bf16(x[:1003 - 1003 % 59], s, 59)
+    want = (x[:1003 - 1003 % 59] * s.repeat_interleave(59)[:, None]).to(BF16)
+    assert torch.equal(got, want)
+    xb = x.to(BF16)
+    acc = torch.ones(328, device="cuda")
+    ops.colsum(xb, acc)
+    assert rel(acc, 1 + xb.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("nchw,c_major", [(True, True), (True, False), (False, False), (False, True)])
+def test_patch_gather_scatter(ops, nchw, c_major):
+    from einops import rearrange
+
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, C, H, W, p = 2, 6, 8, 12, 2
+    nhwc = torch.randn(B, H, W, C, device="cuda", generator=g)
+    src = nhwc.permute(0, 3, 1, 2).contiguous() if nchw else nhwc
+    got = ops.patch_gather(src, nchw=nchw, c_major=c_major, B=B, Cc=C, H=H, W=W, p=p)
+    pat = "b (h py) (w px) c -> (b h w) (c py px)" if c_major else "b (h py) (w px) c -> (b h w) (py px c)"
+    want = rearrange(nhwc, pat, py=p, px=p)
+    assert torch.equal(got, want.to(BF16))
+    back = ops.patch_scatter(want.contiguous(), c_major=c_major, B=B, Cc=C, H=H, W=W, p=p)
+    assert torch.equal(back, nhwc)  # scatter is the exact inverse permutation
+
+
+def test_pool_fill_rowsum_silu(ops):
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(5, 49, 96, device="cuda", generator=g)
+    assert rel(ops.mean_rows_fwd(x, 5, 49, 96), x.mean(1)) < 1e-6
+    dy = torch.randn(5, 96, device="cuda", generator=g)
+    assert rel(ops.mean_rows_bwd(dy, 5, 49, 96).view(5, 49, 96), (dy / 49)[:, None].expand(5, 49, 96)) < 1e-6
+    out = torch.zeros(49, 96, device="cuda")
+    ops.rowgroup_sum(x, 49 * 96, 5, 49, 96, out)
+    assert rel(out, x.sum(0)) < 1e-6
+    buf = torch.zeros(5, 49, 96, device="cuda")
+    a, b = torch.randn(96, device="cuda", generator=g), torch.randn(96, device="cuda", generator=g)
+    ops.fill_rows(buf, 49 * 96, 5, 96, a, b)
+    assert torch.equal(buf[:, 0], (a + b).expand(5, 96)) and torch.all(buf[:, 1:] == 0)
+    xs = torch.randn(1000, device="cuda", generator=g).requires_grad_(True)
+    ys = torch.nn.functional.silu(xs)
+    assert rel(ops.silu_fwd(xs.detach()), ys) < 1e-5
+    ys.backward(torch.ones_like(ys))
+    assert rel(ops.silu_bwd(xs.detach(), torch.ones_like(xs)), xs.grad) < 1e-4

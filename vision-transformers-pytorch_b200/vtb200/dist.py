@@ -1,0 +1,98 @@
+"""Data-parallel plumbing (reference: train.py:102-108 DDP wrap, factory.py:264 per-GPU batch = global // world).
+
+The path shards by images only: every rank holds a full replica and the single exchange step is the
+gradient all-reduce.  Two reducers are offered:
+  * stock torch DDP (bucketed, overlapped with backward) — what the reference uses;
+  * FlatGradReducer — grads packed into a few large flat fp32 buckets, one NCCL all-reduce each (NVLS over
+    NVSwitch makes the cost ~size/bandwidth, so few big messages beat many small ones), then unpacked.
+Works with gloo on CPU (tests/test_dist_cpu.py) and NCCL on the box.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init_from_env(backend=None):
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, local_rank, world
+
+
+def per_rank_batch(global_batch, world):
+    """factory.py:264."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} not divisible by world size {world}")
+    return global_batch // world
+
+
+def max_over_ranks(x, device):
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def sum_over_ranks(x, device):
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.item()
+
+
+class FlatGradReducer:
+    """Mean all-reduce of .grad over ranks through flat fp32 buckets of ~bucket_mb MiB."""
+
+    def __init__(self, params, bucket_mb=128):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []
+        cur, size, cap = [], 0, bucket_mb * (1 << 20) // 4
+        for p in self.params:
+            if cur and size + p.numel() > cap:
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += p.numel()
+        if cur:
+            self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+
+    def reduce(self):
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        world = dist.get_world_size()
+        works = []
+        for i, bucket in enumerate(self.buckets):
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            n = sum(g.numel() for g in grads)
+            if self._flat[i] is None or self._flat[i].numel() != n or self._flat[i].device != grads[0].device:
+                self._flat[i] = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            flat = self._flat[i]
+            torch.cat([g.reshape(-1) for g in grads], out=flat)
+            works.append((dist.all_reduce(flat, async_op=True), flat, bucket))
+        for work, flat, bucket in works:
+            work.wait()
+            off = 0
+            for p in bucket:
+                n = p.numel()
+                g = flat[off:off + n].view_as(p) / world
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += n

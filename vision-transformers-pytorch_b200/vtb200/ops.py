@@ -12,6 +12,8 @@ import torch
 from . import lib as _l
 
 LAUNCHES = 0
+# When set to a list, every gemm() appends (flops, start_event, end_event): bench.py's live roofline pass.
+PROFILE = None
 BF16 = torch.bfloat16
 F32 = torch.float32
 
@@ -98,7 +100,14 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
         _chk2d(rowmod_add, F32, "gemm(rowmod_add)")
         p.rowmod_add, p.ld_rowmod = rowmod_add.data_ptr(), rowmod_add.stride(0)
     p.alpha = alpha
-    _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
+        e1.record()
+        PROFILE.append((2.0 * M * N * K, e0, e1))
+    else:
+        _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
     _count()
     return out
 
