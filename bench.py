@@ -255,13 +255,28 @@ def main():
     step(x_dev, y_dev)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
-    gemm_flops = sum(f for f, _, _ in prof)
+    gemm = [(n, f, a.elapsed_time(b)) for n, f, a, b in prof if n.startswith("gemm_")]
+    gemm_ms = sum(t for _, _, t in gemm)
+    gemm_flops = sum(f for _, f, _ in gemm)
+    if rank == 0:
+        agg = {}
+        for n, f, a, b in prof:
+            t = a.elapsed_time(b)
+            d = agg.setdefault(n, [0, 0.0, 0.0])
+            d[0] += 1; d[1] += t; d[2] += f
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}.txt"), "w") as fh:
+            tot = sum(v[1] for v in agg.values())
+            fh.write(f"# per-op CUDA-event times of ONE instrumented step ({args.workload}); step (uninstrumented) {ms:.2f} ms, sum of ops {tot:.2f} ms\n")
+            for n, (c, t, f) in rows:
+                tf = f / (t * 1e-3) / 1e12 if f and t > 0 else 0.0
+                fh.write(f"{n:44s} n={c:4d} {t:9.3f} ms {100 * t / tot:5.1f}%  {tf:8.1f} TFLOP/s\n")
     peak_tf, peak_hbm, peak_src = peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                "launches_per_step": len(prof), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
+                "launches_per_step": len(gemm), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
                 "model_tflops": value / world * wl["gflop"] / 1e3, "model_frac": value / world * wl["gflop"] / 1e3 / peak_tf}
 
     # ---------------------------------------------------------------- end-to-end from host buffers (`e2e`)

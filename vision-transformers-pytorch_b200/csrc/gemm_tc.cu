@@ -42,6 +42,7 @@ struct EpiParams {
   const float* rowmod_add;
   int ld_rowmod;
   float alpha;
+  int vec;  // all epilogue pointers / leading dims allow 16-byte vector access
 };
 
 template <int BN>
@@ -65,7 +66,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_
     m_out = (long)g * e.og_stride + e.og_off + m_mod;
   }
   const float rs = e.row_scale ? __ldg(e.row_scale + m / e.rows_per_scale) : 1.f;
-  const bool full = (n0 + 32 <= e.N);
+  const bool full = e.vec && (n0 + 32 <= e.N);
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
@@ -419,17 +420,7 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   VTB_CHECK(p->epilogue != VTB_EPI_SILU_DUAL || (p->out2 && !p->out_f32), -1,
             "vtb_gemm_bf16: SILU_DUAL needs bf16 out and out2");
   VTB_CHECK(p->epilogue != VTB_EPI_SILU_GRAD || p->aux, -1, "vtb_gemm_bf16: SILU_GRAD needs aux");
-  // vector epilogue accesses: full 32-column chunks use 16-byte stores
-  const int oalign = p->out_f32 ? 4 : 8;
-  VTB_CHECK(p->ldo % oalign == 0 && ((uintptr_t)p->out & 15) == 0, -1,
-            "vtb_gemm_bf16: out must be 16-byte aligned with ldo %% %d == 0", oalign);
-  VTB_CHECK(!p->resid || (p->ldr % 4 == 0 && ((uintptr_t)p->resid & 15) == 0), -1,
-            "vtb_gemm_bf16: resid alignment");
-  VTB_CHECK(!p->aux || (p->ldaux % 8 == 0 && ((uintptr_t)p->aux & 15) == 0), -1,
-            "vtb_gemm_bf16: aux alignment");
-  VTB_CHECK(!p->rowmod_add || (p->ld_rowmod % 4 == 0 && ((uintptr_t)p->rowmod_add & 15) == 0 &&
-                               p->out_group_rows > 0),
-            -1, "vtb_gemm_bf16: rowmod_add alignment / needs out_group_rows");
+  VTB_CHECK(!p->rowmod_add || p->out_group_rows > 0, -1, "vtb_gemm_bf16: rowmod_add needs out_group_rows");
   VTB_CHECK(!p->row_scale || p->rows_per_scale > 0, -1, "vtb_gemm_bf16: rows_per_scale");
 
   EpiParams e;
@@ -445,6 +436,15 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   e.og_rows = p->out_group_rows; e.og_stride = p->out_group_stride; e.og_off = p->out_group_off;
   e.rowmod_add = p->rowmod_add; e.ld_rowmod = p->ld_rowmod;
   e.alpha = p->alpha;
+  {  // 16-byte vector epilogue only when every touched row start is 16-byte aligned; scalar path otherwise
+    const int oalign = p->out_f32 ? 4 : 8;
+    bool v = (p->ldo % oalign == 0) && (((uintptr_t)p->out & 15) == 0);
+    if (p->out2) v = v && (((uintptr_t)p->out2 & 15) == 0);
+    if (p->resid) v = v && (p->ldr % 4 == 0) && (((uintptr_t)p->resid & 15) == 0);
+    if (p->aux) v = v && (p->ldaux % 8 == 0) && (((uintptr_t)p->aux & 15) == 0);
+    if (p->rowmod_add) v = v && (p->ld_rowmod % 4 == 0) && (((uintptr_t)p->rowmod_add & 15) == 0);
+    e.vec = v ? 1 : 0;
+  }
 
   // Tile-N choice: widest tile that does not waste more than ~25% of the MMA columns.
   int bn = 256;

@@ -129,13 +129,7 @@ class AttnBranchFn(Function):
             dkv = torch.zeros((qkv.shape[0], 2 * HD), dtype=F32, device=qkv.device)
             ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do,
                               dqkv[:, :HD], dkv[:, :HD], dkv[:, HD:], drel, dkv_f32=True)
-            lib = _l.get()
-            import ctypes as C_
-            _l.check(lib.vtb_cast_f32_bf16_2d(C_.c_void_p(dkv.data_ptr()), dkv.stride(0),
-                                              C_.c_void_p(dqkv[:, HD:].data_ptr()), dqkv.stride(0),
-                                              dkv.shape[0], 2 * HD,
-                                              C_.c_void_p(torch.cuda.current_stream().cuda_stream)), lib)
-            ops._count()
+            ops.cast_bf16_2d(dkv, dqkv[:, HD:])
         else:
             ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do,
                               dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:], drel)
@@ -258,9 +252,20 @@ class LinearFn(Function):
     @_bwd
     def backward(ctx, dy):
         xb, wb, has_b = ctx.stash
-        g = ops.scale_cast_bf16(_c(dy).view(-1, wb.shape[0]))
+        N = wb.shape[0]
+        d2 = _c(dy).view(-1, N)
+        if N % 8 == 0:
+            g = ops.scale_cast_bf16(d2)
+            gw = g
+        else:
+            # odd head widths (tests use n_class=10): MN-major TMA operands need 16-byte row strides,
+            # so the bf16 gradient lives in a zero-padded buffer and dW is sliced back
+            Np = (N + 7) // 8 * 8
+            gw = torch.zeros((d2.shape[0], Np), dtype=BF16, device=dy.device)
+            ops.cast_bf16_2d(d2, gw[:, :N])
+            g = gw[:, :N]
         db = ops.colsum(g) if has_b else None
-        dw = _wgrad(g, xb)
+        dw = _wgrad(gw, xb)[:N]
         dx = _dgrad(g, wb, out_dtype=F32)
         return dx.view(*dy.shape[:-1], wb.shape[1]), dw, db
 
@@ -326,13 +331,8 @@ class ViTPatchEmbedFn(Function):
         d2 = _c(dx).view(B, n + 1, D)
         # patch rows as a strided view [B*n, D] is not expressible in 2-D: cast per image block
         g = torch.empty((B * n, D), dtype=BF16, device=dx.device)
-        lib = _l.get()
-        import ctypes as C_
-        # rows of image b are contiguous: treat [B, (n+1)*D] -> skip first D of each group via 2-D cast
-        _l.check(lib.vtb_cast_f32_bf16_2d(C_.c_void_p(d2.data_ptr() + 4 * D), (n + 1) * D,
-                                          C_.c_void_p(g.data_ptr()), n * D, B, n * D,
-                                          C_.c_void_p(torch.cuda.current_stream().cuda_stream)), lib)
-        ops._count()
+        # rows of image b are contiguous: view [B, (n+1)*D], skip the cls slot (first D) of each image
+        ops.cast_bf16_2d(d2.view(B, (n + 1) * D)[:, D:], g.view(B, n * D))
         db = ops.colsum(g)
         dw = _wgrad(g, A).view(wshape)
         dpos = torch.zeros((n + 1, D), dtype=F32, device=dx.device)
@@ -414,7 +414,10 @@ class PVTPatchEmbedFn(Function):
         B, Cin, H, W = x.shape
         D = w.shape[0]
         n = (H // p) * (W // p)
-        A = ops.patch_gather(_c(x), nchw=True, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
+        if x.permute(0, 2, 3, 1).is_contiguous():  # NCHW *view* of NHWC tokens (pvt.py:261): read in place
+            A = ops.patch_gather(x.permute(0, 2, 3, 1), nchw=False, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
+        else:
+            A = ops.patch_gather(_c(x), nchw=True, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
         wb = ops.cast_bf16(_c(w).view(D, -1))
         lin = ops.gemm(A, wb, out_dtype=F32, bias=b)
         has_cls = cls_token is not None

@@ -12,8 +12,42 @@ import torch
 from . import lib as _l
 
 LAUNCHES = 0
-# When set to a list, every gemm() appends (flops, start_event, end_event): bench.py's live roofline pass.
+# When set to a list, every op appends (name, flops, start_event, end_event): bench.py's live roofline pass
+# and per-kernel time breakdown (CUDA events on the launching stream).
 PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("name", "flops", "e0")
+
+    def __init__(self, name, flops=0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def __exit__(self, *exc):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((self.name, self.flops, self.e0, e1))
+        return False
+
+
+class _NoProf:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOPROF = _NoProf()
+
+
+def _prof(name, flops=0.0):
+    return _NOPROF if PROFILE is None else _Prof(name, flops)
+
 BF16 = torch.bfloat16
 F32 = torch.float32
 
@@ -100,13 +134,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
         _chk2d(rowmod_add, F32, "gemm(rowmod_add)")
         p.rowmod_add, p.ld_rowmod = rowmod_add.data_ptr(), rowmod_add.stride(0)
     p.alpha = alpha
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
-        e1.record()
-        PROFILE.append((2.0 * M * N * K, e0, e1))
-    else:
+    kind = ("wgrad" if a_mn else ("dgrad" if b_mn else "fwd"))
+    with _prof(f"gemm_{kind}[{M}x{N}x{K}]", 2.0 * M * N * K):
         _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
     _count()
     return out
@@ -129,9 +158,10 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, patchify=None, rowmod_
     y = torch.empty((rows, cols), dtype=out_dtype, device=x.device)
     mean = torch.empty(rows, dtype=F32, device=x.device)
     rstd = torch.empty(rows, dtype=F32, device=x.device)
-    _l.check(lib.vtb_layernorm_fwd(_p(x), _p(gamma), _p(beta), float(eps), rows, cols, s, H, W, _p(y),
-                                   int(out_dtype == F32), _p(mean), _p(rstd), _p(rowmod_add),
-                                   group_rows, _stream()), lib)
+    with _prof("layernorm_fwd"):
+        _l.check(lib.vtb_layernorm_fwd(_p(x), _p(gamma), _p(beta), float(eps), rows, cols, s, H, W, _p(y),
+                                       int(out_dtype == F32), _p(mean), _p(rstd), _p(rowmod_add),
+                                       group_rows, _stream()), lib)
     _count()
     return y, mean, rstd
 
@@ -152,9 +182,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_in=None, dx_out=None, patchify
         dgamma = torch.zeros(cols, dtype=F32, device=x.device)
     if dbeta is None:
         dbeta = torch.zeros(cols, dtype=F32, device=x.device)
-    _l.check(lib.vtb_layernorm_bwd(_p(dy), int(dy.dtype == F32), _p(x), _p(gamma), _p(mean), _p(rstd),
-                                   rows, cols, s, H, W, _p(dx_in), _p(dx_out), _p(dxb), _p(row_scale),
-                                   rows_per_scale, _p(dgamma), _p(dbeta), _stream()), lib)
+    with _prof("layernorm_bwd"):
+        _l.check(lib.vtb_layernorm_bwd(_p(dy), int(dy.dtype == F32), _p(x), _p(gamma), _p(mean), _p(rstd),
+                                       rows, cols, s, H, W, _p(dx_in), _p(dx_out), _p(dxb), _p(row_scale),
+                                       rows_per_scale, _p(dgamma), _p(dbeta), _stream()), lib)
     _count()
     return dx_out, dxb, dgamma, dbeta
 
@@ -210,7 +241,8 @@ def attention_fwd(spec, q, k, v):
     o = torch.empty((q.shape[0], spec.heads * spec.dh), dtype=BF16, device=q.device)
     lse = torch.empty((spec.groups, spec.heads, spec.nq), dtype=F32, device=q.device)
     p.o, p.ldo, p.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
-    _l.check(lib.vtb_attention_fwd(C.byref(p), _stream()), lib)
+    with _prof("attention_fwd"):
+        _l.check(lib.vtb_attention_fwd(C.byref(p), _stream()), lib)
     _count()
     return o, lse
 
@@ -233,7 +265,8 @@ def attention_bwd(spec, q, k, v, o, lse, dout, dq, dk, dv, drel_bias=None, dkv_f
     p.delta = delta.data_ptr()
     if drel_bias is not None:
         p.drel_bias = drel_bias.data_ptr()
-    _l.check(lib.vtb_attention_bwd(C.byref(p), _stream()), lib)
+    with _prof("attention_bwd"):
+        _l.check(lib.vtb_attention_bwd(C.byref(p), _stream()), lib)
     _count(2)
 
 
@@ -243,8 +276,23 @@ def cast_bf16(src):
         raise ValueError("vtb200.cast_bf16: contiguous f32 expected")
     dst = torch.empty(src.shape, dtype=BF16, device=src.device)
     if src.numel():
-        _l.check(lib.vtb_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), lib)
+        with _prof("cast_f32_bf16"):
+            _l.check(lib.vtb_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), lib)
         _count()
+    return dst
+
+
+def cast_bf16_2d(src, dst):
+    """dst[r, c] = bf16(src[r, c]) for 2-D row-strided views (src f32, dst bf16, same shape)."""
+    lib = _l.get()
+    _chk2d(src, F32, "cast_bf16_2d(src)")
+    _chk2d(dst, BF16, "cast_bf16_2d(dst)")
+    if src.shape != dst.shape:
+        raise ValueError("vtb200.cast_bf16_2d: shape mismatch")
+    with _prof("cast_f32_bf16_2d"):
+        _l.check(lib.vtb_cast_f32_bf16_2d(_p(src), src.stride(0), _p(dst), dst.stride(0), src.shape[0],
+                                          src.shape[1], _stream()), lib)
+    _count()
     return dst
 
 
@@ -256,8 +304,9 @@ def scale_cast_bf16(src, row_scale=None, rows_per_scale=0):
     cols = src.shape[-1]
     rows = src.numel() // cols
     dst = torch.empty((rows, cols), dtype=BF16, device=src.device)
-    _l.check(lib.vtb_scale_cast_bf16(_p(src), _p(row_scale), rows_per_scale, rows, cols, _p(dst),
-                                     _stream()), lib)
+    with _prof("scale_cast_bf16"):
+        _l.check(lib.vtb_scale_cast_bf16(_p(src), _p(row_scale), rows_per_scale, rows, cols, _p(dst),
+                                         _stream()), lib)
     _count()
     return dst
 
@@ -268,7 +317,8 @@ def colsum(x, out=None):
     M, N = x.shape
     if out is None:
         out = torch.zeros(N, dtype=F32, device=x.device)
-    _l.check(lib.vtb_colsum_bf16(_p(x), M, N, x.stride(0), _p(out), _stream()), lib)
+    with _prof("colsum_bf16"):
+        _l.check(lib.vtb_colsum_bf16(_p(x), M, N, x.stride(0), _p(out), _stream()), lib)
     _count()
     return out
 
@@ -279,8 +329,9 @@ def patch_gather(src, *, nchw, c_major, B, Cc, H, W, p):
         raise ValueError("vtb200.patch_gather: contiguous f32/bf16 expected")
     rows = B * (H // p) * (W // p)
     dst = torch.empty((rows, p * p * Cc), dtype=BF16, device=src.device)
-    _l.check(lib.vtb_patch_gather(_p(src), int(src.dtype == BF16), int(nchw), int(c_major), B, Cc, H, W,
-                                  p, _p(dst), _stream()), lib)
+    with _prof("patch_gather"):
+        _l.check(lib.vtb_patch_gather(_p(src), int(src.dtype == BF16), int(nchw), int(c_major), B, Cc, H, W,
+                                      p, _p(dst), _stream()), lib)
     _count()
     return dst
 
@@ -291,28 +342,32 @@ def patch_scatter(dA, *, c_major, B, Cc, H, W, p, dx=None, accumulate=False):
         raise ValueError("vtb200.patch_scatter: contiguous f32/bf16 expected")
     if dx is None:
         dx = torch.empty((B, H, W, Cc), dtype=F32, device=dA.device)
-    _l.check(lib.vtb_patch_scatter(_p(dA), int(dA.dtype == F32), int(c_major), B, Cc, H, W, p, _p(dx),
-                                   int(accumulate), _stream()), lib)
+    with _prof("patch_scatter"):
+        _l.check(lib.vtb_patch_scatter(_p(dA), int(dA.dtype == F32), int(c_major), B, Cc, H, W, p, _p(dx),
+                                       int(accumulate), _stream()), lib)
     _count()
     return dx
 
 
 def fill_rows(x, group_stride, groups, cols, a, b=None):
     lib = _l.get()
-    _l.check(lib.vtb_fill_rows(_p(x), group_stride, groups, cols, _p(a), _p(b), _stream()), lib)
+    with _prof("fill_rows"):
+        _l.check(lib.vtb_fill_rows(_p(x), group_stride, groups, cols, _p(a), _p(b), _stream()), lib)
     _count()
 
 
 def rowgroup_sum(x, group_stride, groups, rows, cols, out):
     lib = _l.get()
-    _l.check(lib.vtb_rowgroup_sum(_p(x), group_stride, groups, rows, cols, _p(out), _stream()), lib)
+    with _prof("rowgroup_sum"):
+        _l.check(lib.vtb_rowgroup_sum(_p(x), group_stride, groups, rows, cols, _p(out), _stream()), lib)
     _count()
 
 
 def mean_rows_fwd(x, groups, n, cols):
     lib = _l.get()
     out = torch.empty((groups, cols), dtype=F32, device=x.device)
-    _l.check(lib.vtb_mean_rows_fwd(_p(x), groups, n, cols, _p(out), _stream()), lib)
+    with _prof("mean_rows_fwd"):
+        _l.check(lib.vtb_mean_rows_fwd(_p(x), groups, n, cols, _p(out), _stream()), lib)
     _count()
     return out
 
@@ -320,7 +375,8 @@ def mean_rows_fwd(x, groups, n, cols):
 def mean_rows_bwd(dy, groups, n, cols):
     lib = _l.get()
     dx = torch.empty((groups * n, cols), dtype=F32, device=dy.device)
-    _l.check(lib.vtb_mean_rows_bwd(_p(dy), groups, n, cols, _p(dx), _stream()), lib)
+    with _prof("mean_rows_bwd"):
+        _l.check(lib.vtb_mean_rows_bwd(_p(dy), groups, n, cols, _p(dx), _stream()), lib)
     _count()
     return dx
 
@@ -328,7 +384,8 @@ def mean_rows_bwd(dy, groups, n, cols):
 def silu_fwd(x):
     lib = _l.get()
     y = torch.empty_like(x)
-    _l.check(lib.vtb_silu_fwd(_p(x), _p(y), x.numel(), _stream()), lib)
+    with _prof("silu_fwd"):
+        _l.check(lib.vtb_silu_fwd(_p(x), _p(y), x.numel(), _stream()), lib)
     _count()
     return y
 
@@ -336,6 +393,7 @@ def silu_fwd(x):
 def silu_bwd(x, dy):
     lib = _l.get()
     dx = torch.empty_like(x)
-    _l.check(lib.vtb_silu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _stream()), lib)
+    with _prof("silu_bwd"):
+        _l.check(lib.vtb_silu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _stream()), lib)
     _count()
     return dx
