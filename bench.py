@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nvtx-step", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -234,6 +236,13 @@ def main():
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
+    if args.nvtx_step:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()  # process-wide (backward runs on the autograd thread)
+        step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -266,7 +275,7 @@ def main():
             d[0] += 1; d[1] += t; d[2] += f
         rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}.txt"), "w") as fh:
+        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{args.workload}_n{world}.txt"), "w") as fh:
             tot = sum(v[1] for v in agg.values())
             fh.write(f"# per-op CUDA-event times of ONE instrumented step ({args.workload}); step (uninstrumented) {ms:.2f} ms, sum of ops {tot:.2f} ms\n")
             for n, (c, t, f) in rows:

@@ -42,11 +42,11 @@ int vtb_init(void);
  *   VTB_EPI_SILU_DUAL : out  = bf16(v) ; v = silu(float(bf16(v))) ; stored to out2   (layer.py:193)
  *   VTB_EPI_SILU_GRAD : v *= silu'(aux[m,n])                                       (backward of it)
  *   v *= row_scale[m / rows_per_scale]             (DropPath keep-mask/keep-prob, layer.py:176-178)
- *   v += rowmod_add[(m % out_group_rows) * ld_rowmod + n]   (positional embedding, vit.py:143)
- *   v += resid[m_out*ldr + n]                      (residual add, vit.py:60-61 etc.)
- *   out[m_out*ldo + n] = v (bf16 or f32); with accumulate=1: atomicAdd (f32 only; split-K / grad accumulation)
- *   m_out = m                               if out_group_rows == 0
- *         = (m / out_group_rows) * out_group_stride + out_group_off + m % out_group_rows   otherwise
+ *   v += resid[m*ldr + n]                          (residual add, vit.py:60-61 etc.; EPI_NONE, f32 out only)
+ *   out[m*ldo + n] = v (bf16 or f32); with accumulate=1: += (f32 only; split-K / grad accumulation,
+ *                     TMA reduce-add when rows are 16-byte aligned, atomicAdd otherwise)
+ * When out/out2/resid/aux rows are 16-byte aligned the epilogue is staged through shared memory and written
+ * with TMA bulk tensor stores (residual / aux tiles TMA-prefetched); otherwise a direct per-thread path runs.
  * ---------------------------------------------------------------------------------------------- */
 enum { VTB_EPI_NONE = 0, VTB_EPI_SILU_DUAL = 1, VTB_EPI_SILU_GRAD = 2 };
 
@@ -63,8 +63,6 @@ typedef struct {
   int32_t epilogue;
   int32_t splits;                     /* split-K factor; 0 = auto; >1 requires accumulate=1 */
   int32_t accumulate;
-  int32_t out_group_rows, out_group_stride, out_group_off;
-  const float* rowmod_add; int32_t ld_rowmod;
   float alpha;
 } vtb_gemm_params;
 
@@ -169,8 +167,11 @@ int vtb_patch_gather(const void* src, int32_t src_bf16, int32_t src_nchw, int32_
 int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major, int32_t B, int32_t C,
                       int32_t H, int32_t W, int32_t p, float* dx, int32_t accumulate,
                       vtb_stream_t stream);
-/* dst[g*stride + off + r, :] = src[r % src_rows, :] (+ add[...]) helpers for cls tokens:
- * x[b, 0, :] = cls[:] + pos0[:]   (vit.py:141-143, pvt.py:136-140) */
+/* ViT token assembly (vit.py:141-143): x[b, 0, :] = cls + pos[0];  x[b, 1+p, :] = tok[b*n + p, :] + pos[1+p, :]
+ * tok f32 [B*n, D] (patch GEMM output incl. conv bias), pos f32 [n+1, D], x f32 [B, n+1, D]. */
+int vtb_vit_assemble_tokens(const float* tok, const float* cls, const float* pos, int32_t B, int32_t n,
+                            int32_t D, float* x, vtb_stream_t stream);
+/* x[g*row_stride_groups + c] = a[c] + b[c] for g < groups  (cls rows: pvt.py:136-140) */
 int vtb_fill_rows(float* x, int64_t row_stride_groups, int32_t groups, int32_t cols,
                   const float* a, const float* b, vtb_stream_t stream);
 /* out[c] += sum_g x[g*group_stride, c]  (cls_token / pos gradients), f32 */

@@ -88,11 +88,11 @@ def test_gemm_epilogue_silu_grad(ops):
     M, N, K = 264, 384, 128
     G, W = bf(torch.randn(M, K, device="cuda", generator=g)), bf(torch.randn(K, N, device="cuda", generator=g) * 0.1)
     u = bf(torch.randn(M, N, device="cuda", generator=g) * 2)
-    got = ops.gemm(G, W, b_mn=True, epilogue=lib.EPI_SILU_GRAD, aux=u, out_dtype=F32)
+    got = ops.gemm(G, W, b_mn=True, epilogue=lib.EPI_SILU_GRAD, aux=u)
     uf = u.float()
     s = torch.sigmoid(uf)
     want = (G.float() @ W.float()) * (s * (1 + uf * (1 - s)))
-    assert rel(got, want) < 2e-4  # __expf in the derivative
+    assert got.dtype == BF16 and rel(got.float(), want) < 4e-3  # bf16 store
 
 
 def test_gemm_epilogue_residual_droppath(ops):
@@ -118,16 +118,25 @@ def test_gemm_splitk_accumulate_and_group_rows(ops):
     assert rel(got, want) < 1e-5
     got2 = ops.gemm(Gd, X, a_mn=True, b_mn=True, out=got.clone(), accumulate=True, splits=3)
     assert rel(got2, 2 * want) < 1e-5
-    # row remap + per-row-in-group add (patch embedding with a cls slot per image)
-    Bn, n, D, Kp = 3, 16, 64, 96
-    A, W = bf(torch.randn(Bn * n, Kp, device="cuda", generator=g)), bf(torch.randn(D, Kp, device="cuda", generator=g))
-    pos = torch.randn(n + 1, D, device="cuda", generator=g)
-    out = torch.full((Bn * (n + 1), D), 7.0, device="cuda")
-    ops.gemm(A, W, out=out, out_group=(n, n + 1, 1), rowmod_add=pos[1:])
-    o3 = out.view(Bn, n + 1, D)
-    assert torch.all(o3[:, 0] == 7.0)
-    want = (A.float() @ W.float().t()).view(Bn, n, D) + pos[1:]
-    assert rel(o3[:, 1:], want) < 1e-5
+
+
+def test_gemm_unaligned_output_falls_back_to_direct_path(ops):
+    """N=10 / N=50 heads: rows are not 16-byte multiples -> per-thread epilogue instead of TMA stores."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for N in (10, 50, 1000):
+        A, W = bf(torch.randn(77, 64, device="cuda", generator=g)), bf(torch.randn(N, 64, device="cuda", generator=g))
+        bias = torch.randn(N, device="cuda", generator=g)
+        got = ops.gemm(A, W, out_dtype=F32, bias=bias)
+        assert rel(got, A.float() @ W.float().t() + bias) < 1e-5
+
+
+def test_vit_assemble_tokens(ops):
+    g = torch.Generator(device="cuda").manual_seed(14)
+    B, n, D = 3, 16, 64
+    tok, cls, pos = (torch.randn(s, device="cuda", generator=g) for s in ((B * n, D), (D,), (n + 1, D)))
+    x = ops.vit_assemble_tokens(tok, cls, pos, B, n, D)
+    want = torch.cat((cls.expand(B, 1, D), tok.view(B, n, D)), 1) + pos
+    assert torch.equal(x, want)
 
 
 def test_gemm_rejects_bad_arguments(ops):

@@ -154,6 +154,22 @@ __global__ void patch_scatter_kernel(const T* __restrict__ dA, int c_major, Patc
   }
 }
 
+__global__ void vit_assemble_kernel(const float* __restrict__ tok, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, int B, int n, int D, float* __restrict__ x) {
+  const int D4 = D >> 2;
+  const long total = (long)B * (n + 1) * D4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % D4);
+    const long r = i / D4;
+    const int t = (int)(r % (n + 1));
+    const long b = r / (n + 1);
+    const float4 p = reinterpret_cast<const float4*>(pos)[(long)t * D4 + c];
+    const float4 s = (t == 0) ? reinterpret_cast<const float4*>(cls)[c]
+                              : reinterpret_cast<const float4*>(tok)[(b * n + (t - 1)) * D4 + c];
+    reinterpret_cast<float4*>(x)[i] = make_float4(s.x + p.x, s.y + p.y, s.z + p.z, s.w + p.w);
+  }
+}
+
 __global__ void fill_rows_kernel(float* __restrict__ x, long stride, int groups, int cols,
                                  const float* __restrict__ a, const float* __restrict__ b) {
   const long total = (long)groups * cols;
@@ -289,6 +305,15 @@ extern "C" int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major
     patch_scatter_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const float*)dA, c_major, g, dx, accumulate);
   else
     patch_scatter_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dA, c_major, g, dx, accumulate);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_vit_assemble_tokens(const float* tok, const float* cls, const float* pos, int32_t B,
+                                       int32_t n, int32_t D, float* x, vtb_stream_t s) {
+  VTB_CHECK(tok && cls && pos && x && B > 0 && n > 0 && D > 0 && D % 4 == 0, -1,
+            "vtb_vit_assemble_tokens: bad args");
+  vit_assemble_kernel<<<grid_for((long)B * (n + 1) * (D / 4), 256, 2), 256, 0, (cudaStream_t)s>>>(tok, cls, pos, B, n, D, x);
   VTB_LAUNCH_CHECK();
   return 0;
 }

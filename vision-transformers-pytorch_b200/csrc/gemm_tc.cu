@@ -2,7 +2,10 @@
 //   warp 0      : TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      : UMMA issuer  (tcgen05.mma cta_group::1, M=128, N=BN, K=16; fp32 accumulators in TMEM)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue (tcgen05.ld -> registers -> fused epilogue -> global)
+//   warps 4..7  : epilogue: tcgen05.ld -> registers -> fused epilogue -> 128B-swizzled smem staging ->
+//                 TMA store (cp.async.bulk.tensor; cp.reduce.async.bulk .add for split-K); residual /
+//                 pre-activation tiles are TMA-prefetched into smem three sub-tiles ahead.
+//                 (Unaligned outputs fall back to direct per-thread global stores.)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 // Operands may be K-major or MN-major (wgrad / dgrad read the same buffers the forward wrote,
 // no transposes are materialised).  See include/vtb200.h for the contract.
@@ -15,6 +18,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int EPI_BUF_BYTES = BM * 128;     // one staged sub-tile: 128 rows x 128 B (64 bf16 or 32 f32 columns)
+constexpr int N_AUX = 3;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -38,33 +43,27 @@ struct EpiParams {
   int ldaux;
   int epilogue;
   int accumulate;
-  int og_rows, og_stride, og_off;
-  const float* rowmod_add;
-  int ld_rowmod;
   float alpha;
-  int vec;  // all epilogue pointers / leading dims allow 16-byte vector access
+  int vec;  // all epilogue pointers / leading dims allow 16-byte vector access (direct path)
+  int tma;  // 1: staged TMA-store epilogue (tensor maps valid)
 };
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 512 / 256 / 128
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: 2 output buffers + 3 aux buffers (second output, or prefetched residual / pre-activation)
+  static constexpr int STAGING_BYTES = (2 + 3) * EPI_BUF_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // One 32-column chunk of one accumulator row -> global memory with the fused epilogue.
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_t (&acc)[32],
                                                int m, int n0) {
   if (m >= e.M) return;
-  long m_out = m;
-  int m_mod = 0;
-  if (e.og_rows > 0) {
-    int g = m / e.og_rows;
-    m_mod = m - g * e.og_rows;
-    m_out = (long)g * e.og_stride + e.og_off + m_mod;
-  }
+  const long m_out = m;
   const float rs = e.row_scale ? __ldg(e.row_scale + m / e.rows_per_scale) : 1.f;
   const bool full = e.vec && (n0 + 32 <= e.N);
   float v[32];
@@ -123,18 +122,6 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= rs;
   }
-  if (e.rowmod_add) {
-    const float* pa = e.rowmod_add + (long)m_mod * e.ld_rowmod + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 t = *reinterpret_cast<const float4*>(pa + j);
-        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-      }
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < e.N) v[j] += pa[j];
-    }
-  }
   if (e.resid) {
     const float* pr = e.resid + m_out * e.ldr + n0;
     if (full) {
@@ -178,19 +165,24 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               int m_tiles, int n_tiles, int k_blocks, int splits, EpiParams epi) {
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
+               const __grid_constant__ CUtensorMap tma_aux, int m_tiles, int n_tiles, int k_blocks,
+               int splits, EpiParams epi) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* sOut = smem + C::STAGES * C::STAGE_BYTES;          // [2][EPI_BUF_BYTES]
+  uint8_t* sAux = sOut + 2 * EPI_BUF_BYTES;                   // [N_AUX][EPI_BUF_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* aux_full = bars + 2 * C::STAGES + 4;              // [N_AUX]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + N_AUX);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
+    for (int i = 0; i < N_AUX; ++i) mbar_init(&aux_full[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -299,27 +292,204 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mn = tile / splits;
-      const int n_blk = mn % n_tiles;
-      const int m_blk = mn / n_tiles;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const int m = m_blk * BM + ew * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
+    if (!epi.tma) {
+      // direct path (unaligned outputs): per-thread row stores
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mn = tile / splits;
+        const int n_blk = mn % n_tiles;
+        const int m_blk = mn / n_tiles;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const int m = m_blk * BM + ew * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= epi.N) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld_32x32(t_row + c * 32, acc);
-        tmem_ld_wait();
-        epilogue_chunk(epi, acc, m, n0);
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= epi.N) break;  // warp-uniform
+          uint32_t acc[32];
+          tmem_ld_32x32(t_row + c * 32, acc);
+          tmem_ld_wait();
+          epilogue_chunk(epi, acc, m, n0);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+    } else {
+      // staged path: sub-tiles of SUBN columns (one 128-byte row each) -> swizzled smem -> TMA store.
+      const bool f32out = epi.out_f32 != 0;
+      const int SUBN = f32out ? 32 : 64;
+      const int n_sub = BN / SUBN;
+      const bool dual = epi.epilogue == VTB_EPI_SILU_DUAL;
+      const bool aux_in = (epi.resid != nullptr) || (epi.epilogue == VTB_EPI_SILU_GRAD);
+      const bool issuer = (threadIdx.x == 128);
+      const int row = ew * 32 + lane;              // row inside the tile == TMEM lane
+      const uint32_t swz = (uint32_t)(row & 7);
+      const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const long total_q = (long)my_tiles * n_sub;
+      auto q_coords = [&](long q, int& m0, int& n0) {
+        const int tl = (int)(q / n_sub), sidx = (int)(q - (long)tl * n_sub);
+        const int tile = blockIdx.x + tl * gridDim.x;
+        const int mn = tile / splits;
+        m0 = (mn / n_tiles) * BM;
+        n0 = (mn % n_tiles) * BN + sidx * SUBN;
+      };
+      auto issue_aux = [&](long q) {
+        int m0, n0;
+        q_coords(q, m0, n0);
+        uint64_t* bar = &aux_full[q % N_AUX];
+        mbar_expect_tx(bar, EPI_BUF_BYTES);
+        tma_load_2d(sAux + (q % N_AUX) * EPI_BUF_BYTES, &tma_aux, bar, n0, m0);
+      };
+      if (aux_in && issuer)
+        for (long q = 0; q < N_AUX && q < total_q; ++q) issue_aux(q);
+      long q = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mn = tile / splits;
+        const int n_blk = mn % n_tiles;
+        const int m_blk = mn / n_tiles;
+        const int m = m_blk * BM + row;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
+        const float rs = (epi.row_scale && m < epi.M) ? __ldg(epi.row_scale + m / epi.rows_per_scale) : 1.f;
+#pragma unroll 1
+        for (int sidx = 0; sidx < n_sub; ++sidx, ++q) {
+          const int n0 = n_blk * BN + sidx * SUBN;
+          const bool live = n0 < epi.N;            // CTA-uniform
+          uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES;
+          uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES;
+          // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (live) {
+#pragma unroll 1
+            for (int hc = 0; hc < SUBN / 32; ++hc) {
+              uint32_t acc[32];
+              tmem_ld_32x32(t_row + sidx * SUBN + hc * 32, acc);
+              tmem_ld_wait();
+              if (sidx == n_sub - 1 && hc == SUBN / 32 - 1) {
+                // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+              }
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * epi.alpha;
+              const int nc = n0 + hc * 32;
+              if (epi.bias) {
+                if (nc + 32 <= epi.N) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.bias + nc + j));
+                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (nc + j < epi.N) v[j] += __ldg(epi.bias + nc + j);
+                }
+              }
+              if (aux_in && hc == 0) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
+              if (dual) {
+                // out <- bf16(u) ; out2 <- bf16(silu(float(bf16(u))))     (layer.py:191-193 under autocast)
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint32_t pu[4], ph[4];
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    pu[t] = pack_bf16(v[j + 2 * t], v[j + 2 * t + 1]);
+                    const float2 ur = unpack_bf16(pu[t]);
+                    ph[t] = pack_bf16(silu_f(ur.x), silu_f(ur.y));
+                  }
+                  const uint32_t chunk = (uint32_t)(hc * 4 + j / 8);
+                  const uint32_t off = row * 128 + ((chunk ^ swz) << 4);
+                  *reinterpret_cast<uint4*>(ob + off) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
+                  *reinterpret_cast<uint4*>(ab + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                }
+                continue;
+              }
+              if (epi.epilogue == VTB_EPI_SILU_GRAD) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint32_t chunk = (uint32_t)(hc * 4 + j / 8);
+                  const uint4 raw = *reinterpret_cast<const uint4*>(ab + row * 128 + ((chunk ^ swz) << 4));
+                  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 u = unpack_bf16(w[t]);
+                    v[j + 2 * t] *= silu_grad_f(u.x);
+                    v[j + 2 * t + 1] *= silu_grad_f(u.y);
+                  }
+                }
+              }
+              if (epi.row_scale) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= rs;
+              }
+              if (epi.resid) {  // f32 residual sub-tile (32 columns) prefetched by TMA
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const uint32_t chunk = (uint32_t)(j / 4);
+                  const float4 t = *reinterpret_cast<const float4*>(ab + row * 128 + ((chunk ^ swz) << 4));
+                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+              }
+              if (f32out) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const uint32_t chunk = (uint32_t)(j / 4);
+                  *reinterpret_cast<float4*>(ob + row * 128 + ((chunk ^ swz) << 4)) =
+                      make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint32_t chunk = (uint32_t)(hc * 4 + j / 8);
+                  *reinterpret_cast<uint4*>(ob + row * 128 + ((chunk ^ swz) << 4)) =
+                      make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                 pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+                }
+              }
+            }
+          } else {
+            if (sidx == n_sub - 1) {  // dead trailing sub-tile: still release the TMEM stage
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            }
+            if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            if (live) {
+              const int m0 = m_blk * BM;
+              if (epi.accumulate) {
+                asm volatile(
+                    "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
+                    "r"(smem_u32(ob)), "r"(n0), "r"(m0)
+                    : "memory");
+              } else {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
+                             "r"(smem_u32(ob)), "r"(n0), "r"(m0)
+                             : "memory");
+                if (dual)
+                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out2),
+                               "r"(smem_u32(ab)), "r"(n0), "r"(m0)
+                               : "memory");
+              }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // every thread is past its reads of aux buffer q % N_AUX: refill it for sub-tile q + N_AUX
+            if (aux_in && q + N_AUX < total_q) issue_aux(q + N_AUX);
+          }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
 
@@ -332,19 +502,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-              uint32_t box_inner, uint32_t box_outer) {
+              uint32_t box_inner, uint32_t box_outer, bool f32 = false) {
+  const uint64_t esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint64_t strides[1] = {ld_elems * esz};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = g_encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    vtb_set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
+    vtb_set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u f32=%d",
                   (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
-                  (unsigned long long)ld_elems, box_inner, box_outer);
+                  (unsigned long long)ld_elems, box_inner, box_outer, (int)f32);
     return -3;
   }
   return 0;
@@ -361,6 +532,24 @@ int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStrea
   if (!B_MN) rc = make_tmap(&tb, p->B, p->K, p->N, p->ldb, BK, BN);
   else       rc = make_tmap(&tb, p->B, p->N, p->K, p->ldb, 64, BK);
   if (rc) return rc;
+  CUtensorMap to = ta, to2 = ta, tx = ta;  // placeholders when the staged epilogue is off
+  if (epi.tma) {
+    const bool f32 = p->out_f32 != 0;
+    const uint32_t subn = f32 ? 32 : 64;
+    rc = make_tmap(&to, p->out, p->N, p->M, p->ldo, subn, BM, f32);
+    if (rc) return rc;
+    if (p->out2) {
+      rc = make_tmap(&to2, p->out2, p->N, p->M, p->ldo, 64, BM, false);
+      if (rc) return rc;
+    }
+    if (p->resid) {
+      rc = make_tmap(&tx, p->resid, p->N, p->M, p->ldr, 32, BM, true);
+      if (rc) return rc;
+    } else if (p->epilogue == VTB_EPI_SILU_GRAD) {
+      rc = make_tmap(&tx, p->aux, p->N, p->M, p->ldaux, 64, BM, false);
+      if (rc) return rc;
+    }
+  }
   const int m_tiles = (p->M + BM - 1) / BM;
   const int n_tiles = (p->N + BN - 1) / BN;
   const int k_blocks = (p->K + BK - 1) / BK;
@@ -372,7 +561,7 @@ int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStrea
   }
   const int total = m_tiles * n_tiles * splits;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, m_tiles, n_tiles, k_blocks, splits, epi);
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, to, to2, tx, m_tiles, n_tiles, k_blocks, splits, epi);
   VTB_LAUNCH_CHECK();
   return 0;
 }
@@ -420,7 +609,10 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   VTB_CHECK(p->epilogue != VTB_EPI_SILU_DUAL || (p->out2 && !p->out_f32), -1,
             "vtb_gemm_bf16: SILU_DUAL needs bf16 out and out2");
   VTB_CHECK(p->epilogue != VTB_EPI_SILU_GRAD || p->aux, -1, "vtb_gemm_bf16: SILU_GRAD needs aux");
-  VTB_CHECK(!p->rowmod_add || p->out_group_rows > 0, -1, "vtb_gemm_bf16: rowmod_add needs out_group_rows");
+  VTB_CHECK(!(p->bias && p->splits > 1), -1, "vtb_gemm_bf16: bias cannot be combined with split-K");
+  VTB_CHECK(!(p->resid && p->epilogue != VTB_EPI_NONE), -1, "vtb_gemm_bf16: resid only with EPI_NONE");
+  VTB_CHECK(!p->resid || p->out_f32, -1, "vtb_gemm_bf16: resid needs an f32 output");
+  VTB_CHECK(p->epilogue != VTB_EPI_SILU_GRAD || !p->out_f32, -1, "vtb_gemm_bf16: SILU_GRAD writes bf16");
   VTB_CHECK(!p->row_scale || p->rows_per_scale > 0, -1, "vtb_gemm_bf16: rows_per_scale");
 
   EpiParams e;
@@ -433,8 +625,6 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   e.aux = reinterpret_cast<const bf16*>(p->aux); e.ldaux = p->ldaux;
   e.epilogue = p->epilogue;
   e.accumulate = p->accumulate;
-  e.og_rows = p->out_group_rows; e.og_stride = p->out_group_stride; e.og_off = p->out_group_off;
-  e.rowmod_add = p->rowmod_add; e.ld_rowmod = p->ld_rowmod;
   e.alpha = p->alpha;
   {  // 16-byte vector epilogue only when every touched row start is 16-byte aligned; scalar path otherwise
     const int oalign = p->out_f32 ? 4 : 8;
@@ -442,8 +632,9 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
     if (p->out2) v = v && (((uintptr_t)p->out2 & 15) == 0);
     if (p->resid) v = v && (p->ldr % 4 == 0) && (((uintptr_t)p->resid & 15) == 0);
     if (p->aux) v = v && (p->ldaux % 8 == 0) && (((uintptr_t)p->aux & 15) == 0);
-    if (p->rowmod_add) v = v && (p->ld_rowmod % 4 == 0) && (((uintptr_t)p->rowmod_add & 15) == 0);
     e.vec = v ? 1 : 0;
+    // staged TMA epilogue needs the same alignment plus a 16-byte aligned bias (float4 loads)
+    e.tma = (v && (!p->bias || ((uintptr_t)p->bias & 15) == 0)) ? 1 : 0;
   }
 
   // Tile-N choice: widest tile that does not waste more than ~25% of the MMA columns.
@@ -461,7 +652,7 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   int splits = p->splits;
   if (splits <= 0) {
     splits = 1;
-    if (p->accumulate) {
+    if (p->accumulate && !p->bias) {
       // fill the machine: enough split-K slices for >= 2 waves' worth of tiles, >= 8 k-blocks each
       const int tiles = m_tiles * n_tiles;
       int want = (2 * g_num_sms + tiles - 1) / tiles;

@@ -305,8 +305,8 @@ class SiLUFn(Function):
 class ViTPatchEmbedFn(Function):
     """conv k=s=p (+bias) -> tokens, cls concat, + pos_embed  (vit.py:73-76,141-143) -> f32 [B, 1+n, D].
 
-    The conv is a GEMM over gathered patches; bias, positional embedding and the token offset (row 0 of
-    every image is the cls token) are folded into the GEMM epilogue.
+    The conv is a GEMM over gathered patches (bias in the epilogue); one assembly kernel then adds the
+    positional embedding and places the cls row of every image.
     """
 
     @staticmethod
@@ -318,11 +318,10 @@ class ViTPatchEmbedFn(Function):
         A = ops.patch_gather(_c(img), nchw=True, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
         wb = ops.cast_bf16(_c(w).view(D, -1))
         pos = _c(pos_embed).view(n + 1, D)
-        x = torch.empty((B * (n + 1), D), dtype=F32, device=img.device)
-        ops.gemm(A, wb, out=x, bias=b, out_group=(n, n + 1, 1), rowmod_add=pos[1:])
-        ops.fill_rows(x, (n + 1) * D, B, D, _c(cls_token).view(D), pos[0])
+        tok = ops.gemm(A, wb, out_dtype=F32, bias=b)
+        x = ops.vit_assemble_tokens(tok, _c(cls_token).view(D), pos, B, n, D)
         ctx.stash = (A, B, n, D, w.shape)
-        return x.view(B, n + 1, D)
+        return x
 
     @staticmethod
     @_bwd

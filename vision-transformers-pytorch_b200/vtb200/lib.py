@@ -18,7 +18,7 @@ SYMBOLS = [
     "vtb_last_error", "vtb_version", "vtb_init", "vtb_gemm_bf16", "vtb_layernorm_fwd",
     "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_cast_f32_bf16",
     "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
-    "vtb_patch_scatter", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
+    "vtb_patch_scatter", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
     "vtb_silu_fwd", "vtb_silu_bwd",
 ]
 
@@ -35,8 +35,6 @@ class GemmParams(C.Structure):
         ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
         ("aux", C.c_void_p), ("ldaux", C.c_int32),
         ("epilogue", C.c_int32), ("splits", C.c_int32), ("accumulate", C.c_int32),
-        ("out_group_rows", C.c_int32), ("out_group_stride", C.c_int32), ("out_group_off", C.c_int32),
-        ("rowmod_add", C.c_void_p), ("ld_rowmod", C.c_int32),
         ("alpha", C.c_float),
     ]
 
@@ -97,6 +95,7 @@ def load():
     lib.vtb_colsum_bf16.argtypes = [vp, i64, i32, i32, vp, vp]
     lib.vtb_patch_gather.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.vtb_patch_scatter.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+    lib.vtb_vit_assemble_tokens.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.vtb_fill_rows.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     lib.vtb_rowgroup_sum.argtypes = [vp, i64, i32, i32, i32, vp, vp]
     lib.vtb_mean_rows_fwd.argtypes = [vp, i32, i32, i32, vp, vp]

@@ -73,7 +73,7 @@ def _chk2d(t, dtype, name):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, resid=None,
          row_scale=None, rows_per_scale=0, epilogue=_l.EPI_NONE, aux=None, out2=None, accumulate=False,
-         splits=0, out_group=None, rowmod_add=None, alpha=1.0):
+         splits=0, alpha=1.0):
     """C[M,N] = alpha * sum_k A(m,k) B(n,k) with the fused epilogue of vtb_gemm_bf16.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] or [K,N] (b_mn=True); both bf16 row-major
@@ -87,14 +87,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
     if K != Kb:
         raise ValueError(f"vtb200.gemm: K mismatch {K} vs {Kb}")
     rows_out = M
-    if out_group is not None:
-        g_rows, g_stride, g_off = out_group
-        if M % g_rows:
-            raise ValueError("vtb200.gemm: M must be a multiple of out_group rows")
-        rows_out = (M // g_rows) * g_stride
     if out is None:
-        if out_group is not None:
-            raise ValueError("vtb200.gemm: out_group needs an explicit out tensor")
         out = (torch.zeros if accumulate else torch.empty)((M, N), dtype=out_dtype, device=a.device)
     _chk2d(out, out.dtype, "gemm(out)")
     if out.shape[0] < rows_out or out.shape[1] != N:
@@ -128,11 +121,6 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
         _chk2d(aux, BF16, "gemm(aux)")
         p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
     p.epilogue, p.splits, p.accumulate = epilogue, splits, int(accumulate)
-    if out_group is not None:
-        p.out_group_rows, p.out_group_stride, p.out_group_off = out_group
-    if rowmod_add is not None:
-        _chk2d(rowmod_add, F32, "gemm(rowmod_add)")
-        p.rowmod_add, p.ld_rowmod = rowmod_add.data_ptr(), rowmod_add.stride(0)
     p.alpha = alpha
     kind = ("wgrad" if a_mn else ("dgrad" if b_mn else "fwd"))
     with _prof(f"gemm_{kind}[{M}x{N}x{K}]", 2.0 * M * N * K):
@@ -347,6 +335,16 @@ def patch_scatter(dA, *, c_major, B, Cc, H, W, p, dx=None, accumulate=False):
                                        int(accumulate), _stream()), lib)
     _count()
     return dx
+
+
+def vit_assemble_tokens(tok, cls, pos, B, n, D):
+    """x[b,0] = cls + pos[0]; x[b,1+p] = tok[b*n+p] + pos[1+p]  ->  f32 [B, n+1, D]."""
+    lib = _l.get()
+    x = torch.empty((B, n + 1, D), dtype=F32, device=tok.device)
+    with _prof("vit_assemble_tokens"):
+        _l.check(lib.vtb_vit_assemble_tokens(_p(tok), _p(cls), _p(pos), B, n, D, _p(x), _stream()), lib)
+    _count()
+    return x
 
 
 def fill_rows(x, group_stride, groups, cols, a, b=None):
