@@ -629,6 +629,10 @@ int make_geom(const vtb_attn_params* p, Geom* g, long* groups, const char* who) 
 
 }  // namespace
 
+bool vtb_attn_resident_ok(const vtb_attn_params* p);
+int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
+int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
+
 extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Geom g;
@@ -636,6 +640,7 @@ extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_)
   int rc = make_geom(p, &g, &groups, "vtb_attention_fwd");
   if (rc) return rc;
   VTB_CHECK(p->o && p->ldo % 2 == 0, -1, "vtb_attention_fwd: o");
+  if (vtb_attn_resident_ok(p)) return vtb_attn_resident_fwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const long blocks = groups * p->heads * q_tiles;
   VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd: grid too large");
@@ -658,6 +663,7 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
   VTB_CHECK(p->lddq % 2 == 0 && (p->dkv_f32 || (p->lddk % 2 == 0 && p->lddv % 2 == 0)), -1,
             "vtb_attention_bwd: dq/dk/dv leading dims");
   const vtb_attn_params& q = *p;
+  if (vtb_attn_resident_ok(p)) return vtb_attn_resident_bwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const int kv_tiles = (p->nkv + BKV - 1) / BKV;
   const long b1 = groups * p->heads * q_tiles, b2 = groups * p->heads * kv_tiles;
@@ -670,6 +676,555 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
     attn_bwd_dq_kernel<32><<<(unsigned)b1, NTHREADS, 0, stream>>>(q, g, q_tiles);
     VTB_LAUNCH_CHECK();
     attn_bwd_dkv_kernel<32><<<(unsigned)b2, NTHREADS, 0, stream>>>(q, g, kv_tiles);
+  }
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// "Resident" attention (nq <= 256 and nkv <= 256: ViT/DeiT global, Swin/Twins windows, Halo, PVT stage 4).
+// One CTA per (group, head); Q/K/V (and dO) are loaded ONCE into XOR-swizzled shared memory, the combined
+// relative-position-bias + mask tile is built once per CTA, and each warp owns one 16-row tile: there is
+// no block barrier inside the compute loops and no tile is padded beyond the next multiple of 16.
+// Backward is ONE kernel: phase A (warp = 16 queries) produces dQ and the bias gradient, phase B
+// (warp = 16 keys) produces dK and dV from the same resident operands.
+// =====================================================================================================
+namespace {
+
+constexpr int RES_MAX = 208;      // 13 warps x 16 rows
+constexpr int RES_THREADS = 416;
+
+// element offset of 16-byte chunk `c` of row `r` in a [rows][DH] bf16 tile, XOR-swizzled so that ldmatrix
+// (8 rows x 16 B) and the cooperative 16-byte stores are bank-conflict free without padding.
+template <int DH>
+__device__ __forceinline__ int soff(int r, int c) {
+  if (DH == 64) return r * 64 + ((c ^ (r & 7)) << 3);
+  return r * 32 + ((c ^ ((r >> 1) & 3)) << 3);
+}
+
+template <int DH>
+__device__ __forceinline__ void res_load_rows(bf16* dst, int rows16, const bf16* base, int ld, int head_off,
+                                              const int* toks) {
+  constexpr int CH = DH / 8;
+  for (int c = threadIdx.x; c < rows16 * CH; c += blockDim.x) {
+    const int r = c / CH, cc = c - r * CH;
+    const int t = toks[r];
+    const bf16* src = base + (long)(t < 0 ? 0 : t) * ld + head_off + cc * 8;
+    cp_async16(smem_u32(dst + soff<DH>(r, cc)), src, t >= 0);
+  }
+}
+
+struct ResSmem {
+  bf16 *q, *k, *v, *dO;
+  float *bias, *lse, *delta, *dtab;
+  unsigned short* pos;
+  int *qtok, *ktok;
+  int nq16, nkv16, bias_ld;
+};
+
+// nq_loc = query rows staged by this CTA (forward may split the queries of a (group, head) over CTAs)
+template <int DH>
+__device__ __forceinline__ ResSmem res_carve(uint8_t* base, int nq_loc, int nq, int nkv, bool bwd, bool has_bias,
+                                             int n_pos) {
+  ResSmem s;
+  s.nq16 = (nq_loc + 15) & ~15;
+  s.nkv16 = (nkv + 15) & ~15;
+  s.bias_ld = (nkv + 3) & ~3;
+  uint8_t* p = base;
+  s.q = reinterpret_cast<bf16*>(p); p += s.nq16 * DH * 2;
+  s.k = reinterpret_cast<bf16*>(p); p += s.nkv16 * DH * 2;
+  s.v = reinterpret_cast<bf16*>(p); p += s.nkv16 * DH * 2;
+  s.dO = reinterpret_cast<bf16*>(p); if (bwd) p += s.nq16 * DH * 2;
+  s.bias = reinterpret_cast<float*>(p); if (has_bias) p += (size_t)nq * s.bias_ld * 4;
+  s.lse = reinterpret_cast<float*>(p); if (bwd) p += s.nq16 * 4;
+  s.delta = reinterpret_cast<float*>(p); if (bwd) p += s.nq16 * 4;
+  s.dtab = reinterpret_cast<float*>(p); if (bwd && has_bias) p += n_pos * 4;
+  s.qtok = reinterpret_cast<int*>(p); p += s.nq16 * 4;
+  s.ktok = reinterpret_cast<int*>(p); p += s.nkv16 * 4;
+  s.pos = reinterpret_cast<unsigned short*>(p);  // [nq][bias_ld] u16 (bwd with bias only)
+  return s;
+}
+
+size_t res_smem_bytes(int DH, int nq_loc, int nq, int nkv, bool bwd, bool has_bias, bool has_table, int n_pos) {
+  const int nq16 = (nq_loc + 15) & ~15, nkv16 = (nkv + 15) & ~15, bld = (nkv + 3) & ~3;
+  size_t b = (size_t)(nq16 + 2 * nkv16) * DH * 2 + (size_t)(nq16 + nkv16) * 4;
+  if (bwd) b += (size_t)nq16 * DH * 2 + (size_t)nq16 * 8;
+  if (has_bias) b += (size_t)nq * bld * 4;
+  if (bwd && has_table) b += (size_t)n_pos * 4 + (size_t)nq * bld * 2;
+  return b + 16;
+}
+
+// builds token indices, the bias(+mask) tile and (bwd) the pos tile; issues the cp.async row loads
+template <int DH>
+__device__ __forceinline__ void res_prologue(const vtb_attn_params& p, const Geom& g, int grp, int h,
+                                             const ResSmem& s, bool bwd, int qbase, int q_end) {
+  for (int i = threadIdx.x; i < s.nq16; i += blockDim.x)
+    s.qtok[i] = (qbase + i < q_end) ? (int)q_token(g, grp, qbase + i) : -1;
+  for (int j = threadIdx.x; j < s.nkv16; j += blockDim.x) s.ktok[j] = (int)kv_token(g, grp, j);
+  const bool has_bias = p.rel_bias || p.mask;
+  if (has_bias) {
+    const uint8_t* mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+    for (int e = threadIdx.x; e < g.nq * g.nkv; e += blockDim.x) {
+      const int i = e / g.nkv, j = e - i * g.nkv;
+      float b = 0.f;
+      if (p.rel_bias) {
+        const int pi = __ldg(p.pos + e);
+        b = __ldg(p.rel_bias + (long)pi * g.heads + h);
+        if (bwd) s.pos[i * s.bias_ld + j] = (unsigned short)pi;
+      }
+      if (mask && mask[e]) b = -INFINITY;
+      s.bias[i * s.bias_ld + j] = b;
+    }
+    if (bwd && p.rel_bias)
+      for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) s.dtab[t] = 0.f;
+  }
+  __syncthreads();  // token indices visible
+  res_load_rows<DH>(s.q, s.nq16, reinterpret_cast<const bf16*>(p.q), p.ldq, h * DH, s.qtok);
+  res_load_rows<DH>(s.k, s.nkv16, reinterpret_cast<const bf16*>(p.k), p.ldk, h * DH, s.ktok);
+  res_load_rows<DH>(s.v, s.nkv16, reinterpret_cast<const bf16*>(p.v), p.ldv, h * DH, s.ktok);
+  if (bwd) res_load_rows<DH>(s.dO, s.nq16, reinterpret_cast<const bf16*>(p.dout), p.lddo, h * DH, s.qtok);
+  cp_async_commit();
+}
+
+// A fragments (16 rows x DH) of a swizzled tile
+template <int DH>
+__device__ __forceinline__ void res_ld_a(uint32_t (&f)[DH / 16][4], const bf16* tile, int r0, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; ++kk)
+    ldsm_x4(f[kk], smem_u32(tile + soff<DH>(r0 + (lane & 15), kk * 2 + (lane >> 4))));
+}
+// B fragments for two adjacent n8 tiles (16 "n" rows starting at n0), contraction chunk kk (16 wide), non-transposed
+template <int DH>
+__device__ __forceinline__ void res_ld_b(uint32_t (&r)[4], const bf16* tile, int n0, int kk, int lane) {
+  ldsm_x4(r, smem_u32(tile + soff<DH>(n0 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1))));
+}
+// transposed B fragments: contraction rows k0..k0+15 of the tile, output columns d2*16..+15
+template <int DH>
+__device__ __forceinline__ void res_ld_bt(uint32_t (&r)[4], const bf16* tile, int k0, int d2, int lane) {
+  ldsm_x4_t(r, smem_u32(tile + soff<DH>(k0 + (lane & 7) + (((lane >> 3) & 1) << 3), d2 * 2 + (lane >> 4))));
+}
+
+template <int DH>
+__global__ void __launch_bounds__(RES_THREADS, 1)
+attn_res_fwd_kernel(vtb_attn_params p, Geom g, int nsplit, int q_per_cta) {
+  extern __shared__ __align__(16) uint8_t res_smem[];
+  const int split = blockIdx.x % nsplit;
+  const int gh = blockIdx.x / nsplit;
+  const int h = gh % g.heads;
+  const int grp = gh / g.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool has_bias = p.rel_bias || p.mask;
+  const int qbase = split * q_per_cta;
+  const int q_end = min(g.nq, qbase + q_per_cta);
+  const ResSmem s = res_carve<DH>(res_smem, q_per_cta, g.nq, g.nkv, false, has_bias, p.n_pos);
+  res_prologue<DH>(p, g, grp, h, s, false, qbase, q_end);
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  if (qbase + r0 >= q_end) return;
+  uint32_t qf[DH / 16][4];
+  res_ld_a<DH>(qf, s.q, r0, lane);
+  float o[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  for (int j0 = 0; j0 < g.nkv; j0 += 64) {
+    const int npair = min(4, (s.nkv16 - j0) >> 4);  // valid 16-key groups in this block
+    float sc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        if (n2 < npair) {
+          uint32_t kb[4];
+          res_ld_b<DH>(kb, s.k, j0 + n2 * 16, kk, lane);
+          uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+          mma_bf16_16816(sc[2 * n2], qf[kk], b0);
+          mma_bf16_16816(sc[2 * n2 + 1], qf[kk], b1);
+        }
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = qbase + r0 + gq + (e >> 1) * 8;
+        const int j = j0 + n * 8 + 2 * tq + (e & 1);
+        float v = sc[n][e] * p.scale;
+        if (j >= g.nkv) v = -INFINITY;
+        else if (has_bias) v += s.bias[min(i, g.nq - 1) * s.bias_ld + j];
+        sc[n][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2], m_use[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = __expf(m_run[r] - m_use[r]);
+      m_run[r] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = __expf(sc[n][e] - m_use[e >> 1]);
+        sc[n][e] = pv;
+        rs[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      l_run[r] = l_run[r] * corr[r] + rs[r];
+    }
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1];
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      if (k2 < npair) {
+        uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                          pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                          pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+#pragma unroll
+        for (int d2 = 0; d2 < DH / 16; ++d2) {
+          uint32_t vb[4];
+          res_ld_bt<DH>(vb, s.v, j0 + k2 * 16, d2, lane);
+          uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+          mma_bf16_16816(o[2 * d2], pa, b0);
+          mma_bf16_16816(o[2 * d2 + 1], pa, b1);
+        }
+      }
+    }
+  }
+
+  bf16* O = reinterpret_cast<bf16*>(p.o);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = r0 + gq + r * 8;
+    const int tok = s.qtok[row];
+    if (tok < 0) continue;
+    const float inv = 1.f / l_run[r];
+    bf16* dst = O + (long)tok * p.ldo + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n)
+      *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) = pack_bf16(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+    if (tq == 0 && p.lse) p.lse[((long)grp * g.heads + h) * g.nq + qbase + row] = m_run[r] + __logf(l_run[r]);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(RES_THREADS, 1)
+attn_res_bwd_kernel(vtb_attn_params p, Geom g) {
+  extern __shared__ __align__(16) uint8_t res_smem[];
+  const int h = blockIdx.x % g.heads;
+  const int grp = blockIdx.x / g.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool has_bias = p.rel_bias || p.mask;
+  const bool has_tab = p.rel_bias != nullptr;
+  const ResSmem s = res_carve<DH>(res_smem, g.nq, g.nq, g.nkv, true, has_bias, has_tab ? p.n_pos : 0);
+  res_prologue<DH>(p, g, grp, h, s, true, 0, g.nq);
+  // delta_i = sum_d dO[i,d] O[i,d] and lse_i, two threads per row (straight from global; O is not staged)
+  {
+    const bf16* O = reinterpret_cast<const bf16*>(p.o);
+    const bf16* dO = reinterpret_cast<const bf16*>(p.dout);
+    for (int t = threadIdx.x; t < 2 * s.nq16; t += blockDim.x) {
+      const int row = t >> 1, half = t & 1;
+      const int tok = s.qtok[row];
+      float acc = 0.f;
+      if (tok >= 0) {
+        const bf16* a = dO + (long)tok * p.lddo + h * DH + half * (DH / 2);
+        const bf16* b = O + (long)tok * p.ldo + h * DH + half * (DH / 2);
+#pragma unroll
+        for (int d = 0; d < DH / 2; d += 8) {
+          const uint4 ra = *reinterpret_cast<const uint4*>(a + d);
+          const uint4 rb = *reinterpret_cast<const uint4*>(b + d);
+          const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
+            acc += fa.x * fb.x + fa.y * fb.y;
+          }
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // partner thread t^1 is in the same warp
+      if (half == 0) {
+        s.delta[row] = acc;
+        s.lse[row] = tok >= 0 ? p.lse[((long)grp * g.heads + h) * g.nq + row] : 0.f;
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase A: dQ (+ bias gradient)
+  {
+    const int r0 = warp * 16;
+    if (r0 < s.nq16) {
+      float lse_r[2], dl_r[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) { lse_r[r] = s.lse[r0 + gq + r * 8]; dl_r[r] = s.delta[r0 + gq + r * 8]; }
+      float dq[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
+      for (int j0 = 0; j0 < g.nkv; j0 += 64) {
+        const int npair = min(4, (s.nkv16 - j0) >> 4);
+        float sc[8][4], dp[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+          dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          // A fragments are re-read from shared memory per k-step (keeps the kernel under 128 registers)
+          uint32_t qf[4], dof[4];
+          ldsm_x4(qf, smem_u32(s.q + soff<DH>(r0 + (lane & 15), kk * 2 + (lane >> 4))));
+          ldsm_x4(dof, smem_u32(s.dO + soff<DH>(r0 + (lane & 15), kk * 2 + (lane >> 4))));
+#pragma unroll
+          for (int n2 = 0; n2 < 4; ++n2) {
+            if (n2 < npair) {
+              uint32_t kb[4], vb[4];
+              res_ld_b<DH>(kb, s.k, j0 + n2 * 16, kk, lane);
+              res_ld_b<DH>(vb, s.v, j0 + n2 * 16, kk, lane);
+              uint32_t k0[2] = {kb[0], kb[1]}, k1[2] = {kb[2], kb[3]};
+              uint32_t v0[2] = {vb[0], vb[1]}, v1[2] = {vb[2], vb[3]};
+              mma_bf16_16816(sc[2 * n2], qf, k0);
+              mma_bf16_16816(sc[2 * n2 + 1], qf, k1);
+              mma_bf16_16816(dp[2 * n2], dof, v0);
+              mma_bf16_16816(dp[2 * n2 + 1], dof, v1);
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = e >> 1;
+            const int i = r0 + gq + r * 8;
+            const int j = j0 + n * 8 + 2 * tq + (e & 1);
+            float ds = 0.f;
+            if (j < g.nkv && i < g.nq) {
+              float v = sc[n][e] * p.scale;
+              if (has_bias) v += s.bias[i * s.bias_ld + j];
+              const float pv = __expf(v - lse_r[r]);  // exp(-inf) = 0 for masked entries
+              ds = pv * (dp[n][e] - dl_r[r]);
+              if (has_tab && p.drel_bias && ds != 0.f) atomicAdd(&s.dtab[s.pos[i * s.bias_ld + j]], ds);
+            }
+            sc[n][e] = ds;
+          }
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          if (k2 < npair) {
+            uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                              pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                              pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+#pragma unroll
+            for (int d2 = 0; d2 < DH / 16; ++d2) {
+              uint32_t kb[4];
+              res_ld_bt<DH>(kb, s.k, j0 + k2 * 16, d2, lane);
+              uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+              mma_bf16_16816(dq[2 * d2], pa, b0);
+              mma_bf16_16816(dq[2 * d2 + 1], pa, b1);
+            }
+          }
+        }
+      }
+      bf16* dQ = reinterpret_cast<bf16*>(p.dq);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int tok = s.qtok[r0 + gq + r * 8];
+        if (tok < 0) continue;
+        bf16* dst = dQ + (long)tok * p.lddq + h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) =
+              pack_bf16(dq[n][2 * r] * p.scale, dq[n][2 * r + 1] * p.scale);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ phase B: dK, dV (rows = keys)
+  {
+    const int c0 = warp * 16;
+    if (c0 < s.nkv16) {
+      constexpr int PB = (DH == 64) ? 2 : 4;  // 16-query groups per pass (register budget: 128/thread)
+      float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+        dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+      }
+      for (int i0 = 0; i0 < g.nq; i0 += 16 * PB) {
+        const int npair = min(PB, (s.nq16 - i0) >> 4);
+        float sc[2 * PB][4], dp[2 * PB][4];
+#pragma unroll
+        for (int n = 0; n < 2 * PB; ++n) {
+          sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+          dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          uint32_t kf[4], vf[4];
+          ldsm_x4(kf, smem_u32(s.k + soff<DH>(c0 + (lane & 15), kk * 2 + (lane >> 4))));
+          ldsm_x4(vf, smem_u32(s.v + soff<DH>(c0 + (lane & 15), kk * 2 + (lane >> 4))));
+#pragma unroll
+          for (int n2 = 0; n2 < PB; ++n2) {
+            if (n2 < npair) {
+              uint32_t qb[4], ob[4];
+              res_ld_b<DH>(qb, s.q, i0 + n2 * 16, kk, lane);
+              res_ld_b<DH>(ob, s.dO, i0 + n2 * 16, kk, lane);
+              uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+              uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+              mma_bf16_16816(sc[2 * n2], kf, q0);
+              mma_bf16_16816(sc[2 * n2 + 1], kf, q1);
+              mma_bf16_16816(dp[2 * n2], vf, o0);
+              mma_bf16_16816(dp[2 * n2 + 1], vf, o1);
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < 2 * PB; ++n) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = c0 + gq + (e >> 1) * 8;
+            const int i = i0 + n * 8 + 2 * tq + (e & 1);
+            float pv = 0.f, ds = 0.f;
+            if (j < g.nkv && i < g.nq) {
+              float v = sc[n][e] * p.scale;
+              if (has_bias) v += s.bias[i * s.bias_ld + j];
+              pv = __expf(v - s.lse[i]);
+              ds = pv * (dp[n][e] - s.delta[i]);
+            }
+            sc[n][e] = pv;
+            dp[n][e] = ds;
+          }
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < PB; ++k2) {
+          if (k2 < npair) {
+            uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                              pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                              pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+            uint32_t da[4] = {pack_bf16(dp[2 * k2][0], dp[2 * k2][1]), pack_bf16(dp[2 * k2][2], dp[2 * k2][3]),
+                              pack_bf16(dp[2 * k2 + 1][0], dp[2 * k2 + 1][1]),
+                              pack_bf16(dp[2 * k2 + 1][2], dp[2 * k2 + 1][3])};
+#pragma unroll
+            for (int d2 = 0; d2 < DH / 16; ++d2) {
+              uint32_t ob[4], qb[4];
+              res_ld_bt<DH>(ob, s.dO, i0 + k2 * 16, d2, lane);
+              res_ld_bt<DH>(qb, s.q, i0 + k2 * 16, d2, lane);
+              uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+              uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+              mma_bf16_16816(dv[2 * d2], pa, o0);
+              mma_bf16_16816(dv[2 * d2 + 1], pa, o1);
+              mma_bf16_16816(dk[2 * d2], da, q0);
+              mma_bf16_16816(dk[2 * d2 + 1], da, q1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int tok = s.ktok[c0 + gq + r * 8];
+        if (tok < 0) continue;
+        if (p.dkv_f32) {
+          float* dKp = reinterpret_cast<float*>(p.dk) + (long)tok * p.lddk + h * DH;
+          float* dVp = reinterpret_cast<float*>(p.dv) + (long)tok * p.lddv + h * DH;
+#pragma unroll
+          for (int n = 0; n < DH / 8; ++n) {
+            atomicAdd(dKp + n * 8 + 2 * tq, dk[n][2 * r] * p.scale);
+            atomicAdd(dKp + n * 8 + 2 * tq + 1, dk[n][2 * r + 1] * p.scale);
+            atomicAdd(dVp + n * 8 + 2 * tq, dv[n][2 * r]);
+            atomicAdd(dVp + n * 8 + 2 * tq + 1, dv[n][2 * r + 1]);
+          }
+        } else {
+          bf16* dKp = reinterpret_cast<bf16*>(p.dk) + (long)tok * p.lddk + h * DH;
+          bf16* dVp = reinterpret_cast<bf16*>(p.dv) + (long)tok * p.lddv + h * DH;
+#pragma unroll
+          for (int n = 0; n < DH / 8; ++n) {
+            *reinterpret_cast<uint32_t*>(dKp + n * 8 + 2 * tq) =
+                pack_bf16(dk[n][2 * r] * p.scale, dk[n][2 * r + 1] * p.scale);
+            *reinterpret_cast<uint32_t*>(dVp + n * 8 + 2 * tq) = pack_bf16(dv[n][2 * r], dv[n][2 * r + 1]);
+          }
+        }
+      }
+    }
+  }
+
+  if (has_tab && p.drel_bias) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) {
+      const float v = s.dtab[t];
+      if (v != 0.f) atomicAdd(p.drel_bias + (long)t * g.heads + h, v);
+    }
+  }
+}
+
+template <typename K>
+int res_set_smem(K kern, size_t bytes) {
+  VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  (void)bytes;
+  return 0;
+}
+
+}  // namespace
+
+bool vtb_attn_resident_ok(const vtb_attn_params* p) { return p->nq <= RES_MAX && p->nkv <= RES_MAX; }
+
+int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+  const bool has_bias = p->rel_bias || p->mask;
+  // split the queries of one (group, head) over CTAs so that >= 2-3 CTAs fit an SM (K/V are re-read from L2)
+  const int tiles = (p->nq + 15) / 16;
+  const int nsplit = tiles > 8 ? 2 : 1;
+  const int q_per_cta = ((tiles + nsplit - 1) / nsplit) * 16;
+  const size_t smem = res_smem_bytes(p->dh, q_per_cta, p->nq, p->nkv, false, has_bias, p->rel_bias != nullptr, p->n_pos);
+  VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_fwd: resident tile needs %zu B of shared memory", smem);
+  const int warps = q_per_cta / 16;
+  const long blocks = groups * p->heads * nsplit;
+  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd: grid too large");
+  static bool set64 = false, set32 = false;
+  if (p->dh == 64) {
+    if (!set64) { int rc = res_set_smem(attn_res_fwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
+    attn_res_fwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, nsplit, q_per_cta);
+  } else {
+    if (!set32) { int rc = res_set_smem(attn_res_fwd_kernel<32>, smem); if (rc) return rc; set32 = true; }
+    attn_res_fwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, nsplit, q_per_cta);
+  }
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+  const bool has_bias = p->rel_bias || p->mask;
+  const size_t smem = res_smem_bytes(p->dh, p->nq, p->nq, p->nkv, true, has_bias, p->rel_bias != nullptr, p->n_pos);
+  VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_bwd: resident tile needs %zu B of shared memory", smem);
+  const int nmax = p->nq > p->nkv ? p->nq : p->nkv;
+  const int warps = (nmax + 15) / 16;
+  const long blocks = groups * p->heads;
+  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_bwd: grid too large");
+  static bool set64 = false, set32 = false;
+  if (p->dh == 64) {
+    if (!set64) { int rc = res_set_smem(attn_res_bwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
+    attn_res_bwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g);
+  } else {
+    if (!set32) { int rc = res_set_smem(attn_res_bwd_kernel<32>, smem); if (rc) return rc; set32 = true; }
+    attn_res_bwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g);
   }
   VTB_LAUNCH_CHECK();
   return 0;

@@ -70,30 +70,63 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __rest
     dx[i] = dy[i] * silu_grad_f(x[i]);
 }
 
-// out[n] += sum_m X[m, n]; CTA = 32 column-pairs x 8 row lanes, rows strided by the grid.y
+// out[n] += sum_m X[m, n]; each thread owns 8 consecutive columns (one 16-byte load per row), 8 row lanes
+// per CTA, rows partitioned over grid.y; 4 independent row loads in flight per thread.
 constexpr int CS_ROWS = 8;
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ X, long M, int N, int ld, float* __restrict__ out,
               long rows_per_block) {
-  __shared__ float2 part[CS_ROWS][32];
-  const int cp = blockIdx.x * 32 + (threadIdx.x & 31);  // column pair
+  __shared__ float part[CS_ROWS][32][8];
+  const int c8 = blockIdx.x * 32 + (threadIdx.x & 31);  // group of 8 columns
   const int rl = threadIdx.x >> 5;
   const long r0 = (long)blockIdx.y * rows_per_block;
   const long r1 = min(M, r0 + rows_per_block);
-  float2 acc = make_float2(0.f, 0.f);
-  if (2 * cp < N) {
-    for (long r = r0 + rl; r < r1; r += CS_ROWS) {
-      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(X + r * ld + 2 * cp));
-      acc.x += v.x; acc.y += v.y;
-    }
-  }
-  part[rl][threadIdx.x & 31] = acc;
-  __syncthreads();
-  if (rl == 0 && 2 * cp < N) {
+  float acc[8];
 #pragma unroll
-    for (int i = 1; i < CS_ROWS; ++i) { acc.x += part[i][threadIdx.x].x; acc.y += part[i][threadIdx.x].y; }
-    atomicAdd(out + 2 * cp, acc.x);
-    if (2 * cp + 1 < N) atomicAdd(out + 2 * cp + 1, acc.y);
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bool vec = (8 * c8 + 8 <= N);
+  if (vec) {
+    long r = r0 + rl;
+    for (; r + 3 * CS_ROWS < r1; r += 4 * CS_ROWS) {
+      uint4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const uint4*>(X + (r + u * CS_ROWS) * ld + 8 * c8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16(w[q]);
+          acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += CS_ROWS) {
+      const uint4 t = *reinterpret_cast<const uint4*>(X + r * ld + 8 * c8);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16(w[q]);
+        acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
+      }
+    }
+  } else if (8 * c8 < N) {
+    for (long r = r0 + rl; r < r1; r += CS_ROWS)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (8 * c8 + j < N) acc[j] += __bfloat162float(X[r * ld + 8 * c8 + j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rl][threadIdx.x & 31][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && 8 * c8 < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < CS_ROWS; ++i) v += part[i][threadIdx.x][j];
+      if (8 * c8 + j < N) atomicAdd(out + 8 * c8 + j, v);
+    }
   }
 }
 
@@ -265,11 +298,11 @@ extern "C" int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t 
 
 extern "C" int vtb_colsum_bf16(const void* X, int64_t M, int32_t N, int32_t ld, float* out, vtb_stream_t s) {
   VTB_CHECK(X && out && M > 0 && N > 0, -1, "vtb_colsum_bf16: bad args");
-  VTB_CHECK(ld % 2 == 0 && ((uintptr_t)X & 3) == 0, -1, "vtb_colsum_bf16: alignment");
-  const int gx = ((N + 1) / 2 + 31) / 32;
-  int gy = (4 * (vtb_num_sms() > 0 ? vtb_num_sms() : 148) + gx - 1) / gx;
+  VTB_CHECK(ld % 8 == 0 && ((uintptr_t)X & 15) == 0, -1, "vtb_colsum_bf16: rows must be 16-byte aligned");
+  const int gx = ((N + 7) / 8 + 31) / 32;
+  int gy = (8 * (vtb_num_sms() > 0 ? vtb_num_sms() : 148) + gx - 1) / gx;
   long rpb = (M + gy - 1) / gy;
-  if (rpb < 64) rpb = 64;
+  if (rpb < 128) rpb = 128;
   gy = (int)((M + rpb - 1) / rpb);
   colsum_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)s>>>((const bf16*)X, M, N, ld, out, rpb);
   VTB_LAUNCH_CHECK();

@@ -93,10 +93,12 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
-// Backward.  Each CTA accumulates dgamma/dbeta partials in shared memory (one slot per column),
-// then issues one atomicAdd per column per CTA.
-template <bool DY_F32, int MAX_V4_PER_LANE>
-__global__ void __launch_bounds__(LN_THREADS)
+// Backward.  One warp per row, NV = ceil(cols / 128) float4 per lane (exact, so registers stay low enough
+// for >= 2 CTAs per SM: the kernel is HBM-bound and needs the loads of many rows in flight).  dy stays packed
+// (bf16) in registers between the two passes; dgamma/dbeta partials live in registers across the rows a warp
+// processes, are combined per CTA in shared memory, then one atomicAdd per column per CTA.
+template <bool DY_F32, int NV>
+__global__ void __launch_bounds__(LN_THREADS, (NV <= 2) ? 3 : ((NV <= 6) ? 2 : 1))
 ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, long rows, RowMap g,
@@ -109,56 +111,73 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   for (int i = threadIdx.x; i < 2 * g.cols; i += LN_THREADS) s_part[i] = 0.f;
   __syncthreads();
 
-  float4 dg[MAX_V4_PER_LANE], db[MAX_V4_PER_LANE];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < MAX_V4_PER_LANE; ++i) {
+  for (int i = 0; i < NV; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   for (long r = (long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); r < rows;
        r += (long)gridDim.x * LN_WARPS) {
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    float4 xh[MAX_V4_PER_LANE], gy[MAX_V4_PER_LANE];
-    float s1 = 0.f, s2 = 0.f;
+    float4 xv[NV];
+    float4 dvf[DY_F32 ? NV : 1];
+    uint2 dvh[DY_F32 ? 1 : NV];
+    // issue every load of the row first
 #pragma unroll
-    for (int i = 0; i < MAX_V4_PER_LANE; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nv) {
-        const float4 xv = *reinterpret_cast<const float4*>(x + row_v4_offset(g, r, v));
+        xv[i] = *reinterpret_cast<const float4*>(x + row_v4_offset(g, r, v));
+        if (DY_F32)
+          dvf[DY_F32 ? i : 0] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + r * (long)g.cols + v * 4);
+        else
+          dvh[DY_F32 ? 0 : i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy) + r * (long)g.cols + v * 4);
+      }
+    }
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nv) {
         float4 d;
-        if (DY_F32) {
-          d = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) +
-                                               r * (long)g.cols + v * 4);
-        } else {
-          const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy) +
-                                                            r * (long)g.cols + v * 4);
-          const float2 a = unpack_bf16(raw.x), b = unpack_bf16(raw.y);
+        if (DY_F32) d = dvf[DY_F32 ? i : 0];
+        else {
+          const float2 a = unpack_bf16(dvh[DY_F32 ? 0 : i].x), b = unpack_bf16(dvh[DY_F32 ? 0 : i].y);
           d = make_float4(a.x, a.y, b.x, b.y);
         }
-        const float4 gm = *reinterpret_cast<const float4*>(gamma + v * 4);
-        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
-                            (xv.w - mean) * rstd);
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y;
-        dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + v * 4));
+        // xv <- xhat
+        xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd,
+                            (xv[i].w - mean) * rstd);
+        dg[i].x += d.x * xv[i].x; dg[i].y += d.y * xv[i].y;
+        dg[i].z += d.z * xv[i].z; dg[i].w += d.w * xv[i].w;
         db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-        gy[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
-        s2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
+        const float gx = d.x * gm.x, gy = d.y * gm.y, gz = d.z * gm.z, gw = d.w * gm.w;
+        s1 += gx + gy + gz + gw;
+        s2 += gx * xv[i].x + gy * xv[i].y + gz * xv[i].z + gw * xv[i].w;
       }
     }
     s1 = warp_sum(s1) / g.cols;
     s2 = warp_sum(s2) / g.cols;
     const float rs = row_scale ? row_scale[r / rows_per_scale] : 1.f;
 #pragma unroll
-    for (int i = 0; i < MAX_V4_PER_LANE; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nv) {
+        float4 d;
+        if (DY_F32) d = dvf[DY_F32 ? i : 0];
+        else {
+          const float2 a = unpack_bf16(dvh[DY_F32 ? 0 : i].x), b = unpack_bf16(dvh[DY_F32 ? 0 : i].y);
+          d = make_float4(a.x, a.y, b.x, b.y);
+        }
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + v * 4));
         float4 o;
-        o.x = rstd * (gy[i].x - s1 - xh[i].x * s2);
-        o.y = rstd * (gy[i].y - s1 - xh[i].y * s2);
-        o.z = rstd * (gy[i].z - s1 - xh[i].z * s2);
-        o.w = rstd * (gy[i].w - s1 - xh[i].w * s2);
+        o.x = rstd * (d.x * gm.x - s1 - xv[i].x * s2);
+        o.y = rstd * (d.y * gm.y - s1 - xv[i].y * s2);
+        o.z = rstd * (d.z * gm.z - s1 - xv[i].z * s2);
+        o.w = rstd * (d.w * gm.w - s1 - xv[i].w * s2);
         const long off = row_v4_offset(g, r, v);
         if (dx_in) {
           const float4 p = *reinterpret_cast<const float4*>(dx_in + off);
@@ -174,7 +193,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   }
   // CTA-level reduction of the parameter gradients
 #pragma unroll
-  for (int i = 0; i < MAX_V4_PER_LANE; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < nv) {
       float* pg = s_part + v * 4;
@@ -249,18 +268,26 @@ extern "C" int vtb_layernorm_bwd(const void* dy, int32_t dy_f32, const float* x,
   VTB_CHECK(dy && x && gamma && mean && rstd && dx_out, -1, "vtb_layernorm_bwd: null pointer");
   VTB_CHECK(!row_scale || rows_per_scale > 0, -1, "vtb_layernorm_bwd: rows_per_scale");
   long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-  const long cap = (long)vtb_num_sms() * 4;  // fewer CTAs => fewer global atomics per column
+  const long cap = (long)vtb_num_sms() * 6;  // few CTAs => few global atomics per column; 2-3 resident per SM
   if (cap > 0 && blocks > cap) blocks = cap;
   const size_t smem = 2 * (size_t)cols * sizeof(float);
 #define LN_BWD(F32, MV)                                                \
   ln_bwd_kernel<F32, MV><<<(int)blocks, LN_THREADS, smem, stream>>>(   \
       dy, x, gamma, mean, rstd, rows, g, dx_in, dx_out, reinterpret_cast<bf16*>(dx_bf16), \
       row_scale, rows_per_scale, dgamma, dbeta)
-  if (dy_f32) {
-    if (cols <= 512) LN_BWD(true, 4); else if (cols <= 1024) LN_BWD(true, 8); else LN_BWD(true, 12);
-  } else {
-    if (cols <= 512) LN_BWD(false, 4); else if (cols <= 1024) LN_BWD(false, 8); else LN_BWD(false, 12);
-  }
+#define LN_BWD_NV(F32)                                   \
+  do {                                                   \
+    const int nvl = (cols / 4 + 31) / 32;                \
+    if (nvl <= 1) LN_BWD(F32, 1);                        \
+    else if (nvl <= 2) LN_BWD(F32, 2);                   \
+    else if (nvl <= 3) LN_BWD(F32, 3);                   \
+    else if (nvl <= 4) LN_BWD(F32, 4);                   \
+    else if (nvl <= 6) LN_BWD(F32, 6);                   \
+    else if (nvl <= 8) LN_BWD(F32, 8);                   \
+    else LN_BWD(F32, 12);                                \
+  } while (0)
+  if (dy_f32) LN_BWD_NV(true); else LN_BWD_NV(false);
+#undef LN_BWD_NV
 #undef LN_BWD
   VTB_LAUNCH_CHECK();
   return 0;
