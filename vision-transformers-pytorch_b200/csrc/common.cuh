@@ -54,10 +54,17 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid(x) = 0.5 + 0.5 tanh(x/2): ONE MUFU op (tanh.approx, ~2^-11 rel. error) instead of ex2 + rcp;
+// the GEMM epilogues are MUFU-bound, the result is rounded to bf16 anyway.
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
-  return s * (1.f + x * (1.f - s));
+  const float s = sigmoid_f(x);
+  return s * fmaf(x, 1.f - s, 1.f);
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -162,6 +169,22 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[CW]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x16(taddr, r); }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

@@ -2,7 +2,7 @@
 //   warp 0      : TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      : UMMA issuer  (tcgen05.mma cta_group::1, M=128, N=BN, K=16; fp32 accumulators in TMEM)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue: tcgen05.ld -> registers -> fused epilogue -> 128B-swizzled smem staging ->
+//   warps 4..11 : epilogue (two warps per TMEM lane quarter, each taking half the columns): tcgen05.ld -> registers -> fused epilogue -> 128B-swizzled smem staging ->
 //                 TMA store (cp.async.bulk.tensor; cp.reduce.async.bulk .add for split-K); residual /
 //                 pre-activation tiles are TMA-prefetched into smem three sub-tiles ahead.
 //                 (Unaligned outputs fall back to direct per-thread global stores.)
@@ -162,8 +162,84 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_
   }
 }
 
+// Staged epilogue of one warp's share (CW columns) of a sub-tile row: TMEM registers -> fused math ->
+// swizzled smem staging (chunks cb..cb+3 of the 128-byte row).  ob/ab point at this thread's row.
+template <int CW>
+__device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&acc)[CW], int nc, float rs,
+                                           uint8_t* ob, uint8_t* ab, uint32_t cb, uint32_t swz, bool dual,
+                                           bool f32out) {
+  float v[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+  if (e.bias) {
+    if (nc + CW <= e.N) {
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + nc + j));
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (nc + j < e.N) v[j] += __ldg(e.bias + nc + j);
+    }
+  }
+  if (dual) {
+    // out <- bf16(u) ; out2 <- bf16(silu(float(bf16(u))))     (layer.py:191-193 under autocast)
+#pragma unroll
+    for (int j = 0; j < CW; j += 8) {
+      uint32_t pu[4], ph[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        pu[t] = pack_bf16(v[j + 2 * t], v[j + 2 * t + 1]);
+        const float2 ur = unpack_bf16(pu[t]);
+        ph[t] = pack_bf16(silu_f(ur.x), silu_f(ur.y));
+      }
+      const uint32_t off = ((cb + j / 8) ^ swz) << 4;
+      *reinterpret_cast<uint4*>(ob + off) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
+      *reinterpret_cast<uint4*>(ab + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    }
+    return;
+  }
+  if (e.epilogue == VTB_EPI_SILU_GRAD) {
+#pragma unroll
+    for (int j = 0; j < CW; j += 8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(ab + (((cb + j / 8) ^ swz) << 4));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 u = unpack_bf16(w[t]);
+        v[j + 2 * t] *= silu_grad_f(u.x);
+        v[j + 2 * t + 1] *= silu_grad_f(u.y);
+      }
+    }
+  }
+  if (e.row_scale) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] *= rs;
+  }
+  if (f32out) {
+    if (e.resid) {  // f32 residual sub-tile prefetched by TMA
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(ab + (((cb + j / 4) ^ swz) << 4));
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CW; j += 4)
+      *reinterpret_cast<float4*>(ob + (((cb + j / 4) ^ swz) << 4)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < CW; j += 8)
+      *reinterpret_cast<uint4*>(ob + (((cb + j / 8) ^ swz) << 4)) =
+          make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                     pack_bf16(v[j + 6], v[j + 7]));
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
                const __grid_constant__ CUtensorMap tma_aux, int m_tiles, int n_tiles, int k_blocks,
@@ -198,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     for (int i = 0; i < N_AUX; ++i) mbar_init(&aux_full[i], 1);
     mbar_fence_init();
@@ -293,7 +369,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     if (!epi.tma) {
-      // direct path (unaligned outputs): per-thread row stores
+      // direct path (unaligned outputs): per-thread row stores; the two warps of a lane quarter alternate chunks
+      const int ehalf = (warp - 4) >> 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mn = tile / splits;
         const int n_blk = mn % n_tiles;
@@ -303,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int m = m_blk * BM + ew * 32 + lane;
         const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = ehalf; c < BN / 32; c += 2) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= epi.N) break;  // warp-uniform
           uint32_t acc[32];
@@ -324,8 +401,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const bool dual = epi.epilogue == VTB_EPI_SILU_DUAL;
       const bool aux_in = (epi.resid != nullptr) || (epi.epilogue == VTB_EPI_SILU_GRAD);
       const bool issuer = (threadIdx.x == 128);
+      const int ehalf = (warp - 4) >> 2;           // which half of the sub-tile's columns this warp owns
+      const int CWr = SUBN / 2;                    // 32 (bf16 out) or 16 (f32 out) columns per warp
       const int row = ew * 32 + lane;              // row inside the tile == TMEM lane
       const uint32_t swz = (uint32_t)(row & 7);
+      const uint32_t cb = (uint32_t)(ehalf * 4);   // first 16-byte chunk of this warp's 64-byte share
       const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const long total_q = (long)my_tiles * n_sub;
       auto q_coords = [&](long q, int& m0, int& n0) {
@@ -358,104 +438,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int sidx = 0; sidx < n_sub; ++sidx, ++q) {
           const int n0 = n_blk * BN + sidx * SUBN;
           const bool live = n0 < epi.N;            // CTA-uniform
-          uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES;
-          uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES;
+          uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES + row * 128;
+          uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES + row * 128;
           // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const bool last = (sidx == n_sub - 1);
           if (live) {
-#pragma unroll 1
-            for (int hc = 0; hc < SUBN / 32; ++hc) {
-              uint32_t acc[32];
-              tmem_ld_32x32(t_row + sidx * SUBN + hc * 32, acc);
+            const int nc = n0 + ehalf * CWr;
+            if (f32out) {
+              uint32_t acc[16];
+              tmem_ld_cols<16>(t_row + sidx * SUBN + ehalf * 16, acc);
               tmem_ld_wait();
-              if (sidx == n_sub - 1 && hc == SUBN / 32 - 1) {
-                // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+              if (last) {  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
               }
-              float v[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * epi.alpha;
-              const int nc = n0 + hc * 32;
-              if (epi.bias) {
-                if (nc + 32 <= epi.N) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(epi.bias + nc + j));
-                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (nc + j < epi.N) v[j] += __ldg(epi.bias + nc + j);
-                }
+              if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
+              staged_row<16>(epi, acc, nc, rs, ob, ab, cb, swz, false, true);
+            } else {
+              uint32_t acc[32];
+              tmem_ld_cols<32>(t_row + sidx * SUBN + ehalf * 32, acc);
+              tmem_ld_wait();
+              if (last) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
               }
-              if (aux_in && hc == 0) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
-              if (dual) {
-                // out <- bf16(u) ; out2 <- bf16(silu(float(bf16(u))))     (layer.py:191-193 under autocast)
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint32_t pu[4], ph[4];
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    pu[t] = pack_bf16(v[j + 2 * t], v[j + 2 * t + 1]);
-                    const float2 ur = unpack_bf16(pu[t]);
-                    ph[t] = pack_bf16(silu_f(ur.x), silu_f(ur.y));
-                  }
-                  const uint32_t chunk = (uint32_t)(hc * 4 + j / 8);
-                  const uint32_t off = row * 128 + ((chunk ^ swz) << 4);
-                  *reinterpret_cast<uint4*>(ob + off) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
-                  *reinterpret_cast<uint4*>(ab + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                }
-                continue;
-              }
-              if (epi.epilogue == VTB_EPI_SILU_GRAD) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint32_t chunk = (uint32_t)(hc * 4 + j / 8);
-                  const uint4 raw = *reinterpret_cast<const uint4*>(ab + row * 128 + ((chunk ^ swz) << 4));
-                  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 u = unpack_bf16(w[t]);
-                    v[j + 2 * t] *= silu_grad_f(u.x);
-                    v[j + 2 * t + 1] *= silu_grad_f(u.y);
-                  }
-                }
-              }
-              if (epi.row_scale) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= rs;
-              }
-              if (epi.resid) {  // f32 residual sub-tile (32 columns) prefetched by TMA
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const uint32_t chunk = (uint32_t)(j / 4);
-                  const float4 t = *reinterpret_cast<const float4*>(ab + row * 128 + ((chunk ^ swz) << 4));
-                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                }
-              }
-              if (f32out) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const uint32_t chunk = (uint32_t)(j / 4);
-                  *reinterpret_cast<float4*>(ob + row * 128 + ((chunk ^ swz) << 4)) =
-                      make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint32_t chunk = (uint32_t)(hc * 4 + j / 8);
-                  *reinterpret_cast<uint4*>(ob + row * 128 + ((chunk ^ swz) << 4)) =
-                      make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                 pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-                }
-              }
+              if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
+              staged_row<32>(epi, acc, nc, rs, ob, ab, cb, swz, dual, false);
             }
           } else {
-            if (sidx == n_sub - 1) {  // dead trailing sub-tile: still release the TMEM stage
+            if (last) {  // dead trailing sub-tile: still release the TMEM stage
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -463,22 +478,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (issuer) {
             if (live) {
               const int m0 = m_blk * BM;
+              const uint32_t so = smem_u32(sOut + (q & 1) * EPI_BUF_BYTES);
               if (epi.accumulate) {
                 asm volatile(
                     "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
-                    "r"(smem_u32(ob)), "r"(n0), "r"(m0)
+                    "r"(so), "r"(n0), "r"(m0)
                     : "memory");
               } else {
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
-                             "r"(smem_u32(ob)), "r"(n0), "r"(m0)
+                             "r"(so), "r"(n0), "r"(m0)
                              : "memory");
                 if (dual)
                   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out2),
-                               "r"(smem_u32(ab)), "r"(n0), "r"(m0)
+                               "r"(smem_u32(sAux + (q % N_AUX) * EPI_BUF_BYTES)), "r"(n0), "r"(m0)
                                : "memory");
               }
             }
@@ -561,7 +577,7 @@ int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStrea
   }
   const int total = m_tiles * n_tiles * splits;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, to, to2, tx, m_tiles, n_tiles, k_blocks, splits, epi);
+  kern<<<grid, 384, C::SMEM_BYTES, stream>>>(ta, tb, to, to2, tx, m_tiles, n_tiles, k_blocks, splits, epi);
   VTB_LAUNCH_CHECK();
   return 0;
 }
@@ -653,13 +669,21 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   if (splits <= 0) {
     splits = 1;
     if (p->accumulate && !p->bias) {
-      // fill the machine: enough split-K slices for >= 2 waves' worth of tiles, >= 8 k-blocks each
+      // split-K so that the tile count fills whole waves of the persistent grid: among the split factors
+      // that leave >= 8 k-blocks per slice pick the one with the best wave efficiency (fewest slices on ties)
       const int tiles = m_tiles * n_tiles;
-      int want = (2 * g_num_sms + tiles - 1) / tiles;
       int maxs = k_blocks / 8;
       if (maxs < 1) maxs = 1;
-      splits = want < maxs ? want : maxs;
-      if (splits < 1) splits = 1;
+      if (maxs > 64) maxs = 64;
+      double best = -1.0;
+      for (int sp = 1; sp <= maxs; ++sp) {
+        const long t = (long)tiles * sp;
+        const long waves = (t + g_num_sms - 1) / g_num_sms;
+        double eff = (double)t / (double)(waves * g_num_sms);
+        if (t < g_num_sms) eff = (double)t / g_num_sms;
+        eff -= 0.002 * sp;  // reduce-add traffic grows with the split factor
+        if (eff > best + 1e-9) { best = eff; splits = sp; }
+      }
     }
   }
   if (splits > k_blocks) splits = k_blocks;
