@@ -162,11 +162,22 @@ int vtb_colsum_bf16(const void* X, int64_t M, int32_t N, int32_t ld, float* out,
 int vtb_patch_gather(const void* src, int32_t src_bf16, int32_t src_nchw, int32_t c_major,
                      int32_t B, int32_t C, int32_t H, int32_t W, int32_t p, void* dst,
                      vtb_stream_t stream);
-/* Adjoint of vtb_patch_gather for NHWC/pos-major f32 destinations: dx[b,y,x,c] (+)= dA[row, feat]
- * (dA bf16 or f32).  accumulate=0 overwrites. */
+/* Adjoint of vtb_patch_gather: dx (+)= dA[row, feat]  (dA bf16 or f32; dx f32, NHWC [b,y,x,c] or, with
+ * dst_nchw=1, NCHW [b,c,y,x]).  accumulate=0 overwrites. */
 int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major, int32_t B, int32_t C,
-                      int32_t H, int32_t W, int32_t p, float* dx, int32_t accumulate,
+                      int32_t H, int32_t W, int32_t p, float* dx, int32_t accumulate, int32_t dst_nchw,
                       vtb_stream_t stream);
+/* dst[b, w, h, :] = src[b, h, w, :]  (bf16 or f32 rows of C elements).  The Twins global attention feeds its
+ * reduce-conv with `input.transpose(1, 2).reshape(B, C, H, W)` (twins.py:70): a transposed copy that is then
+ * REINTERPRETED as NCHW — this kernel makes the copy, vtb_patch_gather(src_nchw=1) does the reinterpretation. */
+int vtb_transpose_hw(const void* src, void* dst, int32_t is_f32, int32_t B, int32_t H, int32_t W, int32_t C,
+                     vtb_stream_t stream);
+/* Depthwise 3x3 conv (padding 1, no bias) + identity on NHWC f32: y = dwconv(x, w) + x  (twins.py:25-36,
+ * PositionalEncodingGenerator; w is [C,1,3,3]) and its adjoints: dx = dwconv^T(dy, w) + dy, dw += sum dy*x. */
+int vtb_dwconv3x3_fwd(const float* x, const float* w, int32_t B, int32_t H, int32_t W, int32_t C, float* y,
+                      vtb_stream_t stream);
+int vtb_dwconv3x3_bwd(const float* x, const float* w, const float* dy, int32_t B, int32_t H, int32_t W,
+                      int32_t C, float* dx, float* dw, vtb_stream_t stream);
 /* ViT token assembly (vit.py:141-143): x[b, 0, :] = cls + pos[0];  x[b, 1+p, :] = tok[b*n + p, :] + pos[1+p, :]
  * tok f32 [B*n, D] (patch GEMM output incl. conv bias), pos f32 [n+1, D], x f32 [B, n+1, D]. */
 int vtb_vit_assemble_tokens(const float* tok, const float* cls, const float* pos, int32_t B, int32_t n,

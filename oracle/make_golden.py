@@ -48,6 +48,12 @@ CASES = {
     "halo_w7": ("halo", dict(image_size=(224, 224), n_class=10, depths=(1, 1, 1, 1), dims=(32, 32, 32, 32), dim_head=32,
                              n_heads=(1, 1, 1, 1), dim_ffs=(32, 32, 32, 32), window_size=7, halo_size=3),
                 [(1, 3, 224, 224)], dict(depths=(1, 1, 1, 1), n_heads=(1, 1, 1, 1), dim_head=32, window=7, halo=3)),
+    "twins_w2": ("twins", dict(n_class=10, depths=(1, 2, 1, 1), dims=(32, 32, 64, 64), dim_head=32, n_heads=(1, 1, 2, 2),
+                               dim_ffs=(64, 64, 128, 128), window_size=2), [(2, 3, 64, 64)],
+                 dict(depths=(1, 2, 1, 1), n_heads=(1, 1, 2, 2), dim_head=32, window=2)),
+    "twins_w7": ("twins", dict(n_class=10, depths=(1, 1, 1, 1), dims=(32, 32, 32, 32), dim_head=32, n_heads=(1, 1, 1, 1),
+                               dim_ffs=(32, 32, 32, 32), window_size=7), [(1, 3, 224, 224)],
+                 dict(depths=(1, 1, 1, 1), n_heads=(1, 1, 1, 1), dim_head=32, window=7)),
 }
 
 FULL = {
@@ -64,6 +70,8 @@ FULL = {
     "halo_t": ("halo", dict(image_size=(224, 224), n_class=1000, depths=(2, 2, 6, 2), dims=(96, 192, 384, 768),
                             dim_head=32, n_heads=(3, 6, 12, 24), dim_ffs=(384, 768, 1536, 3072), window_size=7,
                             halo_size=3)),
+    "twins_s": ("twins", dict(n_class=1000, depths=(2, 2, 10, 4), dims=(64, 128, 256, 512), dim_head=32,
+                              n_heads=(2, 4, 8, 16), dim_ffs=(256, 512, 1024, 2048), window_size=7, drop_path=0.2)),
 }
 
 
@@ -76,16 +84,22 @@ def build(ref, family, kw):
         return ref.pvt.PyramidVisionTransformer(**kw)
     if family == "halo":
         return ref.halo_transformer.HaloTransformer(**kw)
+    if family == "twins":
+        return ref.twins.TwinsSVT(**kw)
     raise KeyError(family)
 
 
-ORACLE_FWD = {"vit": R.vit_forward, "swin": R.swin_forward, "pvt": R.pvt_forward, "halo": R.halo_forward}
+ORACLE_FWD = {"vit": R.vit_forward, "swin": R.swin_forward, "pvt": R.pvt_forward, "halo": R.halo_forward,
+              "twins": R.twins_forward}
 
 
 def main():
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
     for seed, (name, (family, kw, in_shapes, okw)) in enumerate(CASES.items(), start=100):
+        if os.path.exists(os.path.join(OUT, name + ".pt")) and "--all" not in sys.argv:
+            print(f"{name}: exists, kept (pass --all to regenerate)")
+            continue
         torch.manual_seed(seed)
         model = R.randomize_(build(ref, family, kw).eval(), seed)
         g = torch.Generator().manual_seed(seed + 1000)

@@ -335,6 +335,82 @@ def halo_forward(sd, img, *, depths, n_heads, dim_head, window, halo, dp_scales=
     return linear(x, sd["classifier.2.weight"], sd["classifier.2.bias"])
 
 
+# ------------------------------------------------------------------------------------------ Twins
+def twins_scrambled_image(x):
+    """twins.py:70 as an explicit index map: the [B,H,W,C] map is copied as [B,W,H,C] and the flat
+    buffer is then read as [B,C,H,W]:  img[b,c',y',x'] = flat[(c'*H + y')*W + x'],  flat[(w*H + h)*C + c] = x[b,h,w,c]."""
+    B, H, W, C = x.shape
+    pos = torch.arange(C * H * W, device=x.device)  # flat position of img[c', y', x'] in row-major (C,H,W)
+    c = pos % C
+    h = (pos // C) % H
+    w = pos // (C * H)
+    return x[:, h, w, c].view(B, C, H, W)
+
+
+def twins_global_attention(x, sd, pre, heads, R):
+    """twins.py:58-93: q from every token; K/V from a k=s=R conv over the scrambled image (no LayerNorm)."""
+    B, H, W, C = x.shape
+    q = rearrange(linear(x, sd[pre + "linear_q.weight"]), "b h w (n d) -> b n (h w) d", n=heads)
+    if R > 1:
+        img = twins_scrambled_image(x)
+        a = rearrange(img, "b c (h py) (w px) -> b (h w) c py px", py=R, px=R)
+        kvin = torch.einsum("bncyx,ocyx->bno", a, sd[pre + "reduce_conv.weight"]) + sd[pre + "reduce_conv.bias"]
+    else:
+        kvin = x.reshape(B, H * W, C)
+    k, v = rearrange(linear(kvin, sd[pre + "linear_kv.weight"]), "b n (s h d) -> s b h n d", s=2, h=heads)
+    o = rearrange(softmax_attention(q, k, v), "b n (h w) d -> b h w (n d)", h=H)
+    return linear(o, sd[pre + "linear.weight"], sd[pre + "linear.bias"])
+
+
+def twins_local_attention(x, sd, pre, heads, dh, W):
+    """twins.py:109-152: plain window attention (no shift, bias or mask)."""
+    B, Hs, Ws, _ = x.shape
+    qkv = linear(x, sd[pre + "weight.weight"], sd[pre + "weight.bias"])
+    q, k, v = rearrange(qkv, "b (wy ty) (wx tx) (s h d) -> s b (wy wx) h (ty tx) d", ty=W, tx=W, s=3, h=heads)
+    o = softmax_attention(q, k, v)
+    o = rearrange(o, "b (wy wx) h (ty tx) d -> b (wy ty) (wx tx) (h d)", wy=Hs // W, ty=W)
+    return linear(o, sd[pre + "linear.weight"], sd[pre + "linear.bias"])
+
+
+def peg(x, w):
+    """twins.py:31-36: depthwise 3x3 conv (zero padding 1, no bias) + identity, NHWC."""
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+    B, H, W, C = x.shape
+    out = x
+    for ky in range(3):
+        for kx in range(3):
+            out = out + xp[:, ky:ky + H, kx:kx + W, :] * w[:, 0, ky, kx]
+    return out
+
+
+def twins_forward(sd, img, *, depths, n_heads, dim_head, window, dp_scales=None):
+    """TwinsSVT.forward (twins.py:347-356)."""
+    dps = DropPathScales(dp_scales)
+    x = img.permute(0, 2, 3, 1)
+    for st in range(4):
+        pre = f"block{st + 1}."
+        x = patchify(x, (4, 2, 2, 2)[st])
+        x = linear(x, sd[pre + "0.linear.weight"], sd[pre + "0.linear.bias"])
+        x = layer_norm(x, sd[pre + "0.norm.weight"], sd[pre + "0.norm.bias"], 1e-5)
+        idx = 1
+        for i in range(depths[st]):
+            lp = f"{pre}{idx}."
+            ln = lambda t, nm: layer_norm(t, sd[lp + nm + ".weight"], sd[lp + nm + ".bias"], 1e-6)  # noqa: E731
+            x = x + _dp(twins_local_attention(ln(x, "norm_attn_local"), sd, lp + "attn_local.", n_heads[st], dim_head,
+                                              window), dps.next())
+            x = x + _dp(ffn(ln(x, "norm_ff_local"), sd, lp + "ff_local."), dps.next())
+            x = x + _dp(twins_global_attention(ln(x, "norm_attn_global"), sd, lp + "attn_global.", n_heads[st], window),
+                        dps.next())
+            x = x + _dp(ffn(ln(x, "norm_ff_global"), sd, lp + "ff_global."), dps.next())
+            idx += 1
+            if i == 0:
+                x = peg(x, sd[f"{pre}{idx}.proj.weight"])
+                idx += 1
+    x = layer_norm(x, sd["final_linear.0.weight"], sd["final_linear.0.bias"], 1e-5)
+    x = x.mean((1, 2))
+    return linear(x, sd["classifier.2.weight"], sd["classifier.2.bias"])
+
+
 # ------------------------------------------------------------------------------------------ helpers
 def randomize_(module, seed):
     """Seeded re-randomisation of every parameter so zero-initialised tables (rel_pos) and unit LayerNorm
@@ -350,6 +426,8 @@ def randomize_(module, seed):
                     p.copy_(0.1 * torch.randn(p.shape, generator=g))
             elif "rel_pos" in name:
                 p.copy_(0.5 * torch.randn(p.shape, generator=g))
+            elif name.endswith("proj.weight") and p.dim() == 4 and p.shape[1] == 1:  # PEG depthwise kernel
+                p.copy_(0.2 * torch.randn(p.shape, generator=g))
             else:
                 p.copy_(0.02 * torch.randn(p.shape, generator=g))
     return module

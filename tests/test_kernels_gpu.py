@@ -380,3 +380,38 @@ def test_pool_fill_rowsum_silu(ops):
     assert rel(ops.silu_fwd(xs.detach()), ys) < 1e-5
     ys.backward(torch.ones_like(ys))
     assert rel(ops.silu_bwd(xs.detach(), torch.ones_like(xs)), xs.grad) < 1e-4
+
+
+def test_transpose_hw_and_nchw_scatter(ops):
+    g = torch.Generator(device="cuda").manual_seed(15)
+    B, H, W, C = 2, 6, 10, 8
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    assert torch.equal(ops.transpose_hw(x, B, H, W, C), x.transpose(1, 2).contiguous())
+    xb = x.to(BF16)
+    assert torch.equal(ops.transpose_hw(xb, B, H, W, C), xb.transpose(1, 2).contiguous())
+    # Twins scramble (twins.py:70): transposed copy read as NCHW, gathered for a k=s=2 conv
+    from oracle import restate as R
+    from einops import rearrange
+
+    img = R.twins_scrambled_image(x)  # [B, C, H, W]
+    got = ops.patch_gather(ops.transpose_hw(x, B, H, W, C), nchw=True, c_major=True, B=B, Cc=C, H=H, W=W, p=2)
+    want = rearrange(img, "b c (h py) (w px) -> (b h w) (c py px)", py=2, px=2)
+    assert torch.equal(got, want.to(BF16))
+    back = ops.patch_scatter(want.contiguous(), c_major=True, B=B, Cc=C, H=H, W=W, p=2, dst_nchw=True)
+    assert torch.equal(back, img)
+
+
+def test_dwconv3x3_peg(ops):
+    from oracle import restate as R
+
+    g = torch.Generator(device="cuda").manual_seed(16)
+    B, H, W, C = 2, 7, 9, 32
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).requires_grad_(True)
+    w = (0.3 * torch.randn(C, 1, 3, 3, device="cuda", generator=g)).requires_grad_(True)
+    y = ops.dwconv3x3_fwd(x.detach(), w.detach())
+    want = R.peg(x, w)
+    assert rel(y, want) < 1e-6
+    dy = torch.randn(B, H, W, C, device="cuda", generator=g)
+    want.backward(dy)
+    dx, dw = ops.dwconv3x3_bwd(x.detach(), w.detach(), dy)
+    assert rel(dx, x.grad) < 1e-6 and rel(dw, w.grad) < 1e-5

@@ -30,15 +30,17 @@ def cos(a, b):
 
 def build(fx):
     import models
+    import models.twins
 
     ctor = {"vit": models.VisionTransformer, "swin": models.SwinTransformer, "pvt": models.PyramidVisionTransformer,
-            "halo": models.HaloTransformer}[fx["family"]]
+            "halo": models.HaloTransformer, "twins": models.twins.TwinsSVT}[fx["family"]]
     m = ctor(**fx["ctor"])
     m.load_state_dict(fx["state_dict"], strict=True)
     return m.cuda()
 
 
-@pytest.mark.parametrize("name", ["vit_tiny", "vit_multicrop", "swin_w2", "swin_w7", "pvt_tiny", "halo_w2", "halo_w7"])
+@pytest.mark.parametrize("name", ["vit_tiny", "vit_multicrop", "swin_w2", "swin_w7", "pvt_tiny", "halo_w2", "halo_w7",
+                                  "twins_w2", "twins_w7"])
 def test_model_matches_reference_golden(name):
     fx = load_golden(name)
     model = build(fx).eval()

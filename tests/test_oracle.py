@@ -6,8 +6,9 @@ import torch
 from conftest import load_golden
 from oracle import ref_loader, restate as R
 
-CASES = ["vit_tiny", "vit_multicrop", "swin_w2", "swin_w7", "pvt_tiny", "halo_w2", "halo_w7"]
-FWD = {"vit": R.vit_forward, "swin": R.swin_forward, "pvt": R.pvt_forward, "halo": R.halo_forward}
+CASES = ["vit_tiny", "vit_multicrop", "swin_w2", "swin_w7", "pvt_tiny", "halo_w2", "halo_w7", "twins_w2", "twins_w7"]
+FWD = {"vit": R.vit_forward, "swin": R.swin_forward, "pvt": R.pvt_forward, "halo": R.halo_forward,
+       "twins": R.twins_forward}
 
 
 def rel(a, b):

@@ -10,6 +10,7 @@ import torch
 from conftest import GOLDEN, load_golden
 
 import models
+import models.twins
 from models.halo_transformer import halo_pos
 from models.swin_transformer import window_tables
 from oracle import restate as R
@@ -25,6 +26,8 @@ FULL = {
                                                          (512, 1024, 1280, 2048), (8, 4, 2, 1)),
     "halo_t": lambda: models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
                                              (384, 768, 1536, 3072), window_size=7, halo_size=3),
+    "twins_s": lambda: models.twins.TwinsSVT(1000, (2, 2, 10, 4), (64, 128, 256, 512), 32, (2, 4, 8, 16),
+                                             (256, 512, 1024, 2048), 7, drop_path=0.2),
 }
 
 
@@ -62,6 +65,7 @@ def test_swin_tables_equal_oracle_tables():
 @pytest.mark.parametrize("name,ctor", [
     ("vit_tiny", models.VisionTransformer), ("swin_w2", models.SwinTransformer), ("swin_w7", models.SwinTransformer),
     ("pvt_tiny", models.PyramidVisionTransformer), ("halo_w2", models.HaloTransformer), ("halo_w7", models.HaloTransformer),
+    ("twins_w2", models.twins.TwinsSVT), ("twins_w7", models.twins.TwinsSVT),
 ])
 def test_reference_checkpoints_load_strictly(name, ctor):
     fx = load_golden(name)
@@ -78,6 +82,9 @@ def test_drop_path_schedules():
     assert abs(v.layers[-1].drop_path.p - 0.1) < 1e-7 and v.layers[0].drop_path.p == 0
     v.set_drop_path(0.2)
     assert abs(v.layers[-1].drop_path.p - 0.2) < 1e-7
+    t = FULL["twins_s"]()
+    trates = [l.drop_path.p for st in t.blocks() for l in st if hasattr(l, "drop_path")]
+    assert len(trates) == 18 and trates[0] == 0 and abs(trates[-1] - 0.2 * 17 / 18) < 1e-12
     p = FULL["pvt_small"]()
     p.set_drop_path(0.1)
     assert abs(p.block4[-1].drop_path.p - 0.1) < 1e-7

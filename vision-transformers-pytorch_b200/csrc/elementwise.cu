@@ -168,7 +168,7 @@ __global__ void patch_gather_kernel(const T* __restrict__ src, int src_nchw, int
 
 template <typename T>
 __global__ void patch_scatter_kernel(const T* __restrict__ dA, int c_major, PatchGeom g,
-                                     float* __restrict__ dx, int accumulate) {
+                                     float* __restrict__ dx, int accumulate, int dst_nchw) {
   const long total = (long)g.B * g.Ho * g.Wo * g.F;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ff = (int)(i % g.F);
@@ -181,7 +181,8 @@ __global__ void patch_scatter_kernel(const T* __restrict__ dA, int c_major, Patc
     if (c_major) { c = ff / (g.p * g.p); const int r = ff - c * g.p * g.p; py = r / g.p; px = r - py * g.p; }
     else { const int s = ff / g.C; c = ff - s * g.C; py = s / g.p; px = s - py * g.p; }
     const int y = by * g.p + py, x = bx * g.p + px;
-    const long off = (((long)b * g.H + y) * g.W + x) * g.C + c;  // NHWC destination
+    const long off = dst_nchw ? (((long)b * g.C + c) * g.H + y) * g.W + x
+                              : (((long)b * g.H + y) * g.W + x) * g.C + c;
     const float v = ldf<T>(dA + i);
     dx[off] = accumulate ? dx[off] + v : v;  // patches do not overlap: no atomics needed
   }
@@ -201,6 +202,109 @@ __global__ void vit_assemble_kernel(const float* __restrict__ tok, const float* 
                               : reinterpret_cast<const float4*>(tok)[(b * n + (t - 1)) * D4 + c];
     reinterpret_cast<float4*>(x)[i] = make_float4(s.x + p.x, s.y + p.y, s.z + p.z, s.w + p.w);
   }
+}
+
+// dst[b, w, h, :] = src[b, h, w, :] in 8-byte units (4 bf16 or 2 f32)
+__global__ void transpose_hw_kernel(const uint2* __restrict__ src, uint2* __restrict__ dst, int B, int H, int W,
+                                    int C8) {
+  const long total = (long)B * H * W * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long t = i / C8;
+    const int h = (int)(t % H); t /= H;
+    const int w = (int)(t % W);
+    const long b = t / W;
+    dst[i] = src[((b * H + h) * W + w) * C8 + c];
+  }
+}
+
+// y[b,y,x,c] = x[b,y,x,c] + sum_{ky,kx} w[c,ky,kx] x[b,y+ky-1,x+kx-1,c]; one thread per float4 of channels
+__global__ void dwconv3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int B, int H,
+                                     int W, int C, float* __restrict__ y) {
+  const int C4 = C >> 2;
+  const long total = (long)B * H * W * C4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long t = i / C4;
+    const int px = (int)(t % W); t /= W;
+    const int py = (int)(t % H);
+    const long b = t / H;
+    float4 acc = reinterpret_cast<const float4*>(x)[i];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float4 v = reinterpret_cast<const float4*>(x)[((b * H + yy) * W + xx) * C4 + c4];
+        const int c = c4 * 4;
+        acc.x += __ldg(w + (c + 0) * 9 + ky * 3 + kx) * v.x;
+        acc.y += __ldg(w + (c + 1) * 9 + ky * 3 + kx) * v.y;
+        acc.z += __ldg(w + (c + 2) * 9 + ky * 3 + kx) * v.z;
+        acc.w += __ldg(w + (c + 3) * 9 + ky * 3 + kx) * v.w;
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = acc;
+  }
+}
+
+// dx = dy + sum_k w[c,k] dy[shifted by -k]; dw[c,k] += sum dy[b,y,x,c] x[b,y+ky-1,x+kx-1,c].
+// blockDim = (C4 lanes, PIX pixels): each thread keeps 9x4 dw partials over its pixels, CTA-reduces in smem.
+constexpr int DW_PIX = 8;
+__global__ void dwconv3x3_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ dy, int B, int H, int W, int C,
+                                     float* __restrict__ dx, float* __restrict__ dw, long pix_per_block) {
+  extern __shared__ float s_dw[];  // [C][9]
+  const int C4 = C >> 2;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C * 9; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
+  __syncthreads();
+  const long npix = (long)B * H * W;
+  const long p0 = (long)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+    float part[9][4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) part[k][0] = part[k][1] = part[k][2] = part[k][3] = 0.f;
+    const int c = c4 * 4;
+    for (long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      const int px = (int)(p % W);
+      const long t = p / W;
+      const int py = (int)(t % H);
+      const long b = t / H;
+      const float4 g = reinterpret_cast<const float4*>(dy)[p * C4 + c4];
+      float4 acc = g;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int k = ky * 3 + kx;
+          // forward tap: y[p] += w[k] x[p + (ky-1, kx-1)]  => dw[k] += dy[p] x[p + off]; dx[p] += w[k] dy[p - off]
+          const int yy = py + ky - 1, xx = px + kx - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float4 v = reinterpret_cast<const float4*>(x)[((b * H + yy) * W + xx) * C4 + c4];
+            part[k][0] += g.x * v.x; part[k][1] += g.y * v.y; part[k][2] += g.z * v.z; part[k][3] += g.w * v.w;
+          }
+          const int y2 = py - (ky - 1), x2 = px - (kx - 1);
+          if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            const float4 d = reinterpret_cast<const float4*>(dy)[((b * H + y2) * W + x2) * C4 + c4];
+            acc.x += __ldg(w + (c + 0) * 9 + k) * d.x;
+            acc.y += __ldg(w + (c + 1) * 9 + k) * d.y;
+            acc.z += __ldg(w + (c + 2) * 9 + k) * d.z;
+            acc.w += __ldg(w + (c + 3) * 9 + k) * d.w;
+          }
+        }
+      }
+      reinterpret_cast<float4*>(dx)[p * C4 + c4] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&s_dw[(c + e) * 9 + k], part[k][e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C * 9; i += blockDim.x * blockDim.y)
+    if (s_dw[i] != 0.f) atomicAdd(dw + i, s_dw[i]);
 }
 
 __global__ void fill_rows_kernel(float* __restrict__ x, long stride, int groups, int cols,
@@ -328,16 +432,16 @@ extern "C" int vtb_patch_gather(const void* src, int32_t src_bf16, int32_t src_n
 
 extern "C" int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major, int32_t B, int32_t C,
                                  int32_t H, int32_t W, int32_t p, float* dx, int32_t accumulate,
-                                 vtb_stream_t s) {
+                                 int32_t dst_nchw, vtb_stream_t s) {
   PatchGeom g;
   int rc = patch_geom("vtb_patch_scatter", B, C, H, W, p, &g);
   if (rc) return rc;
   VTB_CHECK(dA && dx, -1, "vtb_patch_scatter: null pointer");
   const long total = (long)B * g.Ho * g.Wo * g.F;
   if (dA_f32)
-    patch_scatter_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const float*)dA, c_major, g, dx, accumulate);
+    patch_scatter_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const float*)dA, c_major, g, dx, accumulate, dst_nchw);
   else
-    patch_scatter_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dA, c_major, g, dx, accumulate);
+    patch_scatter_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)dA, c_major, g, dx, accumulate, dst_nchw);
   VTB_LAUNCH_CHECK();
   return 0;
 }
@@ -347,6 +451,44 @@ extern "C" int vtb_vit_assemble_tokens(const float* tok, const float* cls, const
   VTB_CHECK(tok && cls && pos && x && B > 0 && n > 0 && D > 0 && D % 4 == 0, -1,
             "vtb_vit_assemble_tokens: bad args");
   vit_assemble_kernel<<<grid_for((long)B * (n + 1) * (D / 4), 256, 2), 256, 0, (cudaStream_t)s>>>(tok, cls, pos, B, n, D, x);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_transpose_hw(const void* src, void* dst, int32_t is_f32, int32_t B, int32_t H, int32_t W,
+                                int32_t C, vtb_stream_t s) {
+  VTB_CHECK(src && dst && B > 0 && H > 0 && W > 0 && C > 0, -1, "vtb_transpose_hw: bad args");
+  const int per8 = is_f32 ? 2 : 4;
+  VTB_CHECK(C % per8 == 0 && ((uintptr_t)src & 7) == 0 && ((uintptr_t)dst & 7) == 0, -1,
+            "vtb_transpose_hw: rows must be multiples of 8 bytes");
+  const int C8 = C / per8;
+  transpose_hw_kernel<<<grid_for((long)B * H * W * C8, 256, 2), 256, 0, (cudaStream_t)s>>>(
+      (const uint2*)src, (uint2*)dst, B, H, W, C8);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_dwconv3x3_fwd(const float* x, const float* w, int32_t B, int32_t H, int32_t W, int32_t C,
+                                 float* y, vtb_stream_t s) {
+  VTB_CHECK(x && w && y && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, -1, "vtb_dwconv3x3_fwd: bad args");
+  dwconv3x3_fwd_kernel<<<grid_for((long)B * H * W * (C / 4), 256, 2), 256, 0, (cudaStream_t)s>>>(x, w, B, H, W, C, y);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_dwconv3x3_bwd(const float* x, const float* w, const float* dy, int32_t B, int32_t H,
+                                 int32_t W, int32_t C, float* dx, float* dw, vtb_stream_t s) {
+  VTB_CHECK(x && w && dy && dx && dw && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, -1,
+            "vtb_dwconv3x3_bwd: bad args");
+  const long npix = (long)B * H * W;
+  int bx = C / 4 < 32 ? C / 4 : 32;
+  dim3 block(bx, DW_PIX);
+  long blocks = (long)(vtb_num_sms() > 0 ? vtb_num_sms() : 148) * 8;
+  long ppb = (npix + blocks - 1) / blocks;
+  if (ppb < DW_PIX) ppb = DW_PIX;
+  blocks = (npix + ppb - 1) / ppb;
+  dwconv3x3_bwd_kernel<<<(unsigned)blocks, block, (size_t)C * 9 * sizeof(float), (cudaStream_t)s>>>(
+      x, w, dy, B, H, W, C, dx, dw, ppb);
   VTB_LAUNCH_CHECK();
   return 0;
 }

@@ -4,6 +4,7 @@ the transformer-block path and is not re-implemented here."""
 from .halo_transformer import HaloTransformer
 from .pvt import PyramidVisionTransformer
 from .swin_transformer import SwinTransformer
+from .twins import TwinsSVT  # noqa: F401  (not exported by the reference's __init__, registered as "twins_svt")
 from .vit import DINOHead, FusedLinear, VisionTransformer, dino
 
 __all__ = ["HaloTransformer", "PyramidVisionTransformer", "SwinTransformer", "VisionTransformer",

@@ -143,16 +143,22 @@ class AttnBranchFn(Function):
 
 # ------------------------------------------------------------------- spatial-reduction attention branch
 class SRABranchFn(Function):
-    """PVT attention branch (pvt.py:32-69 inside :97): q from LN(x); K/V from LN(x) reduced by a k=s=R
-    conv (+LN) when R > 1; global attention with Nq != Nkv; output projection; DropPath; residual.
+    """Spatial-reduction attention branch: q from LN(x); K/V from LN(x) reduced by a k=s=R conv when R > 1;
+    global attention with Nq != Nkv; output projection; DropPath; residual.
+      PVT   (pvt.py:32-69 inside :97)    : reduce conv -> LayerNorm -> kv            cfg: kv_norm=True
+      Twins (twins.py:58-93 inside :195) : reduce conv on `input.transpose(1,2).reshape(B,C,H,W)` (a transposed
+                                           copy REINTERPRETED as NCHW, twins.py:70) -> kv   cfg: scramble=True
     """
 
     @staticmethod
     @_fwd
     def forward(ctx, x, dp_scale, eps, rows_per_sample, cfg, ln_w, ln_b, w_q, w_kv, w_o, b_o, w_r, b_r,
                 rn_w, rn_b):
-        B, N, C = x.shape
+        shape = x.shape
+        B, C = shape[0], shape[-1]
+        N = x.numel() // (B * C)
         heads, R, Hs, Ws = cfg["heads"], cfg["reduction"], cfg["height"], cfg["width"]
+        kv_norm, scramble = cfg.get("kv_norm", True), cfg.get("scramble", False)
         dh = C // heads
         x2 = _c(x).view(-1, C)
         y, mean, rstd = ops.layernorm_fwd(x2, ln_w, ln_b, eps)
@@ -161,11 +167,19 @@ class SRABranchFn(Function):
         red_stash = None
         if R > 1:
             wrb = ops.cast_bf16(_c(w_r).view(C, -1))
-            A = ops.patch_gather(y, nchw=False, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R)
-            red = ops.gemm(A, wrb, out_dtype=F32, bias=b_r)
-            kvin, rmean, rrstd = ops.layernorm_fwd(red, rn_w, rn_b, eps)
+            if scramble:
+                yt = ops.transpose_hw(y, B, Hs, Ws, C)  # [B,W,H,C] memory, read below as if it were [B,C,H,W]
+                A = ops.patch_gather(yt, nchw=True, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R)
+            else:
+                A = ops.patch_gather(y, nchw=False, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R)
             nkv = (Hs // R) * (Ws // R)
-            red_stash = (A, wrb, red, rmean, rrstd)
+            if kv_norm:
+                red = ops.gemm(A, wrb, out_dtype=F32, bias=b_r)
+                kvin, rmean, rrstd = ops.layernorm_fwd(red, rn_w, rn_b, eps)
+                red_stash = (A, wrb, red, rmean, rrstd)
+            else:
+                kvin = ops.gemm(A, wrb, bias=b_r)
+                red_stash = (A, wrb, None, None, None)
         else:
             kvin, nkv = y, N
         kv = ops.gemm(kvin, wkvb)
@@ -175,14 +189,15 @@ class SRABranchFn(Function):
                        rows_per_scale=rows_per_sample)
         ctx.save_for_backward(x2, ln_w, mean, rstd, rn_w)
         ctx.stash = (y, q, kv, kvin, o, lse, wqb, wkvb, wob, dp_scale, rows_per_sample, spec, red_stash,
-                     (B, N, C, R, Hs, Ws), w_r.shape if w_r is not None else None)
-        return out.view(B, N, C)
+                     (B, N, C, R, Hs, Ws), w_r.shape if w_r is not None else None, kv_norm, scramble)
+        return out.view(shape)
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         x2, ln_w, mean, rstd, rn_w = ctx.saved_tensors
-        (y, q, kv, kvin, o, lse, wqb, wkvb, wob, dp_scale, rps, spec, red_stash, dims, wr_shape) = ctx.stash
+        (y, q, kv, kvin, o, lse, wqb, wkvb, wob, dp_scale, rps, spec, red_stash, dims, wr_shape, kv_norm,
+         scramble) = ctx.stash
         B, N, C, R, Hs, Ws = dims
         d2 = _c(dout).view(-1, C)
         g = ops.scale_cast_bf16(d2, dp_scale, rps)
@@ -198,11 +213,18 @@ class SRABranchFn(Function):
         if R > 1:
             A, wrb, red, rmean, rrstd = red_stash
             dkvin = _dgrad(dkv, wkvb)
-            _, dred, drn_w, drn_b = ops.layernorm_bwd(dkvin, red, rn_w, rmean, rrstd, want_bf16=True)
+            if kv_norm:
+                _, dred, drn_w, drn_b = ops.layernorm_bwd(dkvin, red, rn_w, rmean, rrstd, want_bf16=True)
+            else:
+                dred = dkvin
             db_r = ops.colsum(dred)
             dw_r = _wgrad(dred, A).view(wr_shape)
             dA = _dgrad(dred, wrb)
-            dy_kv = ops.patch_scatter(dA, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R).view(-1, C)
+            if scramble:
+                dflat = ops.patch_scatter(dA, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R, dst_nchw=True)
+                dy_kv = ops.transpose_hw(dflat, B, Ws, Hs, C).view(-1, C)  # [B,W,H,C] -> [B,H,W,C]
+            else:
+                dy_kv = ops.patch_scatter(dA, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R).view(-1, C)
             dy = _dgrad(dq, wqb, out_dtype=F32, resid=dy_kv)
         else:
             dy_kv = _dgrad(dkv, wkvb, out_dtype=F32)
@@ -210,6 +232,24 @@ class SRABranchFn(Function):
         dx, _, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2)
         return (dx.view(dout.shape), None, None, None, None, dg, dbeta, dw_q, dw_kv, dw_o, db_o, dw_r,
                 db_r, drn_w, drn_b)
+
+
+class PEGFn(Function):
+    """Positional-encoding generator: depthwise 3x3 conv + identity on NHWC f32 (twins.py:25-36)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, w):
+        x, w = _c(x), _c(w)
+        ctx.save_for_backward(x, w)
+        return ops.dwconv3x3_fwd(x, w)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw = ops.dwconv3x3_bwd(x, w, _c(dy))
+        return dx, dw
 
 
 # ----------------------------------------------------------------------------------------- small pieces

@@ -324,15 +324,15 @@ def patch_gather(src, *, nchw, c_major, B, Cc, H, W, p):
     return dst
 
 
-def patch_scatter(dA, *, c_major, B, Cc, H, W, p, dx=None, accumulate=False):
+def patch_scatter(dA, *, c_major, B, Cc, H, W, p, dx=None, accumulate=False, dst_nchw=False):
     lib = _l.get()
     if not dA.is_contiguous() or dA.dtype not in (F32, BF16):
         raise ValueError("vtb200.patch_scatter: contiguous f32/bf16 expected")
     if dx is None:
-        dx = torch.empty((B, H, W, Cc), dtype=F32, device=dA.device)
+        dx = torch.empty((B, Cc, H, W) if dst_nchw else (B, H, W, Cc), dtype=F32, device=dA.device)
     with _prof("patch_scatter"):
         _l.check(lib.vtb_patch_scatter(_p(dA), int(dA.dtype == F32), int(c_major), B, Cc, H, W, p, _p(dx),
-                                       int(accumulate), _stream()), lib)
+                                       int(accumulate), int(dst_nchw), _stream()), lib)
     _count()
     return dx
 
@@ -395,3 +395,36 @@ def silu_bwd(x, dy):
         _l.check(lib.vtb_silu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _stream()), lib)
     _count()
     return dx
+
+
+def transpose_hw(x, B, H, W, Cc):
+    """[B,H,W,C] -> [B,W,H,C] copy (bf16 or f32)."""
+    lib = _l.get()
+    if not x.is_contiguous() or x.dtype not in (F32, BF16):
+        raise ValueError("vtb200.transpose_hw: contiguous f32/bf16 expected")
+    dst = torch.empty((B, W, H, Cc), dtype=x.dtype, device=x.device)
+    with _prof("transpose_hw"):
+        _l.check(lib.vtb_transpose_hw(_p(x), _p(dst), int(x.dtype == F32), B, H, W, Cc, _stream()), lib)
+    _count()
+    return dst
+
+
+def dwconv3x3_fwd(x, w):
+    lib = _l.get()
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    with _prof("dwconv3x3_fwd"):
+        _l.check(lib.vtb_dwconv3x3_fwd(_p(x), _p(w), B, H, W, Cc, _p(y), _stream()), lib)
+    _count()
+    return y
+
+
+def dwconv3x3_bwd(x, w, dy):
+    lib = _l.get()
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    dw = torch.zeros((Cc, 1, 3, 3), dtype=F32, device=x.device)
+    with _prof("dwconv3x3_bwd"):
+        _l.check(lib.vtb_dwconv3x3_bwd(_p(x), _p(w), _p(dy), B, H, W, Cc, _p(dx), _p(dw), _stream()), lib)
+    _count()
+    return dx, dw
