@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--nvtx-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -209,7 +210,10 @@ def main():
     model = build_model(args.workload).to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
     net, reducer = model, None
+    use_graph = not args.no_graph and not args.nvtx_step
     if world > 1:
+        if use_graph:
+            args.reducer = "flat"  # the captured graph holds fwd+bwd; gradients are all-reduced right after replay
         if args.reducer == "ddp":
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
                                                             gradient_as_bucket_view=True, bucket_cap_mb=64)
@@ -218,11 +222,23 @@ def main():
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
 
-    def step(x, y):
+    def fwd_bwd(x, y):
         for p in params:
             p.grad = None
         loss = torch.nn.functional.cross_entropy(net(x), y)
         loss.backward()
+        return loss
+
+    graphed = None
+
+    def step(x, y):
+        if graphed is not None:
+            if x is not x_dev:
+                x_dev.copy_(x, non_blocking=True)
+                y_dev.copy_(y, non_blocking=True)
+            loss = graphed.replay()
+        else:
+            loss = fwd_bwd(x, y)
         if reducer is not None:
             reducer.reduce()
         return loss
@@ -233,6 +249,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident timing (`value`)
+    if use_graph:
+        from vtb200.graph import GraphedStep
+
+        graphed = GraphedStep(fwd_bwd, (x_dev, y_dev), warmup=2)
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
@@ -250,8 +270,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         step(x_dev, y_dev)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # host time to ISSUE a step (no sync)
     e1.record()
     barrier()
     ms = vd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
@@ -260,9 +282,14 @@ def main():
     value = world * B / (ms * 1e-3)
 
     # ---------------------------------------------------------------- live roofline pass (dominant kernel: GEMM)
+    # one EAGER step with CUDA events around every library call (also counts the launches a replayed graph contains)
     ops.PROFILE = []
-    step(x_dev, y_dev)
+    l1 = ops.LAUNCHES
+    fwd_bwd(x_dev, y_dev)
     torch.cuda.synchronize()
+    launches_per_step = ops.LAUNCHES - l1
+    if use_graph:
+        launches = launches_per_step * args.steps
     prof, ops.PROFILE = ops.PROFILE, None
     gemm = [(n, f, a.elapsed_time(b)) for n, f, a, b in prof if n.startswith("gemm_")]
     gemm_ms = sum(t for _, _, t in gemm)
@@ -350,7 +377,9 @@ def main():
                 "config": {"workload": args.workload, "desc": wl["desc"], "batch_per_gpu": B, "global_batch": B * world,
                            "parallelism": f"dp{world}", "reducer": args.reducer if world > 1 else "none",
                            "l2": "inputs_exceed_l2 (154 MB batch + multi-GB activations per step >> 126 MB L2)",
-                           "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric"},
+                           "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric",
+                           "execution": "CUDA graph replay of the captured step" if use_graph else "eager launches",
+                           "host_issue_ms_per_step": host_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

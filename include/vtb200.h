@@ -25,6 +25,9 @@ const char* vtb_last_error(void);
 int vtb_version(void);
 /* Resolve cuTensorMapEncodeTiled through the runtime, query SM count.  Idempotent. */
 int vtb_init(void);
+/* Runtime switches.  "gemm_cluster" (0/1): run the GEMM as CTA pairs (thread-block clusters of 2) that
+ * TMA-multicast the shared B tile into both CTAs' shared memory.  Default 0: measured neutral on B200. */
+int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 (TMA -> smem -> UMMA -> TMEM -> epilogue):  C[M,N] = alpha * sum_k A(m,k) B(n,k)

@@ -54,6 +54,44 @@ def test_gemm_layouts(ops, M, N, K, layout):
     assert rel(got16.float(), want) < 4e-3
 
 
+@pytest.mark.parametrize("layout", ["nt", "nn", "tt", "tn"])
+def test_gemm_cluster_pairs_multicast(ops, layout):
+    """>= 148 tiles -> CTA pairs with TMA-multicast B; odd number of row tiles -> one phantom tile per group."""
+    from vtb200 import lib
+
+    lib.set_option("gemm_cluster", 1)
+    try:
+        _cluster_case(ops, lib, layout)
+    finally:
+        lib.set_option("gemm_cluster", 0)
+
+
+def _cluster_case(ops, lib, layout):
+    g = torch.Generator(device="cuda").manual_seed(21)
+    M, N, K = 128 * 65 - 24, 1024 - 8, 192
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g) * 0.2)
+    want = A.float() @ B.float().t()
+    a_mn, b_mn = layout[0] == "t", layout[1] == "n"
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=F32)
+    assert rel(got, want) < 1e-5
+    if layout == "nt":
+        bias = torch.randn(N, device="cuda", generator=g)
+        resid = torch.randn(M, N, device="cuda", generator=g)
+        got = ops.gemm(a, b, out_dtype=F32, bias=bias, resid=resid)
+        assert rel(got, want + bias + resid) < 1e-5
+        u = torch.empty(M, N, dtype=BF16, device="cuda")
+        h = torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(a, b, out=u, out2=h, bias=bias, epilogue=lib.EPI_SILU_DUAL)
+        assert rel(u.float(), want + bias) < 4e-3
+        assert rel(h.float(), torch.nn.functional.silu(u.float())) < 4e-3
+    if layout in ("tt", "tn"):  # split-K reduce-add through the pair path
+        got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=F32, accumulate=True, splits=2)
+        assert rel(got, want) < 1e-5
+
+
 def test_gemm_strided_views(ops):
     """Operands that are column slices of wider buffers (q/k/v inside the fused qkv buffer)."""
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; timeout ${TMO:-600} "$@" > gpurun_out/$name.log 2>&1; echo "$name exit=$?" | tee -a gpurun_out/summary.txt; tail -n ${TAILN:-8} gpurun_out/$name.log; }
+: > gpurun_out/summary.txt
+run t_gemm python -m pytest tests/test_kernels_gpu.py -q -m gpu --no-header -p no:cacheprovider -k "gemm"
+run t_models python -m pytest tests/test_models_gpu.py -q -m gpu --no-header -p no:cacheprovider
+TAILN=2 run bench_vit python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e
+VTB_GEMM_CLUSTER=0 TAILN=2 run bench_vit_nocl python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e
+TAILN=2 run bench_swin python bench.py --steps 5 --warmup 3 --no-cpu-baseline --workload swin_s --no-e2e

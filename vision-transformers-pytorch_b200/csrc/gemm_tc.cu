@@ -11,6 +11,8 @@
 // no transposes are materialised).  See include/vtb200.h for the contract.
 #include "common.cuh"
 #include "../../include/vtb200.h"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -27,6 +29,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
+bool g_use_clusters = false;  // CTA-pair TMA multicast of B: measured neutral on B200 (L2 dedups), so opt-in
+                              // (vtb_set_option("gemm_cluster", 1) or VTB_GEMM_CLUSTER=1)
 
 struct EpiParams {
   int M, N;
@@ -238,7 +242,12 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// CL = CTAs per cluster along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent
+// output tiles that share the same B tile: each CTA fetches HALF of B and TMA-multicasts it into both CTAs'
+// shared memory, so L2 -> SM operand traffic per tile drops from 48 KB to 32 KB per k-block (the mainloop is
+// L2-bandwidth bound: profiles/r01_ncu_gemm_*.txt).  Stage release is signalled to both producers by a
+// multicast tcgen05.commit; the CTAs stay in lock-step because they walk identical (n, k) sequences.
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
@@ -270,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -281,11 +290,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = m_tiles * n_tiles * splits;
+  // work items are (m-group of CL tiles, n tile, k split); this CTA takes row `rank` of its cluster's group
+  const int rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
+  const int cta = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+  const int total_tiles = ((m_tiles + CL - 1) / CL) * n_tiles * splits;
   const int kb_per_split = (k_blocks + splits - 1) / splits;
 
   if (warp == 0) {
@@ -293,11 +305,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < total_tiles; tile += ncl) {
         const int ks = tile % splits;
         const int mn = tile / splits;
         const int n_blk = mn % n_tiles;
-        const int m_blk = mn / n_tiles;
+        const int m_blk = (mn / n_tiles) * CL + rank;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(k_blocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -313,13 +325,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               tma_load_2d(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64,
                           kb * BK);
           }
-          if (!B_MN) {
-            tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+          if (CL == 1) {
+            if (!B_MN) {
+              tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(b_dst + i * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + i * 64,
-                          kb * BK);
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(b_dst + i * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+            }
+          } else {
+            // this CTA's half of the B tile, delivered to the same smem offset of BOTH CTAs of the cluster
+            constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
+            if (!B_MN) {
+              tma_load_2d_mc(b_dst + rank * (BN / CL) * 128, &tma_b, &full_bar[stage], kb * BK,
+                             n_blk * BN + rank * (BN / CL), mask);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64 / CL; ++i) {
+                const int bi = rank * (BN / 64 / CL) + i;
+                tma_load_2d_mc(b_dst + bi * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + bi * 64, kb * BK, mask);
+              }
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -333,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < total_tiles; tile += ncl) {
         const int ks = tile % splits;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(k_blocks, kb0 + kb_per_split);
@@ -356,7 +382,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                         : umma_desc_sw128(b_base + k * (UMMA_K * 2), 0, 1024);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          else umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));  // ... in every CTA of the cluster
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
@@ -371,10 +398,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (!epi.tma) {
       // direct path (unaligned outputs): per-thread row stores; the two warps of a lane quarter alternate chunks
       const int ehalf = (warp - 4) >> 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < total_tiles; tile += ncl) {
         const int mn = tile / splits;
         const int n_blk = mn % n_tiles;
-        const int m_blk = mn / n_tiles;
+        const int m_blk = (mn / n_tiles) * CL + rank;
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         const int m = m_blk * BM + ew * 32 + lane;
@@ -406,13 +433,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int row = ew * 32 + lane;              // row inside the tile == TMEM lane
       const uint32_t swz = (uint32_t)(row & 7);
       const uint32_t cb = (uint32_t)(ehalf * 4);   // first 16-byte chunk of this warp's 64-byte share
-      const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int my_tiles = (total_tiles - cta + ncl - 1) / ncl;
       const long total_q = (long)my_tiles * n_sub;
       auto q_coords = [&](long q, int& m0, int& n0) {
         const int tl = (int)(q / n_sub), sidx = (int)(q - (long)tl * n_sub);
-        const int tile = blockIdx.x + tl * gridDim.x;
+        const int tile = cta + tl * ncl;
         const int mn = tile / splits;
-        m0 = (mn / n_tiles) * BM;
+        m0 = ((mn / n_tiles) * CL + rank) * BM;
         n0 = (mn % n_tiles) * BN + sidx * SUBN;
       };
       auto issue_aux = [&](long q) {
@@ -425,10 +452,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (aux_in && issuer)
         for (long q = 0; q < N_AUX && q < total_q; ++q) issue_aux(q);
       long q = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < total_tiles; tile += ncl) {
         const int mn = tile / splits;
         const int n_blk = mn % n_tiles;
-        const int m_blk = mn / n_tiles;
+        const int m_blk = (mn / n_tiles) * CL + rank;
         const int m = m_blk * BM + row;
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
@@ -510,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers may still multicast into / arrive on our smem
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -537,7 +564,7 @@ int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb;
@@ -545,7 +572,7 @@ int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStrea
   if (!A_MN) rc = make_tmap(&ta, p->A, p->K, p->M, p->lda, BK, BM);
   else       rc = make_tmap(&ta, p->A, p->M, p->K, p->lda, 64, BK);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap(&tb, p->B, p->K, p->N, p->ldb, BK, BN);
+  if (!B_MN) rc = make_tmap(&tb, p->B, p->K, p->N, p->ldb, BK, BN / CL);  // each CTA of a cluster loads BN/CL rows
   else       rc = make_tmap(&tb, p->B, p->N, p->K, p->ldb, 64, BK);
   if (rc) return rc;
   CUtensorMap to = ta, to2 = ta, tx = ta;  // placeholders when the staged epilogue is off
@@ -569,25 +596,38 @@ int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStrea
   const int m_tiles = (p->M + BM - 1) / BM;
   const int n_tiles = (p->N + BN - 1) / BN;
   const int k_blocks = (p->K + BK - 1) / BK;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int total = m_tiles * n_tiles * splits;
-  const int grid = total < g_num_sms ? total : g_num_sms;
-  kern<<<grid, 384, C::SMEM_BYTES, stream>>>(ta, tb, to, to2, tx, m_tiles, n_tiles, k_blocks, splits, epi);
+  const int total = ((m_tiles + CL - 1) / CL) * n_tiles * splits;  // work items per cluster
+  int nclusters = g_num_sms / CL;
+  if (total < nclusters) nclusters = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VTB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, tx, m_tiles, n_tiles, k_blocks, splits, epi));
   VTB_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 int dispatch_major(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStream_t s) {
-  if (!p->a_mn_major && !p->b_mn_major) return launch<BN, false, false>(p, epi, splits, s);
-  if (!p->a_mn_major && p->b_mn_major) return launch<BN, false, true>(p, epi, splits, s);
-  if (p->a_mn_major && p->b_mn_major) return launch<BN, true, true>(p, epi, splits, s);
-  return launch<BN, true, false>(p, epi, splits, s);
+  if (!p->a_mn_major && !p->b_mn_major) return launch<BN, false, false, CL>(p, epi, splits, s);
+  if (!p->a_mn_major && p->b_mn_major) return launch<BN, false, true, CL>(p, epi, splits, s);
+  if (p->a_mn_major && p->b_mn_major) return launch<BN, true, true, CL>(p, epi, splits, s);
+  return launch<BN, true, false, CL>(p, epi, splits, s);
 }
 
 }  // namespace
@@ -603,10 +643,18 @@ int vtb_gemm_init() {
   VTB_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, -2,
             "cuTensorMapEncodeTiled not available from the driver");
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* e = getenv("VTB_GEMM_CLUSTER")) g_use_clusters = (e[0] != '0');
   return 0;
 }
 
 int vtb_num_sms() { return g_num_sms; }
+
+extern "C" int vtb_set_option(const char* name, int32_t value) {
+  VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
+  if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value != 0; return 0; }
+  vtb_set_error("vtb_set_option: unknown option '%s'", name);
+  return -1;
+}
 
 extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -691,9 +739,12 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
     int per = (k_blocks + splits - 1) / splits;
     splits = (k_blocks + per - 1) / per;
   }
+  // CTA pairs with multicast B whenever there are at least two row tiles and enough work for every SM
+  const bool pair = g_use_clusters && m_tiles >= 2 && (long)m_tiles * n_tiles * splits >= g_num_sms &&
+                    !(p->b_mn_major && bn < 128);  // an MN-major B tile of 64 columns is one TMA box: cannot be halved
   switch (bn) {
-    case 256: return dispatch_major<256>(p, e, splits, stream);
-    case 128: return dispatch_major<128>(p, e, splits, stream);
-    default:  return dispatch_major<64>(p, e, splits, stream);
+    case 256: return pair ? dispatch_major<256, 2>(p, e, splits, stream) : dispatch_major<256, 1>(p, e, splits, stream);
+    case 128: return pair ? dispatch_major<128, 2>(p, e, splits, stream) : dispatch_major<128, 1>(p, e, splits, stream);
+    default:  return pair ? dispatch_major<64, 2>(p, e, splits, stream) : dispatch_major<64, 1>(p, e, splits, stream);
   }
 }

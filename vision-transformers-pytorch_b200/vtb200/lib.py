@@ -15,7 +15,7 @@ ATTN_GLOBAL, ATTN_WINDOW, ATTN_HALO = 0, 1, 2
 
 # every symbol include/vtb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "vtb_last_error", "vtb_version", "vtb_init", "vtb_gemm_bf16", "vtb_layernorm_fwd",
+    "vtb_last_error", "vtb_version", "vtb_init", "vtb_set_option", "vtb_gemm_bf16", "vtb_layernorm_fwd",
     "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_cast_f32_bf16",
     "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
     "vtb_patch_scatter", "vtb_transpose_hw", "vtb_dwconv3x3_fwd", "vtb_dwconv3x3_bwd", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
@@ -83,6 +83,7 @@ def load():
     lib.vtb_last_error.argtypes = []
     lib.vtb_version.restype = i32
     lib.vtb_init.restype = i32
+    lib.vtb_set_option.argtypes = [C.c_char_p, i32]
     lib.vtb_gemm_bf16.argtypes = [C.POINTER(GemmParams), vp]
     lib.vtb_layernorm_fwd.argtypes = [vp, vp, vp, f32, i64, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp]
     lib.vtb_layernorm_bwd.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp,
@@ -137,3 +138,8 @@ def check(rc, lib=None):
         lib = lib or load()
         msg = lib.vtb_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"vtb200 error {rc}: {msg}")
+
+
+def set_option(name, value):
+    lib = get()
+    check(lib.vtb_set_option(name.encode(), int(value)), lib)
