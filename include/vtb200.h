@@ -26,7 +26,9 @@ int vtb_version(void);
 /* Resolve cuTensorMapEncodeTiled through the runtime, query SM count.  Idempotent. */
 int vtb_init(void);
 /* Runtime switches.  "gemm_cluster" (0/1): run the GEMM as CTA pairs (thread-block clusters of 2) that
- * TMA-multicast the shared B tile into both CTAs' shared memory.  Default 0: measured neutral on B200. */
+ * TMA-multicast the shared B tile into both CTAs' shared memory.  Default 0: measured neutral on B200.
+ * "attn_tc" (0/1, default 1): use the tcgen05/TMEM attention kernels where they apply (global attention,
+ * dh = 64, <= 256 keys); 0 forces the mma.sync kernels (A/B measurements, cross-checks). */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------

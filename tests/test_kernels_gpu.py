@@ -272,6 +272,30 @@ def test_attention_global(ops, B, H, dh, Nq, Nkv):
     assert rel(dkv[:, HD:].reshape(B, Nkv, H, dh).permute(0, 2, 1, 3).float(), wdv) < 1.5e-2
 
 
+def test_attention_tcgen05_and_mma_paths_agree(ops):
+    """The tcgen05/TMEM kernels and the mma.sync kernels implement the same contract (A/B via vtb_set_option)."""
+    from vtb200 import lib
+
+    B, H, dh, N = 3, 4, 64, 197
+    HD = H * dh
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = bf(torch.randn(B * N, 3 * HD, device="cuda", generator=g))
+    do = bf(torch.randn(B * N, HD, device="cuda", generator=g))
+    spec = ops.AttnSpec(lib.ATTN_GLOBAL, B, H, dh, N, N)
+    res = {}
+    for mode in (1, 0):
+        lib.set_option("attn_tc", mode)
+        try:
+            o, lse = ops.attention_fwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:])
+            d = torch.empty_like(qkv)
+            ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, d[:, :HD], d[:, HD:2 * HD],
+                              d[:, 2 * HD:])
+            res[mode] = (o.float(), lse, d.float())
+        finally:
+            lib.set_option("attn_tc", 1)
+    assert rel(res[1][0], res[0][0]) < 6e-3 and rel(res[1][1], res[0][1]) < 1e-4 and rel(res[1][2], res[0][2]) < 1.5e-2
+
+
 def _window_case(ops, Hs, W, shift, H, dh, B, seed, use_bias=True):
     """Window attention on a fused qkv buffer vs the oracle's gather-form restatement."""
     from oracle import restate as R

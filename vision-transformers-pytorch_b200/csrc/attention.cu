@@ -629,6 +629,10 @@ int make_geom(const vtb_attn_params* p, Geom* g, long* groups, const char* who) 
 
 }  // namespace
 
+bool vtb_attn_tc_fwd_ok(const vtb_attn_params* p);
+int vtb_attn_tc_fwd(const vtb_attn_params* p, cudaStream_t stream);
+bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p);
+int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_resident_ok(const vtb_attn_params* p);
 int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
 int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
@@ -640,6 +644,7 @@ extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_)
   int rc = make_geom(p, &g, &groups, "vtb_attention_fwd");
   if (rc) return rc;
   VTB_CHECK(p->o && p->ldo % 2 == 0, -1, "vtb_attention_fwd: o");
+  if (vtb_attn_tc_fwd_ok(p)) return vtb_attn_tc_fwd(p, stream);  // tcgen05 / TMEM path (global, dh 64, <= 256 keys)
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_fwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const long blocks = groups * p->heads * q_tiles;
@@ -663,6 +668,7 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
   VTB_CHECK(p->lddq % 2 == 0 && (p->dkv_f32 || (p->lddk % 2 == 0 && p->lddv % 2 == 0)), -1,
             "vtb_attention_bwd: dq/dk/dv leading dims");
   const vtb_attn_params& q = *p;
+  if (vtb_attn_tc_bwd_ok(p)) return vtb_attn_tc_bwd(p, stream);  // tcgen05 / TMEM path
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_bwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const int kv_tiles = (p->nkv + BKV - 1) / BKV;
