@@ -312,7 +312,8 @@ int vtb_attn_tc_fwd(const vtb_attn_params* p, cudaStream_t stream) {
 // =====================================================================================================
 namespace {
 
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;   // warp 0 TMA/alloc, warp 1 UMMA issuer, warps 2-9 math (two per TMEM lane quarter)
+constexpr int BWD_MATH = 256;
 constexpr int TILE_BYTES = 256 * 128;  // one resident operand: 256 token rows x 128 B
 constexpr int PT_BYTES = 128 * 256;    // P^T / dS^T tile: 128 key rows x 128 queries (two 64-query blocks)
 constexpr int SMEM_BWD = 4 * TILE_BYTES + 2 * PT_BYTES + 2 * 256 * 4 + 1024 + 256;
@@ -354,8 +355,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
-      mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 4); mbar_init(bar_pds, 4);
-      mbar_init(bar_pdsfree, 1); mbar_init(bar_dkv, 1); mbar_init(bar_dkvfree, 4); mbar_init(bar_dq, 1);
+      mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 8); mbar_init(bar_pds, 8);
+      mbar_init(bar_pdsfree, 1); mbar_init(bar_dkv, 1); mbar_init(bar_dkvfree, 8); mbar_init(bar_dq, 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -431,13 +432,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   } else {
     // ---------------------------------------------------------------- math + epilogue warps (2..5)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;               // the two warps of a lane quarter alternate 32-column chunks
     const int row = quarter * 32 + lane;            // key row inside the tile == TMEM lane
-    const int mt = threadIdx.x - 64;                // 0..127
+    const int mt = threadIdx.x - 64;                // 0..255
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
     const float sl2 = scale * 1.4426950408889634f;
     // delta_i = sum_d dO[i,d] O[i,d]; lse2_i = lse_i log2(e)   (two rows per thread, straight from global)
-    for (int i = mt; i < 256; i += 128) {
+    for (int i = mt; i < 256; i += BWD_MATH) {
       float acc = 0.f, l2 = INFINITY;
       if (i < nq) {
         const bf16* a = dO + ((long)b * nq + i) * lddo + h * DH;
@@ -458,7 +460,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       sDelta[i] = acc;
       sLse2[i] = l2;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // delta / lse2 visible to all math warps
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // delta / lse2 visible to all math warps
 
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
@@ -468,7 +470,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         mbar_wait(bar_s, (uint32_t)(it & 1));
         tc_fence_after();
         if (it > 0) mbar_wait(bar_pdsfree, (uint32_t)((it - 1) & 1));  // previous tiles no longer read by UMMA
-        for (int c = 0; c < nqh; c += 32) {
+        for (int c = half * 32; c < nqh; c += 64) {
           uint32_t st[32], dp[32];
           if (nqh - c >= 32) {
             tmem_ld_32x32(t_row + C_ST + c, st);
@@ -520,7 +522,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       {
         const int j = kt * 128 + row;
 #pragma unroll
-        for (int part = 0; part < 4; ++part) {  // dV cols 0-31, 32-63, dK cols 0-31, 32-63
+        for (int part = half * 2; part < half * 2 + 2; ++part) {  // half 0: dV cols 0-31, 32-63; half 1: dK
           uint32_t a[32];
           tmem_ld_32x32(t_row + (part < 2 ? C_DV : C_DK) + (part & 1) * 32, a);
           tmem_ld_wait();
@@ -545,8 +547,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     tc_fence_after();
     for (int hq = 0; hq < nhq; ++hq) {
       const int i = hq * 128 + row;
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
+      {
+        const int part = half;
         uint32_t a[32];
         tmem_ld_32x32(t_row + C_DQ + hq * 64 + part * 32, a);
         tmem_ld_wait();
