@@ -722,8 +722,9 @@ __device__ __forceinline__ void res_load_rows(bf16* dst, int rows16, const bf16*
 
 struct ResSmem {
   bf16 *q, *k, *v, *dO;
-  float *bias, *lse, *delta, *dtab;
+  float *bias, *lse, *delta, *dtab, *tab;
   unsigned short* pos;
+  uint8_t* maskb;
   int *qtok, *ktok;
   int nq16, nkv16, bias_ld;
 };
@@ -745,9 +746,11 @@ __device__ __forceinline__ ResSmem res_carve(uint8_t* base, int nq_loc, int nq, 
   s.lse = reinterpret_cast<float*>(p); if (bwd) p += s.nq16 * 4;
   s.delta = reinterpret_cast<float*>(p); if (bwd) p += s.nq16 * 4;
   s.dtab = reinterpret_cast<float*>(p); if (bwd && has_bias) p += n_pos * 4;
+  s.tab = reinterpret_cast<float*>(p); if (has_bias) p += n_pos * 4;   // rel_bias[:, h] staged once per CTA
   s.qtok = reinterpret_cast<int*>(p); p += s.nq16 * 4;
   s.ktok = reinterpret_cast<int*>(p); p += s.nkv16 * 4;
-  s.pos = reinterpret_cast<unsigned short*>(p);  // [nq][bias_ld] u16 (bwd with bias only)
+  s.pos = reinterpret_cast<unsigned short*>(p); if (bwd && has_bias) p += (size_t)nq * s.bias_ld * 2;  // u16 tile
+  s.maskb = p;                                                          // [nq][bias_ld] u8 mask of the current group
   return s;
 }
 
@@ -755,34 +758,49 @@ size_t res_smem_bytes(int DH, int nq_loc, int nq, int nkv, bool bwd, bool has_bi
   const int nq16 = (nq_loc + 15) & ~15, nkv16 = (nkv + 15) & ~15, bld = (nkv + 3) & ~3;
   size_t b = (size_t)(nq16 + 2 * nkv16) * DH * 2 + (size_t)(nq16 + nkv16) * 4;
   if (bwd) b += (size_t)nq16 * DH * 2 + (size_t)nq16 * 8;
-  if (has_bias) b += (size_t)nq * bld * 4;
+  if (has_bias) b += (size_t)nq * bld * 4 + (size_t)n_pos * 4 + (size_t)nq * bld;  // bias tile, table, mask bytes
   if (bwd && has_table) b += (size_t)n_pos * 4 + (size_t)nq * bld * 2;
   return b + 16;
 }
 
-// builds token indices, the bias(+mask) tile and (bwd) the pos tile; issues the cp.async row loads
+// Once per CTA: stage rel_bias[:, h] in shared memory, then build the group-independent bias tile
+// bias[i][j] = table[pos[i][j]] (and the u16 pos tile for the backward's bias gradient).  The table goes through
+// smem first so that no global load depends on another one.
 template <int DH>
-__device__ __forceinline__ void res_prologue(const vtb_attn_params& p, const Geom& g, int grp, int h,
-                                             const ResSmem& s, bool bwd, int qbase, int q_end) {
+__device__ __forceinline__ void res_once(const vtb_attn_params& p, const Geom& g, int h, const ResSmem& s, bool bwd) {
+  const bool has_bias = p.rel_bias || p.mask;
+  if (!has_bias) return;
+  if (p.rel_bias)
+    for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) {
+      s.tab[t] = __ldg(p.rel_bias + (long)t * g.heads + h);
+      if (bwd) s.dtab[t] = 0.f;
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < g.nq * g.nkv; e += blockDim.x) {
+    const int i = e / g.nkv, j = e - i * g.nkv;
+    float b = 0.f;
+    if (p.rel_bias) {
+      const int pi = __ldg(p.pos + e);
+      b = s.tab[pi];
+      if (bwd) s.pos[i * s.bias_ld + j] = (unsigned short)pi;
+    }
+    s.bias[i * s.bias_ld + j] = b;
+  }
+}
+
+// Per group: token indices, the group's mask bytes, and the cp.async row loads.
+template <int DH>
+__device__ __forceinline__ void res_group(const vtb_attn_params& p, const Geom& g, int grp, int h,
+                                          const ResSmem& s, bool bwd, int qbase, int q_end) {
   for (int i = threadIdx.x; i < s.nq16; i += blockDim.x)
     s.qtok[i] = (qbase + i < q_end) ? (int)q_token(g, grp, qbase + i) : -1;
   for (int j = threadIdx.x; j < s.nkv16; j += blockDim.x) s.ktok[j] = (int)kv_token(g, grp, j);
-  const bool has_bias = p.rel_bias || p.mask;
-  if (has_bias) {
-    const uint8_t* mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  if (p.mask) {
+    const uint8_t* mask = p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv;
     for (int e = threadIdx.x; e < g.nq * g.nkv; e += blockDim.x) {
       const int i = e / g.nkv, j = e - i * g.nkv;
-      float b = 0.f;
-      if (p.rel_bias) {
-        const int pi = __ldg(p.pos + e);
-        b = __ldg(p.rel_bias + (long)pi * g.heads + h);
-        if (bwd) s.pos[i * s.bias_ld + j] = (unsigned short)pi;
-      }
-      if (mask && mask[e]) b = -INFINITY;
-      s.bias[i * s.bias_ld + j] = b;
+      s.maskb[i * s.bias_ld + j] = mask[e];
     }
-    if (bwd && p.rel_bias)
-      for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) s.dtab[t] = 0.f;
   }
   __syncthreads();  // token indices visible
   res_load_rows<DH>(s.q, s.nq16, reinterpret_cast<const bf16*>(p.q), p.ldq, h * DH, s.qtok);
@@ -790,6 +808,12 @@ __device__ __forceinline__ void res_prologue(const vtb_attn_params& p, const Geo
   res_load_rows<DH>(s.v, s.nkv16, reinterpret_cast<const bf16*>(p.v), p.ldv, h * DH, s.ktok);
   if (bwd) res_load_rows<DH>(s.dO, s.nq16, reinterpret_cast<const bf16*>(p.dout), p.lddo, h * DH, s.qtok);
   cp_async_commit();
+}
+
+// bias (+ -inf where masked) of element (i, j)
+__device__ __forceinline__ float res_bias(const ResSmem& s, bool has_mask, int i, int j) {
+  const int o = i * s.bias_ld + j;
+  return (has_mask && s.maskb[o]) ? -INFINITY : s.bias[o];
 }
 
 // A fragments (16 rows x DH) of a swizzled tile
@@ -812,24 +836,29 @@ __device__ __forceinline__ void res_ld_bt(uint32_t (&r)[4], const bf16* tile, in
 
 template <int DH>
 __global__ void __launch_bounds__(RES_THREADS, 1)
-attn_res_fwd_kernel(vtb_attn_params p, Geom g, int nsplit, int q_per_cta) {
+attn_res_fwd_kernel(vtb_attn_params p, Geom g, int nsplit, int q_per_cta, int groups, int nchunks) {
   extern __shared__ __align__(16) uint8_t res_smem[];
+  // blockIdx -> (query split, head, chunk); the CTA then walks groups chunk, chunk + nchunks, ... (persistent:
+  // the per-head bias table / tile is staged once per CTA)
   const int split = blockIdx.x % nsplit;
   const int gh = blockIdx.x / nsplit;
   const int h = gh % g.heads;
-  const int grp = gh / g.heads;
+  const int chunk = gh / g.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
   const bool has_bias = p.rel_bias || p.mask;
+  const bool has_mask = p.mask != nullptr;
   const int qbase = split * q_per_cta;
   const int q_end = min(g.nq, qbase + q_per_cta);
   const ResSmem s = res_carve<DH>(res_smem, q_per_cta, g.nq, g.nkv, false, has_bias, p.n_pos);
-  res_prologue<DH>(p, g, grp, h, s, false, qbase, q_end);
+  res_once<DH>(p, g, h, s, false);
+  const int r0 = warp * 16;
+  for (int grp = chunk; grp < groups; grp += nchunks) {
+  __syncthreads();  // previous group's shared-memory reads are done (and the one-time tiles are visible)
+  res_group<DH>(p, g, grp, h, s, false, qbase, q_end);
   cp_async_wait<0>();
   __syncthreads();
-
-  const int r0 = warp * 16;
-  if (qbase + r0 >= q_end) return;
+  if (qbase + r0 < q_end) {
   uint32_t qf[DH / 16][4];
   res_ld_a<DH>(qf, s.q, r0, lane);
   float o[DH / 8][4];
@@ -864,7 +893,7 @@ attn_res_fwd_kernel(vtb_attn_params p, Geom g, int nsplit, int q_per_cta) {
         const int j = j0 + n * 8 + 2 * tq + (e & 1);
         float v = sc[n][e] * p.scale;
         if (j >= g.nkv) v = -INFINITY;
-        else if (has_bias) v += s.bias[min(i, g.nq - 1) * s.bias_ld + j];
+        else if (has_bias) v += res_bias(s, has_mask, min(i, g.nq - 1), j);
         sc[n][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);
       }
@@ -930,20 +959,26 @@ attn_res_fwd_kernel(vtb_attn_params p, Geom g, int nsplit, int q_per_cta) {
       *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) = pack_bf16(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
     if (tq == 0 && p.lse) p.lse[((long)grp * g.heads + h) * g.nq + qbase + row] = m_run[r] + __logf(l_run[r]);
   }
+  }  // active warp
+  }  // groups
 }
 
 template <int DH>
 __global__ void __launch_bounds__(RES_THREADS, 1)
-attn_res_bwd_kernel(vtb_attn_params p, Geom g) {
+attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks) {
   extern __shared__ __align__(16) uint8_t res_smem[];
   const int h = blockIdx.x % g.heads;
-  const int grp = blockIdx.x / g.heads;
+  const int chunk = blockIdx.x / g.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
   const bool has_bias = p.rel_bias || p.mask;
   const bool has_tab = p.rel_bias != nullptr;
+  const bool has_mask = p.mask != nullptr;
   const ResSmem s = res_carve<DH>(res_smem, g.nq, g.nq, g.nkv, true, has_bias, has_tab ? p.n_pos : 0);
-  res_prologue<DH>(p, g, grp, h, s, true, 0, g.nq);
+  res_once<DH>(p, g, h, s, true);
+  for (int grp = chunk; grp < groups; grp += nchunks) {
+  __syncthreads();  // previous group's shared-memory reads are done (and the one-time tiles are visible)
+  res_group<DH>(p, g, grp, h, s, true, 0, g.nq);
   // delta_i = sum_d dO[i,d] O[i,d] and lse_i, two threads per row (straight from global; O is not staged)
   {
     const bf16* O = reinterpret_cast<const bf16*>(p.o);
@@ -1026,7 +1061,7 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g) {
             float ds = 0.f;
             if (j < g.nkv && i < g.nq) {
               float v = sc[n][e] * p.scale;
-              if (has_bias) v += s.bias[i * s.bias_ld + j];
+              if (has_bias) v += res_bias(s, has_mask, i, j);
               const float pv = __expf(v - lse_r[r]);  // exp(-inf) = 0 for masked entries
               ds = pv * (dp[n][e] - dl_r[r]);
               if (has_tab && p.drel_bias && ds != 0.f) atomicAdd(&s.dtab[s.pos[i * s.bias_ld + j]], ds);
@@ -1113,7 +1148,7 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g) {
             float pv = 0.f, ds = 0.f;
             if (j < g.nkv && i < g.nq) {
               float v = sc[n][e] * p.scale;
-              if (has_bias) v += s.bias[i * s.bias_ld + j];
+              if (has_bias) v += res_bias(s, has_mask, i, j);
               pv = __expf(v - s.lse[i]);
               ds = pv * (dp[n][e] - s.delta[i]);
             }
@@ -1173,6 +1208,7 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g) {
     }
   }
 
+  }  // groups: the bias-gradient table keeps accumulating across them and is flushed once per CTA
   if (has_tab && p.drel_bias) {
     __syncthreads();
     for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) {
@@ -1202,15 +1238,25 @@ int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, 
   const size_t smem = res_smem_bytes(p->dh, q_per_cta, p->nq, p->nkv, false, has_bias, p->rel_bias != nullptr, p->n_pos);
   VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_fwd: resident tile needs %zu B of shared memory", smem);
   const int warps = q_per_cta / 16;
-  const long blocks = groups * p->heads * nsplit;
-  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd: grid too large");
   static bool set64 = false, set32 = false;
+  if (p->dh == 64 && !set64) { int rc = res_set_smem(attn_res_fwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
+  if (p->dh == 32 && !set32) { int rc = res_set_smem(attn_res_fwd_kernel<32>, smem); if (rc) return rc; set32 = true; }
+  // persistent over groups when a bias table / mask has to be staged per CTA; one group per CTA otherwise
+  long nchunks = groups;
+  if (has_bias) {  // one resident wave: CTAs per SM from the occupancy calculator
+    int per_sm = 1;
+    if (p->dh == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_res_fwd_kernel<64>, warps * 32, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_res_fwd_kernel<32>, warps * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const long target = (long)vtb_num_sms() * per_sm / ((long)p->heads * nsplit);
+    nchunks = target < 1 ? 1 : (target < groups ? target : groups);
+  }
+  const long blocks = nchunks * p->heads * nsplit;
+  VTB_CHECK(blocks < (1L << 31) && groups < (1L << 31), -1, "vtb_attention_fwd: grid too large");
   if (p->dh == 64) {
-    if (!set64) { int rc = res_set_smem(attn_res_fwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
-    attn_res_fwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, nsplit, q_per_cta);
+    attn_res_fwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, nsplit, q_per_cta, (int)groups, (int)nchunks);
   } else {
-    if (!set32) { int rc = res_set_smem(attn_res_fwd_kernel<32>, smem); if (rc) return rc; set32 = true; }
-    attn_res_fwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, nsplit, q_per_cta);
+    attn_res_fwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, nsplit, q_per_cta, (int)groups, (int)nchunks);
   }
   VTB_LAUNCH_CHECK();
   return 0;
@@ -1222,15 +1268,24 @@ int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, 
   VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_bwd: resident tile needs %zu B of shared memory", smem);
   const int nmax = p->nq > p->nkv ? p->nq : p->nkv;
   const int warps = (nmax + 15) / 16;
-  const long blocks = groups * p->heads;
-  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_bwd: grid too large");
   static bool set64 = false, set32 = false;
+  if (p->dh == 64 && !set64) { int rc = res_set_smem(attn_res_bwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
+  if (p->dh == 32 && !set32) { int rc = res_set_smem(attn_res_bwd_kernel<32>, smem); if (rc) return rc; set32 = true; }
+  long nchunks = groups;
+  if (has_bias) {
+    int per_sm = 1;
+    if (p->dh == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_res_bwd_kernel<64>, warps * 32, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_res_bwd_kernel<32>, warps * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const long target = (long)vtb_num_sms() * per_sm / (long)p->heads;
+    nchunks = target < 1 ? 1 : (target < groups ? target : groups);
+  }
+  const long blocks = nchunks * p->heads;
+  VTB_CHECK(blocks < (1L << 31) && groups < (1L << 31), -1, "vtb_attention_bwd: grid too large");
   if (p->dh == 64) {
-    if (!set64) { int rc = res_set_smem(attn_res_bwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
-    attn_res_bwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g);
+    attn_res_bwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks);
   } else {
-    if (!set32) { int rc = res_set_smem(attn_res_bwd_kernel<32>, smem); if (rc) return rc; set32 = true; }
-    attn_res_bwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g);
+    attn_res_bwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks);
   }
   VTB_LAUNCH_CHECK();
   return 0;
