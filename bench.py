@@ -34,6 +34,9 @@ WORKLOADS = {
     "pvt_small": dict(gflop=22.875, batch=128, desc="PVT-Small 224x224 fwd+bwd, batch 128/GPU"),
     "halo_t": dict(gflop=29.36, batch=128, desc="Halo-T* 224x224 fwd+bwd, batch 128/GPU"),
     "vit_tiny": dict(gflop=7.463, batch=64, desc="ViT-Tiny/16 224x224 fwd+bwd (plumbing)"),
+    # BASELINE config 5: per source image 2x224^2 + 8x96^2 student fwd+bwd, 2x224^2 teacher fwd, + head
+    "dino_deit_s": dict(gflop=113.4, batch=128, desc="DINO DeiT-S/16 multi-crop (2x224^2 + 8x96^2), 128 source images/GPU: "
+                                                      "teacher fwd + student fwd/bwd + DINO loss + EMA"),
 }
 
 
@@ -52,6 +55,11 @@ def build_model(workload, drop_path=None):
     if workload == "pvt_small":
         return models.PyramidVisionTransformer(224, 1000, 3, (3, 4, 6, 3), (64, 128, 320, 512), (1, 2, 5, 8),
                                                (512, 1024, 1280, 2048), (8, 4, 2, 1), drop_path=0.1)
+    if workload == "dino_deit_s":  # config/dino_deit-s-16.conf:1-19
+        return models.dino(image_size=224, window_size=16, depth=12, dim=384, n_head=6, dim_ff=1536, dropout=0.,
+                           drop_attn=0., drop_ff=0., drop_path=0.1 if drop_path is None else drop_path,
+                           dim_head_out=65536, use_bn=False, norm_last_layer=False, depth_head=3, dim_head_ff=2048,
+                           dim_head_bottleneck=256)
     if workload == "halo_t":
         return models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
                                       (384, 768, 1536, 3072), window_size=7, halo_size=3, drop_path=0.1)
@@ -124,6 +132,26 @@ def cpu_reference_step(workload, batch, threads):
     torch.manual_seed(1234)
     model = build_model(workload, drop_path=0.0)
     sd = {k: (v.detach().clone().requires_grad_(v.is_floating_point())) for k, v in model.state_dict().items()}
+    if workload == "dino_deit_s":
+        xs = [torch.randn(batch, 3, 224, 224) for _ in range(2)] + [torch.randn(batch, 3, 96, 96) for _ in range(8)]
+        tsd = {k: v.detach().clone() for k, v in sd.items()}
+        center = torch.zeros(1, 65536)
+
+        def dino_step():
+            for v in sd.values():
+                if v.is_floating_point():
+                    v.grad = None
+            with torch.no_grad():
+                t_out = R.vit_forward(tsd, xs[:2], patch=16, depth=12, heads=6, head_fn=lambda f: R.dino_head(tsd, f))
+            s_out = R.vit_forward(sd, xs, patch=16, depth=12, heads=6, head_fn=lambda f: R.dino_head(sd, f))
+            loss = R.dino_loss(s_out, t_out, center, 10)
+            loss.backward()
+            with torch.no_grad():
+                for k in tsd:
+                    tsd[k].mul_(0.996).add_(sd[k].detach(), alpha=0.004)
+            return loss.item()
+
+        return dino_step
     x = torch.randn(batch, 3, 224, 224)
     y = torch.randint(0, 1000, (batch,))
 
@@ -154,7 +182,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 8
+    batch = 2 if args.workload == "dino_deit_s" else 8
     step = cpu_reference_step(args.workload, batch, threads)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
@@ -209,6 +237,14 @@ def main():
     torch.manual_seed(1234 + rank)
     model = build_model(args.workload).to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
+    is_dino = args.workload == "dino_deit_s"
+    if is_dino:
+        args.no_graph = True  # list inputs + EMA + centre all-reduce: issued eagerly
+        teacher = build_model(args.workload, drop_path=0.0).to(dev)
+        teacher.load_state_dict(model.state_dict())
+        for p in teacher.parameters():
+            p.requires_grad_(False)
+        center = torch.zeros(1, 65536, device=dev)
     net, reducer = model, None
     use_graph = not args.no_graph and not args.nvtx_step
     if world > 1:
@@ -221,10 +257,41 @@ def main():
             reducer = vd.FlatGradReducer(params)
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
+    if is_dino:
+        crops_dev = [torch.randn(B, 3, 224, 224, device=dev) for _ in range(2)] + \
+                    [torch.randn(B, 3, 96, 96, device=dev) for _ in range(8)]
+        x_dev = crops_dev
+
+    def dino_loss_fn(student, teacher_out):
+        """loss.py:119-152 restated with torch ops (DINOLoss is a "next" row): centred / sharpened teacher
+        softmax vs student log-softmax over every other crop, then the EMA centre update with its all-reduce."""
+        nonlocal center
+        s = (student / 0.1).chunk(10)
+        t = torch.softmax((teacher_out - center) / 0.04, -1).detach().chunk(2)
+        total, n = 0.0, 0
+        for iq, q in enumerate(t):
+            for v in range(10):
+                if v != iq:
+                    total = total + (-q * torch.log_softmax(s[v], -1)).sum(-1).mean()
+                    n += 1
+        bc = teacher_out.sum(0, keepdim=True)
+        if world > 1:
+            dist.all_reduce(bc)
+        center = center * 0.9 + bc / (teacher_out.shape[0] * world) * 0.1
+        return total / n
 
     def fwd_bwd(x, y):
         for p in params:
             p.grad = None
+        if is_dino:
+            with torch.no_grad():
+                t_out = teacher(x[:2])
+            loss = dino_loss_fn(net(x), t_out)
+            loss.backward()
+            with torch.no_grad():  # EMA teacher (train_dino.py:257-261)
+                torch._foreach_mul_(list(teacher.parameters()), 0.996)
+                torch._foreach_add_(list(teacher.parameters()), list(model.parameters()), alpha=0.004)
+            return loss
         loss = torch.nn.functional.cross_entropy(net(x), y)
         loss.backward()
         return loss
@@ -317,7 +384,26 @@ def main():
 
     # ---------------------------------------------------------------- end-to-end from host buffers (`e2e`)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and is_dino:
+        crops_host = [c.cpu().pin_memory() for c in crops_dev]
+
+        def e2e_dino(n):
+            tot = 0.0
+            for _ in range(n):
+                xd = [c.to(dev, non_blocking=True) for c in crops_host]
+                tot += step(xd, None).item()
+            return tot
+
+        e2e_dino(1)
+        barrier()
+        e0.record()
+        e2e_dino(args.steps)
+        e1.record()
+        barrier()
+        ms2 = vd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        e2e = {"value": world * B / (ms2 * 1e-3), "unit": "images/s", "ms_per_step": ms2,
+               "h2d_bytes_per_step": sum(c.numel() * 4 for c in crops_host), "d2h_bytes_per_step": 4}
+    elif not args.no_e2e:
         n_host = 3
         xs = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(n_host)]
         ys = [torch.randint(0, 1000, (B,)).pin_memory() for _ in range(n_host)]
@@ -359,7 +445,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cb = 8
+        cb = 2 if is_dino else 8
         cstep = cpu_reference_step(args.workload, cb, threads)
         cstep()
         n = 3

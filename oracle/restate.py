@@ -140,6 +140,34 @@ def vit_forward(sd, inputs, *, patch, depth, heads, head_fn=None, dp_scales=None
     return head_fn(out) if head_fn is not None else out
 
 
+def dino_head(sd, x, pre="head."):
+    """DINOHead.forward (vit.py:257-262): MLP with exact GELU, L2-normalise, weight-normed Linear (no bias)."""
+    i = 0
+    while f"{pre}mlp.{i}.weight" in sd:
+        x = linear(x, sd[f"{pre}mlp.{i}.weight"], sd[f"{pre}mlp.{i}.bias"])
+        if f"{pre}mlp.{i + 2}.weight" in sd:
+            x = 0.5 * x * (1 + torch.erf(x / math.sqrt(2.0)))
+        i += 2
+    x = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    v, g = sd[pre + "last.weight_v"], sd[pre + "last.weight_g"]
+    return x @ (v * (g / v.norm(dim=1, keepdim=True))).t()
+
+
+def dino_loss(student, teacher, center, n_crops, t_student=0.1, t_teacher=0.04):
+    """DINOLoss.forward (loss.py:119-142): cross-entropy between the centred/sharpened teacher distribution of each
+    global crop and the student distribution of every OTHER crop, averaged over the pairs."""
+    s = (student / t_student).chunk(n_crops)
+    t = torch.softmax((teacher - center) / t_teacher, -1).detach().chunk(2)
+    total, n = 0.0, 0
+    for iq, q in enumerate(t):
+        for v in range(n_crops):
+            if v == iq:
+                continue
+            total = total + (-q * torch.log_softmax(s[v], -1)).sum(-1).mean()
+            n += 1
+    return total / n
+
+
 # ------------------------------------------------------------------------------------------ patchify
 def patchify(x, s):
     """NHWC block gather, feature order (sy, sx, c) (swin:15-22)."""

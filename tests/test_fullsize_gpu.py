@@ -1,0 +1,105 @@
+"""Parity at BASELINE.json's full model sizes (ViT-B/16, Swin-S, PVT-Small, Halo-T*, 224x224), through the oracle on
+a few images and through size-independent properties on the full batch:
+  * per-image independence / batch-permutation equivariance of the forward (bit-exact: no kernel couples images);
+  * every parameter receives a finite fp32 gradient;
+  * the backward is linear in the upstream gradient (scaling the probe by 2 scales every gradient by 2).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _vit_b():
+    import models
+
+    return models.VisionTransformer(models.FusedLinear(768, 1000), 224, 16, 12, 768, 12, 3072, 0., 0., 0., 0.)
+
+
+def test_vit_b16_full_batch_properties_and_oracle():
+    from oracle import restate as R
+
+    torch.manual_seed(0)
+    model = R.randomize_(_vit_b(), 11).cuda().eval()
+    B = 256
+    x = torch.randn(B, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        out = model(x)
+        perm = torch.randperm(B, device="cuda")
+        out_p = model(x[perm])
+    assert out.shape == (B, 1000) and torch.isfinite(out).all()
+    assert torch.equal(out_p, out[perm]), "forward must not couple images (bit-exact under batch permutation)"
+    # oracle on 4 of the 256 images (fp32, same device)
+    idx = torch.tensor([0, 77, 128, 255], device="cuda")
+    sd = dict(model.state_dict())
+    with torch.no_grad():
+        want = R.vit_forward(sd, x[idx], patch=16, depth=12, heads=12,
+                             head_fn=lambda f: R.linear(f, sd["head.weight"], sd["head.bias"]))
+    assert rel(out[idx], want) < 2e-2, rel(out[idx], want)
+
+
+def test_vit_b16_backward_is_linear_in_upstream_gradient():
+    from oracle import restate as R
+
+    torch.manual_seed(1)
+    model = R.randomize_(_vit_b(), 12).cuda().train()
+    x = torch.randn(32, 3, 224, 224, device="cuda")
+    probe = torch.randn(32, 1000, device="cuda")
+
+    def grads(scale):
+        for p in model.parameters():
+            p.grad = None
+        (model(x) * (probe * scale)).sum().backward()
+        return {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    g1, g2 = grads(1.0), grads(2.0)
+    for k in g1:
+        assert torch.isfinite(g1[k]).all(), k
+        # x2 is exact in bf16 and fp32; only the fp32 split-K reduce-add order may differ between runs
+        assert rel(g2[k], 2 * g1[k]) < 1e-4, (k, rel(g2[k], 2 * g1[k]))
+
+
+@pytest.mark.parametrize("family", ["swin_s", "pvt_small", "halo_t"])
+def test_full_size_models_match_oracle(family):
+    import models
+    from oracle import restate as R
+
+    torch.manual_seed(2)
+    if family == "swin_s":
+        kw = dict(image_size=(224, 224), n_class=1000, depths=(2, 2, 18, 2), dims=(96, 192, 384, 768), dim_head=32,
+                  n_heads=(3, 6, 12, 24), dim_ffs=(384, 768, 1536, 3072), window_size=7)
+        model = models.SwinTransformer(**kw)
+        fwd = lambda sd, x: R.swin_forward(sd, x, depths=kw["depths"], n_heads=kw["n_heads"], dim_head=32, window=7)  # noqa: E731
+    elif family == "pvt_small":
+        model = models.PyramidVisionTransformer(224, 1000, 3, (3, 4, 6, 3), (64, 128, 320, 512), (1, 2, 5, 8),
+                                                (512, 1024, 1280, 2048), (8, 4, 2, 1))
+        fwd = lambda sd, x: R.pvt_forward(sd, x, depths=(3, 4, 6, 3), n_heads=(1, 2, 5, 8), reductions=(8, 4, 2, 1))  # noqa: E731
+    else:
+        model = models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
+                                       (384, 768, 1536, 3072), window_size=7, halo_size=3)
+        fwd = lambda sd, x: R.halo_forward(sd, x, depths=(2, 2, 6, 2), n_heads=(3, 6, 12, 24), dim_head=32, window=7,  # noqa: E731
+                                           halo=3)
+    model = R.randomize_(model, 13).cuda().train()
+    x = torch.randn(4, 3, 224, 224, device="cuda")
+    out = model(x)
+    sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in model.state_dict().items()}
+    want = fwd(sd, x)
+    assert rel(out, want) < 2e-2, rel(out, want)
+    probe = torch.randn_like(out)
+    (out * probe).sum().backward()
+    (want * probe).sum().backward()
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        g = sd[k].grad
+        if g.norm() < 1e-6 * max(1.0, g.numel() ** 0.5):
+            continue
+        r = rel(p.grad, g)
+        if r > worst[1]:
+            worst = (k, r)
+    assert worst[1] < 6e-2, worst
