@@ -5,7 +5,8 @@ from .halo_transformer import HaloTransformer
 from .pvt import PyramidVisionTransformer
 from .swin_transformer import SwinTransformer
 from .twins import TwinsSVT  # noqa: F401  (not exported by the reference's __init__, registered as "twins_svt")
-from .vit import DINOHead, FusedLinear, VisionTransformer, dino
+from .dino import DINOHead, dino
+from .vit import FusedLinear, VisionTransformer
 
 __all__ = ["HaloTransformer", "PyramidVisionTransformer", "SwinTransformer", "VisionTransformer",
            "DINOHead", "FusedLinear", "dino"]

@@ -9,7 +9,8 @@ ordinary out-of-place residual, which is what runs here.
 import torch
 from torch import nn
 
-from .layer import DropPath, PositionwiseFeedForward, check_no_dropout, ffn_branch
+from .layer import (DropPath, PositionwiseFeedForward, assign_drop_path, check_no_dropout, ffn_branch,
+                    init_transformer_weights, make_classifier, ramp_rates, transformer_layers)
 
 
 def halo_pos(window, halo):
@@ -123,20 +124,10 @@ class HaloTransformer(nn.Module):
             nn.LayerNorm(dims[-1] * 2),
             nn.SiLU(inplace=True),
         )
-        linear = nn.Linear(dims[-1] * 2, n_class)
-        nn.init.normal_(linear.weight, std=0.01)
-        nn.init.zeros_(linear.bias)
-        self.classifier = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(1), linear)
+        self.classifier = make_classifier(dims[-1] * 2, n_class, std=0.01)
         self.apply(self.init_weights)
 
-    def init_weights(self, module):
-        if isinstance(module, nn.Linear):
-            nn.init.normal_(module.weight, std=0.02)
-            if module.bias is not None:
-                nn.init.zeros_(module.bias)
-        elif isinstance(module, nn.LayerNorm):
-            nn.init.ones_(module.weight)
-            nn.init.zeros_(module.bias)
+    init_weights = staticmethod(init_transformer_weights)
 
     def make_block(self, depth, in_dim, dim, n_head, dim_head, dim_ff, window_size, halo_size, reduction,
                    drop_ff, drop_attn, drop_path):

@@ -70,3 +70,44 @@ def ffn_branch(x, drop_path, norm, ff, rows_per_sample):
     w1, b1, w2, b2 = ff.params()
     return FFNBranchFn.apply(x, drop_path.scale(x.shape[0]), norm.eps, rows_per_sample, norm.weight,
                              norm.bias, w1, b1, w2, b2)
+
+
+def init_transformer_weights(module, std=0.02):
+    """The initialisation every transformer family of the zoo applies through `self.apply(...)`
+    (vit.py:128-137, swin:323-333, pvt.py:227-237, halo:225-235, twins:306-316): N(0, std) Linear weights,
+    zero Linear biases, unit LayerNorm."""
+    if isinstance(module, nn.Linear):
+        nn.init.normal_(module.weight, std=std)
+        if module.bias is not None:
+            nn.init.zeros_(module.bias)
+    elif isinstance(module, nn.LayerNorm):
+        nn.init.ones_(module.weight)
+        nn.init.zeros_(module.bias)
+
+
+def transformer_layers(stages):
+    """Every sub-module with a `set_drop_path` method, in stage order (patch embeds / merges / PEGs are skipped)."""
+    return [m for stage in stages for m in stage if hasattr(m, "set_drop_path")]
+
+
+def assign_drop_path(layers, rates):
+    for layer, p in zip(layers, rates):
+        layer.set_drop_path(float(p))
+
+
+def linspace_rates(drop_path, n):
+    """torch.linspace(0, drop_path, n) as python floats (vit.py:104, pvt.py:207)."""
+    return torch.linspace(0, drop_path, n).tolist()
+
+
+def ramp_rates(drop_path, n):
+    """drop_path * i / n for i < n (swin:287-288, twins:268-269)."""
+    return [drop_path * float(i) / n for i in range(n)]
+
+
+def make_classifier(dim, n_class, std=0.02):
+    """AdaptiveAvgPool2d(1) - Flatten - Linear holder with the reference's names/indices (swin:278-281)."""
+    linear = nn.Linear(dim, n_class)
+    nn.init.normal_(linear.weight, std=std)
+    nn.init.zeros_(linear.bias)
+    return nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(1), linear)

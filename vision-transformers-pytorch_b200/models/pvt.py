@@ -2,9 +2,11 @@
 import torch
 from torch import nn
 
-from .layer import DropPath, PositionwiseFeedForward, check_no_dropout, ffn_branch, tuple2
+from .layer import (DropPath, PositionwiseFeedForward, assign_drop_path, check_no_dropout, ffn_branch,
+                    init_transformer_weights, linspace_rates, transformer_layers, tuple2)
 
-LayerNorm = lambda x: nn.LayerNorm(x, eps=1e-6)  # noqa: E731  (pvt.py:9)
+def LayerNorm(dim):  # pvt.py:9
+    return nn.LayerNorm(dim, eps=1e-6)
 
 
 class MultiHeadedAttention(nn.Module):
@@ -87,67 +89,55 @@ class PatchEmbedding(nn.Module):
 
 
 class PyramidVisionTransformer(nn.Module):
-    """pvt.py:146-280."""
+    """pvt.py:146-280: four stages of (conv patch embedding, SRA transformer layers); cls token at the last stage."""
+
+    PATCH_SIZES = (4, 2, 2, 2)
 
     def __init__(self, image_size, n_class, in_dim, depths, patch_embed_dims, n_heads, dim_ffs, reductions,
                  drop_ff=0, drop_attn=0, drop_path=0):
         super().__init__()
         self.depths = depths
-        self.patch_embedding = nn.ModuleList()
-        patch_embed_dims = list(patch_embed_dims)
-        patch_sizes = (4, 2, 2, 2)
-        img_size = tuple2(image_size)
-        in_dims = [in_dim] + patch_embed_dims[:-1]
-        for i, (p_in, p_out, p_size) in enumerate(zip(in_dims, patch_embed_dims, patch_sizes)):
-            last = i == len(patch_embed_dims) - 1
-            self.patch_embedding.append(
-                PatchEmbedding(img_size, p_in, p_out, p_size, cls_token=last, dropout=drop_ff))
-            img_size = (img_size[0] // p_size, img_size[1] // p_size)
-        for i in range(4):
-            setattr(self, f"block{i + 1}", self.make_block(depths[i], patch_embed_dims[i], n_heads[i],
-                                                           dim_ffs[i], reductions[i], drop_ff, drop_attn))
-        self.norm = LayerNorm(patch_embed_dims[-1])
-        self.classifier = nn.Linear(patch_embed_dims[-1], n_class)
+        dims = list(patch_embed_dims)
+        size = tuple2(image_size)
+        embeds = []
+        for stage, (width_in, width_out, patch) in enumerate(zip([in_dim] + dims[:-1], dims, self.PATCH_SIZES)):
+            embeds.append(PatchEmbedding(size, width_in, width_out, patch, cls_token=(stage == len(dims) - 1),
+                                         dropout=drop_ff))
+            size = (size[0] // patch, size[1] // patch)
+        self.patch_embedding = nn.ModuleList(embeds)
+        for stage in range(4):
+            layers = self.make_block(depths[stage], dims[stage], n_heads[stage], dim_ffs[stage], reductions[stage],
+                                     drop_ff, drop_attn)
+            setattr(self, f"block{stage + 1}", layers)
+        self.norm = LayerNorm(dims[-1])
+        self.classifier = nn.Linear(dims[-1], n_class)
         self.apply(self.init_weights)
         self.set_drop_path(drop_path)
+
+    init_weights = staticmethod(init_transformer_weights)
 
     def blocks(self):
         return (self.block1, self.block2, self.block3, self.block4)
 
     def set_drop_path(self, drop_path):
-        p = torch.linspace(0, drop_path, sum(self.depths)).tolist()
-        i = 0
-        for stage in self.blocks():
-            for layer in stage:
-                layer.set_drop_path(p[i])
-                i += 1
-
-    def init_weights(self, module):
-        if isinstance(module, nn.Linear):
-            nn.init.normal_(module.weight, std=0.02)
-            if module.bias is not None:
-                nn.init.zeros_(module.bias)
-        elif isinstance(module, nn.LayerNorm):
-            nn.init.ones_(module.weight)
-            nn.init.zeros_(module.bias)
+        layers = transformer_layers(self.blocks())
+        assign_drop_path(layers, linspace_rates(drop_path, len(layers)))
 
     def make_block(self, depth, dim, n_head, dim_ff, reduction, drop_ff, drop_attn):
-        return nn.ModuleList(
-            [TransformerLayer(dim, n_head, dim_ff, reduction=reduction, drop_ff=drop_ff, drop_attn=drop_attn)
-             for _ in range(depth)])
+        return nn.ModuleList(TransformerLayer(dim, n_head, dim_ff, reduction=reduction, drop_ff=drop_ff,
+                                              drop_attn=drop_attn) for _ in range(depth))
 
     def forward(self, input):
         from vtb200.blocks import LayerNormFn, LinearFn
 
-        batch = input.shape[0]
-        out = input
-        for i, stage in enumerate(self.blocks()):
-            out, (height, width) = self.patch_embedding[i](out)
-            for layer in stage:
+        batch, out = input.shape[0], input
+        for stage, layers in enumerate(self.blocks()):
+            out, (height, width) = self.patch_embedding[stage](out)
+            for layer in layers:
                 out = layer(out, height, width)
-            if i < 3:
-                # tokens -> NCHW view for the next stage's conv (pvt.py:261); stays a view, the patch
-                # gather reads the NHWC memory directly
+            if stage < 3:
+                # tokens -> NCHW *view* for the next stage's conv (pvt.py:261): no copy, the patch gather reads
+                # the NHWC memory directly
                 out = out.reshape(batch, height, width, -1).permute(0, 3, 1, 2)
-        out = LayerNormFn.apply(out[:, 0], self.norm.weight, self.norm.bias, self.norm.eps)
-        return LinearFn.apply(out, self.classifier.weight, self.classifier.bias)
+        cls = LayerNormFn.apply(out[:, 0], self.norm.weight, self.norm.bias, self.norm.eps)
+        return LinearFn.apply(cls, self.classifier.weight, self.classifier.bias)

@@ -8,7 +8,8 @@ from pydantic import StrictFloat, StrictInt
 from torch import nn
 
 from ._compat import config_model
-from .layer import DropPath, PositionwiseFeedForward, check_no_dropout, ffn_branch
+from .layer import (DropPath, PositionwiseFeedForward, assign_drop_path, check_no_dropout, ffn_branch,
+                    init_transformer_weights, make_classifier, ramp_rates, transformer_layers)
 
 LayerNorm = lambda x: nn.LayerNorm(x, eps=1e-6)  # noqa: E731  (twins.py:12)
 
@@ -140,10 +141,7 @@ class TwinsSVT(nn.Module):
             setattr(self, f"block{i + 1}", self.make_block(depths[i], in_dims[i], dims[i], n_heads[i], dim_head,
                                                            dim_ffs[i], window_size, red, drop_ff, drop_attn))
         self.final_linear = nn.Sequential(nn.LayerNorm(dims[-1]))
-        linear = nn.Linear(dims[-1], n_class)
-        nn.init.normal_(linear.weight, std=0.02)
-        nn.init.zeros_(linear.bias)
-        self.classifier = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(1), linear)
+        self.classifier = make_classifier(dims[-1], n_class)
         self.apply(self.init_weights)
         self.set_dropout(None, drop_path)
 
@@ -152,22 +150,10 @@ class TwinsSVT(nn.Module):
 
     def set_dropout(self, dropout, drop_path):
         """Linear ramp over transformer layers in stage order; patch embeds / PEGs are skipped (twins.py:267-304)."""
-        n_blocks = sum(self.depths)
-        i = 0
-        for stage in self.blocks():
-            for layer in stage:
-                if isinstance(layer, TransformerLayer):
-                    layer.set_drop_path(drop_path * float(i) / n_blocks)
-                    i += 1
+        layers = transformer_layers(self.blocks())
+        assign_drop_path(layers, ramp_rates(drop_path, sum(self.depths)))
 
-    def init_weights(self, module):
-        if isinstance(module, nn.Linear):
-            nn.init.normal_(module.weight, std=0.02)
-            if module.bias is not None:
-                nn.init.zeros_(module.bias)
-        elif isinstance(module, nn.LayerNorm):
-            nn.init.ones_(module.weight)
-            nn.init.zeros_(module.bias)
+    init_weights = staticmethod(init_transformer_weights)
 
     def make_block(self, depth, in_dim, dim, n_head, dim_head, dim_ff, window_size, reduction, drop_ff, drop_attn):
         block = [PatchEmbedding(in_dim, dim, reduction)]
