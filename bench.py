@@ -376,9 +376,16 @@ def main():
                 tf = f / (t * 1e-3) / 1e12 if f and t > 0 else 0.0
                 fh.write(f"{n:44s} n={c:4d} {t:9.3f} ms {100 * t / tot:5.1f}%  {tf:8.1f} TFLOP/s\n")
     peak_tf, peak_hbm, peak_src = peaks()
+    # DRAM traffic of the GEMM launches from the committed ncu capture of this same command (per launch, like `achieved`)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", f"r01_gemm_traffic_{args.workload}.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_unit": "bytes per GEMM launch (ncu dram__bytes_read+write, profiles/r01_gemm_traffic_*.json)",
+                "flop_per_launch": (gemm_flops / len(gemm)) if gemm else None, "peak_source": peak_src,
                 "launches_per_step": len(gemm), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
                 "model_tflops": value / world * wl["gflop"] / 1e3, "model_frac": value / world * wl["gflop"] / 1e3 / peak_tf}
 
