@@ -28,7 +28,8 @@ int vtb_init(void);
 /* Runtime switches.  "gemm_cluster" (0/1): run the GEMM as CTA pairs (thread-block clusters of 2) that
  * TMA-multicast the shared B tile into both CTAs' shared memory.  Default 0: measured neutral on B200.
  * "attn_tc" (0/1, default 1): use the tcgen05/TMEM attention kernels where they apply (global attention,
- * dh = 64, <= 256 keys); 0 forces the mma.sync kernels (A/B measurements, cross-checks). */
+ * dh = 64, <= 256 keys); 0 forces the mma.sync kernels (A/B measurements, cross-checks).
+ * "attn_wp" (0/1, default 1): one warp per (window, head) problem when nq, nkv <= 64; 0 = one CTA per problem. */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -126,8 +127,9 @@ typedef struct {
   const float* rel_bias;       /* [n_pos, heads] f32 (rel_pos.weight) or NULL */
   const int32_t* pos;          /* [nq, nkv] or NULL */
   int32_t n_pos;               /* rows of rel_bias (swin 169, halo 253; <= 512) */
-  const uint8_t* mask;         /* [n_mask, nq, nkv], 1 = masked (swin local_mask) or NULL */
+  const uint8_t* mask;         /* [n_mask, nq, mask_ld], 1 = masked (swin local_mask) or NULL */
   int32_t n_mask;
+  int32_t mask_ld;             /* row pitch of mask in bytes; 0 = nkv.  64 lets the window kernels fetch rows with 16-byte loads */
   /* backward only */
   const void* dout; int32_t lddo;
   void* dq; int32_t lddq;      /* bf16 */

@@ -66,15 +66,15 @@ __device__ __forceinline__ void load_rows(bf16 (*dst)[DH + 8], const bf16* base,
 struct BiasCtx {
   const float* table;   // smem copy of rel_bias[:, h] or null
   const int* pos;       // global [nq, nkv]
-  const uint8_t* mask;  // global, already offset to this group's [nq, nkv] slice, or null
-  int nq, nkv;
+  const uint8_t* mask;  // global, already offset to this group's [nq, mask_ld] slice, or null
+  int nq, nkv, mld;
 };
 __device__ __forceinline__ float score_bias(const BiasCtx& c, int i, int j, bool& masked) {
   masked = false;
   if (i >= c.nq) i = c.nq - 1;
   float b = 0.f;
   if (c.table) b = c.table[__ldg(c.pos + (long)i * c.nkv + j)];
-  if (c.mask && c.mask[(long)i * c.nkv + j]) masked = true;
+  if (c.mask && c.mask[(long)i * c.mld + j]) masked = true;
   return b;
 }
 
@@ -111,7 +111,8 @@ attn_fwd_kernel(vtb_attn_params p, Geom g, int q_tiles) {
   BiasCtx bc;
   bc.table = p.rel_bias ? sTab : nullptr;
   bc.pos = p.pos;
-  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  bc.mld = p.mask_ld > 0 ? p.mask_ld : g.nkv;
+  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * bc.mld : nullptr;
   bc.nq = g.nq; bc.nkv = g.nkv;
 
   float o[DH / 8][4];
@@ -310,7 +311,8 @@ attn_bwd_dq_kernel(vtb_attn_params p, Geom g, int q_tiles) {
   BiasCtx bc;
   bc.table = p.rel_bias ? sTab : nullptr;
   bc.pos = p.pos;
-  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  bc.mld = p.mask_ld > 0 ? p.mask_ld : g.nkv;
+  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * bc.mld : nullptr;
   bc.nq = g.nq; bc.nkv = g.nkv;
 
   float dq[DH / 8][4];
@@ -461,7 +463,8 @@ attn_bwd_dkv_kernel(vtb_attn_params p, Geom g, int kv_tiles) {
   BiasCtx bc;
   bc.table = p.rel_bias ? sTab : nullptr;
   bc.pos = p.pos;
-  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv : nullptr;
+  bc.mld = p.mask_ld > 0 ? p.mask_ld : g.nkv;
+  bc.mask = p.mask ? p.mask + (long)(grp % p.n_mask) * g.nq * bc.mld : nullptr;
   bc.nq = g.nq; bc.nkv = g.nkv;
 
   float dk[DH / 8][4], dv[DH / 8][4];
@@ -622,6 +625,7 @@ int make_geom(const vtb_attn_params* p, Geom* g, long* groups, const char* who) 
             -1, "%s: q/k/v must be 16-byte aligned rows", who);
   VTB_CHECK((p->rel_bias == nullptr) == (p->pos == nullptr), -1, "%s: rel_bias and pos go together", who);
   VTB_CHECK(!p->mask || p->n_mask > 0, -1, "%s: n_mask", who);
+  VTB_CHECK(!p->mask || p->mask_ld == 0 || p->mask_ld >= p->nkv, -1, "%s: mask_ld", who);
   VTB_CHECK(!p->rel_bias || (p->n_pos > 0 && p->n_pos <= MAX_POS), -1,
             "%s: rel_bias rows n_pos=%d must be in (0, %d]", who, p->n_pos, MAX_POS);
   return 0;
@@ -629,6 +633,9 @@ int make_geom(const vtb_attn_params* p, Geom* g, long* groups, const char* who) 
 
 }  // namespace
 
+bool vtb_attn_wp_ok(const vtb_attn_params* p, bool bwd);
+int vtb_attn_wp_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
+int vtb_attn_wp_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
 bool vtb_attn_tc_fwd_ok(const vtb_attn_params* p);
 int vtb_attn_tc_fwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p);
@@ -645,6 +652,7 @@ extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_)
   if (rc) return rc;
   VTB_CHECK(p->o && p->ldo % 2 == 0, -1, "vtb_attention_fwd: o");
   if (vtb_attn_tc_fwd_ok(p)) return vtb_attn_tc_fwd(p, stream);  // tcgen05 / TMEM path (global, dh 64, <= 256 keys)
+  if (vtb_attn_wp_ok(p, false)) return vtb_attn_wp_fwd(p, g, groups, stream);  // one warp per (window, head)
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_fwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const long blocks = groups * p->heads * q_tiles;
@@ -669,6 +677,7 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
             "vtb_attention_bwd: dq/dk/dv leading dims");
   const vtb_attn_params& q = *p;
   if (vtb_attn_tc_bwd_ok(p)) return vtb_attn_tc_bwd(p, stream);  // tcgen05 / TMEM path
+  if (vtb_attn_wp_ok(p, true)) return vtb_attn_wp_bwd(p, g, groups, stream);
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_bwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const int kv_tiles = (p->nkv + BKV - 1) / BKV;
@@ -796,10 +805,11 @@ __device__ __forceinline__ void res_group(const vtb_attn_params& p, const Geom& 
     s.qtok[i] = (qbase + i < q_end) ? (int)q_token(g, grp, qbase + i) : -1;
   for (int j = threadIdx.x; j < s.nkv16; j += blockDim.x) s.ktok[j] = (int)kv_token(g, grp, j);
   if (p.mask) {
-    const uint8_t* mask = p.mask + (long)(grp % p.n_mask) * g.nq * g.nkv;
+    const int mld = p.mask_ld > 0 ? p.mask_ld : g.nkv;
+    const uint8_t* mask = p.mask + (long)(grp % p.n_mask) * g.nq * mld;
     for (int e = threadIdx.x; e < g.nq * g.nkv; e += blockDim.x) {
       const int i = e / g.nkv, j = e - i * g.nkv;
-      s.maskb[i * s.bias_ld + j] = mask[e];
+      s.maskb[i * s.bias_ld + j] = mask[(long)i * mld + j];
     }
   }
   __syncthreads();  // token indices visible
@@ -1289,4 +1299,501 @@ int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, 
   }
   VTB_LAUNCH_CHECK();
   return 0;
+}
+
+// =====================================================================================================
+// Warp-per-problem attention for small problems (nq <= 64 and nkv <= 64: 7x7 windows of Swin / Twins).
+// With 49 tokens a (window, head) problem is only four 16-row MMA tiles; spreading it over four warps makes
+// every warp pay the whole per-problem overhead (token indices, loads, barriers) for a quarter of the work
+// (ncu: 11 k warp-instructions per problem, < 5 % of them MMAs).  Here ONE warp owns a problem end to end,
+// walks its tiles sequentially out of its private shared-memory slice, and loops over problems with no block
+// barrier at all; the four warps of a CTA share the per-head bias tile.  Mask rows arrive with 16-byte loads
+// (mask_ld = padded row pitch).
+// =====================================================================================================
+namespace {
+
+constexpr int WP_WARPS = 4;
+constexpr int WP_LD = 64;  // pitch of the bias / mask / pos tiles (key slots padded to 64)
+
+struct WpSmem {
+  float* bias;           // [nq][64]   shared by the CTA (table[pos], -inf beyond nkv)
+  unsigned short* pos;   // [nq][64]   (bwd)
+  float* tab;            // [n_pos]
+  float* dtab;           // [n_pos]    (bwd)
+  bf16 *q, *k, *v, *dO;  // per warp [64][DH]
+  uint8_t* maskb;        // per warp [nq][64]
+  float *lse, *delta;    // per warp [64] (bwd)
+  int *qtok, *ktok;      // per warp [64]
+};
+
+template <int DH>
+size_t wp_smem_bytes(int nq, bool bwd, int n_pos) {
+  size_t shared = (size_t)nq * WP_LD * 4 + (size_t)n_pos * 4 * (bwd ? 2 : 1) + (bwd ? (size_t)nq * WP_LD * 2 : 0);
+  size_t per_warp = (size_t)(bwd ? 4 : 3) * 64 * DH * 2 + (size_t)nq * WP_LD + 2 * 64 * 4 + (bwd ? 2 * 64 * 4 : 0);
+  return ((shared + 15) & ~(size_t)15) + WP_WARPS * ((per_warp + 15) & ~(size_t)15) + 32;
+}
+
+template <int DH>
+__device__ __forceinline__ WpSmem wp_carve(uint8_t* base, int nq, bool bwd, int n_pos, int warp) {
+  WpSmem s;
+  uint8_t* p = base;
+  s.bias = reinterpret_cast<float*>(p); p += (size_t)nq * WP_LD * 4;
+  s.tab = reinterpret_cast<float*>(p); p += (size_t)n_pos * 4;
+  s.dtab = reinterpret_cast<float*>(p); if (bwd) p += (size_t)n_pos * 4;
+  s.pos = reinterpret_cast<unsigned short*>(p); if (bwd) p += (size_t)nq * WP_LD * 2;
+  p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+  size_t per_warp = (size_t)(bwd ? 4 : 3) * 64 * DH * 2 + (size_t)nq * WP_LD + 2 * 64 * 4 + (bwd ? 2 * 64 * 4 : 0);
+  per_warp = (per_warp + 15) & ~(size_t)15;
+  p += (size_t)warp * per_warp;
+  s.q = reinterpret_cast<bf16*>(p); p += 64 * DH * 2;
+  s.k = reinterpret_cast<bf16*>(p); p += 64 * DH * 2;
+  s.v = reinterpret_cast<bf16*>(p); p += 64 * DH * 2;
+  s.dO = reinterpret_cast<bf16*>(p); if (bwd) p += 64 * DH * 2;
+  s.maskb = p; p += (size_t)nq * WP_LD;
+  s.qtok = reinterpret_cast<int*>(p); p += 64 * 4;
+  s.ktok = reinterpret_cast<int*>(p); p += 64 * 4;
+  s.lse = reinterpret_cast<float*>(p); if (bwd) p += 64 * 4;
+  s.delta = reinterpret_cast<float*>(p);
+  return s;
+}
+
+// once per CTA: per-head table -> smem, bias tile (and pos tile) with -inf padding beyond nkv
+__device__ __forceinline__ void wp_once(const vtb_attn_params& p, const Geom& g, int h, const WpSmem& s, bool bwd) {
+  if (p.rel_bias)
+    for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) {
+      s.tab[t] = __ldg(p.rel_bias + (long)t * g.heads + h);
+      if (bwd) s.dtab[t] = 0.f;
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < g.nq * WP_LD; e += blockDim.x) {
+    const int i = e / WP_LD, j = e - i * WP_LD;
+    float b = (j < g.nkv) ? 0.f : -INFINITY;
+    unsigned short pi = 0;
+    if (p.rel_bias && j < g.nkv) {
+      pi = (unsigned short)__ldg(p.pos + i * g.nkv + j);
+      b = s.tab[pi];
+    }
+    s.bias[e] = b;
+    if (bwd) s.pos[e] = pi;
+  }
+  __syncthreads();
+}
+
+// per problem, executed by ONE warp: token indices, mask rows, cp.async row loads
+template <int DH>
+__device__ __forceinline__ void wp_load(const vtb_attn_params& p, const Geom& g, int grp, int h, const WpSmem& s,
+                                        bool bwd, int lane, int mask_ld) {
+  for (int i = lane; i < 64; i += 32) {
+    s.qtok[i] = (int)q_token(g, grp, i);
+    s.ktok[i] = (int)kv_token(g, grp, i);
+  }
+  if (p.mask) {
+    const uint8_t* m = p.mask + (long)(grp % p.n_mask) * g.nq * mask_ld;
+    if (mask_ld == WP_LD) {
+      for (int c = lane; c < g.nq * (WP_LD / 16); c += 32)
+        cp_async16(smem_u32(s.maskb + c * 16), m + c * 16, true);
+    } else {
+      for (int e = lane; e < g.nq * g.nkv; e += 32) {
+        const int i = e / g.nkv, j = e - i * g.nkv;
+        s.maskb[i * WP_LD + j] = m[(long)i * mask_ld + j];
+      }
+    }
+  }
+  __syncwarp();
+  constexpr int CH = DH / 8;
+  for (int c = lane; c < 64 * CH; c += 32) {
+    const int r = c / CH, cc = c - r * CH;
+    const int tq_ = s.qtok[r], tk_ = s.ktok[r];
+    const long oq = (long)(tq_ < 0 ? 0 : tq_), ok = (long)(tk_ < 0 ? 0 : tk_);
+    cp_async16(smem_u32(s.q + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.q) + oq * p.ldq + h * DH + cc * 8, tq_ >= 0);
+    cp_async16(smem_u32(s.k + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.k) + ok * p.ldk + h * DH + cc * 8, tk_ >= 0);
+    cp_async16(smem_u32(s.v + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.v) + ok * p.ldv + h * DH + cc * 8, tk_ >= 0);
+    if (bwd)
+      cp_async16(smem_u32(s.dO + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.dout) + oq * p.lddo + h * DH + cc * 8, tq_ >= 0);
+  }
+  cp_async_commit();
+}
+
+template <int DH>
+__global__ void __launch_bounds__(WP_WARPS * 32, 2)
+attn_wp_fwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_ld) {
+  extern __shared__ __align__(16) uint8_t wp_smem[];
+  const int h = blockIdx.x % g.heads;
+  const int chunk = blockIdx.x / g.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool has_mask = p.mask != nullptr;
+  const WpSmem s = wp_carve<DH>(wp_smem, g.nq, false, p.rel_bias ? p.n_pos : 0, warp);
+  wp_once(p, g, h, s, false);
+  const int mtiles = (g.nq + 15) >> 4;
+  const int npair = (g.nkv + 15) >> 4;  // 16-key groups that hold real keys
+  const float sl2 = p.scale * 1.4426950408889634f;
+  bf16* O = reinterpret_cast<bf16*>(p.o);
+
+  for (int grp = chunk * WP_WARPS + warp; grp < groups; grp += nchunks * WP_WARPS) {
+    __syncwarp();  // previous problem's reads of this warp's slice are done
+    wp_load<DH>(p, g, grp, h, s, false, lane, mask_ld);
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int mt = 0; mt < mtiles; ++mt) {
+      const int r0 = mt * 16;
+      float sc[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) { sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        uint32_t qf[4];
+        ldsm_x4(qf, smem_u32(s.q + soff<DH>(r0 + (lane & 15), kk * 2 + (lane >> 4))));
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+          if (n2 < npair) {
+            uint32_t kb[4];
+            res_ld_b<DH>(kb, s.k, n2 * 16, kk, lane);
+            uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+            mma_bf16_16816(sc[2 * n2], qf, b0);
+            mma_bf16_16816(sc[2 * n2 + 1], qf, b1);
+          }
+        }
+      }
+      // logits in the log2 domain: s*scale*log2e + bias*log2e (bias tile already holds -inf for key padding)
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = min(r0 + gq + r * 8, g.nq - 1);
+        const float* brow = s.bias + i * WP_LD + 2 * tq;
+        const uint8_t* mrow = s.maskb + i * WP_LD + 2 * tq;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float v = fmaf(sc[n][2 * r + e], sl2, brow[n * 8 + e] * 1.4426950408889634f);
+            if (has_mask && mrow[n * 8 + e]) v = -INFINITY;
+            sc[n][2 * r + e] = v;
+            mx[r] = fmaxf(mx[r], v);
+          }
+        }
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_use = (mx[r] == -INFINITY) ? 0.f : mx[r];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = exp2f(sc[n][2 * r + e] - m_use);
+            sc[n][2 * r + e] = pv;
+            rs[r] += pv;
+          }
+        }
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      }
+      float o[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        if (k2 < npair) {
+          uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                            pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                            pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+#pragma unroll
+          for (int d2 = 0; d2 < DH / 16; ++d2) {
+            uint32_t vb[4];
+            res_ld_bt<DH>(vb, s.v, k2 * 16, d2, lane);
+            uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+            mma_bf16_16816(o[2 * d2], pa, b0);
+            mma_bf16_16816(o[2 * d2 + 1], pa, b1);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = r0 + gq + r * 8;
+        const int tok = s.qtok[row];
+        if (tok < 0) continue;
+        const float inv = 1.f / rs[r];
+        bf16* dst = O + (long)tok * p.ldo + h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) = pack_bf16(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+        if (tq == 0 && p.lse)
+          p.lse[((long)grp * g.heads + h) * g.nq + row] = (mx[r] + log2f(rs[r])) * 0.6931471805599453f;
+      }
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(WP_WARPS * 32, 2)
+attn_wp_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_ld) {
+  extern __shared__ __align__(16) uint8_t wp_smem[];
+  const int h = blockIdx.x % g.heads;
+  const int chunk = blockIdx.x / g.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool has_mask = p.mask != nullptr;
+  const bool has_tab = p.rel_bias != nullptr && p.drel_bias != nullptr;
+  const WpSmem s = wp_carve<DH>(wp_smem, g.nq, true, p.rel_bias ? p.n_pos : 0, warp);
+  wp_once(p, g, h, s, true);
+  const int qtiles = (g.nq + 15) >> 4, ktiles = (g.nkv + 15) >> 4;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  constexpr float L2E = 1.4426950408889634f;
+  const bf16* Og = reinterpret_cast<const bf16*>(p.o);
+  const bf16* dOg = reinterpret_cast<const bf16*>(p.dout);
+
+  for (int grp = chunk * WP_WARPS + warp; grp < groups; grp += nchunks * WP_WARPS) {
+    __syncwarp();
+    wp_load<DH>(p, g, grp, h, s, true, lane, mask_ld);
+    // delta_i = sum_d dO[i,d] O[i,d];  lse2_i = lse_i log2(e) (+inf for padding rows so that p = 0)
+    for (int row = lane; row < 64; row += 32) {
+      const int tok = s.qtok[row];
+      float acc = 0.f, l2 = INFINITY;
+      if (tok >= 0) {
+        const bf16* a = dOg + (long)tok * p.lddo + h * DH;
+        const bf16* b = Og + (long)tok * p.ldo + h * DH;
+#pragma unroll
+        for (int d = 0; d < DH; d += 8) {
+          const uint4 ra = *reinterpret_cast<const uint4*>(a + d);
+          const uint4 rb = *reinterpret_cast<const uint4*>(b + d);
+          const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
+            acc += fa.x * fb.x + fa.y * fb.y;
+          }
+        }
+        l2 = p.lse[((long)grp * g.heads + h) * g.nq + row] * L2E;
+      }
+      s.delta[row] = acc;
+      s.lse[row] = l2;
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // ---------------------------------------------------------------- phase A: dQ (+ bias gradient), rows = queries
+    for (int mt = 0; mt < qtiles; ++mt) {
+      const int r0 = mt * 16;
+      float sc[8][4], dp[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        uint32_t qf[4], dof[4];
+        ldsm_x4(qf, smem_u32(s.q + soff<DH>(r0 + (lane & 15), kk * 2 + (lane >> 4))));
+        ldsm_x4(dof, smem_u32(s.dO + soff<DH>(r0 + (lane & 15), kk * 2 + (lane >> 4))));
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+          if (n2 < ktiles) {
+            uint32_t kb[4], vb[4];
+            res_ld_b<DH>(kb, s.k, n2 * 16, kk, lane);
+            res_ld_b<DH>(vb, s.v, n2 * 16, kk, lane);
+            uint32_t k0[2] = {kb[0], kb[1]}, k1[2] = {kb[2], kb[3]};
+            uint32_t v0[2] = {vb[0], vb[1]}, v1[2] = {vb[2], vb[3]};
+            mma_bf16_16816(sc[2 * n2], qf, k0);
+            mma_bf16_16816(sc[2 * n2 + 1], qf, k1);
+            mma_bf16_16816(dp[2 * n2], dof, v0);
+            mma_bf16_16816(dp[2 * n2 + 1], dof, v1);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = min(r0 + gq + r * 8, g.nq - 1);
+        const float l2 = s.lse[r0 + gq + r * 8], dl = s.delta[r0 + gq + r * 8];
+        const float* brow = s.bias + i * WP_LD + 2 * tq;
+        const uint8_t* mrow = s.maskb + i * WP_LD + 2 * tq;
+        const unsigned short* prow = s.pos + i * WP_LD + 2 * tq;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float v = fmaf(sc[n][2 * r + e], sl2, fmaf(brow[n * 8 + e], L2E, -l2));
+            if (has_mask && mrow[n * 8 + e]) v = -INFINITY;
+            const float ds = exp2f(v) * (dp[n][2 * r + e] - dl);  // exp2(-inf) = 0: masked / padded entries vanish
+            sc[n][2 * r + e] = ds;
+            if (has_tab && ds != 0.f) atomicAdd(&s.dtab[prow[n * 8 + e]], ds);
+          }
+        }
+      }
+      float dq[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        if (k2 < ktiles) {
+          uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                            pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                            pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+#pragma unroll
+          for (int d2 = 0; d2 < DH / 16; ++d2) {
+            uint32_t kb[4];
+            res_ld_bt<DH>(kb, s.k, k2 * 16, d2, lane);
+            uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+            mma_bf16_16816(dq[2 * d2], pa, b0);
+            mma_bf16_16816(dq[2 * d2 + 1], pa, b1);
+          }
+        }
+      }
+      bf16* dQ = reinterpret_cast<bf16*>(p.dq);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int tok = s.qtok[r0 + gq + r * 8];
+        if (tok < 0) continue;
+        bf16* dst = dQ + (long)tok * p.lddq + h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n)
+          *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * tq) =
+              pack_bf16(dq[n][2 * r] * p.scale, dq[n][2 * r + 1] * p.scale);
+      }
+    }
+
+    // ---------------------------------------------------------------- phase B: dK, dV, rows = keys
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const int c0 = kt * 16;
+      float sc[8][4], dp[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        uint32_t kf[4], vf[4];
+        ldsm_x4(kf, smem_u32(s.k + soff<DH>(c0 + (lane & 15), kk * 2 + (lane >> 4))));
+        ldsm_x4(vf, smem_u32(s.v + soff<DH>(c0 + (lane & 15), kk * 2 + (lane >> 4))));
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+          if (n2 < qtiles) {
+            uint32_t qb[4], ob[4];
+            res_ld_b<DH>(qb, s.q, n2 * 16, kk, lane);
+            res_ld_b<DH>(ob, s.dO, n2 * 16, kk, lane);
+            uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+            uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+            mma_bf16_16816(sc[2 * n2], kf, q0);
+            mma_bf16_16816(sc[2 * n2 + 1], kf, q1);
+            mma_bf16_16816(dp[2 * n2], vf, o0);
+            mma_bf16_16816(dp[2 * n2 + 1], vf, o1);
+          }
+        }
+      }
+      // element (key j = c0 + gq + r*8, query i = n*8 + 2tq + e): bias / mask are indexed [i][j]
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = n * 8 + 2 * tq + e;
+          const int ic = min(i, g.nq - 1);
+          const float l2 = s.lse[i], dl = s.delta[i];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int j = c0 + gq + r * 8;
+            float v = fmaf(sc[n][2 * r + e], sl2, fmaf(s.bias[ic * WP_LD + j], L2E, -l2));
+            if (has_mask && s.maskb[ic * WP_LD + j]) v = -INFINITY;
+            const float pv = exp2f(v);
+            sc[n][2 * r + e] = pv;
+            dp[n][2 * r + e] = pv * (dp[n][2 * r + e] - dl);
+          }
+        }
+      }
+      float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+        dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        if (k2 < qtiles) {
+          uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                            pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                            pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+          uint32_t da[4] = {pack_bf16(dp[2 * k2][0], dp[2 * k2][1]), pack_bf16(dp[2 * k2][2], dp[2 * k2][3]),
+                            pack_bf16(dp[2 * k2 + 1][0], dp[2 * k2 + 1][1]),
+                            pack_bf16(dp[2 * k2 + 1][2], dp[2 * k2 + 1][3])};
+#pragma unroll
+          for (int d2 = 0; d2 < DH / 16; ++d2) {
+            uint32_t ob[4], qb[4];
+            res_ld_bt<DH>(ob, s.dO, k2 * 16, d2, lane);
+            res_ld_bt<DH>(qb, s.q, k2 * 16, d2, lane);
+            uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+            uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+            mma_bf16_16816(dv[2 * d2], pa, o0);
+            mma_bf16_16816(dv[2 * d2 + 1], pa, o1);
+            mma_bf16_16816(dk[2 * d2], da, q0);
+            mma_bf16_16816(dk[2 * d2 + 1], da, q1);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int tok = s.ktok[c0 + gq + r * 8];
+        if (tok < 0) continue;
+        bf16* dKp = reinterpret_cast<bf16*>(p.dk) + (long)tok * p.lddk + h * DH;
+        bf16* dVp = reinterpret_cast<bf16*>(p.dv) + (long)tok * p.lddv + h * DH;
+#pragma unroll
+        for (int n = 0; n < DH / 8; ++n) {
+          *reinterpret_cast<uint32_t*>(dKp + n * 8 + 2 * tq) =
+              pack_bf16(dk[n][2 * r] * p.scale, dk[n][2 * r + 1] * p.scale);
+          *reinterpret_cast<uint32_t*>(dVp + n * 8 + 2 * tq) = pack_bf16(dv[n][2 * r], dv[n][2 * r + 1]);
+        }
+      }
+    }
+  }
+  if (has_tab) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) {
+      const float v = s.dtab[t];
+      if (v != 0.f) atomicAdd(p.drel_bias + (long)t * g.heads + h, v);
+    }
+  }
+}
+
+bool g_attn_wp = true;
+
+template <int DH, bool BWD>
+int wp_launch(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+  const size_t smem = wp_smem_bytes<DH>(p->nq, BWD, p->rel_bias ? p->n_pos : 0);
+  VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention: warp-per-problem tile needs %zu B of shared memory", smem);
+  auto kern = BWD ? attn_wp_bwd_kernel<DH> : attn_wp_fwd_kernel<DH>;
+  static bool set = false;
+  if (!set) {
+    VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    set = true;
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WP_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  long nchunks = (long)vtb_num_sms() * per_sm / p->heads;
+  const long need = (groups + WP_WARPS - 1) / WP_WARPS;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > need) nchunks = need;
+  const long blocks = nchunks * p->heads;
+  VTB_CHECK(blocks < (1L << 31) && groups < (1L << 31), -1, "vtb_attention: grid too large");
+  const int mask_ld = p->mask ? (p->mask_ld > 0 ? p->mask_ld : p->nkv) : 0;
+  kern<<<(unsigned)blocks, WP_WARPS * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks, mask_ld);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+void vtb_attn_wp_set(bool on) { g_attn_wp = on; }
+
+bool vtb_attn_wp_ok(const vtb_attn_params* p, bool bwd) {
+  return g_attn_wp && p->mode != VTB_ATTN_HALO && p->nq <= 64 && p->nkv <= 64 && !(bwd && p->dkv_f32) &&
+         (!p->rel_bias || p->n_pos <= MAX_POS);
+}
+
+int vtb_attn_wp_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+  return p->dh == 64 ? wp_launch<64, false>(p, g, groups, stream) : wp_launch<32, false>(p, g, groups, stream);
+}
+int vtb_attn_wp_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+  return p->dh == 64 ? wp_launch<64, true>(p, g, groups, stream) : wp_launch<32, true>(p, g, groups, stream);
 }

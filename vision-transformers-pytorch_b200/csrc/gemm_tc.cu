@@ -650,11 +650,13 @@ int vtb_gemm_init() {
 int vtb_num_sms() { return g_num_sms; }
 
 void vtb_attn_tc_set(bool on);
+void vtb_attn_wp_set(bool on);
 
 extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value != 0; return 0; }
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
+  if (strcmp(name, "attn_wp") == 0) { vtb_attn_wp_set(value != 0); return 0; }
   vtb_set_error("vtb_set_option: unknown option '%s'", name);
   return -1;
 }

@@ -75,7 +75,13 @@ class MultiHeadedLocalAttention(nn.Module):
         key = (self.pos.device, self.pos._version, self.pos.data_ptr())
         if self._tab is None or self._tab[0] != key:
             pos32 = self.pos.to(torch.int32).contiguous()
-            mask8 = self.local_mask.to(torch.uint8).contiguous() if self.shift else None
+            mask8 = None
+            if self.shift:
+                # rows padded to a 64-byte pitch when they fit: the window kernels fetch them with 16-byte loads
+                m = self.local_mask.to(torch.uint8)
+                pitch = 64 if m.shape[2] <= 64 else m.shape[2]
+                mask8 = torch.zeros((m.shape[0], m.shape[1], pitch), dtype=torch.uint8, device=m.device)
+                mask8[:, :, :m.shape[2]] = m
             self._tab = (key, pos32, mask8)
         return self._tab[1], self._tab[2]
 

@@ -52,7 +52,7 @@ class AttnParams(C.Structure):
         ("lse", C.c_void_p),
         ("rel_bias", C.c_void_p),
         ("pos", C.c_void_p), ("n_pos", C.c_int32),
-        ("mask", C.c_void_p), ("n_mask", C.c_int32),
+        ("mask", C.c_void_p), ("n_mask", C.c_int32), ("mask_ld", C.c_int32),
         ("dout", C.c_void_p), ("lddo", C.c_int32),
         ("dq", C.c_void_p), ("lddq", C.c_int32),
         ("dk", C.c_void_p), ("lddk", C.c_int32),

@@ -207,9 +207,11 @@ class AttnSpec:
                 raise ValueError("vtb200.attention: pos must be contiguous int32 [nq, nkv]")
             p.rel_bias, p.pos, p.n_pos = self.rel_bias.data_ptr(), self.pos.data_ptr(), self.rel_bias.shape[0]
         if self.mask is not None:
-            if self.mask.dtype != torch.uint8 or not self.mask.is_contiguous():
-                raise ValueError("vtb200.attention: mask must be contiguous uint8 [n_mask, nq, nkv]")
-            p.mask, p.n_mask = self.mask.data_ptr(), self.mask.shape[0]
+            if self.mask.dtype != torch.uint8 or not self.mask.is_contiguous() or self.mask.dim() != 3:
+                raise ValueError("vtb200.attention: mask must be contiguous uint8 [n_mask, nq, nkv or padded pitch]")
+            if self.mask.shape[1] != self.nq or self.mask.shape[2] < self.nkv:
+                raise ValueError("vtb200.attention: mask shape does not match nq / nkv")
+            p.mask, p.n_mask, p.mask_ld = self.mask.data_ptr(), self.mask.shape[0], self.mask.shape[2]
 
 
 def _qkv_fill(p, q, k, v):
