@@ -1380,28 +1380,29 @@ __device__ __forceinline__ void wp_once(const vtb_attn_params& p, const Geom& g,
 }
 
 // per problem, executed by ONE warp: token indices, mask rows, cp.async row loads
-template <int DH>
+template <int DH, int NL = 32>
 __device__ __forceinline__ void wp_load(const vtb_attn_params& p, const Geom& g, int grp, int h, const WpSmem& s,
-                                        bool bwd, int lane, int mask_ld) {
-  for (int i = lane; i < 64; i += 32) {
+                                        bool bwd, int lane, int mask_ld, int pair_bar = 0) {
+  for (int i = lane; i < 64; i += NL) {
     s.qtok[i] = (int)q_token(g, grp, i);
     s.ktok[i] = (int)kv_token(g, grp, i);
   }
   if (p.mask) {
     const uint8_t* m = p.mask + (long)(grp % p.n_mask) * g.nq * mask_ld;
     if (mask_ld == WP_LD) {
-      for (int c = lane; c < g.nq * (WP_LD / 16); c += 32)
+      for (int c = lane; c < g.nq * (WP_LD / 16); c += NL)
         cp_async16(smem_u32(s.maskb + c * 16), m + c * 16, true);
     } else {
-      for (int e = lane; e < g.nq * g.nkv; e += 32) {
+      for (int e = lane; e < g.nq * g.nkv; e += NL) {
         const int i = e / g.nkv, j = e - i * g.nkv;
         s.maskb[i * WP_LD + j] = m[(long)i * mask_ld + j];
       }
     }
   }
-  __syncwarp();
+  if (NL == 32) __syncwarp();
+  else asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
   constexpr int CH = DH / 8;
-  for (int c = lane; c < 64 * CH; c += 32) {
+  for (int c = lane; c < 64 * CH; c += NL) {
     const int r = c / CH, cc = c - r * CH;
     const int tq_ = s.qtok[r], tk_ = s.ktok[r];
     const long oq = (long)(tq_ < 0 ? 0 : tq_), ok = (long)(tk_ < 0 ? 0 : tk_);
@@ -1527,13 +1528,16 @@ attn_wp_fwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_
   }
 }
 
+// Backward: TWO warps per problem share one shared-memory slice — warp role 0 runs phase A (dQ + bias gradient),
+// role 1 runs phase B (dK, dV) at the same time; they meet on a 64-thread named barrier around the loads.
 template <int DH>
-__global__ void __launch_bounds__(WP_WARPS * 32, 2)
+__global__ void __launch_bounds__(WP_WARPS * 64, 2)
 attn_wp_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_ld) {
   extern __shared__ __align__(16) uint8_t wp_smem[];
   const int h = blockIdx.x % g.heads;
   const int chunk = blockIdx.x / g.heads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) >> 1, role = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+  const int lane64 = role * 32 + lane;  // index inside the warp pair
   const int gq = lane >> 2, tq = lane & 3;
   const bool has_mask = p.mask != nullptr;
   const bool has_tab = p.rel_bias != nullptr && p.drel_bias != nullptr;
@@ -1546,10 +1550,11 @@ attn_wp_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_
   const bf16* dOg = reinterpret_cast<const bf16*>(p.dout);
 
   for (int grp = chunk * WP_WARPS + warp; grp < groups; grp += nchunks * WP_WARPS) {
-    __syncwarp();
-    wp_load<DH>(p, g, grp, h, s, true, lane, mask_ld);
+    asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");  // both warps are done with the previous problem
+    wp_load<DH, 64>(p, g, grp, h, s, true, lane64, mask_ld, warp + 1);
     // delta_i = sum_d dO[i,d] O[i,d];  lse2_i = lse_i log2(e) (+inf for padding rows so that p = 0)
-    for (int row = lane; row < 64; row += 32) {
+    {
+      const int row = lane64;
       const int tok = s.qtok[row];
       float acc = 0.f, l2 = INFINITY;
       if (tok >= 0) {
@@ -1572,9 +1577,10 @@ attn_wp_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_
       s.lse[row] = l2;
     }
     cp_async_wait<0>();
-    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");  // tiles, lse2, delta visible to the pair
 
     // ---------------------------------------------------------------- phase A: dQ (+ bias gradient), rows = queries
+    if (role == 0)
     for (int mt = 0; mt < qtiles; ++mt) {
       const int r0 = mt * 16;
       float sc[8][4], dp[8][4];
@@ -1655,6 +1661,7 @@ attn_wp_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int mask_
     }
 
     // ---------------------------------------------------------------- phase B: dK, dV, rows = keys
+    if (role == 1)
     for (int kt = 0; kt < ktiles; ++kt) {
       const int c0 = kt * 16;
       float sc[8][4], dp[8][4];
@@ -1767,8 +1774,9 @@ int wp_launch(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t
     VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     set = true;
   }
+  const int threads = BWD ? WP_WARPS * 64 : WP_WARPS * 32;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WP_WARPS * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
   if (per_sm < 1) per_sm = 1;
   long nchunks = (long)vtb_num_sms() * per_sm / p->heads;
   const long need = (groups + WP_WARPS - 1) / WP_WARPS;
@@ -1777,7 +1785,7 @@ int wp_launch(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t
   const long blocks = nchunks * p->heads;
   VTB_CHECK(blocks < (1L << 31) && groups < (1L << 31), -1, "vtb_attention: grid too large");
   const int mask_ld = p->mask ? (p->mask_ld > 0 ? p->mask_ld : p->nkv) : 0;
-  kern<<<(unsigned)blocks, WP_WARPS * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks, mask_ld);
+  kern<<<(unsigned)blocks, threads, smem, stream>>>(*p, g, (int)groups, (int)nchunks, mask_ld);
   VTB_LAUNCH_CHECK();
   return 0;
 }
