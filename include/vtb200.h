@@ -155,6 +155,10 @@ int vtb_cast_f32_bf16_2d(const float* src, int64_t lds, void* dst, int64_t ldd, 
  * bf16 copy of the residual-stream gradient that feeds the branch's dgrad/wgrad GEMMs (layer.py:178 adjoint). */
 int vtb_scale_cast_bf16(const float* src, const float* row_scale, int32_t rows_per_scale, int64_t rows,
                         int32_t cols, void* dst, vtb_stream_t stream);
+/* Same, and colsum[c] += sum_r dst[r, c] in the same pass (the bias gradient of the Linear that closes a branch:
+ * the scaled gradient IS that Linear's output gradient).  colsum f32 [cols], accumulated with atomicAdd. */
+int vtb_scale_cast_colsum_bf16(const float* src, const float* row_scale, int32_t rows_per_scale, int64_t rows,
+                               int32_t cols, void* dst, float* colsum, vtb_stream_t stream);
 /* SiLU on f32 (halo_transformer.py:218) and its adjoint. */
 int vtb_silu_fwd(const float* x, float* y, int64_t n, vtb_stream_t stream);
 int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, vtb_stream_t stream);

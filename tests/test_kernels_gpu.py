@@ -369,11 +369,18 @@ def test_attention_halo(ops, Hs, W, hl):
     dkv = torch.zeros(T, 2 * HD, dtype=F32, device="cuda")
     drel = torch.zeros_like(table)
     ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, dq, dkv[:, :HD], dkv[:, HD:], drel,
-                      dkv_f32=True)
+                      dkv_f32=True)  # query-centric path: fp32 atomics
     xg = x.grad.view(T, C3)
     assert rel(dq.float(), xg[:, :HD]) < 1.5e-2
     assert rel(dkv, xg[:, HD:]) < 1.5e-2
     assert rel(drel, tab.grad) < 1e-2
+    # key-centric path: bf16 dK / dV written without atomics by walking the neighbouring query blocks
+    d2 = torch.empty(T, 3 * HD, dtype=BF16, device="cuda")
+    drel2 = torch.zeros_like(table)
+    ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, d2[:, :HD], d2[:, HD:2 * HD],
+                      d2[:, 2 * HD:], drel2)
+    assert rel(d2.float(), xg) < 1.5e-2, rel(d2.float(), xg)
+    assert rel(drel2, tab.grad) < 1e-2
 
 
 def test_attention_fully_masked_rows_do_not_nan(ops):
@@ -402,6 +409,8 @@ def test_cast_colsum_scalecast(ops):
     got = ops.scale_cast_bf16(x[:1003 - 1003 % 59], s, 59)
     want = (x[:1003 - 1003 % 59] * s.repeat_interleave(59)[:, None]).to(BF16)
     assert torch.equal(got, want)
+    got2, cs = ops.scale_cast_colsum_bf16(x[:1003 - 1003 % 59], s, 59)
+    assert torch.equal(got2, want) and rel(cs, want.float().sum(0)) < 1e-5
     xb = x.to(BF16)
     acc = torch.ones(328, device="cuda")
     ops.colsum(xb, acc)

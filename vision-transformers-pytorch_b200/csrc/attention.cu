@@ -633,6 +633,8 @@ int make_geom(const vtb_attn_params* p, Geom* g, long* groups, const char* who) 
 
 }  // namespace
 
+bool vtb_attn_halo_dkv_ok(const vtb_attn_params* p);
+int vtb_attn_halo_dkv(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
 bool vtb_attn_wp_ok(const vtb_attn_params* p, bool bwd);
 int vtb_attn_wp_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
 int vtb_attn_wp_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
@@ -642,7 +644,7 @@ bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p);
 int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_resident_ok(const vtb_attn_params* p);
 int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
-int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
+int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream, int skip_dkv = 0);
 
 extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -678,6 +680,12 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
   const vtb_attn_params& q = *p;
   if (vtb_attn_tc_bwd_ok(p)) return vtb_attn_tc_bwd(p, stream);  // tcgen05 / TMEM path
   if (vtb_attn_wp_ok(p, true)) return vtb_attn_wp_bwd(p, g, groups, stream);
+  if (vtb_attn_resident_ok(p) && vtb_attn_halo_dkv_ok(p)) {
+    // halo: dQ + bias gradient query-centric (resident kernel, phase A only), dK / dV key-centric without atomics
+    int rc2 = vtb_attn_resident_bwd(p, g, groups, stream, 1);
+    if (rc2) return rc2;
+    return vtb_attn_halo_dkv(p, g, groups, stream);
+  }
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_bwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
   const int kv_tiles = (p->nkv + BKV - 1) / BKV;
@@ -975,7 +983,7 @@ attn_res_fwd_kernel(vtb_attn_params p, Geom g, int nsplit, int q_per_cta, int gr
 
 template <int DH>
 __global__ void __launch_bounds__(RES_THREADS, 1)
-attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks) {
+attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int skip_dkv) {
   extern __shared__ __align__(16) uint8_t res_smem[];
   const int h = blockIdx.x % g.heads;
   const int chunk = blockIdx.x / g.heads;
@@ -1111,7 +1119,7 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks) {
   }
 
   // ------------------------------------------------------------------ phase B: dK, dV (rows = keys)
-  {
+  if (!skip_dkv) {
     const int c0 = warp * 16;
     if (c0 < s.nkv16) {
       constexpr int PB = (DH == 64) ? 2 : 4;  // 16-query groups per pass (register budget: 128/thread)
@@ -1272,11 +1280,11 @@ int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, 
   return 0;
 }
 
-int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream, int skip_dkv) {
   const bool has_bias = p->rel_bias || p->mask;
   const size_t smem = res_smem_bytes(p->dh, p->nq, p->nq, p->nkv, true, has_bias, p->rel_bias != nullptr, p->n_pos);
   VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_bwd: resident tile needs %zu B of shared memory", smem);
-  const int nmax = p->nq > p->nkv ? p->nq : p->nkv;
+  const int nmax = (skip_dkv || p->nq > p->nkv) ? p->nq : p->nkv;  // phase A only needs one warp per 16 queries
   const int warps = (nmax + 15) / 16;
   static bool set64 = false, set32 = false;
   if (p->dh == 64 && !set64) { int rc = res_set_smem(attn_res_bwd_kernel<64>, smem); if (rc) return rc; set64 = true; }
@@ -1293,9 +1301,9 @@ int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, 
   const long blocks = nchunks * p->heads;
   VTB_CHECK(blocks < (1L << 31) && groups < (1L << 31), -1, "vtb_attention_bwd: grid too large");
   if (p->dh == 64) {
-    attn_res_bwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks);
+    attn_res_bwd_kernel<64><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks, skip_dkv);
   } else {
-    attn_res_bwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks);
+    attn_res_bwd_kernel<32><<<(unsigned)blocks, warps * 32, smem, stream>>>(*p, g, (int)groups, (int)nchunks, skip_dkv);
   }
   VTB_LAUNCH_CHECK();
   return 0;
@@ -1804,4 +1812,240 @@ int vtb_attn_wp_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaSt
 }
 int vtb_attn_wp_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
   return p->dh == 64 ? wp_launch<64, true>(p, g, groups, stream) : wp_launch<32, true>(p, g, groups, stream);
+}
+
+// =====================================================================================================
+// Halo attention backward, key-centric dK / dV (halo_transformer.py:74-106 adjoint).
+// A key/value token lies in the (W+2h)^2 halo of up to (2*ceil(h/W)+1)^2 blocks, so the query-centric kernel has
+// to scatter dK/dV with fp32 atomics (21 k atomics per (block, head)).  Here each CTA owns the W^2 tokens of ONE
+// block as keys and walks the neighbouring blocks whose halo covers them as queries: for neighbour (dy, dx) the
+// centre key (cy, cx) sits in slot (cy - W*dy + h, cx - W*dx + h) of that neighbour's halo window (valid when
+// inside [0, W+2h)^2).  S^T, P^T, dS^T are recomputed per neighbour from the neighbour's Q / dO / O / lse;
+// dK, dV accumulate in registers and are written once, in bf16, without atomics.
+// =====================================================================================================
+namespace {
+
+template <int DH>
+__global__ void __launch_bounds__(128, 3)
+attn_halo_dkv_kernel(vtb_attn_params p, Geom g) {
+  extern __shared__ __align__(16) uint8_t hk_smem[];
+  const int h = blockIdx.x % g.heads;
+  const int grp = blockIdx.x / g.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int W = g.window, HL = g.halo, KW = W + 2 * HL;
+  const int nq = g.nq;                       // W*W tokens per block
+  const int b = grp / g.nw, wi = grp - b * g.nw;
+  const int by = wi / g.nwx, bx = wi - by * g.nwx;
+  const int nby = g.Hs / W;
+  const int reach = (HL + W - 1) / W;        // neighbour blocks whose halo can reach this block
+  const float sl2 = p.scale * 1.4426950408889634f;
+  constexpr float L2E = 1.4426950408889634f;
+
+  // smem: K, V (own tokens), Q, dO (current neighbour) [64][DH]; lse2, delta [64]; tab [n_pos]; pos u16 [nq][nkv]
+  bf16* sK = reinterpret_cast<bf16*>(hk_smem);
+  bf16* sV = sK + 64 * DH;
+  bf16* sQ = sV + 64 * DH;
+  bf16* sdO = sQ + 64 * DH;
+  float* sLse = reinterpret_cast<float*>(sdO + 64 * DH);
+  float* sDelta = sLse + 64;
+  float* sTab = sDelta + 64;
+  int* sTok = reinterpret_cast<int*>(sTab + p.n_pos);       // [64] own tokens
+  int* sNTok = sTok + 64;                                   // [64] neighbour tokens
+  unsigned short* sPos = reinterpret_cast<unsigned short*>(sNTok + 64);  // [nq][nkv]
+
+  for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) sTab[t] = __ldg(p.rel_bias + (long)t * g.heads + h);
+  for (int e = threadIdx.x; e < nq * g.nkv; e += blockDim.x) sPos[e] = (unsigned short)__ldg(p.pos + e);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    int tok = -1;
+    if (i < nq) {
+      const int cy = i / W, cx = i - cy * W;
+      tok = (b * g.Hs + by * W + cy) * g.Ws + bx * W + cx;
+    }
+    sTok[i] = tok;
+  }
+  __syncthreads();
+  {
+    constexpr int CH = DH / 8;
+    for (int c = threadIdx.x; c < 64 * CH; c += blockDim.x) {
+      const int r = c / CH, cc = c - r * CH;
+      const int tok = sTok[r];
+      const long o = (long)(tok < 0 ? 0 : tok);
+      cp_async16(smem_u32(sK + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.k) + o * p.ldk + h * DH + cc * 8, tok >= 0);
+      cp_async16(smem_u32(sV + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.v) + o * p.ldv + h * DH + cc * 8, tok >= 0);
+    }
+    cp_async_commit();
+  }
+
+  const int c0 = warp * 16;  // this warp's 16 centre keys
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) {
+    dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+    dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+  }
+  const bf16* Og = reinterpret_cast<const bf16*>(p.o);
+  const bf16* dOg = reinterpret_cast<const bf16*>(p.dout);
+
+  for (int dy = -reach; dy <= reach; ++dy) {
+    const int ny = by + dy;
+    if (ny < 0 || ny >= nby) continue;         // CTA-uniform
+    for (int dx = -reach; dx <= reach; ++dx) {
+      const int nx = bx + dx;
+      if (nx < 0 || nx >= g.nwx) continue;
+      const int ngrp = b * g.nw + ny * g.nwx + nx;
+      __syncthreads();  // previous neighbour's tiles fully consumed
+      // neighbour query tokens, lse2, delta (two threads per row)
+      {
+        const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+        int tok = -1;
+        if (row < nq) {
+          const int ty = row / W, tx = row - ty * W;
+          tok = (b * g.Hs + ny * W + ty) * g.Ws + nx * W + tx;
+        }
+        float acc = 0.f;
+        if (tok >= 0) {
+          const bf16* a = dOg + (long)tok * p.lddo + h * DH + half * (DH / 2);
+          const bf16* c = Og + (long)tok * p.ldo + h * DH + half * (DH / 2);
+#pragma unroll
+          for (int d = 0; d < DH / 2; d += 8) {
+            const uint4 ra = *reinterpret_cast<const uint4*>(a + d);
+            const uint4 rc = *reinterpret_cast<const uint4*>(c + d);
+            const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wc[4] = {rc.x, rc.y, rc.z, rc.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fa = unpack_bf16(wa[q]), fc = unpack_bf16(wc[q]);
+              acc += fa.x * fc.x + fa.y * fc.y;
+            }
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0) {
+          sNTok[row] = tok;
+          sDelta[row] = acc;
+          sLse[row] = tok >= 0 ? p.lse[((long)ngrp * g.heads + h) * nq + row] * L2E : INFINITY;
+        }
+      }
+      __syncthreads();
+      {
+        constexpr int CH = DH / 8;
+        for (int c = threadIdx.x; c < 64 * CH; c += blockDim.x) {
+          const int r = c / CH, cc = c - r * CH;
+          const int tok = sNTok[r];
+          const long o = (long)(tok < 0 ? 0 : tok);
+          cp_async16(smem_u32(sQ + soff<DH>(r, cc)), reinterpret_cast<const bf16*>(p.q) + o * p.ldq + h * DH + cc * 8, tok >= 0);
+          cp_async16(smem_u32(sdO + soff<DH>(r, cc)), dOg + o * p.lddo + h * DH + cc * 8, tok >= 0);
+        }
+        cp_async_commit();
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+
+      // S^T = K Q^T, dP^T = V dO^T  (16 centre keys x 64 neighbour queries per warp)
+      float sc[8][4], dp[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        uint32_t kf[4], vf[4];
+        ldsm_x4(kf, smem_u32(sK + soff<DH>(c0 + (lane & 15), kk * 2 + (lane >> 4))));
+        ldsm_x4(vf, smem_u32(sV + soff<DH>(c0 + (lane & 15), kk * 2 + (lane >> 4))));
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+          uint32_t qb[4], ob[4];
+          res_ld_b<DH>(qb, sQ, n2 * 16, kk, lane);
+          res_ld_b<DH>(ob, sdO, n2 * 16, kk, lane);
+          uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+          uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+          mma_bf16_16816(sc[2 * n2], kf, q0);
+          mma_bf16_16816(sc[2 * n2 + 1], kf, q1);
+          mma_bf16_16816(dp[2 * n2], vf, o0);
+          mma_bf16_16816(dp[2 * n2 + 1], vf, o1);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int c = c0 + gq + r * 8;          // centre key index
+        const int cy = c / W, cx = c - cy * W;
+        const int ky = cy - W * dy + HL, kx = cx - W * dx + HL;
+        const bool kvalid = (c < nq) && ky >= 0 && ky < KW && kx >= 0 && kx < KW;
+        const int slot = kvalid ? ky * KW + kx : 0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int t = n * 8 + 2 * tq + e;   // neighbour query index
+            float pv = 0.f, ds = 0.f;
+            if (kvalid && t < nq) {
+              const float bias = sTab[sPos[t * g.nkv + slot]];
+              pv = exp2f(fmaf(sc[n][2 * r + e], sl2, fmaf(bias, L2E, -sLse[t])));
+              ds = pv * (dp[n][2 * r + e] - sDelta[t]);
+            }
+            sc[n][2 * r + e] = pv;
+            dp[n][2 * r + e] = ds;
+          }
+        }
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        uint32_t pa[4] = {pack_bf16(sc[2 * k2][0], sc[2 * k2][1]), pack_bf16(sc[2 * k2][2], sc[2 * k2][3]),
+                          pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]),
+                          pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3])};
+        uint32_t da[4] = {pack_bf16(dp[2 * k2][0], dp[2 * k2][1]), pack_bf16(dp[2 * k2][2], dp[2 * k2][3]),
+                          pack_bf16(dp[2 * k2 + 1][0], dp[2 * k2 + 1][1]),
+                          pack_bf16(dp[2 * k2 + 1][2], dp[2 * k2 + 1][3])};
+#pragma unroll
+        for (int d2 = 0; d2 < DH / 16; ++d2) {
+          uint32_t ob[4], qb[4];
+          res_ld_bt<DH>(ob, sdO, k2 * 16, d2, lane);
+          res_ld_bt<DH>(qb, sQ, k2 * 16, d2, lane);
+          uint32_t o0[2] = {ob[0], ob[1]}, o1[2] = {ob[2], ob[3]};
+          uint32_t q0[2] = {qb[0], qb[1]}, q1[2] = {qb[2], qb[3]};
+          mma_bf16_16816(dv[2 * d2], pa, o0);
+          mma_bf16_16816(dv[2 * d2 + 1], pa, o1);
+          mma_bf16_16816(dk[2 * d2], da, q0);
+          mma_bf16_16816(dk[2 * d2 + 1], da, q1);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int tok = sTok[c0 + gq + r * 8];
+    if (tok < 0) continue;
+    bf16* dKp = reinterpret_cast<bf16*>(p.dk) + (long)tok * p.lddk + h * DH;
+    bf16* dVp = reinterpret_cast<bf16*>(p.dv) + (long)tok * p.lddv + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<uint32_t*>(dKp + n * 8 + 2 * tq) = pack_bf16(dk[n][2 * r] * p.scale, dk[n][2 * r + 1] * p.scale);
+      *reinterpret_cast<uint32_t*>(dVp + n * 8 + 2 * tq) = pack_bf16(dv[n][2 * r], dv[n][2 * r + 1]);
+    }
+  }
+}
+
+}  // namespace
+
+bool vtb_attn_halo_dkv_ok(const vtb_attn_params* p) {
+  return p->mode == VTB_ATTN_HALO && !p->dkv_f32 && p->nq <= 64 && p->rel_bias != nullptr && p->n_pos <= MAX_POS;
+}
+
+int vtb_attn_halo_dkv(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
+  const size_t smem = (size_t)4 * 64 * p->dh * 2 + 2 * 64 * 4 + (size_t)p->n_pos * 4 + 2 * 64 * 4 +
+                      (size_t)p->nq * p->nkv * 2 + 16;
+  VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_bwd: halo dK/dV tile needs %zu B of shared memory", smem);
+  const long blocks = groups * p->heads;
+  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_bwd: grid too large");
+  static bool set64 = false, set32 = false;
+  if (p->dh == 64) {
+    if (!set64) { VTB_CUDA(cudaFuncSetAttribute(attn_halo_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set64 = true; }
+    attn_halo_dkv_kernel<64><<<(unsigned)blocks, 128, smem, stream>>>(*p, g);
+  } else {
+    if (!set32) { VTB_CUDA(cudaFuncSetAttribute(attn_halo_dkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set32 = true; }
+    attn_halo_dkv_kernel<32><<<(unsigned)blocks, 128, smem, stream>>>(*p, g);
+  }
+  VTB_LAUNCH_CHECK();
+  return 0;
 }

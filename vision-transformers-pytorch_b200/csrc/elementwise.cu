@@ -60,6 +60,40 @@ __global__ void scale_cast_kernel(const float* __restrict__ src, const float* __
   }
 }
 
+// g = bf16(src * scale[row]) and per-column sums of the ROUNDED values; thread = 4 consecutive columns,
+// blockDim.y row lanes, rows partitioned over blockIdx.y; CTA-level reduction in smem then one atomic per column.
+__global__ void __launch_bounds__(256)
+scale_cast_colsum_kernel(const float* __restrict__ src, const float* __restrict__ row_scale, int rows_per_scale,
+                         long rows, int cols, bf16* __restrict__ dst, float* __restrict__ colsum, long rows_per_block) {
+  __shared__ float part[8][32][4];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;  // group of 4 columns
+  const int rl = threadIdx.y;
+  const long r0 = (long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (4 * c4 < cols) {
+    for (long r = r0 + rl; r < r1; r += 8) {
+      const float sc = row_scale ? __ldg(row_scale + r / rows_per_scale) : 1.f;
+      const float4 v = *reinterpret_cast<const float4*>(src + r * cols + 4 * c4);
+      const uint32_t lo = pack_bf16(v.x * sc, v.y * sc), hi = pack_bf16(v.z * sc, v.w * sc);
+      *reinterpret_cast<uint2*>(dst + r * cols + 4 * c4) = make_uint2(lo, hi);
+      const float2 f0 = unpack_bf16(lo), f1 = unpack_bf16(hi);
+      a0 += f0.x; a1 += f0.y; a2 += f1.x; a3 += f1.y;
+    }
+  }
+  part[rl][threadIdx.x][0] = a0; part[rl][threadIdx.x][1] = a1;
+  part[rl][threadIdx.x][2] = a2; part[rl][threadIdx.x][3] = a3;
+  __syncthreads();
+  if (rl == 0 && 4 * c4 < cols) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v += part[i][threadIdx.x][j];
+      atomicAdd(colsum + 4 * c4 + j, v);
+    }
+  }
+}
+
 __global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = silu_f(x[i]);
@@ -383,6 +417,22 @@ extern "C" int vtb_scale_cast_bf16(const float* src, const float* row_scale, int
   VTB_CHECK(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, -1, "vtb_scale_cast_bf16: alignment");
   scale_cast_kernel<<<grid_for(rows * (cols / 4), 256, 2), 256, 0, (cudaStream_t)s>>>(
       src, row_scale, rows_per_scale, rows, cols, (bf16*)dst);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vtb_scale_cast_colsum_bf16(const float* src, const float* row_scale, int32_t rows_per_scale,
+                                          int64_t rows, int32_t cols, void* dst, float* colsum, vtb_stream_t s) {
+  VTB_CHECK(src && dst && colsum && rows > 0 && cols > 0 && cols % 4 == 0, -1, "vtb_scale_cast_colsum_bf16: bad args");
+  VTB_CHECK(!row_scale || rows_per_scale > 0, -1, "vtb_scale_cast_colsum_bf16: rows_per_scale");
+  VTB_CHECK(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, -1, "vtb_scale_cast_colsum_bf16: alignment");
+  const int gx = (cols / 4 + 31) / 32;
+  int gy = (6 * (vtb_num_sms() > 0 ? vtb_num_sms() : 148) + gx - 1) / gx;
+  long rpb = (rows + gy - 1) / gy;
+  if (rpb < 64) rpb = 64;
+  gy = (int)((rows + rpb - 1) / rpb);
+  scale_cast_colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)s>>>(src, row_scale, rows_per_scale, rows, cols,
+                                                                            (bf16*)dst, colsum, rpb);
   VTB_LAUNCH_CHECK();
   return 0;
 }

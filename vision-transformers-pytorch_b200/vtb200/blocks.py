@@ -72,8 +72,7 @@ class FFNBranchFn(Function):
         y, u, h, w1b, w2b, dp_scale, rps = ctx.stash
         C = x2.shape[1]
         d2 = _c(dout).view(-1, C)
-        g = ops.scale_cast_bf16(d2, dp_scale, rps)
-        db2 = ops.colsum(g)
+        g, db2 = ops.scale_cast_colsum_bf16(d2, dp_scale, rps)
         dw2 = _wgrad(g, h)
         du = _dgrad(g, w2b, epilogue=_l.EPI_SILU_GRAD, aux=u)
         db1 = ops.colsum(du)
@@ -118,14 +117,14 @@ class AttnBranchFn(Function):
         C = x2.shape[1]
         HD = spec.heads * spec.dh
         d2 = _c(dout).view(-1, C)
-        g = ops.scale_cast_bf16(d2, dp_scale, rps)
-        db_o = ops.colsum(g)
+        g, db_o = ops.scale_cast_colsum_bf16(d2, dp_scale, rps)
         dw_o = _wgrad(g, o)
         do = _dgrad(g, wob)
         dqkv = torch.empty_like(qkv)
         drel = torch.zeros_like(spec.rel_bias) if spec.rel_bias is not None else None
-        if spec.mode == _l.ATTN_HALO:
-            # key/value tokens are shared by neighbouring blocks' halos -> fp32 atomics, then one cast
+        if spec.mode == _l.ATTN_HALO and spec.nq > 64:
+            # large halo blocks: key/value tokens shared by neighbouring blocks -> fp32 atomics, then one cast
+            # (blocks of <= 64 tokens take the key-centric kernel below, which writes bf16 without atomics)
             dkv = torch.zeros((qkv.shape[0], 2 * HD), dtype=F32, device=qkv.device)
             ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do,
                               dqkv[:, :HD], dkv[:, :HD], dkv[:, HD:], drel, dkv_f32=True)
@@ -200,8 +199,7 @@ class SRABranchFn(Function):
          scramble) = ctx.stash
         B, N, C, R, Hs, Ws = dims
         d2 = _c(dout).view(-1, C)
-        g = ops.scale_cast_bf16(d2, dp_scale, rps)
-        db_o = ops.colsum(g)
+        g, db_o = ops.scale_cast_colsum_bf16(d2, dp_scale, rps)
         dw_o = _wgrad(g, o)
         do = _dgrad(g, wob)
         dq = torch.empty_like(q)

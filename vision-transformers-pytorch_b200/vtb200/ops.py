@@ -301,6 +301,22 @@ def scale_cast_bf16(src, row_scale=None, rows_per_scale=0):
     return dst
 
 
+def scale_cast_colsum_bf16(src, row_scale=None, rows_per_scale=0):
+    """(bf16(src * row_scale[row // rows_per_scale]), its column sums) in one pass over src."""
+    lib = _l.get()
+    if src.dtype != F32 or not src.is_contiguous():
+        raise ValueError("vtb200.scale_cast_colsum_bf16: contiguous f32 expected")
+    cols = src.shape[-1]
+    rows = src.numel() // cols
+    dst = torch.empty((rows, cols), dtype=BF16, device=src.device)
+    cs = torch.zeros(cols, dtype=F32, device=src.device)
+    with _prof("scale_cast_colsum_bf16"):
+        _l.check(lib.vtb_scale_cast_colsum_bf16(_p(src), _p(row_scale), rows_per_scale, rows, cols, _p(dst), _p(cs),
+                                                _stream()), lib)
+    _count()
+    return dst, cs
+
+
 def colsum(x, out=None):
     lib = _l.get()
     _chk2d(x, BF16, "colsum")
