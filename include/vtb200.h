@@ -94,12 +94,15 @@ int vtb_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
  *   if dx_bf16 != NULL: dx_bf16[r] = bf16(dx_out[r] * (row_scale ? row_scale[r / rows_per_scale] : 1))
  *   partial dgamma/dbeta are accumulated into dgamma/dbeta (f32 [cols], atomicAdd; caller zeroes or
  *   passes the .grad buffer to accumulate into).
+ *   if dx_colsum != NULL (needs dx_bf16, dense rows, cols <= 768): dx_colsum[c] += sum_r float(dx_bf16[r, c]) — the
+ *   bias gradient of the Linear that produced this residual stream (its DropPath scale folded in through
+ *   row_scale), so the caller's next backward step needs no separate cast / column-sum pass over dx_out.
  */
 int vtb_layernorm_bwd(const void* dy, int32_t dy_f32, const float* x, const float* gamma,
                       const float* mean, const float* rstd, int64_t rows, int32_t cols,
                       int32_t patch_s, int32_t Hin, int32_t Win, const float* dx_in, float* dx_out,
                       void* dx_bf16, const float* row_scale, int32_t rows_per_scale,
-                      float* dgamma, float* dbeta, vtb_stream_t stream);
+                      float* dgamma, float* dbeta, float* dx_colsum, vtb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-head attention, all four variants of the reference through one geometry descriptor:

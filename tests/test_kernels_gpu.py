@@ -30,13 +30,24 @@ def bf(t):
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+@pytest.fixture(params=[0, 2], ids=["tiles_1cta", "tiles_pair"])
+def gemm_mode(request):
+    """Every GEMM test runs with independent 128-row tiles and with CTA pairs (cta_group::2, 256-row tiles) forced
+    wherever legal; the library default (1) picks pairs only when they can fill the machine."""
+    from vtb200 import lib
+
+    lib.set_option("gemm_cluster", request.param)
+    yield request.param
+    lib.set_option("gemm_cluster", 1)
+
+
 GEMM_SHAPES = [(128, 64, 64), (256, 256, 128), (300, 200, 72), (128, 96, 48), (1000, 768, 768), (197 * 4, 2304, 768),
                (64, 1000, 768), (513, 328, 1096)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("layout", ["nt", "nn", "tt", "tn"])
-def test_gemm_layouts(ops, M, N, K, layout):
+def test_gemm_layouts(ops, gemm_mode, M, N, K, layout):
     """C = A B^T for all four operand-major combinations (forward / dgrad / wgrad read layouts)."""
     if layout != "nt" and (M % 8 or N % 8):
         pytest.skip("MN-major operands need M, N multiples of 8 (16-byte TMA strides)")
@@ -55,15 +66,11 @@ def test_gemm_layouts(ops, M, N, K, layout):
 
 
 @pytest.mark.parametrize("layout", ["nt", "nn", "tt", "tn"])
-def test_gemm_cluster_pairs_multicast(ops, layout):
-    """>= 148 tiles -> CTA pairs with TMA-multicast B; odd number of row tiles -> one phantom tile per group."""
+def test_gemm_cta_pairs_default_heuristic(ops, layout):
+    """>= 74 pair tiles -> the default heuristic takes CTA pairs; odd number of row tiles -> one phantom half tile."""
     from vtb200 import lib
 
-    lib.set_option("gemm_cluster", 1)
-    try:
-        _cluster_case(ops, lib, layout)
-    finally:
-        lib.set_option("gemm_cluster", 0)
+    _cluster_case(ops, lib, layout)
 
 
 def _cluster_case(ops, lib, layout):
@@ -92,7 +99,7 @@ def _cluster_case(ops, lib, layout):
         assert rel(got, want) < 1e-5
 
 
-def test_gemm_strided_views(ops):
+def test_gemm_strided_views(ops, gemm_mode):
     """Operands that are column slices of wider buffers (q/k/v inside the fused qkv buffer)."""
     g = torch.Generator(device="cuda").manual_seed(5)
     big = bf(torch.randn(400, 3 * 128, device="cuda", generator=g))
@@ -103,7 +110,7 @@ def test_gemm_strided_views(ops):
         assert rel(got, a.float() @ W.float().t()) < 1e-5
 
 
-def test_gemm_epilogue_bias_silu_dual(ops):
+def test_gemm_epilogue_bias_silu_dual(ops, gemm_mode):
     g = torch.Generator(device="cuda").manual_seed(1)
     M, N, K = 392, 512, 192
     A, W = bf(torch.randn(M, K, device="cuda", generator=g)), bf(torch.randn(N, K, device="cuda", generator=g) * 0.1)
@@ -119,7 +126,7 @@ def test_gemm_epilogue_bias_silu_dual(ops):
     assert rel(h.float(), want_h) < 4e-3
 
 
-def test_gemm_epilogue_silu_grad(ops):
+def test_gemm_epilogue_silu_grad(ops, gemm_mode):
     from vtb200 import lib
 
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -133,7 +140,7 @@ def test_gemm_epilogue_silu_grad(ops):
     assert got.dtype == BF16 and rel(got.float(), want) < 4e-3  # bf16 store
 
 
-def test_gemm_epilogue_residual_droppath(ops):
+def test_gemm_epilogue_residual_droppath(ops, gemm_mode):
     g = torch.Generator(device="cuda").manual_seed(3)
     B, n, N, K = 6, 50, 256, 320
     M = B * n
@@ -147,7 +154,7 @@ def test_gemm_epilogue_residual_droppath(ops):
     assert torch.equal(got[:n], resid[:n])  # dropped sample: the branch contributes exactly zero
 
 
-def test_gemm_splitk_accumulate_and_group_rows(ops):
+def test_gemm_splitk_accumulate_and_group_rows(ops, gemm_mode):
     g = torch.Generator(device="cuda").manual_seed(4)
     T, N, K = 4096 + 72, 256, 192
     Gd, X = bf(torch.randn(T, N, device="cuda", generator=g)), bf(torch.randn(T, K, device="cuda", generator=g))
@@ -158,7 +165,7 @@ def test_gemm_splitk_accumulate_and_group_rows(ops):
     assert rel(got2, 2 * want) < 1e-5
 
 
-def test_gemm_unaligned_output_falls_back_to_direct_path(ops):
+def test_gemm_unaligned_output_falls_back_to_direct_path(ops, gemm_mode):
     """N=10 / N=50 heads: rows are not 16-byte multiples -> per-thread epilogue instead of TMA stores."""
     g = torch.Generator(device="cuda").manual_seed(8)
     for N in (10, 50, 1000):
@@ -186,7 +193,8 @@ def test_gemm_rejects_bad_arguments(ops):
 
 
 # ----------------------------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("rows,cols", [(197 * 3, 768), (1000, 96), (77, 1536), (64, 32), (5, 384)])
+@pytest.mark.parametrize("rows,cols", [(197 * 3, 768), (1000, 96), (77, 1536), (64, 32), (5, 384), (4099, 768),
+                                       (20001, 96), (3001, 320), (2500, 512), (1003, 192), (9, 64)])
 @pytest.mark.parametrize("eps", [1e-6, 1e-5])
 def test_layernorm_fwd_bwd(ops, rows, cols, eps):
     from oracle import restate as R
@@ -211,6 +219,31 @@ def test_layernorm_fwd_bwd(ops, rows, cols, eps):
     assert rel(dg, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4  # fp32 atomics: order-dependent
     dx2, _, _, _ = ops.layernorm_bwd(dy.to(BF16), x.detach(), w.detach(), mean, rstd)
     assert rel(dx2, x.grad) < 5e-3
+    if cols <= 768:  # fused column sums of the scaled bf16 copy (the producer Linear's bias gradient)
+        cs = torch.zeros(cols, device="cuda")
+        _, dxb2, _, _ = ops.layernorm_bwd(dy.to(BF16), x.detach(), w.detach(), mean, rstd, dx_in=dx_in, want_bf16=True,
+                                          row_scale=scale, rows_per_scale=1, colsum_out=cs)
+        assert rel(cs, dxb2.float().sum(0)) < 1e-4
+
+
+def test_layernorm_stream_and_register_kernels_agree(ops):
+    """The bulk-copy streaming kernels against the register-resident ones (vtb_set_option ln_stream)."""
+    from vtb200 import lib as L
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(5000, 384, device="cuda", generator=g) * 3 + 1
+    w = 1 + 0.1 * torch.randn(384, device="cuda", generator=g)
+    b = 0.1 * torch.randn(384, device="cuda", generator=g)
+    dy = torch.randn(5000, 384, device="cuda", generator=g).to(BF16)
+    res = []
+    for on in (1, 0):
+        L.set_option("ln_stream", on)
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
+        dx, _, dg, db = ops.layernorm_bwd(dy, x, w, mean, rstd, dx_in=x)
+        res.append((y.float(), mean, rstd, dx, dg, db))
+    L.set_option("ln_stream", 1)
+    for a, c in zip(*res):
+        assert rel(a, c) < 1e-5
 
 
 def test_layernorm_patchify_prologue(ops):

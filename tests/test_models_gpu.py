@@ -99,6 +99,36 @@ def test_vit_train_mode_droppath_matches_oracle_with_shared_masks(monkeypatch):
             assert rel(p.grad, sd[k].grad) < GRAD_TOL, k
 
 
+@pytest.mark.parametrize("drop_path", [0.0, 0.5])
+def test_backward_handoff_is_used_and_changes_nothing(drop_path):
+    """The LayerNorm backward hands bf16(dx * scale) + its column sums to the next branch backward
+    (vtb200.blocks hand-off slot): same gradients as the stand-alone cast + column-sum pass, and actually taken."""
+    import models
+    from oracle import restate as R
+    from vtb200 import blocks
+
+    cfg = dict(head=None, image_size=64, window_size=16, depth=3, dim=128, n_head=2, dim_ff=256, dropout=0., drop_attn=0.,
+               drop_ff=0., drop_path=drop_path)
+    model = R.randomize_(models.VisionTransformer(**cfg), 5).cuda().train()
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    grads = []
+    for on in (True, False):
+        blocks.HANDOFF = on
+        blocks.STATS.update(handoff=0, recomputed=0)
+        torch.manual_seed(1)  # same DropPath masks
+        model.zero_grad(set_to_none=True)
+        model(x).square().sum().backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+        if on:
+            assert blocks.STATS["handoff"] == 5 and blocks.STATS["recomputed"] == 1, blocks.STATS
+        else:
+            assert blocks.STATS["handoff"] == 0
+    blocks.HANDOFF = True
+    for k in grads[0]:
+        if grads[1][k].norm() > 1e-6:
+            assert rel(grads[0][k], grads[1][k]) < 1e-4, k
+
+
 def test_swin_stage_shapes_at_224_match_oracle():
     """One full-resolution Swin forward (window 7, all four stage geometries incl. the 7x7 wrap-around stage)."""
     import models

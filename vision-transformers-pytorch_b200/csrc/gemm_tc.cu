@@ -29,8 +29,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
-bool g_use_clusters = false;  // CTA-pair TMA multicast of B: measured neutral on B200 (L2 dedups), so opt-in
-                              // (vtb_set_option("gemm_cluster", 1) or VTB_GEMM_CLUSTER=1)
+int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces 1-CTA tiles,
+                              // 2 forces pairs wherever legal (tests)
 
 struct EpiParams {
   int M, N;
@@ -52,14 +52,16 @@ struct EpiParams {
   int tma;  // 1: staged TMA-store epilogue (tensor maps valid)
 };
 
-template <int BN>
+template <int BN, int CL>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  // CL = 2: CTA pair (cta_group::2), each CTA stages its 128 rows of A and HALF of the B tile
+  static constexpr int B_STAGE_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 512 / 256 / 128
   // epilogue staging: 2 output buffers + 3 aux buffers (second output, or prefetched residual / pre-activation)
   static constexpr int STAGING_BYTES = (2 + 3) * EPI_BUF_BYTES;
+  static constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align*/ - 256 /*barriers*/;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 6 ? 6 : (RING_BUDGET / STAGE_BYTES);  // 3/4/6 (CL=1), 4/6/6 (CL=2)
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 512 / 256 / 128
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -242,18 +244,20 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
   }
 }
 
-// CL = CTAs per cluster along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent
-// output tiles that share the same B tile: each CTA fetches HALF of B and TMA-multicasts it into both CTAs'
-// shared memory, so L2 -> SM operand traffic per tile drops from 48 KB to 32 KB per k-block (the mainloop is
-// L2-bandwidth bound: profiles/r01_ncu_gemm_*.txt).  Stage release is signalled to both producers by a
-// multicast tcgen05.commit; the CTAs stay in lock-step because they walk identical (n, k) sequences.
+// CL = CTAs per cluster along M (1 or 2).  CL = 2 is the CTA-pair mode of the 5th-gen tensor cores: ONE
+// tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA drives the tensor cores of both SMs on a 256 x BN output
+// tile; each CTA stages its own 128 rows of A and HALF of the B tile (the halves are exchanged by the hardware), so
+// per-SM operand traffic (L2 -> smem writes and smem -> tensor-core reads) drops by a third against two independent
+// 128 x BN tiles and the ring gets deeper.  Both producers credit the LEADER's full barrier; the leader's
+// tcgen05.commit multicasts stage release / accumulator-ready to both CTAs; the peer's epilogue warps hand the TMEM
+// stage back with remote mbarrier arrives.
 template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
                const __grid_constant__ CUtensorMap tma_aux, int m_tiles, int n_tiles, int k_blocks,
                int splits, EpiParams epi) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -279,16 +283,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 8 * CL);  // every epilogue warp of the pair arrives on the leader's barrier
     }
     for (int i = 0; i < N_AUX; ++i) mbar_init(&aux_full[i], 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (CL == 1) tmem_alloc(tmem_slot, C::TMEM_COLS); else tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
@@ -314,18 +320,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int kb1 = min(k_blocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
           uint8_t* b_dst = sB + stage * C::B_STAGE_BYTES;
-          if (!A_MN) {
-            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              tma_load_2d(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64,
-                          kb * BK);
-          }
           if (CL == 1) {
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+            }
             if (!B_MN) {
               tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
             } else {
@@ -334,17 +339,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 tma_load_2d(b_dst + i * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
             }
           } else {
-            // this CTA's half of the B tile, delivered to the same smem offset of BOTH CTAs of the cluster
-            constexpr uint16_t mask = (uint16_t)((1u << CL) - 1);
-            if (!B_MN) {
-              tma_load_2d_mc(b_dst + rank * (BN / CL) * 128, &tma_b, &full_bar[stage], kb * BK,
-                             n_blk * BN + rank * (BN / CL), mask);
+            // the leader's barrier collects the bytes of BOTH CTAs (its expect_tx may race with the peer's
+            // complete_tx: the phase cannot complete before the leader's own arrive)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES * CL);
+            if (!A_MN) {
+              tma_load_2d_pair(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64 / CL; ++i) {
-                const int bi = rank * (BN / 64 / CL) + i;
-                tma_load_2d_mc(b_dst + bi * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + bi * 64, kb * BK, mask);
-              }
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d_pair(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+            }
+            // this CTA's half of the B tile's N range
+            if (!B_MN) {
+              tma_load_2d_pair(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN + rank * (BN / CL));
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64 / CL; ++i)
+                tma_load_2d_pair(b_dst + i * (BK * 128), &tma_b, &full_bar[stage],
+                                 n_blk * BN + (rank * (BN / 64 / CL) + i) * 64, kb * BK);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -352,9 +364,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ------------------------------------------------------------ UMMA issuer (the leader CTA only in pair mode)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -380,13 +392,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                         : umma_desc_sw128(a_base + k * (UMMA_K * 2), 0, 1024);
             const uint64_t bdesc = B_MN ? umma_desc_sw128(b_base + k * (UMMA_K * 128), BK * 128, 1024)
                                         : umma_desc_sw128(b_base + k * (UMMA_K * 2), 0, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CL == 1) umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          else umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));  // ... in every CTA of the cluster
+          else umma_commit_pair(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs in pair mode)
+        if (CL == 1) umma_commit(&tmem_full[as]); else umma_commit_pair(&tmem_full[as], (uint16_t)0x3);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -417,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     } else {
@@ -480,7 +494,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (last) {  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
               }
               if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
               staged_row<16>(epi, acc, nc, rs, ob, ab, cb, swz, false, true);
@@ -491,7 +505,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (last) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
               }
               if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
               staged_row<32>(epi, acc, nc, rs, ob, ab, cb, swz, dual, false);
@@ -500,7 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (last) {  // dead trailing sub-tile: still release the TMEM stage
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[as]);
+              if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
             }
             if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
           }
@@ -540,7 +554,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // peers may still multicast into / arrive on our smem
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CL == 1) tmem_dealloc(tmem_base, C::TMEM_COLS); else tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -566,7 +580,7 @@ int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
 
 template <int BN, bool A_MN, bool B_MN, int CL>
 int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   CUtensorMap ta, tb;
   int rc;
   if (!A_MN) rc = make_tmap(&ta, p->A, p->K, p->M, p->lda, BK, BM);
@@ -643,7 +657,7 @@ int vtb_gemm_init() {
   VTB_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, -2,
             "cuTensorMapEncodeTiled not available from the driver");
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (const char* e = getenv("VTB_GEMM_CLUSTER")) g_use_clusters = (e[0] != '0');
+  if (const char* e = getenv("VTB_GEMM_CLUSTER")) g_use_clusters = atoi(e);
   return 0;
 }
 
@@ -651,12 +665,14 @@ int vtb_num_sms() { return g_num_sms; }
 
 void vtb_attn_tc_set(bool on);
 void vtb_attn_wp_set(bool on);
+void vtb_ln_stream_set(bool on);
 
 extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
-  if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value != 0; return 0; }
+  if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
   if (strcmp(name, "attn_wp") == 0) { vtb_attn_wp_set(value != 0); return 0; }
+  if (strcmp(name, "ln_stream") == 0) { vtb_ln_stream_set(value != 0); return 0; }
   vtb_set_error("vtb_set_option: unknown option '%s'", name);
   return -1;
 }
@@ -718,22 +734,26 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   const int m_tiles = (p->M + BM - 1) / BM;
   const int n_tiles = (p->N + bn - 1) / bn;
   const int k_blocks = (p->K + BK - 1) / BK;
+  // CTA pairs (256 x bn tiles, cta_group::2) whenever there are at least two row tiles and the pairs can fill the
+  // machine; an MN-major B tile of 64 columns is one TMA box and cannot be halved
+  bool pair = g_use_clusters && m_tiles >= 2 && !(p->b_mn_major && bn < 128);
+  const long units = (long)(pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;  // work items before split-K
+  const int slots = pair ? g_num_sms / 2 : g_num_sms;                        // concurrently resident work items
   int splits = p->splits;
   if (splits <= 0) {
     splits = 1;
     if (p->accumulate && !p->bias) {
-      // split-K so that the tile count fills whole waves of the persistent grid: among the split factors
-      // that leave >= 8 k-blocks per slice pick the one with the best wave efficiency (fewest slices on ties)
-      const int tiles = m_tiles * n_tiles;
+      // split-K so that the work items fill whole waves of the persistent grid: among the split factors that
+      // leave >= 8 k-blocks per slice pick the one with the best wave efficiency (fewest slices on ties)
       int maxs = k_blocks / 8;
       if (maxs < 1) maxs = 1;
       if (maxs > 64) maxs = 64;
       double best = -1.0;
       for (int sp = 1; sp <= maxs; ++sp) {
-        const long t = (long)tiles * sp;
-        const long waves = (t + g_num_sms - 1) / g_num_sms;
-        double eff = (double)t / (double)(waves * g_num_sms);
-        if (t < g_num_sms) eff = (double)t / g_num_sms;
+        const long t = units * sp;
+        const long waves = (t + slots - 1) / slots;
+        double eff = (double)t / (double)(waves * slots);
+        if (t < slots) eff = (double)t / slots;
         eff -= 0.002 * sp;  // reduce-add traffic grows with the split factor
         if (eff > best + 1e-9) { best = eff; splits = sp; }
       }
@@ -744,9 +764,7 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
     int per = (k_blocks + splits - 1) / splits;
     splits = (k_blocks + per - 1) / per;
   }
-  // CTA pairs with multicast B whenever there are at least two row tiles and enough work for every SM
-  const bool pair = g_use_clusters && m_tiles >= 2 && (long)m_tiles * n_tiles * splits >= g_num_sms &&
-                    !(p->b_mn_major && bn < 128);  // an MN-major B tile of 64 columns is one TMA box: cannot be halved
+  if (pair && g_use_clusters != 2 && units * splits < slots) pair = false;  // too little work for pairs: independent 128-row tiles spread wider
   switch (bn) {
     case 256: return pair ? dispatch_major<256, 2>(p, e, splits, stream) : dispatch_major<256, 1>(p, e, splits, stream);
     case 128: return pair ? dispatch_major<128, 2>(p, e, splits, stream) : dispatch_major<128, 1>(p, e, splits, stream);

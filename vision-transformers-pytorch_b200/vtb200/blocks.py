@@ -8,6 +8,9 @@ the reference-named modules (models/*.py); bf16 operand copies are made per call
 Reference call sites: vit.py:59-63, swin_transformer.py:193-197, pvt.py:97-101,
 halo_transformer.py:146-150 (restated out-of-place), twins.py:191-197, layer.py:166-196.
 """
+import threading
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -31,6 +34,62 @@ def _dgrad(g, w_bf16, **kw):
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------ residual-stream gradient hand-off
+# Every branch backward starts with g = bf16(dout * DropPath scale) and its column sums (the output Linear's bias
+# gradient), and ends with a LayerNorm backward that WRITES the tensor the next branch backward receives as dout.
+# The LayerNorm-backward kernel can emit that g and its column sums while dx is still in registers, which removes
+# one full read of the fp32 gradient per branch.  The producer of a branch input is recorded at forward time
+# (single slot: branches chain directly through the residual stream); the hint produced at backward time is also a
+# single slot and is only used if the consumer sees the very same, unmodified tensor with the very same scale.
+class _Slots(threading.local):
+    producer = None  # (weakref to the last branch output, dp_scale, rows_per_scale)
+    hint = None      # (dx, version, g_bf16, colsum, dp_scale, rows_per_scale)
+
+
+_slots = _Slots()
+HANDOFF = True  # module switch (tests / A-B timing)
+STATS = {"handoff": 0, "recomputed": 0}
+
+
+def _producer_of(x):
+    """(dp_scale, rows_per_scale) of the branch whose output IS this branch's input tensor, else None."""
+    p = _slots.producer
+    if HANDOFF and p is not None and p[0]() is x and x.is_contiguous() and x.shape[-1] <= 768:
+        return p[1], p[2]
+    return None
+
+
+def _register_output(out, dp_scale, rows_per_scale):
+    _slots.producer = (weakref.ref(out), dp_scale, rows_per_scale)
+    return out
+
+
+def _grad_operand(d2, dp_scale, rows_per_scale):
+    """(bf16(d2 * scale), column sums): taken from the hand-off slot when the LayerNorm backward that produced d2
+    already made them, else one fused cast + column-sum pass."""
+    h, _slots.hint = _slots.hint, None
+    if (h is not None and h[0].data_ptr() == d2.data_ptr() and h[0].numel() == d2.numel() and h[1] == d2._version
+            and h[4] is dp_scale and (dp_scale is None or h[5] == rows_per_scale)):
+        STATS["handoff"] += 1
+        return h[2], h[3]
+    STATS["recomputed"] += 1
+    return ops.scale_cast_colsum_bf16(d2, dp_scale, rows_per_scale)
+
+
+def _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up):
+    """LayerNorm backward of a branch (+ residual gradient d2); with a known producer `up` = (scale, rows_per_scale)
+    also emits that producer's gradient operand and bias gradient into the hand-off slot."""
+    if up is None:
+        dx, _, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2)
+        return dx, dg, dbeta
+    scale, rps = up
+    cs = torch.zeros(x2.shape[1], dtype=F32, device=x2.device)
+    dx, g, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2, want_bf16=True, row_scale=scale,
+                                         rows_per_scale=rps if scale is not None else 0, colsum_out=cs)
+    _slots.hint = (dx, dx._version, g, cs, scale, rps)
+    return dx, dg, dbeta
 
 
 def make_drop_path_scale(module_training, p, batch, like):
@@ -62,23 +121,23 @@ class FFNBranchFn(Function):
         out = ops.gemm(h, w2b, out_dtype=F32, bias=b2, resid=x2, row_scale=dp_scale,
                        rows_per_scale=rows_per_sample)
         ctx.save_for_backward(x2, ln_w, mean, rstd)
-        ctx.stash = (y, u, h, w1b, w2b, dp_scale, rows_per_sample)
-        return out.view(shape)
+        ctx.stash = (y, u, h, w1b, w2b, dp_scale, rows_per_sample, _producer_of(x))
+        return _register_output(out.view(shape), dp_scale, rows_per_sample)
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         x2, ln_w, mean, rstd = ctx.saved_tensors
-        y, u, h, w1b, w2b, dp_scale, rps = ctx.stash
+        y, u, h, w1b, w2b, dp_scale, rps, up = ctx.stash
         C = x2.shape[1]
         d2 = _c(dout).view(-1, C)
-        g, db2 = ops.scale_cast_colsum_bf16(d2, dp_scale, rps)
+        g, db2 = _grad_operand(d2, dp_scale, rps)
         dw2 = _wgrad(g, h)
         du = _dgrad(g, w2b, epilogue=_l.EPI_SILU_GRAD, aux=u)
         db1 = ops.colsum(du)
         dw1 = _wgrad(du, y)
         dy = _dgrad(du, w1b)
-        dx, _, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2)
+        dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
         return dx.view(dout.shape), None, None, None, dg, dbeta, dw1, db1, dw2, db2
 
 
@@ -106,18 +165,18 @@ class AttnBranchFn(Function):
         out = ops.gemm(o, wob, out_dtype=F32, bias=b_o, resid=x2, row_scale=dp_scale,
                        rows_per_scale=rows_per_sample)
         ctx.save_for_backward(x2, ln_w, mean, rstd)
-        ctx.stash = (y, qkv, o, lse, wqb, wob, dp_scale, rows_per_sample, spec, b_qkv is not None)
-        return out.view(shape)
+        ctx.stash = (y, qkv, o, lse, wqb, wob, dp_scale, rows_per_sample, spec, b_qkv is not None, _producer_of(x))
+        return _register_output(out.view(shape), dp_scale, rows_per_sample)
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         x2, ln_w, mean, rstd = ctx.saved_tensors
-        y, qkv, o, lse, wqb, wob, dp_scale, rps, spec, has_bqkv = ctx.stash
+        y, qkv, o, lse, wqb, wob, dp_scale, rps, spec, has_bqkv, up = ctx.stash
         C = x2.shape[1]
         HD = spec.heads * spec.dh
         d2 = _c(dout).view(-1, C)
-        g, db_o = ops.scale_cast_colsum_bf16(d2, dp_scale, rps)
+        g, db_o = _grad_operand(d2, dp_scale, rps)
         dw_o = _wgrad(g, o)
         do = _dgrad(g, wob)
         dqkv = torch.empty_like(qkv)
@@ -135,7 +194,7 @@ class AttnBranchFn(Function):
         db_qkv = ops.colsum(dqkv) if has_bqkv else None
         dw_qkv = _wgrad(dqkv, y)
         dy = _dgrad(dqkv, wqb)
-        dx, _, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2)
+        dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
         return (dx.view(dout.shape), None, None, None, None, None, None, dg, dbeta, dw_qkv, db_qkv, dw_o,
                 db_o, drel)
 
@@ -188,18 +247,19 @@ class SRABranchFn(Function):
                        rows_per_scale=rows_per_sample)
         ctx.save_for_backward(x2, ln_w, mean, rstd, rn_w)
         ctx.stash = (y, q, kv, kvin, o, lse, wqb, wkvb, wob, dp_scale, rows_per_sample, spec, red_stash,
-                     (B, N, C, R, Hs, Ws), w_r.shape if w_r is not None else None, kv_norm, scramble)
-        return out.view(shape)
+                     (B, N, C, R, Hs, Ws), w_r.shape if w_r is not None else None, kv_norm, scramble,
+                     _producer_of(x))
+        return _register_output(out.view(shape), dp_scale, rows_per_sample)
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         x2, ln_w, mean, rstd, rn_w = ctx.saved_tensors
         (y, q, kv, kvin, o, lse, wqb, wkvb, wob, dp_scale, rps, spec, red_stash, dims, wr_shape, kv_norm,
-         scramble) = ctx.stash
+         scramble, up) = ctx.stash
         B, N, C, R, Hs, Ws = dims
         d2 = _c(dout).view(-1, C)
-        g, db_o = ops.scale_cast_colsum_bf16(d2, dp_scale, rps)
+        g, db_o = _grad_operand(d2, dp_scale, rps)
         dw_o = _wgrad(g, o)
         do = _dgrad(g, wob)
         dq = torch.empty_like(q)
@@ -227,7 +287,7 @@ class SRABranchFn(Function):
         else:
             dy_kv = _dgrad(dkv, wkvb, out_dtype=F32)
             dy = _dgrad(dq, wqb, out_dtype=F32, resid=dy_kv)
-        dx, _, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2)
+        dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
         return (dx.view(dout.shape), None, None, None, None, dg, dbeta, dw_q, dw_kv, dw_o, db_o, dw_r,
                 db_r, drn_w, drn_b)
 

@@ -87,7 +87,7 @@ def load():
     lib.vtb_gemm_bf16.argtypes = [C.POINTER(GemmParams), vp]
     lib.vtb_layernorm_fwd.argtypes = [vp, vp, vp, f32, i64, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp]
     lib.vtb_layernorm_bwd.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp,
-                                      i32, vp, vp, vp]
+                                      i32, vp, vp, vp, vp]
     lib.vtb_attention_fwd.argtypes = [C.POINTER(AttnParams), vp]
     lib.vtb_attention_bwd.argtypes = [C.POINTER(AttnParams), vp]
     lib.vtb_cast_f32_bf16.argtypes = [vp, vp, i64, vp]

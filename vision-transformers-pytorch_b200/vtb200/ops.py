@@ -155,8 +155,9 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, patchify=None, rowmod_
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_in=None, dx_out=None, patchify=None, want_bf16=False,
-                  row_scale=None, rows_per_scale=0, dgamma=None, dbeta=None):
-    """Returns dx (f32, same shape as x), optional bf16 scaled copy, dgamma, dbeta (accumulated)."""
+                  row_scale=None, rows_per_scale=0, dgamma=None, dbeta=None, colsum_out=None):
+    """Returns dx (f32, same shape as x), optional bf16 scaled copy, dgamma, dbeta (accumulated).
+    colsum_out (f32 [cols], pre-zeroed) additionally receives the column sums of the bf16 copy."""
     lib = _l.get()
     cols = dy.shape[-1]
     rows = dy.numel() // cols
@@ -173,7 +174,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_in=None, dx_out=None, patchify
     with _prof("layernorm_bwd"):
         _l.check(lib.vtb_layernorm_bwd(_p(dy), int(dy.dtype == F32), _p(x), _p(gamma), _p(mean), _p(rstd),
                                        rows, cols, s, H, W, _p(dx_in), _p(dx_out), _p(dxb), _p(row_scale),
-                                       rows_per_scale, _p(dgamma), _p(dbeta), _stream()), lib)
+                                       rows_per_scale, _p(dgamma), _p(dbeta), _p(colsum_out), _stream()), lib)
     _count()
     return dx_out, dxb, dgamma, dbeta
 
