@@ -141,6 +141,10 @@ typedef struct {
   int32_t dkv_f32;
   float* delta;                /* workspace [groups, H, Nq] */
   float* drel_bias;            /* [n_pos, heads] f32, atomicAdd */
+  /* optional, lets WINDOW problems with a mask take the tcgen05 window kernels: the mask as one 64-bit word per row,
+   * [n_mask][2][64] uint64: word [m][0][i] has bit j set where mask[m, i, j] != 0 (query rows, forward),
+   * word [m][1][j] has bit i set where mask[m, i, j] != 0 (key rows, backward).  NULL with mask != NULL -> mma.sync path. */
+  const void* mask_bits;
 } vtb_attn_params;
 
 int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream);

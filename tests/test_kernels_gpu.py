@@ -371,6 +371,38 @@ def test_attention_window_swin(ops, Hs, shift):
     _window_case(ops, Hs, 7, shift, H=3, dh=32, B=2, seed=Hs + int(shift))
 
 
+@pytest.mark.parametrize("B,Hs,shift", [(3, 7, True), (2, 14, True), (1, 21, False), (5, 7, False)])
+def test_attention_window_tcgen05_and_mma_paths_agree(ops, B, Hs, shift):
+    """The tcgen05 window kernels (two windows per 128-row tile) and the mma.sync warp-per-window kernels implement the
+    same contract; odd group counts leave half a tile empty."""
+    from oracle import restate as R
+    from vtb200 import lib
+
+    H, dh, W = 3, 32, 7
+    HD, T = H * dh, B * Hs * Hs
+    g = torch.Generator(device="cuda").manual_seed(100 + Hs + B)
+    qkv = bf(torch.randn(T, 3 * HD, device="cuda", generator=g))
+    do = bf(torch.randn(T, HD, device="cuda", generator=g))
+    pos, mask = R.swin_tables(Hs, Hs, W, shift)
+    table = 0.5 * torch.randn((2 * W - 1) ** 2, H, device="cuda", generator=g)
+    spec = ops.AttnSpec(lib.ATTN_WINDOW, B, H, dh, W * W, W * W, Hs=Hs, Ws=Hs, window=W, shift=(W // 2) if shift else 0,
+                        rel_bias=table, pos=pos.to(torch.int32).cuda(), mask=mask.to(torch.uint8).cuda() if shift else None)
+    res = {}
+    for mode in (1, 0):
+        lib.set_option("attn_wt", mode)
+        try:
+            o, lse = ops.attention_fwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:])
+            d = torch.empty_like(qkv)
+            drel = torch.zeros_like(table)
+            ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, d[:, :HD], d[:, HD:2 * HD],
+                              d[:, 2 * HD:], drel)
+            res[mode] = (o.float(), lse, d.float(), drel)
+        finally:
+            lib.set_option("attn_wt", 1)
+    assert rel(res[1][0], res[0][0]) < 6e-3 and rel(res[1][1], res[0][1]) < 1e-4
+    assert rel(res[1][2], res[0][2]) < 1.5e-2 and rel(res[1][3], res[0][3]) < 1e-2
+
+
 def test_attention_window_plain_twins(ops):
     _window_case(ops, 14, 7, False, H=2, dh=64, B=2, seed=77, use_bias=False)
 

@@ -642,6 +642,9 @@ bool vtb_attn_tc_fwd_ok(const vtb_attn_params* p);
 int vtb_attn_tc_fwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p);
 int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream);
+bool vtb_attn_wt_ok(const vtb_attn_params* p, bool bwd);
+int vtb_attn_wt_fwd(const vtb_attn_params* p, cudaStream_t stream);
+int vtb_attn_wt_bwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_resident_ok(const vtb_attn_params* p);
 int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
 int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream, int skip_dkv = 0);
@@ -654,6 +657,7 @@ extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_)
   if (rc) return rc;
   VTB_CHECK(p->o && p->ldo % 2 == 0, -1, "vtb_attention_fwd: o");
   if (vtb_attn_tc_fwd_ok(p)) return vtb_attn_tc_fwd(p, stream);  // tcgen05 / TMEM path (global, dh 64, <= 256 keys)
+  if (vtb_attn_wt_ok(p, false)) return vtb_attn_wt_fwd(p, stream);  // tcgen05 window tiles (two windows per 128-row tile, dh 32)
   if (vtb_attn_wp_ok(p, false)) return vtb_attn_wp_fwd(p, g, groups, stream);  // one warp per (window, head)
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_fwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
@@ -679,6 +683,7 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
             "vtb_attention_bwd: dq/dk/dv leading dims");
   const vtb_attn_params& q = *p;
   if (vtb_attn_tc_bwd_ok(p)) return vtb_attn_tc_bwd(p, stream);  // tcgen05 / TMEM path
+  if (vtb_attn_wt_ok(p, true)) return vtb_attn_wt_bwd(p, stream);
   if (vtb_attn_wp_ok(p, true)) return vtb_attn_wp_bwd(p, g, groups, stream);
   if (vtb_attn_resident_ok(p) && vtb_attn_halo_dkv_ok(p)) {
     // halo: dQ + bias gradient query-centric (resident kernel, phase A only), dK / dV key-centric without atomics

@@ -1,0 +1,670 @@
+// tcgen05 / TMEM shifted-window attention (Swin / Twins-LSA: W^2 <= 64 tokens per window, dh = 32), forward and
+// backward.  swin_transformer.py:103-160, twins.py:109-152.
+//
+// A window is a 49 x 49 x 32 problem — far below one UMMA tile — so TWO windows share every 128-row tile and the
+// two problems are kept apart by stacking them along the CONTRACTION dimension:
+//     A rows (w, t) hold window w's 32 features in columns [32 w, 32 w + 32) of a 64-wide K axis, zeros elsewhere
+//     B rows  t     hold [window 0 features | window 1 features]
+//   =>  D[(w, t), u] = A_w[t] . B_w[u]: the two diagonal blocks of the 128 x 128 product in 64 TMEM columns, no
+//       off-diagonal work and no garbage.  The same tiles serve the other products as MN-major operands (the padded
+//       tile as B kills the cross-window terms), so nothing is transposed or copied.
+// One persistent CTA per SM, fixed head per CTA (its bias tile lives in shared memory for the whole kernel):
+//   warps 0-1  : loaders, one token row of each window per thread, cp.async 16-byte gathers straight out of the
+//                fused qkv buffer (window partition and cyclic shift are address arithmetic), two tiles in flight
+//   warp 2     : tcgen05.mma issuer (one thread), TMEM allocation
+//   warps 4-11 : math, one tile row (TMEM lane) per thread, scores read straight from TMEM
+// Relative-position bias and shift mask are an fp32 tile (pre-multiplied by log2 e, -inf on key padding) and one
+// 64-bit word per row; the bias gradient is accumulated in registers over every window a thread sees and reduced
+// once per CTA.
+#include "common.cuh"
+#include "../../include/vtb200.h"
+#include <math.h>
+
+namespace {
+
+constexpr int WT_THREADS = 384;
+constexpr float WT_L2E = 1.4426950408889634f;
+constexpr float WT_LN2 = 0.6931471805599453f;
+
+struct WtGeom {
+  int heads, nq, Hs, Ws, window, shift, nwx, nw, groups;
+};
+
+// token of in-window position t of group grp, -1 for padding
+__device__ __forceinline__ int wt_token(const WtGeom& g, int grp, int t) {
+  if (t >= g.nq || grp >= g.groups) return -1;
+  const int b = grp / g.nw, wi = grp - b * g.nw;
+  const int wy = wi / g.nwx, wx = wi - wy * g.nwx;
+  const int ty = t / g.window, tx = t - ty * g.window;
+  int y = wy * g.window + ty + g.shift, x = wx * g.window + tx + g.shift;
+  if (y >= g.Hs) y -= g.Hs;
+  if (x >= g.Ws) x -= g.Ws;
+  return (b * g.Hs + y) * g.Ws + x;
+}
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) {
+  return (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ float wt_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void wt_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void wt_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void wt_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// release a barrier once per warp after every lane is done
+__device__ __forceinline__ void wt_warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+// 32 fp32 -> bf16 (x scale) -> 64 contiguous bytes of global memory
+__device__ __forceinline__ void wt_store_row32(bf16* dst, const uint32_t (&a)[32], float s) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 8)
+    *reinterpret_cast<uint4*>(dst + e) =
+        make_uint4(pack_bf16(__uint_as_float(a[e]) * s, __uint_as_float(a[e + 1]) * s),
+                   pack_bf16(__uint_as_float(a[e + 2]) * s, __uint_as_float(a[e + 3]) * s),
+                   pack_bf16(__uint_as_float(a[e + 4]) * s, __uint_as_float(a[e + 5]) * s),
+                   pack_bf16(__uint_as_float(a[e + 6]) * s, __uint_as_float(a[e + 7]) * s));
+}
+
+// bias tile shared by forward (rows = queries, cols = keys) and backward (rows = keys, cols = queries):
+// tile[row][col] (fp32, 16-byte chunks XOR-swizzled by row & 7) = rel_bias[pos[i, j], h] * log2(e); -inf where the KEY
+// index is padding (>= nq); 0 where only the query index is padding.
+__device__ __forceinline__ void wt_build_bias(const vtb_attn_params& p, int nq, int heads, int h, float* tab,
+                                              uint8_t* tile, bool rows_are_keys) {
+  if (p.rel_bias)
+    for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) tab[t] = __ldg(p.rel_bias + (long)t * heads + h) * WT_L2E;
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int row = e >> 6, col = e & 63;
+    const int i = rows_are_keys ? col : row, j = rows_are_keys ? row : col;
+    float v = 0.f;
+    if (j >= nq) v = -INFINITY;
+    else if (i < nq && p.rel_bias) v = tab[__ldg(p.pos + i * nq + j)];
+    *reinterpret_cast<float*>(tile + row * 256 + ((((col >> 2) ^ (row & 7))) << 4) + (col & 3) * 4) = v;
+  }
+  __syncthreads();
+}
+
+// =====================================================================================================
+// forward
+//   S[(w,i), j] = Qpad . Kcat^T (M 128, N 64, K 64)   -> softmax per row (one thread per row) -> P (bf16) back
+//   into TMEM over S -> O[(w,i), (w',d)] = P . Vcat (A from TMEM, B MN-major); columns w' = w are the output.
+//   4 smem stages / 4 TMEM buffers; the two math groups take alternate tiles.
+// =====================================================================================================
+constexpr int F_STAGES = 4;
+constexpr int F_STAGE_BYTES = 16384 + 8192 + 8192;
+constexpr int F_SIDE_BYTES = 128 * 4 + 128 * 8;  // tok, mask bits
+constexpr int F_SMEM = F_STAGES * F_STAGE_BYTES + 16384 + F_STAGES * F_SIDE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sStage = smem;
+  uint8_t* sBias = smem + F_STAGES * F_STAGE_BYTES;
+  uint8_t* sSide = sBias + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSide + F_STAGES * F_SIDE_BYTES);
+  uint64_t* full = bars;                 // [4] loader warps (2) -> issuer / math
+  uint64_t* empty = bars + 4;            // [4] PV retired -> loaders
+  uint64_t* s_full = bars + 8;           // [4] S complete
+  uint64_t* p_full = bars + 12;          // [4] P written (4 warps)
+  uint64_t* o_full = bars + 16;          // [4] O complete
+  uint64_t* o_free = bars + 20;          // [4] O drained (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % g.heads;
+  const int chunk = blockIdx.x / g.heads;
+  const int my_tiles = (ntiles - chunk + nchunks - 1) / nchunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  // zero the operand ring once (the zero halves of Qpad never change; padding rows are re-zeroed by the loaders)
+  for (int e = threadIdx.x; e < F_STAGES * F_STAGE_BYTES / 16; e += WT_THREADS)
+    reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  wt_build_bias(p, g.nq, g.heads, h, reinterpret_cast<float*>(sStage + 3 * F_STAGE_BYTES), sBias, false);
+  // the table scratch lived in stage 3: clear it again
+  for (int e = threadIdx.x; e < 2048 / 16; e += WT_THREADS)
+    reinterpret_cast<uint4*>(sStage + 3 * F_STAGE_BYTES)[e] = make_uint4(0, 0, 0, 0);
+  wt_proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 2) {
+    // ------------------------------------------------------------------ loaders: thread = rows (0, tt) and (1, tt)
+    const int tt = threadIdx.x;
+    int pend_stage = -1;
+    for (int n = 0; n < my_tiles; ++n) {
+      const int tile = chunk + n * nchunks;
+      const int stage = n & 3;
+      mbar_wait(&empty[stage], ((n >> 2) & 1) ^ 1);
+      uint8_t* st = sStage + stage * F_STAGE_BYTES;
+      int* s_tok = reinterpret_cast<int*>(sSide + stage * F_SIDE_BYTES);
+      unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * F_SIDE_BYTES + 512);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int grp = tile * 2 + w, t = w * 64 + tt;
+        const int tok = wt_token(g, grp, tt);
+        const long row = (long)(tok < 0 ? 0 : tok);
+        const bf16* qs = reinterpret_cast<const bf16*>(p.q) + row * p.ldq + h * 32;
+        const bf16* ks = reinterpret_cast<const bf16*>(p.k) + row * p.ldk + h * 32;
+        const bf16* vs = reinterpret_cast<const bf16*>(p.v) + row * p.ldv + h * 32;
+        const bool ok = tok >= 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          cp_async16(smem_u32(st + sw128(t, w * 4 + cc)), qs + cc * 8, ok);
+          cp_async16(smem_u32(st + 16384 + sw128(tt, w * 4 + cc)), ks + cc * 8, ok);
+          cp_async16(smem_u32(st + 24576 + sw128(tt, w * 4 + cc)), vs + cc * 8, ok);
+        }
+        s_tok[t] = tok;
+        s_mb[t] = (p.mask_bits && ok) ? __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits) +
+                                              (long)(grp % p.n_mask) * 128 + tt)
+                                      : 0ull;
+      }
+      cp_async_commit();
+      if (pend_stage >= 0) {
+        cp_async_wait<1>();
+        wt_proxy_fence();
+        wt_warp_arrive(&full[pend_stage], lane);
+      }
+      pend_stage = stage;
+    }
+    cp_async_wait<0>();
+    wt_proxy_fence();
+    wt_warp_arrive(&full[pend_stage], lane);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      auto issue_s = [&](int n) {
+        const int b = n & 3;
+        mbar_wait(&full[b], (n >> 2) & 1);
+        mbar_wait(&o_free[b], ((n >> 2) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sStage + b * F_STAGE_BYTES), ka = qa + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + b * 128, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+      };
+      issue_s(0);
+      if (my_tiles > 1) issue_s(1);
+      for (int n = 0; n < my_tiles; ++n) {
+        if (n + 2 < my_tiles) issue_s(n + 2);
+        const int b = n & 3;
+        mbar_wait(&p_full[b], (n >> 2) & 1);
+        tc_fence_after();
+        const uint32_t va = smem_u32(sStage + b * F_STAGE_BYTES) + 24576;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          wt_umma_ts(tmem_base + b * 128 + 64, tmem_base + b * 128 + k * 8, umma_desc_sw128(va + k * 2048, 0, 1024),
+                     idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&o_full[b]);
+        umma_commit(&empty[b]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ math: thread = query row (w, i)
+    const int grpi = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane, w = r >> 6, i = r & 63;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * WT_L2E;
+    const uint8_t* brow = sBias + i * 256;
+    const int sx = i & 7;
+    bf16* O = reinterpret_cast<bf16*>(p.o);
+    for (int n = grpi; n < my_tiles; n += 2) {
+      const int tile = chunk + n * nchunks;
+      const int b = n & 3;
+      mbar_wait(&full[b], (n >> 2) & 1);
+      const int tok = reinterpret_cast<const int*>(sSide + b * F_SIDE_BYTES)[r];
+      const unsigned long long mb = reinterpret_cast<const unsigned long long*>(sSide + b * F_SIDE_BYTES + 512)[r];
+      mbar_wait(&s_full[b], (n >> 2) & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32(t_lane + b * 128, s0);
+      tmem_ld_32x32(t_lane + b * 128 + 32, s1);
+      tmem_ld_wait();
+      float x[64];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 bb = *reinterpret_cast<const float4*>(brow + ((c ^ sx) << 4));
+        const uint32_t* src = (c < 8) ? &s0[c * 4] : &s1[(c - 8) * 4];
+        x[c * 4 + 0] = fmaf(__uint_as_float(src[0]), sl2, bb.x);
+        x[c * 4 + 1] = fmaf(__uint_as_float(src[1]), sl2, bb.y);
+        x[c * 4 + 2] = fmaf(__uint_as_float(src[2]), sl2, bb.z);
+        x[c * 4 + 3] = fmaf(__uint_as_float(src[3]), sl2, bb.w);
+      }
+      if (__any_sync(0xffffffffu, mb != 0ull)) {
+        const uint32_t lo = (uint32_t)mb, hi = (uint32_t)(mb >> 32);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (lo & (1u << j)) x[j] = -INFINITY;
+          if (hi & (1u << j)) x[32 + j] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 64; ++j) mx = fmaxf(mx, x[j]);
+      const float m_use = (mx == -INFINITY) ? 0.f : mx;
+      float sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) {
+        const float p0 = wt_ex2(x[j] - m_use), p1 = wt_ex2(x[j + 1] - m_use);
+        sum += p0 + p1;
+        pk[j >> 1] = pack_bf16(p0, p1);
+      }
+      wt_tmem_st16(t_lane + b * 128, pk);
+      wt_tmem_st16(t_lane + b * 128 + 16, pk + 16);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      wt_warp_arrive(&p_full[b], lane);
+      // epilogue: O / l -> bf16 -> global; lse = ln 2 * (max + log2(sum))
+      mbar_wait(&o_full[b], (n >> 2) & 1);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld_32x32(t_lane + b * 128 + 64 + w * 32, a);
+      tmem_ld_wait();
+      tc_fence_before();
+      wt_warp_arrive(&o_free[b], lane);
+      if (tok >= 0) {
+        wt_store_row32(O + (long)tok * p.ldo + h * 32, a, 1.f / sum);
+        if (p.lse) p.lse[((long)(tile * 2 + w) * g.heads + h) * g.nq + i] = (mx + log2f(sum)) * WT_LN2;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// backward (keys on the tile rows, as in the global tcgen05 backward):
+//   S^T[(w,j), i] = Kpad . Qcat^T      dP^T[(w,j), i] = Vpad . dOcat^T             (M 128, N 64, K 64)
+//   P^T = exp2(S^T sl2 + bias - lse2[i]),  dS^T = P^T (dP^T - delta[i])   -> bf16 tiles in shared memory
+//   dV[(w,j), (w',d)] = P^T . dOcat     dK = dS^T . Qcat    (A K-major, B MN-major; columns w' = w are the result)
+//   dQ[i, (w,d)]      = dS . Kpad       (A = the dS^T tile read MN-major, B MN-major; the padded tile separates
+//                                        the windows; rows 64-127 of the accumulator are a don't-care second M atom)
+// TMEM: S^T 2 x 64 | dP^T 2 x 64 | dV 64 | dK 64 | dQ 64.   3 operand stages, P^T / dS^T single-buffered.
+// =====================================================================================================
+constexpr int B_STAGES = 3;
+constexpr int B_OFF_V = 16384, B_OFF_Q = 32768, B_OFF_DO = 40960, B_OFF_O = 49152;
+constexpr int B_STAGE_BYTES = 57344;  // Kpad 16K | Vpad 16K | Qcat 8K | dOcat 8K | O rows 8K (plain, for delta)
+constexpr int B_SIDE_BYTES = 128 * 4 * 3 + 128 * 8;  // tok, lse2, delta, mask bits
+constexpr int B_SMEM = B_STAGES * B_STAGE_BYTES + 2 * 16384 + 16384 + B_STAGES * B_SIDE_BYTES + 256 + 1024;
+constexpr uint32_t C_ST = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sStage = smem;
+  uint8_t* sdS = smem + B_STAGES * B_STAGE_BYTES;   // [128 key rows][64 queries] bf16, 128B-swizzled
+  uint8_t* sP = sdS + 16384;                        // directly behind dS^T: the dQ product's second M atom lands here
+  uint8_t* sBias = sP + 16384;
+  uint8_t* sSide = sBias + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSide + B_STAGES * B_SIDE_BYTES);
+  uint64_t* full = bars;            // [3] count 2 (loader warps)
+  uint64_t* empty = bars + 3;       // [3] gradient MMAs of the tile retired
+  uint64_t* s_full = bars + 6;      // [2] S^T / dP^T complete
+  uint64_t* s_free = bars + 8;      // [2] read out of TMEM (8 warps)
+  uint64_t* pds_full = bars + 10;   // P^T / dS^T tiles written (8 warps)
+  uint64_t* pds_free = bars + 11;   // ... and consumed by the gradient MMAs
+  uint64_t* g_full = bars + 12;     // dV / dK / dQ complete
+  uint64_t* g_free = bars + 13;     // ... and drained (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % g.heads;
+  const int chunk = blockIdx.x / g.heads;
+  const int my_tiles = (ntiles - chunk + nchunks - 1) / nchunks;
+  const bool has_tab = p.rel_bias != nullptr && p.drel_bias != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); }
+    mbar_init(pds_full, 8); mbar_init(pds_free, 1); mbar_init(g_full, 1); mbar_init(g_free, 8);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  for (int e = threadIdx.x; e < (B_STAGES * B_STAGE_BYTES + 2 * 16384) / 16; e += WT_THREADS)
+    reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  wt_build_bias(p, g.nq, g.heads, h, reinterpret_cast<float*>(sP), sBias, true);
+  for (int e = threadIdx.x; e < 2048 / 16; e += WT_THREADS) reinterpret_cast<uint4*>(sP)[e] = make_uint4(0, 0, 0, 0);
+  wt_proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 2) {
+    // ------------------------------------------------------------------ loaders: thread = rows (0, tt) and (1, tt)
+    const int tt = threadIdx.x;
+    int pend_stage = -1;
+    float pend_lse[2] = {0.f, 0.f};
+    // signal the previous tile: its rows have landed -> delta from shared memory, side info, release
+    auto finish = [&](int stage, const float (&lse_v)[2]) {
+      uint8_t* st = sStage + stage * B_STAGE_BYTES;
+      float* side = reinterpret_cast<float*>(sSide + stage * B_SIDE_BYTES);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int t = w * 64 + tt;
+        float acc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint4 ra = *reinterpret_cast<const uint4*>(st + B_OFF_DO + sw128(tt, w * 4 + cc));
+          const uint4 rb = *reinterpret_cast<const uint4*>(st + B_OFF_O + t * 64 + cc * 16);
+          const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
+            acc += fa.x * fb.x + fa.y * fb.y;
+          }
+        }
+        side[128 + t] = lse_v[w];
+        side[256 + t] = acc;
+      }
+      wt_proxy_fence();
+      wt_warp_arrive(&full[stage], lane);
+    };
+    for (int n = 0; n < my_tiles; ++n) {
+      const int tile = chunk + n * nchunks;
+      const int stage = n % 3;
+      mbar_wait(&empty[stage], ((n / 3) & 1) ^ 1);
+      uint8_t* st = sStage + stage * B_STAGE_BYTES;
+      int* s_tok = reinterpret_cast<int*>(sSide + stage * B_SIDE_BYTES);
+      unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * B_SIDE_BYTES + 1536);
+      float lse_v[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int grp = tile * 2 + w, t = w * 64 + tt;
+        const int tok = wt_token(g, grp, tt);
+        const long row = (long)(tok < 0 ? 0 : tok);
+        const bool ok = tok >= 0;
+        const bf16* qs = reinterpret_cast<const bf16*>(p.q) + row * p.ldq + h * 32;
+        const bf16* ks = reinterpret_cast<const bf16*>(p.k) + row * p.ldk + h * 32;
+        const bf16* vs = reinterpret_cast<const bf16*>(p.v) + row * p.ldv + h * 32;
+        const bf16* dos = reinterpret_cast<const bf16*>(p.dout) + row * p.lddo + h * 32;
+        const bf16* os = reinterpret_cast<const bf16*>(p.o) + row * p.ldo + h * 32;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          cp_async16(smem_u32(st + sw128(t, w * 4 + cc)), ks + cc * 8, ok);
+          cp_async16(smem_u32(st + B_OFF_V + sw128(t, w * 4 + cc)), vs + cc * 8, ok);
+          cp_async16(smem_u32(st + B_OFF_Q + sw128(tt, w * 4 + cc)), qs + cc * 8, ok);
+          cp_async16(smem_u32(st + B_OFF_DO + sw128(tt, w * 4 + cc)), dos + cc * 8, ok);
+          cp_async16(smem_u32(st + B_OFF_O + t * 64 + cc * 16), os + cc * 8, ok);
+        }
+        s_tok[t] = tok;
+        s_mb[t] = (p.mask_bits && ok) ? __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits) +
+                                              (long)(grp % p.n_mask) * 128 + 64 + tt)
+                                      : 0ull;
+        lse_v[w] = ok ? __ldg(p.lse + ((long)grp * g.heads + h) * g.nq + tt) * WT_L2E : INFINITY;
+      }
+      cp_async_commit();
+      if (pend_stage >= 0) {
+        cp_async_wait<1>();
+        finish(pend_stage, pend_lse);
+      }
+      pend_stage = stage;
+      pend_lse[0] = lse_v[0];
+      pend_lse[1] = lse_v[1];
+    }
+    cp_async_wait<0>();
+    finish(pend_stage, pend_lse);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
+      auto issue_s = [&](int n) {
+        const int stage = n % 3, b = n & 1;
+        mbar_wait(&full[stage], (n / 3) & 1);
+        mbar_wait(&s_free[b], ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sStage + stage * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + C_ST + b * 64, umma_desc_sw128(ka + k * 32, 0, 1024),
+                    umma_desc_sw128(ka + B_OFF_Q + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + C_DP + b * 64, umma_desc_sw128(ka + B_OFF_V + k * 32, 0, 1024),
+                    umma_desc_sw128(ka + B_OFF_DO + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+      };
+      issue_s(0);
+      for (int n = 0; n < my_tiles; ++n) {
+        if (n + 1 < my_tiles) issue_s(n + 1);
+        const int stage = n % 3;
+        mbar_wait(pds_full, n & 1);
+        mbar_wait(g_free, (n & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sStage + stage * B_STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_bf16(tmem_base + C_DV, umma_desc_sw128(pa + s * 32, 0, 1024),
+                    umma_desc_sw128(ka + B_OFF_DO + s * 2048, 0, 1024), idesc_g, s > 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_bf16(tmem_base + C_DK, umma_desc_sw128(sa + s * 32, 0, 1024),
+                    umma_desc_sw128(ka + B_OFF_Q + s * 2048, 0, 1024), idesc_g, s > 0 ? 1u : 0u);
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          umma_bf16(tmem_base + C_DQ, umma_desc_sw128(sa + s * 2048, 16384, 1024),
+                    umma_desc_sw128(ka + s * 2048, 0, 1024), idesc_q, s > 0 ? 1u : 0u);
+        umma_commit(g_full);
+        umma_commit(pds_free);
+        umma_commit(&empty[stage]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ math: thread = key row (w, j), 32 of the 64 queries
+    const int half = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane, w = r >> 6, j = r & 63;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * WT_L2E;
+    const uint8_t* brow = sBias + j * 256;
+    const int sx = j & 7;
+    bf16* dQ = reinterpret_cast<bf16*>(p.dq);
+    bf16* dK = reinterpret_cast<bf16*>(p.dk);
+    bf16* dV = reinterpret_cast<bf16*>(p.dv);
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    int ptok_r = -1, ptok_q = -1;
+
+    auto epilogue = [&](int n, int tok_r, int tok_q) {
+      mbar_wait(g_full, n & 1);
+      tc_fence_after();
+      uint32_t a[32], bq[32];
+      tmem_ld_32x32(t_lane + (half ? C_DK : C_DV) + w * 32, a);
+      if (quarter < 2) tmem_ld_32x32(t_lane + C_DQ + half * 32, bq);
+      tmem_ld_wait();
+      tc_fence_before();
+      wt_warp_arrive(g_free, lane);
+      if (tok_r >= 0) {
+        if (half) wt_store_row32(dK + (long)tok_r * p.lddk + h * 32, a, p.scale);
+        else      wt_store_row32(dV + (long)tok_r * p.lddv + h * 32, a, 1.f);
+      }
+      if (quarter < 2 && tok_q >= 0) wt_store_row32(dQ + (long)tok_q * p.lddq + h * 32, bq, p.scale);
+    };
+
+    for (int n = 0; n < my_tiles; ++n) {
+      const int stage = n % 3, b = n & 1;
+      mbar_wait(&full[stage], (n / 3) & 1);
+      const uint8_t* side = sSide + stage * B_SIDE_BYTES;
+      const int tok_r = reinterpret_cast<const int*>(side)[r];
+      const int tok_q = reinterpret_cast<const int*>(side)[half * 64 + j];  // dQ row (query j of window `half`)
+      const float* lrow = reinterpret_cast<const float*>(side + 512) + w * 64 + half * 32;
+      const float* drow = reinterpret_cast<const float*>(side + 1024) + w * 64 + half * 32;
+      const unsigned long long mb64 = reinterpret_cast<const unsigned long long*>(side + 1536)[r];
+      const uint32_t mb = half ? (uint32_t)(mb64 >> 32) : (uint32_t)mb64;
+      mbar_wait(&s_full[b], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t st[32], dp[32];
+      tmem_ld_32x32(t_lane + C_ST + b * 64 + half * 32, st);
+      tmem_ld_32x32(t_lane + C_DP + b * 64 + half * 32, dp);
+      tmem_ld_wait();
+      tc_fence_before();
+      wt_warp_arrive(&s_free[b], lane);
+      const bool any_mask = __any_sync(0xffffffffu, mb != 0u);
+      uint32_t pp[16], dd[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 bb = *reinterpret_cast<const float4*>(brow + (((half * 8 + c) ^ sx) << 4));
+        const float4 ll = *reinterpret_cast<const float4*>(lrow + c * 4);
+        const float4 dl = *reinterpret_cast<const float4*>(drow + c * 4);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, lv[4] = {ll.x, ll.y, ll.z, ll.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
+        float pv[4], sv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x = fmaf(__uint_as_float(st[c * 4 + e]), sl2, bv[e]) - lv[e];
+          if (any_mask && (mb & (1u << (c * 4 + e)))) x = -INFINITY;
+          pv[e] = wt_ex2(x);
+          sv[e] = pv[e] * (__uint_as_float(dp[c * 4 + e]) - dv[e]);
+          acc[c * 4 + e] += sv[e];
+        }
+        pp[c * 2] = pack_bf16(pv[0], pv[1]); pp[c * 2 + 1] = pack_bf16(pv[2], pv[3]);
+        dd[c * 2] = pack_bf16(sv[0], sv[1]); dd[c * 2 + 1] = pack_bf16(sv[2], sv[3]);
+      }
+      mbar_wait(pds_free, (n & 1) ^ 1);  // the previous tile's gradient MMAs no longer read the tiles
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t off = sw128(r, half * 4 + q4);
+        *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+        *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+      }
+      wt_proxy_fence();
+      wt_warp_arrive(pds_full, lane);
+      if (n > 0) epilogue(n - 1, ptok_r, ptok_q);
+      ptok_r = tok_r;
+      ptok_q = tok_q;
+    }
+    epilogue(my_tiles - 1, ptok_r, ptok_q);
+
+    // bias gradient: registers -> per-CTA table in shared memory (over the retired P^T tile) -> global atomics
+    if (has_tab) {
+      float* dtab = reinterpret_cast<float*>(sP);
+      const int mt = threadIdx.x - 128;  // 0..255
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = mt; e < p.n_pos; e += 256) dtab[e] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (j < g.nq) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int i = half * 32 + c;
+          if (i < g.nq && acc[c] != 0.f) atomicAdd(&dtab[__ldg(p.pos + i * g.nq + j)], acc[c]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = mt; e < p.n_pos; e += 256) {
+        const float v = dtab[e];
+        if (v != 0.f) atomicAdd(p.drel_bias + (long)e * g.heads + h, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool g_attn_wt = true;
+
+int wt_geom(const vtb_attn_params* p, WtGeom* g) {
+  g->heads = p->heads; g->nq = p->nq; g->Hs = p->Hs; g->Ws = p->Ws; g->window = p->window; g->shift = p->shift;
+  g->nwx = p->Ws / p->window;
+  g->nw = (p->Hs / p->window) * g->nwx;
+  const long groups = (long)p->batch * g->nw;
+  VTB_CHECK(groups < (1L << 30) && (long)p->batch * p->Hs * p->Ws < (1L << 31), -1,
+            "vtb_attention(window tcgen05): problem too large for 32-bit token indices");
+  g->groups = (int)groups;
+  return 0;
+}
+
+template <typename K>
+int wt_launch(K kern, size_t smem, const vtb_attn_params* p, cudaStream_t stream, bool* attr_set) {
+  WtGeom g;
+  if (int rc = wt_geom(p, &g)) return rc;
+  if (!*attr_set) {
+    VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *attr_set = true;
+  }
+  const int ntiles = (g.groups + 1) / 2;
+  int nchunks = vtb_num_sms() / p->heads;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > ntiles) nchunks = ntiles;
+  kern<<<(unsigned)(nchunks * p->heads), WT_THREADS, smem, stream>>>(*p, g, ntiles, nchunks);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+void vtb_attn_wt_set(bool on) { g_attn_wt = on; }
+
+bool vtb_attn_wt_ok(const vtb_attn_params* p, bool bwd) {
+  if (!g_attn_wt || p->mode != VTB_ATTN_WINDOW || p->dh != 32 || p->nq > 64 || p->nkv != p->nq) return false;
+  if (p->mask && !p->mask_bits) return false;
+  if (p->rel_bias && p->n_pos > 512) return false;
+  if (p->heads > 148) return false;
+  uintptr_t al = (uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (uintptr_t)p->o;
+  int ld = p->ldq | p->ldk | p->ldv | p->ldo;
+  if (bwd) {
+    if (p->dkv_f32) return false;
+    al |= (uintptr_t)p->dout | (uintptr_t)p->dq | (uintptr_t)p->dk | (uintptr_t)p->dv;
+    ld |= p->lddo | p->lddq | p->lddk | p->lddv;
+  }
+  return (al & 15) == 0 && (ld & 7) == 0;
+}
+
+int vtb_attn_wt_fwd(const vtb_attn_params* p, cudaStream_t stream) {
+  static bool attr = false;
+  return wt_launch(attn_wt_fwd_kernel, (size_t)F_SMEM, p, stream, &attr);
+}
+int vtb_attn_wt_bwd(const vtb_attn_params* p, cudaStream_t stream) {
+  static bool attr = false;
+  return wt_launch(attn_wt_bwd_kernel, (size_t)B_SMEM, p, stream, &attr);
+}

@@ -665,6 +665,7 @@ int vtb_num_sms() { return g_num_sms; }
 
 void vtb_attn_tc_set(bool on);
 void vtb_attn_wp_set(bool on);
+void vtb_attn_wt_set(bool on);
 void vtb_ln_stream_set(bool on);
 
 extern "C" int vtb_set_option(const char* name, int32_t value) {
@@ -672,6 +673,7 @@ extern "C" int vtb_set_option(const char* name, int32_t value) {
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
   if (strcmp(name, "attn_wp") == 0) { vtb_attn_wp_set(value != 0); return 0; }
+  if (strcmp(name, "attn_wt") == 0) { vtb_attn_wt_set(value != 0); return 0; }
   if (strcmp(name, "ln_stream") == 0) { vtb_ln_stream_set(value != 0); return 0; }
   vtb_set_error("vtb_set_option: unknown option '%s'", name);
   return -1;

@@ -60,6 +60,7 @@ class AttnParams(C.Structure):
         ("dkv_f32", C.c_int32),
         ("delta", C.c_void_p),
         ("drel_bias", C.c_void_p),
+        ("mask_bits", C.c_void_p),
     ]
 
 

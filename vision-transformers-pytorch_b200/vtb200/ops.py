@@ -179,6 +179,27 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_in=None, dx_out=None, patchify
     return dx_out, dxb, dgamma, dbeta
 
 
+_MASK_BITS = {}
+
+
+def _mask_bits(mask, n):
+    """[n_mask, 2, 64] int64 row words of a uint8 mask [n_mask, n, pitch] (include/vtb200.h: mask_bits): word
+    [m, 0, i] bit j / word [m, 1, j] bit i set where mask[m, i, j] != 0.  Built once per mask buffer (the masks are
+    constant module buffers) with torch integer ops."""
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), n)
+    bits = _MASK_BITS.get(key)
+    if bits is None:
+        m = (mask[:, :, :n] != 0).to(torch.int64)
+        sh = torch.arange(n, device=mask.device, dtype=torch.int64)
+        bits = torch.zeros((mask.shape[0], 2, 64), dtype=torch.int64, device=mask.device)
+        bits[:, 0, :n] = (m << sh.view(1, 1, n)).sum(2)
+        bits[:, 1, :n] = (m << sh.view(1, n, 1)).sum(1)
+        if len(_MASK_BITS) > 256:
+            _MASK_BITS.clear()
+        _MASK_BITS[key] = bits
+    return bits
+
+
 class AttnSpec:
     """Geometry of one attention call (mirrors vtb_attn_params)."""
 
@@ -213,6 +234,9 @@ class AttnSpec:
             if self.mask.shape[1] != self.nq or self.mask.shape[2] < self.nkv:
                 raise ValueError("vtb200.attention: mask shape does not match nq / nkv")
             p.mask, p.n_mask, p.mask_ld = self.mask.data_ptr(), self.mask.shape[0], self.mask.shape[2]
+            if self.mode == _l.ATTN_WINDOW and self.nq <= 64 and self.nkv == self.nq:
+                self._bits = _mask_bits(self.mask, self.nq)  # keep alive for the call
+                p.mask_bits = self._bits.data_ptr()
 
 
 def _qkv_fill(p, q, k, v):
