@@ -28,7 +28,16 @@ constexpr float WT_LN2 = 0.6931471805599453f;
 
 struct WtGeom {
   int heads, nq, Hs, Ws, window, shift, nwx, nw, groups;
+  float inv_nw, inv_nwx;
 };
+// a / b for 0 <= a < 2^23 with inv = 1 / b (one multiply and a fix-up instead of an integer division)
+__device__ __forceinline__ int wt_div(int a, int b, float inv) {
+  int q = __float2int_rz((float)a * inv);
+  const int r = a - q * b;
+  if (r < 0) --q;
+  else if (r >= b) ++q;
+  return q;
+}
 
 // token of in-window position t of group grp, -1 for padding
 __device__ __forceinline__ int wt_token(const WtGeom& g, int grp, int t) {
@@ -41,6 +50,78 @@ __device__ __forceinline__ int wt_token(const WtGeom& g, int grp, int t) {
   if (x >= g.Ws) x -= g.Ws;
   return (b * g.Hs + y) * g.Ws + x;
 }
+// group part / row part of wt_token (the loaders resolve several rows of the same window)
+struct WtOrigin { int y0, x0, img; };
+__device__ __forceinline__ WtOrigin wt_origin(const WtGeom& g, int grp) {
+  WtOrigin o;
+  if (grp >= g.groups) { o.img = -1; o.y0 = o.x0 = 0; return o; }
+  const int b = wt_div(grp, g.nw, g.inv_nw), wi = grp - b * g.nw;
+  const int wy = wt_div(wi, g.nwx, g.inv_nwx), wx = wi - wy * g.nwx;
+  o.img = b; o.y0 = wy * g.window + g.shift; o.x0 = wx * g.window + g.shift;
+  return o;
+}
+__device__ __forceinline__ int wt_row_token(const WtGeom& g, const WtOrigin& o, int t) {
+  if (t >= g.nq || o.img < 0) return -1;
+  const int ty = t / g.window, tx = t - ty * g.window;
+  int y = o.y0 + ty, x = o.x0 + tx;
+  if (y >= g.Hs) y -= g.Hs;
+  if (x >= g.Ws) x -= g.Ws;
+  return (o.img * g.Hs + y) * g.Ws + x;
+}
+// per-thread constants of the four token rows (it * 16 + r4) a loader thread copies in every window
+struct WtRows {
+  int ty[4], tx[4];
+  bool valid[4];
+};
+__device__ __forceinline__ WtRows wt_rows(const WtGeom& g, int r4) {
+  WtRows r;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 16 + r4;
+    r.valid[it] = row < g.nq;
+    r.ty[it] = row / g.window;
+    r.tx[it] = row - r.ty[it] * g.window;
+  }
+  return r;
+}
+__device__ __forceinline__ int wt_tok(const WtGeom& g, const WtOrigin& o, int ty, int tx) {
+  int y = o.y0 + ty, x = o.x0 + tx;
+  if (y >= g.Hs) y -= g.Hs;
+  if (x >= g.Ws) x -= g.Ws;
+  return (o.img * g.Hs + y) * g.Ws + x;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// arrive on `bar` (without touching its pending count) once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* gp) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gp) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gp) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gp) : "memory");
+}
+// a polling role that makes no progress for ~2 s traps (-> launch error) instead of hanging the GPU
+struct WtWatchdog {
+  long long t0; uint32_t spins;
+  __device__ __forceinline__ void reset() { spins = 0; }
+  __device__ __forceinline__ void idle() {
+    if (spins == 0) t0 = clock64();
+    if ((++spins & 4095u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+};
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
   return (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
 }
@@ -108,11 +189,12 @@ __device__ __forceinline__ void wt_build_bias(const vtb_attn_params& p, int nq, 
 // forward
 //   S[(w,i), j] = Qpad . Kcat^T (M 128, N 64, K 64)   -> softmax per row (one thread per row) -> P (bf16) back
 //   into TMEM over S -> O[(w,i), (w',d)] = P . Vcat (A from TMEM, B MN-major); columns w' = w are the output.
-//   4 smem stages / 4 TMEM buffers; the two math groups take alternate tiles.
+//   6 smem stages (a stage's mbarrier is completed by the cp.async engine itself: the loaders never block on a load)
+//   / 4 TMEM buffers; the two math groups take alternate tiles.
 // =====================================================================================================
-constexpr int F_STAGES = 4;
+constexpr int F_STAGES = 6;
 constexpr int F_STAGE_BYTES = 16384 + 8192 + 8192;
-constexpr int F_SIDE_BYTES = 128 * 4 + 128 * 8;  // tok, mask bits
+constexpr int F_SIDE_BYTES = 128 * 8;  // mask bits
 constexpr int F_SMEM = F_STAGES * F_STAGE_BYTES + 16384 + F_STAGES * F_SIDE_BYTES + 256 + 1024;
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
@@ -123,13 +205,13 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   uint8_t* sBias = smem + F_STAGES * F_STAGE_BYTES;
   uint8_t* sSide = sBias + 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSide + F_STAGES * F_SIDE_BYTES);
-  uint64_t* full = bars;                 // [4] loader warps (2) -> issuer / math
-  uint64_t* empty = bars + 4;            // [4] PV retired -> loaders
-  uint64_t* s_full = bars + 8;           // [4] S complete
-  uint64_t* p_full = bars + 12;          // [4] P written (4 warps)
-  uint64_t* o_full = bars + 16;          // [4] O complete
-  uint64_t* o_free = bars + 20;          // [4] O drained (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* full = bars;                 // [6] 64 cp.async arrivals (loader threads) -> issuer / math
+  uint64_t* empty = bars + 6;            // [6] PV retired -> loaders
+  uint64_t* s_full = bars + 12;          // [4] S complete
+  uint64_t* p_full = bars + 16;          // [4] P written (4 warps)
+  uint64_t* o_full = bars + 20;          // [4] O complete
+  uint64_t* o_free = bars + 24;          // [4] O drained (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % g.heads;
@@ -137,9 +219,9 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   const int my_tiles = (ntiles - chunk + nchunks - 1) / nchunks;
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < F_STAGES; ++i) { mbar_init(&full[i], 64); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
     }
     mbar_fence_init();
   }
@@ -148,10 +230,9 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   for (int e = threadIdx.x; e < F_STAGES * F_STAGE_BYTES / 16; e += WT_THREADS)
     reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  wt_build_bias(p, g.nq, g.heads, h, reinterpret_cast<float*>(sStage + 3 * F_STAGE_BYTES), sBias, false);
-  // the table scratch lived in stage 3: clear it again
-  for (int e = threadIdx.x; e < 2048 / 16; e += WT_THREADS)
-    reinterpret_cast<uint4*>(sStage + 3 * F_STAGE_BYTES)[e] = make_uint4(0, 0, 0, 0);
+  wt_build_bias(p, g.nq, g.heads, h, reinterpret_cast<float*>(sStage), sBias, false);
+  // the table scratch lived in stage 0: clear it again
+  for (int e = threadIdx.x; e < 2048 / 16; e += WT_THREADS) reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
   wt_proxy_fence();
   tc_fence_before();
   __syncthreads();
@@ -159,78 +240,88 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 2) {
-    // ------------------------------------------------------------------ loaders: thread = rows (0, tt) and (1, tt)
-    const int tt = threadIdx.x;
-    int pend_stage = -1;
+    // ------------------------------------------------------------------ loaders (64 threads)
+    // four lanes cover the four 16-byte chunks of one token row (8 rows x 64 B per warp instruction); thread tt also
+    // fetches the mask words of rows (0, tt), (1, tt).  The stage barrier is completed by the copies themselves.
+    const int tt = threadIdx.x, cc = tt & 3, r4 = tt >> 2;
+    const WtRows rows = wt_rows(g, r4);
+    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u;
+    const uint32_t ch[2] = {(uint32_t)((cc ^ (r4 & 7)) << 4), (uint32_t)(((4 + cc) ^ (r4 & 7)) << 4)};
+    const char* qb = reinterpret_cast<const char*>(p.q) + (h * 32 + cc * 8) * 2;
+    const char* kb = reinterpret_cast<const char*>(p.k) + (h * 32 + cc * 8) * 2;
+    const char* vb = reinterpret_cast<const char*>(p.v) + (h * 32 + cc * 8) * 2;
+    const long ldq2 = (long)p.ldq * 2, ldk2 = (long)p.ldk * 2, ldv2 = (long)p.ldv * 2;
     for (int n = 0; n < my_tiles; ++n) {
       const int tile = chunk + n * nchunks;
-      const int stage = n & 3;
-      mbar_wait(&empty[stage], ((n >> 2) & 1) ^ 1);
-      uint8_t* st = sStage + stage * F_STAGE_BYTES;
-      int* s_tok = reinterpret_cast<int*>(sSide + stage * F_SIDE_BYTES);
-      unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * F_SIDE_BYTES + 512);
+      const int stage = n % F_STAGES;
+      mbar_wait(&empty[stage], ((n / F_STAGES) & 1) ^ 1);
+      const uint32_t st = st0 + stage * F_STAGE_BYTES;
+      unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * F_SIDE_BYTES);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        const int grp = tile * 2 + w, t = w * 64 + tt;
-        const int tok = wt_token(g, grp, tt);
-        const long row = (long)(tok < 0 ? 0 : tok);
-        const bf16* qs = reinterpret_cast<const bf16*>(p.q) + row * p.ldq + h * 32;
-        const bf16* ks = reinterpret_cast<const bf16*>(p.k) + row * p.ldk + h * 32;
-        const bf16* vs = reinterpret_cast<const bf16*>(p.v) + row * p.ldv + h * 32;
-        const bool ok = tok >= 0;
+        const int grp = tile * 2 + w;
+        const WtOrigin org = wt_origin(g, grp);
+        if (p.mask_bits && org.img >= 0 && tt < g.nq)
+          cp_async8(smem_u32(&s_mb[w * 64 + tt]),
+                    reinterpret_cast<const unsigned long long*>(p.mask_bits) + (long)(grp % p.n_mask) * 128 + tt);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          cp_async16(smem_u32(st + sw128(t, w * 4 + cc)), qs + cc * 8, ok);
-          cp_async16(smem_u32(st + 16384 + sw128(tt, w * 4 + cc)), ks + cc * 8, ok);
-          cp_async16(smem_u32(st + 24576 + sw128(tt, w * 4 + cc)), vs + cc * 8, ok);
+        for (int it = 0; it < 4; ++it) {
+          if (rows.valid[it]) {  // rows >= nq stay zero from the prologue
+            const bool ok = org.img >= 0;
+            const long gr = ok ? (long)wt_tok(g, org, rows.ty[it], rows.tx[it]) : 0;
+            const uint32_t ro = (uint32_t)(it * 16) * 128u + ch[w];
+            cp_async16(st + (uint32_t)(w * 64) * 128u + ro, qb + gr * ldq2, ok);
+            cp_async16(st + 16384 + ro, kb + gr * ldk2, ok);
+            cp_async16(st + 24576 + ro, vb + gr * ldv2, ok);
+          }
         }
-        s_tok[t] = tok;
-        s_mb[t] = (p.mask_bits && ok) ? __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits) +
-                                              (long)(grp % p.n_mask) * 128 + tt)
-                                      : 0ull;
       }
-      cp_async_commit();
-      if (pend_stage >= 0) {
-        cp_async_wait<1>();
-        wt_proxy_fence();
-        wt_warp_arrive(&full[pend_stage], lane);
-      }
-      pend_stage = stage;
+      cp_async_arrive_noinc(&full[stage]);
     }
-    cp_async_wait<0>();
-    wt_proxy_fence();
-    wt_warp_arrive(&full[pend_stage], lane);
+    cp_async_wait<0>();  // nothing may still be in flight towards this CTA's shared memory at exit
   } else if (warp == 2) {
     // ------------------------------------------------------------------ UMMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-      auto issue_s = [&](int n) {
-        const int b = n & 3;
-        mbar_wait(&full[b], (n >> 2) & 1);
-        mbar_wait(&o_free[b], ((n >> 2) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sStage + b * F_STAGE_BYTES), ka = qa + 16384;
+      // event-driven: whichever of "next score tile" / "next P.V" has its inputs ready is issued, so a late load
+      // never delays a P.V product the math warps are waiting for
+      int ns = 0, np = 0;
+      WtWatchdog dog;
+      dog.reset();
+      while (np < my_tiles) {
+        bool did = false;
+        if (ns < my_tiles && ns < np + 4) {
+          const int b = ns & 3, stage = ns % F_STAGES;
+          if (mbar_test(&full[stage], (ns / F_STAGES) & 1) && mbar_test(&o_free[b], ((ns >> 2) & 1) ^ 1)) {
+            wt_proxy_fence();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sStage + stage * F_STAGE_BYTES), ka = qa + 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + b * 128, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024),
-                    idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[b]);
-      };
-      issue_s(0);
-      if (my_tiles > 1) issue_s(1);
-      for (int n = 0; n < my_tiles; ++n) {
-        if (n + 2 < my_tiles) issue_s(n + 2);
-        const int b = n & 3;
-        mbar_wait(&p_full[b], (n >> 2) & 1);
-        tc_fence_after();
-        const uint32_t va = smem_u32(sStage + b * F_STAGE_BYTES) + 24576;
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + b * 128, umma_desc_sw128(qa + k * 32, 0, 1024),
+                        umma_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[b]);
+            ++ns;
+            did = true;
+          }
+        }
+        if (np < ns) {
+          const int b = np & 3, stage = np % F_STAGES;
+          if (mbar_test(&p_full[b], (np >> 2) & 1)) {
+            tc_fence_after();
+            const uint32_t va = smem_u32(sStage + stage * F_STAGE_BYTES) + 24576;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          wt_umma_ts(tmem_base + b * 128 + 64, tmem_base + b * 128 + k * 8, umma_desc_sw128(va + k * 2048, 0, 1024),
-                     idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(&o_full[b]);
-        umma_commit(&empty[b]);
+            for (int k = 0; k < 4; ++k)
+              wt_umma_ts(tmem_base + b * 128 + 64, tmem_base + b * 128 + k * 8,
+                         umma_desc_sw128(va + k * 2048, 0, 1024), idesc_o, k > 0 ? 1u : 0u);
+            umma_commit(&o_full[b]);
+            umma_commit(&empty[stage]);
+            ++np;
+            did = true;
+          }
+        }
+        if (did) dog.reset(); else dog.idle();
       }
     }
   } else if (warp >= 4) {
@@ -245,10 +336,11 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
     bf16* O = reinterpret_cast<bf16*>(p.o);
     for (int n = grpi; n < my_tiles; n += 2) {
       const int tile = chunk + n * nchunks;
-      const int b = n & 3;
-      mbar_wait(&full[b], (n >> 2) & 1);
-      const int tok = reinterpret_cast<const int*>(sSide + b * F_SIDE_BYTES)[r];
-      const unsigned long long mb = reinterpret_cast<const unsigned long long*>(sSide + b * F_SIDE_BYTES + 512)[r];
+      const int b = n & 3, stage = n % F_STAGES;
+      const int tok = wt_row_token(g, wt_origin(g, tile * 2 + w), i);
+      mbar_wait(&full[stage], (n / F_STAGES) & 1);
+      const unsigned long long mb =
+          (p.mask_bits && tok >= 0) ? reinterpret_cast<const unsigned long long*>(sSide + stage * F_SIDE_BYTES)[r] : 0ull;
       mbar_wait(&s_full[b], (n >> 2) & 1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
@@ -339,7 +431,8 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   uint8_t* sBias = sP + 16384;
   uint8_t* sSide = sBias + 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSide + B_STAGES * B_SIDE_BYTES);
-  uint64_t* full = bars;            // [3] count 2 (loader warps)
+  uint64_t* full = bars;            // [3] count 2 (loader warps, after delta / lse of the landed tile are in place)
+  uint64_t* land = bars + 16;       // [3] 64 cp.async arrivals: the tile's rows have landed
   uint64_t* empty = bars + 3;       // [3] gradient MMAs of the tile retired
   uint64_t* s_full = bars + 6;      // [2] S^T / dP^T complete
   uint64_t* s_free = bars + 8;      // [2] read out of TMEM (8 warps)
@@ -347,7 +440,7 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   uint64_t* pds_free = bars + 11;   // ... and consumed by the gradient MMAs
   uint64_t* g_full = bars + 12;     // dV / dK / dQ complete
   uint64_t* g_free = bars + 13;     // ... and drained (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % g.heads;
@@ -356,7 +449,7 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   const bool has_tab = p.rel_bias != nullptr && p.drel_bias != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&land[i], 64); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); }
     mbar_init(pds_full, 8); mbar_init(pds_free, 1); mbar_init(g_full, 1); mbar_init(g_free, 8);
     mbar_fence_init();
@@ -374,22 +467,24 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 2) {
-    // ------------------------------------------------------------------ loaders: thread = rows (0, tt) and (1, tt)
-    const int tt = threadIdx.x;
-    int pend_stage = -1;
-    float pend_lse[2] = {0.f, 0.f};
-    // signal the previous tile: its rows have landed -> delta from shared memory, side info, release
-    auto finish = [&](int stage, const float (&lse_v)[2]) {
+    // ------------------------------------------------------------------ loaders (64 threads)
+    // data: four lanes cover the four 16-byte chunks of one token row; side info (token, mask word, lse, delta):
+    // thread tt owns rows (0, tt) and (1, tt).  Everything a tile needs arrives by cp.async (no blocking loads);
+    // two tiles in flight.
+    const int tt = threadIdx.x, cc = tt & 3, r4 = tt >> 2;
+    // the previous tile's rows have landed: delta = dO . O and lse * log2(e) from shared memory, then release
+    auto finish = [&](int stage) {
       uint8_t* st = sStage + stage * B_STAGE_BYTES;
       float* side = reinterpret_cast<float*>(sSide + stage * B_SIDE_BYTES);
+      const int* s_tok = reinterpret_cast<const int*>(side);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         const int t = w * 64 + tt;
         float acc = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint4 ra = *reinterpret_cast<const uint4*>(st + B_OFF_DO + sw128(tt, w * 4 + cc));
-          const uint4 rb = *reinterpret_cast<const uint4*>(st + B_OFF_O + t * 64 + cc * 16);
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint4 ra = *reinterpret_cast<const uint4*>(st + B_OFF_DO + sw128(tt, w * 4 + c4));
+          const uint4 rb = *reinterpret_cast<const uint4*>(st + B_OFF_O + t * 64 + c4 * 16);
           const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -397,56 +492,80 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
             acc += fa.x * fb.x + fa.y * fb.y;
           }
         }
-        side[128 + t] = lse_v[w];
+        side[128 + t] = (s_tok[t] >= 0) ? side[128 + t] * WT_L2E : INFINITY;
         side[256 + t] = acc;
       }
       wt_proxy_fence();
       wt_warp_arrive(&full[stage], lane);
     };
-    for (int n = 0; n < my_tiles; ++n) {
+    const WtRows rows = wt_rows(g, r4);
+    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u;
+    const uint32_t so0 = smem_u32(sStage) + B_OFF_O + (uint32_t)r4 * 64u + cc * 16;
+    const uint32_t ch[2] = {(uint32_t)((cc ^ (r4 & 7)) << 4), (uint32_t)(((4 + cc) ^ (r4 & 7)) << 4)};
+    const int colb = (h * 32 + cc * 8) * 2;
+    const char* qb = reinterpret_cast<const char*>(p.q) + colb;
+    const char* kb = reinterpret_cast<const char*>(p.k) + colb;
+    const char* vb = reinterpret_cast<const char*>(p.v) + colb;
+    const char* dob = reinterpret_cast<const char*>(p.dout) + colb;
+    const char* ob = reinterpret_cast<const char*>(p.o) + colb;
+    const long ldq2 = (long)p.ldq * 2, ldk2 = (long)p.ldk * 2, ldv2 = (long)p.ldv * 2, lddo2 = (long)p.lddo * 2,
+               ldo2 = (long)p.ldo * 2;
+    auto issue = [&](int n) {
       const int tile = chunk + n * nchunks;
       const int stage = n % 3;
-      mbar_wait(&empty[stage], ((n / 3) & 1) ^ 1);
-      uint8_t* st = sStage + stage * B_STAGE_BYTES;
-      int* s_tok = reinterpret_cast<int*>(sSide + stage * B_SIDE_BYTES);
+      const uint32_t st = st0 + stage * B_STAGE_BYTES, so = so0 + stage * B_STAGE_BYTES;
+      float* side = reinterpret_cast<float*>(sSide + stage * B_SIDE_BYTES);
+      int* s_tok = reinterpret_cast<int*>(side);
       unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * B_SIDE_BYTES + 1536);
-      float lse_v[2];
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        const int grp = tile * 2 + w, t = w * 64 + tt;
-        const int tok = wt_token(g, grp, tt);
-        const long row = (long)(tok < 0 ? 0 : tok);
-        const bool ok = tok >= 0;
-        const bf16* qs = reinterpret_cast<const bf16*>(p.q) + row * p.ldq + h * 32;
-        const bf16* ks = reinterpret_cast<const bf16*>(p.k) + row * p.ldk + h * 32;
-        const bf16* vs = reinterpret_cast<const bf16*>(p.v) + row * p.ldv + h * 32;
-        const bf16* dos = reinterpret_cast<const bf16*>(p.dout) + row * p.lddo + h * 32;
-        const bf16* os = reinterpret_cast<const bf16*>(p.o) + row * p.ldo + h * 32;
+        const int grp = tile * 2 + w;
+        const WtOrigin org = wt_origin(g, grp);
+        const int tok_side = wt_row_token(g, org, tt);
+        s_tok[w * 64 + tt] = tok_side;
+        if (p.mask_bits && tok_side >= 0)
+          cp_async8(smem_u32(&s_mb[w * 64 + tt]),
+                    reinterpret_cast<const unsigned long long*>(p.mask_bits) + (long)(grp % p.n_mask) * 128 + 64 + tt);
+        else
+          s_mb[w * 64 + tt] = 0ull;
+        if (tok_side >= 0)
+          cp_async4(smem_u32(&side[128 + w * 64 + tt]), p.lse + ((long)grp * g.heads + h) * g.nq + tt);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          cp_async16(smem_u32(st + sw128(t, w * 4 + cc)), ks + cc * 8, ok);
-          cp_async16(smem_u32(st + B_OFF_V + sw128(t, w * 4 + cc)), vs + cc * 8, ok);
-          cp_async16(smem_u32(st + B_OFF_Q + sw128(tt, w * 4 + cc)), qs + cc * 8, ok);
-          cp_async16(smem_u32(st + B_OFF_DO + sw128(tt, w * 4 + cc)), dos + cc * 8, ok);
-          cp_async16(smem_u32(st + B_OFF_O + t * 64 + cc * 16), os + cc * 8, ok);
+        for (int it = 0; it < 4; ++it) {
+          if (rows.valid[it]) {  // rows >= nq stay zero from the prologue
+            const bool ok = org.img >= 0;
+            const long gr = ok ? (long)wt_tok(g, org, rows.ty[it], rows.tx[it]) : 0;
+            const uint32_t ro = (uint32_t)(it * 16) * 128u + ch[w];
+            cp_async16(st + (uint32_t)(w * 64) * 128u + ro, kb + gr * ldk2, ok);
+            cp_async16(st + B_OFF_V + (uint32_t)(w * 64) * 128u + ro, vb + gr * ldv2, ok);
+            cp_async16(st + B_OFF_Q + ro, qb + gr * ldq2, ok);
+            cp_async16(st + B_OFF_DO + ro, dob + gr * lddo2, ok);
+            cp_async16(so + (uint32_t)(w * 64 + it * 16) * 64u, ob + gr * ldo2, ok);
+          }
         }
-        s_tok[t] = tok;
-        s_mb[t] = (p.mask_bits && ok) ? __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits) +
-                                              (long)(grp % p.n_mask) * 128 + 64 + tt)
-                                      : 0ull;
-        lse_v[w] = ok ? __ldg(p.lse + ((long)grp * g.heads + h) * g.nq + tt) * WT_L2E : INFINITY;
       }
-      cp_async_commit();
-      if (pend_stage >= 0) {
-        cp_async_wait<1>();
-        finish(pend_stage, pend_lse);
+      cp_async_arrive_noinc(&land[stage]);
+    };
+    // event-driven (warp-uniform votes): fetch the next tile as soon as its stage is free, publish a tile as soon
+    // as the copy engine reports it landed — the loaders never block on a load
+    int ni = 0, nf = 0;
+    WtWatchdog dog;
+    dog.reset();
+    while (nf < my_tiles) {
+      bool did = false;
+      if (ni < my_tiles && __all_sync(0xffffffffu, mbar_test(&empty[ni % 3], ((ni / 3) & 1) ^ 1))) {
+        issue(ni);
+        ++ni;
+        did = true;
       }
-      pend_stage = stage;
-      pend_lse[0] = lse_v[0];
-      pend_lse[1] = lse_v[1];
+      if (nf < ni && __all_sync(0xffffffffu, mbar_test(&land[nf % 3], (nf / 3) & 1))) {
+        finish(nf % 3);
+        ++nf;
+        did = true;
+      }
+      if (did) dog.reset(); else dog.idle();
     }
     cp_async_wait<0>();
-    finish(pend_stage, pend_lse);
   } else if (warp == 2) {
     // ------------------------------------------------------------------ UMMA issuer
     if (lane == 0) {
@@ -454,45 +573,55 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 1, 1);
       const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
-      auto issue_s = [&](int n) {
-        const int stage = n % 3, b = n & 1;
-        mbar_wait(&full[stage], (n / 3) & 1);
-        mbar_wait(&s_free[b], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t ka = smem_u32(sStage + stage * B_STAGE_BYTES);
+      int ns = 0, ng = 0;  // next score tile / next gradient tile (event-driven, see the forward issuer)
+      WtWatchdog dog;
+      dog.reset();
+      while (ng < my_tiles) {
+        bool did = false;
+        if (ns < my_tiles && ns < ng + 2) {
+          const int stage = ns % 3, b = ns & 1;
+          if (mbar_test(&full[stage], (ns / 3) & 1) && mbar_test(&s_free[b], ((ns >> 1) & 1) ^ 1)) {
+            wt_proxy_fence();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
+            tc_fence_after();
+            const uint32_t ka = smem_u32(sStage + stage * B_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + C_ST + b * 64, umma_desc_sw128(ka + k * 32, 0, 1024),
-                    umma_desc_sw128(ka + B_OFF_Q + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + C_ST + b * 64, umma_desc_sw128(ka + k * 32, 0, 1024),
+                        umma_desc_sw128(ka + B_OFF_Q + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + C_DP + b * 64, umma_desc_sw128(ka + B_OFF_V + k * 32, 0, 1024),
-                    umma_desc_sw128(ka + B_OFF_DO + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[b]);
-      };
-      issue_s(0);
-      for (int n = 0; n < my_tiles; ++n) {
-        if (n + 1 < my_tiles) issue_s(n + 1);
-        const int stage = n % 3;
-        mbar_wait(pds_full, n & 1);
-        mbar_wait(g_free, (n & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t ka = smem_u32(sStage + stage * B_STAGE_BYTES);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + C_DP + b * 64, umma_desc_sw128(ka + B_OFF_V + k * 32, 0, 1024),
+                        umma_desc_sw128(ka + B_OFF_DO + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[b]);
+            ++ns;
+            did = true;
+          }
+        }
+        if (ng < ns) {
+          if (mbar_test(pds_full, ng & 1) && mbar_test(g_free, (ng & 1) ^ 1)) {
+            tc_fence_after();
+            const int stage = ng % 3;
+            const uint32_t ka = smem_u32(sStage + stage * B_STAGE_BYTES);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-          umma_bf16(tmem_base + C_DV, umma_desc_sw128(pa + s * 32, 0, 1024),
-                    umma_desc_sw128(ka + B_OFF_DO + s * 2048, 0, 1024), idesc_g, s > 0 ? 1u : 0u);
+            for (int s2 = 0; s2 < 4; ++s2)
+              umma_bf16(tmem_base + C_DV, umma_desc_sw128(pa + s2 * 32, 0, 1024),
+                        umma_desc_sw128(ka + B_OFF_DO + s2 * 2048, 0, 1024), idesc_g, s2 > 0 ? 1u : 0u);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-          umma_bf16(tmem_base + C_DK, umma_desc_sw128(sa + s * 32, 0, 1024),
-                    umma_desc_sw128(ka + B_OFF_Q + s * 2048, 0, 1024), idesc_g, s > 0 ? 1u : 0u);
+            for (int s2 = 0; s2 < 4; ++s2)
+              umma_bf16(tmem_base + C_DK, umma_desc_sw128(sa + s2 * 32, 0, 1024),
+                        umma_desc_sw128(ka + B_OFF_Q + s2 * 2048, 0, 1024), idesc_g, s2 > 0 ? 1u : 0u);
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-          umma_bf16(tmem_base + C_DQ, umma_desc_sw128(sa + s * 2048, 16384, 1024),
-                    umma_desc_sw128(ka + s * 2048, 0, 1024), idesc_q, s > 0 ? 1u : 0u);
-        umma_commit(g_full);
-        umma_commit(pds_free);
-        umma_commit(&empty[stage]);
+            for (int s2 = 0; s2 < 8; ++s2)
+              umma_bf16(tmem_base + C_DQ, umma_desc_sw128(sa + s2 * 2048, 16384, 1024),
+                        umma_desc_sw128(ka + s2 * 2048, 0, 1024), idesc_q, s2 > 0 ? 1u : 0u);
+            umma_commit(g_full);
+            umma_commit(pds_free);
+            umma_commit(&empty[stage]);
+            ++ng;
+            did = true;
+          }
+        }
+        if (did) dog.reset(); else dog.idle();
       }
     }
   } else if (warp >= 4) {
@@ -621,6 +750,9 @@ int wt_geom(const vtb_attn_params* p, WtGeom* g) {
   VTB_CHECK(groups < (1L << 30) && (long)p->batch * p->Hs * p->Ws < (1L << 31), -1,
             "vtb_attention(window tcgen05): problem too large for 32-bit token indices");
   g->groups = (int)groups;
+  g->inv_nw = 1.f / (float)g->nw;
+  g->inv_nwx = 1.f / (float)g->nwx;
+  VTB_CHECK(groups < (1L << 22), -1, "vtb_attention(window tcgen05): too many windows");
   return 0;
 }
 
