@@ -13,6 +13,7 @@
 #include "../../include/vtb200.h"
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 namespace {
 
@@ -171,24 +172,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_
 // Staged epilogue of one warp's share (CW columns) of a sub-tile row: TMEM registers -> fused math ->
 // swizzled smem staging (chunks cb..cb+3 of the 128-byte row).  ob/ab point at this thread's row.
 template <int CW>
-__device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&acc)[CW], int nc, float rs,
+__device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&acc)[CW], float bias_lane, float rs,
                                            uint8_t* ob, uint8_t* ab, uint32_t cb, uint32_t swz, bool dual,
                                            bool f32out) {
   float v[CW];
 #pragma unroll
   for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-  if (e.bias) {
-    if (nc + CW <= e.N) {
+  if (e.bias) {  // lane j of the warp holds the bias of this warp's column j (prefetched one sub-tile ahead)
 #pragma unroll
-      for (int j = 0; j < CW; j += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + nc + j));
-        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CW; ++j)
-        if (nc + j < e.N) v[j] += __ldg(e.bias + nc + j);
-    }
+    for (int j = 0; j < CW; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
   }
   if (dual) {
     // out <- bf16(u) ; out2 <- bf16(silu(float(bf16(u))))     (layer.py:191-193 under autocast)
@@ -270,8 +262,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
-  uint64_t* aux_full = bars + 2 * C::STAGES + 4;              // [N_AUX]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + N_AUX);
+  uint64_t* aux_full = bars + 2 * C::STAGES + 4;              // [4 lane quarters][N_AUX]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 4 * N_AUX);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -289,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8 * CL);  // every epilogue warp of the pair arrives on the leader's barrier
     }
-    for (int i = 0; i < N_AUX; ++i) mbar_init(&aux_full[i], 1);
+    for (int i = 0; i < 4 * N_AUX; ++i) mbar_init(&aux_full[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -436,14 +428,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     } else {
       // staged path: sub-tiles of SUBN columns (one 128-byte row each) -> swizzled smem -> TMA store.
+      // The four TMEM lane quarters run INDEPENDENTLY: the two warps of a quarter share a 32-row slab of every staging
+      // buffer, meet on their own 64-thread named barrier, and one of them issues the quarter's own TMA stores /
+      // aux prefetches (32-row boxes), so a quarter never waits for the other three and their TMEM-load, MUFU and
+      // fence latencies overlap.
       const bool f32out = epi.out_f32 != 0;
       const int SUBN = f32out ? 32 : 64;
       const int n_sub = BN / SUBN;
       const bool dual = epi.epilogue == VTB_EPI_SILU_DUAL;
       const bool aux_in = (epi.resid != nullptr) || (epi.epilogue == VTB_EPI_SILU_GRAD);
-      const bool issuer = (threadIdx.x == 128);
+      const bool issuer = (warp < 8) && (lane == 0);  // one per lane quarter
+      const uint32_t qoff = (uint32_t)ew * 4096u;    // this quarter's 32-row slab inside a staging buffer
+      uint64_t* aux_q = aux_full + ew * N_AUX;
+      const int qbar = 1 + ew;                       // named barrier of the quarter's two warps
       const int ehalf = (warp - 4) >> 2;           // which half of the sub-tile's columns this warp owns
-      const int CWr = SUBN / 2;                    // 32 (bf16 out) or 16 (f32 out) columns per warp
       const int row = ew * 32 + lane;              // row inside the tile == TMEM lane
       const uint32_t swz = (uint32_t)(row & 7);
       const uint32_t cb = (uint32_t)(ehalf * 4);   // first 16-byte chunk of this warp's 64-byte share
@@ -459,93 +457,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       auto issue_aux = [&](long q) {
         int m0, n0;
         q_coords(q, m0, n0);
-        uint64_t* bar = &aux_full[q % N_AUX];
-        mbar_expect_tx(bar, EPI_BUF_BYTES);
-        tma_load_2d(sAux + (q % N_AUX) * EPI_BUF_BYTES, &tma_aux, bar, n0, m0);
+        uint64_t* bar = &aux_q[q % N_AUX];
+        mbar_expect_tx(bar, EPI_BUF_BYTES / 4);
+        tma_load_2d(sAux + (q % N_AUX) * EPI_BUF_BYTES + qoff, &tma_aux, bar, n0, m0 + ew * 32);
       };
       if (aux_in && issuer)
         for (long q = 0; q < N_AUX && q < total_q; ++q) issue_aux(q);
+      // One sub-tile step.  The TMEM load of the NEXT sub-tile and the bias values of the next sub-tile are issued
+      // before this sub-tile's math, so their latencies hide behind it (accumulator registers ping-pong).
       long q = 0;
-      for (int tile = cta; tile < total_tiles; tile += ncl) {
-        const int mn = tile / splits;
-        const int n_blk = mn % n_tiles;
-        const int m_blk = (mn / n_tiles) * CL + rank;
-        const int m = m_blk * BM + row;
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
-        const float rs = (epi.row_scale && m < epi.M) ? __ldg(epi.row_scale + m / epi.rows_per_scale) : 1.f;
-#pragma unroll 1
-        for (int sidx = 0; sidx < n_sub; ++sidx, ++q) {
-          const int n0 = n_blk * BN + sidx * SUBN;
-          const bool live = n0 < epi.N;            // CTA-uniform
-          uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES + row * 128;
-          uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES + row * 128;
-          // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const bool last = (sidx == n_sub - 1);
-          if (live) {
-            const int nc = n0 + ehalf * CWr;
-            if (f32out) {
-              uint32_t acc[16];
-              tmem_ld_cols<16>(t_row + sidx * SUBN + ehalf * 16, acc);
-              tmem_ld_wait();
-              if (last) {  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
-              }
-              if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
-              staged_row<16>(epi, acc, nc, rs, ob, ab, cb, swz, false, true);
-            } else {
-              uint32_t acc[32];
-              tmem_ld_cols<32>(t_row + sidx * SUBN + ehalf * 32, acc);
-              tmem_ld_wait();
-              if (last) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
-              }
-              if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
-              staged_row<32>(epi, acc, nc, rs, ob, ab, cb, swz, dual, false);
-            }
-          } else {
-            if (last) {  // dead trailing sub-tile: still release the TMEM stage
+      auto run = [&](auto cw_tag) {
+        constexpr int CW = decltype(cw_tag)::value;   // columns per warp per sub-tile
+        constexpr int SUBC = 2 * CW;
+        constexpr int NSUB = BN / SUBC;
+        for (int tile = cta; tile < total_tiles; tile += ncl) {
+          const int mn = tile / splits;
+          const int n_blk = mn % n_tiles;
+          const int m_blk = (mn / n_tiles) * CL + rank;
+          const int m = m_blk * BM + row;
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + ehalf * CW;
+          const float rs = (epi.row_scale && m < epi.M) ? __ldg(epi.row_scale + m / epi.rows_per_scale) : 1.f;
+          auto bias_at = [&](int sidx) -> float {
+            const int col = n_blk * BN + sidx * SUBC + ehalf * CW + lane;
+            return (epi.bias && lane < CW && col < epi.N) ? __ldg(epi.bias + col) : 0.f;
+          };
+          uint32_t accA[CW], accB[CW];
+          tmem_ld_cols<CW>(t_row, accA);
+          float b_cur = bias_at(0);
+          auto step = [&](const uint32_t (&cur)[CW], uint32_t (&nxt)[CW], int sidx) {
+            const int n0 = n_blk * BN + sidx * SUBC;
+            const bool live = n0 < epi.N;            // CTA-uniform
+            const bool last = (sidx == NSUB - 1);
+            uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES + row * 128;
+            uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES + row * 128;
+            const float b_nxt = last ? 0.f : bias_at(sidx + 1);
+            // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+            tmem_ld_wait();
+            if (!last) {
+              tmem_ld_cols<CW>(t_row + (sidx + 1) * SUBC, nxt);
+            } else {  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               __syncwarp();
               if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
             }
-            if (aux_in) mbar_wait(&aux_full[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (issuer) {
-            if (live) {
-              const int m0 = m_blk * BM;
-              const uint32_t so = smem_u32(sOut + (q & 1) * EPI_BUF_BYTES);
-              if (epi.accumulate) {
-                asm volatile(
-                    "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
-                    "r"(so), "r"(n0), "r"(m0)
-                    : "memory");
-              } else {
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
-                             "r"(so), "r"(n0), "r"(m0)
-                             : "memory");
-                if (dual)
-                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out2),
-                               "r"(smem_u32(sAux + (q % N_AUX) * EPI_BUF_BYTES)), "r"(n0), "r"(m0)
+            if (aux_in) mbar_wait(&aux_q[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
+            if (live) staged_row<CW>(epi, cur, b_cur, rs, ob, ab, cb, swz, dual, CW == 16);
+            b_cur = b_nxt;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
+            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+            if (issuer) {
+              if (live) {
+                const int m0 = m_blk * BM + ew * 32;
+                const uint32_t so = smem_u32(sOut + (q & 1) * EPI_BUF_BYTES) + qoff;
+                if (epi.accumulate) {
+                  asm volatile(
+                      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
+                      "r"(so), "r"(n0), "r"(m0)
+                      : "memory");
+                } else {
+                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
+                               "r"(so), "r"(n0), "r"(m0)
                                : "memory");
+                  if (dual)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out2),
+                                 "r"(smem_u32(sAux + (q % N_AUX) * EPI_BUF_BYTES) + qoff), "r"(n0), "r"(m0)
+                                 : "memory");
+                }
               }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              // every thread is past its reads of aux buffer q % N_AUX: refill it for sub-tile q + N_AUX
+              if (aux_in && q + N_AUX < total_q) issue_aux(q + N_AUX);
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // every thread is past its reads of aux buffer q % N_AUX: refill it for sub-tile q + N_AUX
-            if (aux_in && q + N_AUX < total_q) issue_aux(q + N_AUX);
+            ++q;
+          };
+#pragma unroll 1
+          for (int sidx = 0; sidx < NSUB; sidx += 2) {
+            step(accA, accB, sidx);
+            if (NSUB > 1) step(accB, accA, sidx + 1);  // NSUB is 1 (BN 64, bf16 out) or even
           }
+          if (++as == 2) { as = 0; aphase ^= 1; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
-      }
+      };
+      if (f32out) run(std::integral_constant<int, 16>{}); else run(std::integral_constant<int, 32>{});
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
@@ -593,17 +590,17 @@ int launch(const vtb_gemm_params* p, const EpiParams& epi, int splits, cudaStrea
   if (epi.tma) {
     const bool f32 = p->out_f32 != 0;
     const uint32_t subn = f32 ? 32 : 64;
-    rc = make_tmap(&to, p->out, p->N, p->M, p->ldo, subn, BM, f32);
+    rc = make_tmap(&to, p->out, p->N, p->M, p->ldo, subn, 32, f32);  // one box per TMEM lane quarter
     if (rc) return rc;
     if (p->out2) {
-      rc = make_tmap(&to2, p->out2, p->N, p->M, p->ldo, 64, BM, false);
+      rc = make_tmap(&to2, p->out2, p->N, p->M, p->ldo, 64, 32, false);
       if (rc) return rc;
     }
     if (p->resid) {
-      rc = make_tmap(&tx, p->resid, p->N, p->M, p->ldr, 32, BM, true);
+      rc = make_tmap(&tx, p->resid, p->N, p->M, p->ldr, 32, 32, true);
       if (rc) return rc;
     } else if (p->epilogue == VTB_EPI_SILU_GRAD) {
-      rc = make_tmap(&tx, p->aux, p->N, p->M, p->ldaux, 64, BM, false);
+      rc = make_tmap(&tx, p->aux, p->N, p->M, p->ldaux, 64, 32, false);
       if (rc) return rc;
     }
   }
