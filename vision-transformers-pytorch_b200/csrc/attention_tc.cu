@@ -321,7 +321,7 @@ constexpr int SMEM_BWD = 4 * TILE_BYTES + 2 * PT_BYTES + 2 * 256 * 4 + 1024 + 25
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
-                   const bf16* __restrict__ O, int ldo, const bf16* __restrict__ dO, int lddo,
+                   const __grid_constant__ CUtensorMap to,
                    const float* __restrict__ lse, bf16* __restrict__ dQ, int lddq, bf16* __restrict__ dK,
                    int lddk, bf16* __restrict__ dV, int lddv, int heads, int nq, int nkv, float scale) {
   extern __shared__ uint8_t smem_raw[];
@@ -355,6 +355,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+      tma_prefetch_desc(&to);
       mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 8); mbar_init(bar_pds, 8);
       mbar_init(bar_pdsfree, 1); mbar_init(bar_dkv, 1); mbar_init(bar_dkvfree, 8); mbar_init(bar_dq, 1);
       mbar_fence_init();
@@ -370,10 +371,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_load, (uint32_t)((2 * nhq + 2 * nkt) * 128 * 128));
+      // O is only needed for delta = rowsum(dO * O): it lands in the (not yet used) P^T tile
+      mbar_expect_tx(bar_load, (uint32_t)((3 * nhq + 2 * nkt) * 128 * 128));
       for (int i = 0; i < nhq; ++i) {
         tma_load_3d(sQ + i * 128 * 128, &tq, bar_load, h * DH, i * 128, b);
         tma_load_3d(sdO + i * 128 * 128, &tdo, bar_load, h * DH, i * 128, b);
+        tma_load_3d(sP + i * 128 * 128, &to, bar_load, h * DH, i * 128, b);
       }
       for (int i = 0; i < nkt; ++i) {
         tma_load_3d(sK + i * 128 * 128, &tk, bar_load, h * DH, i * 128, b);
@@ -388,27 +391,32 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
       mbar_wait(bar_load, 0);
       tc_fence_after();
+      // score products of iteration `i` (key tile i / nhq, query half i % nhq)
+      auto issue_scores = [&](int i) {
+        const int kt = i / nhq, hq = i - kt * nhq;
+        const uint32_t idesc_s = umma_idesc_bf16(128, nq_half(hq), 0, 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + C_ST, umma_desc_sw128(ka + kt * 16384 + k * 32, 0, 1024),
+                    umma_desc_sw128(qa + hq * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + C_DPT, umma_desc_sw128(va + kt * 16384 + k * 32, 0, 1024),
+                    umma_desc_sw128(oa + hq * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      };
+      issue_scores(0);
       int it = 0;
       for (int kt = 0; kt < nkt; ++kt) {
         const int nk = nk_tile(kt);
         for (int hq = 0; hq < nhq; ++hq, ++it) {
           const int nqh = nq_half(hq);
-          const uint32_t idesc_s = umma_idesc_bf16(128, nqh, 0, 0);
-          // S^T / dP^T need the TMEM columns back from the previous iteration's math
-          mbar_wait(bar_sfree, (uint32_t)((it & 1) ^ 1));
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_bf16(tmem_base + C_ST, umma_desc_sw128(ka + kt * 16384 + k * 32, 0, 1024),
-                      umma_desc_sw128(qa + hq * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_bf16(tmem_base + C_DPT, umma_desc_sw128(va + kt * 16384 + k * 32, 0, 1024),
-                      umma_desc_sw128(oa + hq * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(bar_s);
-          // gradient products of this (kt, hq) once the math warps have produced P^T / dS^T
+          // the math warps have turned S^T / dP^T of this iteration into the P^T / dS^T tiles (and are done with TMEM)
           mbar_wait(bar_pds, (uint32_t)(it & 1));
+          mbar_wait(bar_sfree, (uint32_t)(it & 1));
           tc_fence_after();
+          // next scores FIRST: the math warps start on them while this iteration's gradient products run
+          if (it + 1 < nkt * nhq) issue_scores(it + 1);
           if (hq == 0 && kt > 0) {  // dV / dK accumulators are about to be overwritten: previous tile drained?
             mbar_wait(bar_dkvfree, (uint32_t)((kt - 1) & 1));
             tc_fence_after();
@@ -438,16 +446,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
     const float sl2 = scale * 1.4426950408889634f;
-    // delta_i = sum_d dO[i,d] O[i,d]; lse2_i = lse_i log2(e)   (two rows per thread, straight from global)
-    for (int i = mt; i < 256; i += BWD_MATH) {
+    // delta_i = sum_d dO[i,d] O[i,d] from the TMA-loaded tiles (both carry the same 128B swizzle, so equal physical
+    // chunks hold equal columns; chunk order rotated by the row so that 8 neighbouring rows hit 8 bank groups);
+    // lse2_i = lse_i log2(e).  One row per thread.
+    mbar_wait(bar_load, 0);
+    {
+      const int i = mt;
       float acc = 0.f, l2 = INFINITY;
       if (i < nq) {
-        const bf16* a = dO + ((long)b * nq + i) * lddo + h * DH;
-        const bf16* c = O + ((long)b * nq + i) * ldo + h * DH;
+        const uint8_t* a = sdO + i * 128;
+        const uint8_t* c = sP + i * 128;
 #pragma unroll
-        for (int d = 0; d < DH; d += 8) {
-          const uint4 ra = *reinterpret_cast<const uint4*>(a + d);
-          const uint4 rc = *reinterpret_cast<const uint4*>(c + d);
+        for (int k = 0; k < 8; ++k) {
+          const int ch = ((k ^ (i & 7)) << 4);
+          const uint4 ra = *reinterpret_cast<const uint4*>(a + ch);
+          const uint4 rc = *reinterpret_cast<const uint4*>(c + ch);
           const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wc[4] = {rc.x, rc.y, rc.z, rc.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -469,7 +482,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const int nqh = nq_half(hq);
         mbar_wait(bar_s, (uint32_t)(it & 1));
         tc_fence_after();
-        if (it > 0) mbar_wait(bar_pdsfree, (uint32_t)((it - 1) & 1));  // previous tiles no longer read by UMMA
+        bool tiles_free = (it == 0);  // the delta pass above is done with the O rows in the P^T tile (bar.sync)
         for (int c = half * 32; c < nqh; c += 64) {
           uint32_t st[32], dp[32];
           if (nqh - c >= 32) {
@@ -497,6 +510,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             }
             pp[j >> 1] = pack_bf16(p0, p1);
             dd[j >> 1] = pack_bf16(d0, d1);
+          }
+          if (!tiles_free) {  // the previous iteration's gradient products no longer read the tiles
+            mbar_wait(bar_pdsfree, (uint32_t)((it - 1) & 1));
+            tiles_free = true;
           }
           // 32 queries = 4 chunks of 16 B in this thread's row of the 64-query block (c / 64)
           const uint32_t blk = (uint32_t)(c >> 6) * 16384u + (uint32_t)row * 128u;
@@ -586,8 +603,9 @@ bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p) {
 int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream) {
   if (int rc0 = ensure_encode()) return rc0;
   const uint64_t cols = (uint64_t)p->heads * DH;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, to;
   int rc;
+  if ((rc = make_tmap3(&to, p->o, cols, p->nq, p->batch, p->ldo, 128))) return rc;
   if ((rc = make_tmap3(&tq, p->q, cols, p->nq, p->batch, p->ldq, 128))) return rc;
   if ((rc = make_tmap3(&tk, p->k, cols, p->nkv, p->batch, p->ldk, 128))) return rc;
   if ((rc = make_tmap3(&tv, p->v, cols, p->nkv, p->batch, p->ldv, 128))) return rc;
@@ -600,8 +618,7 @@ int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream) {
   const long blocks = (long)p->batch * p->heads;
   VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_bwd: grid too large");
   attn_tc_bwd_kernel<<<(unsigned)blocks, BWD_THREADS, SMEM_BWD, stream>>>(
-      tq, tk, tv, tdo, reinterpret_cast<const bf16*>(p->o), p->ldo, reinterpret_cast<const bf16*>(p->dout), p->lddo,
-      p->lse, reinterpret_cast<bf16*>(p->dq), p->lddq, reinterpret_cast<bf16*>(p->dk), p->lddk,
+      tq, tk, tv, tdo, to, p->lse, reinterpret_cast<bf16*>(p->dq), p->lddq, reinterpret_cast<bf16*>(p->dk), p->lddk,
       reinterpret_cast<bf16*>(p->dv), p->lddv, p->heads, p->nq, p->nkv, p->scale);
   VTB_LAUNCH_CHECK();
   return 0;
