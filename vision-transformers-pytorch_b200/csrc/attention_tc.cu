@@ -475,6 +475,34 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");  // delta / lse2 visible to all math warps
 
+    // dV, dK of key tile kt: TMEM -> bf16 -> global rows of the keys.  Deferred by one iteration (run after the first
+    // math pass of the NEXT key tile) so that the wait for the gradient products hides behind that pass.
+    auto drain_dkv = [&](int kt) {
+      mbar_wait(bar_dkv, (uint32_t)(kt & 1));
+      tc_fence_after();
+      {
+        const int j = kt * 128 + row;
+#pragma unroll
+        for (int part = half * 2; part < half * 2 + 2; ++part) {  // half 0: dV cols 0-31, 32-63; half 1: dK
+          uint32_t a[32];
+          tmem_ld_32x32(t_row + (part < 2 ? C_DV : C_DK) + (part & 1) * 32, a);
+          tmem_ld_wait();
+          if (j < nkv) {
+            bf16* dst = (part < 2 ? dV + ((long)b * nkv + j) * lddv : dK + ((long)b * nkv + j) * lddk) + h * DH + (part & 1) * 32;
+#pragma unroll
+            for (int e = 0; e < 32; e += 8)
+              *reinterpret_cast<uint4*>(dst + e) = make_uint4(
+                  pack_bf16(__uint_as_float(a[e]), __uint_as_float(a[e + 1])),
+                  pack_bf16(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3])),
+                  pack_bf16(__uint_as_float(a[e + 4]), __uint_as_float(a[e + 5])),
+                  pack_bf16(__uint_as_float(a[e + 6]), __uint_as_float(a[e + 7])));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dkvfree);
+    };
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
       const bool key_ok = (kt * 128 + row) < nkv;
@@ -532,33 +560,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) { mbar_arrive(bar_sfree); mbar_arrive(bar_pds); }
+        if (hq == 0 && kt > 0) drain_dkv(kt - 1);
       }
-      // dV, dK of this key tile: TMEM -> bf16 -> global rows of the keys
-      mbar_wait(bar_dkv, (uint32_t)(kt & 1));
-      tc_fence_after();
-      {
-        const int j = kt * 128 + row;
-#pragma unroll
-        for (int part = half * 2; part < half * 2 + 2; ++part) {  // half 0: dV cols 0-31, 32-63; half 1: dK
-          uint32_t a[32];
-          tmem_ld_32x32(t_row + (part < 2 ? C_DV : C_DK) + (part & 1) * 32, a);
-          tmem_ld_wait();
-          if (j < nkv) {
-            bf16* dst = (part < 2 ? dV + ((long)b * nkv + j) * lddv : dK + ((long)b * nkv + j) * lddk) + h * DH + (part & 1) * 32;
-#pragma unroll
-            for (int e = 0; e < 32; e += 8)
-              *reinterpret_cast<uint4*>(dst + e) = make_uint4(
-                  pack_bf16(__uint_as_float(a[e]), __uint_as_float(a[e + 1])),
-                  pack_bf16(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3])),
-                  pack_bf16(__uint_as_float(a[e + 4]), __uint_as_float(a[e + 5])),
-                  pack_bf16(__uint_as_float(a[e + 6]), __uint_as_float(a[e + 7])));
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dkvfree);
     }
+    drain_dkv(nkt - 1);
     // dQ: rows = queries
     mbar_wait(bar_dq, 0);
     tc_fence_after();
