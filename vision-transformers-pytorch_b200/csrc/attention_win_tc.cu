@@ -9,10 +9,11 @@
 //       off-diagonal work and no garbage.  The same tiles serve the other products as MN-major operands (the padded
 //       tile as B kills the cross-window terms), so nothing is transposed or copied.
 // One persistent CTA per SM, fixed head per CTA (its bias tile lives in shared memory for the whole kernel):
-//   warps 0-1  : loaders, one token row of each window per thread, cp.async 16-byte gathers straight out of the
-//                fused qkv buffer (window partition and cyclic shift are address arithmetic), two tiles in flight
-//   warp 2     : tcgen05.mma issuer (one thread), TMEM allocation
+//   warps 0-3  : loaders, cp.async 16-byte gathers straight out of the fused qkv buffer (window partition and
+//                cyclic shift are address arithmetic); the copies themselves complete the stage barriers
 //   warps 4-11 : math, one tile row (TMEM lane) per thread, scores read straight from TMEM
+//   warp 12    : tcgen05.mma issuer (one thread), TMEM allocation
+// Registers are re-balanced with setmaxnreg: loader / issuer warpgroups give theirs to the two math warpgroups.
 // Relative-position bias and shift mask are an fp32 tile (pre-multiplied by log2 e, -inf on key padding) and one
 // 64-bit word per row; the bias gradient is accumulated in registers over every window a thread sees and reduced
 // once per CTA.
@@ -22,7 +23,7 @@
 
 namespace {
 
-constexpr int WT_THREADS = 384;
+constexpr int WT_THREADS = 512;
 constexpr float WT_L2E = 1.4426950408889634f;
 constexpr float WT_LN2 = 0.6931471805599453f;
 
@@ -51,13 +52,13 @@ __device__ __forceinline__ int wt_token(const WtGeom& g, int grp, int t) {
   return (b * g.Hs + y) * g.Ws + x;
 }
 // group part / row part of wt_token (the loaders resolve several rows of the same window)
-struct WtOrigin { int y0, x0, img; };
+struct WtOrigin { int y0, x0, img, wi; };
 __device__ __forceinline__ WtOrigin wt_origin(const WtGeom& g, int grp) {
   WtOrigin o;
-  if (grp >= g.groups) { o.img = -1; o.y0 = o.x0 = 0; return o; }
+  if (grp >= g.groups) { o.img = -1; o.y0 = o.x0 = o.wi = 0; return o; }
   const int b = wt_div(grp, g.nw, g.inv_nw), wi = grp - b * g.nw;
   const int wy = wt_div(wi, g.nwx, g.inv_nwx), wx = wi - wy * g.nwx;
-  o.img = b; o.y0 = wy * g.window + g.shift; o.x0 = wx * g.window + g.shift;
+  o.img = b; o.wi = wi; o.y0 = wy * g.window + g.shift; o.x0 = wx * g.window + g.shift;
   return o;
 }
 __device__ __forceinline__ int wt_row_token(const WtGeom& g, const WtOrigin& o, int t) {
@@ -149,6 +150,8 @@ __device__ __forceinline__ void wt_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+template <int N> __device__ __forceinline__ void wt_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void wt_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void wt_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // release a barrier once per warp after every lane is done
 __device__ __forceinline__ void wt_warp_arrive(uint64_t* bar, int lane) {
@@ -205,7 +208,7 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   uint8_t* sBias = smem + F_STAGES * F_STAGE_BYTES;
   uint8_t* sSide = sBias + 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSide + F_STAGES * F_SIDE_BYTES);
-  uint64_t* full = bars;                 // [6] 64 cp.async arrivals (loader threads) -> issuer / math
+  uint64_t* full = bars;                 // [6] 128 cp.async arrivals (loader threads) -> issuer / math
   uint64_t* empty = bars + 6;            // [6] PV retired -> loaders
   uint64_t* s_full = bars + 12;          // [4] S complete
   uint64_t* p_full = bars + 16;          // [4] P written (4 warps)
@@ -219,13 +222,13 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   const int my_tiles = (ntiles - chunk + nchunks - 1) / nchunks;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < F_STAGES; ++i) { mbar_init(&full[i], 64); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < F_STAGES; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
   // zero the operand ring once (the zero halves of Qpad never change; padding rows are re-zeroed by the loaders)
   for (int e = threadIdx.x; e < F_STAGES * F_STAGE_BYTES / 16; e += WT_THREADS)
     reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
@@ -239,14 +242,15 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 2) {
-    // ------------------------------------------------------------------ loaders (64 threads)
-    // four lanes cover the four 16-byte chunks of one token row (8 rows x 64 B per warp instruction); thread tt also
-    // fetches the mask words of rows (0, tt), (1, tt).  The stage barrier is completed by the copies themselves.
-    const int tt = threadIdx.x, cc = tt & 3, r4 = tt >> 2;
+  if (warp < 4) {
+    // ------------------------------------------------------------------ loaders (128 threads)
+    // thread = (window w, chunk cc of rows r4 + 16 it): four lanes cover the four 16-byte chunks of one token row
+    // (8 rows x 64 B per warp instruction); thread tt also fetches the mask word of tile row tt.
+    wt_reg_dec<80>();
+    const int tt = threadIdx.x, w = tt >> 6, tl = tt & 63, cc = tl & 3, r4 = tl >> 2;
     const WtRows rows = wt_rows(g, r4);
-    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u;
-    const uint32_t ch[2] = {(uint32_t)((cc ^ (r4 & 7)) << 4), (uint32_t)(((4 + cc) ^ (r4 & 7)) << 4)};
+    const uint32_t ch = (uint32_t)(((w * 4 + cc) ^ (r4 & 7)) << 4);
+    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u + ch;
     const char* qb = reinterpret_cast<const char*>(p.q) + (h * 32 + cc * 8) * 2;
     const char* kb = reinterpret_cast<const char*>(p.k) + (h * 32 + cc * 8) * 2;
     const char* vb = reinterpret_cast<const char*>(p.v) + (h * 32 + cc * 8) * 2;
@@ -257,31 +261,29 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       mbar_wait(&empty[stage], ((n / F_STAGES) & 1) ^ 1);
       const uint32_t st = st0 + stage * F_STAGE_BYTES;
       unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * F_SIDE_BYTES);
+      const int grp = tile * 2 + w;
+      const WtOrigin org = wt_origin(g, grp);
+      const bool ok = org.img >= 0;
+      if (p.mask_bits && ok && tl < g.nq)
+        cp_async8(smem_u32(&s_mb[tt]), reinterpret_cast<const unsigned long long*>(p.mask_bits) +
+                                           (long)(p.n_mask == g.nw ? org.wi : grp % p.n_mask) * 128 + tl);
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int grp = tile * 2 + w;
-        const WtOrigin org = wt_origin(g, grp);
-        if (p.mask_bits && org.img >= 0 && tt < g.nq)
-          cp_async8(smem_u32(&s_mb[w * 64 + tt]),
-                    reinterpret_cast<const unsigned long long*>(p.mask_bits) + (long)(grp % p.n_mask) * 128 + tt);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (rows.valid[it]) {  // rows >= nq stay zero from the prologue
-            const bool ok = org.img >= 0;
-            const long gr = ok ? (long)wt_tok(g, org, rows.ty[it], rows.tx[it]) : 0;
-            const uint32_t ro = (uint32_t)(it * 16) * 128u + ch[w];
-            cp_async16(st + (uint32_t)(w * 64) * 128u + ro, qb + gr * ldq2, ok);
-            cp_async16(st + 16384 + ro, kb + gr * ldk2, ok);
-            cp_async16(st + 24576 + ro, vb + gr * ldv2, ok);
-          }
+      for (int it = 0; it < 4; ++it) {
+        if (rows.valid[it]) {  // rows >= nq stay zero from the prologue
+          const long gr = ok ? (long)wt_tok(g, org, rows.ty[it], rows.tx[it]) : 0;
+          const uint32_t ro = (uint32_t)(it * 16) * 128u;
+          cp_async16(st + (uint32_t)(w * 64) * 128u + ro, qb + gr * ldq2, ok);
+          cp_async16(st + 16384 + ro, kb + gr * ldk2, ok);
+          cp_async16(st + 24576 + ro, vb + gr * ldv2, ok);
         }
       }
       cp_async_arrive_noinc(&full[stage]);
     }
     cp_async_wait<0>();  // nothing may still be in flight towards this CTA's shared memory at exit
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ UMMA issuer (warp 12, one thread)
+    wt_reg_dec<40>();
+    if (warp == 12 && lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       // event-driven: whichever of "next score tile" / "next P.V" has its inputs ready is issued, so a late load
@@ -324,8 +326,9 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
         if (did) dog.reset(); else dog.idle();
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------------ math: thread = query row (w, i)
+    wt_reg_inc<192>();
     const int grpi = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane, w = r >> 6, i = r & 63;
@@ -399,7 +402,7 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -431,8 +434,8 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   uint8_t* sBias = sP + 16384;
   uint8_t* sSide = sBias + 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSide + B_STAGES * B_SIDE_BYTES);
-  uint64_t* full = bars;            // [3] count 2 (loader warps, after delta / lse of the landed tile are in place)
-  uint64_t* land = bars + 16;       // [3] 64 cp.async arrivals: the tile's rows have landed
+  uint64_t* full = bars;            // [3] count 4 (loader warps, after delta / lse of the landed tile are in place)
+  uint64_t* land = bars + 16;       // [3] 128 cp.async arrivals: the tile's rows have landed
   uint64_t* empty = bars + 3;       // [3] gradient MMAs of the tile retired
   uint64_t* s_full = bars + 6;      // [2] S^T / dP^T complete
   uint64_t* s_free = bars + 8;      // [2] read out of TMEM (8 warps)
@@ -449,12 +452,12 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   const bool has_tab = p.rel_bias != nullptr && p.drel_bias != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); mbar_init(&land[i], 64); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); mbar_init(&land[i], 128); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); }
     mbar_init(pds_full, 8); mbar_init(pds_free, 1); mbar_init(g_full, 1); mbar_init(g_free, 8);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
   for (int e = threadIdx.x; e < (B_STAGES * B_STAGE_BYTES + 2 * 16384) / 16; e += WT_THREADS)
     reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -466,42 +469,38 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 2) {
-    // ------------------------------------------------------------------ loaders (64 threads)
-    // data: four lanes cover the four 16-byte chunks of one token row; side info (token, mask word, lse, delta):
-    // thread tt owns rows (0, tt) and (1, tt).  Everything a tile needs arrives by cp.async (no blocking loads);
-    // two tiles in flight.
-    const int tt = threadIdx.x, cc = tt & 3, r4 = tt >> 2;
-    // the previous tile's rows have landed: delta = dO . O and lse * log2(e) from shared memory, then release
+  if (warp < 4) {
+    // ------------------------------------------------------------------ loaders (128 threads)
+    // data: thread = (window w, chunk cc of rows r4 + 16 it), four lanes per token row; side info (token, mask word,
+    // lse, delta): thread tt owns tile row tt.  Everything a tile needs arrives by cp.async (no blocking loads).
+    wt_reg_dec<80>();
+    const int tt = threadIdx.x, w = tt >> 6, tl = tt & 63, cc = tl & 3, r4 = tl >> 2;
+    // a tile's rows have landed: delta = dO . O and lse * log2(e) from shared memory, then release
     auto finish = [&](int stage) {
       uint8_t* st = sStage + stage * B_STAGE_BYTES;
       float* side = reinterpret_cast<float*>(sSide + stage * B_SIDE_BYTES);
       const int* s_tok = reinterpret_cast<const int*>(side);
+      float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int t = w * 64 + tt;
-        float acc = 0.f;
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const uint4 ra = *reinterpret_cast<const uint4*>(st + B_OFF_DO + sw128(tl, w * 4 + c4));
+        const uint4 rb = *reinterpret_cast<const uint4*>(st + B_OFF_O + tt * 64 + c4 * 16);
+        const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const uint4 ra = *reinterpret_cast<const uint4*>(st + B_OFF_DO + sw128(tt, w * 4 + c4));
-          const uint4 rb = *reinterpret_cast<const uint4*>(st + B_OFF_O + t * 64 + c4 * 16);
-          const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
-            acc += fa.x * fb.x + fa.y * fb.y;
-          }
+        for (int q = 0; q < 4; ++q) {
+          const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
+          acc += fa.x * fb.x + fa.y * fb.y;
         }
-        side[128 + t] = (s_tok[t] >= 0) ? side[128 + t] * WT_L2E : INFINITY;
-        side[256 + t] = acc;
       }
+      side[128 + tt] = (s_tok[tt] >= 0) ? side[128 + tt] * WT_L2E : INFINITY;
+      side[256 + tt] = acc;
       wt_proxy_fence();
       wt_warp_arrive(&full[stage], lane);
     };
     const WtRows rows = wt_rows(g, r4);
-    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u;
-    const uint32_t so0 = smem_u32(sStage) + B_OFF_O + (uint32_t)r4 * 64u + cc * 16;
-    const uint32_t ch[2] = {(uint32_t)((cc ^ (r4 & 7)) << 4), (uint32_t)(((4 + cc) ^ (r4 & 7)) << 4)};
+    const uint32_t ch = (uint32_t)(((w * 4 + cc) ^ (r4 & 7)) << 4);
+    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u + ch;
+    const uint32_t so0 = smem_u32(sStage) + B_OFF_O + (uint32_t)(w * 64 + r4) * 64u + cc * 16;
     const int colb = (h * 32 + cc * 8) * 2;
     const char* qb = reinterpret_cast<const char*>(p.q) + colb;
     const char* kb = reinterpret_cast<const char*>(p.k) + colb;
@@ -517,31 +516,27 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       float* side = reinterpret_cast<float*>(sSide + stage * B_SIDE_BYTES);
       int* s_tok = reinterpret_cast<int*>(side);
       unsigned long long* s_mb = reinterpret_cast<unsigned long long*>(sSide + stage * B_SIDE_BYTES + 1536);
+      const int grp = tile * 2 + w;
+      const WtOrigin org = wt_origin(g, grp);
+      const bool ok = org.img >= 0;
+      const int tok_side = wt_row_token(g, org, tl);
+      s_tok[tt] = tok_side;
+      if (p.mask_bits && tok_side >= 0)
+        cp_async8(smem_u32(&s_mb[tt]), reinterpret_cast<const unsigned long long*>(p.mask_bits) +
+                                           (long)(p.n_mask == g.nw ? org.wi : grp % p.n_mask) * 128 + 64 + tl);
+      else
+        s_mb[tt] = 0ull;
+      if (tok_side >= 0) cp_async4(smem_u32(&side[128 + tt]), p.lse + ((long)grp * g.heads + h) * g.nq + tl);
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int grp = tile * 2 + w;
-        const WtOrigin org = wt_origin(g, grp);
-        const int tok_side = wt_row_token(g, org, tt);
-        s_tok[w * 64 + tt] = tok_side;
-        if (p.mask_bits && tok_side >= 0)
-          cp_async8(smem_u32(&s_mb[w * 64 + tt]),
-                    reinterpret_cast<const unsigned long long*>(p.mask_bits) + (long)(grp % p.n_mask) * 128 + 64 + tt);
-        else
-          s_mb[w * 64 + tt] = 0ull;
-        if (tok_side >= 0)
-          cp_async4(smem_u32(&side[128 + w * 64 + tt]), p.lse + ((long)grp * g.heads + h) * g.nq + tt);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (rows.valid[it]) {  // rows >= nq stay zero from the prologue
-            const bool ok = org.img >= 0;
-            const long gr = ok ? (long)wt_tok(g, org, rows.ty[it], rows.tx[it]) : 0;
-            const uint32_t ro = (uint32_t)(it * 16) * 128u + ch[w];
-            cp_async16(st + (uint32_t)(w * 64) * 128u + ro, kb + gr * ldk2, ok);
-            cp_async16(st + B_OFF_V + (uint32_t)(w * 64) * 128u + ro, vb + gr * ldv2, ok);
-            cp_async16(st + B_OFF_Q + ro, qb + gr * ldq2, ok);
-            cp_async16(st + B_OFF_DO + ro, dob + gr * lddo2, ok);
-            cp_async16(so + (uint32_t)(w * 64 + it * 16) * 64u, ob + gr * ldo2, ok);
-          }
+      for (int it = 0; it < 4; ++it) {
+        if (rows.valid[it]) {  // rows >= nq stay zero from the prologue
+          const long gr = ok ? (long)wt_tok(g, org, rows.ty[it], rows.tx[it]) : 0;
+          const uint32_t ro = (uint32_t)(it * 16) * 128u;
+          cp_async16(st + (uint32_t)(w * 64) * 128u + ro, kb + gr * ldk2, ok);
+          cp_async16(st + B_OFF_V + (uint32_t)(w * 64) * 128u + ro, vb + gr * ldv2, ok);
+          cp_async16(st + B_OFF_Q + ro, qb + gr * ldq2, ok);
+          cp_async16(st + B_OFF_DO + ro, dob + gr * lddo2, ok);
+          cp_async16(so + (uint32_t)(it * 16) * 64u, ob + gr * ldo2, ok);
         }
       }
       cp_async_arrive_noinc(&land[stage]);
@@ -566,9 +561,10 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       if (did) dog.reset(); else dog.idle();
     }
     cp_async_wait<0>();
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ UMMA issuer (warp 12, one thread)
+    wt_reg_dec<40>();
+    if (warp == 12 && lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 1, 1);
@@ -624,8 +620,9 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
         if (did) dog.reset(); else dog.idle();
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------------ math: thread = key row (w, j), 32 of the 64 queries
+    wt_reg_inc<192>();
     const int half = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane, w = r >> 6, j = r & 63;
@@ -734,7 +731,7 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
