@@ -2,6 +2,8 @@
 //   warp 0      : TMA producer (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1      : UMMA issuer  (tcgen05.mma cta_group::1, M=128, N=BN, K=16; fp32 accumulators in TMEM)
 //   warp 2      : TMEM allocator
+//   warp 3      : epilogue TMA helper: lanes 0-3 issue the TMA stores / aux prefetches of the four TMEM lane quarters
+//                 (a bulk-tensor instruction costs its issuing thread 250-800 cycles, measured: off the math warps)
 //   warps 4..11 : epilogue (two warps per TMEM lane quarter, each taking half the columns): tcgen05.ld -> registers -> fused epilogue -> 128B-swizzled smem staging ->
 //                 TMA store (cp.async.bulk.tensor; cp.reduce.async.bulk .add for split-K); residual /
 //                 pre-activation tiles are TMA-prefetched into smem three sub-tiles ahead.
@@ -30,6 +32,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
+#ifdef VTB_GEMM_TRACE
+__device__ unsigned long long g_trace[16];
+#define TRACE_T(i) const long long tr##i = clock64()
+#else
+#define TRACE_T(i)
+#endif
 int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces 1-CTA tiles,
                               // 2 forces pairs wherever legal (tests)
 
@@ -60,10 +68,10 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // epilogue staging: 2 output buffers + 3 aux buffers (second output, or prefetched residual / pre-activation)
   static constexpr int STAGING_BYTES = (2 + 3) * EPI_BUF_BYTES;
-  static constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align*/ - 256 /*barriers*/;
+  static constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align*/ - 512 /*barriers*/;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 6 ? 6 : (RING_BUDGET / STAGE_BYTES);  // 3/4/6 (CL=1), 4/6/6 (CL=2)
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 512 / 256 / 128
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 // One 32-column chunk of one accumulator row -> global memory with the fused epilogue.
@@ -176,8 +184,13 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
                                            uint8_t* ob, uint8_t* ab, uint32_t cb, uint32_t swz, bool dual,
                                            bool f32out) {
   float v[CW];
+  if (e.alpha != 1.f) {
 #pragma unroll
-  for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+  } else {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]);
+  }
   if (e.bias) {  // lane j of the warp holds the bias of this warp's column j (prefetched one sub-tile ahead)
 #pragma unroll
     for (int j = 0; j < CW; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
@@ -263,7 +276,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
   uint64_t* aux_full = bars + 2 * C::STAGES + 4;              // [4 lane quarters][N_AUX]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 4 * N_AUX);
+  uint64_t* staged_bar = aux_full + 4 * N_AUX;                // [4 quarters][2]: sub-tile written + fenced (2 warps)
+  uint64_t* free_bar = staged_bar + 8;                        // [4 quarters][2]: TMA has read the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -282,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&tmem_empty[i], 8 * CL);  // every epilogue warp of the pair arrives on the leader's barrier
     }
     for (int i = 0; i < 4 * N_AUX; ++i) mbar_init(&aux_full[i], 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&staged_bar[i], 2); mbar_init(&free_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -396,6 +412,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ epilogue TMA helper (staged path only)
+    if (epi.tma && lane < 4) {
+      const int k = lane;                            // TMEM lane quarter served by this lane
+      const bool f32out = epi.out_f32 != 0;
+      const int SUBN = f32out ? 32 : 64;
+      const int n_sub = BN / SUBN;
+      const bool dual = epi.epilogue == VTB_EPI_SILU_DUAL;
+      const bool aux_in = (epi.resid != nullptr) || (epi.epilogue == VTB_EPI_SILU_GRAD);
+      const uint32_t qoff = (uint32_t)k * 4096u;
+      uint64_t* aux_q = aux_full + k * N_AUX;
+      const int my_tiles = (total_tiles - cta + ncl - 1) / ncl;
+      const long total_q = (long)my_tiles * n_sub;
+      auto q_coords = [&](long q, int& m0, int& n0) {
+        const int tl = (int)(q / n_sub), sidx = (int)(q - (long)tl * n_sub);
+        const int tile = cta + tl * ncl;
+        const int mn = tile / splits;
+        m0 = ((mn / n_tiles) * CL + rank) * BM + k * 32;
+        n0 = (mn % n_tiles) * BN + sidx * SUBN;
+      };
+      auto issue_aux = [&](long q) {
+        int m0, n0;
+        q_coords(q, m0, n0);
+        uint64_t* bar = &aux_q[q % N_AUX];
+        mbar_expect_tx(bar, EPI_BUF_BYTES / 4);
+        tma_load_2d(sAux + (q % N_AUX) * EPI_BUF_BYTES + qoff, &tma_aux, bar, n0, m0);
+      };
+      tma_prefetch_desc(&tma_out);
+      if (dual) tma_prefetch_desc(&tma_out2);
+      if (aux_in) {
+        tma_prefetch_desc(&tma_aux);
+        for (long q = 0; q < N_AUX && q < total_q; ++q) issue_aux(q);
+      }
+      for (long q = 0; q < total_q; ++q) {
+        mbar_wait(&staged_bar[k * 2 + (q & 1)], (uint32_t)((q >> 1) & 1));
+        if (q >= 1) {
+          // the store of sub-tile q-1 (issued a whole sub-tile ago) has been read out of its staging buffer: hand the
+          // buffer back BEFORE the slow bulk-tensor issue below, the math warps want it for sub-tile q+1
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&free_bar[k * 2 + ((q - 1) & 1)]);
+        }
+        int m0, n0;
+        q_coords(q, m0, n0);
+        if (n0 < epi.N) {
+          const uint32_t so = smem_u32(sOut + (q & 1) * EPI_BUF_BYTES) + qoff;
+          if (epi.accumulate) {
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
+                "r"(so), "r"(n0), "r"(m0)
+                : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
+                         "r"(so), "r"(n0), "r"(m0)
+                         : "memory");
+            if (dual)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out2),
+                           "r"(smem_u32(sAux + (q % N_AUX) * EPI_BUF_BYTES) + qoff), "r"(n0), "r"(m0)
+                           : "memory");
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // both warps of the quarter are past their reads of aux buffer q % N_AUX: refill it for sub-tile q + N_AUX
+        if (aux_in && q + N_AUX < total_q) issue_aux(q + N_AUX);
+      }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
@@ -429,40 +511,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else {
       // staged path: sub-tiles of SUBN columns (one 128-byte row each) -> swizzled smem -> TMA store.
       // The four TMEM lane quarters run INDEPENDENTLY: the two warps of a quarter share a 32-row slab of every staging
-      // buffer, meet on their own 64-thread named barrier, and one of them issues the quarter's own TMA stores /
-      // aux prefetches (32-row boxes), so a quarter never waits for the other three and their TMEM-load, MUFU and
-      // fence latencies overlap.
+      // buffer; a finished slab is handed (mbarrier) to the quarter's lane of the helper warp, which issues the TMA
+      // store / aux prefetch (32-row boxes) and hands the buffer back once TMA has read it.  The math warps execute no
+      // bulk-tensor instruction, no wait_group and no named barrier.
       const bool f32out = epi.out_f32 != 0;
       const int SUBN = f32out ? 32 : 64;
       const int n_sub = BN / SUBN;
       const bool dual = epi.epilogue == VTB_EPI_SILU_DUAL;
       const bool aux_in = (epi.resid != nullptr) || (epi.epilogue == VTB_EPI_SILU_GRAD);
-      const bool issuer = (warp < 8) && (lane == 0);  // one per lane quarter
-      const uint32_t qoff = (uint32_t)ew * 4096u;    // this quarter's 32-row slab inside a staging buffer
       uint64_t* aux_q = aux_full + ew * N_AUX;
-      const int qbar = 1 + ew;                       // named barrier of the quarter's two warps
+      uint64_t* staged_q = staged_bar + ew * 2;
+      uint64_t* free_q = free_bar + ew * 2;
       const int ehalf = (warp - 4) >> 2;           // which half of the sub-tile's columns this warp owns
       const int row = ew * 32 + lane;              // row inside the tile == TMEM lane
       const uint32_t swz = (uint32_t)(row & 7);
       const uint32_t cb = (uint32_t)(ehalf * 4);   // first 16-byte chunk of this warp's 64-byte share
-      const int my_tiles = (total_tiles - cta + ncl - 1) / ncl;
-      const long total_q = (long)my_tiles * n_sub;
-      auto q_coords = [&](long q, int& m0, int& n0) {
-        const int tl = (int)(q / n_sub), sidx = (int)(q - (long)tl * n_sub);
-        const int tile = cta + tl * ncl;
-        const int mn = tile / splits;
-        m0 = ((mn / n_tiles) * CL + rank) * BM;
-        n0 = (mn % n_tiles) * BN + sidx * SUBN;
-      };
-      auto issue_aux = [&](long q) {
-        int m0, n0;
-        q_coords(q, m0, n0);
-        uint64_t* bar = &aux_q[q % N_AUX];
-        mbar_expect_tx(bar, EPI_BUF_BYTES / 4);
-        tma_load_2d(sAux + (q % N_AUX) * EPI_BUF_BYTES + qoff, &tma_aux, bar, n0, m0 + ew * 32);
-      };
-      if (aux_in && issuer)
-        for (long q = 0; q < N_AUX && q < total_q; ++q) issue_aux(q);
       // One sub-tile step.  The TMEM load of the NEXT sub-tile and the bias values of the next sub-tile are issued
       // before this sub-tile's math, so their latencies hide behind it (accumulator registers ping-pong).
       long q = 0;
@@ -493,10 +556,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES + row * 128;
             uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES + row * 128;
             const float b_nxt = last ? 0.f : bias_at(sidx + 1);
-            // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+            TRACE_T(0);
+            TRACE_T(1);
+            TRACE_T(2);
             tmem_ld_wait();
+            TRACE_T(3);
             if (!last) {
               tmem_ld_cols<CW>(t_row + (sidx + 1) * SUBC, nxt);
             } else {  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
@@ -505,33 +569,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
             }
             if (aux_in) mbar_wait(&aux_q[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
+            // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
+            mbar_wait(&free_q[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));
+            TRACE_T(4);
             if (live) staged_row<CW>(epi, cur, b_cur, rs, ob, ab, cb, swz, dual, CW == 16);
             b_cur = b_nxt;
+            TRACE_T(5);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
-            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
-            if (issuer) {
-              if (live) {
-                const int m0 = m_blk * BM + ew * 32;
-                const uint32_t so = smem_u32(sOut + (q & 1) * EPI_BUF_BYTES) + qoff;
-                if (epi.accumulate) {
-                  asm volatile(
-                      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
-                      "r"(so), "r"(n0), "r"(m0)
-                      : "memory");
-                } else {
-                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
-                               "r"(so), "r"(n0), "r"(m0)
-                               : "memory");
-                  if (dual)
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out2),
-                                 "r"(smem_u32(sAux + (q % N_AUX) * EPI_BUF_BYTES) + qoff), "r"(n0), "r"(m0)
-                                 : "memory");
-                }
-              }
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              // every thread is past its reads of aux buffer q % N_AUX: refill it for sub-tile q + N_AUX
-              if (aux_in && q + N_AUX < total_q) issue_aux(q + N_AUX);
+            TRACE_T(6);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&staged_q[q & 1]);
+            TRACE_T(7);
+#ifdef VTB_GEMM_TRACE
+            if (lane == 0 && blockIdx.x == 7) {
+              const long long tr8 = clock64();
+              const long long d[8] = {tr1 - tr0, tr2 - tr1, tr3 - tr2, tr4 - tr3, tr5 - tr4, tr6 - tr5, tr7 - tr6, tr8 - tr7};
+              for (int i = 0; i < 8; ++i) atomicAdd(&g_trace[i + (ehalf ? 8 : 0)], (unsigned long long)d[i]);
             }
+#endif
             ++q;
           };
 #pragma unroll 1
@@ -543,7 +598,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       };
       if (f32out) run(std::integral_constant<int, 16>{}); else run(std::integral_constant<int, 32>{});
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
   }
 
@@ -770,3 +824,11 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
     default:  return pair ? dispatch_major<64, 2>(p, e, splits, stream) : dispatch_major<64, 1>(p, e, splits, stream);
   }
 }
+
+#ifdef VTB_GEMM_TRACE
+extern "C" int vtb_debug_gemm_trace(unsigned long long* out, int reset) {
+  if (out) VTB_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; VTB_CUDA(cudaMemcpyToSymbol(g_trace, z, sizeof(z))); }
+  return 0;
+}
+#endif
