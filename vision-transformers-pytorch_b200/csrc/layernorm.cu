@@ -15,20 +15,26 @@ struct RowMap {
   int cols;
 };
 
-// pointer to the float4 #v of logical row r
-__device__ __forceinline__ long row_v4_offset(const RowMap& g, long r, int v) {
-  if (g.patch_s <= 1) return r * (long)g.cols + (long)v * 4;
+// Address of float4 #v of logical row r = row_base(r) + seg_off(v): the patchify gather (swin:15-22) splits into a
+// per-row part (three 32-bit divisions per ROW) and a per-lane part that does not depend on the row at all, so the
+// kernels below compute seg_off once per thread and row_base once per row instead of dividing per element.
+__device__ __forceinline__ long row_base(const RowMap& g, long r) {
+  if (g.patch_s <= 1) return r * (long)g.cols;
   const int s = g.patch_s;
-  const int Ho = g.Hin / s, Wo = g.Win / s;
-  const int bx = (int)(r % Wo);
-  const long t = r / Wo;
-  const int by = (int)(t % Ho);
-  const long b = t / Ho;
+  const unsigned Ho = g.Hin / s, Wo = g.Win / s;
+  const unsigned ri = (unsigned)r;       // rows < 2^31 (checked on the host)
+  const unsigned t = ri / Wo, bx = ri - t * Wo;
+  const unsigned b = t / Ho, by = t - b * Ho;
+  return (((long)b * g.Hin + (long)by * s) * g.Win + (long)bx * s) * g.C;
+}
+__device__ __forceinline__ int seg_off(const RowMap& g, int v) {
   const int f = v * 4;
+  if (g.patch_s <= 1) return f;
+  const int s = g.patch_s;
   const int seg = f / g.C;  // sy*s + sx
   const int c = f - seg * g.C;
   const int sy = seg / s, sx = seg - sy * s;
-  return ((b * g.Hin + (long)by * s + sy) * g.Win + (long)bx * s + sx) * g.C + c;
+  return (sy * g.Win + sx) * g.C + c;
 }
 
 template <bool OUT_F32, int MAX_V4_PER_LANE>
@@ -39,15 +45,19 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ rowmod_add, int group_rows) {
   const int lane = threadIdx.x & 31;
   const int nv = g.cols >> 2;
+  int soff[MAX_V4_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAX_V4_PER_LANE; ++i) soff[i] = seg_off(g, lane + i * 32);
   for (long r = (long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); r < rows;
        r += (long)gridDim.x * LN_WARPS) {
     float4 xv[MAX_V4_PER_LANE];
     float s = 0.f;
+    const float* xr = x + row_base(g, r);
 #pragma unroll
     for (int i = 0; i < MAX_V4_PER_LANE; ++i) {
       const int v = lane + i * 32;
       if (v < nv) {
-        xv[i] = *reinterpret_cast<const float4*>(x + row_v4_offset(g, r, v));
+        xv[i] = *reinterpret_cast<const float4*>(xr + soff[i]);
         s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
       }
     }
@@ -112,10 +122,12 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   __syncthreads();
 
   float4 dg[NV], db[NV];
+  int soff[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    soff[i] = seg_off(g, lane + i * 32);
   }
 
   for (long r = (long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); r < rows;
@@ -123,12 +135,13 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     float4 xv[NV];
     float4 dvf[DY_F32 ? NV : 1];
     uint2 dvh[DY_F32 ? 1 : NV];
+    const long rbase = row_base(g, r);
     // issue every load of the row first
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nv) {
-        xv[i] = *reinterpret_cast<const float4*>(x + row_v4_offset(g, r, v));
+        xv[i] = *reinterpret_cast<const float4*>(x + rbase + soff[i]);
         if (DY_F32)
           dvf[DY_F32 ? i : 0] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + r * (long)g.cols + v * 4);
         else
@@ -178,7 +191,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
         o.y = rstd * (d.y * gm.y - s1 - xv[i].y * s2);
         o.z = rstd * (d.z * gm.z - s1 - xv[i].z * s2);
         o.w = rstd * (d.w * gm.w - s1 - xv[i].w * s2);
-        const long off = row_v4_offset(g, r, v);
+        const long off = rbase + soff[i];
         if (dx_in) {
           const float4 p = *reinterpret_cast<const float4*>(dx_in + off);
           o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
@@ -556,7 +569,7 @@ size_t stream_geom(long rows, int cols, size_t bytes_per_elem, size_t fixed_byte
 }
 
 int check_geom(const char* who, long rows, int cols, int patch_s, int Hin, int Win, RowMap* g) {
-  VTB_CHECK(rows > 0 && cols > 0, -1, "%s: bad shape rows=%ld cols=%d", who, rows, cols);
+  VTB_CHECK(rows > 0 && rows < (1L << 31) && cols > 0, -1, "%s: bad shape rows=%ld cols=%d", who, rows, cols);
   VTB_CHECK(cols % 4 == 0 && cols <= MAX_COLS, -1,
             "%s: cols=%d must be a multiple of 4 and <= %d", who, cols, MAX_COLS);
   g->patch_s = patch_s; g->Hin = Hin; g->Win = Win; g->cols = cols; g->C = cols;
