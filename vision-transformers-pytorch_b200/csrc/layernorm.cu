@@ -235,6 +235,15 @@ constexpr int ST_MAX_STAGES = 12;
 bool g_ln_stream = true;  // vtb_set_option("ln_stream", 0) falls back to the register-resident kernels (A/B timing)
 constexpr int ST_GROUP_WARPS = 4;
 
+// sum over the LPR lanes that share a row (LPR = 32: the whole warp; LPR = 8: four rows per warp for narrow rows,
+// so that all lanes load and the shuffle chain is 3 steps instead of 5)
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -248,7 +257,7 @@ struct StreamGeom {
   long n_tiles;
 };
 
-template <int NV, bool OUT_F32, int GROUPS>
+template <int NV, bool OUT_F32, int GROUPS, int LPR>
 __global__ void __launch_bounds__((GROUPS * ST_GROUP_WARPS + 1) * 32, 1)
 ln_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, StreamGeom g, void* __restrict__ y,
@@ -284,12 +293,14 @@ ln_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     return;
   }
   const int grp = warp / ST_GROUP_WARPS, wl = warp % ST_GROUP_WARPS;
+  constexpr int RPW = 32 / LPR;                 // rows a warp works on at a time
+  const int sub = lane / LPR, ll = lane % LPR;  // row slot inside the warp, lane inside the row
   constexpr bool GB_REGS = NV <= 6;  // affine parameters held in registers when they fit
   float4 gm[GB_REGS ? NV : 1], bt[GB_REGS ? NV : 1];
   if (GB_REGS) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int v = lane + i * 32;
+      const int v = ll + i * LPR;
       if (v < nv) {
         gm[GB_REGS ? i : 0] = __ldg(reinterpret_cast<const float4*>(gamma) + v);
         bt[GB_REGS ? i : 0] = __ldg(reinterpret_cast<const float4*>(beta) + v);
@@ -306,38 +317,40 @@ ln_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamm
       const float* xs = ring + s * tile_elems;
       const long r0 = tile * g.tile_rows;
       const int rows_here = (int)min((long)g.tile_rows, g.rows - r0);
-      for (int rl = wl; rl < rows_here; rl += ST_GROUP_WARPS) {
-        const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)rl * g.cols);
+      for (int rb = wl * RPW; rb < rows_here; rb += ST_GROUP_WARPS * RPW) {
+        const int rl = rb + sub;
+        const bool rv = rl < rows_here;  // (warp-uniform when LPR == 32)
+        const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)(rv ? rl : rb) * g.cols);
         float4 xv[NV];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int v = lane + i * 32;
+          const int v = ll + i * LPR;
           if (v < nv) {
             xv[i] = xr[v];
             sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
           }
         }
-        const float mean = warp_sum(sum) * inv_cols;
+        const float mean = group_sum<LPR>(sum) * inv_cols;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int v = lane + i * 32;
+          const int v = ll + i * LPR;
           if (v < nv) {
             const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
             q += (a * a + b * b) + (c * c + d * d);
           }
         }
-        const float rstd = rsqrtf(warp_sum(q) * inv_cols + eps);
+        const float rstd = rsqrtf(group_sum<LPR>(q) * inv_cols + eps);
         const long r = r0 + rl;
-        if (lane == 0) {
+        if (ll == 0 && rv) {
           if (mean_out) mean_out[r] = mean;
           if (rstd_out) rstd_out[r] = rstd;
         }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int v = lane + i * 32;
-          if (v < nv) {
+          const int v = ll + i * LPR;
+          if (v < nv && rv) {
             const float4 gmi = GB_REGS ? gm[GB_REGS ? i : 0] : __ldg(reinterpret_cast<const float4*>(gamma) + v);
             const float4 bti = GB_REGS ? bt[GB_REGS ? i : 0] : __ldg(reinterpret_cast<const float4*>(beta) + v);
             float4 o;
@@ -364,7 +377,7 @@ ln_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // Backward.  Stage = x (f32) | dy (bf16 or f32) | dx_in (f32, optional) tiles.  Extra fused output for the
 // caller's NEXT backward step: dx_bf16 = bf16(dx_out * row_scale) and (COLSUM) its column sums, which is the
 // operand / bias gradient of the Linear that produced this residual stream (DropPath scale folded in).
-template <int NV, bool DY_F32, bool COLSUM, int GROUPS>
+template <int NV, bool DY_F32, bool COLSUM, int GROUPS, int LPR>
 __global__ void __launch_bounds__((GROUPS * ST_GROUP_WARPS + 1) * 32, 1)
 ln_bwd_stream_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
@@ -409,6 +422,8 @@ ln_bwd_stream_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     }
   } else {
     const int grp = warp / ST_GROUP_WARPS, wl = warp % ST_GROUP_WARPS;
+    constexpr int RPW = 32 / LPR;                 // rows a warp works on at a time
+    const int sub = lane / LPR, ll = lane % LPR;  // row slot inside the warp, lane inside the row
     float4 dg[NV], db[NV], dc[COLSUM ? NV : 1];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -426,20 +441,22 @@ ln_bwd_stream_kernel(const void* __restrict__ dy, const float* __restrict__ x,
         const int rows_here = (int)min((long)g.tile_rows, g.rows - r0);
         // row statistics of this warp's first row: issued before the wait so the latency hides behind it
         float mean = 0.f, rstd = 0.f, rs = 1.f;
-        if (wl < rows_here) {
-          mean = __ldg(mean_in + r0 + wl);
-          rstd = __ldg(rstd_in + r0 + wl);
-          if (row_scale) rs = __ldg(row_scale + (r0 + wl) / rows_per_scale);
+        if (wl * RPW + sub < rows_here) {
+          mean = __ldg(mean_in + r0 + wl * RPW + sub);
+          rstd = __ldg(rstd_in + r0 + wl * RPW + sub);
+          if (row_scale) rs = __ldg(row_scale + (r0 + wl * RPW + sub) / rows_per_scale);
         }
         mbar_wait(&full[s], ph);
         const uint8_t* st = ring + s * stage_bytes;
-        for (int rl = wl; rl < rows_here; rl += ST_GROUP_WARPS) {
+        for (int rb = wl * RPW; rb < rows_here; rb += ST_GROUP_WARPS * RPW) {
+          const bool rv = rb + sub < rows_here;  // (warp-uniform when LPR == 32)
+          const int rl = rv ? rb + sub : rb;     // idle row slots re-read a valid row and write nothing
           const long r = r0 + rl;
           float mean_n = 0.f, rstd_n = 0.f, rs_n = 1.f;
-          if (rl + ST_GROUP_WARPS < rows_here) {
-            mean_n = __ldg(mean_in + r + ST_GROUP_WARPS);
-            rstd_n = __ldg(rstd_in + r + ST_GROUP_WARPS);
-            if (row_scale) rs_n = __ldg(row_scale + (r + ST_GROUP_WARPS) / rows_per_scale);
+          if (rb + sub + ST_GROUP_WARPS * RPW < rows_here) {
+            mean_n = __ldg(mean_in + r + ST_GROUP_WARPS * RPW);
+            rstd_n = __ldg(rstd_in + r + ST_GROUP_WARPS * RPW);
+            if (row_scale) rs_n = __ldg(row_scale + (r + ST_GROUP_WARPS * RPW) / rows_per_scale);
           }
           const float4* xr = reinterpret_cast<const float4*>(st) + (size_t)rl * nv;
           const uint8_t* dyr = st + tile_elems * 4 + (size_t)rl * g.cols * (DY_F32 ? 4 : 2);
@@ -448,8 +465,8 @@ ln_bwd_stream_kernel(const void* __restrict__ dy, const float* __restrict__ x,
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            const int v = lane + i * 32;
-            if (v < nv) {
+            const int v = ll + i * LPR;
+            if (v < nv && rv) {
               float4 d;
               if (DY_F32) d = reinterpret_cast<const float4*>(dyr)[v];
               else {
@@ -470,13 +487,13 @@ ln_bwd_stream_kernel(const void* __restrict__ dy, const float* __restrict__ x,
               s2 += (t.x * xh[i].x + t.y * xh[i].y) + (t.z * xh[i].z + t.w * xh[i].w);
             }
           }
-          s1 = warp_sum(s1) * inv_cols;
-          s2 = warp_sum(s2) * inv_cols;
+          s1 = group_sum<LPR>(s1) * inv_cols;
+          s2 = group_sum<LPR>(s2) * inv_cols;
           const float4* pin = reinterpret_cast<const float4*>(st + tile_elems * 4 + dy_bytes) + (size_t)rl * nv;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            const int v = lane + i * 32;
-            if (v < nv) {
+            const int v = ll + i * LPR;
+            if (v < nv && rv) {
               float4 t;
               if (KEEP_GD) t = gd[KEEP_GD ? i : 0];
               else {
@@ -520,7 +537,7 @@ ln_bwd_stream_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int v = lane + i * 32;
+      const int v = ll + i * LPR;
       if (v < nv) {
         float* pg = s_part + v * 4;
         float* pb = s_part + g.cols + v * 4;
@@ -605,22 +622,27 @@ extern "C" int vtb_layernorm_fwd(const float* x, const float* gamma, const float
     const size_t smem = stream_geom(rows, cols, 4, 0, G, &sg);
     if (smem) {
       const int grid = (int)(sg.n_tiles < vtb_num_sms() ? sg.n_tiles : vtb_num_sms());
-      const int nvl = (cols / 4 + 31) / 32;
-#define LN_FWD_ST(F32, NVV)                                                                              \
+      const bool narrow = cols <= 128;  // <= 32 float4 per row: four rows per warp, 8 lanes each
+      const int nvl = narrow ? (cols / 4 + 7) / 8 : (cols / 4 + 31) / 32;
+#define LN_FWD_ST(F32, NVV, LPRV)                                                                        \
   do {                                                                                                   \
-    auto kern = ln_fwd_stream_kernel<NVV, F32, G>;                                                       \
+    auto kern = ln_fwd_stream_kernel<NVV, F32, G, LPRV>;                                                 \
     VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));      \
     kern<<<grid, (G * ST_GROUP_WARPS + 1) * 32, smem, stream>>>(x, gamma, beta, eps, sg, y, mean, rstd); \
   } while (0)
-#define LN_FWD_ST_NV(F32)                   \
-  do {                                      \
-    if (nvl <= 1) LN_FWD_ST(F32, 1);        \
-    else if (nvl <= 2) LN_FWD_ST(F32, 2);   \
-    else if (nvl <= 3) LN_FWD_ST(F32, 3);   \
-    else if (nvl <= 4) LN_FWD_ST(F32, 4);   \
-    else if (nvl <= 6) LN_FWD_ST(F32, 6);   \
-    else if (nvl <= 8) LN_FWD_ST(F32, 8);   \
-    else LN_FWD_ST(F32, 12);                \
+#define LN_FWD_ST_NV(F32)                        \
+  do {                                           \
+    if (narrow) {                                \
+      if (nvl <= 1) LN_FWD_ST(F32, 1, 8);        \
+      else if (nvl <= 2) LN_FWD_ST(F32, 2, 8);   \
+      else if (nvl <= 3) LN_FWD_ST(F32, 3, 8);   \
+      else LN_FWD_ST(F32, 4, 8);                 \
+    } else if (nvl <= 2) LN_FWD_ST(F32, 2, 32);  \
+    else if (nvl <= 3) LN_FWD_ST(F32, 3, 32);    \
+    else if (nvl <= 4) LN_FWD_ST(F32, 4, 32);    \
+    else if (nvl <= 6) LN_FWD_ST(F32, 6, 32);    \
+    else if (nvl <= 8) LN_FWD_ST(F32, 8, 32);    \
+    else LN_FWD_ST(F32, 12, 32);                 \
   } while (0)
       if (y_f32) LN_FWD_ST_NV(true); else LN_FWD_ST_NV(false);
 #undef LN_FWD_ST_NV
@@ -665,29 +687,34 @@ extern "C" int vtb_layernorm_bwd(const void* dy, int32_t dy_f32, const float* x,
             "vtb_layernorm_bwd: dx_colsum needs dense 16-byte aligned rows with cols <= 768");
   if (stream_ok) {
     StreamGeom sg;
-    const int nvl = (cols / 4 + 31) / 32;
-    const int groups = (nvl > 4 && dx_colsum) ? 2 : 3;  // == G of the instantiation chosen below
+    const bool narrow = cols <= 128;  // <= 32 float4 per row: four rows per warp, 8 lanes each
+    const int nvl = narrow ? (cols / 4 + 7) / 8 : (cols / 4 + 31) / 32;
+    const int groups = (!narrow && nvl > 4 && dx_colsum) ? 2 : 3;  // == G of the instantiation chosen below
     const size_t smem = stream_geom(rows, cols, 4 + (dy_f32 ? 4 : 2) + (dx_in ? 4 : 0), 3 * (size_t)cols * 4, groups, &sg);
     VTB_CHECK(smem != 0, -1, "vtb_layernorm_bwd: stream geometry");
     const int grid = (int)(sg.n_tiles < vtb_num_sms() ? sg.n_tiles : vtb_num_sms());
     // 3 consumer groups (13 warps, 128 registers) up to 512 columns; 2 groups (9 warps, 168 registers) above, where
     // the per-lane accumulators of dgamma / dbeta / column sums need the room
-#define LN_BWD_ST(F32, CS, NVV)                                                                          \
+#define LN_BWD_ST(F32, CS, NVV, LPRV)                                                                    \
   do {                                                                                                   \
-    constexpr int G = (NVV > 4 && CS) ? 2 : 3;                                                                \
-    auto kern = ln_bwd_stream_kernel<NVV, F32, CS, G>;                                                   \
+    constexpr int G = (LPRV == 32 && NVV > 4 && CS) ? 2 : 3;                                             \
+    auto kern = ln_bwd_stream_kernel<NVV, F32, CS, G, LPRV>;                                             \
     VTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));      \
     kern<<<grid, (G * ST_GROUP_WARPS + 1) * 32, smem, stream>>>(                                         \
         dy, x, gamma, mean, rstd, sg, dx_in, dx_out, reinterpret_cast<bf16*>(dx_bf16), row_scale,        \
         rows_per_scale, dgamma, dbeta, dx_colsum);                                                       \
   } while (0)
-#define LN_BWD_ST_NV(F32, CS)                  \
-  do {                                         \
-    if (nvl <= 1) LN_BWD_ST(F32, CS, 1);       \
-    else if (nvl <= 2) LN_BWD_ST(F32, CS, 2);  \
-    else if (nvl <= 3) LN_BWD_ST(F32, CS, 3);  \
-    else if (nvl <= 4) LN_BWD_ST(F32, CS, 4);  \
-    else LN_BWD_ST(F32, CS, 6);                \
+#define LN_BWD_ST_NV(F32, CS)                        \
+  do {                                               \
+    if (narrow) {                                    \
+      if (nvl <= 1) LN_BWD_ST(F32, CS, 1, 8);        \
+      else if (nvl <= 2) LN_BWD_ST(F32, CS, 2, 8);   \
+      else if (nvl <= 3) LN_BWD_ST(F32, CS, 3, 8);   \
+      else LN_BWD_ST(F32, CS, 4, 8);                 \
+    } else if (nvl <= 2) LN_BWD_ST(F32, CS, 2, 32);  \
+    else if (nvl <= 3) LN_BWD_ST(F32, CS, 3, 32);    \
+    else if (nvl <= 4) LN_BWD_ST(F32, CS, 4, 32);    \
+    else LN_BWD_ST(F32, CS, 6, 32);                  \
   } while (0)
     if (dy_f32) { if (dx_colsum) LN_BWD_ST_NV(true, true); else LN_BWD_ST_NV(true, false); }
     else        { if (dx_colsum) LN_BWD_ST_NV(false, true); else LN_BWD_ST_NV(false, false); }
