@@ -70,6 +70,11 @@ typedef struct {
   int32_t splits;                     /* split-K factor; 0 = auto; >1 requires accumulate=1 */
   int32_t accumulate;
   float alpha;
+  /* optional, a_mn_major=1 only (weight gradients dW = dy^T x): a_colsum[m] += sum_k A(m, k), i.e. the column sums
+   * of the dy operand = the bias gradient of the same Linear (layer.py:191 / vit.py:30 ...), accumulated by the
+   * otherwise idle epilogue warps from the operand tiles already staged in shared memory, so the bias gradient
+   * costs no extra pass over dy.  f32 [M], atomicAdd; needs EPI_NONE without resid / out2. */
+  float* a_colsum;
 } vtb_gemm_params;
 
 int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream);

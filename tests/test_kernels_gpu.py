@@ -165,6 +165,21 @@ def test_gemm_splitk_accumulate_and_group_rows(ops, gemm_mode):
     assert rel(got2, 2 * want) < 1e-5
 
 
+@pytest.mark.parametrize("T,N,K", [(1000, 384, 96), (50432 // 8, 3072, 768), (197 * 3, 200, 64)])
+def test_gemm_wgrad_with_fused_bias_gradient(ops, gemm_mode, T, N, K):
+    """dW = g^T x and db = column sums of g from ONE launch (a_colsum: the epilogue warps add up the A tiles in smem)."""
+    gen = torch.Generator(device="cuda").manual_seed(T + N)
+    g = bf(torch.randn(T, N, device="cuda", generator=gen))
+    x = bf(torch.randn(T, K, device="cuda", generator=gen))
+    db = torch.zeros(N, device="cuda")
+    dw = ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True, a_colsum=db)
+    assert rel(dw, g.float().t() @ x.float()) < 1e-5
+    assert rel(db, g.float().sum(0)) < 1e-5
+    # accumulates into the caller's buffer
+    ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True, a_colsum=db)
+    assert rel(db, 2 * g.float().sum(0)) < 1e-5
+
+
 def test_gemm_unaligned_output_falls_back_to_direct_path(ops, gemm_mode):
     """N=10 / N=50 heads: rows are not 16-byte multiples -> per-thread epilogue instead of TMA stores."""
     g = torch.Generator(device="cuda").manual_seed(8)

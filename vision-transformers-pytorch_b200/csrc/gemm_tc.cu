@@ -59,6 +59,7 @@ struct EpiParams {
   float alpha;
   int vec;  // all epilogue pointers / leading dims allow 16-byte vector access (direct path)
   int tma;  // 1: staged TMA-store epilogue (tensor maps valid)
+  float* a_colsum;  // MN-major A only: += column sums of the A operand (bias gradient riding on a wgrad)
 };
 
 template <int BN, int CL>
@@ -290,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], (A_MN && epi.a_colsum) ? 9 : 1);  // + the 8 epilogue warps that read the A tiles
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -483,10 +484,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     int as = 0;
     uint32_t aphase = 0;
+    // Bias gradient riding on a weight gradient (A = dy, MN-major): while the tensor cores work through a tile's
+    // k-blocks the epilogue warps have nothing to do, so they add up the columns of the A tiles sitting in the ring
+    // (A stage = two boxes of 64 k-rows x 64 m, 128B-swizzled: thread = one 16-byte chunk column of 4 k-rows) and hand
+    // each stage back themselves (its `empty` barrier counts 1 commit + 8 warps).  Only CTAs on the first n-tile add.
+    int rd_stage = 0;
+    uint32_t rd_phase = 0;
+    auto a_colsum_phase = [&](int tile) {
+      if (!(A_MN && epi.a_colsum)) return;
+      const int ks = tile % splits;
+      const int mn = tile / splits;
+      const bool mine = (mn % n_tiles) == 0;
+      const int m_blk = (mn / n_tiles) * CL + rank;
+      const int kb0 = ks * kb_per_split, kb1 = min(k_blocks, kb0 + kb_per_split);
+      const int t = threadIdx.x - 128;                  // 0..255
+      const int cc = t & 7, box = (t >> 3) & 1, rg = t >> 4;
+      const uint32_t off = (uint32_t)box * (BK * 128) + (uint32_t)rg * 128u + (uint32_t)((cc ^ (rg & 7)) << 4);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[rd_stage], rd_phase);
+        if (mine) {
+          const uint8_t* a = sA + rd_stage * A_STAGE_BYTES + off;
+#pragma unroll
+          for (int r4 = 0; r4 < 4; ++r4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(a + r4 * (16 * 128));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = unpack_bf16(w[q]);
+              acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[rd_stage]);
+        if (++rd_stage == C::STAGES) { rd_stage = 0; rd_phase ^= 1; }
+      }
+      if (mine) {  // 16 row groups -> one value per column of the tile (scratch: the unused aux staging) -> global
+        float* s_col = reinterpret_cast<float*>(sAux);
+        if (t < BM) s_col[t] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&s_col[box * 64 + cc * 8 + j], acc[j]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (t < BM && m_blk * BM + t < epi.M) atomicAdd(epi.a_colsum + m_blk * BM + t, s_col[t]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    };
     if (!epi.tma) {
       // direct path (unaligned outputs): per-thread row stores; the two warps of a lane quarter alternate chunks
       const int ehalf = (warp - 4) >> 2;
       for (int tile = cta; tile < total_tiles; tile += ncl) {
+        a_colsum_phase(tile);
         const int mn = tile / splits;
         const int n_blk = mn % n_tiles;
         const int m_blk = (mn / n_tiles) * CL + rank;
@@ -534,6 +585,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         constexpr int SUBC = 2 * CW;
         constexpr int NSUB = BN / SUBC;
         for (int tile = cta; tile < total_tiles; tile += ncl) {
+          a_colsum_phase(tile);
           const int mn = tile / splits;
           const int n_blk = mn % n_tiles;
           const int m_blk = (mn / n_tiles) * CL + rank;
@@ -752,6 +804,8 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   VTB_CHECK(!p->resid || p->out_f32, -1, "vtb_gemm_bf16: resid needs an f32 output");
   VTB_CHECK(p->epilogue != VTB_EPI_SILU_GRAD || !p->out_f32, -1, "vtb_gemm_bf16: SILU_GRAD writes bf16");
   VTB_CHECK(!p->row_scale || p->rows_per_scale > 0, -1, "vtb_gemm_bf16: rows_per_scale");
+  VTB_CHECK(!p->a_colsum || (p->a_mn_major && p->epilogue == VTB_EPI_NONE && !p->resid && !p->out2), -1,
+            "vtb_gemm_bf16: a_colsum needs an MN-major A operand and a plain epilogue");
 
   EpiParams e;
   e.M = p->M; e.N = p->N;
@@ -764,6 +818,7 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   e.epilogue = p->epilogue;
   e.accumulate = p->accumulate;
   e.alpha = p->alpha;
+  e.a_colsum = p->a_colsum;
   {  // 16-byte vector epilogue only when every touched row start is 16-byte aligned; scalar path otherwise
     const int oalign = p->out_f32 ? 4 : 8;
     bool v = (p->ldo % oalign == 0) && (((uintptr_t)p->out & 15) == 0);
@@ -790,6 +845,7 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   // CTA pairs (256 x bn tiles, cta_group::2) whenever there are at least two row tiles and the pairs can fill the
   // machine; an MN-major B tile of 64 columns is one TMA box and cannot be halved
   bool pair = g_use_clusters && m_tiles >= 2 && !(p->b_mn_major && bn < 128);
+  if (p->a_colsum) pair = false;  // the readers of the A tiles wait on their own CTA's `full` barrier (leader-only in pairs)
   const long units = (long)(pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;  // work items before split-K
   const int slots = pair ? g_num_sms / 2 : g_num_sms;                        // concurrently resident work items
   int splits = p->splits;

@@ -22,9 +22,13 @@ _fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = torch.amp.custom_bwd(device_type="cuda")
 
 
-def _wgrad(g, x):
-    """dW[N,K] = g[T,N]^T x[T,K]  (both operands MN-major views of the forward buffers; split-K)."""
-    return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True)
+def _wgrad(g, x, bias_grad=False):
+    """dW[N,K] = g[T,N]^T x[T,K]  (both operands MN-major views of the forward buffers; split-K).  With bias_grad the
+    same launch also returns db[N] = column sums of g, taken from the operand tiles while they sit in shared memory."""
+    if not bias_grad:
+        return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True)
+    db = ops.zeros(g.shape[1], F32, g.device)
+    return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True, a_colsum=db), db
 
 
 def _dgrad(g, w_bf16, **kw):
@@ -85,7 +89,7 @@ def _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up):
         dx, _, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2)
         return dx, dg, dbeta
     scale, rps = up
-    cs = torch.zeros(x2.shape[1], dtype=F32, device=x2.device)
+    cs = ops.zeros(x2.shape[1], F32, x2.device)
     dx, g, dg, dbeta = ops.layernorm_bwd(dy, x2, ln_w, mean, rstd, dx_in=d2, want_bf16=True, row_scale=scale,
                                          rows_per_scale=rps if scale is not None else 0, colsum_out=cs)
     _slots.hint = (dx, dx._version, g, cs, scale, rps)
@@ -134,8 +138,7 @@ class FFNBranchFn(Function):
         g, db2 = _grad_operand(d2, dp_scale, rps)
         dw2 = _wgrad(g, h)
         du = _dgrad(g, w2b, epilogue=_l.EPI_SILU_GRAD, aux=u)
-        db1 = ops.colsum(du)
-        dw1 = _wgrad(du, y)
+        dw1, db1 = _wgrad(du, y, bias_grad=True)
         dy = _dgrad(du, w1b)
         dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
         return dx.view(dout.shape), None, None, None, dg, dbeta, dw1, db1, dw2, db2
@@ -180,7 +183,7 @@ class AttnBranchFn(Function):
         dw_o = _wgrad(g, o)
         do = _dgrad(g, wob)
         dqkv = torch.empty_like(qkv)
-        drel = torch.zeros_like(spec.rel_bias) if spec.rel_bias is not None else None
+        drel = ops.zeros(spec.rel_bias.shape, F32, spec.rel_bias.device) if spec.rel_bias is not None else None
         if spec.mode == _l.ATTN_HALO and spec.nq > 64:
             # large halo blocks: key/value tokens shared by neighbouring blocks -> fp32 atomics, then one cast
             # (blocks of <= 64 tokens take the key-centric kernel below, which writes bf16 without atomics)
@@ -191,8 +194,10 @@ class AttnBranchFn(Function):
         else:
             ops.attention_bwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do,
                               dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:], drel)
-        db_qkv = ops.colsum(dqkv) if has_bqkv else None
-        dw_qkv = _wgrad(dqkv, y)
+        if has_bqkv:
+            dw_qkv, db_qkv = _wgrad(dqkv, y, bias_grad=True)
+        else:
+            dw_qkv, db_qkv = _wgrad(dqkv, y), None
         dy = _dgrad(dqkv, wqb)
         dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
         return (dx.view(dout.shape), None, None, None, None, None, None, dg, dbeta, dw_qkv, db_qkv, dw_o,

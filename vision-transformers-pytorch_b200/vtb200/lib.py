@@ -36,6 +36,7 @@ class GemmParams(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_int32),
         ("epilogue", C.c_int32), ("splits", C.c_int32), ("accumulate", C.c_int32),
         ("alpha", C.c_float),
+        ("a_colsum", C.c_void_p),
     ]
 
 

@@ -6,6 +6,7 @@ byte moved on the hot path happens inside libvtb200.so.  LAUNCHES counts the lib
 """
 import ctypes as C
 import math
+import threading
 
 import torch
 
@@ -52,6 +53,43 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+class _ZeroArena(threading.local):
+    """Zero-initialised outputs (split-K weight gradients, bias / LayerNorm-parameter / table gradients: ~150 per ViT-B
+    step, ~330 per Swin-S step) are carved out of 64 MiB chunks that are cleared with ONE memset each instead of one
+    fill kernel per tensor.  A chunk stays alive for as long as any tensor carved from it does."""
+    CHUNK = 64 << 20
+    buf = None
+    off = 0
+    capturing = False  # a chunk allocated while a CUDA graph is being captured belongs to that graph's pool
+
+    def take(self, shape, dtype, device):
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        if nbytes == 0 or nbytes > self.CHUNK // 4:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        need = (nbytes + 255) // 256 * 256
+        cap = torch.cuda.is_current_stream_capturing()
+        if (self.buf is None or cap != self.capturing or self.buf.device != torch.device(device)
+                or self.off + need > self.CHUNK):
+            self.buf = torch.zeros(self.CHUNK, dtype=torch.uint8, device=device)
+            self.off, self.capturing = 0, cap
+        t = self.buf[self.off:self.off + nbytes].view(dtype).view(shape)
+        self.off += need
+        return t
+
+
+_arena = _ZeroArena()
+
+
+def zeros(shape, dtype=F32, device="cuda"):
+    """torch.zeros for the many small accumulate-into outputs of a step (see _ZeroArena)."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    return _arena.take(tuple(shape), dtype, device)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -73,7 +111,7 @@ def _chk2d(t, dtype, name):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, resid=None,
          row_scale=None, rows_per_scale=0, epilogue=_l.EPI_NONE, aux=None, out2=None, accumulate=False,
-         splits=0, alpha=1.0):
+         splits=0, alpha=1.0, a_colsum=None):
     """C[M,N] = alpha * sum_k A(m,k) B(n,k) with the fused epilogue of vtb_gemm_bf16.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] or [K,N] (b_mn=True); both bf16 row-major
@@ -88,7 +126,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
         raise ValueError(f"vtb200.gemm: K mismatch {K} vs {Kb}")
     rows_out = M
     if out is None:
-        out = (torch.zeros if accumulate else torch.empty)((M, N), dtype=out_dtype, device=a.device)
+        out = zeros((M, N), out_dtype, a.device) if accumulate else torch.empty((M, N), dtype=out_dtype, device=a.device)
     _chk2d(out, out.dtype, "gemm(out)")
     if out.shape[0] < rows_out or out.shape[1] != N:
         raise ValueError(f"vtb200.gemm: out shape {tuple(out.shape)} vs ({rows_out},{N})")
@@ -122,6 +160,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
         p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
     p.epilogue, p.splits, p.accumulate = epilogue, splits, int(accumulate)
     p.alpha = alpha
+    if a_colsum is not None:  # column sums of the MN-major A operand (the bias gradient that goes with a wgrad)
+        if not a_mn or a_colsum.dtype != F32 or a_colsum.numel() != M or not a_colsum.is_contiguous():
+            raise ValueError("vtb200.gemm: a_colsum needs a_mn=True and a contiguous f32 [M] accumulator")
+        p.a_colsum = a_colsum.data_ptr()
     kind = ("wgrad" if a_mn else ("dgrad" if b_mn else "fwd"))
     with _prof(f"gemm_{kind}[{M}x{N}x{K}]", 2.0 * M * N * K):
         _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
@@ -168,9 +210,9 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_in=None, dx_out=None, patchify
         dx_out = torch.empty_like(x)
     dxb = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
     if dgamma is None:
-        dgamma = torch.zeros(cols, dtype=F32, device=x.device)
+        dgamma = zeros(cols, F32, x.device)
     if dbeta is None:
-        dbeta = torch.zeros(cols, dtype=F32, device=x.device)
+        dbeta = zeros(cols, F32, x.device)
     with _prof("layernorm_bwd"):
         _l.check(lib.vtb_layernorm_bwd(_p(dy), int(dy.dtype == F32), _p(x), _p(gamma), _p(mean), _p(rstd),
                                        rows, cols, s, H, W, _p(dx_in), _p(dx_out), _p(dxb), _p(row_scale),
@@ -334,7 +376,7 @@ def scale_cast_colsum_bf16(src, row_scale=None, rows_per_scale=0):
     cols = src.shape[-1]
     rows = src.numel() // cols
     dst = torch.empty((rows, cols), dtype=BF16, device=src.device)
-    cs = torch.zeros(cols, dtype=F32, device=src.device)
+    cs = zeros(cols, F32, src.device)
     with _prof("scale_cast_colsum_bf16"):
         _l.check(lib.vtb_scale_cast_colsum_bf16(_p(src), _p(row_scale), rows_per_scale, rows, cols, _p(dst), _p(cs),
                                                 _stream()), lib)
@@ -347,7 +389,7 @@ def colsum(x, out=None):
     _chk2d(x, BF16, "colsum")
     M, N = x.shape
     if out is None:
-        out = torch.zeros(N, dtype=F32, device=x.device)
+        out = zeros(N, F32, x.device)
     with _prof("colsum_bf16"):
         _l.check(lib.vtb_colsum_bf16(_p(x), M, N, x.stride(0), _p(out), _stream()), lib)
     _count()
