@@ -23,11 +23,17 @@ _bwd = torch.amp.custom_bwd(device_type="cuda")
 
 
 def _wgrad(g, x, bias_grad=False):
-    """dW[N,K] = g[T,N]^T x[T,K]  (both operands MN-major views of the forward buffers; split-K).  With bias_grad the
-    same launch also returns db[N] = column sums of g, taken from the operand tiles while they sit in shared memory."""
+    """dW[N,K] = g[T,N]^T x[T,K]  (both operands MN-major views of the forward buffers; split-K).  With bias_grad also
+    returns db[N] = column sums of g.  Where the weight gradient is bandwidth-bound (narrow layers: N K / (N + K) below
+    ~450 flop/byte, measured: Swin stages 1-3 yes, ViT-B no) the sums ride on the same launch — the idle epilogue warps
+    add up the operand tiles while they sit in shared memory; on tensor-bound shapes that slows the GEMM by more than
+    the separate pass costs, so the bias gradient takes its own column-sum kernel there."""
     if not bias_grad:
         return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True)
-    db = ops.zeros(g.shape[1], F32, g.device)
+    n, k = g.shape[1], x.shape[1]
+    if n * k >= 450 * (n + k) or g.stride(0) % 8 or x.stride(0) % 8:
+        return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True), ops.colsum(g)
+    db = ops.zeros(n, F32, g.device)
     return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True, a_colsum=db), db
 
 
