@@ -358,12 +358,13 @@ def main():
     if use_graph:
         launches = launches_per_step * args.steps
     prof, ops.PROFILE = ops.PROFILE, None
-    gemm = [(n, f, a.elapsed_time(b)) for n, f, a, b in prof if n.startswith("gemm_")]
-    gemm_ms = sum(t for _, _, t in gemm)
-    gemm_flops = sum(f for _, f, _ in gemm)
+    gemm = [(n, f, a.elapsed_time(b), nb) for n, f, a, b, nb in prof if n.startswith("gemm_")]
+    gemm_ms = sum(t for _, _, t, _ in gemm)
+    gemm_flops = sum(f for _, f, _, _ in gemm)
+    gemm_bytes = sum(nb for _, _, _, nb in gemm)
     if rank == 0:
         agg = {}
-        for n, f, a, b in prof:
+        for n, f, a, b, _nb in prof:
             t = a.elapsed_time(b)
             d = agg.setdefault(n, [0, 0.0, 0.0])
             d[0] += 1; d[1] += t; d[2] += f
@@ -382,8 +383,18 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+    achieved_gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0
+    # the GEMM launches of a step are bound by whichever resource they use the larger fraction of: the tensor pipe
+    # (ViT-B: K, N >= 768) or HBM (Swin / PVT / Halo: narrow layers, the fp32 residual stream and bf16 activations dominate)
+    hbm_bound = achieved_gbs / peak_hbm > achieved / peak_tf
+    roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": "gemm_tc_kernel (tcgen05)",
+                "achieved": achieved_gbs if hbm_bound else achieved, "peak": peak_hbm if hbm_bound else peak_tf,
+                "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                "frac": (achieved_gbs / peak_hbm) if hbm_bound else (achieved / peak_tf),
+                "tensor": {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf},
+                "hbm": {"achieved": achieved_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": achieved_gbs / peak_hbm,
+                        "algorithmic_bytes_per_launch": (gemm_bytes / len(gemm)) if gemm else None},
+                "traffic": traffic,
                 "traffic_unit": "bytes per GEMM launch (ncu dram__bytes_read+write, profiles/r01_gemm_traffic_*.json)",
                 "flop_per_launch": (gemm_flops / len(gemm)) if gemm else None, "peak_source": peak_src,
                 "launches_per_step": len(gemm), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,

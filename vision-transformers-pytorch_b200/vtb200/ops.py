@@ -19,10 +19,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ("name", "flops", "e0")
+    __slots__ = ("name", "flops", "nbytes", "e0")
 
-    def __init__(self, name, flops=0.0):
-        self.name, self.flops = name, flops
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
 
     def __enter__(self):
         self.e0 = torch.cuda.Event(enable_timing=True)
@@ -31,7 +31,7 @@ class _Prof:
     def __exit__(self, *exc):
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        PROFILE.append((self.name, self.flops, self.e0, e1))
+        PROFILE.append((self.name, self.flops, self.e0, e1, self.nbytes))
         return False
 
 
@@ -46,8 +46,9 @@ class _NoProf:
 _NOPROF = _NoProf()
 
 
-def _prof(name, flops=0.0):
-    return _NOPROF if PROFILE is None else _Prof(name, flops)
+def _prof(name, flops=0.0, nbytes=0.0):
+    """flops / nbytes: ALGORITHMIC work of the call (operands and outputs touched once), for the live roofline pass."""
+    return _NOPROF if PROFILE is None else _Prof(name, flops, nbytes)
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -165,7 +166,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
             raise ValueError("vtb200.gemm: a_colsum needs a_mn=True and a contiguous f32 [M] accumulator")
         p.a_colsum = a_colsum.data_ptr()
     kind = ("wgrad" if a_mn else ("dgrad" if b_mn else "fwd"))
-    with _prof(f"gemm_{kind}[{M}x{N}x{K}]", 2.0 * M * N * K):
+    osz = 4 if out.dtype == F32 else 2
+    nbytes = 2.0 * K * (M + N) + float(M) * N * (osz * (2 if accumulate else 1) + (2 if out2 is not None else 0)
+                                                  + (4 if resid is not None else 0) + (2 if aux is not None else 0))
+    with _prof(f"gemm_{kind}[{M}x{N}x{K}]", 2.0 * M * N * K, nbytes):
         _l.check(lib.vtb_gemm_bf16(C.byref(p), _stream()), lib)
     _count()
     return out
