@@ -29,7 +29,10 @@ int vtb_init(void);
  * TMA-multicast the shared B tile into both CTAs' shared memory.  Default 0: measured neutral on B200.
  * "attn_tc" (0/1, default 1): use the tcgen05/TMEM attention kernels where they apply (global attention,
  * dh = 64, <= 256 keys); 0 forces the mma.sync kernels (A/B measurements, cross-checks).
- * "attn_wp" (0/1, default 1): one warp per (window, head) problem when nq, nkv <= 64; 0 = one CTA per problem. */
+ * "attn_wp" (0/1, default 1): one warp per (window, head) problem when nq, nkv <= 64; 0 = one CTA per problem.
+ * "attn_wt" (0/1, default 1): tcgen05 window kernels (two windows per 128-row tile) for WINDOW problems with dh = 32 and
+ * <= 64 tokens per window; 0 forces the mma.sync kernels (A/B measurements, cross-checks).
+ * "ln_stream" (0/1, default 1): streaming (bulk-copy staged) LayerNorm kernels; 0 = register-resident kernels. */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------
