@@ -254,7 +254,7 @@ def main():
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
                                                             gradient_as_bucket_view=True, bucket_cap_mb=64)
         else:
-            reducer = vd.FlatGradReducer(params)
+            reducer = vd.FlatGradReducer(params).attach()  # .grad = views into the NCCL buckets
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
     if is_dino:
@@ -281,8 +281,11 @@ def main():
         return total / n
 
     def fwd_bwd(x, y):
-        for p in params:
-            p.grad = None
+        if reducer is not None and reducer.attached:
+            reducer.zero()  # one memset per flat bucket; backward accumulates into the bucket views
+        else:
+            for p in params:
+                p.grad = None
         if is_dino:
             with torch.no_grad():
                 t_out = teacher(x[:2])

@@ -34,6 +34,17 @@ def _worker(rank, world, port, q):
     want = sum(gathered) / world
     got = torch.cat([p.grad.flatten() for p in model.parameters()])
     ok = torch.allclose(got, want, atol=1e-6)
+    # attached mode: .grad are views into the flat buckets, backward accumulates into them, reduce() is in place
+    model2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    model2.load_state_dict(model.state_dict())
+    red2 = vd.FlatGradReducer(model2.parameters(), bucket_mb=1).attach()
+    for _ in range(2):  # second round checks zero() really clears the views
+        red2.zero()
+        model2(x).sum().backward()
+        red2.reduce()
+    got2 = torch.cat([p.grad.flatten() for p in model2.parameters()])
+    ok = ok and torch.allclose(got2, want, atol=1e-6)
+    ok = ok and all(p.grad.data_ptr() >= red2._flat[0].data_ptr() for p in red2.buckets[0])
     mx = vd.max_over_ranks(rank + 10, "cpu")
     sm = vd.sum_over_ranks(rank + 1, "cpu")
     q.put((rank, bool(ok), mx, sm, vd.per_rank_batch(256, world)))
