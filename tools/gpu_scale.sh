@@ -3,6 +3,6 @@
 N=$1
 mkdir -p gpurun_out
 for wl in vit_b16 swin_s; do
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 10 --warmup 3 --workload $wl --no-cpu-baseline --no-e2e > gpurun_out/scale_${wl}_n$N.log 2>&1
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 10 --warmup 3 --workload $wl --no-cpu-baseline --no-e2e > gpurun_out/scale_${wl}_n$N.log 2>&1
 echo "$wl n=$N exit=$?"; grep '^{' gpurun_out/scale_${wl}_n$N.log | tail -1 | cut -c1-160
 done
