@@ -67,12 +67,16 @@ struct Cfg {
   // CL = 2: CTA pair (cta_group::2), each CTA stages its 128 rows of A and HALF of the B tile
   static constexpr int B_STAGE_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // epilogue staging: 2 output buffers + 3 aux buffers (second output, or prefetched residual / pre-activation)
-  static constexpr int STAGING_BYTES = (2 + 3) * EPI_BUF_BYTES;
-  static constexpr int RING_BUDGET = 227 * 1024 - STAGING_BYTES - 1024 /*align*/ - 512 /*barriers*/;
-  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 6 ? 6 : (RING_BUDGET / STAGE_BYTES);  // 3/4/6 (CL=1), 4/6/6 (CL=2)
+  static constexpr int BAR_BYTES = 1536;  // mbarriers (< 1 KB) + 512 B scratch for the a_colsum reduction
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - BAR_BYTES;
+  static constexpr int clamp6(int v) { return v > 6 ? 6 : v; }
+  // epilogue staging: 2 (or 3) output buffers + 3 aux buffers (second output, or prefetched residual / pre-activation);
+  // the third output buffer is taken only where it does not cost a ring stage
+  static constexpr int STAGES = clamp6((BUDGET - (2 + 3) * EPI_BUF_BYTES) / STAGE_BYTES);  // 3/4/6 (CL=1), 4/6/6 (CL=2)
+  static constexpr int N_OUT = (clamp6((BUDGET - (3 + 3) * EPI_BUF_BYTES) / STAGE_BYTES) == STAGES) ? 3 : 2;
+  static constexpr int STAGING_BYTES = (N_OUT + 3) * EPI_BUF_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 512 / 256 / 128
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + BAR_BYTES;
 };
 
 // One 32-column chunk of one accumulator row -> global memory with the fused epilogue.
@@ -270,16 +274,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
   uint8_t* sOut = smem + C::STAGES * C::STAGE_BYTES;          // [2][EPI_BUF_BYTES]
-  uint8_t* sAux = sOut + 2 * EPI_BUF_BYTES;                   // [N_AUX][EPI_BUF_BYTES]
+  uint8_t* sAux = sOut + C::N_OUT * EPI_BUF_BYTES;            // [N_AUX][EPI_BUF_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
   uint64_t* aux_full = bars + 2 * C::STAGES + 4;              // [4 lane quarters][N_AUX]
-  uint64_t* staged_bar = aux_full + 4 * N_AUX;                // [4 quarters][2]: sub-tile written + fenced (2 warps)
-  uint64_t* free_bar = staged_bar + 8;                        // [4 quarters][2]: TMA has read the staging buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 8);
+  constexpr int MAXOB = 8;                                    // output staging buffers per quarter (<= N_OUT + N_AUX)
+  uint64_t* staged_bar = aux_full + 4 * N_AUX;                // [4 quarters][MAXOB]: sub-tile written + fenced (2 warps)
+  uint64_t* free_bar = staged_bar + 4 * MAXOB;                // [4 quarters][MAXOB]: TMA has read the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 4 * MAXOB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&tmem_empty[i], 8 * CL);  // every epilogue warp of the pair arrives on the leader's barrier
     }
     for (int i = 0; i < 4 * N_AUX; ++i) mbar_init(&aux_full[i], 1);
-    for (int i = 0; i < 8; ++i) { mbar_init(&staged_bar[i], 2); mbar_init(&free_bar[i], 1); }
+    for (int i = 0; i < 4 * 8; ++i) { mbar_init(&staged_bar[i], 2); mbar_init(&free_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -446,18 +451,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_aux);
         for (long q = 0; q < N_AUX && q < total_q; ++q) issue_aux(q);
       }
+      // output staging ring of this launch: the aux buffers join it when the epilogue neither prefetches through
+      // them nor stages a second output (sOut and sAux are contiguous)
+      const int nob = (aux_in || dual) ? C::N_OUT : C::N_OUT + N_AUX;
+      long qb = 0;       // q % nob, q / nob kept incrementally
+      uint32_t qph = 0;
       for (long q = 0; q < total_q; ++q) {
-        mbar_wait(&staged_bar[k * 2 + (q & 1)], (uint32_t)((q >> 1) & 1));
-        if (q >= 1) {
-          // the store of sub-tile q-1 (issued a whole sub-tile ago) has been read out of its staging buffer: hand the
-          // buffer back BEFORE the slow bulk-tensor issue below, the math warps want it for sub-tile q+1
+        mbar_wait(&staged_bar[k * MAXOB + qb], qph);
+        if (nob == 2 && q >= 1) {
+          // two buffers: the math warps want the buffer of sub-tile q-1 back for q+1 — hand it over BEFORE the slow
+          // bulk-tensor issue below (its store was issued a whole sub-tile ago and has been read out by now)
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(&free_bar[k * 2 + ((q - 1) & 1)]);
+          mbar_arrive(&free_bar[k * MAXOB + (int)((q - 1) & 1)]);
         }
         int m0, n0;
         q_coords(q, m0, n0);
         if (n0 < epi.N) {
-          const uint32_t so = smem_u32(sOut + (q & 1) * EPI_BUF_BYTES) + qoff;
+          const uint32_t so = smem_u32(sOut + qb * EPI_BUF_BYTES) + qoff;
           if (epi.accumulate) {
             asm volatile(
                 "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_out),
@@ -476,6 +486,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         // both warps of the quarter are past their reads of aux buffer q % N_AUX: refill it for sub-tile q + N_AUX
         if (aux_in && q + N_AUX < total_q) issue_aux(q + N_AUX);
+        if (nob > 2 && q >= 1) {
+          // three or more buffers: sub-tile q-1's buffer is not needed again before q+2, so its read-out may finish
+          // behind the issue of store q
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(&free_bar[k * MAXOB + (qb == 0 ? nob - 1 : qb - 1)]);
+        }
+        if (++qb == nob) { qb = 0; qph ^= 1; }
       }
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -522,8 +539,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) mbar_arrive(&empty_bar[rd_stage]);
         if (++rd_stage == C::STAGES) { rd_stage = 0; rd_phase ^= 1; }
       }
-      if (mine) {  // 16 row groups -> one value per column of the tile (scratch: the unused aux staging) -> global
-        float* s_col = reinterpret_cast<float*>(sAux);
+      if (mine) {  // 16 row groups -> one value per column of the tile (scratch behind the mbarriers) -> global
+        float* s_col = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);
         if (t < BM) s_col[t] = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
@@ -571,8 +588,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const bool dual = epi.epilogue == VTB_EPI_SILU_DUAL;
       const bool aux_in = (epi.resid != nullptr) || (epi.epilogue == VTB_EPI_SILU_GRAD);
       uint64_t* aux_q = aux_full + ew * N_AUX;
-      uint64_t* staged_q = staged_bar + ew * 2;
-      uint64_t* free_q = free_bar + ew * 2;
+      uint64_t* staged_q = staged_bar + ew * MAXOB;
+      uint64_t* free_q = free_bar + ew * MAXOB;
+      const int nob = (aux_in || dual) ? C::N_OUT : C::N_OUT + N_AUX;  // output staging ring (see the helper warp)
+      int qb = 0;        // q % nob, (q / nob) & 1 kept incrementally
+      uint32_t qph = 0;
       const int ehalf = (warp - 4) >> 2;           // which half of the sub-tile's columns this warp owns
       const int row = ew * 32 + lane;              // row inside the tile == TMEM lane
       const uint32_t swz = (uint32_t)(row & 7);
@@ -605,7 +625,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int n0 = n_blk * BN + sidx * SUBC;
             const bool live = n0 < epi.N;            // CTA-uniform
             const bool last = (sidx == NSUB - 1);
-            uint8_t* ob = sOut + (q & 1) * EPI_BUF_BYTES + row * 128;
+            uint8_t* ob = sOut + qb * EPI_BUF_BYTES + row * 128;
             uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES + row * 128;
             const float b_nxt = last ? 0.f : bias_at(sidx + 1);
             TRACE_T(0);
@@ -621,8 +641,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (lane == 0) { if (CL == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0); }
             }
             if (aux_in) mbar_wait(&aux_q[q % N_AUX], (uint32_t)((q / N_AUX) & 1));
-            // staging buffer (q & 1) was handed to TMA at iteration q-2: wait until it has been read
-            mbar_wait(&free_q[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));
+            // staging buffer qb was handed to TMA `nob` sub-tiles ago: wait until it has been read out
+            mbar_wait(&free_q[qb], qph ^ 1);
             TRACE_T(4);
             if (live) staged_row<CW>(epi, cur, b_cur, rs, ob, ab, cb, swz, dual, CW == 16);
             b_cur = b_nxt;
@@ -630,7 +650,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
             TRACE_T(6);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&staged_q[q & 1]);
+            if (lane == 0) mbar_arrive(&staged_q[qb]);
+            if (++qb == nob) { qb = 0; qph ^= 1; }
             TRACE_T(7);
 #ifdef VTB_GEMM_TRACE
             if (lane == 0 && blockIdx.x == 7) {
