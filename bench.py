@@ -239,7 +239,8 @@ def main():
     params = [p for p in model.parameters() if p.requires_grad]
     is_dino = args.workload == "dino_deit_s"
     if is_dino:
-        args.no_graph = True  # list inputs + EMA + centre all-reduce: issued eagerly
+        if world > 1:
+            args.no_graph = True  # the centre all-reduce sits in the middle of the step: issued eagerly with the rest
         teacher = build_model(args.workload, drop_path=0.0).to(dev)
         teacher.load_state_dict(model.state_dict())
         for p in teacher.parameters():
@@ -277,7 +278,7 @@ def main():
         bc = teacher_out.sum(0, keepdim=True)
         if world > 1:
             dist.all_reduce(bc)
-        center = center * 0.9 + bc / (teacher_out.shape[0] * world) * 0.1
+        center.mul_(0.9).add_(bc, alpha=0.1 / (teacher_out.shape[0] * world))  # in place: the buffer is part of the graph
         return total / n
 
     def fwd_bwd(x, y):
@@ -304,8 +305,12 @@ def main():
     def step(x, y):
         if graphed is not None:
             if x is not x_dev:
-                x_dev.copy_(x, non_blocking=True)
-                y_dev.copy_(y, non_blocking=True)
+                if isinstance(x_dev, (list, tuple)):
+                    for dst, src in zip(x_dev, x):
+                        dst.copy_(src, non_blocking=True)
+                else:
+                    x_dev.copy_(x, non_blocking=True)
+                    y_dev.copy_(y, non_blocking=True)
             loss = graphed.replay()
         else:
             loss = fwd_bwd(x, y)
@@ -322,7 +327,13 @@ def main():
     if use_graph:
         from vtb200.graph import GraphedStep
 
-        graphed = GraphedStep(fwd_bwd, (x_dev, y_dev), warmup=2)
+        try:
+            graphed = GraphedStep(fwd_bwd, (x_dev, y_dev), warmup=2)
+        except Exception as exc:  # noqa: BLE001  (a step that cannot be captured is issued eagerly and says so)
+            if not is_dino:
+                raise
+            print(f"bench.py: CUDA-graph capture of the DINO step failed ({exc!r}); issuing eagerly", file=sys.stderr)
+            graphed, use_graph = None, False
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
