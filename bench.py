@@ -264,22 +264,17 @@ def main():
         x_dev = crops_dev
 
     def dino_loss_fn(student, teacher_out):
-        """loss.py:119-152 restated with torch ops (DINOLoss is a "next" row): centred / sharpened teacher
-        softmax vs student log-softmax over every other crop, then the EMA centre update with its all-reduce."""
-        nonlocal center
-        s = (student / 0.1).chunk(10)
-        t = torch.softmax((teacher_out - center) / 0.04, -1).detach().chunk(2)
-        total, n = 0.0, 0
-        for iq, q in enumerate(t):
-            for v in range(10):
-                if v != iq:
-                    total = total + (-q * torch.log_softmax(s[v], -1)).sum(-1).mean()
-                    n += 1
+        """DINOLoss.forward (loss.py:119-152): centred / sharpened teacher softmax vs student log-softmax over every
+        other crop as ONE fused kernel (vtb_dino_loss: loss + student gradient), then the EMA centre update with its
+        all-reduce."""
+        from vtb200.blocks import DINOLossFn
+
+        loss = DINOLossFn.apply(student.float(), teacher_out.float(), center, 10, 0.1, 0.04)
         bc = teacher_out.sum(0, keepdim=True)
         if world > 1:
             dist.all_reduce(bc)
         center.mul_(0.9).add_(bc, alpha=0.1 / (teacher_out.shape[0] * world))  # in place: the buffer is part of the graph
-        return total / n
+        return loss
 
     def fwd_bwd(x, y):
         if reducer is not None and reducer.attached:

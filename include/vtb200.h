@@ -221,6 +221,17 @@ int vtb_mean_rows_fwd(const float* x, int32_t groups, int32_t n, int32_t cols, f
 int vtb_mean_rows_bwd(const float* dy, int32_t groups, int32_t n, int32_t cols, float* dx,
                       vtb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused DINO loss (loss.py:119-142, DINOLoss.forward): one launch computes
+ *   loss += mean over pairs (iq, v != iq) and images of  -sum_k softmax((teacher[iq]-center)/t_teacher)[k]
+ *                                                          * log_softmax(student[v]/t_student)[k]
+ * and (dstudent != NULL) the gradient of that loss w.r.t. student.  student f32 [n_crops*batch, dim] (crop-major chunks,
+ * the first two crops are the global ones), teacher f32 [2*batch, dim], center f32 [dim], loss f32 [1] (atomicAdd: zero it),
+ * dstudent f32 [n_crops*batch, dim].  One CTA per image, two streaming passes over its rows.
+ * ---------------------------------------------------------------------------------------------- */
+int vtb_dino_loss(const float* student, const float* teacher, const float* center, int32_t n_crops, int32_t batch,
+                  int32_t dim, float t_student, float t_teacher, float* loss, float* dstudent, vtb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -566,3 +566,33 @@ def test_dwconv3x3_peg(ops):
     want.backward(dy)
     dx, dw = ops.dwconv3x3_bwd(x.detach(), w.detach(), dy)
     assert rel(dx, x.grad) < 1e-6 and rel(dw, w.grad) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- DINO loss (§8f)
+@pytest.mark.parametrize("B,K,n_crops", [(3, 256, 10), (4, 65536, 10), (2, 1000, 4), (1, 64, 2)])
+def test_dino_loss_fused_vs_oracle(ops, B, K, n_crops):
+    """vtb_dino_loss (one kernel: loss + gradient) vs the oracle restatement of DINOLoss.forward (loss.py:119-142) and
+    torch autograd through it; the drop-in `loss.DINOLoss` module also updates the centre like the reference."""
+    from oracle import restate as R
+    from vtb200.blocks import DINOLossFn
+
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + n_crops)
+    student = (3.0 * torch.randn(n_crops * B, K, device="cuda", generator=g)).requires_grad_(True)
+    teacher = 3.0 * torch.randn(2 * B, K, device="cuda", generator=g)
+    center = 0.5 * torch.randn(1, K, device="cuda", generator=g)
+    want = R.dino_loss(student, teacher, center, n_crops, 0.1, 0.04)
+    (gw,) = torch.autograd.grad(want * 1.7, student)
+    s2 = student.detach().clone().requires_grad_(True)
+    got = DINOLossFn.apply(s2, teacher, center, n_crops, 0.1, 0.04)
+    (gg,) = torch.autograd.grad(got * 1.7, s2)
+    assert abs(got.item() - want.item()) < 2e-5 * max(1.0, abs(want.item())), (got.item(), want.item())
+    assert rel(gg, gw) < 2e-5, rel(gg, gw)
+    # module-level drop-in: same constructor as the reference, centre EMA (loss.py:144-152)
+    import loss as L
+
+    mod = L.DINOLoss(K, n_crops, 0.04, 0.04, 0, 10).cuda()
+    mod.center.copy_(center)
+    out = mod(student.detach(), teacher, 0)
+    assert abs(out.item() - want.item()) < 2e-5 * max(1.0, abs(want.item()))
+    want_center = center * 0.9 + teacher.sum(0, keepdim=True) / teacher.shape[0] * 0.1
+    assert rel(mod.center, want_center) < 1e-6

@@ -564,3 +564,23 @@ class PVTPatchEmbedFn(Function):
             dx_nhwc = ops.patch_scatter(dA, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
             dx = dx_nhwc.permute(0, 3, 1, 2)
         return dx, None, None, dw, db, dg, dbeta, dpos, dcls
+
+
+class DINOLossFn(Function):
+    """DINOLoss.forward (loss.py:119-142): loss and d loss / d student from ONE kernel; the teacher side is detached as
+    in the reference (`teacher_out.detach()`, loss.py:125)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, student, teacher, center, n_crops, t_student, t_teacher):
+        need = ctx.needs_input_grad[0]
+        loss, ds = ops.dino_loss(_c(student), _c(teacher.detach()), _c(center.detach()), n_crops, t_student, t_teacher,
+                                 want_grad=need)
+        ctx.stash = ds
+        return loss.view(())
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        ds = ctx.stash
+        return (ds * g if ds is not None else None), None, None, None, None, None

@@ -19,7 +19,7 @@ SYMBOLS = [
     "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_cast_f32_bf16",
     "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_scale_cast_colsum_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
     "vtb_patch_scatter", "vtb_transpose_hw", "vtb_dwconv3x3_fwd", "vtb_dwconv3x3_bwd", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
-    "vtb_silu_fwd", "vtb_silu_bwd",
+    "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.vtb_mean_rows_bwd.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.vtb_silu_fwd.argtypes = [vp, vp, i64, vp]
     lib.vtb_silu_bwd.argtypes = [vp, vp, vp, i64, vp]
+    lib.vtb_dino_loss.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vtb_last_error",):

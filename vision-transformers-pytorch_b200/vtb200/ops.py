@@ -517,3 +517,23 @@ def dwconv3x3_bwd(x, w, dy):
         _l.check(lib.vtb_dwconv3x3_bwd(_p(x), _p(w), _p(dy), B, H, W, Cc, _p(dx), _p(dw), _stream()), lib)
     _count()
     return dx, dw
+
+
+def dino_loss(student, teacher, center, n_crops, t_student, t_teacher, want_grad=True):
+    """Fused DINOLoss.forward (loss.py:119-142) and its gradient.  student f32 [n_crops*B, K], teacher f32 [2*B, K],
+    center f32 [1, K] or [K].  Returns (loss f32 [1], dstudent f32 like student or None)."""
+    lib = _l.get()
+    for t, nm in ((student, "student"), (teacher, "teacher"), (center, "center")):
+        if t.dtype != F32 or not t.is_contiguous():
+            raise ValueError(f"vtb200.dino_loss: {nm} must be contiguous f32")
+    K = student.shape[-1]
+    B = teacher.shape[0] // 2
+    if teacher.shape != (2 * B, K) or student.shape != (n_crops * B, K) or center.numel() != K:
+        raise ValueError("vtb200.dino_loss: shapes must be student [n_crops*B, K], teacher [2*B, K], center [K]")
+    loss = zeros(1, F32, student.device)
+    dstudent = torch.empty_like(student) if want_grad else None
+    with _prof("dino_loss", 0.0, 4.0 * (2 * (student.numel() + teacher.numel()) + (student.numel() if want_grad else 0))):
+        _l.check(lib.vtb_dino_loss(_p(student), _p(teacher), _p(center), n_crops, B, K, float(t_student),
+                                   float(t_teacher), _p(loss), _p(dstudent), _stream()), lib)
+    _count()
+    return loss, dstudent
