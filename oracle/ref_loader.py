@@ -62,3 +62,20 @@ def load():
     for name in ("layer", "vit", "swin_transformer", "pvt", "halo_transformer", "twins"):
         setattr(mod, name, importlib.import_module(f"ref_models.{name}"))
     return mod
+
+
+def load_reference_module(name):
+    """Import a top-level file of the reference tree (e.g. `loss` -> loss.py) under the name `ref_<name>`; None when the
+    reference tree is absent (GPU box)."""
+    root = reference_root()
+    if root is None:
+        return None
+    key = f"ref_{name}"
+    if key in sys.modules:
+        return sys.modules[key]
+    _install_tensorfn_stub()
+    spec = importlib.util.spec_from_file_location(key, os.path.join(root, f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[key] = mod
+    spec.loader.exec_module(mod)
+    return mod

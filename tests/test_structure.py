@@ -106,3 +106,25 @@ def test_forward_on_cpu_fails_loudly():
     v = models.VisionTransformer(None, 32, 8, 1, 64, 2, 128, 0., 0., 0., 0.)
     with pytest.raises(RuntimeError, match="CUDA device required"):
         v(torch.randn(1, 3, 32, 32))
+
+
+def test_dino_loss_module_matches_reference_schema():
+    """loss.DINOLoss (drop-in for loss.py:89-152): same constructor arguments, same buffer, same temperature schedule."""
+    import inspect
+
+    import loss as L
+    from oracle import ref_loader
+
+    ref = ref_loader.load_reference_module("loss") if hasattr(ref_loader, "load_reference_module") else None
+    mine = L.DINOLoss(4096, 10, 0.04, 0.07, 3, 10)
+    assert list(mine.state_dict().keys()) == ["center"] and mine.center.shape == (1, 4096)
+    assert len(mine.teacher_temperature_schedule) == 10 and abs(mine.teacher_temperature_schedule[0] - 0.04) < 1e-7
+    assert abs(mine.teacher_temperature_schedule[-1] - 0.07) < 1e-7
+    want_args = ["self", "out_dim", "n_crop", "warmup_teacher_temperature", "teacher_temperature", "warmup_teacher_epoch",
+                 "n_epoch", "student_temperature", "center_momentum"]
+    assert list(inspect.signature(L.DINOLoss.__init__).parameters) == want_args
+    if ref is not None:
+        theirs = ref.DINOLoss(4096, 10, 0.04, 0.07, 3, 10)
+        assert list(theirs.state_dict().keys()) == list(mine.state_dict().keys())
+        assert theirs.teacher_temperature_schedule == mine.teacher_temperature_schedule
+        assert list(inspect.signature(ref.DINOLoss.__init__).parameters) == want_args

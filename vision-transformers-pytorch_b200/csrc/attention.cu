@@ -4,9 +4,11 @@
 // padding and the relative-position bias / mask are folded into the load addressing, so none of the
 // reference's roll / reshape / unfold / masked_fill / softmax kernels (and their HBM traffic) exist.
 //
-// v1 tensor path: mma.sync m16n8k16 bf16 (fp32 accumulate), 4 warps x 16 rows per CTA, online softmax
-// over 64-key blocks.  (Attention is 4 % of the path's FLOPs — SURVEY §3 — the tcgen05 GEMM carries
-// the rest; a tcgen05/TMEM variant of this kernel is the follow-up.)
+// This file holds the dispatcher (vtb_attention_fwd / vtb_attention_bwd) and the mma.sync m16n8k16 kernels that remain
+// for the shapes the tcgen05 kernels do not cover: Halo blocks (49 x 169), dh = 64 windows (Twins-LSA), global attention
+// with more than 256 queries in backward (PVT stages 1-2, streaming kernels) and unaligned / odd shapes.  Global
+// attention with dh = 64 and <= 256 tokens runs in attention_tc.cu, shifted-window attention with dh = 32 in
+// attention_win_tc.cu (both tcgen05 / TMEM).
 #include "common.cuh"
 #include "../../include/vtb200.h"
 #include <math.h>
