@@ -513,6 +513,25 @@ def test_patch_gather_scatter(ops, nchw, c_major):
     assert torch.equal(back, nhwc)  # scatter is the exact inverse permutation
 
 
+@pytest.mark.parametrize("src_bf16", [True, False])
+@pytest.mark.parametrize("B,C,H,W,p", [(2, 64, 16, 24, 8), (3, 320, 14, 14, 2), (1, 8, 4, 4, 4)])
+def test_patch_gather_scatter_vectorised_nhwc(ops, src_bf16, B, C, H, W, p):
+    """The 16-byte-vector pos-major path (NHWC source, C a multiple of 8 / 4) is an exact permutation both ways."""
+    from einops import rearrange
+
+    g = torch.Generator(device="cuda").manual_seed(C + p)
+    nhwc = bf(torch.randn(B, H, W, C, device="cuda", generator=g)).float()  # bf16-representable values
+    src = nhwc.to(BF16) if src_bf16 else nhwc
+    got = ops.patch_gather(src, nchw=False, c_major=False, B=B, Cc=C, H=H, W=W, p=p)
+    want = rearrange(nhwc, "b (h py) (w px) c -> (b h w) (py px c)", py=p, px=p)
+    assert torch.equal(got, want.to(BF16))
+    dA = want.to(BF16).contiguous() if src_bf16 else want.contiguous()
+    back = ops.patch_scatter(dA, c_major=False, B=B, Cc=C, H=H, W=W, p=p)
+    assert torch.equal(back, nhwc)
+    acc = ops.patch_scatter(dA, c_major=False, B=B, Cc=C, H=H, W=W, p=p, dx=back.clone(), accumulate=True)
+    assert torch.equal(acc, 2 * nhwc)
+
+
 def test_pool_fill_rowsum_silu(ops):
     g = torch.Generator(device="cuda").manual_seed(13)
     x = torch.randn(5, 49, 96, device="cuda", generator=g)

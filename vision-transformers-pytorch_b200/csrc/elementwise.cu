@@ -200,6 +200,86 @@ __global__ void patch_gather_kernel(const T* __restrict__ src, int src_nchw, int
   }
 }
 
+// Vectorised pos-major gather / scatter for NHWC tensors (feature = (py*p + px)*C + c: the `patchify` order, and — with the
+// conv weight permuted to [C_out, p, p, C] — also the order used for the k = s convolutions over NHWC token maps).  The
+// per-vector source offset inside a patch does not depend on the patch, so it is tabulated once per CTA; per patch only
+// two 32-bit divisions remain (per thread per ROW, not per element).  16-byte loads, 8/16-byte stores, fully coalesced.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+patch_gather_nhwc_vec_kernel(const T* __restrict__ src, PatchGeom g, bf16* __restrict__ dst, int rows_total,
+                             int rows_per_cta) {
+  extern __shared__ int s_delta[];
+  const int cv = g.C / V, vpr = g.p * g.p * cv;
+  for (int v = threadIdx.x; v < vpr; v += blockDim.x) {
+    const int sidx = v / cv, vc = v - sidx * cv;
+    const int py = sidx / g.p, px = sidx - py * g.p;
+    s_delta[v] = (py * g.W + px) * g.C + vc * V;
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows_total, r0 + rows_per_cta);
+  for (int row = r0; row < r1; ++row) {
+    const int q = row / g.Wo, bx = row - q * g.Wo;
+    const int b = q / g.Ho, by = q - b * g.Ho;
+    const T* sp = src + (((long)b * g.H + (long)by * g.p) * g.W + (long)bx * g.p) * g.C;
+    bf16* dp = dst + (long)row * g.F;
+    for (int v = threadIdx.x; v < vpr; v += blockDim.x) {
+      if (V == 8) {  // bf16 source: a 16-byte copy
+        *reinterpret_cast<uint4*>(dp + v * 8) = __ldg(reinterpret_cast<const uint4*>(sp + s_delta[v]));
+      } else {       // f32 source: 4 floats -> 4 bf16
+        const float4 x = __ldg(reinterpret_cast<const float4*>(sp + s_delta[v]));
+        *reinterpret_cast<uint2*>(dp + v * 4) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+      }
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+patch_scatter_nhwc_vec_kernel(const T* __restrict__ dA, PatchGeom g, float* __restrict__ dx, int accumulate,
+                              int rows_total, int rows_per_cta) {
+  extern __shared__ int s_delta[];
+  const int cv = g.C / V, vpr = g.p * g.p * cv;
+  for (int v = threadIdx.x; v < vpr; v += blockDim.x) {
+    const int sidx = v / cv, vc = v - sidx * cv;
+    const int py = sidx / g.p, px = sidx - py * g.p;
+    s_delta[v] = (py * g.W + px) * g.C + vc * V;
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows_total, r0 + rows_per_cta);
+  for (int row = r0; row < r1; ++row) {
+    const int q = row / g.Wo, bx = row - q * g.Wo;
+    const int b = q / g.Ho, by = q - b * g.Ho;
+    float* op = dx + (((long)b * g.H + (long)by * g.p) * g.W + (long)bx * g.p) * g.C;
+    const T* ip = dA + (long)row * g.F;
+    for (int v = threadIdx.x; v < vpr; v += blockDim.x) {
+      float x[V];
+      if (V == 8) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(ip + v * 8));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(w[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+      } else {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(ip + v * 4));
+        x[0] = r.x; x[1] = r.y; x[2] = r.z; x[3] = r.w;
+      }
+      float4* o = reinterpret_cast<float4*>(op + s_delta[v]);
+#pragma unroll
+      for (int k = 0; k < V / 4; ++k) {
+        float4 t = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+        if (accumulate) { const float4 old = o[k]; t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w; }
+        o[k] = t;  // patches do not overlap: no atomics needed
+      }
+    }
+  }
+}
+
+// rows per CTA so that the grid is a few CTAs per SM
+inline int patch_rows_per_cta(long rows) {
+  const long ctas = (long)(vtb_num_sms() > 0 ? vtb_num_sms() : 148) * 8;
+  long r = (rows + ctas - 1) / ctas;
+  return (int)(r < 1 ? 1 : r);
+}
+
 template <typename T>
 __global__ void patch_scatter_kernel(const T* __restrict__ dA, int c_major, PatchGeom g,
                                      float* __restrict__ dx, int accumulate, int dst_nchw) {
@@ -471,6 +551,22 @@ extern "C" int vtb_patch_gather(const void* src, int32_t src_bf16, int32_t src_n
   if (rc) return rc;
   VTB_CHECK(src && dst, -1, "vtb_patch_gather: null pointer");
   VTB_CHECK(g.F % 2 == 0, -1, "vtb_patch_gather: feature count must be even");
+  {  // vectorised path: pos-major features of an NHWC source whose channel rows split into 16-byte vectors
+    const int V = src_bf16 ? 8 : 4;
+    const long rows = (long)B * g.Ho * g.Wo;
+    const size_t tab = (size_t)p * p * (C / V) * sizeof(int);
+    if (!c_major && !src_nchw && C % V == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 &&
+        rows < (1L << 31) && tab <= 48 * 1024) {
+      const int rpc = patch_rows_per_cta(rows);
+      const int grid = (int)((rows + rpc - 1) / rpc);
+      if (src_bf16)
+        patch_gather_nhwc_vec_kernel<bf16, 8><<<grid, 256, tab, (cudaStream_t)s>>>((const bf16*)src, g, (bf16*)dst, (int)rows, rpc);
+      else
+        patch_gather_nhwc_vec_kernel<float, 4><<<grid, 256, tab, (cudaStream_t)s>>>((const float*)src, g, (bf16*)dst, (int)rows, rpc);
+      VTB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const long total = (long)B * g.Ho * g.Wo * (g.F / 2);
   if (src_bf16)
     patch_gather_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const bf16*)src, src_nchw, c_major, g, (bf16*)dst);
@@ -487,6 +583,22 @@ extern "C" int vtb_patch_scatter(const void* dA, int32_t dA_f32, int32_t c_major
   int rc = patch_geom("vtb_patch_scatter", B, C, H, W, p, &g);
   if (rc) return rc;
   VTB_CHECK(dA && dx, -1, "vtb_patch_scatter: null pointer");
+  {  // vectorised path (see vtb_patch_gather)
+    const int V = dA_f32 ? 4 : 8;
+    const long rows = (long)B * g.Ho * g.Wo;
+    const size_t tab = (size_t)p * p * (C / V) * sizeof(int);
+    if (!c_major && !dst_nchw && C % V == 0 && ((uintptr_t)dA & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
+        rows < (1L << 31) && tab <= 48 * 1024) {
+      const int rpc = patch_rows_per_cta(rows);
+      const int grid = (int)((rows + rpc - 1) / rpc);
+      if (dA_f32)
+        patch_scatter_nhwc_vec_kernel<float, 4><<<grid, 256, tab, (cudaStream_t)s>>>((const float*)dA, g, dx, accumulate, (int)rows, rpc);
+      else
+        patch_scatter_nhwc_vec_kernel<bf16, 8><<<grid, 256, tab, (cudaStream_t)s>>>((const bf16*)dA, g, dx, accumulate, (int)rows, rpc);
+      VTB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const long total = (long)B * g.Ho * g.Wo * g.F;
   if (dA_f32)
     patch_scatter_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>((const float*)dA, c_major, g, dx, accumulate, dst_nchw);

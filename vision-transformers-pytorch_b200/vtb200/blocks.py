@@ -235,12 +235,15 @@ class SRABranchFn(Function):
         q = ops.gemm(y, wqb)
         red_stash = None
         if R > 1:
-            wrb = ops.cast_bf16(_c(w_r).view(C, -1))
             if scramble:
+                wrb = ops.cast_bf16(_c(w_r).view(C, -1))
                 yt = ops.transpose_hw(y, B, Hs, Ws, C)  # [B,W,H,C] memory, read below as if it were [B,C,H,W]
                 A = ops.patch_gather(yt, nchw=True, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R)
             else:
-                A = ops.patch_gather(y, nchw=False, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R)
+                # NHWC tokens: gather in (py, px, c) order — contiguous channel runs, 16-byte vectors — and permute the
+                # (small) conv weight [C, C, R, R] -> [C, R, R, C] instead of transposing every patch to (c, py, px)
+                wrb = ops.cast_bf16(w_r.permute(0, 2, 3, 1).reshape(C, -1))
+                A = ops.patch_gather(y, nchw=False, c_major=False, B=B, Cc=C, H=Hs, W=Ws, p=R)
             nkv = (Hs // R) * (Ws // R)
             if kv_norm:
                 red = ops.gemm(A, wrb, out_dtype=F32, bias=b_r)
@@ -287,13 +290,15 @@ class SRABranchFn(Function):
             else:
                 dred = dkvin
             db_r = ops.colsum(dred)
-            dw_r = _wgrad(dred, A).view(wr_shape)
             dA = _dgrad(dred, wrb)
             if scramble:
+                dw_r = _wgrad(dred, A).view(wr_shape)
                 dflat = ops.patch_scatter(dA, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R, dst_nchw=True)
                 dy_kv = ops.transpose_hw(dflat, B, Ws, Hs, C).view(-1, C)  # [B,W,H,C] -> [B,H,W,C]
             else:
-                dy_kv = ops.patch_scatter(dA, c_major=True, B=B, Cc=C, H=Hs, W=Ws, p=R).view(-1, C)
+                co, ci, kh, kw = wr_shape  # gradient comes out in the permuted [C_out, R, R, C_in] order
+                dw_r = _wgrad(dred, A).view(co, kh, kw, ci).permute(0, 3, 1, 2).contiguous()
+                dy_kv = ops.patch_scatter(dA, c_major=False, B=B, Cc=C, H=Hs, W=Ws, p=R).view(-1, C)
             dy = _dgrad(dq, wqb, out_dtype=F32, resid=dy_kv)
         else:
             dy_kv = _dgrad(dkv, wkvb, out_dtype=F32)
@@ -522,11 +527,14 @@ class PVTPatchEmbedFn(Function):
         B, Cin, H, W = x.shape
         D = w.shape[0]
         n = (H // p) * (W // p)
-        if x.permute(0, 2, 3, 1).is_contiguous():  # NCHW *view* of NHWC tokens (pvt.py:261): read in place
-            A = ops.patch_gather(x.permute(0, 2, 3, 1), nchw=False, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
+        nhwc = x.permute(0, 2, 3, 1).is_contiguous()  # NCHW *view* of NHWC tokens (pvt.py:261): read in place
+        if nhwc:
+            # (py, px, c) feature order: contiguous channel runs; the conv weight is permuted to match (see SRABranchFn)
+            A = ops.patch_gather(x.permute(0, 2, 3, 1), nchw=False, c_major=False, B=B, Cc=Cin, H=H, W=W, p=p)
+            wb = ops.cast_bf16(w.permute(0, 2, 3, 1).reshape(D, -1))
         else:
             A = ops.patch_gather(_c(x), nchw=True, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
-        wb = ops.cast_bf16(_c(w).view(D, -1))
+            wb = ops.cast_bf16(_c(w).view(D, -1))
         lin = ops.gemm(A, wb, out_dtype=F32, bias=b)
         has_cls = cls_token is not None
         pos = _c(pos)
@@ -539,14 +547,14 @@ class PVTPatchEmbedFn(Function):
         else:
             out = y.view(B, n, D)
         ctx.save_for_backward(lin, ln_w, mean, rstd)
-        ctx.stash = (A, wb, (B, Cin, H, W, p, D, n), has_cls, w.shape)
+        ctx.stash = (A, wb, (B, Cin, H, W, p, D, n), has_cls, w.shape, nhwc)
         return out
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         lin, ln_w, mean, rstd = ctx.saved_tensors
-        A, wb, (B, Cin, H, W, p, D, n), has_cls, wshape = ctx.stash
+        A, wb, (B, Cin, H, W, p, D, n), has_cls, wshape, nhwc = ctx.stash
         dout = _c(dout)
         ntok = n + 1 if has_cls else n
         dpos = torch.zeros((ntok, D), dtype=F32, device=dout.device)
@@ -555,13 +563,16 @@ class PVTPatchEmbedFn(Function):
         d2 = _c(dout[:, 1:]).view(-1, D) if has_cls else dout.view(-1, D)
         _, g, dg, dbeta = ops.layernorm_bwd(d2, lin, ln_w, mean, rstd, want_bf16=True)
         db = ops.colsum(g)
-        dw = _wgrad(g, A).view(wshape)
+        if nhwc:
+            dw = _wgrad(g, A).view(wshape[0], wshape[2], wshape[3], wshape[1]).permute(0, 3, 1, 2).contiguous()
+        else:
+            dw = _wgrad(g, A).view(wshape)
         dx = None
         if ctx.needs_input_grad[0]:
             dA = _dgrad(g, wb)
-            # adjoint of the NCHW c-major gather: scatter to NHWC then view as NCHW is a permute; the PVT
-            # stage inputs are NHWC tokens permuted to NCHW (pvt.py:261), so hand back that permuted view.
-            dx_nhwc = ops.patch_scatter(dA, c_major=True, B=B, Cc=Cin, H=H, W=W, p=p)
+            # adjoint of the gather: scatter to NHWC then view as NCHW is a permute; the PVT stage inputs are NHWC
+            # tokens permuted to NCHW (pvt.py:261), so hand back that permuted view.
+            dx_nhwc = ops.patch_scatter(dA, c_major=not nhwc, B=B, Cc=Cin, H=H, W=W, p=p)
             dx = dx_nhwc.permute(0, 3, 1, 2)
         return dx, None, None, dw, db, dg, dbeta, dpos, dcls
 
