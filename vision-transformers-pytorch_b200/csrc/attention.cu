@@ -747,7 +747,7 @@ __device__ __forceinline__ void res_load_rows(bf16* dst, int rows16, const bf16*
 struct ResSmem {
   bf16 *q, *k, *v, *dO;
   float *bias, *lse, *delta, *dtab, *tab;
-  unsigned short* pos;
+  float* dsum;   // [nq][bias_ld] (bwd): running sum of dS over every group this CTA processes (bias gradient)
   uint8_t* maskb;
   int *qtok, *ktok;
   int nq16, nkv16, bias_ld;
@@ -773,7 +773,7 @@ __device__ __forceinline__ ResSmem res_carve(uint8_t* base, int nq_loc, int nq, 
   s.tab = reinterpret_cast<float*>(p); if (has_bias) p += n_pos * 4;   // rel_bias[:, h] staged once per CTA
   s.qtok = reinterpret_cast<int*>(p); p += s.nq16 * 4;
   s.ktok = reinterpret_cast<int*>(p); p += s.nkv16 * 4;
-  s.pos = reinterpret_cast<unsigned short*>(p); if (bwd && has_bias) p += (size_t)nq * s.bias_ld * 2;  // u16 tile
+  s.dsum = reinterpret_cast<float*>(p); if (bwd && has_bias) p += (size_t)nq * s.bias_ld * 4;
   s.maskb = p;                                                          // [nq][bias_ld] u8 mask of the current group
   return s;
 }
@@ -783,12 +783,12 @@ size_t res_smem_bytes(int DH, int nq_loc, int nq, int nkv, bool bwd, bool has_bi
   size_t b = (size_t)(nq16 + 2 * nkv16) * DH * 2 + (size_t)(nq16 + nkv16) * 4;
   if (bwd) b += (size_t)nq16 * DH * 2 + (size_t)nq16 * 8;
   if (has_bias) b += (size_t)nq * bld * 4 + (size_t)n_pos * 4 + (size_t)nq * bld;  // bias tile, table, mask bytes
-  if (bwd && has_table) b += (size_t)n_pos * 4 + (size_t)nq * bld * 2;
+  if (bwd && has_table) b += (size_t)n_pos * 4 + (size_t)nq * bld * 4;
   return b + 16;
 }
 
 // Once per CTA: stage rel_bias[:, h] in shared memory, then build the group-independent bias tile
-// bias[i][j] = table[pos[i][j]] (and the u16 pos tile for the backward's bias gradient).  The table goes through
+// bias[i][j] = table[pos[i][j]] (and clear the backward's dS accumulation tile).  The table goes through
 // smem first so that no global load depends on another one.
 template <int DH>
 __device__ __forceinline__ void res_once(const vtb_attn_params& p, const Geom& g, int h, const ResSmem& s, bool bwd) {
@@ -806,7 +806,7 @@ __device__ __forceinline__ void res_once(const vtb_attn_params& p, const Geom& g
     if (p.rel_bias) {
       const int pi = __ldg(p.pos + e);
       b = s.tab[pi];
-      if (bwd) s.pos[i * s.bias_ld + j] = (unsigned short)pi;
+      if (bwd) s.dsum[i * s.bias_ld + j] = 0.f;
     }
     s.bias[i * s.bias_ld + j] = b;
   }
@@ -1089,7 +1089,10 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int skip
               if (has_bias) v += res_bias(s, has_mask, i, j);
               const float pv = __expf(v - lse_r[r]);  // exp(-inf) = 0 for masked entries
               ds = pv * (dp[n][e] - dl_r[r]);
-              if (has_tab && p.drel_bias && ds != 0.f) atomicAdd(&s.dtab[s.pos[i * s.bias_ld + j]], ds);
+              // bias gradient: element (i, j) belongs to exactly this thread in every group the CTA processes, so the
+              // running sum is a plain read-modify-write (shared-memory float atomics are CAS loops: they were most of
+              // this kernel's time on Halo blocks); table indices are applied once per CTA after the last group
+              if (has_tab && p.drel_bias) s.dsum[i * s.bias_ld + j] += ds;
             }
             sc[n][e] = ds;
           }
@@ -1233,8 +1236,14 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int skip
     }
   }
 
-  }  // groups: the bias-gradient table keeps accumulating across them and is flushed once per CTA
+  }  // groups: the dS tile keeps accumulating across them; folded into the table and flushed once per CTA
   if (has_tab && p.drel_bias) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < g.nq * g.nkv; e += blockDim.x) {
+      const int i = e / g.nkv, j = e - i * g.nkv;
+      const float v = s.dsum[i * s.bias_ld + j];
+      if (v != 0.f) atomicAdd(&s.dtab[__ldg(p.pos + e)], v);
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) {
       const float v = s.dtab[t];
