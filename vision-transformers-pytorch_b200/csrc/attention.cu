@@ -1031,6 +1031,8 @@ attn_res_bwd_kernel(vtb_attn_params p, Geom g, int groups, int nchunks, int skip
       if (half == 0) {
         s.delta[row] = acc;
         s.lse[row] = tok >= 0 ? p.lse[((long)grp * g.heads + h) * g.nq + row] : 0.f;
+        // also kept in the caller's workspace: the key-centric Halo dK / dV kernel that follows reads it from there
+        if (tok >= 0 && p.delta) p.delta[((long)grp * g.heads + h) * g.nq + row] = acc;
       }
     }
   }
@@ -1843,35 +1845,39 @@ namespace {
 
 template <int DH>
 __global__ void __launch_bounds__(128, 3)
-attn_halo_dkv_kernel(vtb_attn_params p, Geom g) {
+attn_halo_dkv_kernel(vtb_attn_params p, Geom g, int groups, int nchunks) {
   extern __shared__ __align__(16) uint8_t hk_smem[];
   const int h = blockIdx.x % g.heads;
-  const int grp = blockIdx.x / g.heads;
+  const int chunk = blockIdx.x / g.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
   const int W = g.window, HL = g.halo, KW = W + 2 * HL;
   const int nq = g.nq;                       // W*W tokens per block
-  const int b = grp / g.nw, wi = grp - b * g.nw;
-  const int by = wi / g.nwx, bx = wi - by * g.nwx;
   const int nby = g.Hs / W;
   const int reach = (HL + W - 1) / W;        // neighbour blocks whose halo can reach this block
   const float sl2 = p.scale * 1.4426950408889634f;
   constexpr float L2E = 1.4426950408889634f;
 
-  // smem: K, V (own tokens), Q, dO (current neighbour) [64][DH]; lse2, delta [64]; tab [n_pos]; pos u16 [nq][nkv]
+  // smem: K, V (own tokens), Q, dO (current neighbour) [64][DH]; lse2, delta [64]; bias tile f32 [nq][nkv] (x log2 e)
   bf16* sK = reinterpret_cast<bf16*>(hk_smem);
   bf16* sV = sK + 64 * DH;
   bf16* sQ = sV + 64 * DH;
   bf16* sdO = sQ + 64 * DH;
   float* sLse = reinterpret_cast<float*>(sdO + 64 * DH);
   float* sDelta = sLse + 64;
-  float* sTab = sDelta + 64;
-  int* sTok = reinterpret_cast<int*>(sTab + p.n_pos);       // [64] own tokens
+  int* sTok = reinterpret_cast<int*>(sDelta + 64);          // [64] own tokens
   int* sNTok = sTok + 64;                                   // [64] neighbour tokens
-  unsigned short* sPos = reinterpret_cast<unsigned short*>(sNTok + 64);  // [nq][nkv]
+  float* sBias = reinterpret_cast<float*>(sNTok + 64);      // [nq][nkv], built once per CTA (fixed head)
 
-  for (int t = threadIdx.x; t < p.n_pos; t += blockDim.x) sTab[t] = __ldg(p.rel_bias + (long)t * g.heads + h);
-  for (int e = threadIdx.x; e < nq * g.nkv; e += blockDim.x) sPos[e] = (unsigned short)__ldg(p.pos + e);
+  constexpr float L2E_ = 1.4426950408889634f;
+  for (int e = threadIdx.x; e < nq * g.nkv; e += blockDim.x)
+    sBias[e] = __ldg(p.rel_bias + (long)__ldg(p.pos + e) * g.heads + h) * L2E_;
+
+  // persistent over the blocks of this head: the bias tile is built once per CTA
+  for (int grp = chunk; grp < groups; grp += nchunks) {
+  const int b = grp / g.nw, wi = grp - b * g.nw;
+  const int by = wi / g.nwx, bx = wi - by * g.nwx;
+  __syncthreads();  // previous block's tiles fully consumed (and the bias tile visible)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
     int tok = -1;
     if (i < nq) {
@@ -1911,36 +1917,18 @@ attn_halo_dkv_kernel(vtb_attn_params p, Geom g) {
       if (nx < 0 || nx >= g.nwx) continue;
       const int ngrp = b * g.nw + ny * g.nwx + nx;
       __syncthreads();  // previous neighbour's tiles fully consumed
-      // neighbour query tokens, lse2, delta (two threads per row)
-      {
-        const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+      // neighbour query tokens, lse2 and delta (= rowsum(dO o O), left in the workspace by the dQ kernel)
+      if (threadIdx.x < 64) {
+        const int row = threadIdx.x;
         int tok = -1;
         if (row < nq) {
           const int ty = row / W, tx = row - ty * W;
           tok = (b * g.Hs + ny * W + ty) * g.Ws + nx * W + tx;
         }
-        float acc = 0.f;
-        if (tok >= 0) {
-          const bf16* a = dOg + (long)tok * p.lddo + h * DH + half * (DH / 2);
-          const bf16* c = Og + (long)tok * p.ldo + h * DH + half * (DH / 2);
-#pragma unroll
-          for (int d = 0; d < DH / 2; d += 8) {
-            const uint4 ra = *reinterpret_cast<const uint4*>(a + d);
-            const uint4 rc = *reinterpret_cast<const uint4*>(c + d);
-            const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wc[4] = {rc.x, rc.y, rc.z, rc.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 fa = unpack_bf16(wa[q]), fc = unpack_bf16(wc[q]);
-              acc += fa.x * fc.x + fa.y * fc.y;
-            }
-          }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (half == 0) {
-          sNTok[row] = tok;
-          sDelta[row] = acc;
-          sLse[row] = tok >= 0 ? p.lse[((long)ngrp * g.heads + h) * nq + row] * L2E : INFINITY;
-        }
+        const long li = ((long)ngrp * g.heads + h) * nq + row;
+        sNTok[row] = tok;
+        sDelta[row] = tok >= 0 ? __ldg(p.delta + li) : 0.f;
+        sLse[row] = tok >= 0 ? __ldg(p.lse + li) * L2E : INFINITY;
       }
       __syncthreads();
       {
@@ -1996,8 +1984,7 @@ attn_halo_dkv_kernel(vtb_attn_params p, Geom g) {
             const int t = n * 8 + 2 * tq + e;   // neighbour query index
             float pv = 0.f, ds = 0.f;
             if (kvalid && t < nq) {
-              const float bias = sTab[sPos[t * g.nkv + slot]];
-              pv = exp2f(fmaf(sc[n][2 * r + e], sl2, fmaf(bias, L2E, -sLse[t])));
+              pv = exp2f(fmaf(sc[n][2 * r + e], sl2, sBias[t * g.nkv + slot] - sLse[t]));
               ds = pv * (dp[n][2 * r + e] - sDelta[t]);
             }
             sc[n][2 * r + e] = pv;
@@ -2040,28 +2027,34 @@ attn_halo_dkv_kernel(vtb_attn_params p, Geom g) {
       *reinterpret_cast<uint32_t*>(dVp + n * 8 + 2 * tq) = pack_bf16(dv[n][2 * r], dv[n][2 * r + 1]);
     }
   }
+  }  // blocks
 }
 
 }  // namespace
 
 bool vtb_attn_halo_dkv_ok(const vtb_attn_params* p) {
-  return p->mode == VTB_ATTN_HALO && !p->dkv_f32 && p->nq <= 64 && p->rel_bias != nullptr && p->n_pos <= MAX_POS;
+  return p->mode == VTB_ATTN_HALO && !p->dkv_f32 && p->nq <= 64 && p->rel_bias != nullptr && p->n_pos <= MAX_POS &&
+         p->delta != nullptr;
 }
 
 int vtb_attn_halo_dkv(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream) {
-  const size_t smem = (size_t)4 * 64 * p->dh * 2 + 2 * 64 * 4 + (size_t)p->n_pos * 4 + 2 * 64 * 4 +
-                      (size_t)p->nq * p->nkv * 2 + 16;
+  const size_t smem = (size_t)4 * 64 * p->dh * 2 + 2 * 64 * 4 + 2 * 64 * 4 + (size_t)p->nq * p->nkv * 4 + 16;
   VTB_CHECK(smem <= 227 * 1024, -1, "vtb_attention_bwd: halo dK/dV tile needs %zu B of shared memory", smem);
-  const long blocks = groups * p->heads;
-  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_bwd: grid too large");
   static bool set64 = false, set32 = false;
-  if (p->dh == 64) {
-    if (!set64) { VTB_CUDA(cudaFuncSetAttribute(attn_halo_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set64 = true; }
-    attn_halo_dkv_kernel<64><<<(unsigned)blocks, 128, smem, stream>>>(*p, g);
-  } else {
-    if (!set32) { VTB_CUDA(cudaFuncSetAttribute(attn_halo_dkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set32 = true; }
-    attn_halo_dkv_kernel<32><<<(unsigned)blocks, 128, smem, stream>>>(*p, g);
-  }
+  if (p->dh == 64 && !set64) { VTB_CUDA(cudaFuncSetAttribute(attn_halo_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set64 = true; }
+  if (p->dh == 32 && !set32) { VTB_CUDA(cudaFuncSetAttribute(attn_halo_dkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set32 = true; }
+  // one resident wave, persistent over the blocks of a head (the bias tile is built once per CTA)
+  int per_sm = 1;
+  if (p->dh == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_halo_dkv_kernel<64>, 128, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_halo_dkv_kernel<32>, 128, smem);
+  if (per_sm < 1) per_sm = 1;
+  long nchunks = (long)vtb_num_sms() * per_sm / p->heads;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > groups) nchunks = groups;
+  const long blocks = nchunks * p->heads;
+  VTB_CHECK(blocks < (1L << 31) && groups < (1L << 31), -1, "vtb_attention_bwd: grid too large");
+  if (p->dh == 64) attn_halo_dkv_kernel<64><<<(unsigned)blocks, 128, smem, stream>>>(*p, g, (int)groups, (int)nchunks);
+  else attn_halo_dkv_kernel<32><<<(unsigned)blocks, 128, smem, stream>>>(*p, g, (int)groups, (int)nchunks);
   VTB_LAUNCH_CHECK();
   return 0;
 }
