@@ -213,6 +213,11 @@ def main():
     ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weight-arena", action="store_true",
+                    help="cast every weight to bf16 in its own launch (autocast's behaviour) instead of one multi-tensor "
+                         "cast per forward (vtb200.multi.enable_weight_arena)")
+    ap.add_argument("--no-optimizer-leg", action="store_true",
+                    help="skip the secondary `with_optimizer` measurement (clip_grad_norm_ + AdamW after every step)")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--nvtx-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
@@ -222,7 +227,8 @@ def main():
 
     import torch.distributed as dist
     from vtb200 import dist as vd
-    from vtb200 import ops
+    import loss as vloss
+    from vtb200 import multi, ops
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: a CUDA device is required (the sm_100a kernels are the only implementation)")
@@ -246,6 +252,12 @@ def main():
         for p in teacher.parameters():
             p.requires_grad_(False)
         center = torch.zeros(1, 65536, device=dev)
+        ema_dst = multi.TensorList([p.detach() for p in teacher.parameters()])
+        ema_src = multi.TensorList([p.detach() for p in model.parameters()])
+    if not args.no_weight_arena:  # one multi-tensor bf16 cast of all weights per forward instead of one launch per Linear
+        multi.enable_weight_arena(model)
+        if is_dino:
+            multi.enable_weight_arena(teacher)
     net, reducer = model, None
     use_graph = not args.no_graph and not args.nvtx_step
     if world > 1:
@@ -287,11 +299,9 @@ def main():
                 t_out = teacher(x[:2])
             loss = dino_loss_fn(net(x), t_out)
             loss.backward()
-            with torch.no_grad():  # EMA teacher (train_dino.py:257-261)
-                torch._foreach_mul_(list(teacher.parameters()), 0.996)
-                torch._foreach_add_(list(teacher.parameters()), list(model.parameters()), alpha=0.004)
+            multi.ema(ema_dst, ema_src, 0.996)  # EMA teacher (train_dino.py:257-261), one launch
             return loss
-        loss = torch.nn.functional.cross_entropy(net(x), y)
+        loss = vloss.cross_entropy(net(x), y)  # fused log-softmax + NLL + gradient (vtb_mix_loss)
         loss.backward()
         return loss
 
@@ -329,6 +339,7 @@ def main():
                 raise
             print(f"bench.py: CUDA-graph capture of the DINO step failed ({exc!r}); issuing eagerly", file=sys.stderr)
             graphed, use_graph = None, False
+    graph_grads = [p.grad for p in params] if use_graph else None  # the graph's own (address-stable) gradient buffers
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
@@ -367,6 +378,9 @@ def main():
     if use_graph:
         launches = launches_per_step * args.steps
     prof, ops.PROFILE = ops.PROFILE, None
+    if graph_grads is not None and not (reducer is not None and reducer.attached):
+        for p, g in zip(params, graph_grads):  # the eager pass re-created .grad; replays write the captured buffers
+            p.grad = g
     gemm = [(n, f, a.elapsed_time(b), nb) for n, f, a, b, nb in prof if n.startswith("gemm_")]
     gemm_ms = sum(t for _, _, t, _ in gemm)
     gemm_flops = sum(f for _, f, _, _ in gemm)
@@ -468,6 +482,41 @@ def main():
         e2e = {"value": world * B / (ms2 * 1e-3), "unit": "images/s", "ms_per_step": ms2,
                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8, "d2h_bytes_per_step": 4}
 
+    # ---------------------------------------------------------------- secondary: the same step + optimizer (§8d "also
+    # reported included"): clip_grad_norm_ (train.py:294) + AdamW (config/swin-transformer-s.conf:39-42), both multi-tensor
+    with_opt = None
+    if not args.no_optimizer_leg and not is_dino:
+        import optimizer as vopt
+        import train_util as vtu
+
+        def wd_skip(name, p):  # factory.py:25-39
+            return p.ndim == 1 or any(k in name for k in ("bias", "cls", "norm", "bn", "gain"))
+
+        groups, _ = vtu.add_weight_decay(model.named_parameters(), 0.05, wd_skip)
+        opt = vopt.AdamW(list(groups), lr=2.5e-4)
+
+        def opt_step():
+            loss = step(x_dev, y_dev)
+            vopt.clip_grad_norm_(params, 5.0, defer_to=opt)
+            opt.step()
+            return loss
+
+        l2 = ops.LAUNCHES
+        opt_step()
+        opt_launches = ops.LAUNCHES - l2 - (0 if use_graph else launches_per_step)
+        opt_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            opt_step()
+        e1.record()
+        barrier()
+        ms3 = vd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        with_opt = {"value": world * B / (ms3 * 1e-3), "unit": "images/s", "ms_per_step": ms3,
+                    "optimizer_ms_per_step": ms3 - ms, "optimizer_launches_per_step": opt_launches,
+                    "includes": "fwd+bwd step + clip_grad_norm_(5.0) folded into AdamW(lr 2.5e-4, wd 0.05 / no-decay "
+                                "groups): vtb_mt_grad_norm + vtb_mt_adamw"}
+
     # ---------------------------------------------------------------- CPU baseline (oracle port, bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -492,8 +541,10 @@ def main():
                            "l2": "inputs_exceed_l2 (154 MB batch + multi-GB activations per step >> 126 MB L2)",
                            "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric",
                            "execution": "CUDA graph replay of the captured step" if use_graph else "eager launches",
+                           "weight_cast": "per Linear" if args.no_weight_arena else "one multi-tensor launch per forward",
                            "host_issue_ms_per_step": host_ms},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "with_optimizer": with_opt}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -232,6 +232,78 @@ int vtb_mean_rows_bwd(const float* dy, int32_t groups, int32_t n, int32_t cols, 
 int vtb_dino_loss(const float* student, const float* teacher, const float* center, int32_t n_crops, int32_t batch,
                   int32_t dim, float t_student, float t_teacher, float* loss, float* dstudent, vtb_stream_t stream);
 
+/* DINO projection head (vit.py:206-262).  One warp per row.
+ *   l2norm:      y = bf16(x / max(||x||_2, eps))  (F.normalize, vit.py:259; eps 1e-12), inv[r] = 1 / max(||x_r||, eps)
+ *                dx = inv (dy - y (y . dy))
+ *   weight_norm: w = bf16(v * g / ||v||_row)       (nn.utils.weight_norm of the last Linear, vit.py:244-248; g is [rows])
+ *                dg = (dW . v) inv;  dv = g inv (dW - v (dW . v) inv^2)          (dg may be NULL: norm_last_layer)
+ * Both emit the bf16 GEMM operand directly; x, v, dy, dW, dx, dv f32 [rows, cols] contiguous.
+ *   gelu:        y = x Phi(x) (exact erf form, nn.GELU() vit.py:228,236), f32 and/or bf16 output; dx = dy (Phi + x phi). */
+int vtb_l2norm_fwd(const float* x, int64_t rows, int32_t cols, float eps, void* y_bf16, float* inv, vtb_stream_t stream);
+int vtb_l2norm_bwd(const float* dy, const float* x, const float* inv, int64_t rows, int32_t cols, float* dx,
+                   vtb_stream_t stream);
+int vtb_weight_norm_fwd(const float* v, const float* g, int64_t rows, int32_t cols, void* w_bf16, float* inv,
+                        vtb_stream_t stream);
+int vtb_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv, int64_t rows, int32_t cols,
+                        float* dv, float* dg, vtb_stream_t stream);
+int vtb_gelu_fwd(const float* x, float* y, void* y_bf16, int64_t n, vtb_stream_t stream);
+int vtb_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, vtb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-tensor step-side kernels: the per-parameter loops of the training step restated as ONE
+ * launch over a tensor list.  A list is given as HOST arrays of DEVICE pointers + element counts; the library packs
+ * them into kernel parameters (no device-side table, nothing allocated) and splits lists longer than
+ * VTB_MT_MAX_TENSORS into several launches.  All tensors f32 contiguous unless stated.  Scalars that the reference
+ * holds on the device (clip coefficient) stay on the device: no host synchronisation anywhere.
+ * ---------------------------------------------------------------------------------------------- */
+#define VTB_MT_MAX_TENSORS 256
+#define VTB_MT_CHUNK 8192 /* elements one CTA streams */
+/* Number of CTAs (= partial sums) vtb_mt_sumsq uses for this list: sizes its `partials` workspace. */
+int64_t vtb_mt_num_chunks(const int64_t* numel, int32_t n);
+/* dst[i] = bf16(src[i]) for every tensor of the list (autocast's per-weight casts, train.py:273, in one launch). */
+int vtb_mt_cast_f32_bf16(const void* const* src, void* const* dst, const int64_t* numel, int32_t n,
+                         vtb_stream_t stream);
+/* dst = dst*decay + src*(1-decay): train_util.py:70-84 (`accumulate`) and the DINO teacher update train_dino.py:257-261. */
+int vtb_mt_ema(void* const* dst, const void* const* src, const int64_t* numel, int32_t n, double decay,
+               vtb_stream_t stream);
+/* Global gradient norm + clip coefficient (torch.nn.utils.clip_grad_norm_, train.py:294 / train_dino.py:243):
+ *   out[0] = sqrt(sum of squares of every element), out[1] = min(1, max_norm / (out[0] + 1e-6)).
+ * partials: f32 workspace of vtb_mt_num_chunks() floats.  Deterministic (fixed summation order). */
+int vtb_mt_grad_norm(const void* const* grad, const int64_t* numel, int32_t n, float max_norm, float* partials,
+                     float* out, vtb_stream_t stream);
+/* x *= *scale (device scalar; the clip coefficient of vtb_mt_grad_norm).  Tensors are left untouched when *scale == 1. */
+int vtb_mt_scale(void* const* x, const int64_t* numel, int32_t n, const float* scale, vtb_stream_t stream);
+/* Adaptive gradient clipping, optimizer.py:12-26: per unit (row 0-slice of an ndim>1 tensor, the whole tensor otherwise)
+ *   max_norm = max(||p_unit||, eps) * clipping;  g_unit *= max_norm / max(||g_unit||, 1e-6)  if ||g_unit|| >= max_norm.
+ * units[i] = number of units of tensor i (shape[0] or 1); numel[i] % units[i] == 0. */
+int vtb_mt_agc(const void* const* param, void* const* grad, const int64_t* numel, const int64_t* units, int32_t n,
+               float clipping, float eps, vtb_stream_t stream);
+/* One AdamW step (torch.optim.AdamW, the `adamw` optimizer of config/swin-transformer-s.conf:39-42 and
+ * config/dino_deit-s-16.conf:52-55) over a parameter group:
+ *   g' = g * (*grad_scale)            (grad_scale NULL => 1; the clip coefficient, folding clip_grad_norm_'s pass in)
+ *   p *= 1 - lr*weight_decay;  m = m + (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2
+ *   p -= (lr / (1-beta1^step)) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)
+ * p_bf16 (may be NULL, entries may be NULL): bf16 copy of the updated parameter written in the same pass (the operand
+ * copy the next forward would otherwise cast). */
+int vtb_mt_adamw(void* const* param, const void* const* grad, void* const* exp_avg, void* const* exp_avg_sq,
+                 void* const* p_bf16, const int64_t* numel, int32_t n, double lr, double beta1, double beta2,
+                 double eps, double weight_decay, int64_t step, const float* grad_scale, vtb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused MixLoss + accuracy (loss.py:53-86, train_util.py:53-67; the loss/metric of train.py:273-281):
+ *   logp = log_softmax(logits);  t = inter*T(target1) + (1-inter)*T(target2),  T(c) = eps/n + (1-eps)[k == c]
+ *   loss[0] += sum_rows sum_k t_k (log t_k - logp_k) * loss_scale          (KL, 0 log 0 = 0; loss_scale = 1/B for "mean")
+ *   dlogits = (softmax(logits) - t) * loss_scale                           (dlogits may be NULL)
+ *   row_loss[r] = sum_k t_k (log t_k - logp_k)                              (reduction "none"; row_loss may be NULL)
+ *   correct[0] += #rows whose target1 logit is the maximum, correct[1] += #rows with it among the `topk` largest
+ *   (correct NULL ok; with loss, row_loss and dlogits all NULL the call is `accuracy` alone)
+ * logits f32 [rows, n_class] with row stride ld, targets int64 (target2 NULL => target1), inter f32 [rows] (NULL => 1),
+ * loss f32 [1] (atomicAdd: zero it; may be NULL), correct int32 [2].
+ * ---------------------------------------------------------------------------------------------- */
+int vtb_mix_loss(const float* logits, int64_t ld, const int64_t* target1, const int64_t* target2, const float* inter,
+                 int32_t rows, int32_t n_class, double eps, float loss_scale, float* loss, float* row_loss,
+                 float* dlogits, int32_t* correct, int32_t topk, vtb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -615,3 +615,68 @@ def test_dino_loss_fused_vs_oracle(ops, B, K, n_crops):
     assert abs(out.item() - want.item()) < 2e-5 * max(1.0, abs(want.item()))
     want_center = center * 0.9 + teacher.sum(0, keepdim=True) / teacher.shape[0] * 0.1
     assert rel(mod.center, want_center) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- DINO head rows (a7)
+@pytest.mark.parametrize("rows,cols", [(37, 256), (5, 33), (1, 8), (300, 64)])
+def test_dino_head_row_kernels_vs_torch(ops, rows, cols):
+    """vtb_l2norm_*, vtb_weight_norm_*, vtb_gelu_* against F.normalize / nn.utils.weight_norm / nn.GELU in fp32 autograd."""
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = torch.randn(rows, cols, device="cuda", generator=g).requires_grad_()
+    dy = torch.randn(rows, cols, device="cuda", generator=g)
+    # L2 normalisation (vit.py:259); a zero row exercises the eps clamp
+    with torch.no_grad():
+        x[0].mul_(0.0 if rows > 1 else 1.0)
+    want = torch.nn.functional.normalize(x, dim=-1, p=2)
+    (dx_w,) = torch.autograd.grad(want, x, dy)
+    yb, inv = ops.l2norm_fwd(x.detach())
+    sl = slice(1, None) if rows > 1 else slice(None)
+    assert rel(yb.float(), want.detach()) < 3e-3 and (rows == 1 or not yb[0].any())
+    dx = ops.l2norm_bwd(dy, x.detach(), inv)
+    assert rel(dx[sl], dx_w[sl]) < 1e-5
+    # weight norm (vit.py:244-248)
+    v = torch.randn(rows, cols, device="cuda", generator=g).requires_grad_()
+    gg = (torch.rand(rows, 1, device="cuda", generator=g) + 0.5).requires_grad_()
+    w_want = v * (gg / v.norm(dim=1, keepdim=True))
+    dv_w, dg_w = torch.autograd.grad(w_want, (v, gg), dy)
+    wb, inv_w = ops.weight_norm_fwd(v.detach(), gg.detach())
+    assert rel(wb.float(), w_want.detach()) < 3e-3
+    dv, dg = ops.weight_norm_bwd(dy, v.detach(), gg.detach(), inv_w)
+    assert dg.shape == gg.shape and rel(dv, dv_w) < 1e-5 and rel(dg, dg_w) < 1e-5
+    assert ops.weight_norm_bwd(dy, v.detach(), gg.detach(), inv_w, want_dg=False)[1] is None
+    # GELU (exact)
+    u = (3 * torch.randn(rows, cols, device="cuda", generator=g)).requires_grad_()
+    a_want = torch.nn.functional.gelu(u)
+    (du_w,) = torch.autograd.grad(a_want, u, dy)
+    ab, a = ops.gelu_fwd(u.detach(), want_f32=True)
+    assert rel(a, a_want.detach()) < 1e-6 and torch.equal(ab, a.to(torch.bfloat16))
+    assert rel(ops.gelu_bwd(u.detach(), dy), du_w) < 1e-5
+
+
+def test_dino_head_module_vs_oracle(ops):
+    """DINOHead forward + every gradient (vit.py:206-262) against the oracle restatement in fp32 autograd."""
+    from models.dino import DINOHead
+    from oracle import restate as R
+
+    torch.manual_seed(5)
+    head = DINOHead(64, 1024, norm_last_layer=False, depth=3, dim_ff=128, dim_bottleneck=32).cuda()
+    with torch.no_grad():
+        for p in head.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    x = torch.randn(3, 8, 64, device="cuda").requires_grad_()
+    dy = torch.randn(3, 8, 1024, device="cuda")
+    y = head(x)
+    y.backward(dy)
+    got = {n: p.grad.clone() for n, p in head.named_parameters()}
+    sd = {k: v.detach().clone().requires_grad_() for k, v in head.state_dict().items()}
+    xr = x.detach().clone().requires_grad_()
+    want = R.dino_head(sd, xr, pre="")
+    want.backward(dy)
+    assert y.shape == want.shape and rel(y, want) < 1e-2
+    assert rel(x.grad, xr.grad) < 3e-2
+    for n, gr in got.items():
+        assert rel(gr, sd[n].grad) < 3e-2, n
+    # norm_last_layer=True (config/dino_deit-s-16.conf keeps weight_g trainable = False): no gradient for it
+    head2 = DINOHead(64, 1024, norm_last_layer=True, depth=1, dim_bottleneck=32).cuda()
+    head2(x.detach()).sum().backward()
+    assert head2.last.weight_g.grad is None and head2.last.weight_v.grad is not None

@@ -1,0 +1,464 @@
+"""Step-side multi-tensor kernels: EMA `accumulate`, clip_grad_norm_, adaptive_grad_clip, AdamW,
+MixLoss + accuracy, the multi-tensor weight cast.
+
+CPU: the numpy oracle (oracle/step_ops.py) against tests/golden/step_ops.pt — outputs of the REFERENCE's own functions
+(optimizer.py:12-26, train_util.py:53-84, loss.py:53-86) and of torch.optim.AdamW / nn.utils.clip_grad_norm_, written by
+oracle/make_step_golden.py — and, when /root/reference is present, the drop-in host helpers against the reference's.
+GPU: the CUDA kernels, called through the C-ABI, against the same golden vectors and against the oracle on ragged lists.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def np_list(ts):
+    return [t.numpy() for t in ts]
+
+
+@pytest.fixture(scope="module")
+def G():
+    return load_golden("step_ops")
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs golden
+def test_oracle_ema_matches_reference(G):
+    from oracle import step_ops as S
+
+    for got, want in zip(S.ema(np_list(G["ema_dst"]), np_list(G["ema_src"]), G["ema_decay"]), G["ema_out"]):
+        assert np.abs(got - want.numpy()).max() <= 1.2e-7 * max(1.0, np.abs(want.numpy()).max())
+
+
+def test_oracle_clip_grad_norm_matches_torch(G):
+    from oracle import step_ops as S
+
+    for tag in ("clip", "noclip"):
+        got, total = S.clip_grad_norm(np_list(G["clip_grads"]), G[f"{tag}_max_norm"])
+        assert abs(float(total) - G[f"{tag}_total"].item()) < 1e-5 * G[f"{tag}_total"].item()
+        for a, b in zip(got, G[f"{tag}_out"]):
+            assert rel(a, b) < 1e-6
+
+
+def test_oracle_agc_matches_reference(G):
+    from oracle import step_ops as S
+
+    got = S.adaptive_grad_clip(np_list(G["agc_params"]), np_list(G["agc_grads"]))
+    changed = 0
+    for a, b, g in zip(got, G["agc_out"], G["agc_grads"]):
+        assert rel(a, b) < 1e-6
+        changed += int(not torch.equal(b, g))
+    assert changed >= 3  # the fixture really clips
+    assert torch.equal(G["agc_out"][0][2], G["agc_grads"][0][2])  # ... and leaves the small unit alone
+
+
+def test_oracle_adamw_matches_torch(G):
+    from oracle import step_ops as S
+
+    hp = G["adamw_hp"]
+    ps = np_list(G["adamw_params"])
+    ms = [np.zeros_like(p) for p in ps]
+    vs = [np.zeros_like(p) for p in ps]
+    for step in range(3):
+        for i, g in enumerate(np_list(G["adamw_grads"][step])):
+            ps[i], ms[i], vs[i] = S.adamw_step(ps[i], g, ms[i], vs[i], lr=hp["lr"], beta1=hp["betas"][0],
+                                               beta2=hp["betas"][1], eps=hp["eps"], weight_decay=G["adamw_wd"][i],
+                                               step=step + 1)
+        for a, b in zip(ps, G["adamw_out"][step]):
+            assert rel(a, b) < 1e-6
+    for a, b in zip(ms, G["adamw_exp_avg"]):
+        assert rel(a, b) < 1e-6
+    for a, b in zip(vs, G["adamw_exp_avg_sq"]):
+        assert rel(a, b) < 1e-6
+
+
+def test_oracle_mix_loss_and_accuracy_match_reference(G):
+    from oracle import step_ops as S
+
+    x, t1, t2, w = G["mix_logits"].numpy(), G["mix_t1"].numpy(), G["mix_t2"].numpy(), G["mix_inter"].numpy()
+    for eps in (0.1, 0.0):
+        for red in ("mean", "none", "sum"):
+            loss, grad = S.mix_loss(x, t1, t2, w, eps, red)
+            assert rel(loss, G[f"mix_{eps}_{red}_loss"]) < 2e-6, (eps, red)
+            assert rel(grad, G[f"mix_{eps}_{red}_grad"]) < 2e-6, (eps, red)
+    assert S.accuracy(x, t1, (1, 5)) == pytest.approx([t.item() for t in G["acc_1_5"]])
+    assert S.accuracy(x, t1, (1, 3, 5)) == pytest.approx([t.item() for t in G["acc_1_3_5"]])
+
+
+# ------------------------------------------------------------------------------------------------ host helpers
+def test_train_util_host_helpers(G):
+    import train_util as T
+
+    assert T.cosine_schedule(1.0, 0.1, 12, warmup=4, warmup_start=0.0) == pytest.approx(G["cosine"], abs=0)
+    assert T.cosine_schedule(1.0, 0.1, 5) == pytest.approx(
+        [0.1 + 0.45 * (1 + math.cos(math.pi * i / 5)) for i in range(5)], rel=1e-6)
+    assert T.cosine_schedule(1.0, 0.1, 3, warmup=3) == pytest.approx([0.0, 0.5, 1.0])
+    m = T.Meter()
+    m.update(2.0, 3)
+    m.update(4.0, 1)
+    assert (m.val, m.sum, m.count, m.avg) == (4.0, 10.0, 4, 2.5)
+
+    net = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.LayerNorm(4))
+    net[1].weight.requires_grad_(False)
+    groups, names = T.add_weight_decay(net.named_parameters(), 0.05, lambda n, p: p.ndim == 1)
+    assert names == (["0.bias", "1.bias"], ["0.weight"])
+    assert groups[0]["weight_decay"] == 0.0 and groups[0]["no_decay"] is True and groups[1]["weight_decay"] == 0.05
+    assert [tuple(p.shape) for p in groups[1]["params"]] == [(4, 3)]
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Linear(2, 2)
+            self.last_layer = torch.nn.Linear(2, 2)
+
+    net = Net()
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    T.cancel_last_layer_grad(1, net, 1)
+    assert all(p.grad is not None for p in net.parameters())
+    T.cancel_last_layer_grad(0, net, 1)
+    assert net.last_layer.weight.grad is None and net.body.weight.grad is not None
+
+
+def test_host_modules_mirror_the_reference_api():
+    """Same public names and call signatures as the reference's optimizer.py / train_util.py / loss.MixLoss."""
+    import inspect
+
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (build container only)")
+    import loss as L
+    import optimizer as O
+    import train_util as T
+
+    ref_o, ref_t = ref_loader.load_reference_module("optimizer"), ref_loader.load_reference_module("train_util")
+    ref_l = ref_loader.load_reference_module("loss")
+    for ours, ref, names in ((O, ref_o, ["adaptive_grad_clip"]),
+                             (T, ref_t, ["cosine_schedule", "cancel_last_layer_grad", "accuracy", "accumulate",
+                                         "add_weight_decay"])):
+        for n in names:
+            a = inspect.signature(inspect.unwrap(getattr(ours, n)))
+            b = inspect.signature(inspect.unwrap(getattr(ref, n)))
+            assert list(a.parameters) == list(b.parameters), n
+            assert [p.default for p in a.parameters.values()] == [p.default for p in b.parameters.values()], n
+    assert inspect.signature(L.MixLoss.__init__) == inspect.signature(ref_l.MixLoss.__init__)
+    assert list(inspect.signature(L.MixLoss.forward).parameters) == list(
+        inspect.signature(ref_l.MixLoss.forward).parameters)
+    assert set(vars(T.Meter())) == set(vars(ref_t.Meter()))
+
+
+def test_adamw_keeps_the_torch_optimizer_surface():
+    """Constructor defaults, param_groups and hyper-parameter validation of torch.optim.AdamW (no launch involved)."""
+    import optimizer as O
+
+    w = torch.nn.Parameter(torch.zeros(3, 3))
+    b = torch.nn.Parameter(torch.zeros(3))
+    ours = O.AdamW([{"params": [b], "weight_decay": 0.0, "no_decay": True}, {"params": [w]}], lr=2.5e-4)
+    ref = torch.optim.AdamW([{"params": [b], "weight_decay": 0.0, "no_decay": True}, {"params": [w]}], lr=2.5e-4)
+    for go, gr in zip(ours.param_groups, ref.param_groups):
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            assert go[k] == gr[k]
+    assert ours.param_groups[0]["no_decay"] is True
+    with pytest.raises(NotImplementedError):
+        O.AdamW([w], amsgrad=True)
+    with pytest.raises(ValueError):
+        O.AdamW([w], lr=-1.0)
+    ours.step()  # no gradients anywhere: nothing to launch, no state
+    assert len(ours.state) == 0
+
+
+# ------------------------------------------------------------------------------------------------ CUDA vs golden / oracle
+def cuda_list(ts):
+    return [t.clone().cuda() for t in ts]
+
+
+RAGGED = [1, 3, 4, 8191, 8192, 8193, 5, 0, 20000, 7]
+
+
+def ragged(seed, n_rep=1, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(n, generator=g) * scale for n in RAGGED * n_rep]
+
+
+@pytest.mark.gpu
+def test_mt_ema_golden_and_ragged(G):
+    from oracle import step_ops as S
+    from vtb200 import multi
+
+    dst = cuda_list(G["ema_dst"])
+    multi.ema(dst, cuda_list(G["ema_src"]), G["ema_decay"])
+    for a, b in zip(dst, G["ema_out"]):
+        assert (a.cpu() - b).abs().max() <= 1.2e-7 * max(1.0, b.abs().max().item())
+    # 300 tensors (> one parameter pack), sizes around the chunk boundary, an empty tensor, unaligned views
+    d, s = ragged(1, 30), ragged(2, 30)
+    want = S.ema(np_list(d), np_list(s), 0.9)
+    base_d = [torch.zeros(t.numel() + 1).cuda() for t in d]
+    dv = [b[1:] for b in base_d]  # 4-byte aligned only: the scalar path
+    for v, t in zip(dv, d):
+        v.copy_(t)
+    multi.ema(dv, cuda_list(s), 0.9)
+    for a, b in zip(dv, want):
+        assert np.abs(a.cpu().numpy() - b).max() <= 1.2e-7 * max(1.0, np.abs(b).max(initial=0.0))
+
+
+@pytest.mark.gpu
+def test_mt_cast_ragged():
+    from vtb200 import multi
+
+    src = cuda_list(ragged(3, 30))
+    dst = [torch.empty(t.numel(), dtype=torch.bfloat16, device="cuda") for t in src]
+    multi.cast_bf16(src, dst)
+    for a, b in zip(dst, src):
+        assert torch.equal(a, b.to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        multi.cast_bf16(src[:2], dst[:3])
+
+
+@pytest.mark.gpu
+def test_mt_clip_grad_norm_golden_and_ragged(G):
+    import optimizer as O
+    from oracle import step_ops as S
+
+    for tag in ("clip", "noclip"):
+        ps = [torch.nn.Parameter(torch.zeros_like(g).cuda()) for g in G["clip_grads"]]
+        for p, g in zip(ps, G["clip_grads"]):
+            p.grad = g.clone().cuda()
+        total = O.clip_grad_norm_(ps, G[f"{tag}_max_norm"])
+        assert abs(total.item() - G[f"{tag}_total"].item()) < 1e-6 * G[f"{tag}_total"].item()
+        for p, b in zip(ps, G[f"{tag}_out"]):
+            assert rel(p.grad, b) < 1e-6
+    gs = ragged(4, 30)
+    want, total = S.clip_grad_norm(np_list(gs), 2.0)
+    ps = [torch.nn.Parameter(torch.zeros_like(g).cuda()) for g in gs]
+    for p, g in zip(ps, gs):
+        p.grad = g.clone().cuda()
+    got_total = O.clip_grad_norm_(ps, 2.0)
+    assert abs(got_total.item() - float(total)) < 1e-6 * float(total)
+    for p, b in zip(ps, want):
+        assert p.grad.numel() == 0 or rel(p.grad, b) < 1e-6
+    # deterministic: same list, same bits
+    assert O.clip_grad_norm_(ps, 1e9).item() == O.clip_grad_norm_(ps, 1e9).item()
+
+
+@pytest.mark.gpu
+def test_mt_agc_golden_and_wide_units(G):
+    import optimizer as O
+    from oracle import step_ops as S
+
+    ps = [torch.nn.Parameter(p.clone().cuda()) for p in G["agc_params"]]
+    for p, g in zip(ps, G["agc_grads"]):
+        p.grad = g.clone().cuda()
+    ps.append(torch.nn.Parameter(torch.ones(4, device="cuda")))  # no gradient: skipped (optimizer.py:18-19)
+    O.adaptive_grad_clip(ps, clipping=0.01, eps=1e-3)
+    for p, b in zip(ps, G["agc_out"]):
+        assert rel(p.grad, b) < 1e-6
+    assert torch.equal(ps[0].grad[2].cpu(), G["agc_grads"][0][2])
+    # transformer-sized units, odd widths (scalar path), a [1, N, D] position table (one unit), zero weights (eps floor)
+    g = torch.Generator().manual_seed(9)
+    shapes = [(300, 768), (5, 1001), (1, 197, 64), (64,), (6, 3, 4, 4)]
+    params = [torch.randn(s, generator=g) * 0.02 for s in shapes]
+    params[3].zero_()
+    grads = [torch.randn(s, generator=g) * (1e-3 if i % 2 else 1e-5) for i, s in enumerate(shapes)]
+    want = S.adaptive_grad_clip(np_list(params), np_list(grads), 0.02, 1e-3)
+    ps = [torch.nn.Parameter(p.clone().cuda()) for p in params]
+    for p, gr in zip(ps, grads):
+        p.grad = gr.clone().cuda()
+    O.adaptive_grad_clip(ps, clipping=0.02, eps=1e-3)
+    for p, b in zip(ps, want):
+        assert rel(p.grad, b) < 1e-6
+
+
+@pytest.mark.gpu
+def test_mt_adamw_golden_three_steps(G):
+    import optimizer as O
+
+    hp = G["adamw_hp"]
+    ps = [torch.nn.Parameter(p.clone().cuda()) for p in G["adamw_params"]]
+    opt = O.AdamW([{"params": ps[:3], "weight_decay": 0.05}, {"params": ps[3:], "weight_decay": 0.0}], **hp)
+    for step in range(3):
+        for p, g in zip(ps, G["adamw_grads"][step]):
+            p.grad = g.clone().cuda()
+        opt.step()
+        for p, b in zip(ps, G["adamw_out"][step]):
+            assert rel(p, b) < 1e-6, step
+    for p, m, v in zip(ps, G["adamw_exp_avg"], G["adamw_exp_avg_sq"]):
+        assert rel(opt.state[p]["exp_avg"], m) < 1e-6 and rel(opt.state[p]["exp_avg_sq"], v) < 1e-6
+        assert opt.state[p]["step"].item() == 3
+    # state_dict round trip into torch.optim.AdamW (same layout) and one more identical step on both
+    ref_ps = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.AdamW([{"params": ref_ps[:3], "weight_decay": 0.05}, {"params": ref_ps[3:], "weight_decay": 0.0}],
+                            foreach=False, **hp)
+    ref.load_state_dict(opt.state_dict())
+    for p, q in zip(ps, ref_ps):
+        g = torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel()))
+        p.grad, q.grad = g.cuda(), g.cuda()
+    opt.step()
+    ref.step()
+    for p, q in zip(ps, ref_ps):
+        assert rel(p, q) < 1e-6
+
+
+@pytest.mark.gpu
+def test_mt_adamw_ragged_with_deferred_clip_and_bf16_copy():
+    import optimizer as O
+    from oracle import step_ops as S
+    from vtb200 import multi
+
+    params, grads = ragged(5, 30, 0.1), ragged(6, 30)
+    hp = dict(lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-8, weight_decay=0.1)
+    _, total = S.clip_grad_norm(np_list(grads), 1.0)
+    coef = min(1.0, 1.0 / (float(total) + 1e-6))
+    ps = [torch.nn.Parameter(p.clone().cuda()) for p in params]
+    for p, g in zip(ps, grads):
+        p.grad = g.clone().cuda()
+    opt = O.AdamW(ps, lr=hp["lr"], betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    total_dev = O.clip_grad_norm_(ps, 1.0, defer_to=opt)
+    assert abs(total_dev.item() - float(total)) < 1e-6 * float(total)
+    assert all(torch.equal(p.grad.cpu(), g) for p, g in zip(ps, grads))  # gradients untouched: the scale is deferred
+    opt.step()
+    assert opt.grad_scale is None
+    for p, p0, g in zip(ps, params, grads):
+        if p0.numel() == 0:
+            continue
+        want, _, _ = S.adamw_step(p0.numpy(), g.numpy(), np.zeros_like(p0.numpy()), np.zeros_like(p0.numpy()), step=1,
+                                  grad_scale=coef, **hp)
+        assert rel(p, want) < 1e-6
+    # raw list call with bf16 copies (None holes allowed)
+    p2 = cuda_list(params[:4])
+    m2, v2 = [torch.zeros_like(p) for p in p2], [torch.zeros_like(p) for p in p2]
+    pb = [torch.empty(p.numel(), dtype=torch.bfloat16, device="cuda") if i != 1 else None for i, p in enumerate(p2)]
+    multi.adamw(p2, cuda_list(grads[:4]), m2, v2, step=1, bf16_out=pb, **hp)
+    for p, b in zip(p2, pb):
+        assert b is None or torch.equal(b, p.to(torch.bfloat16))
+
+
+@pytest.mark.gpu
+def test_mix_loss_and_accuracy_golden(G):
+    import loss as L
+    import train_util as T
+
+    t1, t2, w = G["mix_t1"].cuda(), G["mix_t2"].cuda(), G["mix_inter"].cuda()
+    for eps in (0.1, 0.0):
+        for red in ("mean", "none", "sum"):
+            x = G["mix_logits"].clone().cuda().requires_grad_()
+            out = L.MixLoss(eps=eps, reduction=red)(x, t1, t2, w)
+            assert out.shape == G[f"mix_{eps}_{red}_loss"].shape
+            assert rel(out, G[f"mix_{eps}_{red}_loss"]) < 2e-6, (eps, red)
+            out.sum().backward()
+            assert rel(x.grad, G[f"mix_{eps}_{red}_grad"]) < 2e-6, (eps, red)
+    x = G["mix_logits"].cuda()
+    assert [t.item() for t in T.accuracy(x, t1, topk=(1, 5))] == pytest.approx([t.item() for t in G["acc_1_5"]])
+    assert [t.item() for t in T.accuracy(x, t1, topk=(1, 3, 5))] == pytest.approx([t.item() for t in G["acc_1_3_5"]])
+    assert [t.item() for t in T.accuracy(x, t1)] == pytest.approx([G["acc_1_5"][0].item()])
+
+
+@pytest.mark.gpu
+def test_mix_loss_imagenet_shape_vs_oracle_and_grad_scaling():
+    """[256, 1000] logits (train.py:273-281 at the BASELINE batch), bf16 logits promoted like autocast does, a scaled
+    upstream gradient (loss / grad_accum, GradScaler), a Python-float interpolation."""
+    import loss as L
+    import train_util as T
+    from oracle import step_ops as S
+
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(256, 1000, generator=g) * 4
+    t1, t2 = torch.randint(0, 1000, (256,), generator=g), torch.randint(0, 1000, (256,), generator=g)
+    w = torch.rand(256, generator=g)
+    want, grad = S.mix_loss(x.numpy(), t1.numpy(), t2.numpy(), w.numpy(), 0.1, "mean")
+    xc = x.cuda().requires_grad_()
+    out = L.MixLoss(eps=0.1)(xc, t1.cuda(), t2.cuda(), w.cuda())
+    (out / 2 * 1024.0).backward()
+    assert abs(out.item() - want) < 2e-6 * want
+    assert rel(xc.grad, grad * 512.0) < 2e-6
+    assert [t.item() for t in T.accuracy(xc.detach(), t1.cuda(), (1, 5))] == pytest.approx(S.accuracy(x.numpy(), t1.numpy(), (1, 5)))
+    # cross entropy (train.py:155) = the same kernel with eps 0 and no partner
+    xe = x.cuda().requires_grad_()
+    ce = L.cross_entropy(xe, t1.cuda())
+    ce.backward()
+    xr = x.cuda().requires_grad_()
+    ce_ref = torch.nn.functional.cross_entropy(xr, t1.cuda())
+    ce_ref.backward()
+    assert abs(ce.item() - ce_ref.item()) < 2e-6 * ce_ref.item() and rel(xe.grad, xr.grad) < 2e-6
+    xb = x.to(torch.bfloat16)
+    want_b, _ = S.mix_loss(xb.float().numpy(), t1.numpy(), t2.numpy(), np.full(256, 0.3, np.float32), 0.1, "mean")
+    out_b = L.MixLoss(eps=0.1)(xb.cuda(), t1.cuda(), t2.cuda(), 0.3)
+    assert abs(out_b.item() - want_b) < 2e-6 * want_b
+
+
+@pytest.mark.gpu
+def test_accumulate_matches_reference_loop_on_a_model():
+    """train_util.accumulate on two ViT-Tiny drop-in models == the reference's per-parameter loop (train_util.py:76-77)."""
+    import train_util as T
+    from models.vit import VisionTransformer
+
+    torch.manual_seed(0)
+    a = VisionTransformer(None, 32, 16, 2, 64, 2, 128, 0.0, 0.0, 0.0, 0.0).cuda()
+    b = VisionTransformer(None, 32, 16, 2, 64, 2, 128, 0.0, 0.0, 0.0, 0.0).cuda()
+    with torch.no_grad():
+        for p in b.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+    want = {k: p.detach().clone().mul_(0.99).add_(dict(b.named_parameters())[k].detach(), alpha=1 - 0.99)
+            for k, p in a.named_parameters()}
+    T.accumulate(a, b, decay=0.99)
+    for k, p in a.named_parameters():
+        assert (p.detach() - want[k]).abs().max().item() <= 1.2e-7 * max(1.0, want[k].abs().max().item()), k
+    T.accumulate(a, b, 0)  # train.py:110: decay 0 copies
+    for k, p in a.named_parameters():
+        assert torch.equal(p.detach(), dict(b.named_parameters())[k].detach()), k
+
+
+@pytest.mark.gpu
+def test_weight_arena_matches_per_call_casts_and_tracks_updates():
+    """enable_weight_arena: same logits and gradients as the per-Linear casts, fewer launches, and weights rewritten
+    between forwards (optimizer step, multi-tensor EMA, load_state_dict) are picked up."""
+    import optimizer as O
+    import train_util as T
+    from models.vit import VisionTransformer
+    from vtb200 import multi, ops
+
+    torch.manual_seed(1)
+    net = VisionTransformer(torch.nn.Linear(64, 10), 32, 16, 2, 64, 2, 128, 0.0, 0.0, 0.0, 0.0).cuda()
+    x = torch.randn(4, 3, 32, 32, device="cuda")
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        n0 = ops.LAUNCHES
+        y = net(x)
+        y.square().sum().backward()
+        return y.detach().clone(), [p.grad.clone() for p in net.parameters()], ops.LAUNCHES - n0
+
+    y0, g0, l0 = run()
+    arena = multi.enable_weight_arena(net)
+    try:
+        y1, g1, l1 = run()
+        assert torch.equal(y0, y1) and all(torch.equal(a, b) for a, b in zip(g0, g1))
+        assert l1 < l0, (l0, l1)
+        # optimizer step through the library (invisible to torch's version counters), then through torch
+        opt = O.AdamW(net.parameters(), lr=1e-2)
+        opt.step()
+        y2, _, _ = run()
+        multi.disable_weight_arena(net)
+        y2_ref, _, _ = run()
+        assert torch.equal(y2, y2_ref) and not torch.equal(y2, y1)
+        arena = multi.enable_weight_arena(net)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.5)
+        # a sub-module called directly (no top-level forward => no refresh) must not see stale copies
+        blk = net.layers[0]
+        t = torch.randn(4, 5, 64, device="cuda")
+        z = blk(t)
+        multi.disable_weight_arena(net)
+        assert torch.equal(z, blk(t))
+    finally:
+        if "_vtb_weight_arena" in net.__dict__:
+            multi.disable_weight_arena(net)
+    assert ops.WEIGHT_LOOKUP is None

@@ -1,4 +1,5 @@
-// Fused DINO loss, forward + gradient in one launch (loss.py:119-142).
+// Fused DINO loss, forward + gradient in one launch (loss.py:119-142), and the row kernels of the
+// DINO projection head (vit.py:206-262): GELU, L2 normalisation, weight-norm reparametrisation.
 //
 //   q_iq  = softmax((teacher[iq] - center) / t_teacher)            iq in {0, 1} (the two global crops)
 //   loss  = mean over the pairs (iq, v != iq) and the images of   - sum_k q_iq[k] log_softmax(student[v] / t_student)[k]
@@ -132,7 +133,129 @@ dino_loss_kernel(const float* __restrict__ student, const float* __restrict__ te
   }
 }
 
+// ------------------------------------------------------------------------------------------------ DINO head (vit.py:206-262)
+// Row kernels, one warp per row.  l2norm: F.normalize(x, dim=-1) (vit.py:259) emitted as the bf16 GEMM operand of the
+// weight-normed last layer; weight_norm: w = v * g / ||v|| per output row (nn.utils.weight_norm, vit.py:244-248) emitted
+// as bf16 as well, so neither the normalised activations nor the 65 536 x 256 effective weight ever exist in fp32.
+constexpr int RN_WARPS = 8;
+
+template <bool WN>  // WN: scale by g[row] (weight norm); else plain L2 normalisation with eps clamp
+__global__ void __launch_bounds__(RN_WARPS * 32)
+rownorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long rows, int cols, float eps,
+                   bf16* __restrict__ y, float* __restrict__ inv_out) {
+  const long r = (long)blockIdx.x * RN_WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + r * cols;
+  float ss = 0.f;
+  for (int c = lane; c < cols; c += 32) ss = fmaf(xr[c], xr[c], ss);
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  if (lane == 0) inv_out[r] = inv;
+  const float sc = WN ? inv * __ldg(g + r) : inv;
+  for (int c = lane; c < cols; c += 32) y[r * cols + c] = __float2bfloat16(xr[c] * sc);
+}
+
+// l2norm bwd:      dx = inv (dy - y (y . dy)),  y = x inv
+// weight_norm bwd: dg = (dW . v) inv;  dv = g inv (dW - v (dW . v) inv^2)
+template <bool WN>
+__global__ void __launch_bounds__(RN_WARPS * 32)
+rownorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
+                   const float* __restrict__ inv_in, long rows, int cols, float* __restrict__ dx,
+                   float* __restrict__ dg) {
+  const long r = (long)blockIdx.x * RN_WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + r * cols;
+  const float* dr = dy + r * cols;
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot = fmaf(xr[c], dr[c], dot);
+  dot = warp_sum(dot);
+  const float inv = inv_in[r];
+  const float sc = WN ? inv * __ldg(g + r) : inv;
+  const float k = dot * inv * inv;
+  if (WN && dg && lane == 0) dg[r] = dot * inv;
+  for (int c = lane; c < cols; c += 32) dx[r * cols + c] = sc * (dr[c] - xr[c] * k);
+}
+
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, bf16* __restrict__ yb, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float o = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() (exact, vit.py:228)
+    if (y) y[i] = o;
+    if (yb) yb[i] = __float2bfloat16(o);
+  }
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+    dx[i] = dy[i] * (cdf + v * pdf);
+  }
+}
+
 }  // namespace
+
+extern "C" int vtb_l2norm_fwd(const float* x, int64_t rows, int32_t cols, float eps, void* y_bf16, float* inv,
+                              vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(x && y_bf16 && inv && rows >= 0 && cols > 0, -1, "vtb_l2norm_fwd: bad arguments");
+  if (rows == 0) return 0;
+  rownorm_fwd_kernel<false><<<(unsigned)((rows + RN_WARPS - 1) / RN_WARPS), RN_WARPS * 32, 0, stream>>>(
+      x, nullptr, rows, cols, eps, static_cast<bf16*>(y_bf16), inv);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_l2norm_bwd(const float* dy, const float* x, const float* inv, int64_t rows, int32_t cols, float* dx,
+                              vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(dy && x && inv && dx && rows >= 0 && cols > 0, -1, "vtb_l2norm_bwd: bad arguments");
+  if (rows == 0) return 0;
+  rownorm_bwd_kernel<false><<<(unsigned)((rows + RN_WARPS - 1) / RN_WARPS), RN_WARPS * 32, 0, stream>>>(
+      dy, x, nullptr, inv, rows, cols, dx, nullptr);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_weight_norm_fwd(const float* v, const float* g, int64_t rows, int32_t cols, void* w_bf16, float* inv,
+                                   vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(v && g && w_bf16 && inv && rows >= 0 && cols > 0, -1, "vtb_weight_norm_fwd: bad arguments");
+  if (rows == 0) return 0;
+  rownorm_fwd_kernel<true><<<(unsigned)((rows + RN_WARPS - 1) / RN_WARPS), RN_WARPS * 32, 0, stream>>>(
+      v, g, rows, cols, 0.f, static_cast<bf16*>(w_bf16), inv);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* inv, int64_t rows,
+                                   int32_t cols, float* dv, float* dg, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(dw && v && g && inv && dv && rows >= 0 && cols > 0, -1, "vtb_weight_norm_bwd: bad arguments");
+  if (rows == 0) return 0;
+  rownorm_bwd_kernel<true><<<(unsigned)((rows + RN_WARPS - 1) / RN_WARPS), RN_WARPS * 32, 0, stream>>>(
+      dw, v, g, inv, rows, cols, dv, dg);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_gelu_fwd(const float* x, float* y, void* y_bf16, int64_t n, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(x && (y || y_bf16) && n >= 0, -1, "vtb_gelu_fwd: bad arguments");
+  if (n == 0) return 0;
+  const long blocks = (n + 255) / 256;
+  gelu_fwd_kernel<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, stream>>>(x, y, static_cast<bf16*>(y_bf16), n);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(x && dy && dx && n >= 0, -1, "vtb_gelu_bwd: bad arguments");
+  if (n == 0) return 0;
+  const long blocks = (n + 255) / 256;
+  gelu_bwd_kernel<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, stream>>>(x, dy, dx, n);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int vtb_dino_loss(const float* student, const float* teacher, const float* center, int32_t n_crops,
                              int32_t batch, int32_t dim, float t_student, float t_teacher, float* loss,

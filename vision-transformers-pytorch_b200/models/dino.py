@@ -1,12 +1,12 @@
 """DINO projection head and the `dino` model factory — drop-in for vit.py:206-307 of the reference.
 
-DINOHead is a "next" row of the hot-path table: its Linears already run on the tcgen05 GEMM, while
-GELU, the L2 normalisation and the weight-norm reparametrisation are left to ATen for now."""
+DINOHead is a "next" row of the hot-path table: its Linears run on the tcgen05 GEMM, GELU, the L2
+normalisation and the weight-norm reparametrisation on row kernels that emit the bf16 GEMM operands directly
+(vtb_gelu_*, vtb_l2norm_*, vtb_weight_norm_*).  BatchNorm1d (use_bn=True; no reference config sets it) stays ATen."""
 from typing import Tuple, Union
 
 from pydantic import StrictBool, StrictFloat, StrictInt
 from torch import nn
-from torch.nn import functional as F
 
 from ._compat import config_model
 
@@ -37,14 +37,17 @@ class DINOHead(nn.Module):
         self.last.weight_g.requires_grad = not norm_last_layer
 
     def forward(self, input):
-        from vtb200.blocks import LinearFn
+        from vtb200.blocks import GeluFn, LinearFn, NormLinearFn
 
         out = input
         for m in ([self.mlp] if isinstance(self.mlp, nn.Linear) else self.mlp):
-            out = LinearFn.apply(out, m.weight, m.bias) if isinstance(m, nn.Linear) else m(out)
-        out = F.normalize(out, dim=-1, p=2)
-        v = self.last.weight_v
-        return LinearFn.apply(out, v * (self.last.weight_g / v.norm(dim=1, keepdim=True)), None)
+            if isinstance(m, nn.Linear):
+                out = LinearFn.apply(out, m.weight, m.bias)
+            elif isinstance(m, nn.GELU):
+                out = GeluFn.apply(out)
+            else:
+                out = m(out)
+        return NormLinearFn.apply(out, self.last.weight_v, self.last.weight_g)
 
 
 @config_model(name="dino", namespace="model", use_type=True)

@@ -384,6 +384,55 @@ class LinearFn(Function):
         return dx.view(*dy.shape[:-1], wb.shape[1]), dw, db
 
 
+class GeluFn(Function):
+    """nn.GELU() (exact erf form) of the DINO head MLP (vit.py:228,236)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return ops.gelu_fwd(x, want_f32=True)[1]
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd(x, _c(dy))
+
+
+class NormLinearFn(Function):
+    """The tail of DINOHead.forward (vit.py:259-260): y = normalize(x) @ (v * g / ||v||_row)^T.  Both operands are
+    emitted as bf16 by their row kernels (vtb_l2norm_fwd, vtb_weight_norm_fwd); the 65 536 x 256 effective weight and its
+    gradient chain (mul / div / norm over 67 MB each in the reference) are one pass forward and one pass backward."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, v, g):
+        shape = x.shape
+        x2 = _c(x).view(-1, shape[-1])
+        v, g = _c(v), _c(g)
+        xb, inv_x = ops.l2norm_fwd(x2)
+        wb, inv_w = ops.weight_norm_fwd(v, g)
+        y = ops.gemm(xb, wb, out_dtype=F32)
+        ctx.save_for_backward(x2, v, g, inv_x, inv_w)
+        ctx.stash = (xb, wb)
+        return y.view(*shape[:-1], v.shape[0])
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        x2, v, g, inv_x, inv_w = ctx.saved_tensors
+        xb, wb = ctx.stash
+        gb = ops.scale_cast_bf16(_c(dy).view(-1, v.shape[0]))
+        dx = dv = dg = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.l2norm_bwd(_dgrad(gb, wb, out_dtype=F32), x2, inv_x).view(*dy.shape[:-1], x2.shape[1])
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dv, dg = ops.weight_norm_bwd(_wgrad(gb, xb), v, g, inv_w, want_dg=ctx.needs_input_grad[2])
+        return dx, dv, dg
+
+
 class MeanRowsFn(Function):
     """[B, n, C] -> [B, C] mean over tokens (AdaptiveAvgPool2d(1)+Flatten, swin:281 / halo:223)."""
 

@@ -19,7 +19,9 @@ SYMBOLS = [
     "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_cast_f32_bf16",
     "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_scale_cast_colsum_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
     "vtb_patch_scatter", "vtb_transpose_hw", "vtb_dwconv3x3_fwd", "vtb_dwconv3x3_bwd", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
-    "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss",
+    "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss", "vtb_mt_num_chunks", "vtb_mt_cast_f32_bf16", "vtb_mt_ema",
+    "vtb_mt_grad_norm", "vtb_mt_scale", "vtb_mt_agc", "vtb_mt_adamw", "vtb_mix_loss", "vtb_l2norm_fwd", "vtb_l2norm_bwd",
+    "vtb_weight_norm_fwd", "vtb_weight_norm_bwd", "vtb_gelu_fwd", "vtb_gelu_bwd",
 ]
 
 
@@ -110,10 +112,26 @@ def load():
     lib.vtb_silu_fwd.argtypes = [vp, vp, i64, vp]
     lib.vtb_silu_bwd.argtypes = [vp, vp, vp, i64, vp]
     lib.vtb_dino_loss.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp]
+    f64 = C.c_double
+    lib.vtb_l2norm_fwd.argtypes = [vp, i64, i32, f32, vp, vp, vp]
+    lib.vtb_l2norm_bwd.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.vtb_weight_norm_fwd.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.vtb_weight_norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
+    lib.vtb_gelu_fwd.argtypes = [vp, vp, vp, i64, vp]
+    lib.vtb_gelu_bwd.argtypes = [vp, vp, vp, i64, vp]
+    lib.vtb_mt_num_chunks.argtypes = [vp, i32]
+    lib.vtb_mt_cast_f32_bf16.argtypes = [vp, vp, vp, i32, vp]
+    lib.vtb_mt_ema.argtypes = [vp, vp, vp, i32, f64, vp]
+    lib.vtb_mt_grad_norm.argtypes = [vp, vp, i32, f32, vp, vp, vp]
+    lib.vtb_mt_scale.argtypes = [vp, vp, i32, vp, vp]
+    lib.vtb_mt_agc.argtypes = [vp, vp, vp, vp, i32, f32, f32, vp]
+    lib.vtb_mt_adamw.argtypes = [vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, f64, f64, i64, vp, vp]
+    lib.vtb_mix_loss.argtypes = [vp, i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vtb_last_error",):
             fn.restype = i32
+    lib.vtb_mt_num_chunks.restype = i64
     _lib = lib
     return lib
 

@@ -331,10 +331,21 @@ def attention_bwd(spec, q, k, v, o, lse, dout, dq, dk, dv, drel_bias=None, dkv_f
     _count(2)
 
 
+# Set by vtb200.multi.enable_weight_arena: maps an f32 weight to its bf16 copy in a model's arena (refreshed by one
+# multi-tensor cast per top-level forward) or None.  WEIGHT_EPOCH is bumped by every library call that rewrites
+# parameters in place (multi-tensor EMA / AdamW), which torch's version counters cannot see.
+WEIGHT_LOOKUP = None
+WEIGHT_EPOCH = 0
+
+
 def cast_bf16(src):
     lib = _l.get()
     if src.dtype != F32 or not src.is_contiguous():
         raise ValueError("vtb200.cast_bf16: contiguous f32 expected")
+    if WEIGHT_LOOKUP is not None:
+        hit = WEIGHT_LOOKUP(src)
+        if hit is not None:
+            return hit
     dst = torch.empty(src.shape, dtype=BF16, device=src.device)
     if src.numel():
         with _prof("cast_f32_bf16"):
@@ -537,3 +548,85 @@ def dino_loss(student, teacher, center, n_crops, t_student, t_teacher, want_grad
                                    float(t_teacher), _p(loss), _p(dstudent), _stream()), lib)
     _count()
     return loss, dstudent
+
+
+# ------------------------------------------------------------------------------------------------ DINO head rows
+def l2norm_fwd(x, eps=1e-12):
+    """F.normalize(x, dim=-1) as the bf16 GEMM operand.  x f32 [rows, cols] -> (y bf16 [rows, cols], inv f32 [rows])."""
+    lib = _l.get()
+    _chk2d(x, F32, "l2norm_fwd(x)")
+    if not x.is_contiguous():
+        raise ValueError("vtb200.l2norm_fwd: contiguous rows expected")
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    inv = torch.empty(x.shape[0], dtype=F32, device=x.device)
+    with _prof("l2norm_fwd", 0.0, 6.0 * x.numel()):
+        _l.check(lib.vtb_l2norm_fwd(_p(x), x.shape[0], x.shape[1], float(eps), _p(y), _p(inv), _stream()), lib)
+    _count()
+    return y, inv
+
+
+def l2norm_bwd(dy, x, inv):
+    lib = _l.get()
+    for t, nm in ((dy, "dy"), (x, "x")):
+        _chk2d(t, F32, f"l2norm_bwd({nm})")
+        if not t.is_contiguous():
+            raise ValueError("vtb200.l2norm_bwd: contiguous rows expected")
+    dx = torch.empty_like(x)
+    with _prof("l2norm_bwd", 0.0, 12.0 * x.numel()):
+        _l.check(lib.vtb_l2norm_bwd(_p(dy), _p(x), _p(inv), x.shape[0], x.shape[1], _p(dx), _stream()), lib)
+    _count()
+    return dx
+
+
+def weight_norm_fwd(v, g):
+    """nn.utils.weight_norm (dim=0): w = v * g / ||v||_row, emitted as bf16.  v f32 [rows, cols], g f32 with `rows`
+    elements -> (w bf16 [rows, cols], inv f32 [rows])."""
+    lib = _l.get()
+    _chk2d(v, F32, "weight_norm_fwd(v)")
+    if not v.is_contiguous() or g.dtype != F32 or g.numel() != v.shape[0] or not g.is_contiguous():
+        raise ValueError("vtb200.weight_norm_fwd: v [rows, cols] and g [rows(, 1)] contiguous f32 expected")
+    w = torch.empty(v.shape, dtype=BF16, device=v.device)
+    inv = torch.empty(v.shape[0], dtype=F32, device=v.device)
+    with _prof("weight_norm_fwd", 0.0, 6.0 * v.numel()):
+        _l.check(lib.vtb_weight_norm_fwd(_p(v), _p(g), v.shape[0], v.shape[1], _p(w), _p(inv), _stream()), lib)
+    _count()
+    return w, inv
+
+
+def weight_norm_bwd(dw, v, g, inv, want_dg=True):
+    lib = _l.get()
+    for t, nm in ((dw, "dw"), (v, "v")):
+        _chk2d(t, F32, f"weight_norm_bwd({nm})")
+        if not t.is_contiguous():
+            raise ValueError("vtb200.weight_norm_bwd: contiguous rows expected")
+    dv = torch.empty_like(v)
+    dg = torch.empty(g.shape, dtype=F32, device=v.device) if want_dg else None
+    with _prof("weight_norm_bwd", 0.0, 12.0 * v.numel()):
+        _l.check(lib.vtb_weight_norm_bwd(_p(dw), _p(v), _p(g), _p(inv), v.shape[0], v.shape[1], _p(dv), _p(dg),
+                                         _stream()), lib)
+    _count()
+    return dv, dg
+
+
+def gelu_fwd(x, want_f32=False):
+    """nn.GELU() (exact): x f32 -> bf16 copy of the activation (the next Linear's operand) and, if asked, f32."""
+    lib = _l.get()
+    if x.dtype != F32 or not x.is_contiguous():
+        raise ValueError("vtb200.gelu_fwd: contiguous f32 expected")
+    yb = torch.empty(x.shape, dtype=BF16, device=x.device)
+    y = torch.empty_like(x) if want_f32 else None
+    with _prof("gelu_fwd", 0.0, (10.0 if want_f32 else 6.0) * x.numel()):
+        _l.check(lib.vtb_gelu_fwd(_p(x), _p(y), _p(yb), x.numel(), _stream()), lib)
+    _count()
+    return yb, y
+
+
+def gelu_bwd(x, dy):
+    lib = _l.get()
+    if x.dtype != F32 or dy.dtype != F32 or not x.is_contiguous() or not dy.is_contiguous() or x.shape != dy.shape:
+        raise ValueError("vtb200.gelu_bwd: contiguous f32 tensors of one shape expected")
+    dx = torch.empty_like(x)
+    with _prof("gelu_bwd", 0.0, 12.0 * x.numel()):
+        _l.check(lib.vtb_gelu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _stream()), lib)
+    _count()
+    return dx
