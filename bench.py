@@ -213,6 +213,9 @@ def main():
     ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-u8", action="store_true",
+                    help="extra leg (opt-in): the step fed through the device input path — pinned uint8 HWC batches + the "
+                         "mixup / cutmix / erasing table -> vtb_input_batch -> step (SURVEY 8f rank 4)")
     ap.add_argument("--no-weight-arena", action="store_true",
                     help="cast every weight to bf16 in its own launch (autocast's behaviour) instead of one multi-tensor "
                          "cast per forward (vtb200.multi.enable_weight_arena)")
@@ -482,6 +485,39 @@ def main():
         e2e = {"value": world * B / (ms2 * 1e-3), "unit": "images/s", "ms_per_step": ms2,
                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8, "d2h_bytes_per_step": 4}
 
+    # ---------------------------------------------------------------- opt-in: e2e through the device input path
+    e2e_u8 = None
+    if args.e2e_u8 and not is_dino:
+        import random as pyrandom
+
+        import device_input as vin
+
+        sampler = vin.MixSampler(0.8, 1.0, 0.25, mix_before_aug=True, rng=pyrandom.Random(rank), noise_seed=rank)
+        pipe = vin.DeviceInput(device=dev)  # config/swin-transformer-s.conf:29-31: erasing 0.25, mixup 0.8, cutmix 1.0
+        n_host = 3
+        srcs = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+        same = {i: i for i in range(B)}  # partners are drawn inside the batch
+        tabs = [vin.pack_table([sampler.sample(i, B, 224, 224) for i in range(B)], same, True, "pixel")
+                for _ in range(n_host)]
+
+        def u8_loop(n):
+            tot = 0.0
+            for i in range(n):
+                xd = pipe(srcs[i % n_host], tabs[i % n_host])  # H2D of the uint8 batch + table, one kernel
+                tot += step(xd, y_dev).item()
+            return tot
+
+        u8_loop(2)
+        barrier()
+        e0.record()
+        u8_loop(args.steps)
+        e1.record()
+        barrier()
+        ms4 = vd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        e2e_u8 = {"value": world * B / (ms4 * 1e-3), "unit": "images/s", "ms_per_step": ms4,
+                  "h2d_bytes_per_step": B * 3 * 224 * 224 + B * vin.TABLE_COLS * 4, "d2h_bytes_per_step": 4,
+                  "includes": "uint8 H2D + vtb_input_batch (normalise, mixup / cutmix, erasing) + fwd+bwd step, one stream"}
+
     # ---------------------------------------------------------------- secondary: the same step + optimizer (§8d "also
     # reported included"): clip_grad_norm_ (train.py:294) + AdamW (config/swin-transformer-s.conf:39-42), both multi-tensor
     with_opt = None
@@ -555,6 +591,8 @@ def main():
                            "host_issue_ms_per_step": host_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "with_optimizer": with_opt}
+        if e2e_u8 is not None:
+            line["e2e_u8"] = e2e_u8
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -304,6 +304,29 @@ int vtb_mix_loss(const float* logits, int64_t ld, const int64_t* target1, const 
                  int32_t rows, int32_t n_class, double eps, float loss_scale, float* loss, float* row_loss,
                  float* dlogits, int32_t* correct, int32_t topk, vtb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device input path: uint8 HWC source images -> normalised f32 NCHW batch, with the per-sample
+ * mixup / cutmix / RandomErasing of the reference's loader applied in the same pass.  Stands in for
+ *   mix_dataset.py:37-90 (MixDataset.__getitem__: Image.blend :66 / paste :84 on uint8, mul + add_ :63 / slice copy :79
+ *   on tensors), factory.py:163-174 (ToTensor + Normalize) and transforms.py:377-407 (RandomErasing._erase, modes
+ *   "pixel" and "const"; factory.py:178-182).
+ * src   u8  [n_src, H, W, 3] device;  out f32 [batch, 3, H, W] device;  mean3 / std3: three HOST floats each.
+ * table i32 [batch, 24] device, one row per output image (the random decisions, drawn on the host in the reference's
+ * order by device_input.MixSampler):
+ *   0 src1   1 src2 (partner)   2 mode (0 none, 1 mixup, 2 cutmix)   3 domain (0 = mix in uint8 like PIL, then
+ *   normalise, then erase box A on the result: mix_before_aug = true;  1 = normalise + erase each source (box A ->
+ *   src1, box B -> src2), then mix the tensors: mix_before_aug = false)
+ *   4 w1 (f32 bits): domain 0 -> PIL blend alpha = (float)(1 - ratio);  domain 1 -> (float)ratio
+ *   5 w2 (f32 bits): domain 1 -> (float)(1 - ratio), the `alpha` of add_;  unused otherwise
+ *   6..9 cutmix box x1, y1, x2, y2 (half-open)    10..13 erase box A top, left, h, w (h = 0: none)    14..17 erase box B
+ *   18, 19 noise seeds of boxes A / B    20 erase mode (0 zeros, 1 N(0,1) per pixel: Philox4x32-10, counter (x, y, 0, 0),
+ *   key (seed, 0x7674B200), Box-Muller -- restated bit-for-bit in oracle/input_ops.py)    21..23 reserved (0)
+ * Results: bit-identical to torchvision/PIL for modes none / cutmix and the uint8 blend; tensor mixup within 1 ulp
+ * (ATen's add_ may or may not contract to an FMA); erase noise is N(0,1) but not torch's CPU stream.
+ * ---------------------------------------------------------------------------------------------- */
+int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t* table, int32_t batch, int32_t H, int32_t W,
+                    const float* mean3, const float* std3, float* out, vtb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

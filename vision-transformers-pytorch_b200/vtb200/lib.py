@@ -21,7 +21,7 @@ SYMBOLS = [
     "vtb_patch_scatter", "vtb_transpose_hw", "vtb_dwconv3x3_fwd", "vtb_dwconv3x3_bwd", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
     "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss", "vtb_mt_num_chunks", "vtb_mt_cast_f32_bf16", "vtb_mt_ema",
     "vtb_mt_grad_norm", "vtb_mt_scale", "vtb_mt_agc", "vtb_mt_adamw", "vtb_mix_loss", "vtb_l2norm_fwd", "vtb_l2norm_bwd",
-    "vtb_weight_norm_fwd", "vtb_weight_norm_bwd", "vtb_gelu_fwd", "vtb_gelu_bwd",
+    "vtb_weight_norm_fwd", "vtb_weight_norm_bwd", "vtb_gelu_fwd", "vtb_gelu_bwd", "vtb_input_batch",
 ]
 
 
@@ -127,6 +127,7 @@ def load():
     lib.vtb_mt_agc.argtypes = [vp, vp, vp, vp, i32, f32, f32, vp]
     lib.vtb_mt_adamw.argtypes = [vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, f64, f64, i64, vp, vp]
     lib.vtb_mix_loss.argtypes = [vp, i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, vp, vp, i32, vp]
+    lib.vtb_input_batch.argtypes = [vp, i32, vp, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vtb_last_error",):
