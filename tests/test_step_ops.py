@@ -105,6 +105,10 @@ def test_train_util_host_helpers(G):
     m.update(2.0, 3)
     m.update(4.0, 1)
     assert (m.val, m.sum, m.count, m.avg) == (4.0, 10.0, 4, 2.5)
+    d = T.DeferredMeter()  # host numbers / CPU tensors take the plain path: same running average
+    d.update_async(2.0, 3)
+    d.update_async(torch.tensor(2.0), 1, scale=2.0)
+    assert (d.val, d.sum, d.count, d.avg) == (4.0, 10.0, 4, 2.5) and d.sync() is d
 
     net = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.LayerNorm(4))
     net[1].weight.requires_grad_(False)

@@ -294,3 +294,21 @@ def test_gpu_make_batch_yields_the_loader_tuple():
     table = D.pack_table(ds, {i: i for i in range(n)}, True, "pixel")
     want = O.input_batch(data, table)
     assert np.abs(batch.cpu().numpy() - want).max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ DeferredMeter (train_util)
+@pytest.mark.gpu
+def test_gpu_deferred_meter_matches_blocking_meter():
+    """The non-blocking meter ends with the same val / sum / count / avg as `Meter` fed by `.item()`,
+    also when more values are in flight than it has slots."""
+    import train_util as T
+
+    vals = torch.arange(1, 41, dtype=torch.float32, device="cuda") * 0.25
+    plain, deferred = T.Meter(), T.DeferredMeter(slots=8)
+    for i, v in enumerate(vals):
+        plain.update(v.item() * 2.0, i % 3 + 1)
+        deferred.update_async(v, i % 3 + 1, scale=2.0)
+    deferred.sync()
+    assert deferred.count == plain.count and deferred.val == plain.val
+    assert deferred.sum == pytest.approx(plain.sum, rel=1e-12) and deferred.avg == pytest.approx(plain.avg, rel=1e-12)
+    assert not deferred._pending

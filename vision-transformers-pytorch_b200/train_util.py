@@ -1,6 +1,7 @@
 """Drop-in for the reference's `train_util.py`: same names and call signatures.  `accuracy` (train_util.py:53-67) and
 `accumulate` (train_util.py:70-84) run as single library launches (vtb_mix_loss in its accuracy-only mode, vtb_mt_ema);
-the rest is host-side bookkeeping restated from the reference's behaviour."""
+the rest is host-side bookkeeping restated from the reference's behaviour.  `DeferredMeter` is an addition (not in the
+reference): the same running average fed from device scalars without a host stall."""
 import math
 
 import torch
@@ -41,6 +42,52 @@ class Meter(object):
         self.sum += val * n
         self.count += n
         self.avg = self.sum / self.count
+
+
+class DeferredMeter(Meter):
+    """A `Meter` fed with DEVICE scalars that never blocks the host (the reference's loop stalls three
+    times per step on `loss.item()`, `prec1.item()`, `prec5.item()`, train.py:277-281).  `update_async(t, n, scale)` queues
+    an asynchronous copy of the 0-dim tensor `t` into a pinned slot and records an event; values are folded into
+    val / avg / sum / count — in submission order — once their event has completed (`poll()`, called by every update),
+    or all at once by `sync()` (call it before reading `.avg` for a log line or at the end of the epoch)."""
+
+    def __init__(self, slots=64):
+        super().__init__()
+        self._slots, self._pinned, self._pending, self._next = slots, None, [], 0
+
+    def update_async(self, value, n=1, scale=1.0):
+        if not isinstance(value, torch.Tensor) or not value.is_cuda:
+            self.update(float(value) * scale, n)  # already a host number
+            return
+        if len(self._pending) >= self._slots:
+            self._drain(block_first=True)  # every slot is in flight: wait for the oldest one only
+        if self._pinned is None:
+            self._pinned = torch.empty(self._slots, dtype=torch.float32).pin_memory()
+        slot = self._next
+        self._next = (self._next + 1) % self._slots
+        self._pinned[slot:slot + 1].copy_(value.detach().reshape(1), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self._pending.append((slot, done, n, scale))
+        self.poll()
+
+    def _drain(self, block_first=False, block_all=False):
+        while self._pending:
+            slot, done, n, scale = self._pending[0]
+            if block_all or block_first:
+                done.synchronize()
+                block_first = False
+            elif not done.query():
+                return
+            self._pending.pop(0)
+            self.update(float(self._pinned[slot]) * scale, n)
+
+    def poll(self):
+        self._drain()
+
+    def sync(self):
+        self._drain(block_all=True)
+        return self
 
 
 @torch.no_grad()
