@@ -267,8 +267,8 @@ def test_gpu_noise_statistics_and_full_size_properties():
     assert torch.equal(out[idx % 8 == 2], plain[idx % 8 == 2])          # weight 1 -> alpha 0 -> img1
     assert torch.equal(out[idx % 8 == 6], plain[partner[idx % 8 == 6]])  # weight 0 -> alpha 1 -> partner
     z = out[idx % 4 == 3].double()
-    assert torch.isfinite(z).all() and abs(z.mean().item()) < 2e-3 and abs(z.std().item() - 1) < 2e-3
-    assert abs((z ** 4).mean().item() - 3) < 0.02
+    assert torch.isfinite(z).all() and abs(z.mean().item()) < 3e-3 and abs(z.std().item() - 1) < 3e-3
+    assert abs((z ** 4).mean().item() - 3) < 0.03
     assert not torch.equal(out[3], out[7])  # different seeds, different noise
     want = O.erase_noise(1003, *np.meshgrid(np.arange(H), np.arange(W), indexing="ij"))
     assert np.abs(out[3].cpu().numpy() - want).max() <= 2e-5
