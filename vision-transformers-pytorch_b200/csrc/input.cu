@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int IN_THREADS = 256;
+constexpr int IN_THREADS = 256;  // = the width of the normalisation table: thread t builds entry t
 constexpr int IN_TABLE_COLS = 24;
 constexpr uint32_t PHILOX_KEY1 = 0x7674B200u;
 
@@ -202,7 +202,8 @@ extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t*
   const int64_t tiles = (HW + (int64_t)IN_THREADS * ppt - 1) / ((int64_t)IN_THREADS * ppt);
   VTB_CHECK(tiles < (1ll << 30), -1, "vtb_input_batch: image too large");
   const int64_t items = (int64_t)batch * tiles;
-  const int64_t cap = (int64_t)vtb_num_sms() * 8;  // 8 resident CTAs of 256 threads per SM
+  const int sms = vtb_num_sms() > 0 ? vtb_num_sms() : 148;  // vtb_init() not called yet: the B200 count
+  const int64_t cap = (int64_t)sms * 8;                     // 8 resident CTAs of 256 threads per SM
   const int grid = (int)(items < cap ? items : cap);
   if (vec)
     input_batch_kernel<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1], mean3[2],
