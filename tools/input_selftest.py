@@ -89,6 +89,102 @@ def table_all_modes(n, H, W, seed, emode):
     return np.stack(rows)
 
 
+NPZ = os.path.join(ROOT, "tools", "_selftest_input.npz")
+
+
+def prepare():
+    """Build container: golden cases + their tables (product sampler) + the BASELINE-size bench tables -> NPZ (no torch needed
+    to read it on the GPU box)."""
+    import random
+
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "vision-transformers-pytorch_b200"))
+    import device_input as D
+
+    G = torch.load(os.path.join(ROOT, "tests", "golden", "input_ops.pt"), map_location="cpu", weights_only=False)
+    out = {"mean": np.array(G["mean"], np.float64), "std": np.array(G["std"], np.float64)}
+    for name, case in G["cases"].items():
+        s = D.MixSampler(case["mixup"], case["cutmix"], case["erasing"], case["mix_before_aug"], rng=random.Random(case["seed"]))
+        ds = [s.sample(i, case["n"], case["H"], case["W"]) for i in range(case["n"])]
+        out[f"g_{name}_table"] = D.pack_table(ds, {i: i for i in range(case["n"])}, case["mix_before_aug"], "const")
+        out[f"g_{name}_u8"], out[f"g_{name}_img"] = case["u8"].numpy(), case["img"].numpy()
+    B = 256
+    for tag, kw in (("none", dict(mixup=0.0, cutmix=0.0, erasing=0.0)), ("swin_conf", dict(mixup=0.8, cutmix=1.0, erasing=0.25)),
+                    ("tensor_order", dict(mixup=0.8, cutmix=1.0, erasing=0.25, mix_before_aug=False))):
+        s = D.MixSampler(rng=random.Random(0), **kw)
+        ds = [s.sample(i, B, 224, 224) for i in range(B)]
+        out[f"b_{tag}"] = D.pack_table(ds, {i: i for i in range(B)}, s.mix_before_aug, "pixel")
+    np.savez_compressed(NPZ, **out)
+    print("wrote", NPZ, os.path.getsize(NPZ), "bytes")
+
+
+def golden_npz():
+    global fails
+    Z = np.load(NPZ)
+    for key in [k for k in Z.files if k.endswith("_table") and k.startswith("g_")]:
+        name = key[2:-6]
+        got, want = run(Z[f"g_{name}_u8"], Z[key], Z["mean"], Z["std"]), Z[f"g_{name}_img"]
+        ok = np.abs(got - want).max() <= 5e-7 if "tensor_mix" in name else np.array_equal(got.view(np.int32), want.view(np.int32))
+        fails += not ok
+        print(f"{'PASS' if ok else 'FAIL'} golden {name}: max |gpu - reference| = {np.abs(got - want).max():.3e}", flush=True)
+
+
+def bench():
+    """BASELINE batch (256 x 224 x 224): device-resident uint8 sources, L2 flushed between launches, CUDA events."""
+    Z = np.load(NPZ)
+    B, H, W = 256, 224, 224
+    peak = 6543.1
+    try:
+        import json
+
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:  # noqa: BLE001
+        pass
+    u8 = np.random.default_rng(1).integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    d_src, d_out, d_flush = dev_alloc(u8.nbytes), dev_alloc(B * 3 * H * W * 4), dev_alloc(256 << 20)
+    ck(rt.cudaMemcpy(d_src, u8.ctypes.data, u8.nbytes, 1), "H2D src")
+    rt.cudaEventCreate.argtypes = [C.POINTER(C.c_void_p)]
+    rt.cudaEventRecord.argtypes = [C.c_void_p, C.c_void_p]
+    rt.cudaEventSynchronize.argtypes = [C.c_void_p]
+    rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+    rt.cudaMemset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    ck(rt.cudaEventCreate(C.byref(e0)), "event")
+    ck(rt.cudaEventCreate(C.byref(e1)), "event")
+    f3 = C.c_float * 3
+    for tag in ("swin_conf", "none", "tensor_order"):
+        table = np.ascontiguousarray(Z[f"b_{tag}"], np.int32)
+        d_tab = dev_alloc(table.nbytes)
+        ck(rt.cudaMemcpy(d_tab, table.ctypes.data, table.nbytes, 1), "H2D table")
+        mixed = int((table[:, 2] != 0).sum())
+        nbytes = B * H * W * 12 + (B + mixed) * H * W * 3  # output written once, every source byte read once per use
+        ts = []
+        for it in range(9):
+            ck(rt.cudaMemset(d_flush, it, 256 << 20), "flush")
+            ck(rt.cudaEventRecord(e0, None), "record")
+            rc = lib.vtb_input_batch(d_src, B, d_tab, B, H, W, f3(*O.MEAN), f3(*O.STD), d_out, None)
+            ck(rt.cudaEventRecord(e1, None), "record")
+            ck(rt.cudaEventSynchronize(e1), "sync")
+            if rc != 0:
+                raise SystemExit(f"FAIL vtb_input_batch rc={rc}: {lib.vtb_last_error().decode()}")
+            ms = C.c_float()
+            ck(rt.cudaEventElapsedTime(C.byref(ms), e0, e1), "elapsed")
+            if it >= 3:
+                ts.append(ms.value)
+        ms = sum(ts) / len(ts)
+        print(f"BENCH {tag:13s} B=256 224x224 ({mixed} mixed): {ms*1e3:7.1f} us  {B/ms*1e3:9.0f} img/s  {nbytes/1e6:6.1f} MB  "
+              f"{nbytes/ms/1e6:6.0f} GB/s = {nbytes/ms/1e6/peak*100:4.1f} % of {peak:.0f} GB/s (min {min(ts)*1e3:.1f} us)", flush=True)
+        rt.cudaFree(d_tab)
+
+
+if "--prepare" in sys.argv:
+    prepare()
+    sys.exit(0)
+if "--bench-only" in sys.argv:
+    ck(rt.cudaSetDevice(0), "cudaSetDevice")
+    bench()
+    sys.exit(0)
 if not EMULATE:
     ck(rt.cudaSetDevice(0), "cudaSetDevice")
 fails = 0
@@ -105,6 +201,13 @@ for (H, W), emode in (((36, 44), 1), ((19, 37), 1), ((36, 44), 0), ((224, 224), 
     fails += not ok
     print(f"{'PASS' if ok else 'FAIL'} H={H} W={W} erase_mode={emode}: max |gpu - oracle| = {err:.3e}, bit-identical {exact*100:.2f} %",
           flush=True)
+
+if os.path.exists(NPZ):
+    golden_npz()
+    if not EMULATE:
+        bench()
+    print(f"input_selftest: {'ALL PASS' if fails == 0 else str(fails) + ' FAILED'} in {time.time() - t_start:.1f} s", flush=True)
+    sys.exit(1 if fails else 0)
 
 try:  # the reference's own batches (golden), decisions re-drawn by the product's sampler; needs torch only to unpickle
     if os.environ.get("VTB_SELFTEST_NO_GOLDEN") == "1":
