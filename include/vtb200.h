@@ -32,7 +32,9 @@ int vtb_init(void);
  * "attn_wp" (0/1, default 1): one warp per (window, head) problem when nq, nkv <= 64; 0 = one CTA per problem.
  * "attn_wt" (0/1, default 1): tcgen05 window kernels (two windows per 128-row tile) for WINDOW problems with dh = 32 and
  * <= 64 tokens per window; 0 forces the mma.sync kernels (A/B measurements, cross-checks).
- * "ln_stream" (0/1, default 1): streaming (bulk-copy staged) LayerNorm kernels; 0 = register-resident kernels. */
+ * "ln_stream" (0/1, default 1): streaming (bulk-copy staged) LayerNorm kernels; 0 = register-resident kernels.
+ * "input_variant" (1/2, default 1): vtb_input_batch kernel; 2 = the division-free row-tiled variant written after the first
+ *   ncu capture (same results; checked on the host build only so far). */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------

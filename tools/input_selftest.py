@@ -24,6 +24,13 @@ else:
     lib = C.CDLL(os.path.join(ROOT, "vision-transformers-pytorch_b200", "vtb200", "libvtb200.so"))
 if not EMULATE:
     lib.vtb_last_error.restype = C.c_char_p
+VARIANT = 2 if "--variant2" in sys.argv else 1  # kernel variant (vtb_set_option("input_variant", v))
+if EMULATE:
+    getattr(lib, "_Z21vtb_input_variant_seti")(VARIANT)
+else:
+    lib.vtb_set_option.argtypes = [C.c_char_p, C.c_int32]
+    assert lib.vtb_set_option(b"input_variant", VARIANT) == 0
+print(f"input_selftest: kernel variant {VARIANT}{' (host emulation)' if EMULATE else ''}", flush=True)
 lib.vtb_input_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                 C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
 rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

@@ -791,11 +791,13 @@ void vtb_attn_tc_set(bool on);
 void vtb_attn_wp_set(bool on);
 void vtb_attn_wt_set(bool on);
 void vtb_ln_stream_set(bool on);
+void vtb_input_variant_set(int v);
 
 extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
+  if (strcmp(name, "input_variant") == 0) { vtb_input_variant_set(value); return 0; }
   if (strcmp(name, "attn_wp") == 0) { vtb_attn_wp_set(value != 0); return 0; }
   if (strcmp(name, "attn_wt") == 0) { vtb_attn_wt_set(value != 0); return 0; }
   if (strcmp(name, "ln_stream") == 0) { vtb_ln_stream_set(value != 0); return 0; }

@@ -185,7 +185,161 @@ input_batch_kernel(const uint8_t* __restrict__ src, int n_src, const int32_t* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------ variant 2
+// Same arithmetic, restructured after the first ncu capture of variant 1 (profiles/r01_ncu_full_input_kernel.txt: XU pipe
+// 94 % busy, 464 warp instructions per 128 pixels, 21 of 27 global loads per thread were the decision row):
+//   * a work item is R whole image rows; a thread's (row, pixel group) inside the item is fixed for the whole kernel, so the
+//     per-item index arithmetic has no division at all (variant 1: three 64-bit divisions per thread and item);
+//   * the decision row is staged once per item in shared memory (24 words) instead of 21 read-only loads per thread;
+//   * uint8 <-> float conversions without the XU pipe: byte -> float by or-ing it into the mantissa of 2^23, the
+//     truncating float -> byte of the PIL blend by a round-toward-zero add of 2^23.
+__device__ __forceinline__ float byte_to_float(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
+
+// out of line: erased pixels are the rare path, and Philox + log + sincos inlined four times per thread would set the
+// register budget of the streaming path
+__device__ __noinline__ float3 noise3_cold(uint32_t seed, int y, int x) {
+  float z[3];
+  noise3(seed, y, x, z);
+  return make_float3(z[0], z[1], z[2]);  // by value: the callers' pixel arrays stay in registers
+}
+
+// The decision row specialised to one image row y: the y half of every box test is folded into the width (0 = miss).
+struct RowY {
+  int mode, domain, erase_mode;
+  float w1, w2;
+  int c_left, c_w, a_left, a_w, b_left, b_w;
+  uint32_t seed_a, seed_b;
+};
+__device__ __forceinline__ bool in_span(int x, int left, int w) { return (unsigned)(x - left) < (unsigned)w; }
+
+__device__ __forceinline__ void pixel2(const RowY& r, const float (*lut)[256], int y, int x, const uint32_t a[3],
+                                       const uint32_t p[3], float v[3]) {
+  const bool boxed = in_span(x, r.c_left, r.c_w);
+  if (r.domain == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t m = a[c];
+      if (r.mode == 1) {
+        const float fa = byte_to_float(a[c]), d = __fsub_rn(byte_to_float(p[c]), fa);  // exact: small integers
+        // 0 <= fa + alpha d <= 255 for alpha in [0, 1]: adding 2^23 toward zero leaves floor() in the low mantissa bits
+        m = __float_as_uint(__fadd_rz(__fadd_rn(fa, __fmul_rn(r.w1, d)), 8388608.0f)) & 255u;
+      } else if (boxed) {
+        m = p[c];
+      }
+      v[c] = lut[c][m];
+    }
+    if (in_span(x, r.a_left, r.a_w)) {
+      if (r.erase_mode == 1) { const float3 z = noise3_cold(r.seed_a, y, x); v[0] = z.x, v[1] = z.y, v[2] = z.z; }
+      else v[0] = v[1] = v[2] = 0.f;
+    }
+    return;
+  }
+  float va[3], vb[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) va[c] = lut[c][a[c]], vb[c] = lut[c][p[c]];
+  if (in_span(x, r.a_left, r.a_w)) {
+    if (r.erase_mode == 1) { const float3 z = noise3_cold(r.seed_a, y, x); va[0] = z.x, va[1] = z.y, va[2] = z.z; }
+    else va[0] = va[1] = va[2] = 0.f;
+  }
+  if (in_span(x, r.b_left, r.b_w)) {
+    if (r.erase_mode == 1) { const float3 z = noise3_cold(r.seed_b, y, x); vb[0] = z.x, vb[1] = z.y, vb[2] = z.z; }
+    else vb[0] = vb[1] = vb[2] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (r.mode == 1) v[c] = __fmaf_rn(vb[c], r.w2, __fmul_rn(va[c], r.w1));
+    else v[c] = boxed ? vb[c] : va[c];
+  }
+}
+
+// tx = threads along a row (= min(pixel groups per row, 256)), R = 256 / tx rows per item
+template <bool VEC>
+__global__ void __launch_bounds__(IN_THREADS, 4)
+input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* __restrict__ table,
+                    float* __restrict__ out, int B, int H, int W, float m0, float m1, float m2, float s0, float s1,
+                    float s2, int tx, int R, int groups_per_row, int tiles_per_image) {
+  __shared__ float lut[3][256];
+  __shared__ int32_t row_s[IN_TABLE_COLS];
+  {
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    const float v = __fdiv_rn((float)threadIdx.x, 255.0f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lut[c][threadIdx.x] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+  }
+  constexpr int PPT = VEC ? 4 : 1;
+  const int64_t HW = (int64_t)H * W;
+  const int ry = (int)threadIdx.x / tx, xs = (int)threadIdx.x - ry * tx;  // the only division: once per thread
+  const uint32_t n_items = (uint32_t)B * (uint32_t)tiles_per_image;
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t b = item / (uint32_t)tiles_per_image, tile = item - b * (uint32_t)tiles_per_image;  // CTA-uniform
+    __syncthreads();  // every reader of the previous item's row is done
+    if (threadIdx.x < IN_TABLE_COLS) row_s[threadIdx.x] = __ldg(table + (int64_t)b * IN_TABLE_COLS + threadIdx.x);
+    __syncthreads();  // row (and, first time round, the table) visible
+    const int y = (int)tile * R + ry;
+    if (ry >= R || y >= H) continue;
+    const int src1 = min(max(row_s[0], 0), n_src - 1), src2 = min(max(row_s[1], 0), n_src - 1);
+    RowY r;
+    r.mode = row_s[2], r.domain = row_s[3], r.erase_mode = row_s[20];
+    r.w1 = __int_as_float(row_s[4]), r.w2 = __int_as_float(row_s[5]);
+    // cutmix box (x1, y1, x2, y2), half-open; erase boxes (top, left, h, w); box B only exists with a partner
+    r.c_left = row_s[6], r.c_w = (r.mode == 2 && y >= row_s[7] && y < row_s[9]) ? max(row_s[8] - row_s[6], 0) : 0;
+    r.a_left = row_s[11], r.a_w = ((unsigned)(y - row_s[10]) < (unsigned)row_s[12]) ? row_s[13] : 0;
+    r.b_left = row_s[15], r.b_w = (r.mode != 0 && (unsigned)(y - row_s[14]) < (unsigned)row_s[16]) ? row_s[17] : 0;
+    r.seed_a = (uint32_t)row_s[18], r.seed_b = (uint32_t)row_s[19];
+    const uint8_t* row1 = src + ((int64_t)src1 * H + y) * W * 3;
+    const uint8_t* row2 = src + ((int64_t)src2 * H + y) * W * 3;
+    float* orow = out + (int64_t)b * 3 * HW + (int64_t)y * W;
+    for (int xg = xs; xg < groups_per_row; xg += tx) {
+      const int x0 = xg * PPT;
+      if constexpr (VEC) {
+        uint32_t wa[3], wb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wa[k] = __ldg(reinterpret_cast<const uint32_t*>(row1 + x0 * 3) + k);
+        if (r.mode != 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) wb[k] = __ldg(reinterpret_cast<const uint32_t*>(row2 + x0 * 3) + k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) wb[k] = wa[k];
+        }
+        float res[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t a[3], p[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int k = j * 3 + c;
+            a[c] = (wa[k >> 2] >> (8 * (k & 3))) & 255u;
+            p[c] = (wb[k >> 2] >> (8 * (k & 3))) & 255u;
+          }
+          float v[3];
+          pixel2(r, lut, y, x0 + j, a, p, v);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) res[c][j] = v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          __stcs(reinterpret_cast<float4*>(orow + c * HW + x0), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+      } else {
+        uint32_t a[3], p[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[c] = __ldg(row1 + x0 * 3 + c);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[c] = r.mode != 0 ? (uint32_t)__ldg(row2 + x0 * 3 + c) : a[c];
+        float v[3];
+        pixel2(r, lut, y, x0, a, p, v);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) __stcs(orow + c * HW + x0, v[c]);
+      }
+    }
+  }
+}
+
+int g_input_variant = 1;  // 1: first (GPU-verified) kernel; 2: the restructured one (vtb_set_option("input_variant", 2))
+
 }  // namespace
+
+void vtb_input_variant_set(int v) { g_input_variant = (v == 2) ? 2 : 1; }
 
 extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t* table, int32_t batch, int32_t H, int32_t W,
                                const float* mean3, const float* std3, float* out, vtb_stream_t stream_) {
@@ -199,11 +353,28 @@ extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t*
   const bool vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   const int ppt = vec ? 4 : 1;
+  const int sms = vtb_num_sms() > 0 ? vtb_num_sms() : 148;  // vtb_init() not called yet: the B200 count
+  const int64_t cap = (int64_t)sms * 8;                     // 8 resident CTAs of 256 threads per SM
+  if (g_input_variant == 2) {
+    const int gpr = (W + ppt - 1) / ppt;                    // pixel groups per row
+    const int tx = gpr < IN_THREADS ? gpr : IN_THREADS;
+    const int R = IN_THREADS / tx;                          // rows per work item
+    const int64_t tiles = (H + R - 1) / R;
+    const int64_t items = (int64_t)batch * tiles;
+    VTB_CHECK(items < (1ll << 31), -1, "vtb_input_batch: batch too large");
+    const int grid = (int)(items < cap ? items : cap);
+    if (vec)
+      input_batch_kernel2<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
+                                                                 mean3[2], std3[0], std3[1], std3[2], tx, R, gpr, (int)tiles);
+    else
+      input_batch_kernel2<false><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
+                                                                  mean3[2], std3[0], std3[1], std3[2], tx, R, gpr, (int)tiles);
+    VTB_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t tiles = (HW + (int64_t)IN_THREADS * ppt - 1) / ((int64_t)IN_THREADS * ppt);
   VTB_CHECK(tiles < (1ll << 30), -1, "vtb_input_batch: image too large");
   const int64_t items = (int64_t)batch * tiles;
-  const int sms = vtb_num_sms() > 0 ? vtb_num_sms() : 148;  // vtb_init() not called yet: the B200 count
-  const int64_t cap = (int64_t)sms * 8;                     // 8 resident CTAs of 256 threads per SM
   const int grid = (int)(items < cap ? items : cap);
   if (vec)
     input_batch_kernel<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1], mean3[2],
