@@ -33,8 +33,8 @@ int vtb_init(void);
  * "attn_wt" (0/1, default 1): tcgen05 window kernels (two windows per 128-row tile) for WINDOW problems with dh = 32 and
  * <= 64 tokens per window; 0 forces the mma.sync kernels (A/B measurements, cross-checks).
  * "ln_stream" (0/1, default 1): streaming (bulk-copy staged) LayerNorm kernels; 0 = register-resident kernels.
- * "input_variant" (1/2, default 1): vtb_input_batch kernel; 2 = the division-free row-tiled variant written after the first
- *   ncu capture (same results; checked on the host build only so far). */
+ * "input_variant" (1/2, default 1): vtb_input_batch kernel; 2 = the leaner variant written after the first ncu capture
+ *   (same results; checked on the host build only so far; needs a 16-byte aligned table, else variant 1 runs). */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------

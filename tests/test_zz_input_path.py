@@ -191,7 +191,7 @@ def test_kernel_source_on_host_matches_golden_and_oracle(G, variant):
         _, table = redraw(case)
         check_against_golden(case, run_emulated(case["u8"].numpy(), table, G["mean"], G["std"]), name)
     # 44 % 4 == 0 -> the 4-pixel path; 37 -> the scalar path; both with every mode, erase modes and a non-default mean / std
-    # 44 / 1100: rows narrower / wider than one CTA (variant 2: several rows per item / an x loop inside the row)
+    # 44 / 1100 / 301: tiles spanning several rows, rows spanning several tiles, odd widths (scalar path)
     for (H, W), emode, mean, std in (((36, 44), "pixel", O.MEAN, O.STD), ((19, 37), "pixel", (0.5, 0.4, 0.3), (0.2, 0.25, 0.3)),
                                      ((36, 44), "const", O.MEAN, O.STD), ((5, 1100), "pixel", O.MEAN, O.STD),
                                      ((3, 301), "const", O.MEAN, O.STD)):

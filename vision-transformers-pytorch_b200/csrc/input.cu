@@ -186,13 +186,18 @@ input_batch_kernel(const uint8_t* __restrict__ src, int n_src, const int32_t* __
 }
 
 // ------------------------------------------------------------------------------------------------ variant 2
-// Same arithmetic, restructured after the first ncu capture of variant 1 (profiles/r01_ncu_full_input_kernel.txt: XU pipe
-// 94 % busy, 464 warp instructions per 128 pixels, 21 of 27 global loads per thread were the decision row):
-//   * a work item is R whole image rows; a thread's (row, pixel group) inside the item is fixed for the whole kernel, so the
-//     per-item index arithmetic has no division at all (variant 1: three 64-bit divisions per thread and item);
-//   * the decision row is staged once per item in shared memory (24 words) instead of 21 read-only loads per thread;
-//   * uint8 <-> float conversions without the XU pipe: byte -> float by or-ing it into the mantissa of 2^23, the
-//     truncating float -> byte of the PIL blend by a round-toward-zero add of 2^23.
+// Same arithmetic and the same flat 1024-pixel tiles as variant 1, leaner per item.  Why: the first ncu capture of variant 1
+// (profiles/r01_ncu_full_input_kernel.txt) shows the XU pipe 94 % busy, 464 warp instructions per 128 pixels and 21 of 27
+// global loads per thread spent on the decision row.  A first rewrite with row-shaped work items, the row staged in shared
+// memory and two barriers per item was parity-green on the B200 but SLOWER (83 vs 72 us, profiles/
+// r01_input_kernel_selftest_rowtiled_variant.log): with 4 CTAs per SM the barriers serialise the row -> source load chain.
+// This variant keeps variant 1's barrier-free loop and only removes work:
+//   * 32-bit index arithmetic (variant 1: three 64-bit divisions per thread and item);
+//   * the decision row as six 16-byte read-only loads, specialised to the thread's image row (the y half of each box test
+//     folded into a width) before the pixel loop;
+//   * uint8 <-> float without the XU pipe: byte -> float by or-ing it into the mantissa of 2^23, the truncating
+//     float -> byte of the PIL blend by a round-toward-zero add of 2^23;
+//   * the erase noise (Philox + log + sincos) out of line, so the streaming path's register budget is not set by it.
 __device__ __forceinline__ float byte_to_float(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
 // out of line: erased pixels are the rare path, and Philox + log + sincos inlined four times per thread would set the
@@ -252,90 +257,88 @@ __device__ __forceinline__ void pixel2(const RowY& r, const float (*lut)[256], i
   }
 }
 
-// tx = threads along a row (= min(pixel groups per row, 256)), R = 256 / tx rows per item
 template <bool VEC>
-__global__ void __launch_bounds__(IN_THREADS, 4)
+__global__ void __launch_bounds__(IN_THREADS)
 input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* __restrict__ table,
                     float* __restrict__ out, int B, int H, int W, float m0, float m1, float m2, float s0, float s1,
-                    float s2, int tx, int R, int groups_per_row, int tiles_per_image) {
+                    float s2, int tiles_per_image) {
   __shared__ float lut[3][256];
-  __shared__ int32_t row_s[IN_TABLE_COLS];
   {
     const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
     const float v = __fdiv_rn((float)threadIdx.x, 255.0f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) lut[c][threadIdx.x] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
   }
+  __syncthreads();
   constexpr int PPT = VEC ? 4 : 1;
-  const int64_t HW = (int64_t)H * W;
-  const int ry = (int)threadIdx.x / tx, xs = (int)threadIdx.x - ry * tx;  // the only division: once per thread
+  const uint32_t HW = (uint32_t)H * (uint32_t)W;  // < 2^31 (host check)
   const uint32_t n_items = (uint32_t)B * (uint32_t)tiles_per_image;
   for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const uint32_t b = item / (uint32_t)tiles_per_image, tile = item - b * (uint32_t)tiles_per_image;  // CTA-uniform
-    __syncthreads();  // every reader of the previous item's row is done
-    if (threadIdx.x < IN_TABLE_COLS) row_s[threadIdx.x] = __ldg(table + (int64_t)b * IN_TABLE_COLS + threadIdx.x);
-    __syncthreads();  // row (and, first time round, the table) visible
-    const int y = (int)tile * R + ry;
-    if (ry >= R || y >= H) continue;
-    const int src1 = min(max(row_s[0], 0), n_src - 1), src2 = min(max(row_s[1], 0), n_src - 1);
+    const uint32_t b = item / (uint32_t)tiles_per_image, tile = item - b * (uint32_t)tiles_per_image;
+    const uint32_t p0 = (tile * IN_THREADS + threadIdx.x) * PPT;
+    if (p0 >= HW) continue;
+    const int y = (int)(p0 / (uint32_t)W), x0 = (int)(p0 - (uint32_t)y * (uint32_t)W);
+    // decision row: words 0..23 as six 16-byte loads (one address per warp)
+    const int4* rp = reinterpret_cast<const int4*>(table + (int64_t)b * IN_TABLE_COLS);
+    const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3), q4 = __ldg(rp + 4),
+               q5 = __ldg(rp + 5);
+    const int src1 = min(max(q0.x, 0), n_src - 1), src2 = min(max(q0.y, 0), n_src - 1);
     RowY r;
-    r.mode = row_s[2], r.domain = row_s[3], r.erase_mode = row_s[20];
-    r.w1 = __int_as_float(row_s[4]), r.w2 = __int_as_float(row_s[5]);
-    // cutmix box (x1, y1, x2, y2), half-open; erase boxes (top, left, h, w); box B only exists with a partner
-    r.c_left = row_s[6], r.c_w = (r.mode == 2 && y >= row_s[7] && y < row_s[9]) ? max(row_s[8] - row_s[6], 0) : 0;
-    r.a_left = row_s[11], r.a_w = ((unsigned)(y - row_s[10]) < (unsigned)row_s[12]) ? row_s[13] : 0;
-    r.b_left = row_s[15], r.b_w = (r.mode != 0 && (unsigned)(y - row_s[14]) < (unsigned)row_s[16]) ? row_s[17] : 0;
-    r.seed_a = (uint32_t)row_s[18], r.seed_b = (uint32_t)row_s[19];
-    const uint8_t* row1 = src + ((int64_t)src1 * H + y) * W * 3;
-    const uint8_t* row2 = src + ((int64_t)src2 * H + y) * W * 3;
-    float* orow = out + (int64_t)b * 3 * HW + (int64_t)y * W;
-    for (int xg = xs; xg < groups_per_row; xg += tx) {
-      const int x0 = xg * PPT;
-      if constexpr (VEC) {
-        uint32_t wa[3], wb[3];
+    r.mode = q0.z, r.domain = q0.w, r.erase_mode = q5.x;
+    r.w1 = __int_as_float(q1.x), r.w2 = __int_as_float(q1.y);
+    // cutmix box (x1 = q1.z, y1 = q1.w, x2 = q2.x, y2 = q2.y), half-open
+    r.c_left = q1.z, r.c_w = (r.mode == 2 && y >= q1.w && y < q2.y) ? max(q2.x - q1.z, 0) : 0;
+    // erase boxes (top, left, h, w): A = q2.z, q2.w, q3.x, q3.y;  B = q3.z, q3.w, q4.x, q4.y (only with a partner)
+    r.a_left = q2.w, r.a_w = ((unsigned)(y - q2.z) < (unsigned)q3.x) ? q3.y : 0;
+    r.b_left = q3.w, r.b_w = (r.mode != 0 && (unsigned)(y - q3.z) < (unsigned)q4.x) ? q4.y : 0;
+    r.seed_a = (uint32_t)q4.z, r.seed_b = (uint32_t)q4.w;
+    const uint8_t* s1p = src + ((int64_t)src1 * HW + p0) * 3;
+    const uint8_t* s2p = src + ((int64_t)src2 * HW + p0) * 3;
+    float* o = out + (int64_t)b * 3 * HW + p0;
+    if constexpr (VEC) {
+      uint32_t wa[3], wb[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wa[k] = __ldg(reinterpret_cast<const uint32_t*>(row1 + x0 * 3) + k);
-        if (r.mode != 0) {
+      for (int k = 0; k < 3; ++k) wa[k] = __ldg(reinterpret_cast<const uint32_t*>(s1p) + k);
+      if (r.mode != 0) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) wb[k] = __ldg(reinterpret_cast<const uint32_t*>(row2 + x0 * 3) + k);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) wb[k] = wa[k];
-        }
-        float res[3][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t a[3], p[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int k = j * 3 + c;
-            a[c] = (wa[k >> 2] >> (8 * (k & 3))) & 255u;
-            p[c] = (wb[k >> 2] >> (8 * (k & 3))) & 255u;
-          }
-          float v[3];
-          pixel2(r, lut, y, x0 + j, a, p, v);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) res[c][j] = v[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          __stcs(reinterpret_cast<float4*>(orow + c * HW + x0), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+        for (int k = 0; k < 3; ++k) wb[k] = __ldg(reinterpret_cast<const uint32_t*>(s2p) + k);
       } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wb[k] = wa[k];
+      }
+      float res[3][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         uint32_t a[3], p[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a[c] = __ldg(row1 + x0 * 3 + c);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) p[c] = r.mode != 0 ? (uint32_t)__ldg(row2 + x0 * 3 + c) : a[c];
+        for (int c = 0; c < 3; ++c) {
+          const int k = j * 3 + c;
+          a[c] = (wa[k >> 2] >> (8 * (k & 3))) & 255u;
+          p[c] = (wb[k >> 2] >> (8 * (k & 3))) & 255u;
+        }
         float v[3];
-        pixel2(r, lut, y, x0, a, p, v);
+        pixel2(r, lut, y, x0 + j, a, p, v);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) __stcs(orow + c * HW + x0, v[c]);
+        for (int c = 0; c < 3; ++c) res[c][j] = v[c];
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        __stcs(reinterpret_cast<float4*>(o + (int64_t)c * HW), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+    } else {
+      uint32_t a[3], p[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[c] = __ldg(s1p + c);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p[c] = r.mode != 0 ? (uint32_t)__ldg(s2p + c) : a[c];
+      float v[3];
+      pixel2(r, lut, y, x0, a, p, v);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) __stcs(o + (int64_t)c * HW, v[c]);
     }
   }
 }
 
-int g_input_variant = 1;  // 1: first (GPU-verified) kernel; 2: the restructured one (vtb_set_option("input_variant", 2))
+int g_input_variant = 1;  // 1: first kernel; 2: the lean one (vtb_set_option("input_variant", 2)) until it has been timed
 
 }  // namespace
 
@@ -355,27 +358,20 @@ extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t*
   const int ppt = vec ? 4 : 1;
   const int sms = vtb_num_sms() > 0 ? vtb_num_sms() : 148;  // vtb_init() not called yet: the B200 count
   const int64_t cap = (int64_t)sms * 8;                     // 8 resident CTAs of 256 threads per SM
-  if (g_input_variant == 2) {
-    const int gpr = (W + ppt - 1) / ppt;                    // pixel groups per row
-    const int tx = gpr < IN_THREADS ? gpr : IN_THREADS;
-    const int R = IN_THREADS / tx;                          // rows per work item
-    const int64_t tiles = (H + R - 1) / R;
-    const int64_t items = (int64_t)batch * tiles;
-    VTB_CHECK(items < (1ll << 31), -1, "vtb_input_batch: batch too large");
-    const int grid = (int)(items < cap ? items : cap);
-    if (vec)
-      input_batch_kernel2<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
-                                                                 mean3[2], std3[0], std3[1], std3[2], tx, R, gpr, (int)tiles);
-    else
-      input_batch_kernel2<false><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
-                                                                  mean3[2], std3[0], std3[1], std3[2], tx, R, gpr, (int)tiles);
-    VTB_LAUNCH_CHECK();
-    return 0;
-  }
   const int64_t tiles = (HW + (int64_t)IN_THREADS * ppt - 1) / ((int64_t)IN_THREADS * ppt);
   VTB_CHECK(tiles < (1ll << 30), -1, "vtb_input_batch: image too large");
   const int64_t items = (int64_t)batch * tiles;
   const int grid = (int)(items < cap ? items : cap);
+  if (g_input_variant == 2 && reinterpret_cast<uintptr_t>(table) % 16 == 0 && HW < (1ll << 31) && items < (1ll << 31)) {
+    if (vec)
+      input_batch_kernel2<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
+                                                                 mean3[2], std3[0], std3[1], std3[2], (int)tiles);
+    else
+      input_batch_kernel2<false><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
+                                                                  mean3[2], std3[0], std3[1], std3[2], (int)tiles);
+    VTB_LAUNCH_CHECK();
+    return 0;
+  }
   if (vec)
     input_batch_kernel<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1], mean3[2],
                                                               std3[0], std3[1], std3[2], (int)tiles);
