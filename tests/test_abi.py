@@ -67,3 +67,28 @@ def test_ops_refuse_to_run_without_cuda():
 
     with pytest.raises(RuntimeError, match="CUDA device required"):
         lib.get()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/vtb200.h compiles as strict C99 (no C++-isms, no torch / CUDA types) and a plain C
+    program links against libvtb200.so and calls through it (no GPU needed for vtb_version / vtb_last_error)."""
+    import subprocess
+
+    from vtb200 import lib
+
+    src = tmp_path / "abi_probe.c"
+    src.write_text(
+        '#include "vtb200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  vtb_gemm_params g; vtb_attn_params a; (void)g; (void)a;\n"
+        "  /* a bad call must fail through the error channel, not crash: NULL source pointers */\n"
+        "  float m[3] = {0, 0, 0}, s[3] = {1, 1, 1};\n"
+        "  int rc = vtb_input_batch(0, 1, 0, 1, 8, 8, m, s, 0, 0);\n"
+        '  printf("%d %d %s\\n", vtb_version(), rc, vtb_last_error());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi_probe"
+    lib_dir = os.path.dirname(lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", lib_dir, "-l:libvtb200.so", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 2)
+    assert int(out[0]) >= 100 and int(out[1]) != 0 and "null pointer" in out[2]
