@@ -205,6 +205,25 @@ def test_kernel_source_on_host_matches_golden_and_oracle(G, variant):
         assert exact > 0.5, exact
 
 
+def test_kernel_source_on_host_random_shapes_and_tables():
+    """Seeded random image sizes (vector and scalar paths, tiles that straddle rows and images), batch sizes and decision
+    rows: both kernel variants, built for the host, against the oracle."""
+    from oracle import input_ops as O
+
+    rng = random.Random(2024)
+    for trial in range(12):
+        H, W = rng.randint(1, 40), rng.choice([4, 8, 12, 36, 100]) if trial % 2 else rng.randint(1, 70)
+        n = rng.randint(2, 5)
+        u8 = np.random.default_rng(trial).integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+        table = mixed_table(n, H, W, seed=trial, erase_mode=rng.choice(["pixel", "const"]))
+        table = table[np.random.default_rng(trial).permutation(len(table))][:rng.randint(1, len(table))]
+        want = O.input_batch(u8, table)
+        for variant in (1, 2):
+            got = run_emulated(u8, table, O.MEAN, O.STD, variant=variant)
+            assert not np.isnan(got).any(), (trial, variant, H, W)
+            assert np.abs(got - want).max() <= 2e-5, (trial, variant, H, W)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def run_device(u8, table, mean, std, variant=1):
     import device_input as D
