@@ -205,6 +205,31 @@ def test_kernel_source_on_host_matches_golden_and_oracle(G, variant):
         assert exact > 0.5, exact
 
 
+def test_kernel_source_on_host_edge_cases():
+    """Empty batch, a 1 x 1 image, a batch that reuses one source for every row, a partner equal to the image itself."""
+    import device_input as D
+    from oracle import input_ops as O
+
+    u8 = np.random.default_rng(0).integers(0, 256, (3, 6, 8, 3), dtype=np.uint8)
+    assert run_emulated(u8, np.zeros((0, D.TABLE_COLS), np.int32), O.MEAN, O.STD).shape == (0, 3, 6, 8)
+    one = np.array([[[[0, 128, 255]]]], np.uint8)
+    d = D.Decision(0)
+    got = run_emulated(one, D.pack_table([d], {0: 0}), O.MEAN, O.STD, variant=2)
+    assert np.array_equal(got, O.input_batch(one, D.pack_table([d], {0: 0})))
+    ds = []
+    for i in range(5):  # every row reads source 1; mixing an image with itself must return it (both domains)
+        d = D.Decision(1)
+        d.mode, d.weight, d.box = 1 + i % 2, 0.3, (1, 1, 7, 5)
+        ds.append(d)
+    for before in (True, False):
+        table = D.pack_table(ds, {1: 1}, before, "const")
+        for variant in (1, 2):
+            got = run_emulated(u8, table, O.MEAN, O.STD, variant=variant)
+            plain = O._to_chw(u8[1], O.normalize_lut())
+            tol = 0 if before else 5e-7  # r x + (1 - r) x in float32
+            assert np.abs(got - plain[None]).max() <= tol, (before, variant)
+
+
 def test_kernel_source_on_host_random_shapes_and_tables():
     """Seeded random image sizes (vector and scalar paths, tiles that straddle rows and images), batch sizes and decision
     rows: both kernel variants, built for the host, against the oracle."""
@@ -237,6 +262,14 @@ def run_device(u8, table, mean, std, variant=1):
     finally:
         lib.set_option("input_variant", 1)
     return out.cpu().numpy()
+
+
+@pytest.mark.gpu
+def test_gpu_empty_batch_is_legal():
+    import device_input as D
+
+    out = D.DeviceInput()(torch.zeros((2, 8, 8, 3), dtype=torch.uint8), np.zeros((0, D.TABLE_COLS), np.int32))
+    assert out.shape == (0, 3, 8, 8) and out.is_cuda
 
 
 @pytest.mark.gpu

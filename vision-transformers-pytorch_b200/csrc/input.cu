@@ -347,11 +347,11 @@ void vtb_input_variant_set(int v) { g_input_variant = (v == 2) ? 2 : 1; }
 extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t* table, int32_t batch, int32_t H, int32_t W,
                                const float* mean3, const float* std3, float* out, vtb_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VTB_CHECK(batch >= 0 && H > 0 && W > 0, -1, "vtb_input_batch: bad shape batch=%d H=%d W=%d", batch, H, W);
+  if (batch == 0) return 0;  // an empty batch is legal (its table and output may be NULL)
   VTB_CHECK(src && table && out && mean3 && std3, -1, "vtb_input_batch: null pointer");
-  VTB_CHECK(n_src > 0 && batch >= 0 && H > 0 && W > 0, -1, "vtb_input_batch: bad shape n_src=%d batch=%d H=%d W=%d", n_src,
-            batch, H, W);
+  VTB_CHECK(n_src > 0, -1, "vtb_input_batch: no source images (n_src=%d) for a batch of %d", n_src, batch);
   VTB_CHECK(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, -1, "vtb_input_batch: zero std");
-  if (batch == 0) return 0;
   const int64_t HW = (int64_t)H * W;
   const bool vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) % 16 == 0);
