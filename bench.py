@@ -426,6 +426,26 @@ def main():
                 "launches_per_step": len(gemm), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
                 "model_tflops": value / world * wl["gflop"] / 1e3, "model_frac": value / world * wl["gflop"] / 1e3 / peak_tf}
 
+    # second half of the BASELINE metric ("attn tensor-pipe %"): the attention launches of the same instrumented step
+    # (CUDA events, algorithmic FLOPs / bytes) next to the tensor-pipe activity ncu measured for these kernels
+    try:
+        att = {k: [(f, a.elapsed_time(b), nb) for n, f, a, b, nb in prof if n == k] for k in ("attention_fwd", "attention_bwd")}
+        if att["attention_fwd"]:
+            pipe = None
+            ppath = os.path.join(ROOT, "profiles", "r01_attn_tensor_pipe.json")
+            if os.path.exists(ppath):
+                pipe = json.load(open(ppath)).get(args.workload)
+            roofline["attention"] = {"tensor_pipe_pct_ncu": pipe}
+            for k, rows in att.items():
+                t = sum(r[1] for r in rows)
+                if rows and t > 0:
+                    fl, nb = sum(r[0] for r in rows), sum(r[2] for r in rows)
+                    roofline["attention"][k] = {"launches": len(rows), "ms_per_step": t, "share_of_step": t / ms,
+                                                "tflops": fl / (t * 1e-3) / 1e12, "tensor_frac": fl / (t * 1e-3) / 1e12 / peak_tf,
+                                                "gbs": nb / (t * 1e-3) / 1e9, "hbm_frac": nb / (t * 1e-3) / 1e9 / peak_hbm}
+    except Exception as exc:  # noqa: BLE001  (reporting only: never lose the bench line over it)
+        roofline["attention"] = {"error": repr(exc)}
+
     # ---------------------------------------------------------------- end-to-end from host buffers (`e2e`)
     e2e = None
     if not args.no_e2e and is_dino:

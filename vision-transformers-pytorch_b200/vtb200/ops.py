@@ -302,7 +302,9 @@ def attention_fwd(spec, q, k, v):
     o = torch.empty((q.shape[0], spec.heads * spec.dh), dtype=BF16, device=q.device)
     lse = torch.empty((spec.groups, spec.heads, spec.nq), dtype=F32, device=q.device)
     p.o, p.ldo, p.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
-    with _prof("attention_fwd"):
+    hd = spec.heads * spec.dh
+    with _prof("attention_fwd", 4.0 * spec.groups * spec.heads * spec.nq * spec.nkv * spec.dh,
+               2.0 * hd * (2 * q.shape[0] + 2 * k.shape[0])):  # q, k, v read once, o written once (bf16)
         _l.check(lib.vtb_attention_fwd(C.byref(p), _stream()), lib)
     _count()
     return o, lse
@@ -326,7 +328,9 @@ def attention_bwd(spec, q, k, v, o, lse, dout, dq, dk, dv, drel_bias=None, dkv_f
     p.delta = delta.data_ptr()
     if drel_bias is not None:
         p.drel_bias = drel_bias.data_ptr()
-    with _prof("attention_bwd"):
+    hd = spec.heads * spec.dh
+    with _prof("attention_bwd", 10.0 * spec.groups * spec.heads * spec.nq * spec.nkv * spec.dh,
+               2.0 * hd * (4 * q.shape[0] + 4 * k.shape[0])):  # q, k, v, o, do read; dq, dk, dv written (bf16)
         _l.check(lib.vtb_attention_bwd(C.byref(p), _stream()), lib)
     _count(2)
 
