@@ -71,3 +71,30 @@ def test_drop_path_scales_are_consumed_in_branch_order():
     out0 = R.vit_forward(sd, x, dp_scales=zeros, **fx["oracle_kwargs"])
     # every branch dropped: the residual stream is just the embedding -> differs from the full model
     assert rel(out0, fx["output"]) > 1e-3
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_reference_bf16_autocast_error_level():
+    """What "matching the reference" can mean in bf16: the UNMODIFIED reference under its own training dtype flow
+    (torch.autocast, train.py:273; here on CPU) differs from its own fp32 output by 3e-3 .. 1e-2 rel-L2 on the golden
+    configurations, and at most a quarter of its logits are within the north star's rtol 1e-3.  The bf16 bars of the GPU
+    suite (outputs 2e-2 rel-L2) sit just above this level; tests/golden/autocast_levels.json records it."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    from oracle.make_golden import build
+
+    levels = json.load(open(os.path.join(GOLDEN, "autocast_levels.json")))["cases"]
+    ref = ref_loader.load()
+    for name in ("vit_tiny", "swin_w7", "pvt_tiny"):
+        fx = load_golden(name)
+        model = build(ref, fx["family"], fx["ctor"]).eval()
+        model.load_state_dict(fx["state_dict"], strict=True)
+        inp = [x.clone() for x in fx["inputs"]]
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            out = model(inp if len(inp) > 1 else inp[0]).float()
+        err = rel(out, fx["output"])
+        assert 1e-3 < err < 2e-2, (name, err)  # above the fp32 target, below the GPU suite's bf16 bar
+        assert err == pytest.approx(levels[name]["rel_l2"], rel=0.5), (name, err, levels[name])
+    assert all(v["rel_l2"] > 1e-3 and v["share_within_rtol_1e-3"] <= 0.5 for v in levels.values())
