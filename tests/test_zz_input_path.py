@@ -84,6 +84,64 @@ def test_oracle_matches_reference_batches(G):
         check_against_golden(case, O.input_batch(case["u8"].numpy(), table, G["mean"], G["std"]), name)
 
 
+def test_sampler_and_oracle_match_live_reference_on_random_configs():
+    """Build container only: 24 seeded random loader configurations (sizes, mixup / cutmix / erasing strengths, both
+    `mix_before_aug` orders) through the reference's OWN MixDataset + RandomErasing + torchvision + PIL, against the host
+    sampler + numpy oracle: labels and ratios equal, images bit-identical (<= 1 ulp for tensor-domain mixup)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree only exists in the build container")
+    from PIL import Image
+    from torchvision import transforms as T
+
+    import device_input as D
+    from oracle import input_ops as O
+
+    ref_mix = ref_loader.load_reference_module("mix_dataset")
+    ref_tf = ref_loader.load_reference_module("transforms")
+
+    class Images:
+        def __init__(self, u8, transform):
+            self.u8, self.transform = u8, transform
+
+        def __len__(self):
+            return len(self.u8)
+
+        def __getitem__(self, i):
+            return self.transform(Image.fromarray(self.u8[i])), int(i)
+
+    cfg = random.Random(77)
+    modes = set()
+    for trial in range(24):
+        H, W, n = cfg.randint(4, 30), cfg.randint(4, 30), cfg.randint(2, 6)
+        mixup, cutmix = cfg.choice([0.0, 0.2, 0.8]), cfg.choice([0.0, 0.5, 1.0])
+        erasing, before, seed = cfg.choice([0.0, 0.3, 0.9]), cfg.random() < 0.5, cfg.randrange(10 ** 6)
+        u8 = np.random.default_rng(trial).integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+        tail = [T.ToTensor(), T.Normalize(mean=list(O.MEAN), std=list(O.STD))]
+        if erasing > 0:
+            tail.append(ref_tf.RandomErasing(erasing, mode="const", max_count=1, num_splits=0, device="cpu"))
+        if before:
+            ds = ref_mix.MixDataset(Images(u8, lambda im: im), T.Compose(tail), mixup, cutmix)
+        else:
+            ds = ref_mix.MixDataset(Images(u8, T.Compose(tail)), T.Compose([]), mixup, cutmix)
+        random.seed(seed)
+        items = [ds[i] for i in range(n)]
+        s = D.MixSampler(mixup, cutmix, erasing, before, rng=random.Random(seed))
+        dec = [s.sample(i, n, H, W) for i in range(n)]
+        what = (trial, H, W, n, mixup, cutmix, erasing, before)
+        assert [d.index for d in dec] == [it[1] for it in items] and [d.partner for d in dec] == [it[2] for it in items], what
+        assert [float(d.ratio) for d in dec] == [float(it[3]) for it in items], what
+        got = O.input_batch(u8, D.pack_table(dec, {i: i for i in range(n)}, before, "const"))
+        want = np.stack([it[0].numpy() for it in items])
+        if not before and mixup > 0:
+            assert ulp_diff(got, want) <= 1, what
+        else:
+            assert np.array_equal(got.view(np.int32), want.view(np.int32)), what
+        modes |= {d.mode for d in dec}
+    assert modes == {0, 1, 2}
+
+
 def test_oracle_philox_known_answers():
     from oracle import input_ops as O
 
