@@ -33,8 +33,9 @@ int vtb_init(void);
  * "attn_wt" (0/1, default 1): tcgen05 window kernels (two windows per 128-row tile) for WINDOW problems with dh = 32 and
  * <= 64 tokens per window; 0 forces the mma.sync kernels (A/B measurements, cross-checks).
  * "ln_stream" (0/1, default 1): streaming (bulk-copy staged) LayerNorm kernels; 0 = register-resident kernels.
- * "input_variant" (1/2, default 1): vtb_input_batch kernel; 2 = the leaner variant written after the first ncu capture
- *   (same results; checked on the host build only so far; needs a 16-byte aligned table, else variant 1 runs). */
+ * "input_variant" (1/2/3, default 1): vtb_input_batch kernel; 2 = the leaner variant written after the first ncu capture,
+ *   3 = the same with 8 pixels per thread when W % 8 == 0 (same results; checked on the host build only so far; both need
+ *   a 16-byte aligned table, else variant 1 runs). */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -45,6 +45,7 @@ struct dim3_ { unsigned x, y, z; };
 static thread_local dim3_ threadIdx, blockIdx;
 static dim3_ gridDim, blockDim;
 struct uint4 { uint32_t x, y, z, w; };
+struct alignas(8) uint2 { uint32_t x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return {a, b, c, d}; }

@@ -240,7 +240,7 @@ def mixed_table(n, H, W, seed, erase_mode):
     return t
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_kernel_source_on_host_matches_golden_and_oracle(G, variant):
     from oracle import input_ops as O
 
@@ -252,6 +252,7 @@ def test_kernel_source_on_host_matches_golden_and_oracle(G, variant):
     # 44 / 1100 / 301: tiles spanning several rows, rows spanning several tiles, odd widths (scalar path)
     for (H, W), emode, mean, std in (((36, 44), "pixel", O.MEAN, O.STD), ((19, 37), "pixel", (0.5, 0.4, 0.3), (0.2, 0.25, 0.3)),
                                      ((36, 44), "const", O.MEAN, O.STD), ((5, 1100), "pixel", O.MEAN, O.STD),
+                                     ((20, 56), "pixel", O.MEAN, O.STD), ((9, 1104), "const", O.MEAN, O.STD),
                                      ((3, 301), "const", O.MEAN, O.STD)):
         u8 = np.random.default_rng(H).integers(0, 256, (7, H, W, 3), dtype=np.uint8)
         table = mixed_table(7, H, W, seed=W, erase_mode=emode)
@@ -281,7 +282,7 @@ def test_kernel_source_on_host_edge_cases():
         ds.append(d)
     for before in (True, False):
         table = D.pack_table(ds, {1: 1}, before, "const")
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             got = run_emulated(u8, table, O.MEAN, O.STD, variant=variant)
             plain = O._to_chw(u8[1], O.normalize_lut())
             tol = 0 if before else 5e-7  # r x + (1 - r) x in float32
@@ -295,13 +296,13 @@ def test_kernel_source_on_host_random_shapes_and_tables():
 
     rng = random.Random(2024)
     for trial in range(12):
-        H, W = rng.randint(1, 40), rng.choice([4, 8, 12, 36, 100]) if trial % 2 else rng.randint(1, 70)
+        H, W = rng.randint(1, 40), rng.choice([4, 8, 12, 16, 36, 72, 104]) if trial % 2 else rng.randint(1, 70)
         n = rng.randint(2, 5)
         u8 = np.random.default_rng(trial).integers(0, 256, (n, H, W, 3), dtype=np.uint8)
         table = mixed_table(n, H, W, seed=trial, erase_mode=rng.choice(["pixel", "const"]))
         table = table[np.random.default_rng(trial).permutation(len(table))][:rng.randint(1, len(table))]
         want = O.input_batch(u8, table)
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             got = run_emulated(u8, table, O.MEAN, O.STD, variant=variant)
             assert not np.isnan(got).any(), (trial, variant, H, W)
             assert np.abs(got - want).max() <= 2e-5, (trial, variant, H, W)
@@ -439,16 +440,17 @@ def test_gpu_deferred_meter_matches_blocking_meter():
 # ------------------------------------------------------------------------------------------------ variant 2 on the GPU
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("VTB_TEST_INPUT_V2") != "1",
-                    reason="variant 2 of the input kernel was written after the last GPU minute of round 1 (host-build parity "
-                           "only); set VTB_TEST_INPUT_V2=1 to run it — first job of round 2")
+                    reason="variants 2 / 3 of the input kernel were written after the last GPU minute of round 1 (host-build "
+                           "parity only); set VTB_TEST_INPUT_V2=1 to run them — first job of round 2")
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("H,W,emode", [(36, 44, "pixel"), (19, 37, "const"), (5, 1100, "pixel"), (224, 224, "pixel")])
-def test_gpu_variant2_matches_oracle_and_golden(G, H, W, emode):
+def test_gpu_lean_variants_match_oracle_and_golden(G, H, W, emode, variant):
     from oracle import input_ops as O
 
     u8 = np.random.default_rng(H).integers(0, 256, (7, H, W, 3), dtype=np.uint8)
     table = mixed_table(7, H, W, seed=W, erase_mode=emode)
-    got, want = run_device(u8, table, O.MEAN, O.STD, variant=2), O.input_batch(u8, table, O.MEAN, O.STD)
+    got, want = run_device(u8, table, O.MEAN, O.STD, variant=variant), O.input_batch(u8, table, O.MEAN, O.STD)
     assert np.abs(got - want).max() <= 2e-5
     for name, case in G["cases"].items():
         _, t = redraw(case)
-        check_against_golden(case, run_device(case["u8"].numpy(), t, G["mean"], G["std"], variant=2), name)
+        check_against_golden(case, run_device(case["u8"].numpy(), t, G["mean"], G["std"], variant=variant), name)

@@ -9,6 +9,7 @@ run() { name=$1; shift; timeout ${TMO:-300} "$@" > gpurun_out/$name.log 2>&1; ec
 [ -f tools/_selftest_input.npz ] || python tools/input_selftest.py --prepare > gpurun_out/prepare.log 2>&1
 TMO=60 TAILN=5 run selftest_v1 python tools/input_selftest.py
 TMO=60 TAILN=5 run selftest_v2 python tools/input_selftest.py --variant2
+TMO=60 TAILN=5 run selftest_v3 python tools/input_selftest.py --variant3
 TMO=120 TAILN=26 run cabi_gemm python tools/cabi_gemm_bench.py
 TMO=120 TAILN=16 run cabi_attn python tools/cabi_attn_bench.py
 TMO=1500 TAILN=12 run t_all env VTB_TEST_INPUT_V2=1 python -m pytest tests/ -x -q -m gpu --no-header -p no:cacheprovider

@@ -24,7 +24,7 @@ else:
     lib = C.CDLL(os.path.join(ROOT, "vision-transformers-pytorch_b200", "vtb200", "libvtb200.so"))
 if not EMULATE:
     lib.vtb_last_error.restype = C.c_char_p
-VARIANT = 2 if "--variant2" in sys.argv else 1  # kernel variant (vtb_set_option("input_variant", v))
+VARIANT = 3 if "--variant3" in sys.argv else (2 if "--variant2" in sys.argv else 1)  # kernel variant (vtb_set_option("input_variant", v))
 if EMULATE:
     getattr(lib, "_Z21vtb_input_variant_seti")(VARIANT)
 else:

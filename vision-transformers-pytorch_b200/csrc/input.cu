@@ -257,7 +257,9 @@ __device__ __forceinline__ void pixel2(const RowY& r, const float (*lut)[256], i
   }
 }
 
-template <bool VEC>
+// PPT pixels per thread: 1 (any width), 4 (W % 4 == 0: 3 x 32-bit loads per source, one 128-bit store per plane) or
+// 8 (W % 8 == 0: 3 x 64-bit loads, two 128-bit stores per plane — variant 3: twice the bytes in flight per thread)
+template <int PPT>
 __global__ void __launch_bounds__(IN_THREADS)
 input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* __restrict__ table,
                     float* __restrict__ out, int B, int H, int W, float m0, float m1, float m2, float s0, float s1,
@@ -270,7 +272,6 @@ input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* _
     for (int c = 0; c < 3; ++c) lut[c][threadIdx.x] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
   }
   __syncthreads();
-  constexpr int PPT = VEC ? 4 : 1;
   const uint32_t HW = (uint32_t)H * (uint32_t)W;  // < 2^31 (host check)
   const uint32_t n_items = (uint32_t)B * (uint32_t)tiles_per_image;
   for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -295,35 +296,57 @@ input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* _
     const uint8_t* s1p = src + ((int64_t)src1 * HW + p0) * 3;
     const uint8_t* s2p = src + ((int64_t)src2 * HW + p0) * 3;
     float* o = out + (int64_t)b * 3 * HW + p0;
-    if constexpr (VEC) {
-      uint32_t wa[3], wb[3];
+    if constexpr (PPT > 1) {
+      constexpr int NW = PPT * 3 / 4;  // 32-bit words of PPT packed RGB pixels
+      uint32_t wa[NW], wb[NW];
+      if constexpr (PPT == 8) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) wa[k] = __ldg(reinterpret_cast<const uint32_t*>(s1p) + k);
-      if (r.mode != 0) {
+        for (int k = 0; k < 3; ++k) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(s1p) + k);
+          wa[2 * k] = t.x, wa[2 * k + 1] = t.y;
+        }
+        if (r.mode != 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wb[k] = __ldg(reinterpret_cast<const uint32_t*>(s2p) + k);
+          for (int k = 0; k < 3; ++k) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(s2p) + k);
+            wb[2 * k] = t.x, wb[2 * k + 1] = t.y;
+          }
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wb[k] = wa[k];
-      }
-      float res[3][4];
+        for (int k = 0; k < NW; ++k) wa[k] = __ldg(reinterpret_cast<const uint32_t*>(s1p) + k);
+        if (r.mode != 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t a[3], p[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int k = j * 3 + c;
-          a[c] = (wa[k >> 2] >> (8 * (k & 3))) & 255u;
-          p[c] = (wb[k >> 2] >> (8 * (k & 3))) & 255u;
+          for (int k = 0; k < NW; ++k) wb[k] = __ldg(reinterpret_cast<const uint32_t*>(s2p) + k);
         }
-        float v[3];
-        pixel2(r, lut, y, x0 + j, a, p, v);
+      }
+      if (r.mode == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) res[c][j] = v[c];
+        for (int k = 0; k < NW; ++k) wb[k] = wa[k];
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        __stcs(reinterpret_cast<float4*>(o + (int64_t)c * HW), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+      for (int half = 0; half < PPT / 4; ++half) {  // four pixels at a time: one 128-bit store per colour plane
+        float res[3][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = half * 4 + jj;
+          uint32_t a[3], p[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int k = j * 3 + c;  // byte index inside the packed group (little-endian words)
+            a[c] = (wa[k >> 2] >> (8 * (k & 3))) & 255u;
+            p[c] = (wb[k >> 2] >> (8 * (k & 3))) & 255u;
+          }
+          float v[3];
+          pixel2(r, lut, y, x0 + j, a, p, v);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) res[c][jj] = v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          __stcs(reinterpret_cast<float4*>(o + (int64_t)c * HW + half * 4),
+                 make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+      }
     } else {
       uint32_t a[3], p[3];
 #pragma unroll
@@ -338,11 +361,11 @@ input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* _
   }
 }
 
-int g_input_variant = 1;  // 1: first kernel; 2: the lean one (vtb_set_option("input_variant", 2)) until it has been timed
+int g_input_variant = 1;  // 1: first kernel; 2: the lean one; 3: lean, 8 pixels per thread (vtb_set_option("input_variant", v))
 
 }  // namespace
 
-void vtb_input_variant_set(int v) { g_input_variant = (v == 2) ? 2 : 1; }
+void vtb_input_variant_set(int v) { g_input_variant = (v == 2 || v == 3) ? v : 1; }
 
 extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t* table, int32_t batch, int32_t H, int32_t W,
                                const float* mean3, const float* std3, float* out, vtb_stream_t stream_) {
@@ -355,20 +378,23 @@ extern "C" int vtb_input_batch(const uint8_t* src, int32_t n_src, const int32_t*
   const int64_t HW = (int64_t)H * W;
   const bool vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) % 16 == 0);
-  const int ppt = vec ? 4 : 1;
+  const bool lean = g_input_variant >= 2 && reinterpret_cast<uintptr_t>(table) % 16 == 0 && HW < (1ll << 31);
+  const bool wide = lean && g_input_variant == 3 && vec && W % 8 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0;
+  const int ppt = wide ? 8 : (vec ? 4 : 1);
   const int sms = vtb_num_sms() > 0 ? vtb_num_sms() : 148;  // vtb_init() not called yet: the B200 count
   const int64_t cap = (int64_t)sms * 8;                     // 8 resident CTAs of 256 threads per SM
   const int64_t tiles = (HW + (int64_t)IN_THREADS * ppt - 1) / ((int64_t)IN_THREADS * ppt);
   VTB_CHECK(tiles < (1ll << 30), -1, "vtb_input_batch: image too large");
   const int64_t items = (int64_t)batch * tiles;
   const int grid = (int)(items < cap ? items : cap);
-  if (g_input_variant == 2 && reinterpret_cast<uintptr_t>(table) % 16 == 0 && HW < (1ll << 31) && items < (1ll << 31)) {
-    if (vec)
-      input_batch_kernel2<true><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
-                                                                 mean3[2], std3[0], std3[1], std3[2], (int)tiles);
-    else
-      input_batch_kernel2<false><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],
-                                                                  mean3[2], std3[0], std3[1], std3[2], (int)tiles);
+  if (lean && items < (1ll << 31)) {
+#define VTB_INPUT_LAUNCH2(P)                                                                                          \
+  input_batch_kernel2<P><<<grid, IN_THREADS, 0, stream>>>(src, n_src, table, out, batch, H, W, mean3[0], mean3[1],    \
+                                                          mean3[2], std3[0], std3[1], std3[2], (int)tiles)
+    if (ppt == 8) VTB_INPUT_LAUNCH2(8);
+    else if (ppt == 4) VTB_INPUT_LAUNCH2(4);
+    else VTB_INPUT_LAUNCH2(1);
+#undef VTB_INPUT_LAUNCH2
     VTB_LAUNCH_CHECK();
     return 0;
   }
