@@ -123,28 +123,35 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_step(workload, batch, threads):
-    """One fwd+bwd of the oracle port on the host: returns a closure and the images per call."""
+def cpu_reference_step(workload, batch, threads, device="cpu", autocast=False):
+    """One fwd+bwd of the oracle port (plain PyTorch ops) — on the host by default (`cpu_baseline`, `--impl reference`);
+    with device="cuda", autocast=True it is the opt-in `--eager-baseline` leg: eager PyTorch under bf16 autocast on the same
+    GPU, the library path the reference itself would take.  Returns a closure running one step."""
+    import contextlib
+
     from oracle import restate as R
     import models
 
     torch.set_num_threads(threads)
     torch.manual_seed(1234)
     model = build_model(workload, drop_path=0.0)
-    sd = {k: (v.detach().clone().requires_grad_(v.is_floating_point())) for k, v in model.state_dict().items()}
+    sd = {k: (v.detach().clone().to(device).requires_grad_(v.is_floating_point())) for k, v in model.state_dict().items()}
+    cast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if autocast else contextlib.nullcontext
     if workload == "dino_deit_s":
-        xs = [torch.randn(batch, 3, 224, 224) for _ in range(2)] + [torch.randn(batch, 3, 96, 96) for _ in range(8)]
+        xs = [torch.randn(batch, 3, 224, 224, device=device) for _ in range(2)] + \
+             [torch.randn(batch, 3, 96, 96, device=device) for _ in range(8)]
         tsd = {k: v.detach().clone() for k, v in sd.items()}
-        center = torch.zeros(1, 65536)
+        center = torch.zeros(1, 65536, device=device)
 
         def dino_step():
             for v in sd.values():
                 if v.is_floating_point():
                     v.grad = None
-            with torch.no_grad():
-                t_out = R.vit_forward(tsd, xs[:2], patch=16, depth=12, heads=6, head_fn=lambda f: R.dino_head(tsd, f))
-            s_out = R.vit_forward(sd, xs, patch=16, depth=12, heads=6, head_fn=lambda f: R.dino_head(sd, f))
-            loss = R.dino_loss(s_out, t_out, center, 10)
+            with cast():
+                with torch.no_grad():
+                    t_out = R.vit_forward(tsd, xs[:2], patch=16, depth=12, heads=6, head_fn=lambda f: R.dino_head(tsd, f))
+                s_out = R.vit_forward(sd, xs, patch=16, depth=12, heads=6, head_fn=lambda f: R.dino_head(sd, f))
+                loss = R.dino_loss(s_out.float(), t_out.float(), center, 10)
             loss.backward()
             with torch.no_grad():
                 for k in tsd:
@@ -152,8 +159,8 @@ def cpu_reference_step(workload, batch, threads):
             return loss.item()
 
         return dino_step
-    x = torch.randn(batch, 3, 224, 224)
-    y = torch.randint(0, 1000, (batch,))
+    x = torch.randn(batch, 3, 224, 224, device=device)
+    y = torch.randint(0, 1000, (batch,), device=device)
 
     def fwd():
         if workload in ("vit_b16", "vit_tiny"):
@@ -170,7 +177,8 @@ def cpu_reference_step(workload, batch, threads):
         for v in sd.values():
             if v.is_floating_point():
                 v.grad = None
-        loss = torch.nn.functional.cross_entropy(fwd(), y)
+        with cast():
+            loss = torch.nn.functional.cross_entropy(fwd().float(), y)
         loss.backward()
         return loss.item()
 
@@ -213,6 +221,9 @@ def main():
     ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager-baseline", action="store_true",
+                    help="extra leg (opt-in): the oracle port (plain PyTorch ops) in eager mode under bf16 autocast on the same "
+                         "GPU — the library path the reference itself would take; a reported baseline")
     ap.add_argument("--e2e-u8", action="store_true",
                     help="extra leg (opt-in): the step fed through the device input path — pinned uint8 HWC batches + the "
                          "mixup / cutmix / erasing table -> vtb_input_batch -> step (SURVEY 8f rank 4)")
@@ -583,6 +594,30 @@ def main():
                     "includes": "fwd+bwd step + clip_grad_norm_(5.0) folded into AdamW(lr 2.5e-4, wd 0.05 / no-decay "
                                 "groups): vtb_mt_grad_norm + vtb_mt_adamw"}
 
+    # ---------------------------------------------------------------- opt-in: eager PyTorch on the same GPU (baseline)
+    eager = None
+    if args.eager_baseline and rank == 0:
+        for eb in (B, B // 2, B // 4, B // 8):
+            try:
+                estep = cpu_reference_step(args.workload, eb, os.cpu_count() or 1, device=dev, autocast=True)
+                estep()
+                estep()
+                torch.cuda.synchronize()
+                n = 5
+                e0.record()
+                for _ in range(n):
+                    estep()
+                e1.record()
+                torch.cuda.synchronize()
+                ems = e0.elapsed_time(e1) / n
+                eager = {"value": eb / (ems * 1e-3), "unit": "images/s", "ms_per_step": ems, "batch": eb,
+                         "kind": "oracle port (plain PyTorch ops: F.linear / matmul / softmax / layer_norm) in eager mode under "
+                                 "bf16 autocast, same GPU, same step (fwd + loss + bwd, loss.item() per step)"}
+                break
+            except torch.OutOfMemoryError:
+                estep = None
+                torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- CPU baseline (oracle port, bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -613,6 +648,8 @@ def main():
                 "with_optimizer": with_opt}
         if e2e_u8 is not None:
             line["e2e_u8"] = e2e_u8
+        if eager is not None:
+            line["eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
