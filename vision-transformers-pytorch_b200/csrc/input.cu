@@ -187,7 +187,7 @@ input_batch_kernel(const uint8_t* __restrict__ src, int n_src, const int32_t* __
 
 // ------------------------------------------------------------------------------------------------ variant 2
 // Same arithmetic and the same flat 1024-pixel tiles as variant 1, leaner per item.  Why: the first ncu capture of variant 1
-// (profiles/r01_ncu_full_input_kernel.txt) shows the XU pipe 94 % busy, 464 warp instructions per 128 pixels and 21 of 27
+// (profiles/r01_ncu_full_input_kernel.txt) shows 68 % of the issue slots busy, 464 warp instructions per 128 pixels, long_scoreboard as the top stall and 21 of 27
 // global loads per thread spent on the decision row.  A first rewrite with row-shaped work items, the row staged in shared
 // memory and two barriers per item was parity-green on the B200 but SLOWER (83 vs 72 us, profiles/
 // r01_input_kernel_selftest_rowtiled_variant.log): with 4 CTAs per SM the barriers serialise the row -> source load chain.
