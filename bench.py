@@ -221,6 +221,11 @@ def main():
     ap.add_argument("--reducer", default="ddp", choices=["ddp", "flat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dino-graph", action="store_true",
+                    help="DINO at N > 1 (opt-in): capture the step as a CUDA graph with the centre update deferred — the column "
+                         "sum of the teacher logits is written to a static buffer inside the graph, its all-reduce and the EMA "
+                         "of the centre run right after the replay (same arithmetic: the loss of a step never sees its own "
+                         "centre update, loss.py:119-152)")
     ap.add_argument("--eager-baseline", action="store_true",
                     help="extra leg (opt-in): the oracle port (plain PyTorch ops) in eager mode under bf16 autocast on the same "
                          "GPU — the library path the reference itself would take; a reported baseline")
@@ -259,7 +264,7 @@ def main():
     params = [p for p in model.parameters() if p.requires_grad]
     is_dino = args.workload == "dino_deit_s"
     if is_dino:
-        if world > 1:
+        if world > 1 and not args.dino_graph:
             args.no_graph = True  # the centre all-reduce sits in the middle of the step: issued eagerly with the rest
         teacher = build_model(args.workload, drop_path=0.0).to(dev)
         teacher.load_state_dict(model.state_dict())
@@ -289,6 +294,10 @@ def main():
                     [torch.randn(B, 3, 96, 96, device=dev) for _ in range(8)]
         x_dev = crops_dev
 
+    # --dino-graph at N > 1: the centre update leaves the captured step (see the flag's help)
+    dino_state = {"defer_center": bool(is_dino and world > 1 and args.dino_graph and not args.no_graph),
+                  "bc": torch.zeros(1, 65536, device=dev) if is_dino else None, "rows": 0}
+
     def dino_loss_fn(student, teacher_out):
         """DINOLoss.forward (loss.py:119-152): centred / sharpened teacher softmax vs student log-softmax over every
         other crop as ONE fused kernel (vtb_dino_loss: loss + student gradient), then the EMA centre update with its
@@ -296,6 +305,10 @@ def main():
         from vtb200.blocks import DINOLossFn
 
         loss = DINOLossFn.apply(student.float(), teacher_out.float(), center, 10, 0.1, 0.04)
+        if dino_state["defer_center"]:
+            dino_state["bc"].copy_(teacher_out.sum(0, keepdim=True))
+            dino_state["rows"] = teacher_out.shape[0]
+            return loss
         bc = teacher_out.sum(0, keepdim=True)
         if world > 1:
             dist.all_reduce(bc)
@@ -333,6 +346,9 @@ def main():
             loss = graphed.replay()
         else:
             loss = fwd_bwd(x, y)
+        if is_dino and dino_state["defer_center"]:
+            dist.all_reduce(dino_state["bc"])
+            center.mul_(0.9).add_(dino_state["bc"], alpha=0.1 / (dino_state["rows"] * world))
         if reducer is not None:
             reducer.reduce()
         return loss
@@ -353,6 +369,7 @@ def main():
                 raise
             print(f"bench.py: CUDA-graph capture of the DINO step failed ({exc!r}); issuing eagerly", file=sys.stderr)
             graphed, use_graph = None, False
+            dino_state["defer_center"] = False
     graph_grads = [p.grad for p in params] if use_graph else None  # the graph's own (address-stable) gradient buffers
     for _ in range(W):
         step(x_dev, y_dev)
