@@ -11,6 +11,7 @@ train.py:265-283 without the optimizer (metric: "images/sec fwd+bwd").  `value` 
 --impl reference times the oracle port of the reference path on the host cores (oracle/restate.py).
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -433,8 +434,9 @@ def main():
     peak_tf, peak_hbm, peak_src = peaks()
     # DRAM traffic of the GEMM launches from the committed ncu capture of this same command (per launch, like `achieved`)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", f"r01_gemm_traffic_{args.workload}.json")
-    if os.path.exists(tpath):
+    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r[0-9][0-9]_gemm_traffic_{args.workload}.json")))
+    tpath = tpaths[-1] if tpaths else None  # the latest round's capture
+    if tpath:
         traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     achieved_gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0
@@ -449,7 +451,8 @@ def main():
                 "hbm": {"achieved": achieved_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": achieved_gbs / peak_hbm,
                         "algorithmic_bytes_per_launch": (gemm_bytes / len(gemm)) if gemm else None},
                 "traffic": traffic,
-                "traffic_unit": "bytes per GEMM launch (ncu dram__bytes_read+write, profiles/r01_gemm_traffic_*.json)",
+                "traffic_unit": "bytes per GEMM launch (ncu dram__bytes_read+write, "
+                                + (("profiles/" + os.path.basename(tpath)) if tpath else "no capture committed") + ")",
                 "flop_per_launch": (gemm_flops / len(gemm)) if gemm else None, "peak_source": peak_src,
                 "launches_per_step": len(gemm), "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
                 "model_tflops": value / world * wl["gflop"] / 1e3, "model_frac": value / world * wl["gflop"] / 1e3 / peak_tf}
@@ -460,9 +463,9 @@ def main():
         att = {k: [(f, a.elapsed_time(b), nb) for n, f, a, b, nb in prof if n == k] for k in ("attention_fwd", "attention_bwd")}
         if att["attention_fwd"]:
             pipe = None
-            ppath = os.path.join(ROOT, "profiles", "r01_attn_tensor_pipe.json")
-            if os.path.exists(ppath):
-                pipe = json.load(open(ppath)).get(args.workload)
+            ppaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_attn_tensor_pipe.json")))
+            if ppaths:
+                pipe = json.load(open(ppaths[-1])).get(args.workload)
             roofline["attention"] = {"tensor_pipe_pct_ncu": pipe}
             for k, rows in att.items():
                 t = sum(r[1] for r in rows)
