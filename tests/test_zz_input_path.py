@@ -308,6 +308,50 @@ def test_kernel_source_on_host_random_shapes_and_tables():
             assert np.abs(got - want).max() <= 2e-5, (trial, variant, H, W)
 
 
+def test_device_input_wrapper_over_host_build(G, monkeypatch):
+    """The Python side of the boundary (DeviceInput, make_batch: validation, table upload, ctypes call, empty batch) run
+    end to end on the CPU against the host build of the kernel source, with the CUDA-only torch calls stubbed out."""
+    import contextlib
+    import types
+
+    import device_input as D
+    import kernel_emulation as K
+    from oracle import input_ops as O
+    from vtb200 import lib
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: the GPU tests cover the wrapper")
+    emul = K.build("input.cu")
+    emul.vtb_input_batch.argtypes = lib.load().vtb_input_batch.argtypes
+    getattr(emul, "_Z21vtb_input_variant_seti")(1)
+    monkeypatch.setattr(lib, "get", lambda: emul)
+    monkeypatch.setattr(lib, "check", lambda rc, handle=None: None if rc == 0 else pytest.fail(f"rc={rc}"))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, stream: None, raising=False)
+    pipe = D.DeviceInput(G["mean"], G["std"], device="cpu")
+    for name, case in G["cases"].items():
+        _, table = redraw(case)
+        check_against_golden(case, pipe(case["u8"], table).numpy(), name)
+    assert pipe(torch.zeros((2, 8, 8, 3), dtype=torch.uint8), np.zeros((0, D.TABLE_COLS), np.int32)).shape == (0, 3, 8, 8)
+    with pytest.raises(ValueError):
+        pipe(torch.zeros((2, 8, 8, 4), dtype=torch.uint8), np.zeros((0, D.TABLE_COLS), np.int32))  # not RGB
+    bad = D.pack_table([D.Decision(0)], {0: 5})
+    with pytest.raises(ValueError):
+        pipe(torch.zeros((2, 8, 8, 3), dtype=torch.uint8), bad)  # source slot 5 of 2
+    n, H, W = 12, 32, 32
+    data = np.random.default_rng(0).integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    labels = list(range(100, 100 + n))
+    mk = lambda: D.MixSampler(0.8, 1.0, 0.25, mix_before_aug=True, rng=random.Random(9), noise_seed=4)  # noqa: E731
+    batch, l1, l2, ratio = D.make_batch([0, 1, 2, 3, 4, 5], lambda i: data[i], n, mk(), D.DeviceInput(device="cpu"), labels)
+    sampler = mk()
+    ds = [sampler.sample(i, n, H, W) for i in range(6)]
+    want = O.input_batch(data, D.pack_table(ds, {i: i for i in range(n)}, True, "pixel"))
+    assert np.abs(batch.numpy() - want).max() <= 2e-5
+    assert l1.tolist() == labels[:6] and l2.tolist() == [labels[d.partner] for d in ds]
+    assert ratio.tolist() == [float(d.ratio) for d in ds]
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def run_device(u8, table, mean, std, variant=1):
     import device_input as D
