@@ -13,5 +13,6 @@ TMO=60 TAILN=5 run selftest_v3 python tools/input_selftest.py --variant3
 TMO=120 TAILN=26 run cabi_gemm python tools/cabi_gemm_bench.py
 TMO=120 TAILN=16 run cabi_attn python tools/cabi_attn_bench.py
 TMO=120 TAILN=12 run cabi_step python tools/cabi_step_bench.py
+TMO=120 TAILN=10 run cabi_ln python tools/cabi_ln_bench.py
 TMO=1500 TAILN=12 run t_all env VTB_TEST_INPUT_V2=1 python -m pytest tests/ -x -q -m gpu --no-header -p no:cacheprovider
 TMO=600 TAILN=1 CUT=5000 run bench_default python bench.py --e2e-u8 --eager-baseline
