@@ -241,10 +241,69 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--nvtx-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    ap.add_argument("--only", action="store_true",
+                    help="one workload, one line: skip the default run's extra legs (no_graph, eager_baseline, swin_s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    return run_default(args)
 
+
+def _release():
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
+def run_default(args):
+    """The driver's default command.  Primary line = `--workload` (vit_b16: the configuration the metric is quoted on); the
+    default run (no --only, no profiling flag) adds, in the same JSON line:
+      no_graph        the drop-in path as the reference trainer drives it (train.py:265-299): every kernel issued from
+                      Python, stock DDP at N > 1, loss.item() per step — no CUDA graph, no flat reducer;
+      eager_baseline  the kernel to beat: the oracle port in eager PyTorch (cuBLASLt / ATen) under bf16 autocast on the
+                      same GPU, same step (rank 0 only, N = 1 semantics);
+      swin_s          the second half of the metric (value / e2e / roofline / clocks of the Swin-S step);
+      speedup_vs_eager_gpu = value / eager_baseline.value per GPU (the honest speed-up; the CPU ratio is not)."""
+    import copy
+
+    import torch.distributed as dist
+
+    extras = not (args.only or args.nvtx_step or args.no_graph or args.workload not in ("vit_b16",))
+    if extras:
+        args.eager_baseline = True
+    line = run_one(args)
+    rank = int(os.environ.get("RANK", 0))
+    if extras:
+        _release()
+        a2 = copy.copy(args)
+        a2.no_graph, a2.reducer, a2.eager_baseline, a2.e2e_u8 = True, "ddp", False, False
+        a2.no_cpu_baseline = a2.no_optimizer_leg = True
+        a2.steps = min(args.steps, 10)
+        ng = run_one(a2, light=True)
+        _release()
+        a3 = copy.copy(args)
+        a3.workload, a3.batch, a3.eager_baseline, a3.e2e_u8 = "swin_s", 0, True, False
+        sw = run_one(a3)
+        if rank == 0:
+            line["no_graph"] = {k: ng[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+            line["no_graph"]["host_issue_ms_per_step"] = ng["config"]["host_issue_ms_per_step"]
+            line["no_graph"]["reducer"] = ng["config"]["reducer"]
+            line["no_graph"]["execution"] = "eager launches from Python (autograd.Function per branch), stock DDP at N > 1"
+            line["swin_s"] = {k: sw.get(k) for k in ("value", "unit", "ms_per_step", "e2e", "roofline", "clocks", "gpu_launches",
+                                                   "cpu_baseline", "eager_baseline", "with_optimizer", "config")}
+    if rank == 0:
+        for d in (line, line.get("swin_s")):
+            if d and d.get("eager_baseline"):  # per GPU: the eager leg runs on one GPU
+                d["speedup_vs_eager_gpu"] = d["value"] / line["n_gpus"] / d["eager_baseline"]["value"]
+        print(json.dumps(line), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def run_one(args, light=False):
+    """One workload through the product path; returns the JSON line as a dict on rank 0 (None elsewhere)."""
     import torch.distributed as dist
     from vtb200 import dist as vd
     import loss as vloss
@@ -381,7 +440,7 @@ def main():
         step(x_dev, y_dev)
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
-        return
+        return None
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -417,7 +476,7 @@ def main():
     gemm_ms = sum(t for _, _, t, _ in gemm)
     gemm_flops = sum(f for _, f, _, _ in gemm)
     gemm_bytes = sum(nb for _, _, _, nb in gemm)
-    if rank == 0:
+    if rank == 0 and not light:
         agg = {}
         for n, f, a, b, _nb in prof:
             t = a.elapsed_time(b)
@@ -653,6 +712,7 @@ def main():
         cpu = {"value": cb / dt, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"{args.workload} fp32 fwd+bwd, batch {cb}, mean of {n} steps after 1 warm-up (oracle/restate.py)"}
 
+    line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -670,9 +730,13 @@ def main():
             line["e2e_u8"] = e2e_u8
         if eager is not None:
             line["eager_baseline"] = eager
-        print(json.dumps(line), flush=True)
+    if getattr(model, "_vtb_weight_arena", None) is not None:
+        multi.disable_weight_arena(model)
+    if is_dino and getattr(teacher, "_vtb_weight_arena", None) is not None:
+        multi.disable_weight_arena(teacher)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()  # rank 0 ran the baselines alone
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -420,6 +420,42 @@ def test_accumulate_matches_reference_loop_on_a_model():
         assert torch.equal(p.detach(), dict(b.named_parameters())[k].detach()), k
 
 
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.gpu
+def test_run_to_run_determinism_contract():
+    """The guarantee, stated and tested: two identical fwd+bwd runs give BIT-EQUAL outputs (no forward kernel uses
+    atomics) and parameter gradients equal to fp32 reduction rounding (rel-L2 < 1e-5): weight / bias / LN-parameter
+    gradients are reduced with fp32 atomics or TMA reduce-add whose arrival order is not fixed.  The reference's ATen
+    path has the same property (cuBLAS split-K, atomicAdd in layer_norm backward / embedding backward)."""
+    import models
+    import models.twins
+    from conftest import load_golden
+
+    nets, xs = [], []
+    for name in ("vit_tiny", "swin_w7", "pvt_tiny", "halo_w7", "twins_w7"):
+        fx = load_golden(name)
+        ctor = {"vit": models.VisionTransformer, "swin": models.SwinTransformer, "pvt": models.PyramidVisionTransformer,
+                "halo": models.HaloTransformer, "twins": models.twins.TwinsSVT}[fx["family"]]
+        m = ctor(**fx["ctor"])
+        m.load_state_dict(fx["state_dict"], strict=True)
+        nets.append(m.cuda().eval())
+        xs.append(fx["inputs"][0].cuda())
+    for net, x in zip(nets, xs):
+        runs = []
+        for _ in range(3):
+            net.zero_grad(set_to_none=True)
+            y = net(x)
+            y.square().sum().backward()
+            runs.append((y.detach().clone(), [p.grad.clone() for p in net.parameters()]))
+        for y, g in runs[1:]:
+            assert torch.equal(y, runs[0][0])
+            for a, b in zip(g, runs[0][1]):
+                assert _rel(a, b) < 1e-5, _rel(a, b)
+
+
 @pytest.mark.gpu
 def test_weight_arena_matches_per_call_casts_and_tracks_updates():
     """enable_weight_arena: same logits and gradients as the per-Linear casts, fewer launches, and weights rewritten
@@ -444,7 +480,12 @@ def test_weight_arena_matches_per_call_casts_and_tracks_updates():
     arena = multi.enable_weight_arena(net)
     try:
         y1, g1, l1 = run()
-        assert torch.equal(y0, y1) and all(torch.equal(a, b) for a, b in zip(g0, g1))
+        # forward: no atomics anywhere -> bit-equal.  Parameter gradients are accumulated with fp32 atomics / TMA
+        # reduce-add (split-K wgrad, a_colsum, LN dgamma/dbeta), so their summation order differs run to run:
+        # equal up to fp32 rounding of the reduction (see test_run_to_run_determinism_contract)
+        assert torch.equal(y0, y1)
+        for a, b in zip(g0, g1):
+            assert _rel(a, b) < 1e-5, _rel(a, b)
         assert l1 < l0, (l0, l1)
         # optimizer step through the library (invisible to torch's version counters), then through torch
         opt = O.AdamW(net.parameters(), lr=1e-2)

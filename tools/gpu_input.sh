@@ -7,7 +7,7 @@ python tools/input_selftest.py --prepare > /dev/null 2>&1 || true   # needs test
 TAILN=20 run selftest_v1 python tools/input_selftest.py
 TAILN=20 run selftest_v2 python tools/input_selftest.py --variant2
 TAILN=20 run selftest_v3 python tools/input_selftest.py --variant3
-TAILN=15 VTB_TEST_INPUT_V2=1 run t_input env VTB_TEST_INPUT_V2=1 python -m pytest tests/test_zz_input_path.py -x -q -m gpu --no-header -p no:cacheprovider
+TAILN=15 VTB_TEST_INPUT_V2=1 run t_input env VTB_TEST_INPUT_V2=1 python -m pytest tests/test_input_path.py -x -q -m gpu --no-header -p no:cacheprovider
 run bench_input python tools/bench_input.py
 TAILN=1 CUT=4000 run bench_e2e_u8 python bench.py --workload swin_s --e2e-u8 --no-cpu-baseline --no-optimizer-leg --steps 10
 TMO=600 run ncu_input ncu --set full --clock-control none --import-source on -k regex:input_batch_kernel -c 3 \
