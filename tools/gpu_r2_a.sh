@@ -7,4 +7,4 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader | te
 nproc | tee -a gpurun_out/summary.txt
 TMO=1200 TAILN=30 run t_all env VTB_TEST_INPUT_V2=1 python -m pytest tests/ -q -m gpu --no-header -p no:cacheprovider
 TMO=900 TAILN=1 CUT=12000 run bench_default python bench.py
-cp gpurun_out/breakdown_*.txt gpurun_out/ 2>/dev/null
+
