@@ -21,6 +21,9 @@ from vtb200 import lib as L  # noqa: E402
 cu.init()
 lib = L.load()
 L.check(lib.vtb_init(), lib)
+for kv in filter(None, os.environ.get("VTB_OPTS", "").split(",")):  # e.g. VTB_OPTS=attn_tc_fwd_version=1,attn_tc_bwd_version=1
+    name, val = kv.split("=")
+    L.check(lib.vtb_set_option(name.encode(), int(val)), lib)
 F32, BF16 = np.float32, np.uint16
 PEAK_GB = 6543.1
 
@@ -196,10 +199,17 @@ def bench(tag, mode, seed, **kw):
 only = os.environ.get("ATTN_ONLY", "")
 Bn = int(os.environ.get("ATTN_BATCH", "256"))
 ok = True
-if only in ("", "global"):
+if os.environ.get("ATTN_SKIP_CHECK"):
+    only_check, only = "none", only
+else:
+    only_check = only
+if only_check in ("", "global"):
     ok &= self_check(L.ATTN_GLOBAL, B=2, H=2, dh=64, n=197)
     ok &= self_check(L.ATTN_GLOBAL, B=3, H=1, dh=64, n=37)
-if only in ("", "window"):
+    for kw in (dict(B=5, H=3, n=197), dict(B=5, H=1, n=37), dict(B=2, H=2, n=50), dict(B=1, H=2, n=256), dict(B=2, H=1, n=128),
+               dict(B=1, H=3, n=129), dict(B=1, H=1, n=16), dict(B=2, H=2, n=145), dict(B=150, H=2, n=197)):
+        ok &= self_check(L.ATTN_GLOBAL, dh=64, **kw)
+if only_check in ("", "window"):
     ok &= self_check(L.ATTN_WINDOW, B=1, H=2, dh=32, n=49, Hs=14, W=7, shift=True)
     ok &= self_check(L.ATTN_WINDOW, B=2, H=3, dh=32, n=49, Hs=14, W=7, shift=False)
 if not ok:

@@ -235,6 +235,318 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward, version 2: PERSISTENT, one CTA per SM, two query tiles in flight, loads prefetched one work item ahead.
+//
+// A work item is a pair of 128-query tiles that share one TMA stage (96 KB: Q0 Q1 | K[256] | V[256]):
+//   * shared mode  (nq > 128 or nkv > 128: ViT-B / DeiT-S at 224^2, PVT): both tiles belong to one (image, head), the
+//     keys / values are loaded ONCE for both (version 1 loaded them once per tile);
+//   * paired mode  (nq <= 128 and nkv <= 128: 96^2 crops with 37 tokens, the PVT cls stage): the tiles are two
+//     different (image, head) problems, tile t uses key rows [128 t, 128 t + nkv) of the stage.
+// warp 0 lane 0: TMA producer (2-stage ring, full / empty mbarriers);   warp 1 lane 0: UMMA issuer;
+// warps 2-5: softmax + epilogue of tile 0, warps 6-9: of tile 1 (one query row per thread = one TMEM lane).
+// TMEM: tile t owns columns [256 t, 256 t + 256): S at +0 (P written back over it as bf16 pairs), O at +128.
+// While set 0 runs its softmax the tensor pipe computes S of tile 1; while set 1 finishes, P V of tile 0 and the
+// next item's S of tile 0 are issued, and the next item's Q / K / V have been in flight since the stage was released.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int F2_THREADS = 320;
+constexpr int F2_STAGE = 6 * 16384;
+constexpr int SMEM_F2 = 2 * F2_STAGE + 1024 + 256;
+
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// work item -> (image * heads + head, first query token) of tile t, and the number of tiles (1 or 2) of the item
+__device__ __forceinline__ int f2_ntile(int item, int ppb, int paired, int n_bh, int nq) {
+  if (paired) return (2 * item + 1 < n_bh) ? 2 : 1;
+  return ((item % ppb) * 256 + 128 < nq) ? 2 : 1;
+}
+__device__ __forceinline__ int f2_bh(int item, int t, int ppb, int paired) { return paired ? 2 * item + t : item / ppb; }
+__device__ __forceinline__ int f2_q0(int item, int t, int ppb, int paired) { return paired ? 0 : (item % ppb) * 256 + t * 128; }
+
+// row maximum over W (16 or 32) score columns already in registers; MASK: columns >= lim do not count
+template <int W, bool MASK>
+__device__ __forceinline__ float f2_rowmax(const uint32_t (&a)[W], int lim, float mx) {
+  float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < W; j += 4) {
+    if (!MASK || j < lim) m0 = fmaxf(m0, __uint_as_float(a[j]));
+    if (!MASK || j + 1 < lim) m1 = fmaxf(m1, __uint_as_float(a[j + 1]));
+    if (!MASK || j + 2 < lim) m2 = fmaxf(m2, __uint_as_float(a[j + 2]));
+    if (!MASK || j + 3 < lim) m3 = fmaxf(m3, __uint_as_float(a[j + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// p = exp2(s * sl2 - mb) for W columns in registers, bf16 pairs stored at `paddr`; returns the row sum of the chunk
+template <int W, bool MASK>
+__device__ __forceinline__ float f2_probs(const uint32_t (&a)[W], uint32_t paddr, int lim, float sl2, float mb) {
+  uint32_t pk[16];
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < W; j += 2) {
+    float p0 = ex2f(fmaf(__uint_as_float(a[j]), sl2, -mb));
+    float p1 = ex2f(fmaf(__uint_as_float(a[j + 1]), sl2, -mb));
+    if (MASK) {
+      p0 = (j < lim) ? p0 : 0.f;
+      p1 = (j + 1 < lim) ? p1 : 0.f;
+    }
+    s0 += p0; s1 += p1;
+    pk[j >> 1] = pack_bf16(p0, p1);
+  }
+  if (W == 32) tmem_st_32x16(paddr, pk);
+  else tmem_st_32x8(paddr, pk);
+  return s0 + s1;
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                    const __grid_constant__ CUtensorMap tv, bf16* __restrict__ O, int ldo, float* __restrict__ lse,
+                    int heads, int nq, int nkv, int n_bh, int n_items, int ppb, int paired, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * F2_STAGE);
+  uint64_t* bar_full = bars;        // [2] TMA -> issuer: the stage's Q / K / V landed
+  uint64_t* bar_empty = bars + 2;   // [2] issuer -> TMA: every MMA reading the stage retired
+  uint64_t* bar_s = bars + 4;       // [2] per tile: S complete
+  uint64_t* bar_p = bars + 6;       // [2] per tile: P written (4 warps)
+  uint64_t* bar_o = bars + 8;       // [2] per tile: O complete
+  uint64_t* bar_free = bars + 10;   // [2] per tile: O read out, the tile's TMEM columns may be overwritten (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ns = (nkv + 15) & ~15;  // UMMA N of the score tile / contraction length of P V
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, 1); mbar_init(bar_s + i, 1); mbar_init(bar_p + i, 4);
+        mbar_init(bar_o + i, 1); mbar_init(bar_free + i, 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int nbox = (nkv > 128) ? 2 : 1;
+      int k = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+        const int s = k & 1;
+        mbar_wait(bar_empty + s, (uint32_t)(((k >> 1) & 1) ^ 1));
+        const int ntile = f2_ntile(item, ppb, paired, n_bh, nq);
+        uint8_t* sQ = smem + s * F2_STAGE;
+        uint8_t* sK = sQ + 2 * 16384;
+        uint8_t* sV = sK + 2 * 16384;
+        const int kv_boxes = paired ? ntile : nbox;
+        mbar_expect_tx(bar_full + s, (uint32_t)((ntile + 2 * kv_boxes) * 16384));
+        for (int t = 0; t < ntile; ++t) {
+          const int bh = f2_bh(item, t, ppb, paired);
+          tma_load_3d(sQ + t * 16384, &tq, bar_full + s, (bh % heads) * DH, f2_q0(item, t, ppb, paired), bh / heads);
+        }
+        for (int i = 0; i < kv_boxes; ++i) {
+          const int bh = f2_bh(item, i, ppb, paired);
+          const int tok = paired ? 0 : i * 128;
+          tma_load_3d(sK + i * 16384, &tk, bar_full + s, (bh % heads) * DH, tok, bh / heads);
+          tma_load_3d(sV + i * 16384, &tv, bar_full + s, (bh % heads) * DH, tok, bh / heads);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(TQ, ns, 0, 0);   // S = Q K^T: both operands K-major
+      const uint32_t idesc_o = umma_idesc_bf16(TQ, DH, 0, 1);   // O = P V: A = P from TMEM, B = V MN-major
+      // The two tiles are independent streams  S_t(i) -> softmax -> PV_t(i) -> epilogue -> S_t(i+1) ...; they are served in
+      // the fixed order  PV_0(i), S_0(i+1), PV_1(i), S_1(i+1): tile 1 then trails tile 0 by at least (P V + epilogue + S), so
+      // the exp-heavy second pass of one warp set overlaps the MUFU-free phases (waits, row max, epilogue) of the other.
+      auto issue_s = [&](int t, int s) {
+        const uint32_t qa = smem_u32(smem + s * F2_STAGE), ka = qa + 2 * 16384;
+        const uint32_t koff = paired ? (uint32_t)t * 16384u : 0u;
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(tmem_base + t * 256, umma_desc_sw128(qa + t * 16384 + kk * 32, 0, 1024),
+                    umma_desc_sw128(ka + koff + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(bar_s + t);
+      };
+      auto issue_pv = [&](int t, int s) {
+        const uint32_t va = smem_u32(smem + s * F2_STAGE) + 4 * 16384;
+        const uint32_t koff = paired ? (uint32_t)t * 16384u : 0u;
+        for (int kk = 0; kk < ns / 16; ++kk)
+          umma_bf16_ts(tmem_base + t * 256 + O_COL, tmem_base + t * 256 + kk * 8,
+                       umma_desc_sw128(va + koff + kk * 2048, 0, 1024), idesc_o, kk > 0 ? 1u : 0u);
+        umma_commit(bar_o + t);
+      };
+      int it0 = 0, it1 = 0, k = 0;   // per-tile iteration counters (tile 1 is absent from some items), local item counter
+      int item = blockIdx.x;
+      if (item < n_items) {
+        mbar_wait(bar_full, 0);
+        tc_fence_after();
+        issue_s(0, 0);
+        if (f2_ntile(item, ppb, paired, n_bh, nq) > 1) issue_s(1, 0);
+      }
+      for (; item < n_items; item += gridDim.x, ++k) {
+        const int s = k & 1;
+        const int ntile = f2_ntile(item, ppb, paired, n_bh, nq);
+        const int nxt = item + gridDim.x;
+        const bool has_next = nxt < n_items;
+        const int ntile_next = has_next ? f2_ntile(nxt, ppb, paired, n_bh, nq) : 0;
+        mbar_wait(bar_p, (uint32_t)(it0 & 1));
+        tc_fence_after();
+        issue_pv(0, s);
+        if (ntile == 1) umma_commit(bar_empty + s);
+        ++it0;
+        if (has_next) {
+          mbar_wait(bar_full + (s ^ 1), (uint32_t)(((k + 1) >> 1) & 1));
+          mbar_wait(bar_free, (uint32_t)((it0 & 1) ^ 1));
+          tc_fence_after();
+          issue_s(0, s ^ 1);
+        }
+        if (ntile > 1) {
+          mbar_wait(bar_p + 1, (uint32_t)(it1 & 1));
+          tc_fence_after();
+          issue_pv(1, s);
+          umma_commit(bar_empty + s);
+          ++it1;
+        }
+        if (ntile_next > 1) {
+          mbar_wait(bar_free + 1, (uint32_t)((it1 & 1) ^ 1));
+          tc_fence_after();
+          issue_s(1, s ^ 1);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + epilogue (warps 2..9)
+    const int t = (warp - 2) >> 2;             // the tile this warp set serves
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;       // query row in the tile == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)t * 256u;
+    const float sl2 = scale * 1.4426950408889634f;  // exp(x) = exp2(x * log2 e)
+    const int nfull = nkv & ~31;               // columns covered by unmasked 32-column chunks
+    const int tail = ns - nfull;               // 0, 16 or 32 masked columns
+    const int n32 = nfull >> 5;                // unmasked 32-column chunks
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      if (t >= f2_ntile(item, ppb, paired, n_bh, nq)) continue;
+      const int bh = f2_bh(item, t, ppb, paired), q0 = f2_q0(item, t, ppb, paired);
+      const int rows_valid = min(128, nq - q0);
+      const bool active = quarter * 32 < rows_valid;  // warps whose 32 rows are all padding only keep the barriers moving
+      mbar_wait(bar_s + t, (uint32_t)(it & 1));
+      tc_fence_after();
+      float mx = -INFINITY, sum = 0.f;
+      if (active) {
+        // Both passes keep one TMEM load in flight: chunk c + 1 is requested before chunk c is processed.
+        uint32_t a[32], b[32];
+        // pass 1: row max of the raw scores (scale > 0, so max commutes with the scaling)
+        if (n32 > 0) tmem_ld_32x32(t_row, a);
+        for (int c = 0; c < n32; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < n32) tmem_ld_32x32(t_row + (c + 1) * 32, b);
+          mx = f2_rowmax<32, false>(a, 32, mx);
+          if (c + 1 < n32) {
+            tmem_ld_wait();
+            if (c + 2 < n32) tmem_ld_32x32(t_row + (c + 2) * 32, a);
+            mx = f2_rowmax<32, false>(b, 32, mx);
+          }
+        }
+        if (tail == 32) {
+          tmem_ld_32x32(t_row + nfull, a);
+          tmem_ld_wait();
+          mx = f2_rowmax<32, true>(a, nkv - nfull, mx);
+        } else if (tail == 16) {
+          uint32_t h16[16];
+          tmem_ld_32x16(t_row + nfull, h16);
+          tmem_ld_wait();
+          mx = f2_rowmax<16, true>(h16, nkv - nfull, mx);
+        }
+        const float mb = mx * sl2;
+        // pass 2: p = exp2(s * sl2 - mb); P (bf16 pairs) overwrites the S columns this thread has already consumed
+        // (chunk c's P lands in columns [16 c, 16 c + 16), below every column still to be read)
+        if (n32 > 0) tmem_ld_32x32(t_row, a);
+        for (int c = 0; c < n32; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < n32) tmem_ld_32x32(t_row + (c + 1) * 32, b);
+          sum += f2_probs<32, false>(a, t_row + c * 16, 32, sl2, mb);
+          if (c + 1 < n32) {
+            tmem_ld_wait();
+            if (c + 2 < n32) tmem_ld_32x32(t_row + (c + 2) * 32, a);
+            sum += f2_probs<32, false>(b, t_row + (c + 1) * 16, 32, sl2, mb);
+          }
+        }
+        if (tail == 32) {
+          tmem_ld_32x32(t_row + nfull, a);
+          tmem_ld_wait();
+          sum += f2_probs<32, true>(a, t_row + (nfull >> 1), nkv - nfull, sl2, mb);
+        } else if (tail == 16) {
+          uint32_t h16[16];
+          tmem_ld_32x16(t_row + nfull, h16);
+          tmem_ld_wait();
+          sum += f2_probs<16, true>(h16, t_row + (nfull >> 1), nkv - nfull, sl2, mb);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + t);
+      if (active) {
+        // epilogue: O / l -> bf16 -> global; lse = max * scale + ln(sum)
+        mbar_wait(bar_o + t, (uint32_t)(it & 1));
+        tc_fence_after();
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(t_row + O_COL, a0);
+        tmem_ld_32x32(t_row + O_COL + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + t);   // O is in registers: the tile's TMEM columns are free
+        if (row < rows_valid) {
+          const int i = q0 + row;
+          const int b = bh / heads, h = bh - b * heads;
+          const float inv = 1.f / sum;
+          bf16* dst = O + ((long)b * nq + i) * ldo + h * DH;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(
+                pack_bf16(__uint_as_float(a0[j]) * inv, __uint_as_float(a0[j + 1]) * inv),
+                pack_bf16(__uint_as_float(a0[j + 2]) * inv, __uint_as_float(a0[j + 3]) * inv),
+                pack_bf16(__uint_as_float(a0[j + 4]) * inv, __uint_as_float(a0[j + 5]) * inv),
+                pack_bf16(__uint_as_float(a0[j + 6]) * inv, __uint_as_float(a0[j + 7]) * inv));
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + 32 + j) = make_uint4(
+                pack_bf16(__uint_as_float(a1[j]) * inv, __uint_as_float(a1[j + 1]) * inv),
+                pack_bf16(__uint_as_float(a1[j + 2]) * inv, __uint_as_float(a1[j + 3]) * inv),
+                pack_bf16(__uint_as_float(a1[j + 4]) * inv, __uint_as_float(a1[j + 5]) * inv),
+                pack_bf16(__uint_as_float(a1[j + 6]) * inv, __uint_as_float(a1[j + 7]) * inv));
+          if (lse) lse[(long)bh * nq + i] = mx * scale + __logf(sum);
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + t);
+      }
+      ++it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // [images][tokens][cols] bf16 view with a 64-column x `box_rows`-token box
 int make_tmap3(CUtensorMap* map, const void* base, uint64_t cols, uint64_t tokens, uint64_t images, uint64_t ld,
                uint32_t box_rows) {
@@ -255,10 +567,16 @@ int make_tmap3(CUtensorMap* map, const void* base, uint64_t cols, uint64_t token
 }
 
 bool g_attn_tc = true;
+int g_attn_tc_fwd_version = 2;  // vtb_set_option("attn_tc_fwd_version", 1): the one-CTA-per-tile kernel (A/B timing)
+int g_attn_tc_bwd_version = 2;
 
 }  // namespace
 
 void vtb_attn_tc_set(bool on) { g_attn_tc = on; }
+void vtb_attn_tc_version_set(int fwd, int bwd) {
+  if (fwd > 0) g_attn_tc_fwd_version = fwd;
+  if (bwd > 0) g_attn_tc_bwd_version = bwd;
+}
 
 bool vtb_attn_tc_fwd_ok(const vtb_attn_params* p) {
   return g_attn_tc && p->mode == VTB_ATTN_GLOBAL && p->dh == DH && p->nkv <= MAXK && p->nkv >= 1 &&
@@ -287,13 +605,28 @@ int vtb_attn_tc_fwd(const vtb_attn_params* p, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     VTB_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ATT));
+    VTB_CUDA(cudaFuncSetAttribute(attn_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_F2));
     attr = true;
   }
   const int q_tiles = (p->nq + TQ - 1) / TQ;
-  const long blocks = (long)p->batch * p->heads * q_tiles;
-  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd: grid too large");
-  attn_tc_fwd_kernel<<<(unsigned)blocks, TC_THREADS, SMEM_ATT, stream>>>(
-      tq, tk, tv, reinterpret_cast<bf16*>(p->o), p->ldo, p->lse, p->heads, p->nq, p->nkv, q_tiles, p->scale);
+  const long n_bh = (long)p->batch * p->heads;
+  if (g_attn_tc_fwd_version == 1) {
+    const long blocks = n_bh * q_tiles;
+    VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd: grid too large");
+    attn_tc_fwd_kernel<<<(unsigned)blocks, TC_THREADS, SMEM_ATT, stream>>>(
+        tq, tk, tv, reinterpret_cast<bf16*>(p->o), p->ldo, p->lse, p->heads, p->nq, p->nkv, q_tiles, p->scale);
+    VTB_LAUNCH_CHECK();
+    return 0;
+  }
+  // persistent kernel: a work item = two 128-query tiles sharing one stage (see attn_tc_fwd2_kernel)
+  const int paired = (p->nq <= 128 && p->nkv <= 128) ? 1 : 0;
+  const int ppb = (q_tiles + 1) / 2;
+  const long n_items = paired ? (n_bh + 1) / 2 : n_bh * ppb;
+  VTB_CHECK(n_items < (1L << 31) && n_bh < (1L << 30), -1, "vtb_attention_fwd: too many work items");
+  const int grid = (int)(n_items < vtb_num_sms() ? n_items : vtb_num_sms());
+  attn_tc_fwd2_kernel<<<grid, F2_THREADS, SMEM_F2, stream>>>(
+      tq, tk, tv, reinterpret_cast<bf16*>(p->o), p->ldo, p->lse, p->heads, p->nq, p->nkv, (int)n_bh, (int)n_items, ppb,
+      paired, p->scale);
   VTB_LAUNCH_CHECK();
   return 0;
 }
@@ -598,6 +931,507 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
 }  // namespace
 
+
+// =====================================================================================================================
+// Backward, version 2: PERSISTENT, one CTA per SM, loads of the next (image, head) problem prefetched into the tile slots
+// the current problem has already released; chunked score tiles double-buffered in TMEM so that the tensor pipe and the
+// two math warp sets run concurrently.
+//
+//   warp 0 lane 0 : TMA producer.  Shared memory is a pool of 16 KB tile slots (128 token rows x 128 B, 128B swizzle);
+//                   a problem owns up to 8 tiles (Q0 Q1 dO0 dO1 K0 K1 V0 V1).  Slots are handed out from a free list and
+//                   recycled in the order the tiles die (K_kt / V_kt after key tile kt, Q_hq / dO_hq after the last key
+//                   tile): the UMMA issuer commits one "released" mbarrier per tile.  11 input slots: the next problem's
+//                   first tiles land while the current problem is still in its second key tile.
+//   warp 1 lane 0 : UMMA issuer.  Work is cut into chunks of <= 64 queries (two per 128-query half):
+//                     scores(c): S^T = K_kt Q_c^T, dP^T = V_kt dO_c^T        (M = 128 keys, N = chunk, K = dh)
+//                     grads(c) : dV_kt += P^T dO_c (A = P^T from TMEM), dK_kt += dS^T Q_c (A = the smem tile, K-major),
+//                                and after the last chunk of a half  dQ_hq += dS K_kt (A = the same tile read MN-major)
+//                   issued as  scores(c+2) right behind grads(c): chunk buffers alternate, so while one math set works on
+//                   chunk c+1 the pipe runs grads(c) and scores(c+2).
+//   warps 2-3     : delta_i = sum_d dO[i,d] O[i,d] and lse_i log2(e) of the NEXT problem, straight from global memory into
+//                   a double-buffered shared array (O never occupies a tile slot).
+//   warps 4-7 / 8-11 : math set 0 / 1 (one key row per thread = one TMEM lane); set h owns chunk buffer h, i.e. every
+//                   other chunk:  P^T = exp2(S^T sl2 - lse2[q])  -> bf16 back into TMEM over the S^T columns already
+//                   consumed;  dS^T = P^T (dP^T - delta[q]) -> bf16, 128B-swizzled shared tile.  The softmax scale is
+//                   applied when dK / dQ are written out.  Drains of dV / dK (per key tile) and dQ (per problem) are
+//                   deferred behind the set's next chunk so that their wait for the tensor pipe is hidden.
+// TMEM (512 columns): chunk buffer b: S^T [128 b, +64) and dP^T [128 b + 64, +64) | dV 256 | dK 320 | dQ_0 384 | dQ_1 448.
+// =====================================================================================================================
+namespace {
+
+constexpr int B2_THREADS = 384;
+constexpr int B2_REGS_AUX = 104, B2_REGS_MATH = 200;   // 384 x 168 at launch = 128 x 104 + 256 x 200
+constexpr int B2_IN_SLOTS = 11;                 // input tile slots; slots 11, 12 = the dS^T tile (two 64-query blocks)
+constexpr int B2_SLOT = 16384;
+constexpr int B2_OFF_DS = B2_IN_SLOTS * B2_SLOT;
+constexpr int B2_OFF_DELTA = B2_OFF_DS + 2 * B2_SLOT;          // float [2][256]
+constexpr int B2_OFF_LSE = B2_OFF_DELTA + 2 * 256 * 4;         // float [2][256]
+constexpr int B2_OFF_BAR = B2_OFF_LSE + 2 * 256 * 4;           // 40 mbarriers
+constexpr int B2_OFF_TSLOT = B2_OFF_BAR + 40 * 8;              // int [2][8]: slot of each tile of the problem parity
+constexpr int B2_OFF_TMEM = B2_OFF_TSLOT + 16 * 4;
+constexpr int SMEM_B2 = B2_OFF_TMEM + 16 + 1024;
+// tile ids
+enum { T_Q0 = 0, T_Q1, T_DO0, T_DO1, T_K0, T_K1, T_V0, T_V1 };
+// barrier indices
+constexpr int BB_FULL = 0;      // [2 parities][3 groups]  G0 = K0 V0 Q0 dO0, G1 = Q1 dO1, G2 = K1 V1
+constexpr int BB_REL = 6;       // [2][8] tile released
+constexpr int BB_S = 22;        // [2] chunk buffer: scores complete
+constexpr int BB_MATH = 24;     // [2] chunk buffer: P^T / dS^T written (4 warps)
+constexpr int BB_DSFREE = 26;   // dQ of a half retired: the dS^T tile may be overwritten
+constexpr int BB_DKV = 27;      // dV, dK of a key tile complete
+constexpr int BB_DKVFREE = 28;  // ... drained (8 warps)
+constexpr int BB_DQ = 29;       // dQ of a problem complete
+constexpr int BB_DQFREE = 30;   // ... drained (8 warps)
+constexpr int BB_DFULL = 31;    // [2] delta / lse2 of the problem parity written (2 warps)
+constexpr int BB_DEMPTY = 33;   // [2] ... no longer needed (8 warps)
+
+// The chunk sequence of one CTA: problems bh = blockIdx.x, + gridDim.x, ...; per problem key tiles, query halves, two
+// chunks per half.  Every role walks the same sequence with its own iterator.
+struct B2Iter {
+  int bh, k;            // problem, local problem counter
+  int kt, hq, part;
+  int nkt, nhq, n_bh, stride;
+  int len_a[2], len_b[2];
+  __device__ __forceinline__ void init(int first, int stride_, int n_bh_, int nq, int nkv) {
+    bh = first; stride = stride_; n_bh = n_bh_; k = 0; kt = hq = part = 0;
+    nkt = (nkv + 127) >> 7; nhq = (nq + 127) >> 7;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int nqh = max(0, min(128, ((nq - h * 128) + 15) & ~15));
+      len_a[h] = min(nqh, ((nqh + 31) >> 5) << 4);   // 128 -> 64 + 64, 80 -> 48 + 32, 48 -> 32 + 16, 16 -> 16 + 0
+      len_b[h] = nqh - len_a[h];
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return bh < n_bh; }
+  __device__ __forceinline__ int len() const { return part ? (hq ? len_b[1] : len_b[0]) : (hq ? len_a[1] : len_a[0]); }
+  __device__ __forceinline__ int qo() const { return part ? (hq ? len_a[1] : len_a[0]) : 0; }   // first query of the chunk inside its half
+  __device__ __forceinline__ bool last_in_half() const { return part == 1 || (hq ? len_b[1] : len_b[0]) == 0; }
+  __device__ __forceinline__ bool last_in_kt() const { return last_in_half() && hq == nhq - 1; }
+  __device__ __forceinline__ bool last_in_problem() const { return last_in_kt() && kt == nkt - 1; }
+  __device__ __forceinline__ bool first_in_kt() const { return hq == 0 && part == 0; }
+  __device__ __forceinline__ void advance() {
+    if (!last_in_half()) { part = 1; return; }
+    part = 0;
+    if (++hq < nhq) return;
+    hq = 0;
+    if (++kt < nkt) return;
+    kt = 0; bh += stride; ++k;
+  }
+};
+
+// One W-column (32 or 16) step of a chunk for one key row: P^T = exp2(S^T sl2 - lse2) -> bf16 pairs back into TMEM over
+// the S^T columns just read; dS^T = P^T (dP^T - delta) -> bf16 into this row of the 128B-swizzled shared tile.
+//   t_s: TMEM address of the S^T columns (dP^T sits 64 columns further), t_p: where the P^T pairs go
+//   l2a / dla: shared addresses of lse2 / delta of the step's first query;  ds_row: shared address of this row in
+//   block 0 of the dS^T tile;  q: first query of the step inside its 128-query half
+template <int W>
+__device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a, uint32_t dla, uint32_t ds_row, uint32_t q,
+                                        uint32_t swz, float sl2, uint64_t* bar_dsfree, uint32_t dsfree_par, bool& ds_free) {
+  uint32_t st[W], dp[W];
+  tmem_ld_cols<W>(t_s, st);
+  tmem_ld_cols<W>(t_s + 64, dp);
+  tmem_ld_wait();
+  uint32_t pp[W / 2], dd[W / 2];
+#pragma unroll
+  for (int j = 0; j < W; j += 4) {
+    const float4 l4 = lds_f4(l2a + j * 4);
+    const float4 d4 = lds_f4(dla + j * 4);
+    const float p0 = ex2f(fmaf(__uint_as_float(st[j]), sl2, -l4.x));
+    const float p1 = ex2f(fmaf(__uint_as_float(st[j + 1]), sl2, -l4.y));
+    const float p2 = ex2f(fmaf(__uint_as_float(st[j + 2]), sl2, -l4.z));
+    const float p3 = ex2f(fmaf(__uint_as_float(st[j + 3]), sl2, -l4.w));
+    pp[j >> 1] = pack_bf16(p0, p1);
+    pp[(j >> 1) + 1] = pack_bf16(p2, p3);
+    dd[j >> 1] = pack_bf16(p0 * (__uint_as_float(dp[j]) - d4.x), p1 * (__uint_as_float(dp[j + 1]) - d4.y));
+    dd[(j >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dp[j + 2]) - d4.z), p3 * (__uint_as_float(dp[j + 3]) - d4.w));
+  }
+  if (W == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(t_p),
+        "r"(pp[0]), "r"(pp[1]), "r"(pp[2]), "r"(pp[3]), "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7]),
+        "r"(pp[W / 2 - 8]), "r"(pp[W / 2 - 7]), "r"(pp[W / 2 - 6]), "r"(pp[W / 2 - 5]), "r"(pp[W / 2 - 4]), "r"(pp[W / 2 - 3]),
+        "r"(pp[W / 2 - 2]), "r"(pp[W / 2 - 1])
+        : "memory");
+  } else {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t_p), "r"(pp[0]),
+                 "r"(pp[1]), "r"(pp[2]), "r"(pp[3]), "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7])
+                 : "memory");
+  }
+  if (!ds_free) {   // the previous half's dQ product no longer reads the dS^T tile
+    mbar_wait(bar_dsfree, dsfree_par);
+    ds_free = true;
+  }
+#pragma unroll
+  for (int g = 0; g < W / 8; ++g) {   // 8 queries = 16 B; query qq of the half sits in 64-query block qq / 64
+    const uint32_t qq = q + g * 8;
+    sts_u4(ds_row + (qq >> 6) * 16384u + ((((qq & 63u) >> 3) ^ swz) << 4), dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2],
+           dd[g * 4 + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(B2_THREADS, 1)
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                    const bf16* __restrict__ Og, int ldo, const bf16* __restrict__ dOg, int lddo,
+                    const float* __restrict__ lse, bf16* __restrict__ dQ, int lddq, bf16* __restrict__ dK, int lddk,
+                    bf16* __restrict__ dV, int lddv, int heads, int nq, int nkv, int n_bh, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sdS = smem + B2_OFF_DS;
+  float* sDelta = reinterpret_cast<float*>(smem + B2_OFF_DELTA);
+  float* sLse2 = reinterpret_cast<float*>(smem + B2_OFF_LSE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BAR);
+  const uint32_t tslot = smem_u32(smem + B2_OFF_TSLOT);   // int [2][8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkt = (nkv + 127) >> 7, nhq = (nq + 127) >> 7;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+      for (int i = 0; i < 22; ++i) mbar_init(bars + i, 1);        // full, released
+      mbar_init(bars + BB_S, 1); mbar_init(bars + BB_S + 1, 1);
+      mbar_init(bars + BB_MATH, 4); mbar_init(bars + BB_MATH + 1, 4);
+      mbar_init(bars + BB_DSFREE, 1);
+      mbar_init(bars + BB_DKV, 1); mbar_init(bars + BB_DKVFREE, 8);
+      mbar_init(bars + BB_DQ, 1); mbar_init(bars + BB_DQFREE, 8);
+      mbar_init(bars + BB_DFULL, 2); mbar_init(bars + BB_DFULL + 1, 2);
+      mbar_init(bars + BB_DEMPTY, 8); mbar_init(bars + BB_DEMPTY + 1, 8);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t C_DV = 256, C_DK = 320, C_DQ = 384;
+
+  // registers: the producer / issuer / delta warpgroup hands most of its share to the two math warpgroups
+  // (384 x 168 at launch = 128 x 88 + 256 x 208)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_AUX));
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int free_list[B2_IN_SLOTS];
+      int nfree = B2_IN_SLOTS;
+      for (int i = 0; i < B2_IN_SLOTS; ++i) free_list[i] = B2_IN_SLOTS - 1 - i;
+      // tiles in flight, in the order they will be released: (barrier index, phase parity, slot)
+      int pend_bar[32], pend_slot[32];
+      uint32_t pend_par[32];
+      int ph = 0, pt = 0;
+      auto acquire = [&]() -> int {
+        if (nfree > 0) return free_list[--nfree];
+        const int e = ph++ & 31;
+        mbar_wait(bars + pend_bar[e], pend_par[e]);
+        return pend_slot[e];
+      };
+      int k = 0;
+      for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
+        const int par = k & 1;
+        const uint32_t use = (uint32_t)((k >> 1) & 1);
+        const int b = bh / heads, c0 = (bh - b * heads) * DH;
+        int slot_of[8];
+        auto load = [&](int tile, const CUtensorMap* map, int tok, uint64_t* bar) {
+          tma_load_3d(smem + slot_of[tile] * B2_SLOT, map, bar, c0, tok, b);
+        };
+        // G0: what the first chunk needs
+        for (int t : {T_K0, T_V0, T_Q0, T_DO0}) { slot_of[t] = acquire(); sts_u32(tslot + (par * 8 + t) * 4, (uint32_t)slot_of[t]); }
+        uint64_t* f0 = bars + BB_FULL + par * 3;
+        mbar_expect_tx(f0, 4 * B2_SLOT);
+        load(T_K0, &tk, 0, f0); load(T_V0, &tv, 0, f0); load(T_Q0, &tq, 0, f0); load(T_DO0, &tdo, 0, f0);
+        if (nhq > 1) {
+          for (int t : {T_Q1, T_DO1}) { slot_of[t] = acquire(); sts_u32(tslot + (par * 8 + t) * 4, (uint32_t)slot_of[t]); }
+          mbar_expect_tx(f0 + 1, 2 * B2_SLOT);
+          load(T_Q1, &tq, 128, f0 + 1); load(T_DO1, &tdo, 128, f0 + 1);
+        }
+        if (nkt > 1) {
+          for (int t : {T_K1, T_V1}) { slot_of[t] = acquire(); sts_u32(tslot + (par * 8 + t) * 4, (uint32_t)slot_of[t]); }
+          mbar_expect_tx(f0 + 2, 2 * B2_SLOT);
+          load(T_K1, &tk, 128, f0 + 2); load(T_V1, &tv, 128, f0 + 2);
+        }
+        // release order of this problem's tiles
+        auto push = [&](int tile) {
+          const int e = pt++ & 31;
+          pend_bar[e] = BB_REL + par * 8 + tile; pend_par[e] = use; pend_slot[e] = slot_of[tile];
+        };
+        if (nkt > 1) { push(T_K0); push(T_V0); }
+        if (nhq > 1) { push(T_Q0); push(T_DO0); }
+        push(nhq > 1 ? T_Q1 : T_Q0); push(nhq > 1 ? T_DO1 : T_DO0);
+        push(nkt > 1 ? T_K1 : T_K0); push(nkt > 1 ? T_V1 : T_V0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dV, dK: A K-major (P^T in TMEM / dS^T), B MN-major
+      const uint32_t idesc_q = umma_idesc_bf16(128, DH, 1, 1);   // dQ   : A MN-major (dS^T as dS), B MN-major
+      const uint32_t sa = smem_u32(sdS), s0 = smem_u32(smem);
+      auto tile_addr = [&](int par, int tile) { return s0 + lds_u32(tslot + (par * 8 + tile) * 4) * B2_SLOT; };
+      auto nk_tile = [&](int kt) { return min(128, ((nkv - kt * 128) + 15) & ~15); };
+
+      auto issue_scores = [&](const B2Iter& c, uint32_t cc) {
+        const int par = c.k & 1;
+        const uint32_t use = (uint32_t)((c.k >> 1) & 1);
+        if (c.part == 0) {   // first touch of a tile group by this problem
+          if (c.kt == 0 && c.hq == 0) mbar_wait(bars + BB_FULL + par * 3, use);
+          if (c.kt == 0 && c.hq == 1) mbar_wait(bars + BB_FULL + par * 3 + 1, use);
+          if (c.kt == 1 && c.hq == 0) mbar_wait(bars + BB_FULL + par * 3 + 2, use);
+          tc_fence_after();
+        }
+        const uint32_t buf = tmem_base + (cc & 1) * 128;
+        const uint32_t ka = tile_addr(par, T_K0 + c.kt), va = tile_addr(par, T_V0 + c.kt);
+        const uint32_t qa = tile_addr(par, T_Q0 + c.hq) + (uint32_t)c.qo() * 128u;
+        const uint32_t oa = tile_addr(par, T_DO0 + c.hq) + (uint32_t)c.qo() * 128u;
+        const uint32_t idesc_s = umma_idesc_bf16(128, c.len(), 0, 0);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(buf, umma_desc_sw128(ka + kk * 32, 0, 1024), umma_desc_sw128(qa + kk * 32, 0, 1024), idesc_s,
+                    kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16(buf + 64, umma_desc_sw128(va + kk * 32, 0, 1024), umma_desc_sw128(oa + kk * 32, 0, 1024), idesc_s,
+                    kk > 0 ? 1u : 0u);
+        umma_commit(bars + BB_S + (cc & 1));
+      };
+
+      uint32_t n_kt_done = 0;   // key-tile iterations whose dV / dK are complete (drain counter)
+      auto issue_grads = [&](const B2Iter& c, uint32_t cc) {
+        const int par = c.k & 1;
+        const uint32_t buf = tmem_base + (cc & 1) * 128;
+        mbar_wait(bars + BB_MATH + (cc & 1), (cc >> 1) & 1);
+        if (c.first_in_kt() && n_kt_done > 0) mbar_wait(bars + BB_DKVFREE, (n_kt_done - 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = tile_addr(par, T_Q0 + c.hq), oa = tile_addr(par, T_DO0 + c.hq);
+        const int st0 = c.qo() >> 4;   // first 16-query step of the chunk inside its half
+        for (int kk = 0; kk < (c.len() >> 4); ++kk) {
+          const int st = st0 + kk;
+          const uint32_t acc = (c.first_in_kt() && kk == 0) ? 0u : 1u;
+          umma_bf16_ts(tmem_base + C_DV, buf + kk * 8, umma_desc_sw128(oa + st * 2048, 0, 1024), idesc_g, acc);
+          umma_bf16(tmem_base + C_DK, umma_desc_sw128(sa + (uint32_t)((st >> 2) * 16384 + (st & 3) * 32), 0, 1024),
+                    umma_desc_sw128(qa + st * 2048, 0, 1024), idesc_g, acc);
+        }
+        if (c.last_in_half()) {
+          if (c.kt == 0 && c.hq == 0 && c.k > 0) {   // the previous problem's dQ has been written out?
+            mbar_wait(bars + BB_DQFREE, (uint32_t)((c.k - 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t ka = tile_addr(par, T_K0 + c.kt);
+          const int nk = nk_tile(c.kt);
+          for (int st = 0; st < (nk >> 4); ++st)   // contraction over the keys of this tile
+            umma_bf16(tmem_base + C_DQ + c.hq * 64, umma_desc_sw128(sa + st * 2048, 16384, 1024),
+                      umma_desc_sw128(ka + st * 2048, 0, 1024), idesc_q, (c.kt > 0 || st > 0) ? 1u : 0u);
+          umma_commit(bars + BB_DSFREE);
+          if (c.kt == nkt - 1) {   // last use of this half's Q / dO tiles
+            umma_commit(bars + BB_REL + par * 8 + T_Q0 + c.hq);
+            umma_commit(bars + BB_REL + par * 8 + T_DO0 + c.hq);
+          }
+        }
+        if (c.last_in_kt()) {
+          umma_commit(bars + BB_REL + par * 8 + T_K0 + c.kt);
+          umma_commit(bars + BB_REL + par * 8 + T_V0 + c.kt);
+          umma_commit(bars + BB_DKV);
+          ++n_kt_done;
+        }
+        if (c.last_in_problem()) umma_commit(bars + BB_DQ);
+      };
+
+      B2Iter sc, gr;
+      sc.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
+      gr = sc;
+      uint32_t cs = 0, cg = 0;
+      for (int i = 0; i < 2 && sc.valid(); ++i) { issue_scores(sc, cs++); sc.advance(); }
+      while (gr.valid()) {
+        issue_grads(gr, cg++);
+        gr.advance();
+        if (sc.valid()) { issue_scores(sc, cs++); sc.advance(); }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ delta / lse2
+    const int t2 = threadIdx.x - 64;   // 0..63
+    int k = 0;
+    for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
+      const int par = k & 1;
+      mbar_wait(bars + BB_DEMPTY + par, (uint32_t)(((k >> 1) & 1) ^ 1));
+      const int b = bh / heads, h = bh - b * heads;
+      for (int i = t2; i < 256; i += 64) {
+        float acc = 0.f, l2 = INFINITY;
+        if (i < nq) {
+          const uint4* o4 = reinterpret_cast<const uint4*>(Og + ((long)b * nq + i) * ldo + h * DH);
+          const uint4* g4 = reinterpret_cast<const uint4*>(dOg + ((long)b * nq + i) * lddo + h * DH);
+#pragma unroll
+          for (int jj = 0; jj < 8; jj += 4) {
+            uint4 ro[4], rg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ro[j] = __ldg(o4 + jj + j); rg[j] = __ldg(g4 + jj + j); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t wo[4] = {ro[j].x, ro[j].y, ro[j].z, ro[j].w}, wg[4] = {rg[j].x, rg[j].y, rg[j].z, rg[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fo = unpack_bf16(wo[e]), fg = unpack_bf16(wg[e]);
+                acc = fmaf(fo.x, fg.x, acc);
+                acc = fmaf(fo.y, fg.y, acc);
+              }
+            }
+          }
+          l2 = lse[(long)bh * nq + i] * 1.4426950408889634f;
+        }
+        sts_f32(smem_u32(sDelta) + (uint32_t)(par * 256 + i) * 4u, acc);   // padding queries: delta 0, lse2 +inf -> P = 0, dS = 0
+        sts_f32(smem_u32(sLse2) + (uint32_t)(par * 256 + i) * 4u, l2);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BB_DFULL + par);
+    }
+  }
+  } else {
+    // ------------------------------------------------------------------------------------------------ math sets
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_REGS_MATH));
+    const int set = (warp - 4) >> 2;                // owns chunk buffer `set`
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;            // key row inside the tile == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_buf = t_row + (uint32_t)set * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const float sl2 = scale * 1.4426950408889634f;
+
+    // dV, dK of one key tile: TMEM -> bf16 -> global rows of the keys (set 0: dV, set 1: dK * scale)
+    auto drain_dkv = [&](int bh, int kt, uint32_t n) {
+      mbar_wait(bars + BB_DKV, n & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(t_row + (set ? C_DK : C_DV), a0);
+      tmem_ld_32x32(t_row + (set ? C_DK : C_DV) + 32, a1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BB_DKVFREE);
+      const int j = kt * 128 + row;
+      if (j < nkv) {
+        const int b = bh / heads, h = bh - b * heads;
+        const float f = set ? scale : 1.f;
+        bf16* dst = (set ? dK + ((long)b * nkv + j) * lddk : dV + ((long)b * nkv + j) * lddv) + h * DH;
+#pragma unroll
+        for (int e = 0; e < 32; e += 8)
+          *reinterpret_cast<uint4*>(dst + e) = make_uint4(
+              pack_bf16(__uint_as_float(a0[e]) * f, __uint_as_float(a0[e + 1]) * f),
+              pack_bf16(__uint_as_float(a0[e + 2]) * f, __uint_as_float(a0[e + 3]) * f),
+              pack_bf16(__uint_as_float(a0[e + 4]) * f, __uint_as_float(a0[e + 5]) * f),
+              pack_bf16(__uint_as_float(a0[e + 6]) * f, __uint_as_float(a0[e + 7]) * f));
+#pragma unroll
+        for (int e = 0; e < 32; e += 8)
+          *reinterpret_cast<uint4*>(dst + 32 + e) = make_uint4(
+              pack_bf16(__uint_as_float(a1[e]) * f, __uint_as_float(a1[e + 1]) * f),
+              pack_bf16(__uint_as_float(a1[e + 2]) * f, __uint_as_float(a1[e + 3]) * f),
+              pack_bf16(__uint_as_float(a1[e + 4]) * f, __uint_as_float(a1[e + 5]) * f),
+              pack_bf16(__uint_as_float(a1[e + 6]) * f, __uint_as_float(a1[e + 7]) * f));
+      }
+    };
+    // dQ of one problem: rows = queries; set s writes columns [32 s, 32 s + 32) of both halves
+    auto drain_dq = [&](int bh, uint32_t n) {
+      mbar_wait(bars + BB_DQ, n & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(t_row + C_DQ + set * 32, a0);
+      if (nhq > 1) tmem_ld_32x32(t_row + C_DQ + 64 + set * 32, a1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BB_DQFREE);
+      const int b = bh / heads, h = bh - b * heads;
+      if (row < nq) {
+        bf16* dst = dQ + ((long)b * nq + row) * lddq + h * DH + set * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 8)
+          *reinterpret_cast<uint4*>(dst + e) = make_uint4(
+              pack_bf16(__uint_as_float(a0[e]) * scale, __uint_as_float(a0[e + 1]) * scale),
+              pack_bf16(__uint_as_float(a0[e + 2]) * scale, __uint_as_float(a0[e + 3]) * scale),
+              pack_bf16(__uint_as_float(a0[e + 4]) * scale, __uint_as_float(a0[e + 5]) * scale),
+              pack_bf16(__uint_as_float(a0[e + 6]) * scale, __uint_as_float(a0[e + 7]) * scale));
+      }
+      if (nhq > 1 && 128 + row < nq) {
+        bf16* dst = dQ + ((long)b * nq + 128 + row) * lddq + h * DH + set * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 8)
+          *reinterpret_cast<uint4*>(dst + e) = make_uint4(
+              pack_bf16(__uint_as_float(a1[e]) * scale, __uint_as_float(a1[e + 1]) * scale),
+              pack_bf16(__uint_as_float(a1[e + 2]) * scale, __uint_as_float(a1[e + 3]) * scale),
+              pack_bf16(__uint_as_float(a1[e + 4]) * scale, __uint_as_float(a1[e + 5]) * scale),
+              pack_bf16(__uint_as_float(a1[e + 6]) * scale, __uint_as_float(a1[e + 7]) * scale));
+      }
+    };
+
+    B2Iter c;
+    c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
+    uint32_t cc = 0, n_half = 0, n_kt = 0;
+    bool pend_dkv = false, pend_dq = false;
+    int pend_dkv_bh = 0, pend_dkv_kt = 0, pend_dq_bh = 0;
+    uint32_t pend_dkv_n = 0, pend_dq_n = 0;
+    int delta_k = -1;   // problem whose delta / lse2 this warp has acquired
+    for (; c.valid(); c.advance(), ++cc) {
+      if ((int)(cc & 1) == set) {
+        const int par = c.k & 1;
+        if (delta_k != c.k) {
+          mbar_wait(bars + BB_DFULL + par, (uint32_t)((c.k >> 1) & 1));
+          delta_k = c.k;
+        }
+        mbar_wait(bars + BB_S + set, (cc >> 1) & 1);
+        tc_fence_after();
+        const int nk16 = min(128, ((nkv - c.kt * 128) + 15) & ~15);
+        if (quarter * 32 < nk16) {   // warps whose 32 key rows are all padding only keep the barriers moving
+          const int len = c.len(), qo = c.qo();
+          const uint32_t l2a = smem_u32(sLse2) + (uint32_t)(par * 256 + c.hq * 128 + qo) * 4u;
+          const uint32_t dla = smem_u32(sDelta) + (uint32_t)(par * 256 + c.hq * 128 + qo) * 4u;
+          const uint32_t ds_row = smem_u32(sdS) + (uint32_t)row * 128u;
+          bool ds_free = (n_half == 0);
+          int c0 = 0;
+          for (; c0 + 32 <= len; c0 += 32)
+            b2_step<32>(t_buf + c0, t_buf + (c0 >> 1), l2a + c0 * 4, dla + c0 * 4, ds_row, (uint32_t)(qo + c0), swz, sl2,
+                        bars + BB_DSFREE, (n_half - 1) & 1, ds_free);
+          if (c0 < len)
+            b2_step<16>(t_buf + c0, t_buf + (c0 >> 1), l2a + c0 * 4, dla + c0 * 4, ds_row, (uint32_t)(qo + c0), swz, sl2,
+                        bars + BB_DSFREE, (n_half - 1) & 1, ds_free);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BB_MATH + set);
+        // deferred drains: their wait for the tensor pipe hides behind the chunk just done
+        if (pend_dkv) { drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n); pend_dkv = false; }
+        if (pend_dq) { drain_dq(pend_dq_bh, pend_dq_n); pend_dq = false; }
+      }
+      if (c.last_in_half()) ++n_half;
+      if (c.last_in_kt()) {
+        if (pend_dkv) drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n);
+        pend_dkv = true; pend_dkv_bh = c.bh; pend_dkv_kt = c.kt; pend_dkv_n = n_kt++;
+      }
+      if (c.last_in_problem()) {
+        if (pend_dq) drain_dq(pend_dq_bh, pend_dq_n);
+        pend_dq = true; pend_dq_bh = c.bh; pend_dq_n = (uint32_t)c.k;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BB_DEMPTY + (c.k & 1));   // this warp is done with the problem's delta / lse2
+      }
+    }
+    if (pend_dkv) drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n);
+    if (pend_dq) drain_dq(pend_dq_bh, pend_dq_n);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
 bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p) {
   return g_attn_tc && p->mode == VTB_ATTN_GLOBAL && p->dh == DH && p->nkv <= 256 && p->nq <= 256 &&
          !p->rel_bias && !p->mask && !p->dkv_f32 && p->lddq % 8 == 0 && p->lddk % 8 == 0 && p->lddv % 8 == 0 &&
@@ -610,7 +1444,6 @@ int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream) {
   const uint64_t cols = (uint64_t)p->heads * DH;
   CUtensorMap tq, tk, tv, tdo, to;
   int rc;
-  if ((rc = make_tmap3(&to, p->o, cols, p->nq, p->batch, p->ldo, 128))) return rc;
   if ((rc = make_tmap3(&tq, p->q, cols, p->nq, p->batch, p->ldq, 128))) return rc;
   if ((rc = make_tmap3(&tk, p->k, cols, p->nkv, p->batch, p->ldk, 128))) return rc;
   if ((rc = make_tmap3(&tv, p->v, cols, p->nkv, p->batch, p->ldv, 128))) return rc;
@@ -618,13 +1451,24 @@ int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     VTB_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
+    VTB_CUDA(cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B2));
     attr = true;
   }
   const long blocks = (long)p->batch * p->heads;
-  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_bwd: grid too large");
-  attn_tc_bwd_kernel<<<(unsigned)blocks, BWD_THREADS, SMEM_BWD, stream>>>(
-      tq, tk, tv, tdo, to, p->lse, reinterpret_cast<bf16*>(p->dq), p->lddq, reinterpret_cast<bf16*>(p->dk), p->lddk,
-      reinterpret_cast<bf16*>(p->dv), p->lddv, p->heads, p->nq, p->nkv, p->scale);
+  VTB_CHECK(blocks < (1L << 30), -1, "vtb_attention_bwd: grid too large");
+  if (g_attn_tc_bwd_version == 1) {
+    if ((rc = make_tmap3(&to, p->o, cols, p->nq, p->batch, p->ldo, 128))) return rc;
+    attn_tc_bwd_kernel<<<(unsigned)blocks, BWD_THREADS, SMEM_BWD, stream>>>(
+        tq, tk, tv, tdo, to, p->lse, reinterpret_cast<bf16*>(p->dq), p->lddq, reinterpret_cast<bf16*>(p->dk), p->lddk,
+        reinterpret_cast<bf16*>(p->dv), p->lddv, p->heads, p->nq, p->nkv, p->scale);
+    VTB_LAUNCH_CHECK();
+    return 0;
+  }
+  const int grid = (int)(blocks < vtb_num_sms() ? blocks : vtb_num_sms());
+  attn_tc_bwd2_kernel<<<grid, B2_THREADS, SMEM_B2, stream>>>(
+      tq, tk, tv, tdo, reinterpret_cast<const bf16*>(p->o), p->ldo, reinterpret_cast<const bf16*>(p->dout), p->lddo,
+      p->lse, reinterpret_cast<bf16*>(p->dq), p->lddq, reinterpret_cast<bf16*>(p->dk), p->lddk,
+      reinterpret_cast<bf16*>(p->dv), p->lddv, p->heads, p->nq, p->nkv, (int)blocks, p->scale);
   VTB_LAUNCH_CHECK();
   return 0;
 }

@@ -788,6 +788,7 @@ int vtb_gemm_init() {
 int vtb_num_sms() { return g_num_sms; }
 
 void vtb_attn_tc_set(bool on);
+void vtb_attn_tc_version_set(int fwd, int bwd);
 void vtb_attn_wp_set(bool on);
 void vtb_attn_wt_set(bool on);
 void vtb_ln_stream_set(bool on);
@@ -797,6 +798,8 @@ extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
+  if (strcmp(name, "attn_tc_fwd_version") == 0) { vtb_attn_tc_version_set(value, 0); return 0; }
+  if (strcmp(name, "attn_tc_bwd_version") == 0) { vtb_attn_tc_version_set(0, value); return 0; }
   if (strcmp(name, "input_variant") == 0) { vtb_input_variant_set(value); return 0; }
   if (strcmp(name, "attn_wp") == 0) { vtb_attn_wp_set(value != 0); return 0; }
   if (strcmp(name, "attn_wt") == 0) { vtb_attn_wt_set(value != 0); return 0; }
