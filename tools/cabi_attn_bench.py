@@ -183,11 +183,43 @@ def self_check(mode, **kw):
     return ok
 
 
+def mbar_debug(where):
+    """Debug builds (-DVTB_MBAR_DEBUG): report the first mbarrier wait that timed out."""
+    if hasattr(lib, "vtb_debug_mbar_timeout"):
+        out = (C.c_uint32 * 4)()
+        lib.vtb_debug_mbar_timeout(out)
+        if out[0]:
+            print(f"MBAR TIMEOUT after {where}: smem addr 0x{out[0]:x} parity {out[1]} block {out[2]} thread {out[3]}", flush=True)
+
+
+def dump_trace(path):
+    """Debug builds (-DVTB_ATTN_TRACE): timeline of block 0 of the last backward launch."""
+    if not hasattr(lib, "vtb_debug_attn_trace"):
+        return
+    out = (C.c_uint32 * (12 * 2 * 1024))()
+    lib.vtb_debug_attn_trace(out)
+    ev = sorted((out[(w * 1024 + i) * 2 + 1], w, out[(w * 1024 + i) * 2]) for w in range(12) for i in range(1024)
+                if out[(w * 1024 + i) * 2])
+    with open(path, "w") as fh:
+        t0 = ev[0][0] if ev else 0
+        for t, w, e in ev:
+            fh.write(f"{(t - t0) & 0xffffffff:10d} warp {w:2d} ev {e}\n")
+    print(f"trace: {len(ev)} events -> {path}", flush=True)
+
+
 def bench(tag, mode, seed, **kw):
     pr = Problem(mode, seed=seed, **kw)
     timer = cu.Timer()
     pr.fwd()
+    cu.ck(cu.rt.cudaDeviceSynchronize(), "sync after fwd")
+    mbar_debug(tag + " fwd")
+    dump_trace("/dev/null")
+    pr.bwd()
+    cu.ck(cu.rt.cudaDeviceSynchronize(), "sync after bwd")
+    dump_trace(os.path.join(ROOT, "gpurun_out", "attn_trace_" + tag.split()[1] + "_" + str(kw.get("n")) + ".txt"))
+    mbar_debug(tag + " bwd")
     tf, tb = timer.time(pr.fwd), timer.time(pr.bwd)
+    mbar_debug(tag + " timing loops")
     T, HD = pr.T, pr.H * pr.dh
     fb, bb = T * HD * 2 * 4, T * HD * 2 * 8  # q, k, v read + o written;  q, k, v, o, do read + dq, dk, dv written
     fl = 4.0 * pr.groups * pr.H * pr.n * pr.n * pr.dh
@@ -207,7 +239,8 @@ if only_check in ("", "global"):
     ok &= self_check(L.ATTN_GLOBAL, B=2, H=2, dh=64, n=197)
     ok &= self_check(L.ATTN_GLOBAL, B=3, H=1, dh=64, n=37)
     for kw in (dict(B=5, H=3, n=197), dict(B=5, H=1, n=37), dict(B=2, H=2, n=50), dict(B=1, H=2, n=256), dict(B=2, H=1, n=128),
-               dict(B=1, H=3, n=129), dict(B=1, H=1, n=16), dict(B=2, H=2, n=145), dict(B=150, H=2, n=197)):
+               dict(B=1, H=3, n=129), dict(B=1, H=1, n=16), dict(B=2, H=2, n=145), dict(B=150, H=2, n=197), dict(B=100, H=6, n=37), dict(B=70, H=5, n=128),
+               dict(B=33, H=7, n=200)):
         ok &= self_check(L.ATTN_GLOBAL, dh=64, **kw)
 if only_check in ("", "window"):
     ok &= self_check(L.ATTN_WINDOW, B=1, H=2, dh=32, n=49, Hs=14, W=7, shift=True)
@@ -218,10 +251,12 @@ rng = np.random.default_rng(1)
 n_seed = 16 << 20
 seed = {BF16: cu.Buf(n_seed, BF16).upload(cu.to_bf16_bits(rng.standard_normal(n_seed, F32))),
         F32: cu.Buf(n_seed, F32).upload(rng.standard_normal(n_seed, F32))}
-if only in ("", "global"):
+if only in ("", "global") and not os.environ.get("ATTN_N37_ONLY"):
     bench(f"global ViT-B   B={Bn} H=12 n=197", L.ATTN_GLOBAL, seed, B=Bn, H=12, dh=64, n=197)
     bench(f"global DeiT-S  B={Bn} H=6  n=197", L.ATTN_GLOBAL, seed, B=Bn, H=6, dh=64, n=197)
-    bench(f"global DeiT-S  B={4 * Bn} H=6  n=37 ", L.ATTN_GLOBAL, seed, B=4 * Bn, H=6, dh=64, n=37)
+if only in ("", "global"):
+    for Bx in ((Bn // 2, Bn, 2 * Bn, 4 * Bn) if os.environ.get("ATTN_N37_ONLY") else (4 * Bn,)):
+        bench(f"global DeiT-S  B={Bx} H=6  n=37 ", L.ATTN_GLOBAL, seed, B=Bx, H=6, dh=64, n=37)
 if only in ("", "window"):
     for Hs, H in ((56, 3), (28, 6), (14, 12), (7, 24)):
         for shift in (True, False):

@@ -959,6 +959,23 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 // =====================================================================================================================
 namespace {
 
+#ifdef VTB_ATTN_TRACE
+// timeline of block 0 (debug builds): per warp a private list of {event id, clock} pairs (plain stores, no atomics: the
+// probe must not stall the warp), fetched with vtb_debug_attn_trace
+__device__ unsigned int g_b2_trace[12 * 2 * 1024];
+#define B2_TRACE_DECL unsigned int trace_i__ = 0
+#define B2_TRACE(ev)                                                                              \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_i__ < 1024) {                         \
+      unsigned int* p__ = g_b2_trace + ((threadIdx.x >> 5) * 1024 + trace_i__) * 2;              \
+      p__[0] = (ev); p__[1] = (unsigned int)clock64();                                            \
+      ++trace_i__;                                                                                \
+    }                                                                                             \
+  } while (0)
+#else
+#define B2_TRACE_DECL do { } while (0)
+#define B2_TRACE(ev) do { } while (0)
+#endif
 constexpr int B2_THREADS = 384;
 constexpr int B2_REGS_AUX = 104, B2_REGS_MATH = 200;   // 384 x 168 at launch = 128 x 104 + 256 x 200
 constexpr int B2_IN_SLOTS = 11;                 // input tile slots; slots 11, 12 = the dS^T tile (two 64-query blocks)
@@ -967,8 +984,7 @@ constexpr int B2_OFF_DS = B2_IN_SLOTS * B2_SLOT;
 constexpr int B2_OFF_DELTA = B2_OFF_DS + 2 * B2_SLOT;          // float [2][256]
 constexpr int B2_OFF_LSE = B2_OFF_DELTA + 2 * 256 * 4;         // float [2][256]
 constexpr int B2_OFF_BAR = B2_OFF_LSE + 2 * 256 * 4;           // 40 mbarriers
-constexpr int B2_OFF_TSLOT = B2_OFF_BAR + 40 * 8;              // int [2][8]: slot of each tile of the problem parity
-constexpr int B2_OFF_TMEM = B2_OFF_TSLOT + 16 * 4;
+constexpr int B2_OFF_TMEM = B2_OFF_BAR + 40 * 8;
 constexpr int SMEM_B2 = B2_OFF_TMEM + 16 + 1024;
 // tile ids
 enum { T_Q0 = 0, T_Q1, T_DO0, T_DO1, T_K0, T_K1, T_V0, T_V1 };
@@ -1082,11 +1098,15 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   float* sDelta = reinterpret_cast<float*>(smem + B2_OFF_DELTA);
   float* sLse2 = reinterpret_cast<float*>(smem + B2_OFF_LSE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BAR);
-  const uint32_t tslot = smem_u32(smem + B2_OFF_TSLOT);   // int [2][8]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  B2_TRACE_DECL;
   const int nkt = (nkv + 127) >> 7, nhq = (nq + 127) >> 7;
+  // tile ring (see the producer): load order K0 V0 Q0 dO0 [Q1 dO1] [K1 V1]; the released-barrier index of a tile is its order
+  const int tpp = 4 + (nhq > 1 ? 2 : 0) + (nkt > 1 ? 2 : 0);   // tiles per problem
+  const int ord_k1 = 4 + (nhq > 1 ? 2 : 0);
+  const int ns = tpp == 4 ? 8 : B2_IN_SLOTS;                    // ring size
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1116,62 +1136,56 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_AUX));
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------------ TMA producer
+    // The input slots form a RING: the tiles of all problems are numbered in load order (K0 V0 Q0 dO0 [Q1 dO1] [K1 V1] per
+    // problem), tile g lives in slot g % ns.  Tiles die in (nearly) the same order, so before loading tile g the producer
+    // waits for the "released" barrier of tile g - ns.  ns <= 2 tiles-per-problem keeps that barrier at most one phase ahead.
     if (lane == 0) {
-      int free_list[B2_IN_SLOTS];
-      int nfree = B2_IN_SLOTS;
-      for (int i = 0; i < B2_IN_SLOTS; ++i) free_list[i] = B2_IN_SLOTS - 1 - i;
-      // tiles in flight, in the order they will be released: (barrier index, phase parity, slot)
-      int pend_bar[32], pend_slot[32];
-      uint32_t pend_par[32];
-      int ph = 0, pt = 0;
-      auto acquire = [&]() -> int {
-        if (nfree > 0) return free_list[--nfree];
-        const int e = ph++ & 31;
-        mbar_wait(bars + pend_bar[e], pend_par[e]);
-        return pend_slot[e];
-      };
       int k = 0;
       for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
         const int par = k & 1;
-        const uint32_t use = (uint32_t)((k >> 1) & 1);
         const int b = bh / heads, c0 = (bh - b * heads) * DH;
-        int slot_of[8];
-        auto load = [&](int tile, const CUtensorMap* map, int tok, uint64_t* bar) {
-          tma_load_3d(smem + slot_of[tile] * B2_SLOT, map, bar, c0, tok, b);
-        };
-        // G0: what the first chunk needs
-        for (int t : {T_K0, T_V0, T_Q0, T_DO0}) { slot_of[t] = acquire(); sts_u32(tslot + (par * 8 + t) * 4, (uint32_t)slot_of[t]); }
         uint64_t* f0 = bars + BB_FULL + par * 3;
+        // wait until the previous occupants of the slots of tiles [ord, ord + n) have been released.  This also orders
+        // the group's expect_tx behind the landing of the same group two problems back (same mbarrier): arriving on a
+        // barrier whose phase is still waiting for bytes would underflow its arrival count.
+        auto reserve = [&](int ord, int n) {
+          for (int i = 0; i < n; ++i) {
+            const int g = tpp * k + ord + i;
+            if (g >= ns) {
+              const int kp = (g - ns) / tpp, op = (g - ns) - kp * tpp;
+              mbar_wait(bars + BB_REL + (kp & 1) * 8 + op, (uint32_t)((kp >> 1) & 1));
+            }
+          }
+        };
+        auto load = [&](int ord, const CUtensorMap* map, int tok, uint64_t* bar) {
+          tma_load_3d(smem + ((tpp * k + ord) % ns) * B2_SLOT, map, bar, c0, tok, b);
+        };
+        reserve(0, 4);
         mbar_expect_tx(f0, 4 * B2_SLOT);
-        load(T_K0, &tk, 0, f0); load(T_V0, &tv, 0, f0); load(T_Q0, &tq, 0, f0); load(T_DO0, &tdo, 0, f0);
+        load(0, &tk, 0, f0); load(1, &tv, 0, f0); load(2, &tq, 0, f0); load(3, &tdo, 0, f0);
         if (nhq > 1) {
-          for (int t : {T_Q1, T_DO1}) { slot_of[t] = acquire(); sts_u32(tslot + (par * 8 + t) * 4, (uint32_t)slot_of[t]); }
+          reserve(4, 2);
           mbar_expect_tx(f0 + 1, 2 * B2_SLOT);
-          load(T_Q1, &tq, 128, f0 + 1); load(T_DO1, &tdo, 128, f0 + 1);
+          load(4, &tq, 128, f0 + 1); load(5, &tdo, 128, f0 + 1);
         }
         if (nkt > 1) {
-          for (int t : {T_K1, T_V1}) { slot_of[t] = acquire(); sts_u32(tslot + (par * 8 + t) * 4, (uint32_t)slot_of[t]); }
+          reserve(ord_k1, 2);
           mbar_expect_tx(f0 + 2, 2 * B2_SLOT);
-          load(T_K1, &tk, 128, f0 + 2); load(T_V1, &tv, 128, f0 + 2);
+          load(ord_k1, &tk, 128, f0 + 2); load(ord_k1 + 1, &tv, 128, f0 + 2);
         }
-        // release order of this problem's tiles
-        auto push = [&](int tile) {
-          const int e = pt++ & 31;
-          pend_bar[e] = BB_REL + par * 8 + tile; pend_par[e] = use; pend_slot[e] = slot_of[tile];
-        };
-        if (nkt > 1) { push(T_K0); push(T_V0); }
-        if (nhq > 1) { push(T_Q0); push(T_DO0); }
-        push(nhq > 1 ? T_Q1 : T_Q0); push(nhq > 1 ? T_DO1 : T_DO0);
-        push(nkt > 1 ? T_K1 : T_K0); push(nkt > 1 ? T_V1 : T_V0);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
+    // All 32 lanes walk the chunk sequence (everything below is warp-uniform); one elected lane issues the tcgen05 ops.
+    {
       const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dV, dK: A K-major (P^T in TMEM / dS^T), B MN-major
       const uint32_t idesc_q = umma_idesc_bf16(128, DH, 1, 1);   // dQ   : A MN-major (dS^T as dS), B MN-major
       const uint32_t sa = smem_u32(sdS), s0 = smem_u32(smem);
-      auto tile_addr = [&](int par, int tile) { return s0 + lds_u32(tslot + (par * 8 + tile) * 4) * B2_SLOT; };
+      // tile order inside a problem: K_kt, V_kt, Q_hq, dO_hq
+      auto ord_k = [&](int kt) { return kt ? ord_k1 : 0; };
+      auto ord_q = [&](int hq) { return hq ? 4 : 2; };
+      auto tile_addr = [&](int k, int ord) { return s0 + (uint32_t)((tpp * k + ord) % ns) * B2_SLOT; };
       auto nk_tile = [&](int kt) { return min(128, ((nkv - kt * 128) + 15) & ~15); };
 
       auto issue_scores = [&](const B2Iter& c, uint32_t cc) {
@@ -1184,60 +1198,81 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           tc_fence_after();
         }
         const uint32_t buf = tmem_base + (cc & 1) * 128;
-        const uint32_t ka = tile_addr(par, T_K0 + c.kt), va = tile_addr(par, T_V0 + c.kt);
-        const uint32_t qa = tile_addr(par, T_Q0 + c.hq) + (uint32_t)c.qo() * 128u;
-        const uint32_t oa = tile_addr(par, T_DO0 + c.hq) + (uint32_t)c.qo() * 128u;
+        const uint32_t ka = tile_addr(c.k, ord_k(c.kt)), va = tile_addr(c.k, ord_k(c.kt) + 1);
+        const uint32_t qa = tile_addr(c.k, ord_q(c.hq)) + (uint32_t)c.qo() * 128u;
+        const uint32_t oa = tile_addr(c.k, ord_q(c.hq) + 1) + (uint32_t)c.qo() * 128u;
         const uint32_t idesc_s = umma_idesc_bf16(128, c.len(), 0, 0);
+        const uint64_t dk = umma_desc_sw128(ka, 0, 1024), dq = umma_desc_sw128(qa, 0, 1024);
+        const uint64_t dv = umma_desc_sw128(va, 0, 1024), dd = umma_desc_sw128(oa, 0, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(buf, umma_desc_sw128(ka + kk * 32, 0, 1024), umma_desc_sw128(qa + kk * 32, 0, 1024), idesc_s,
-                    kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < DH / 16; ++kk) umma_bf16(buf, dk + 2 * kk, dq + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);   // +32 B
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(buf + 64, umma_desc_sw128(va + kk * 32, 0, 1024), umma_desc_sw128(oa + kk * 32, 0, 1024), idesc_s,
-                    kk > 0 ? 1u : 0u);
-        umma_commit(bars + BB_S + (cc & 1));
+          for (int kk = 0; kk < DH / 16; ++kk) umma_bf16(buf + 64, dv + 2 * kk, dd + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(bars + BB_S + (cc & 1));
+        }
+        __syncwarp();
+        B2_TRACE(13);
       };
 
       uint32_t n_kt_done = 0;   // key-tile iterations whose dV / dK are complete (drain counter)
       auto issue_grads = [&](const B2Iter& c, uint32_t cc) {
         const int par = c.k & 1;
         const uint32_t buf = tmem_base + (cc & 1) * 128;
+        B2_TRACE(10);
         mbar_wait(bars + BB_MATH + (cc & 1), (cc >> 1) & 1);
+        B2_TRACE(11);
         if (c.first_in_kt() && n_kt_done > 0) mbar_wait(bars + BB_DKVFREE, (n_kt_done - 1) & 1);
+        const bool dq_now = c.last_in_half();
+        if (dq_now && c.kt == 0 && c.hq == 0 && c.k > 0)   // the previous problem's dQ has been written out?
+          mbar_wait(bars + BB_DQFREE, (uint32_t)((c.k - 1) & 1));
         tc_fence_after();
-        const uint32_t qa = tile_addr(par, T_Q0 + c.hq), oa = tile_addr(par, T_DO0 + c.hq);
         const int st0 = c.qo() >> 4;   // first 16-query step of the chunk inside its half
-        for (int kk = 0; kk < (c.len() >> 4); ++kk) {
-          const int st = st0 + kk;
-          const uint32_t acc = (c.first_in_kt() && kk == 0) ? 0u : 1u;
-          umma_bf16_ts(tmem_base + C_DV, buf + kk * 8, umma_desc_sw128(oa + st * 2048, 0, 1024), idesc_g, acc);
-          umma_bf16(tmem_base + C_DK, umma_desc_sw128(sa + (uint32_t)((st >> 2) * 16384 + (st & 3) * 32), 0, 1024),
-                    umma_desc_sw128(qa + st * 2048, 0, 1024), idesc_g, acc);
-        }
-        if (c.last_in_half()) {
-          if (c.kt == 0 && c.hq == 0 && c.k > 0) {   // the previous problem's dQ has been written out?
-            mbar_wait(bars + BB_DQFREE, (uint32_t)((c.k - 1) & 1));
-            tc_fence_after();
+        const int nst = c.len() >> 4;
+        // MN-major B tiles advance 2048 B (= 128 in descriptor units) per 16-row step
+        const uint64_t d_o = umma_desc_sw128(tile_addr(c.k, ord_q(c.hq) + 1), 0, 1024) + (uint64_t)(st0 * 128);
+        const uint64_t d_q = umma_desc_sw128(tile_addr(c.k, ord_q(c.hq)), 0, 1024) + (uint64_t)(st0 * 128);
+        const uint64_t d_s = umma_desc_sw128(sa, 0, 1024);        // dS^T K-major: step st at (st >> 2) * 16384 + (st & 3) * 32
+        const uint64_t d_sq = umma_desc_sw128(sa, 16384, 1024);   // dS^T read MN-major (queries on M): +2048 B per key step
+        const uint64_t d_k = umma_desc_sw128(tile_addr(c.k, ord_k(c.kt)), 0, 1024);
+        const int nks = nk_tile(c.kt) >> 4;
+        const uint32_t first = c.first_in_kt() ? 0u : 1u;
+        const bool rel_q = dq_now && c.kt == nkt - 1, rel_k = c.last_in_kt(), fin = c.last_in_problem();
+        if (elect_one()) {
+          // straight-line issue (uniform predicates instead of loops): the issuing thread, not the tensor pipe, is what
+          // bounds a run of small MMAs (tools/probes/mma_probe.cu: 36 - 53 cycles each at N = 64)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < nst) {
+              const int st = st0 + kk;
+              const uint32_t acc = kk > 0 ? 1u : first;
+              umma_bf16_ts(tmem_base + C_DV, buf + kk * 8, d_o + (uint64_t)(kk * 128), idesc_g, acc);
+              umma_bf16(tmem_base + C_DK, d_s + (uint64_t)((st >> 2) * 1024 + (st & 3) * 2), d_q + (uint64_t)(kk * 128), idesc_g, acc);
+            }
           }
-          const uint32_t ka = tile_addr(par, T_K0 + c.kt);
-          const int nk = nk_tile(c.kt);
-          for (int st = 0; st < (nk >> 4); ++st)   // contraction over the keys of this tile
-            umma_bf16(tmem_base + C_DQ + c.hq * 64, umma_desc_sw128(sa + st * 2048, 16384, 1024),
-                      umma_desc_sw128(ka + st * 2048, 0, 1024), idesc_q, (c.kt > 0 || st > 0) ? 1u : 0u);
-          umma_commit(bars + BB_DSFREE);
-          if (c.kt == nkt - 1) {   // last use of this half's Q / dO tiles
-            umma_commit(bars + BB_REL + par * 8 + T_Q0 + c.hq);
-            umma_commit(bars + BB_REL + par * 8 + T_DO0 + c.hq);
+          if (dq_now) {
+            const uint32_t dq_acc = c.kt > 0 ? 1u : 0u;
+#pragma unroll
+            for (int st = 0; st < 8; ++st)   // contraction over the keys of this tile
+              if (st < nks)
+                umma_bf16(tmem_base + C_DQ + c.hq * 64, d_sq + (uint64_t)(st * 128), d_k + (uint64_t)(st * 128), idesc_q,
+                          st > 0 ? 1u : dq_acc);
+            umma_commit(bars + BB_DSFREE);
+            if (rel_q) {   // last use of this half's Q / dO tiles
+              umma_commit(bars + BB_REL + par * 8 + ord_q(c.hq));
+              umma_commit(bars + BB_REL + par * 8 + ord_q(c.hq) + 1);
+            }
           }
+          if (rel_k) {
+            umma_commit(bars + BB_REL + par * 8 + ord_k(c.kt));
+            umma_commit(bars + BB_REL + par * 8 + ord_k(c.kt) + 1);
+            umma_commit(bars + BB_DKV);
+          }
+          if (fin) umma_commit(bars + BB_DQ);
         }
-        if (c.last_in_kt()) {
-          umma_commit(bars + BB_REL + par * 8 + T_K0 + c.kt);
-          umma_commit(bars + BB_REL + par * 8 + T_V0 + c.kt);
-          umma_commit(bars + BB_DKV);
-          ++n_kt_done;
-        }
-        if (c.last_in_problem()) umma_commit(bars + BB_DQ);
+        __syncwarp();
+        B2_TRACE(12);
+        if (rel_k) ++n_kt_done;
       };
 
       B2Iter sc, gr;
@@ -1380,8 +1415,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           mbar_wait(bars + BB_DFULL + par, (uint32_t)((c.k >> 1) & 1));
           delta_k = c.k;
         }
+        B2_TRACE(20);
         mbar_wait(bars + BB_S + set, (cc >> 1) & 1);
         tc_fence_after();
+        B2_TRACE(21);
         const int nk16 = min(128, ((nkv - c.kt * 128) + 15) & ~15);
         if (quarter * 32 < nk16) {   // warps whose 32 key rows are all padding only keep the barriers moving
           const int len = c.len(), qo = c.qo();
@@ -1402,9 +1439,11 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BB_MATH + set);
+        B2_TRACE(22);
         // deferred drains: their wait for the tensor pipe hides behind the chunk just done
         if (pend_dkv) { drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n); pend_dkv = false; }
         if (pend_dq) { drain_dq(pend_dq_bh, pend_dq_n); pend_dq = false; }
+        B2_TRACE(23);
       }
       if (c.last_in_half()) ++n_half;
       if (c.last_in_kt()) {
@@ -1472,3 +1511,22 @@ int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream) {
   VTB_LAUNCH_CHECK();
   return 0;
 }
+
+#ifdef VTB_ATTN_TRACE
+extern "C" int vtb_debug_attn_trace(uint32_t* out) {   // uint32 [12 warps][1024][2]; event id 0 = unused entry
+  VTB_CUDA(cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(unsigned int) * 12 * 2 * 1024));
+  static unsigned int zeros[12 * 2 * 1024];
+  VTB_CUDA(cudaMemcpyToSymbol(g_b2_trace, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
+
+#ifdef VTB_MBAR_DEBUG
+// debug builds only: {shared address of the barrier, parity, block, thread} of the first mbarrier wait that timed out
+extern "C" int vtb_debug_mbar_timeout(uint32_t* out) {
+  VTB_CUDA(cudaMemcpyFromSymbol(out, g_mbar_timeout, 16));
+  const uint32_t zero[4] = {0, 0, 0, 0};
+  VTB_CUDA(cudaMemcpyToSymbol(g_mbar_timeout, zero, 16));
+  return 0;
+}
+#endif

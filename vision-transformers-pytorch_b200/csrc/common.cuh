@@ -89,6 +89,21 @@ __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
 
+// one lane of a fully converged warp (the same lane every time: the lowest one).  An issuer warp runs its loop with all
+// 32 lanes and elects only around tcgen05.mma / tcgen05.commit, so that addresses and descriptors stay in uniform registers
+// (inside an `if (lane == 0)` region the compiler has to move every operand vector -> uniform with an ELECT / R2UR loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -117,13 +132,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a broken pipeline traps (-> launch error) instead of hanging the GPU.
+// Bounded spin: a broken pipeline traps (-> launch error) instead of hanging the GPU.  With -DVTB_MBAR_DEBUG the first
+// wait that times out records {shared address, parity, block, thread} in g_mbar_timeout (read back with
+// vtb_debug_mbar_timeout) and every later wait falls through, so the kernel ends and the record can be fetched.
+#ifdef VTB_MBAR_DEBUG
+__device__ unsigned int g_mbar_timeout[4];
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef VTB_MBAR_DEBUG
+    if ((++spins & 255u) == 0) {
+      if (*(volatile unsigned int*)&g_mbar_timeout[0] != 0) return;
+      if (clock64() - t0 > 200000000LL) {
+        if (atomicCAS(&g_mbar_timeout[0], 0u, smem_u32(bar)) == 0u) {
+          g_mbar_timeout[1] = parity; g_mbar_timeout[2] = blockIdx.x; g_mbar_timeout[3] = threadIdx.x;
+          __threadfence();
+        }
+        return;
+      }
+    }
+#else
     if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz
+#endif
   }
 }
 
