@@ -976,41 +976,44 @@ __device__ unsigned int g_b2_trace[12 * 2 * 1024];
 #define B2_TRACE_DECL do { } while (0)
 #define B2_TRACE(ev) do { } while (0)
 #endif
-constexpr int B2_THREADS = 384;
-constexpr int B2_REGS_AUX = 104, B2_REGS_MATH = 200;   // 384 x 168 at launch = 128 x 104 + 256 x 200
-constexpr int B2_IN_SLOTS = 11;                 // input tile slots; slots 11, 12 = the dS^T tile (two 64-query blocks)
+constexpr int B2_THREADS = 512;
+// registers (512 x 128 at launch): producer / issuer / delta warpgroup 96, drain warpgroup 80, the two math warpgroups 168
+constexpr int B2_REGS_AUX = 96, B2_REGS_DRAIN = 80, B2_REGS_MATH = 168;
+constexpr int B2_IN_SLOTS = 9;                  // input tile ring; then two dS^T buffers of two 64-query blocks each
 constexpr int B2_SLOT = 16384;
+constexpr uint32_t B2_DP_OFF = 64;   // dP^T columns of a chunk buffer sit this far behind its S^T columns
 constexpr int B2_OFF_DS = B2_IN_SLOTS * B2_SLOT;
-constexpr int B2_OFF_DELTA = B2_OFF_DS + 2 * B2_SLOT;          // float [2][256]
+constexpr int B2_OFF_DELTA = B2_OFF_DS + 4 * B2_SLOT;          // float [2][256]
 constexpr int B2_OFF_LSE = B2_OFF_DELTA + 2 * 256 * 4;         // float [2][256]
 constexpr int B2_OFF_BAR = B2_OFF_LSE + 2 * 256 * 4;           // 40 mbarriers
 constexpr int B2_OFF_TMEM = B2_OFF_BAR + 40 * 8;
 constexpr int SMEM_B2 = B2_OFF_TMEM + 16 + 1024;
-// tile ids
-enum { T_Q0 = 0, T_Q1, T_DO0, T_DO1, T_K0, T_K1, T_V0, T_V1 };
 // barrier indices
 constexpr int BB_FULL = 0;      // [2 parities][3 groups]  G0 = K0 V0 Q0 dO0, G1 = Q1 dO1, G2 = K1 V1
-constexpr int BB_REL = 6;       // [2][8] tile released
+constexpr int BB_REL = 6;       // [2][8] tile released (index = load order of the tile inside its problem)
 constexpr int BB_S = 22;        // [2] chunk buffer: scores complete
 constexpr int BB_MATH = 24;     // [2] chunk buffer: P^T / dS^T written (4 warps)
-constexpr int BB_DSFREE = 26;   // dQ of a half retired: the dS^T tile may be overwritten
-constexpr int BB_DKV = 27;      // dV, dK of a key tile complete
-constexpr int BB_DKVFREE = 28;  // ... drained (8 warps)
-constexpr int BB_DQ = 29;       // dQ of a problem complete
-constexpr int BB_DQFREE = 30;   // ... drained (8 warps)
-constexpr int BB_DFULL = 31;    // [2] delta / lse2 of the problem parity written (2 warps)
-constexpr int BB_DEMPTY = 33;   // [2] ... no longer needed (8 warps)
+constexpr int BB_DSFREE = 26;   // [2] dS^T buffer: the dQ product that read it retired
+constexpr int BB_DKV = 28;      // dV, dK of a key tile complete
+constexpr int BB_DKVFREE = 29;  // ... read out of TMEM (4 drain warps)
+constexpr int BB_DQ = 30;       // dQ of a problem complete
+constexpr int BB_DQFREE = 31;   // ... read out of TMEM (4 drain warps)
+constexpr int BB_DFULL = 32;    // [2] delta / lse2 of the problem parity written (2 warps)
+constexpr int BB_DEMPTY = 34;   // [2] ... no longer needed (8 math warps)
 
 // The chunk sequence of one CTA: problems bh = blockIdx.x, + gridDim.x, ...; per problem key tiles, query halves, two
-// chunks per half.  Every role walks the same sequence with its own iterator.
+// chunks per half.  Every role walks the same sequence with its own iterator.  `base` is the ring slot of the problem's
+// first tile (tile with load order `ord` sits in slot (base + ord) mod ns).
 struct B2Iter {
   int bh, k;            // problem, local problem counter
   int kt, hq, part;
   int nkt, nhq, n_bh, stride;
+  int tpp, ns, base;
   int len_a[2], len_b[2];
-  __device__ __forceinline__ void init(int first, int stride_, int n_bh_, int nq, int nkv) {
+  __device__ __forceinline__ void init(int first, int stride_, int n_bh_, int nq, int nkv, int tpp_, int ns_) {
     bh = first; stride = stride_; n_bh = n_bh_; k = 0; kt = hq = part = 0;
     nkt = (nkv + 127) >> 7; nhq = (nq + 127) >> 7;
+    tpp = tpp_; ns = ns_; base = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int nqh = max(0, min(128, ((nq - h * 128) + 15) & ~15));
@@ -1025,6 +1028,7 @@ struct B2Iter {
   __device__ __forceinline__ bool last_in_kt() const { return last_in_half() && hq == nhq - 1; }
   __device__ __forceinline__ bool last_in_problem() const { return last_in_kt() && kt == nkt - 1; }
   __device__ __forceinline__ bool first_in_kt() const { return hq == 0 && part == 0; }
+  __device__ __forceinline__ int slot(int ord) const { const int s = base + ord; return s >= ns ? s - ns : s; }
   __device__ __forceinline__ void advance() {
     if (!last_in_half()) { part = 1; return; }
     part = 0;
@@ -1032,20 +1036,23 @@ struct B2Iter {
     hq = 0;
     if (++kt < nkt) return;
     kt = 0; bh += stride; ++k;
+    base += tpp;
+    if (base >= ns) base -= ns;
   }
 };
 
-// One W-column (32 or 16) step of a chunk for one key row: P^T = exp2(S^T sl2 - lse2) -> bf16 pairs back into TMEM over
-// the S^T columns just read; dS^T = P^T (dP^T - delta) -> bf16 into this row of the 128B-swizzled shared tile.
-//   t_s: TMEM address of the S^T columns (dP^T sits 64 columns further), t_p: where the P^T pairs go
+// One W-column (32 or 16) step of a chunk for one key row: P^T = exp2(S^T sl2 - lse2) and dS^T = P^T (dP^T - delta), both
+// as bf16 pairs back into TMEM over the columns just read (A operands of dV / dK); dS^T also into this row of the
+// 128B-swizzled shared tile (dQ = dS K reads it MN-major).
+//   t_s: TMEM address of the S^T columns (dP^T sits B2_DP_OFF columns further), t_p: where the P^T pairs go
 //   l2a / dla: shared addresses of lse2 / delta of the step's first query;  ds_row: shared address of this row in
-//   block 0 of the dS^T tile;  q: first query of the step inside its 128-query half
+//   block 0 of the dS^T buffer;  q: first query of the step inside its 128-query half
 template <int W>
 __device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a, uint32_t dla, uint32_t ds_row, uint32_t q,
                                         uint32_t swz, float sl2, uint64_t* bar_dsfree, uint32_t dsfree_par, bool& ds_free) {
   uint32_t st[W], dp[W];
   tmem_ld_cols<W>(t_s, st);
-  tmem_ld_cols<W>(t_s + 64, dp);
+  tmem_ld_cols<W>(t_s + B2_DP_OFF, dp);
   tmem_ld_wait();
   uint32_t pp[W / 2], dd[W / 2];
 #pragma unroll
@@ -1069,12 +1076,22 @@ __device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a
         "r"(pp[W / 2 - 8]), "r"(pp[W / 2 - 7]), "r"(pp[W / 2 - 6]), "r"(pp[W / 2 - 5]), "r"(pp[W / 2 - 4]), "r"(pp[W / 2 - 3]),
         "r"(pp[W / 2 - 2]), "r"(pp[W / 2 - 1])
         : "memory");
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(t_p + B2_DP_OFF),
+        "r"(dd[0]), "r"(dd[1]), "r"(dd[2]), "r"(dd[3]), "r"(dd[4]), "r"(dd[5]), "r"(dd[6]), "r"(dd[7]),
+        "r"(dd[W / 2 - 8]), "r"(dd[W / 2 - 7]), "r"(dd[W / 2 - 6]), "r"(dd[W / 2 - 5]), "r"(dd[W / 2 - 4]), "r"(dd[W / 2 - 3]),
+        "r"(dd[W / 2 - 2]), "r"(dd[W / 2 - 1])
+        : "memory");
   } else {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t_p), "r"(pp[0]),
                  "r"(pp[1]), "r"(pp[2]), "r"(pp[3]), "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7])
                  : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t_p + B2_DP_OFF), "r"(dd[0]),
+                 "r"(dd[1]), "r"(dd[2]), "r"(dd[3]), "r"(dd[4]), "r"(dd[5]), "r"(dd[6]), "r"(dd[7])
+                 : "memory");
   }
-  if (!ds_free) {   // the previous half's dQ product no longer reads the dS^T tile
+  if (!ds_free) {   // the dQ product that read this dS^T buffer two halves ago has retired
     mbar_wait(bar_dsfree, dsfree_par);
     ds_free = true;
   }
@@ -1084,6 +1101,24 @@ __device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a
     sts_u4(ds_row + (qq >> 6) * 16384u + ((((qq & 63u) >> 3) ^ swz) << 4), dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2],
            dd[g * 4 + 3]);
   }
+}
+
+// 64 fp32 accumulator columns of this thread's TMEM lane -> 64 bf16 (x f) -> one 128-byte row of global memory
+__device__ __forceinline__ void b2_store_row(const uint32_t (&a0)[32], const uint32_t (&a1)[32], float f, bf16* dst) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 8)
+    *reinterpret_cast<uint4*>(dst + e) = make_uint4(
+        pack_bf16(__uint_as_float(a0[e]) * f, __uint_as_float(a0[e + 1]) * f),
+        pack_bf16(__uint_as_float(a0[e + 2]) * f, __uint_as_float(a0[e + 3]) * f),
+        pack_bf16(__uint_as_float(a0[e + 4]) * f, __uint_as_float(a0[e + 5]) * f),
+        pack_bf16(__uint_as_float(a0[e + 6]) * f, __uint_as_float(a0[e + 7]) * f));
+#pragma unroll
+  for (int e = 0; e < 32; e += 8)
+    *reinterpret_cast<uint4*>(dst + 32 + e) = make_uint4(
+        pack_bf16(__uint_as_float(a1[e]) * f, __uint_as_float(a1[e + 1]) * f),
+        pack_bf16(__uint_as_float(a1[e + 2]) * f, __uint_as_float(a1[e + 3]) * f),
+        pack_bf16(__uint_as_float(a1[e + 4]) * f, __uint_as_float(a1[e + 5]) * f),
+        pack_bf16(__uint_as_float(a1[e + 6]) * f, __uint_as_float(a1[e + 7]) * f));
 }
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
@@ -1106,7 +1141,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   // tile ring (see the producer): load order K0 V0 Q0 dO0 [Q1 dO1] [K1 V1]; the released-barrier index of a tile is its order
   const int tpp = 4 + (nhq > 1 ? 2 : 0) + (nkt > 1 ? 2 : 0);   // tiles per problem
   const int ord_k1 = 4 + (nhq > 1 ? 2 : 0);
-  const int ns = tpp == 4 ? 8 : B2_IN_SLOTS;                    // ring size
+  const int ns = tpp == 4 ? 8 : B2_IN_SLOTS;                    // ring size (<= 2 tpp, see the producer)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1114,9 +1149,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       for (int i = 0; i < 22; ++i) mbar_init(bars + i, 1);        // full, released
       mbar_init(bars + BB_S, 1); mbar_init(bars + BB_S + 1, 1);
       mbar_init(bars + BB_MATH, 4); mbar_init(bars + BB_MATH + 1, 4);
-      mbar_init(bars + BB_DSFREE, 1);
-      mbar_init(bars + BB_DKV, 1); mbar_init(bars + BB_DKVFREE, 8);
-      mbar_init(bars + BB_DQ, 1); mbar_init(bars + BB_DQFREE, 8);
+      mbar_init(bars + BB_DSFREE, 1); mbar_init(bars + BB_DSFREE + 1, 1);
+      mbar_init(bars + BB_DKV, 1); mbar_init(bars + BB_DKVFREE, 4);
+      mbar_init(bars + BB_DQ, 1); mbar_init(bars + BB_DQFREE, 4);
       mbar_init(bars + BB_DFULL, 2); mbar_init(bars + BB_DFULL + 1, 2);
       mbar_init(bars + BB_DEMPTY, 8); mbar_init(bars + BB_DEMPTY + 1, 8);
       mbar_fence_init();
@@ -1130,8 +1165,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t C_DV = 256, C_DK = 320, C_DQ = 384;
 
-  // registers: the producer / issuer / delta warpgroup hands most of its share to the two math warpgroups
-  // (384 x 168 at launch = 128 x 88 + 256 x 208)
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_AUX));
   if (warp == 0) {
@@ -1140,7 +1173,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     // problem), tile g lives in slot g % ns.  Tiles die in (nearly) the same order, so before loading tile g the producer
     // waits for the "released" barrier of tile g - ns.  ns <= 2 tiles-per-problem keeps that barrier at most one phase ahead.
     if (lane == 0) {
-      int k = 0;
+      int k = 0, base = 0;
       for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
         const int par = k & 1;
         const int b = bh / heads, c0 = (bh - b * heads) * DH;
@@ -1158,7 +1191,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           }
         };
         auto load = [&](int ord, const CUtensorMap* map, int tok, uint64_t* bar) {
-          tma_load_3d(smem + ((tpp * k + ord) % ns) * B2_SLOT, map, bar, c0, tok, b);
+          const int sl = base + ord;
+          tma_load_3d(smem + (sl >= ns ? sl - ns : sl) * B2_SLOT, map, bar, c0, tok, b);
         };
         reserve(0, 4);
         mbar_expect_tx(f0, 4 * B2_SLOT);
@@ -1173,19 +1207,21 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           mbar_expect_tx(f0 + 2, 2 * B2_SLOT);
           load(ord_k1, &tk, 128, f0 + 2); load(ord_k1 + 1, &tv, 128, f0 + 2);
         }
+        base += tpp;
+        if (base >= ns) base -= ns;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------------ UMMA issuer
     // All 32 lanes walk the chunk sequence (everything below is warp-uniform); one elected lane issues the tcgen05 ops.
     {
-      const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dV, dK: A K-major (P^T in TMEM / dS^T), B MN-major
+      const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dV, dK: A = P^T / dS^T in TMEM, B MN-major
       const uint32_t idesc_q = umma_idesc_bf16(128, DH, 1, 1);   // dQ   : A MN-major (dS^T as dS), B MN-major
       const uint32_t sa = smem_u32(sdS), s0 = smem_u32(smem);
       // tile order inside a problem: K_kt, V_kt, Q_hq, dO_hq
       auto ord_k = [&](int kt) { return kt ? ord_k1 : 0; };
       auto ord_q = [&](int hq) { return hq ? 4 : 2; };
-      auto tile_addr = [&](int k, int ord) { return s0 + (uint32_t)((tpp * k + ord) % ns) * B2_SLOT; };
+      auto tile_addr = [&](const B2Iter& c, int ord) { return s0 + (uint32_t)c.slot(ord) * B2_SLOT; };
       auto nk_tile = [&](int kt) { return min(128, ((nkv - kt * 128) + 15) & ~15); };
 
       auto issue_scores = [&](const B2Iter& c, uint32_t cc) {
@@ -1196,11 +1232,12 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           if (c.kt == 0 && c.hq == 1) mbar_wait(bars + BB_FULL + par * 3 + 1, use);
           if (c.kt == 1 && c.hq == 0) mbar_wait(bars + BB_FULL + par * 3 + 2, use);
           tc_fence_after();
+          B2_TRACE(16);
         }
         const uint32_t buf = tmem_base + (cc & 1) * 128;
-        const uint32_t ka = tile_addr(c.k, ord_k(c.kt)), va = tile_addr(c.k, ord_k(c.kt) + 1);
-        const uint32_t qa = tile_addr(c.k, ord_q(c.hq)) + (uint32_t)c.qo() * 128u;
-        const uint32_t oa = tile_addr(c.k, ord_q(c.hq) + 1) + (uint32_t)c.qo() * 128u;
+        const uint32_t ka = tile_addr(c, ord_k(c.kt)), va = tile_addr(c, ord_k(c.kt) + 1);
+        const uint32_t qa = tile_addr(c, ord_q(c.hq)) + (uint32_t)c.qo() * 128u;
+        const uint32_t oa = tile_addr(c, ord_q(c.hq) + 1) + (uint32_t)c.qo() * 128u;
         const uint32_t idesc_s = umma_idesc_bf16(128, c.len(), 0, 0);
         const uint64_t dk = umma_desc_sw128(ka, 0, 1024), dq = umma_desc_sw128(qa, 0, 1024);
         const uint64_t dv = umma_desc_sw128(va, 0, 1024), dd = umma_desc_sw128(oa, 0, 1024);
@@ -1208,7 +1245,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) umma_bf16(buf, dk + 2 * kk, dq + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);   // +32 B
 #pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk) umma_bf16(buf + 64, dv + 2 * kk, dd + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < DH / 16; ++kk) umma_bf16(buf + B2_DP_OFF, dv + 2 * kk, dd + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
           umma_commit(bars + BB_S + (cc & 1));
         }
         __syncwarp();
@@ -1216,25 +1253,25 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       };
 
       uint32_t n_kt_done = 0;   // key-tile iterations whose dV / dK are complete (drain counter)
+      uint32_t n_half = 0;      // half-iterations whose dQ product has been issued (dS^T buffer = n_half & 1)
       auto issue_grads = [&](const B2Iter& c, uint32_t cc) {
         const int par = c.k & 1;
         const uint32_t buf = tmem_base + (cc & 1) * 128;
         B2_TRACE(10);
         mbar_wait(bars + BB_MATH + (cc & 1), (cc >> 1) & 1);
         B2_TRACE(11);
-        if (c.first_in_kt() && n_kt_done > 0) mbar_wait(bars + BB_DKVFREE, (n_kt_done - 1) & 1);
+        if (c.first_in_kt() && n_kt_done > 0) { mbar_wait(bars + BB_DKVFREE, (n_kt_done - 1) & 1); B2_TRACE(14); }
         const bool dq_now = c.last_in_half();
-        if (dq_now && c.kt == 0 && c.hq == 0 && c.k > 0)   // the previous problem's dQ has been written out?
-          mbar_wait(bars + BB_DQFREE, (uint32_t)((c.k - 1) & 1));
+        if (dq_now && c.kt == 0 && c.hq == 0 && c.k > 0)   // the previous problem's dQ has been read out?
+          { mbar_wait(bars + BB_DQFREE, (uint32_t)((c.k - 1) & 1)); B2_TRACE(15); }
         tc_fence_after();
         const int st0 = c.qo() >> 4;   // first 16-query step of the chunk inside its half
         const int nst = c.len() >> 4;
         // MN-major B tiles advance 2048 B (= 128 in descriptor units) per 16-row step
-        const uint64_t d_o = umma_desc_sw128(tile_addr(c.k, ord_q(c.hq) + 1), 0, 1024) + (uint64_t)(st0 * 128);
-        const uint64_t d_q = umma_desc_sw128(tile_addr(c.k, ord_q(c.hq)), 0, 1024) + (uint64_t)(st0 * 128);
-        const uint64_t d_s = umma_desc_sw128(sa, 0, 1024);        // dS^T K-major: step st at (st >> 2) * 16384 + (st & 3) * 32
-        const uint64_t d_sq = umma_desc_sw128(sa, 16384, 1024);   // dS^T read MN-major (queries on M): +2048 B per key step
-        const uint64_t d_k = umma_desc_sw128(tile_addr(c.k, ord_k(c.kt)), 0, 1024);
+        const uint64_t d_o = umma_desc_sw128(tile_addr(c, ord_q(c.hq) + 1), 0, 1024) + (uint64_t)(st0 * 128);
+        const uint64_t d_q = umma_desc_sw128(tile_addr(c, ord_q(c.hq)), 0, 1024) + (uint64_t)(st0 * 128);
+        const uint64_t d_sq = umma_desc_sw128(sa + (n_half & 1) * 2 * B2_SLOT, 16384, 1024);   // dS^T read MN-major: +2048 B per key step
+        const uint64_t d_k = umma_desc_sw128(tile_addr(c, ord_k(c.kt)), 0, 1024);
         const int nks = nk_tile(c.kt) >> 4;
         const uint32_t first = c.first_in_kt() ? 0u : 1u;
         const bool rel_q = dq_now && c.kt == nkt - 1, rel_k = c.last_in_kt(), fin = c.last_in_problem();
@@ -1244,10 +1281,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (kk < nst) {
-              const int st = st0 + kk;
               const uint32_t acc = kk > 0 ? 1u : first;
               umma_bf16_ts(tmem_base + C_DV, buf + kk * 8, d_o + (uint64_t)(kk * 128), idesc_g, acc);
-              umma_bf16(tmem_base + C_DK, d_s + (uint64_t)((st >> 2) * 1024 + (st & 3) * 2), d_q + (uint64_t)(kk * 128), idesc_g, acc);
+              umma_bf16_ts(tmem_base + C_DK, buf + B2_DP_OFF + kk * 8, d_q + (uint64_t)(kk * 128), idesc_g, acc);
             }
           }
           if (dq_now) {
@@ -1257,7 +1293,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
               if (st < nks)
                 umma_bf16(tmem_base + C_DQ + c.hq * 64, d_sq + (uint64_t)(st * 128), d_k + (uint64_t)(st * 128), idesc_q,
                           st > 0 ? 1u : dq_acc);
-            umma_commit(bars + BB_DSFREE);
+            umma_commit(bars + BB_DSFREE + (n_half & 1));
             if (rel_q) {   // last use of this half's Q / dO tiles
               umma_commit(bars + BB_REL + par * 8 + ord_q(c.hq));
               umma_commit(bars + BB_REL + par * 8 + ord_q(c.hq) + 1);
@@ -1272,11 +1308,12 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         }
         __syncwarp();
         B2_TRACE(12);
+        if (dq_now) ++n_half;
         if (rel_k) ++n_kt_done;
       };
 
       B2Iter sc, gr;
-      sc.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
+      sc.init(blockIdx.x, gridDim.x, n_bh, nq, nkv, tpp, ns);
       gr = sc;
       uint32_t cs = 0, cg = 0;
       for (int i = 0; i < 2 && sc.valid(); ++i) { issue_scores(sc, cs++); sc.advance(); }
@@ -1324,89 +1361,65 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       if (lane == 0) mbar_arrive(bars + BB_DFULL + par);
     }
   }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------------------------------------ drain warps
+    // dV / dK of every key tile and dQ of every problem: TMEM -> bf16 -> global, one accumulator row (128 B) per thread.
+    // Dedicated warps: the accumulators are handed back to the issuer a few hundred cycles after they complete, and the
+    // math sets never stall on the tensor pipe.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_DRAIN));
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t n_kt = 0;
+    int k = 0;
+    for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
+      const int b = bh / heads, h = bh - b * heads;
+      for (int kt = 0; kt < nkt; ++kt, ++n_kt) {
+        mbar_wait(bars + BB_DKV, n_kt & 1);
+        tc_fence_after();
+        const int j = kt * 128 + row;
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(t_row + C_DV, a0);
+        tmem_ld_32x32(t_row + C_DV + 32, a1);
+        tmem_ld_wait();
+        if (j < nkv) b2_store_row(a0, a1, 1.f, dV + ((long)b * nkv + j) * lddv + h * DH);
+        tmem_ld_32x32(t_row + C_DK, a0);
+        tmem_ld_32x32(t_row + C_DK + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BB_DKVFREE);
+        if (j < nkv) b2_store_row(a0, a1, scale, dK + ((long)b * nkv + j) * lddk + h * DH);
+      }
+      mbar_wait(bars + BB_DQ, (uint32_t)(k & 1));
+      tc_fence_after();
+      for (int hq = 0; hq < nhq; ++hq) {
+        const int i = hq * 128 + row;
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(t_row + C_DQ + hq * 64, a0);
+        tmem_ld_32x32(t_row + C_DQ + hq * 64 + 32, a1);
+        tmem_ld_wait();
+        if (hq == nhq - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + BB_DQFREE);
+        }
+        if (i < nq) b2_store_row(a0, a1, scale, dQ + ((long)b * nq + i) * lddq + h * DH);
+      }
+    }
   } else {
     // ------------------------------------------------------------------------------------------------ math sets
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_REGS_MATH));
     const int set = (warp - 4) >> 2;                // owns chunk buffer `set`
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;            // key row inside the tile == TMEM lane
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t t_buf = t_row + (uint32_t)set * 128u;
+    const uint32_t t_buf = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
     const float sl2 = scale * 1.4426950408889634f;
 
-    // dV, dK of one key tile: TMEM -> bf16 -> global rows of the keys (set 0: dV, set 1: dK * scale)
-    auto drain_dkv = [&](int bh, int kt, uint32_t n) {
-      mbar_wait(bars + BB_DKV, n & 1);
-      tc_fence_after();
-      uint32_t a0[32], a1[32];
-      tmem_ld_32x32(t_row + (set ? C_DK : C_DV), a0);
-      tmem_ld_32x32(t_row + (set ? C_DK : C_DV) + 32, a1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BB_DKVFREE);
-      const int j = kt * 128 + row;
-      if (j < nkv) {
-        const int b = bh / heads, h = bh - b * heads;
-        const float f = set ? scale : 1.f;
-        bf16* dst = (set ? dK + ((long)b * nkv + j) * lddk : dV + ((long)b * nkv + j) * lddv) + h * DH;
-#pragma unroll
-        for (int e = 0; e < 32; e += 8)
-          *reinterpret_cast<uint4*>(dst + e) = make_uint4(
-              pack_bf16(__uint_as_float(a0[e]) * f, __uint_as_float(a0[e + 1]) * f),
-              pack_bf16(__uint_as_float(a0[e + 2]) * f, __uint_as_float(a0[e + 3]) * f),
-              pack_bf16(__uint_as_float(a0[e + 4]) * f, __uint_as_float(a0[e + 5]) * f),
-              pack_bf16(__uint_as_float(a0[e + 6]) * f, __uint_as_float(a0[e + 7]) * f));
-#pragma unroll
-        for (int e = 0; e < 32; e += 8)
-          *reinterpret_cast<uint4*>(dst + 32 + e) = make_uint4(
-              pack_bf16(__uint_as_float(a1[e]) * f, __uint_as_float(a1[e + 1]) * f),
-              pack_bf16(__uint_as_float(a1[e + 2]) * f, __uint_as_float(a1[e + 3]) * f),
-              pack_bf16(__uint_as_float(a1[e + 4]) * f, __uint_as_float(a1[e + 5]) * f),
-              pack_bf16(__uint_as_float(a1[e + 6]) * f, __uint_as_float(a1[e + 7]) * f));
-      }
-    };
-    // dQ of one problem: rows = queries; set s writes columns [32 s, 32 s + 32) of both halves
-    auto drain_dq = [&](int bh, uint32_t n) {
-      mbar_wait(bars + BB_DQ, n & 1);
-      tc_fence_after();
-      uint32_t a0[32], a1[32];
-      tmem_ld_32x32(t_row + C_DQ + set * 32, a0);
-      if (nhq > 1) tmem_ld_32x32(t_row + C_DQ + 64 + set * 32, a1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BB_DQFREE);
-      const int b = bh / heads, h = bh - b * heads;
-      if (row < nq) {
-        bf16* dst = dQ + ((long)b * nq + row) * lddq + h * DH + set * 32;
-#pragma unroll
-        for (int e = 0; e < 32; e += 8)
-          *reinterpret_cast<uint4*>(dst + e) = make_uint4(
-              pack_bf16(__uint_as_float(a0[e]) * scale, __uint_as_float(a0[e + 1]) * scale),
-              pack_bf16(__uint_as_float(a0[e + 2]) * scale, __uint_as_float(a0[e + 3]) * scale),
-              pack_bf16(__uint_as_float(a0[e + 4]) * scale, __uint_as_float(a0[e + 5]) * scale),
-              pack_bf16(__uint_as_float(a0[e + 6]) * scale, __uint_as_float(a0[e + 7]) * scale));
-      }
-      if (nhq > 1 && 128 + row < nq) {
-        bf16* dst = dQ + ((long)b * nq + 128 + row) * lddq + h * DH + set * 32;
-#pragma unroll
-        for (int e = 0; e < 32; e += 8)
-          *reinterpret_cast<uint4*>(dst + e) = make_uint4(
-              pack_bf16(__uint_as_float(a1[e]) * scale, __uint_as_float(a1[e + 1]) * scale),
-              pack_bf16(__uint_as_float(a1[e + 2]) * scale, __uint_as_float(a1[e + 3]) * scale),
-              pack_bf16(__uint_as_float(a1[e + 4]) * scale, __uint_as_float(a1[e + 5]) * scale),
-              pack_bf16(__uint_as_float(a1[e + 6]) * scale, __uint_as_float(a1[e + 7]) * scale));
-      }
-    };
-
     B2Iter c;
-    c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
-    uint32_t cc = 0, n_half = 0, n_kt = 0;
-    bool pend_dkv = false, pend_dq = false;
-    int pend_dkv_bh = 0, pend_dkv_kt = 0, pend_dq_bh = 0;
-    uint32_t pend_dkv_n = 0, pend_dq_n = 0;
+    c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv, tpp, ns);
+    uint32_t cc = 0, n_half = 0;
     int delta_k = -1;   // problem whose delta / lse2 this warp has acquired
     for (; c.valid(); c.advance(), ++cc) {
       if ((int)(cc & 1) == set) {
@@ -1424,15 +1437,19 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           const int len = c.len(), qo = c.qo();
           const uint32_t l2a = smem_u32(sLse2) + (uint32_t)(par * 256 + c.hq * 128 + qo) * 4u;
           const uint32_t dla = smem_u32(sDelta) + (uint32_t)(par * 256 + c.hq * 128 + qo) * 4u;
-          const uint32_t ds_row = smem_u32(sdS) + (uint32_t)row * 128u;
-          bool ds_free = (n_half == 0);
+          const uint32_t ds_row = smem_u32(sdS) + (n_half & 1) * 2 * B2_SLOT + (uint32_t)row * 128u;
+          // dS^T buffer n_half & 1 was last read by the dQ product of half-iteration n_half - 2
+          bool ds_free = (n_half < 2);
+          uint64_t* bar_ds = bars + BB_DSFREE + (n_half & 1);
+          const uint32_t ds_par = ((n_half >> 1) + 1) & 1;
           int c0 = 0;
           for (; c0 + 32 <= len; c0 += 32)
-            b2_step<32>(t_buf + c0, t_buf + (c0 >> 1), l2a + c0 * 4, dla + c0 * 4, ds_row, (uint32_t)(qo + c0), swz, sl2,
-                        bars + BB_DSFREE, (n_half - 1) & 1, ds_free);
+            b2_step<32>(t_buf + c0, t_buf + (c0 >> 1), l2a + c0 * 4, dla + c0 * 4, ds_row, (uint32_t)(qo + c0), swz, sl2, bar_ds,
+                        ds_par, ds_free);
           if (c0 < len)
-            b2_step<16>(t_buf + c0, t_buf + (c0 >> 1), l2a + c0 * 4, dla + c0 * 4, ds_row, (uint32_t)(qo + c0), swz, sl2,
-                        bars + BB_DSFREE, (n_half - 1) & 1, ds_free);
+            b2_step<16>(t_buf + c0, t_buf + (c0 >> 1), l2a + c0 * 4, dla + c0 * 4, ds_row, (uint32_t)(qo + c0), swz, sl2, bar_ds,
+                        ds_par, ds_free);
+          B2_TRACE(24);
           tmem_st_wait();
         }
         tc_fence_before();
@@ -1440,25 +1457,13 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BB_MATH + set);
         B2_TRACE(22);
-        // deferred drains: their wait for the tensor pipe hides behind the chunk just done
-        if (pend_dkv) { drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n); pend_dkv = false; }
-        if (pend_dq) { drain_dq(pend_dq_bh, pend_dq_n); pend_dq = false; }
-        B2_TRACE(23);
       }
       if (c.last_in_half()) ++n_half;
-      if (c.last_in_kt()) {
-        if (pend_dkv) drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n);
-        pend_dkv = true; pend_dkv_bh = c.bh; pend_dkv_kt = c.kt; pend_dkv_n = n_kt++;
-      }
       if (c.last_in_problem()) {
-        if (pend_dq) drain_dq(pend_dq_bh, pend_dq_n);
-        pend_dq = true; pend_dq_bh = c.bh; pend_dq_n = (uint32_t)c.k;
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BB_DEMPTY + (c.k & 1));   // this warp is done with the problem's delta / lse2
       }
     }
-    if (pend_dkv) drain_dkv(pend_dkv_bh, pend_dkv_kt, pend_dkv_n);
-    if (pend_dq) drain_dq(pend_dq_bh, pend_dq_n);
   }
 
   tc_fence_before();
