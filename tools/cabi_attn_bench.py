@@ -196,9 +196,9 @@ def dump_trace(path):
     """Debug builds (-DVTB_ATTN_TRACE): timeline of block 0 of the last backward launch."""
     if not hasattr(lib, "vtb_debug_attn_trace"):
         return
-    out = (C.c_uint32 * (12 * 2 * 1024))()
+    out = (C.c_uint32 * (16 * 2 * 1024))()
     lib.vtb_debug_attn_trace(out)
-    ev = sorted((out[(w * 1024 + i) * 2 + 1], w, out[(w * 1024 + i) * 2]) for w in range(12) for i in range(1024)
+    ev = sorted((out[(w * 1024 + i) * 2 + 1], w, out[(w * 1024 + i) * 2]) for w in range(16) for i in range(1024)
                 if out[(w * 1024 + i) * 2])
     with open(path, "w") as fh:
         t0 = ev[0][0] if ev else 0

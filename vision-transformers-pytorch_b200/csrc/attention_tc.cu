@@ -244,8 +244,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 //     keys / values are loaded ONCE for both (version 1 loaded them once per tile);
 //   * paired mode  (nq <= 128 and nkv <= 128: 96^2 crops with 37 tokens, the PVT cls stage): the tiles are two
 //     different (image, head) problems, tile t uses key rows [128 t, 128 t + nkv) of the stage.
-// warp 0 lane 0: TMA producer (2-stage ring, full / empty mbarriers);   warp 1 lane 0: UMMA issuer;
-// warps 2-5: softmax + epilogue of tile 0, warps 6-9: of tile 1 (one query row per thread = one TMEM lane).
+// warps 0-3: softmax + epilogue of tile 0, warps 4-7: of tile 1 (one query row per thread = one TMEM lane);
+// warp 8 lane 0: TMA producer (2-stage ring, full / empty mbarriers);   warp 9 lane 0: UMMA issuer.
 // TMEM: tile t owns columns [256 t, 256 t + 256): S at +0 (P written back over it as bf16 pairs), O at +128.
 // While set 0 runs its softmax the tensor pipe computes S of tile 1; while set 1 finishes, P V of tile 0 and the
 // next item's S of tile 0 are issued, and the next item's Q / K / V have been in flight since the stage was released.
@@ -320,7 +320,9 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ns = (nkv + 15) & ~15;  // UMMA N of the score tile / contraction length of P V
 
-  if (warp == 0) {
+  // warp roles: 0-3 softmax + epilogue of tile 0, 4-7 of tile 1, 8 TMA producer, 9 UMMA issuer (the arbiter prefers the
+  // highest warp id of a scheduler partition: the issuer must not starve behind the softmax warps)
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
       for (int i = 0; i < 2; ++i) {
@@ -337,7 +339,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       const int nbox = (nkv > 128) ? 2 : 1;
       int k = 0;
@@ -362,7 +364,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(TQ, ns, 0, 0);   // S = Q K^T: both operands K-major
       const uint32_t idesc_o = umma_idesc_bf16(TQ, DH, 0, 1);   // O = P V: A = P from TMEM, B = V MN-major
@@ -426,8 +428,8 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 2..9)
-    const int t = (warp - 2) >> 2;             // the tile this warp set serves
+    // ---------------------------------------------------------------- softmax + epilogue (warps 0..7)
+    const int t = warp >> 2;                   // the tile this warp set serves
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;       // query row in the tile == TMEM lane
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)t * 256u;
@@ -541,7 +543,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -962,7 +964,7 @@ namespace {
 #ifdef VTB_ATTN_TRACE
 // timeline of block 0 (debug builds): per warp a private list of {event id, clock} pairs (plain stores, no atomics: the
 // probe must not stall the warp), fetched with vtb_debug_attn_trace
-__device__ unsigned int g_b2_trace[12 * 2 * 1024];
+__device__ unsigned int g_b2_trace[16 * 2 * 1024];
 #define B2_TRACE_DECL unsigned int trace_i__ = 0
 #define B2_TRACE(ev)                                                                              \
   do {                                                                                            \
@@ -1165,9 +1167,11 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t C_DV = 256, C_DK = 320, C_DQ = 384;
 
-  if (warp < 4) {
+  // Warp roles.  The hardware arbiter prefers the HIGHEST warp id of a scheduler partition (warp id % 4), so the UMMA issuer,
+  // whose instruction stream is the critical path, is warp 15; drain warps (bursty, latency-tolerant) are warps 0-3.
+  if (warp >= 12) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_AUX));
-  if (warp == 0) {
+  if (warp == 14) {
     // ------------------------------------------------------------------------------------------------ TMA producer
     // The input slots form a RING: the tiles of all problems are numbered in load order (K0 V0 Q0 dO0 [Q1 dO1] [K1 V1] per
     // problem), tile g lives in slot g % ns.  Tiles die in (nearly) the same order, so before loading tile g the producer
@@ -1211,7 +1215,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         if (base >= ns) base -= ns;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 15) {
     // ------------------------------------------------------------------------------------------------ UMMA issuer
     // All 32 lanes walk the chunk sequence (everything below is warp-uniform); one elected lane issues the tcgen05 ops.
     {
@@ -1325,7 +1329,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------------------------------------ delta / lse2
-    const int t2 = threadIdx.x - 64;   // 0..63
+    const int t2 = threadIdx.x - 12 * 32;   // 0..63
     int k = 0;
     for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
       const int par = k & 1;
@@ -1361,7 +1365,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       if (lane == 0) mbar_arrive(bars + BB_DFULL + par);
     }
   }
-  } else if (warp >= 12) {
+  } else if (warp < 4) {
     // ------------------------------------------------------------------------------------------------ drain warps
     // dV / dK of every key tile and dQ of every problem: TMEM -> bf16 -> global, one accumulator row (128 B) per thread.
     // Dedicated warps: the accumulators are handed back to the issuer a few hundred cycles after they complete, and the
@@ -1518,9 +1522,9 @@ int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream) {
 }
 
 #ifdef VTB_ATTN_TRACE
-extern "C" int vtb_debug_attn_trace(uint32_t* out) {   // uint32 [12 warps][1024][2]; event id 0 = unused entry
-  VTB_CUDA(cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(unsigned int) * 12 * 2 * 1024));
-  static unsigned int zeros[12 * 2 * 1024];
+extern "C" int vtb_debug_attn_trace(uint32_t* out) {   // uint32 [16 warps][1024][2]; event id 0 = unused entry
+  VTB_CUDA(cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(unsigned int) * 16 * 2 * 1024));
+  static unsigned int zeros[16 * 2 * 1024];
   VTB_CUDA(cudaMemcpyToSymbol(g_b2_trace, zeros, sizeof(zeros)));
   return 0;
 }

@@ -153,6 +153,10 @@ def get():
         torch.zeros(1, device="cuda")
         check(lib.vtb_init(), lib)
         _inited = True
+        # A/B switches from the environment, e.g. VTB_OPTS=attn_tc_fwd_version=1,attn_tc_bwd_version=1
+        for kv in filter(None, os.environ.get("VTB_OPTS", "").split(",")):
+            name, _, val = kv.partition("=")
+            check(lib.vtb_set_option(name.strip().encode(), int(val)), lib)
     return lib
 
 
