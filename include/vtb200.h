@@ -302,6 +302,9 @@ int vtb_mt_adamw(void* const* param, const void* const* grad, void* const* exp_a
  *   (correct NULL ok; with loss, row_loss and dlogits all NULL the call is `accuracy` alone)
  * logits f32 [rows, n_class] with row stride ld, targets int64 (target2 NULL => target1), inter f32 [rows] (NULL => 1),
  * loss f32 [1] (atomicAdd: zero it; may be NULL), correct int32 [2].
+ * A row whose target1 / target2 lies outside [0, n_class) is skipped (no loss, zero gradient, no hit, nothing read out of
+ * bounds): MixLoss defines no ignore_index, and with reduction "mean" the divisor stays the full row count.  A row whose
+ * target logit is NaN counts as a miss.
  * ---------------------------------------------------------------------------------------------- */
 int vtb_mix_loss(const float* logits, int64_t ld, const int64_t* target1, const int64_t* target2, const float* inter,
                  int32_t rows, int32_t n_class, double eps, float loss_scale, float* loss, float* row_loss,

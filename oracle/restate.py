@@ -142,6 +142,8 @@ def vit_forward(sd, inputs, *, patch, depth, heads, head_fn=None, dp_scales=None
 
 def dino_head(sd, x, pre="head."):
     """DINOHead.forward (vit.py:257-262): MLP with exact GELU, L2-normalise, weight-normed Linear (no bias)."""
+    if f"{pre}mlp.weight" in sd:   # depth 1: the MLP is a single Linear (vit.py:219-220)
+        x = linear(x, sd[f"{pre}mlp.weight"], sd[f"{pre}mlp.bias"])
     i = 0
     while f"{pre}mlp.{i}.weight" in sd:
         x = linear(x, sd[f"{pre}mlp.{i}.weight"], sd[f"{pre}mlp.{i}.bias"])

@@ -45,6 +45,39 @@ def _worker(rank, world, port, q):
     got2 = torch.cat([p.grad.flatten() for p in model2.parameters()])
     ok = ok and torch.allclose(got2, want, atol=1e-6)
     ok = ok and all(p.grad.data_ptr() >= red2._flat[0].data_ptr() for p in red2.buckets[0])
+    # a detached .grad (train_util.cancel_last_layer_grad sets p.grad = None on the DINO `last` layer; so does
+    # optimizer.zero_grad(set_to_none=True)) must not leave the replicas averaging a stale bucket slice
+    import train_util as T
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Linear(8, 8)
+            self.last = torch.nn.Linear(8, 4)
+
+        def forward(self, t):
+            return self.last(self.body(t))
+
+    torch.manual_seed(1)
+    net = Net()
+    red3 = vd.FlatGradReducer(net.parameters(), bucket_mb=1).attach()
+    red3.zero()
+    net(x).sum().backward()
+    red3.reduce()
+    T.cancel_last_layer_grad(0, net, freeze=1)              # after the all-reduce, as train_dino.py orders it
+    ok = ok and net.last.weight.grad is None and net.body.weight.grad is not None
+    red3.zero()                                             # next step: the link is repaired, not silently lost
+    ok = ok and all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in red3._views())
+    net(x).sum().backward()
+    local3 = torch.cat([p.grad.flatten().clone() for p in net.parameters()])
+    for p in net.last.parameters():                         # detached BEFORE reduce(): copied back into the bucket
+        p.grad = p.grad.clone()
+    repaired = red3.reattach()
+    red3.reduce()
+    g3 = [torch.zeros_like(local3) for _ in range(world)]
+    dist.all_gather(g3, local3)
+    got3 = torch.cat([p.grad.flatten() for p in net.parameters()])
+    ok = ok and repaired == 2 and torch.allclose(got3, sum(g3) / world, atol=1e-6)
     mx = vd.max_over_ranks(rank + 10, "cpu")
     sm = vd.sum_over_ranks(rank + 1, "cpu")
     q.put((rank, bool(ok), mx, sm, vd.per_rank_batch(256, world)))

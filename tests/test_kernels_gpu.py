@@ -680,3 +680,46 @@ def test_dino_head_module_vs_oracle(ops):
     head2 = DINOHead(64, 1024, norm_last_layer=True, depth=1, dim_bottleneck=32).cuda()
     head2(x.detach()).sum().backward()
     assert head2.last.weight_g.grad is None and head2.last.weight_v.grad is not None
+
+
+# ----------------------------------------------------------------------------------------------- DINO vs the reference (a7, f1)
+def test_dino_head_module_vs_reference_golden(ops):
+    """models.dino.DINOHead (tcgen05 Linears + row kernels) against the reference's OWN DINOHead outputs / gradients
+    (tests/golden/dino_ops.pt, oracle/make_dino_golden.py): bf16 operand tolerances."""
+    from conftest import load_golden
+    from models.dino import DINOHead
+
+    for name, h in load_golden("dino_ops")["heads"].items():
+        head = DINOHead(**h["ctor"]).cuda()
+        head.load_state_dict(h["state_dict"])
+        x = h["x"].cuda().requires_grad_()
+        y = head(x)
+        assert y.shape == h["output"].shape and rel(y, h["output"].cuda()) < 1e-2, (name, rel(y, h["output"].cuda()))
+        (y * h["probe"].cuda()).sum().backward()
+        assert rel(x.grad, h["dx"].cuda()) < 3e-2, name
+        for k, p in head.named_parameters():
+            g = h["grads"][k]
+            if g is None:
+                assert p.grad is None, (name, k)
+            else:
+                assert rel(p.grad, g.cuda()) < 3e-2, (name, k, rel(p.grad, g.cuda()))
+
+
+def test_dino_loss_module_vs_reference_golden(ops):
+    """loss.DINOLoss (one fused kernel + centre EMA) against the reference's OWN DINOLoss: loss, student gradient and the
+    centre buffer after one and two calls."""
+    import loss as L
+    from conftest import load_golden
+
+    for name, c in load_golden("dino_ops")["losses"].items():
+        mod = L.DINOLoss(*c["ctor"]).cuda()
+        mod.center.copy_(c["center0"].cuda())
+        s = c["student"].cuda().requires_grad_()
+        out = mod(s, c["teacher"].cuda(), c["epoch"])
+        assert abs(out.item() - c["loss"].item()) < 2e-5 * abs(c["loss"].item()), (name, out.item(), c["loss"].item())
+        out.backward()
+        assert rel(s.grad, c["dstudent"].cuda()) < 2e-5, name
+        assert rel(mod.center, c["center1"].cuda()) < 1e-6, name
+        out2 = mod(c["student2"].cuda(), c["teacher2"].cuda(), c["epoch"])
+        assert abs(out2.item() - c["loss2"].item()) < 2e-5 * abs(c["loss2"].item()), name
+        assert rel(mod.center, c["center2"].cuda()) < 1e-6, name

@@ -98,3 +98,57 @@ def test_reference_bf16_autocast_error_level():
         assert 1e-3 < err < 2e-2, (name, err)  # above the fp32 target, below the GPU suite's bf16 bar
         assert err == pytest.approx(levels[name]["rel_l2"], rel=0.5), (name, err, levels[name])
     assert all(v["rel_l2"] > 1e-3 and v["share_within_rtol_1e-3"] <= 0.5 for v in levels.values())
+
+
+# ------------------------------------------------------------------------------------------------ DINO pins (a7, f1)
+def _dino_fx():
+    return load_golden("dino_ops")
+
+
+def test_oracle_dino_head_matches_reference_golden():
+    """R.dino_head (the checker of the DINOHead kernels) against outputs and autograd gradients of the reference's OWN
+    DINOHead (models/vit.py:206-262; tests/golden/dino_ops.pt written by oracle/make_dino_golden.py)."""
+    from oracle import restate as R
+
+    for name, h in _dino_fx()["heads"].items():
+        sd = {k: v.clone().requires_grad_(True) for k, v in h["state_dict"].items()}
+        x = h["x"].clone().requires_grad_(True)
+        out = R.dino_head(sd, x, pre="")
+        assert rel(out, h["output"]) < 2e-6, (name, rel(out, h["output"]))
+        (out * h["probe"]).sum().backward()
+        assert rel(x.grad, h["dx"]) < 2e-5, name
+        for k, g in h["grads"].items():
+            if g is None:   # frozen weight_g (norm_last_layer=True)
+                continue
+            assert rel(sd[k].grad, g) < 2e-5, (name, k, rel(sd[k].grad, g))
+
+
+def test_oracle_dino_loss_matches_reference_golden():
+    """R.dino_loss against the reference's OWN DINOLoss (loss.py:89-152): value, student gradient, and the centre after
+    one and two calls (update_center at world size 1), in the warm-up and the final temperature regime."""
+    from oracle import restate as R
+
+    for name, c in _dino_fx()["losses"].items():
+        K, n_crop = c["ctor"][0], c["ctor"][1]
+        s = c["student"].clone().requires_grad_(True)
+        loss = R.dino_loss(s, c["teacher"], c["center0"], n_crop, 0.1, c["temperature"])
+        assert abs(loss.item() - c["loss"].item()) < 2e-6 * abs(c["loss"].item()), name
+        loss.backward()
+        assert rel(s.grad, c["dstudent"]) < 2e-5, name
+        center1 = c["center0"] * 0.9 + c["teacher"].sum(0, keepdim=True) / c["teacher"].shape[0] * 0.1   # loss.py:144-152
+        assert rel(center1, c["center1"]) < 1e-6, name
+        loss2 = R.dino_loss(c["student2"], c["teacher2"], center1, n_crop, 0.1, c["temperature"])
+        assert abs(loss2.item() - c["loss2"].item()) < 2e-6 * abs(c["loss2"].item()), name
+
+
+def test_dino_golden_reproduces_from_reference():
+    """In the build container: the committed DINO fixture is what the live reference classes produce."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref = ref_loader.load()
+    for name, h in _dino_fx()["heads"].items():
+        head = ref.vit.DINOHead(**h["ctor"])
+        head.load_state_dict(h["state_dict"])
+        assert rel(head(h["x"]), h["output"]) < 1e-6, name

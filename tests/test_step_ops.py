@@ -399,6 +399,32 @@ def test_mix_loss_imagenet_shape_vs_oracle_and_grad_scaling():
 
 
 @pytest.mark.gpu
+def test_mix_loss_out_of_range_labels_and_nan_logits_are_contained():
+    """a label outside [0, n_class) (CrossEntropyLoss's ignore_index = -100) must not read out of bounds — its
+    row contributes nothing; a row whose target logit is NaN is a miss, not a top-1 hit."""
+    import loss as L
+    import train_util as T
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 50, generator=g).cuda()
+    t = torch.tensor([3, -100, 49, 50, 7, 0]).cuda()
+    xr = x.clone().requires_grad_()
+    out = L.cross_entropy(xr, t)
+    out.backward()
+    ok = torch.tensor([True, False, True, False, True, True]).cuda()
+    xw = x.clone().requires_grad_()
+    want = torch.nn.functional.cross_entropy(xw[ok], t[ok], reduction="sum") / 6   # the mean keeps the full row count
+    want.backward()
+    assert abs(out.item() - want.item()) < 2e-6 * want.item()
+    assert rel(xr.grad[ok], xw.grad[ok]) < 2e-6 and not xr.grad[~ok].any()
+    x2 = x.clone()
+    x2[0] = float("nan")
+    top1, top5 = T.accuracy(x2, torch.tensor([3, 1, 2, 3, 4, 5]).cuda(), (1, 5))
+    ref1, ref5 = T.accuracy(x[1:], torch.tensor([1, 2, 3, 4, 5]).cuda(), (1, 5))
+    assert top1.item() == pytest.approx(ref1.item() * 5 / 6) and top5.item() == pytest.approx(ref5.item() * 5 / 6)
+
+
+@pytest.mark.gpu
 def test_accumulate_matches_reference_loop_on_a_model():
     """train_util.accumulate on two ViT-Tiny drop-in models == the reference's per-parameter loop (train_util.py:76-77)."""
     import train_util as T

@@ -128,3 +128,38 @@ def test_dino_loss_module_matches_reference_schema():
         assert list(theirs.state_dict().keys()) == list(mine.state_dict().keys())
         assert theirs.teacher_temperature_schedule == mine.teacher_temperature_schedule
         assert list(inspect.signature(ref.DINOLoss.__init__).parameters) == want_args
+
+
+def test_cnn_zoo_names_resolve_lazily_to_the_reference():
+    """models/__init__.py:1-7 of the reference also exports NFNet / efficientnet / efficientnetv2 / nfefficientnetv2.  They
+    are outside the transformer hot path; the drop-in package resolves them lazily to the reference's own files (which do
+    `from models import layer` and therefore run against THIS package's layer module)."""
+    import models
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        with pytest.raises(ImportError):
+            models.NFNet  # noqa: B018
+        return
+    ref_loader._install_tensorfn_stub()
+    for name in ("NFNet", "efficientnet", "efficientnetv2", "nfefficientnetv2"):
+        assert name in models.__all__ and callable(getattr(models, name)), name
+    assert models.NFNet.__module__ == "models.nfnet" and models.efficientnetv2.__module__ == "models.efficientnet"
+    # the CNN files import DropPath / WSConv2d / ... from OUR models.layer: the helper classes come from the reference,
+    # DropPath is ours and must behave like the reference's as a stand-alone module (layer.py:166-183)
+    from models.layer import DropPath, ScaledActivation, StochasticDepth, WSConv2d  # noqa: F401
+
+    ref = ref_loader.load()
+    x = torch.randn(16, 3, 5)
+    for p, train in ((0.0, True), (0.4, False), (0.4, True)):
+        ours, theirs = DropPath(p).train(train), ref.layer.DropPath(p).train(train)
+        torch.manual_seed(11)
+        a = ours(x)
+        torch.manual_seed(11)
+        b = theirs(x)
+        assert torch.equal(a, b), (p, train)
+    # one CNN of the zoo runs end to end through the mixed package (tiny input, eval mode)
+    net = models.efficientnet(0.25, 0.25).eval()   # efficientnet.py:214
+    with torch.no_grad():
+        out = net(torch.randn(1, 3, 64, 64))
+    assert out.ndim == 2 and out.shape[0] == 1 and torch.isfinite(out).all()

@@ -254,7 +254,16 @@ mix_loss_kernel(const float* __restrict__ logits, long ld, const long* __restric
   __shared__ float red[ML_THREADS / 32];
   const int r = blockIdx.x;
   const float* x = logits + (long)r * ld;
-  const int t1 = (int)target1[r], t2 = target2 ? (int)target2[r] : t1;
+  const long t1l = target1[r], t2l = target2 ? target2[r] : t1l;
+  // A label outside [0, n_class) (e.g. nn.CrossEntropyLoss's ignore_index = -100, which MixLoss does not define) must
+  // not become an out-of-bounds read: such a row contributes no loss, a zero gradient and no hit.
+  if (t1l < 0 || t1l >= n_class || t2l < 0 || t2l >= n_class) {
+    if (dlogits)
+      for (int k = threadIdx.x; k < n_class; k += ML_THREADS) dlogits[(long)r * n_class + k] = 0.f;
+    if (row_loss && threadIdx.x == 0) row_loss[r] = 0.f;
+    return;
+  }
+  const int t1 = (int)t1l, t2 = (int)t2l;
   const float w = inter ? inter[r] : 1.f;
   const float xt = x[t1];
   // pass 1: row maximum, rank of the target1 logit
@@ -270,7 +279,7 @@ mix_loss_kernel(const float* __restrict__ logits, long ld, const long* __restric
   __syncthreads();
   mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   above = block_sum(above, red);
-  if (correct && threadIdx.x == 0) {
+  if (correct && threadIdx.x == 0 && xt == xt) {  // a NaN target logit (diverged run) is a miss, not rank 0
     if (above < 1.f) atomicAdd(correct, 1);
     if (above < (float)topk) atomicAdd(correct + 1, 1);
   }

@@ -35,7 +35,9 @@ class _MixLossFn(torch.autograd.Function):
 
 def cross_entropy(output, target):
     """nn.CrossEntropyLoss()(output, target) (train.py:155, the validation criterion) through the same row kernel:
-    MixLoss with eps = 0 and no mixing partner is the cross entropy against a one-hot target."""
+    MixLoss with eps = 0 and no mixing partner is the cross entropy against a one-hot target.
+    Labels must lie in [0, n_class): an out-of-range label (nn.CrossEntropyLoss's ignore_index = -100 is not supported;
+    no reference loader produces one) makes its row contribute nothing, and the mean still divides by the full batch."""
     logits = output if output.dtype == torch.float32 else output.float()
     if logits.stride(-1) != 1:
         logits = logits.contiguous()

@@ -37,6 +37,16 @@ class DropPath(nn.Module):
 
         return make_drop_path_scale(self.training, self.p, batch, like)
 
+    def forward(self, input):
+        """Stand-alone use (the CNN zoo calls `DropPath` as a module: efficientnet.py imports it from models.layer):
+        keep-mask per sample / keep probability, identity in eval mode or at p = 0 (layer.py:171-181).  The transformer
+        blocks never call this: there the mask rides in the residual GEMM epilogue (`scale`)."""
+        if not self.training or self.p == 0:
+            return input
+        keep = 1 - self.p
+        mask = input.new_empty([input.shape[0]] + [1] * (input.ndim - 1)).bernoulli_(keep)
+        return input / keep * mask
+
     def __repr__(self):
         return f"{self.__class__.__name__}(p={self.p})"
 
@@ -111,3 +121,18 @@ def make_classifier(dim, n_class, std=0.02):
     nn.init.normal_(linear.weight, std=std)
     nn.init.zeros_(linear.bias)
     return nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(1), linear)
+
+
+def __getattr__(name):
+    """CNN-only helpers of the reference's models/layer.py (ScaledActivation, WSConv2d, StochasticDepth, SqueezeExcite,
+    GlobalContext: used by nfnet.py / nfefficientnet.py, outside the transformer hot path) resolve lazily to the
+    reference's own definitions when its tree is importable (models/_compat.py: reference_file)."""
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from ._compat import load_reference_file
+
+    ref = load_reference_file("layer", as_name="models._reference_layer")
+    try:
+        return getattr(ref, name)
+    except AttributeError:
+        raise AttributeError(f"module 'models.layer' has no attribute {name!r}") from None

@@ -88,15 +88,45 @@ class FlatGradReducer:
         self.attached = True
         return self
 
+    def _views(self):
+        for flat, bucket in zip(self._flat, self.buckets):
+            off = 0
+            for p in bucket:
+                yield p, flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+
+    def reattach(self):
+        """Repair the .grad -> bucket link.  `p.grad = None` (train_util.cancel_last_layer_grad on the DINO `last` layer,
+        optimizer.zero_grad(set_to_none=True)) or a re-assigned .grad makes autograd accumulate OUTSIDE the bucket; the
+        all-reduce would then average a stale slice and the replicas would silently diverge.  Called by zero() and
+        reduce(): a detached gradient is copied into its slice (None = no gradient this step = zeros) and re-pointed.
+        Returns the number of parameters that had to be repaired."""
+        n = 0
+        for p, view in self._views():
+            g = p.grad
+            if g is not None and g.data_ptr() == view.data_ptr() and g.shape == view.shape:
+                continue
+            n += 1
+            with torch.no_grad():
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+            p.grad = view
+        return n
+
     def zero(self):
         for flat in self._flat:
             flat.zero_()
+        if self.attached:
+            self.reattach()
 
     def reduce(self):
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
         world = dist.get_world_size()
         if self.attached:
+            self.reattach()
             works = [dist.all_reduce(flat, async_op=True) for flat in self._flat]
             for work, flat in zip(works, self._flat):
                 work.wait()
