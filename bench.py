@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--nvtx-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="flat reducer without the per-bucket completion events: every all-reduce is issued after the step")
     ap.add_argument("--only", action="store_true",
                     help="one workload, one line: skip the default run's extra legs (no_graph, eager_baseline, swin_s)")
     args = ap.parse_args()
@@ -265,6 +267,8 @@ def run_default(args):
       eager_baseline  the kernel to beat: the oracle port in eager PyTorch (cuBLASLt / ATen) under bf16 autocast on the
                       same GPU, same step (rank 0 only, N = 1 semantics);
       swin_s          the second half of the metric (value / e2e / roofline / clocks of the Swin-S step);
+      dino_deit_s     BASELINE config 5 (DINO DeiT-S/16 multi-crop step: teacher forward, student forward / backward, fused
+                      DINO loss, EMA) captured as one CUDA graph; at N > 1 the centre all-reduce runs right behind the replay;
       speedup_vs_eager_gpu = value / eager_baseline.value per GPU (the honest speed-up; the CPU ratio is not)."""
     import copy
 
@@ -286,6 +290,15 @@ def run_default(args):
         a3 = copy.copy(args)
         a3.workload, a3.batch, a3.eager_baseline, a3.e2e_u8 = "swin_s", 0, True, False
         sw = run_one(a3)
+        _release()
+        a4 = copy.copy(args)
+        a4.workload, a4.batch, a4.eager_baseline, a4.e2e_u8, a4.dino_graph = "dino_deit_s", 0, False, False, True
+        a4.no_cpu_baseline = a4.no_optimizer_leg = True
+        a4.steps = min(args.steps, 10)
+        try:
+            dn = run_one(a4, light=True)
+        except Exception as exc:  # noqa: BLE001  (never lose the primary line over an extra leg)
+            dn = {"error": repr(exc)}
         if rank == 0:
             line["no_graph"] = {k: ng[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
             line["no_graph"]["host_issue_ms_per_step"] = ng["config"]["host_issue_ms_per_step"]
@@ -293,6 +306,9 @@ def run_default(args):
             line["no_graph"]["execution"] = "eager launches from Python (autograd.Function per branch), stock DDP at N > 1"
             line["swin_s"] = {k: sw.get(k) for k in ("value", "unit", "ms_per_step", "e2e", "roofline", "clocks", "gpu_launches",
                                                    "cpu_baseline", "eager_baseline", "with_optimizer", "config")}
+            line["dino_deit_s"] = dn if "error" in dn else dict(
+                {k: dn.get(k) for k in ("value", "unit", "ms_per_step", "e2e", "clocks", "gpu_launches", "config")},
+                crops_per_s=dn["value"] * 10, note="value counts SOURCE images (each = 2 x 224^2 + 8 x 96^2 crops)")
     if rank == 0:
         for d in (line, line.get("swin_s")):
             if d and d.get("eager_baseline"):  # per GPU: the eager leg runs on one GPU
@@ -346,7 +362,9 @@ def run_one(args, light=False):
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
                                                             gradient_as_bucket_view=True, bucket_cap_mb=64)
         else:
-            reducer = vd.FlatGradReducer(params).attach()  # .grad = views into the NCCL buckets
+            # .grad = views into the NCCL buckets; per-bucket "complete" events (external: visible outside the captured
+            # graph) let reduce() queue each all-reduce behind its bucket while the rest of the backward pass still runs
+            reducer = vd.FlatGradReducer(params, bucket_mb=128 if args.no_overlap else 32).attach(overlap=not args.no_overlap)
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
     if is_dino:
@@ -719,6 +737,10 @@ def run_one(args, light=False):
                 "data": "synthetic",
                 "config": {"workload": args.workload, "desc": wl["desc"], "batch_per_gpu": B, "global_batch": B * world,
                            "parallelism": f"dp{world}", "reducer": args.reducer if world > 1 else "none",
+                           "allreduce": ("none" if world == 1 else "stock DDP (overlapped)" if reducer is None else
+                                         "flat buckets, one all-reduce per bucket after the step" if args.no_overlap else
+                                         "flat 32 MiB buckets, all-reduce per bucket behind an external bucket-complete event "
+                                         "(overlaps the replaying backward pass)"),
                            "l2": "inputs_exceed_l2 (154 MB batch + multi-GB activations per step >> 126 MB L2)",
                            "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric",
                            "execution": "CUDA graph replay of the captured step" if use_graph else "eager launches",

@@ -45,6 +45,20 @@ def _worker(rank, world, port, q):
     got2 = torch.cat([p.grad.flatten() for p in model2.parameters()])
     ok = ok and torch.allclose(got2, want, atol=1e-6)
     ok = ok and all(p.grad.data_ptr() >= red2._flat[0].data_ptr() for p in red2.buckets[0])
+    # overlap mode (per-bucket completion hooks; on the CPU the events / side stream are absent, the bookkeeping is the same)
+    model4 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    model4.load_state_dict(model.state_dict())
+    red4 = vd.FlatGradReducer(model4.parameters(), bucket_mb=1)
+    red4.buckets = [[p] for p in red4.params]          # one bucket per parameter: exercises the completion order
+    red4._flat = [None] * len(red4.buckets)
+    red4.attach(overlap=True)
+    for _ in range(2):
+        red4.zero()
+        model4(x).sum().backward()
+        order = list(red4._order)
+        red4.reduce()
+    got4 = torch.cat([p.grad.flatten() for p in model4.parameters()])
+    ok = ok and torch.allclose(got4, want, atol=1e-6) and sorted(order) == list(range(6)) and order[0] >= 4
     # a detached .grad (train_util.cancel_last_layer_grad sets p.grad = None on the DINO `last` layer; so does
     # optimizer.zero_grad(set_to_none=True)) must not leave the replicas averaging a stale bucket slice
     import train_util as T

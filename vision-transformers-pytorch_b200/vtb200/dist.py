@@ -59,6 +59,9 @@ class FlatGradReducer:
     """Mean all-reduce of .grad over ranks through flat fp32 buckets of ~bucket_mb MiB."""
 
     def __init__(self, params, bucket_mb=128):
+        self._events = None       # overlap mode: one "bucket complete" event per bucket (see attach)
+        self._hooks = []
+        self.comm_stream = None
         self.params = [p for p in params if p.requires_grad]
         self.buckets = []
         cur, size, cap = [], 0, bucket_mb * (1 << 20) // 4
@@ -73,10 +76,17 @@ class FlatGradReducer:
         self._flat = [None] * len(self.buckets)
         self.attached = False
 
-    def attach(self):
+    def attach(self, overlap=False):
         """Make every parameter's .grad a VIEW into its flat bucket: backward then accumulates straight into the
         buffers NCCL reduces (no pack / unpack passes, no per-parameter kernels), `zero()` is one memset per bucket
-        and `reduce()` one all-reduce + one scale per bucket.  Call `zero()` instead of setting .grad = None."""
+        and `reduce()` one all-reduce + one scale per bucket.  Call `zero()` instead of setting .grad = None.
+
+        overlap=True (what stock DDP does, train.py:103-107, but compatible with a captured step): a post-accumulate hook
+        per parameter counts the bucket's gradients and records a "bucket complete" EVENT behind the last one.  The events
+        are `external` ones: captured into a CUDA graph they become event-record nodes that streams OUTSIDE the graph can
+        wait on, so `reduce()`, called right after `graph.replay()` was launched, queues each bucket's all-reduce on a side
+        stream behind its event and the collectives run while the rest of the backward pass is still replaying.  No NCCL call
+        is captured.  Every parameter must receive a gradient in every step (DDP's find_unused_parameters=False contract)."""
         for i, bucket in enumerate(self.buckets):
             n = sum(p.numel() for p in bucket)
             flat = torch.zeros(n, dtype=torch.float32, device=bucket[0].device)
@@ -86,7 +96,40 @@ class FlatGradReducer:
                 off += p.numel()
             self._flat[i] = flat
         self.attached = True
+        if overlap:
+            self._arm_overlap()
         return self
+
+    def _new_event(self):
+        return torch.cuda.Event(external=True)
+
+    def _arm_overlap(self):
+        cuda = self._flat[0].is_cuda
+        self._events = [self._new_event() if cuda else None for _ in self.buckets]
+        self._seen = [0] * len(self.buckets)
+        self._order = []          # bucket indices in the order they completed during the last backward
+        self.comm_stream = torch.cuda.Stream(device=self._flat[0].device) if cuda else None
+
+        def make(i, n):
+            def hook(_p):
+                self._seen[i] += 1
+                if self._seen[i] == n:
+                    self._seen[i] = 0
+                    if i in self._order:
+                        self._order.remove(i)
+                    self._order.append(i)
+                    if self._events[i] is not None:
+                        self._events[i].record()   # on the current (possibly capturing) stream
+            return hook
+
+        for i, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._hooks.append(p.register_post_accumulate_grad_hook(make(i, len(bucket))))
+
+    def detach_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks, self._events = [], None
 
     def _views(self):
         for flat, bucket in zip(self._flat, self.buckets):
@@ -125,6 +168,22 @@ class FlatGradReducer:
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
         world = dist.get_world_size()
+        if self.attached and self._events is not None:
+            # overlap mode: one all-reduce per bucket behind its "bucket complete" event, in completion order
+            order = self._order if len(self._order) == len(self.buckets) else list(reversed(range(len(self.buckets))))
+            if self.comm_stream is None:   # CPU / gloo: same logic, no streams
+                for i in order:
+                    dist.all_reduce(self._flat[i])
+                    self._flat[i].mul_(1.0 / world)
+                return
+            main = torch.cuda.current_stream(self._flat[0].device)
+            for i in order:
+                self.comm_stream.wait_event(self._events[i])
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(self._flat[i], async_op=True).wait()
+                    self._flat[i].mul_(1.0 / world)
+            main.wait_stream(self.comm_stream)   # the next step's zero() / the optimizer see reduced gradients
+            return
         if self.attached:
             self.reattach()
             works = [dist.all_reduce(flat, async_op=True) for flat in self._flat]
