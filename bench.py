@@ -364,7 +364,7 @@ def run_one(args, light=False):
         else:
             # .grad = views into the NCCL buckets; per-bucket "complete" events (external: visible outside the captured
             # graph) let reduce() queue each all-reduce behind its bucket while the rest of the backward pass still runs
-            reducer = vd.FlatGradReducer(params, bucket_mb=128 if args.no_overlap else 32).attach(overlap=not args.no_overlap)
+            reducer = vd.FlatGradReducer(params, bucket_mb=int(os.environ.get("VTB_BUCKET_MB", 128))).attach(overlap=not args.no_overlap)
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
     if is_dino:
@@ -739,7 +739,7 @@ def run_one(args, light=False):
                            "parallelism": f"dp{world}", "reducer": args.reducer if world > 1 else "none",
                            "allreduce": ("none" if world == 1 else "stock DDP (overlapped)" if reducer is None else
                                          "flat buckets, one all-reduce per bucket after the step" if args.no_overlap else
-                                         "flat 32 MiB buckets, all-reduce per bucket behind an external bucket-complete event "
+                                         "flat 128 MiB buckets, all-reduce per bucket behind an external bucket-complete event "
                                          "(overlaps the replaying backward pass)"),
                            "l2": "inputs_exceed_l2 (154 MB batch + multi-GB activations per step >> 126 MB L2)",
                            "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric",

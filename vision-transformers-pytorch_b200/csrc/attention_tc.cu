@@ -365,28 +365,41 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    // All 32 lanes run the loop (everything is warp-uniform: addresses and descriptors stay in uniform registers); one
+    // elected lane issues the tcgen05 instructions, straight-line (the issuing thread, not the tensor pipe, bounds a run of
+    // small MMAs: tools/probes/mma_probe.cu).
+    {
       const uint32_t idesc_s = umma_idesc_bf16(TQ, ns, 0, 0);   // S = Q K^T: both operands K-major
       const uint32_t idesc_o = umma_idesc_bf16(TQ, DH, 0, 1);   // O = P V: A = P from TMEM, B = V MN-major
+      const int nks = ns >> 4;
       // The two tiles are independent streams  S_t(i) -> softmax -> PV_t(i) -> epilogue -> S_t(i+1) ...; they are served in
       // the fixed order  PV_0(i), S_0(i+1), PV_1(i), S_1(i+1): tile 1 then trails tile 0 by at least (P V + epilogue + S), so
       // the exp-heavy second pass of one warp set overlaps the MUFU-free phases (waits, row max, epilogue) of the other.
       auto issue_s = [&](int t, int s) {
         const uint32_t qa = smem_u32(smem + s * F2_STAGE), ka = qa + 2 * 16384;
         const uint32_t koff = paired ? (uint32_t)t * 16384u : 0u;
+        const uint64_t dq = umma_desc_sw128(qa + t * 16384, 0, 1024), dk = umma_desc_sw128(ka + koff, 0, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(tmem_base + t * 256, umma_desc_sw128(qa + t * 16384 + kk * 32, 0, 1024),
-                    umma_desc_sw128(ka + koff + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
-        umma_commit(bar_s + t);
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16(tmem_base + t * 256, dq + 2 * kk, dk + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(bar_s + t);
+        }
+        __syncwarp();
       };
-      auto issue_pv = [&](int t, int s) {
+      auto issue_pv = [&](int t, int s, bool release) {
         const uint32_t va = smem_u32(smem + s * F2_STAGE) + 4 * 16384;
         const uint32_t koff = paired ? (uint32_t)t * 16384u : 0u;
-        for (int kk = 0; kk < ns / 16; ++kk)
-          umma_bf16_ts(tmem_base + t * 256 + O_COL, tmem_base + t * 256 + kk * 8,
-                       umma_desc_sw128(va + koff + kk * 2048, 0, 1024), idesc_o, kk > 0 ? 1u : 0u);
-        umma_commit(bar_o + t);
+        const uint64_t dv = umma_desc_sw128(va + koff, 0, 1024);
+        const uint32_t d = tmem_base + t * 256 + O_COL, a = tmem_base + t * 256;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)
+            if (kk < nks) umma_bf16_ts(d, a + kk * 8, dv + (uint64_t)(kk * 128), idesc_o, kk > 0 ? 1u : 0u);
+          umma_commit(bar_o + t);
+          if (release) umma_commit(bar_empty + s);
+        }
+        __syncwarp();
       };
       int it0 = 0, it1 = 0, k = 0;   // per-tile iteration counters (tile 1 is absent from some items), local item counter
       int item = blockIdx.x;
@@ -404,8 +417,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         const int ntile_next = has_next ? f2_ntile(nxt, ppb, paired, n_bh, nq) : 0;
         mbar_wait(bar_p, (uint32_t)(it0 & 1));
         tc_fence_after();
-        issue_pv(0, s);
-        if (ntile == 1) umma_commit(bar_empty + s);
+        issue_pv(0, s, ntile == 1);
         ++it0;
         if (has_next) {
           mbar_wait(bar_full + (s ^ 1), (uint32_t)(((k + 1) >> 1) & 1));
@@ -416,8 +428,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         if (ntile > 1) {
           mbar_wait(bar_p + 1, (uint32_t)(it1 & 1));
           tc_fence_after();
-          issue_pv(1, s);
-          umma_commit(bar_empty + s);
+          issue_pv(1, s, true);
           ++it1;
         }
         if (ntile_next > 1) {
@@ -979,8 +990,10 @@ __device__ unsigned int g_b2_trace[16 * 2 * 1024];
 #define B2_TRACE(ev) do { } while (0)
 #endif
 constexpr int B2_THREADS = 512;
-// registers (512 x 128 at launch): producer / issuer / delta warpgroup 96, drain warpgroup 80, the two math warpgroups 168
-constexpr int B2_REGS_AUX = 96, B2_REGS_DRAIN = 80, B2_REGS_MATH = 168;
+// registers (512 x 128 at launch): producer / issuer / delta warpgroup 88, drain warpgroup 104, the two math warpgroups 160
+// (measured: 272 -> 251 us on ViT-B against 96 / 80 / 168; summing the dqkv columns in the drain warps for the QKV bias
+// gradient was tried and cost 55 us per call against 36 us for the separate column-sum pass: not kept)
+constexpr int B2_REGS_AUX = 88, B2_REGS_DRAIN = 104, B2_REGS_MATH = 160;
 constexpr int B2_IN_SLOTS = 9;                  // input tile ring; then two dS^T buffers of two 64-query blocks each
 constexpr int B2_SLOT = 16384;
 constexpr uint32_t B2_DP_OFF = 64;   // dP^T columns of a chunk buffer sit this far behind its S^T columns
