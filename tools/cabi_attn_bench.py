@@ -59,8 +59,9 @@ def mask_bits(mask, n):
 class Problem:
     """Device buffers + parameter block of one attention call (q, k, v = column slices of a fused [T, 3 H dh] buffer)."""
 
-    def __init__(self, mode, B, H, dh, n, Hs=0, W=0, shift=False, seed=None, host=None):
+    def __init__(self, mode, B, H, dh, n, Hs=0, W=0, shift=False, seed=None, host=None, nkv=None):
         self.mode, self.B, self.H, self.dh, self.n, self.Hs, self.W, self.shift = mode, B, H, dh, n, Hs, W, shift
+        self.nkv = nkv   # None: keys = queries (fused qkv buffer); else a separate [B * nkv, 2 HD] key / value buffer (PVT SRA)
         HD = H * dh
         self.T = B * n if mode == L.ATTN_GLOBAL else B * Hs * Hs
         self.groups = B if mode == L.ATTN_GLOBAL else B * (Hs // W) ** 2
@@ -68,6 +69,8 @@ class Problem:
              (lambda shape, dt: cu.Buf(shape, dt).fill_from(seed[dt]))
         self.qkv, self.do = mk((self.T, 3 * HD), BF16), mk((self.T, HD), BF16)
         self.o, self.dqkv = cu.Buf((self.T, HD), BF16), cu.Buf((self.T, 3 * HD), BF16)
+        if nkv is not None:
+            self.kv, self.dkv = mk((B * nkv, 2 * HD), BF16), cu.Buf((B * nkv, 2 * HD), BF16)
         self.lse, self.delta = cu.Buf((self.groups, H, n), F32), cu.Buf((self.groups, H, n), F32)
         self.keep = []
         p = self.p = L.AttnParams()
@@ -98,6 +101,10 @@ class Problem:
         p.dk, p.lddk = self.dqkv.addr + HD * 2, ld
         p.dv, p.lddv = self.dqkv.addr + 2 * HD * 2, ld
         p.dkv_f32, p.delta = 0, self.delta.addr
+        if nkv is not None:
+            p.nkv = nkv
+            p.k, p.ldk, p.v, p.ldv = self.kv.addr, 2 * HD, self.kv.addr + HD * 2, 2 * HD
+            p.dk, p.lddk, p.dv, p.lddv = self.dkv.addr, 2 * HD, self.dkv.addr + HD * 2, 2 * HD
 
     def fwd(self):
         L.check(lib.vtb_attention_fwd(C.byref(self.p), None), lib)
@@ -106,8 +113,31 @@ class Problem:
         L.check(lib.vtb_attention_bwd(C.byref(self.p), None), lib)
 
     def free(self):
-        for b in [self.qkv, self.do, self.o, self.dqkv, self.lse, self.delta] + self.keep + ([self.dbias] if hasattr(self, "dbias") else []):
+        for b in [self.qkv, self.do, self.o, self.dqkv, self.lse, self.delta] + ([self.kv, self.dkv] if self.nkv is not None else []) + self.keep + ([self.dbias] if hasattr(self, "dbias") else []):
             b.free()
+
+
+def reference_sra(pr, qkv, kv, do):
+    """Separate key / value tokens (PVT spatial-reduction attention): returns o, dq, dkv."""
+    B, H, dh, n, m, HD = pr.B, pr.H, pr.dh, pr.n, pr.nkv, pr.H * pr.dh
+    qkv, kv, do = qkv.astype(np.float64), kv.astype(np.float64), do.astype(np.float64)
+    o, dq, dkv = np.zeros((B * n, HD)), np.zeros((B * n, HD)), np.zeros((B * m, 2 * HD))
+    scale = 1.0 / math.sqrt(dh)
+    for b in range(B):
+        rq, rk = slice(b * n, (b + 1) * n), slice(b * m, (b + 1) * m)
+        for h in range(H):
+            c = slice(h * dh, (h + 1) * dh)
+            q, k, v, g = qkv[rq, c], kv[rk, c], kv[rk, HD + h * dh: HD + (h + 1) * dh], do[rq, c]
+            S = q @ k.T * scale
+            P = np.exp(S - S.max(1, keepdims=True))
+            P /= P.sum(1, keepdims=True)
+            o[rq, c] = P @ v
+            dP = g @ v.T
+            dS = P * (dP - (dP * P).sum(1, keepdims=True))
+            dq[rq, c] = dS @ k * scale
+            dkv[rk, c] = dS.T @ q * scale
+            dkv[rk, HD + h * dh: HD + (h + 1) * dh] = P.T @ g
+    return o, dq, dkv
 
 
 def reference(pr, qkv, do):
@@ -155,6 +185,15 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+def mbar_debug(where):
+    """Debug builds (-DVTB_MBAR_DEBUG): report the first mbarrier wait that timed out."""
+    if hasattr(lib, "vtb_debug_mbar_timeout"):
+        out = (C.c_uint32 * 4)()
+        lib.vtb_debug_mbar_timeout(out)
+        if out[0]:
+            print(f"MBAR TIMEOUT after {where}: smem addr 0x{out[0]:x} parity {out[1]} block {out[2]} thread {out[3]}", flush=True)
+
+
 def self_check(mode, **kw):
     rng = np.random.default_rng(3)
     host = {}
@@ -168,10 +207,17 @@ def self_check(mode, **kw):
     pr.fwd()
     pr.bwd()
     cu.ck(cu.rt.cudaDeviceSynchronize(), "sync")
+    mbar_debug("self-check")
     HD = pr.H * pr.dh
-    o, dqkv, dbias = reference(pr, host[(pr.T, 3 * HD)], host[(pr.T, HD)])
-    e_o = rel(cu.from_bf16_bits(pr.o.download()), o)
-    e_g = rel(cu.from_bf16_bits(pr.dqkv.download()), dqkv)
+    if pr.nkv is not None:
+        o, dq, dkv = reference_sra(pr, host[(pr.T, 3 * HD)][:, :HD], host[(pr.B * pr.nkv, 2 * HD)], host[(pr.T, HD)])
+        e_o = rel(cu.from_bf16_bits(pr.o.download()), o)
+        e_g = max(rel(cu.from_bf16_bits(pr.dqkv.download())[:, :HD], dq), rel(cu.from_bf16_bits(pr.dkv.download()), dkv))
+        dbias = None
+    else:
+        o, dqkv, dbias = reference(pr, host[(pr.T, 3 * HD)], host[(pr.T, HD)])
+        e_o = rel(cu.from_bf16_bits(pr.o.download()), o)
+        e_g = rel(cu.from_bf16_bits(pr.dqkv.download()), dqkv)
     msg = f"self-check mode={mode} {kw}: o rel-L2 {e_o:.2e}, dqkv rel-L2 {e_g:.2e}"
     ok = e_o < 6e-3 and e_g < 1.5e-2  # the kernel-level tolerances of tests/test_kernels_gpu.py (bf16 P and outputs)
     if dbias is not None:
@@ -181,15 +227,6 @@ def self_check(mode, **kw):
     print(("PASS " if ok else "FAIL ") + msg, flush=True)
     pr.free()
     return ok
-
-
-def mbar_debug(where):
-    """Debug builds (-DVTB_MBAR_DEBUG): report the first mbarrier wait that timed out."""
-    if hasattr(lib, "vtb_debug_mbar_timeout"):
-        out = (C.c_uint32 * 4)()
-        lib.vtb_debug_mbar_timeout(out)
-        if out[0]:
-            print(f"MBAR TIMEOUT after {where}: smem addr 0x{out[0]:x} parity {out[1]} block {out[2]} thread {out[3]}", flush=True)
 
 
 def dump_trace(path):
@@ -240,7 +277,9 @@ if only_check in ("", "global"):
     ok &= self_check(L.ATTN_GLOBAL, B=3, H=1, dh=64, n=37)
     for kw in (dict(B=5, H=3, n=197), dict(B=5, H=1, n=37), dict(B=2, H=2, n=50), dict(B=1, H=2, n=256), dict(B=2, H=1, n=128),
                dict(B=1, H=3, n=129), dict(B=1, H=1, n=16), dict(B=2, H=2, n=145), dict(B=150, H=2, n=197), dict(B=100, H=6, n=37), dict(B=70, H=5, n=128),
-               dict(B=33, H=7, n=200)):
+               dict(B=33, H=7, n=200), dict(B=64, H=8, n=50), dict(B=40, H=8, n=64), dict(B=90, H=5, n=130),
+               dict(B=3, H=2, n=196, nkv=49), dict(B=64, H=5, n=196, nkv=49), dict(B=20, H=2, n=784, nkv=49), dict(B=70, H=3, n=100, nkv=200),
+               dict(B=9, H=1, n=3136, nkv=49)):
         ok &= self_check(L.ATTN_GLOBAL, dh=64, **kw)
 if only_check in ("", "window"):
     ok &= self_check(L.ATTN_WINDOW, B=1, H=2, dh=32, n=49, Hs=14, W=7, shift=True)

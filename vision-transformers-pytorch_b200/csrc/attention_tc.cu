@@ -1329,15 +1329,27 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         if (rel_k) ++n_kt_done;
       };
 
+      // Scores run up to two chunks ahead of the gradient products.  Running ahead must never BLOCK: the tiles a score
+      // product waits for may sit in ring slots whose previous occupants are released only by gradient products this warp
+      // has not issued yet (the last chunks of the previous problem).  So a chunk whose tiles have not landed is issued
+      // ahead only if a non-blocking probe says so; the blocking wait happens when there is nothing else left to issue.
+      auto scores_ready = [&](const B2Iter& c) {
+        if (c.part != 0) return true;
+        const int par = c.k & 1;
+        const uint32_t use = (uint32_t)((c.k >> 1) & 1);
+        if (c.kt == 0 && c.hq == 0) return mbar_try_wait(bars + BB_FULL + par * 3, use);
+        if (c.kt == 0 && c.hq == 1) return mbar_try_wait(bars + BB_FULL + par * 3 + 1, use);
+        if (c.kt == 1 && c.hq == 0) return mbar_try_wait(bars + BB_FULL + par * 3 + 2, use);
+        return true;
+      };
       B2Iter sc, gr;
       sc.init(blockIdx.x, gridDim.x, n_bh, nq, nkv, tpp, ns);
       gr = sc;
       uint32_t cs = 0, cg = 0;
-      for (int i = 0; i < 2 && sc.valid(); ++i) { issue_scores(sc, cs++); sc.advance(); }
       while (gr.valid()) {
+        while (cs - cg < 2 && sc.valid() && (cs == cg || scores_ready(sc))) { issue_scores(sc, cs++); sc.advance(); }
         issue_grads(gr, cg++);
         gr.advance();
-        if (sc.valid()) { issue_scores(sc, cs++); sc.advance(); }
       }
     }
   } else {
