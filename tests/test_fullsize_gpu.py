@@ -103,3 +103,31 @@ def test_full_size_models_match_oracle(family):
         if r > worst[1]:
             worst = (k, r)
     assert worst[1] < 6e-2, worst
+
+
+def test_vit_b16_full_size_gradients_match_oracle():
+    """Every parameter gradient of the full-size ViT-B/16 (85.8 M parameters, 12 layers, N = 197)
+    at B = 8 against fp32 autograd through the oracle restatement on the same device — the full-size gradient check the
+    round-1 suite did not have (it only had linearity in the upstream gradient)."""
+    from oracle import restate as R
+
+    torch.manual_seed(4)
+    model = R.randomize_(_vit_b(), 14).cuda().train()
+    x = torch.randn(8, 3, 224, 224, device="cuda")   # the image gets no gradient (neither trainer asks for one)
+    out = model(x)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    want = R.vit_forward(sd, x, patch=16, depth=12, heads=12, head_fn=lambda f: R.linear(f, sd["head.weight"], sd["head.bias"]))
+    assert rel(out, want) < 2e-2, rel(out, want)
+    probe = torch.randn_like(out)
+    (out * probe).sum().backward()
+    (want * probe).sum().backward()
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        g = sd[k].grad
+        if g.norm() < 1e-6 * max(1.0, g.numel() ** 0.5):
+            continue
+        r = rel(p.grad, g)
+        if r > worst[1]:
+            worst = (k, r)
+    assert worst[1] < 6e-2, worst
