@@ -994,65 +994,95 @@ constexpr int B2_THREADS = 512;
 // (measured: 272 -> 251 us on ViT-B against 96 / 80 / 168; summing the dqkv columns in the drain warps for the QKV bias
 // gradient was tried and cost 55 us per call against 36 us for the separate column-sum pass: not kept)
 constexpr int B2_REGS_AUX = 88, B2_REGS_DRAIN = 104, B2_REGS_MATH = 160;
-constexpr int B2_IN_SLOTS = 9;                  // input tile ring; then two dS^T buffers of two 64-query blocks each
 constexpr int B2_SLOT = 16384;
+constexpr int B2_KV_SLOTS = 4;                  // ring of key / value tiles   (slots 0-3)
+constexpr int B2_QO_SLOTS = 5;                  // ring of query / dO tiles    (slots 4-8)
+constexpr int B2_IN_SLOTS = B2_KV_SLOTS + B2_QO_SLOTS;   // then two dS^T buffers of two 64-query blocks each
 constexpr uint32_t B2_DP_OFF = 64;   // dP^T columns of a chunk buffer sit this far behind its S^T columns
 constexpr int B2_OFF_DS = B2_IN_SLOTS * B2_SLOT;
-constexpr int B2_OFF_DELTA = B2_OFF_DS + 4 * B2_SLOT;          // float [2][256]
-constexpr int B2_OFF_LSE = B2_OFF_DELTA + 2 * 256 * 4;         // float [2][256]
-constexpr int B2_OFF_BAR = B2_OFF_LSE + 2 * 256 * 4;           // 40 mbarriers
+constexpr int B2_OFF_DELTA = B2_OFF_DS + 4 * B2_SLOT;          // float [4][128]: delta of the last four query tiles
+constexpr int B2_OFF_LSE = B2_OFF_DELTA + 4 * 128 * 4;         // float [4][128]: lse * log2(e)
+constexpr int B2_OFF_BAR = B2_OFF_LSE + 4 * 128 * 4;           // 40 mbarriers
 constexpr int B2_OFF_TMEM = B2_OFF_BAR + 40 * 8;
 constexpr int SMEM_B2 = B2_OFF_TMEM + 16 + 1024;
 // barrier indices
-constexpr int BB_FULL = 0;      // [2 parities][3 groups]  G0 = K0 V0 Q0 dO0, G1 = Q1 dO1, G2 = K1 V1
-constexpr int BB_REL = 6;       // [2][8] tile released (index = load order of the tile inside its problem)
-constexpr int BB_S = 22;        // [2] chunk buffer: scores complete
-constexpr int BB_MATH = 24;     // [2] chunk buffer: P^T / dS^T written (4 warps)
-constexpr int BB_DSFREE = 26;   // [2] dS^T buffer: the dQ product that read it retired
-constexpr int BB_DKV = 28;      // dV, dK of a key tile complete
-constexpr int BB_DKVFREE = 29;  // ... read out of TMEM (4 drain warps)
-constexpr int BB_DQ = 30;       // dQ of a problem complete
-constexpr int BB_DQFREE = 31;   // ... read out of TMEM (4 drain warps)
-constexpr int BB_DFULL = 32;    // [2] delta / lse2 of the problem parity written (2 warps)
-constexpr int BB_DEMPTY = 34;   // [2] ... no longer needed (8 math warps)
+constexpr int BB_FULL = 0;      // [9] per input slot: the tile landed
+constexpr int BB_REL = 9;       // [9] per input slot: every MMA reading the tile retired
+constexpr int BB_S = 18;        // [2] chunk buffer: scores complete
+constexpr int BB_MATH = 20;     // [2] chunk buffer: P^T / dS^T written (4 warps)
+constexpr int BB_DSFREE = 22;   // [2] dS^T buffer: the dQ product that read it retired
+constexpr int BB_DKV = 24;      // dV, dK of a key tile complete
+constexpr int BB_DKVFREE = 25;  // ... read out of TMEM (4 drain warps)
+constexpr int BB_DQ = 26;       // [2] dQ accumulator (query tile & 1) complete
+constexpr int BB_DQFREE = 28;   // [2] ... read out of TMEM (4 drain warps)
+constexpr int BB_DFULL = 30;    // [4] delta / lse2 of a query tile written (2 warps)
+constexpr int BB_DEMPTY = 34;   // [4] ... no longer needed (8 math warps)
 
-// The chunk sequence of one CTA: problems bh = blockIdx.x, + gridDim.x, ...; per problem key tiles, query halves, two
-// chunks per half.  Every role walks the same sequence with its own iterator.  `base` is the ring slot of the problem's
-// first tile (tile with load order `ord` sits in slot (base + ord) mod ns).
+// A tile of one of the two input rings: slot index and how often the slot has been used before (mbarrier phase).
+struct B2Tile {
+  int slot;
+  uint32_t use;
+};
+
+// The chunk sequence of one CTA: problems bh = blockIdx.x, + gridDim.x, ...; per problem key tiles (<= 2), query tiles of
+// 128 (any number when there is one key tile, <= 2 otherwise), two chunks per query tile.  Every role walks the same
+// sequence with its own iterator.
+//   key / value tiles: ring of 4 slots, tile number gkv = 2 nkt k + 2 kt (+1 for V)
+//   query / dO tiles : ring of 5 slots, tile number gq = 2 nhq k + 2 hq (+1 for dO)
+// Both rings are FIFOs: tiles are loaded in that order and die in that order (K_kt / V_kt after key tile kt, Q_hq / dO_hq
+// after query tile hq of the LAST key tile).  The long-lived key tiles must not share a ring with the streaming query
+// tiles: a query tile waiting for a key tile's slot would wait for the end of the problem it belongs to.
 struct B2Iter {
-  int bh, k;            // problem, local problem counter
+  int bh, k;
   int kt, hq, part;
   int nkt, nhq, n_bh, stride;
-  int tpp, ns, base;
-  int len_a[2], len_b[2];
-  __device__ __forceinline__ void init(int first, int stride_, int n_bh_, int nq, int nkv, int tpp_, int ns_) {
+  int len_fa, len_fb, len_la, len_lb;   // chunk lengths of a full query tile (64 + 64) and of the last one
+  int q_slot;                           // ring position of Q_hq (dO_hq follows)
+  uint32_t q_use;
+  int q0_slot;                          // ... of Q_0 of this problem (key tile 1 walks the query tiles again)
+  uint32_t q0_use;
+  __device__ __forceinline__ void init(int first, int stride_, int n_bh_, int nq, int nkv) {
     bh = first; stride = stride_; n_bh = n_bh_; k = 0; kt = hq = part = 0;
     nkt = (nkv + 127) >> 7; nhq = (nq + 127) >> 7;
-    tpp = tpp_; ns = ns_; base = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int nqh = max(0, min(128, ((nq - h * 128) + 15) & ~15));
-      len_a[h] = min(nqh, ((nqh + 31) >> 5) << 4);   // 128 -> 64 + 64, 80 -> 48 + 32, 48 -> 32 + 16, 16 -> 16 + 0
-      len_b[h] = nqh - len_a[h];
-    }
+    const int last = ((nq - (nhq - 1) * 128) + 15) & ~15;
+    len_fa = 64; len_fb = 64;
+    len_la = min(last, ((last + 31) >> 5) << 4);   // 128 -> 64 + 64, 80 -> 48 + 32, 48 -> 32 + 16, 16 -> 16 + 0
+    len_lb = last - len_la;
+    q_slot = q0_slot = 0; q_use = q0_use = 0;
   }
   __device__ __forceinline__ bool valid() const { return bh < n_bh; }
-  __device__ __forceinline__ int len() const { return part ? (hq ? len_b[1] : len_b[0]) : (hq ? len_a[1] : len_a[0]); }
-  __device__ __forceinline__ int qo() const { return part ? (hq ? len_a[1] : len_a[0]) : 0; }   // first query of the chunk inside its half
-  __device__ __forceinline__ bool last_in_half() const { return part == 1 || (hq ? len_b[1] : len_b[0]) == 0; }
-  __device__ __forceinline__ bool last_in_kt() const { return last_in_half() && hq == nhq - 1; }
+  __device__ __forceinline__ bool last_tile() const { return hq == nhq - 1; }
+  __device__ __forceinline__ int len() const { return last_tile() ? (part ? len_lb : len_la) : (part ? len_fb : len_fa); }
+  __device__ __forceinline__ int qo() const { return part ? (last_tile() ? len_la : len_fa) : 0; }   // first query of the chunk inside its tile
+  __device__ __forceinline__ bool last_in_half() const { return part == 1 || (last_tile() ? len_lb : len_fb) == 0; }
+  __device__ __forceinline__ bool last_in_kt() const { return last_in_half() && last_tile(); }
   __device__ __forceinline__ bool last_in_problem() const { return last_in_kt() && kt == nkt - 1; }
   __device__ __forceinline__ bool first_in_kt() const { return hq == 0 && part == 0; }
-  __device__ __forceinline__ int slot(int ord) const { const int s = base + ord; return s >= ns ? s - ns : s; }
+  __device__ __forceinline__ bool dq_final() const { return last_in_half() && kt == nkt - 1; }   // dQ_hq complete, Q_hq / dO_hq dead
+  // sequence number of the query tile (delta / lse2 buffer = & 3, dQ accumulator = hq & 1)
+  __device__ __forceinline__ uint32_t qseq() const { return (uint32_t)(k * nhq + hq); }
+  __device__ __forceinline__ B2Tile tile_k() const {   // V_kt: slot + 1, same use count (pairs never straddle the ring of 4)
+    const uint32_t g = (uint32_t)(2 * (nkt * k + kt));
+    return B2Tile{(int)(g & 3), g >> 2};
+  }
+  __device__ __forceinline__ B2Tile tile_q() const { return B2Tile{B2_KV_SLOTS + q_slot, q_use}; }
+  __device__ __forceinline__ B2Tile tile_do() const {
+    const int s = q_slot + 1;
+    return s >= B2_QO_SLOTS ? B2Tile{B2_KV_SLOTS + s - B2_QO_SLOTS, q_use + 1} : B2Tile{B2_KV_SLOTS + s, q_use};
+  }
+  __device__ __forceinline__ void step_q() {
+    q_slot += 2;
+    if (q_slot >= B2_QO_SLOTS) { q_slot -= B2_QO_SLOTS; ++q_use; }
+  }
   __device__ __forceinline__ void advance() {
     if (!last_in_half()) { part = 1; return; }
     part = 0;
-    if (++hq < nhq) return;
+    if (++hq < nhq) { step_q(); return; }
     hq = 0;
-    if (++kt < nkt) return;
+    if (++kt < nkt) { q_slot = q0_slot; q_use = q0_use; return; }   // second key tile: the same query tiles again
     kt = 0; bh += stride; ++k;
-    base += tpp;
-    if (base >= ns) base -= ns;
+    step_q();
+    q0_slot = q_slot; q0_use = q_use;
   }
 };
 
@@ -1061,7 +1091,7 @@ struct B2Iter {
 // 128B-swizzled shared tile (dQ = dS K reads it MN-major).
 //   t_s: TMEM address of the S^T columns (dP^T sits B2_DP_OFF columns further), t_p: where the P^T pairs go
 //   l2a / dla: shared addresses of lse2 / delta of the step's first query;  ds_row: shared address of this row in
-//   block 0 of the dS^T buffer;  q: first query of the step inside its 128-query half
+//   block 0 of the dS^T buffer;  q: first query of the step inside its 128-query tile
 template <int W>
 __device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a, uint32_t dla, uint32_t ds_row, uint32_t q,
                                         uint32_t swz, float sl2, uint64_t* bar_dsfree, uint32_t dsfree_par, bool& ds_free) {
@@ -1106,12 +1136,12 @@ __device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a
                  "r"(dd[1]), "r"(dd[2]), "r"(dd[3]), "r"(dd[4]), "r"(dd[5]), "r"(dd[6]), "r"(dd[7])
                  : "memory");
   }
-  if (!ds_free) {   // the dQ product that read this dS^T buffer two halves ago has retired
+  if (!ds_free) {   // the dQ product that read this dS^T buffer two half-iterations ago has retired
     mbar_wait(bar_dsfree, dsfree_par);
     ds_free = true;
   }
 #pragma unroll
-  for (int g = 0; g < W / 8; ++g) {   // 8 queries = 16 B; query qq of the half sits in 64-query block qq / 64
+  for (int g = 0; g < W / 8; ++g) {   // 8 queries = 16 B; query qq of the tile sits in 64-query block qq / 64
     const uint32_t qq = q + g * 8;
     sts_u4(ds_row + (qq >> 6) * 16384u + ((((qq & 63u) >> 3) ^ swz) << 4), dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2],
            dd[g * 4 + 3]);
@@ -1153,22 +1183,17 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   B2_TRACE_DECL;
   const int nkt = (nkv + 127) >> 7, nhq = (nq + 127) >> 7;
-  // tile ring (see the producer): load order K0 V0 Q0 dO0 [Q1 dO1] [K1 V1]; the released-barrier index of a tile is its order
-  const int tpp = 4 + (nhq > 1 ? 2 : 0) + (nkt > 1 ? 2 : 0);   // tiles per problem
-  const int ord_k1 = 4 + (nhq > 1 ? 2 : 0);
-  const int ns = tpp == 4 ? 8 : B2_IN_SLOTS;                    // ring size (<= 2 tpp, see the producer)
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
-      for (int i = 0; i < 22; ++i) mbar_init(bars + i, 1);        // full, released
+      for (int i = 0; i < 18; ++i) mbar_init(bars + i, 1);        // full, released
       mbar_init(bars + BB_S, 1); mbar_init(bars + BB_S + 1, 1);
       mbar_init(bars + BB_MATH, 4); mbar_init(bars + BB_MATH + 1, 4);
       mbar_init(bars + BB_DSFREE, 1); mbar_init(bars + BB_DSFREE + 1, 1);
       mbar_init(bars + BB_DKV, 1); mbar_init(bars + BB_DKVFREE, 4);
-      mbar_init(bars + BB_DQ, 1); mbar_init(bars + BB_DQFREE, 4);
-      mbar_init(bars + BB_DFULL, 2); mbar_init(bars + BB_DFULL + 1, 2);
-      mbar_init(bars + BB_DEMPTY, 8); mbar_init(bars + BB_DEMPTY + 1, 8);
+      for (int i = 0; i < 2; ++i) { mbar_init(bars + BB_DQ + i, 1); mbar_init(bars + BB_DQFREE + i, 4); }
+      for (int i = 0; i < 4; ++i) { mbar_init(bars + BB_DFULL + i, 2); mbar_init(bars + BB_DEMPTY + i, 8); }
       mbar_fence_init();
     }
     __syncwarp();
@@ -1186,46 +1211,33 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_AUX));
   if (warp == 14) {
     // ------------------------------------------------------------------------------------------------ TMA producer
-    // The input slots form a RING: the tiles of all problems are numbered in load order (K0 V0 Q0 dO0 [Q1 dO1] [K1 V1] per
-    // problem), tile g lives in slot g % ns.  Tiles die in (nearly) the same order, so before loading tile g the producer
-    // waits for the "released" barrier of tile g - ns.  ns <= 2 tiles-per-problem keeps that barrier at most one phase ahead.
+    // Tiles in load order; before a slot is refilled its previous tile must have been released (one phase per use).
     if (lane == 0) {
-      int k = 0, base = 0;
-      for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
-        const int par = k & 1;
+      uint32_t gkv = 0;           // key / value tiles loaded so far (ring of 4)
+      int qs = 0;                 // query / dO ring position and use count (ring of 5)
+      uint32_t qu = 0;
+      auto load = [&](int slot, uint32_t use, const CUtensorMap* map, int c0, int tok, int b) {
+        if (use > 0) mbar_wait(bars + BB_REL + slot, (use - 1) & 1);
+        mbar_expect_tx(bars + BB_FULL + slot, B2_SLOT);
+        tma_load_3d(smem + slot * B2_SLOT, map, bars + BB_FULL + slot, c0, tok, b);
+      };
+      auto load_q = [&](const CUtensorMap* map, int c0, int tok, int b) {
+        load(B2_KV_SLOTS + qs, qu, map, c0, tok, b);
+        if (++qs == B2_QO_SLOTS) { qs = 0; ++qu; }
+      };
+      for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x) {
         const int b = bh / heads, c0 = (bh - b * heads) * DH;
-        uint64_t* f0 = bars + BB_FULL + par * 3;
-        // wait until the previous occupants of the slots of tiles [ord, ord + n) have been released.  This also orders
-        // the group's expect_tx behind the landing of the same group two problems back (same mbarrier): arriving on a
-        // barrier whose phase is still waiting for bytes would underflow its arrival count.
-        auto reserve = [&](int ord, int n) {
-          for (int i = 0; i < n; ++i) {
-            const int g = tpp * k + ord + i;
-            if (g >= ns) {
-              const int kp = (g - ns) / tpp, op = (g - ns) - kp * tpp;
-              mbar_wait(bars + BB_REL + (kp & 1) * 8 + op, (uint32_t)((kp >> 1) & 1));
-            }
-          }
-        };
-        auto load = [&](int ord, const CUtensorMap* map, int tok, uint64_t* bar) {
-          const int sl = base + ord;
-          tma_load_3d(smem + (sl >= ns ? sl - ns : sl) * B2_SLOT, map, bar, c0, tok, b);
-        };
-        reserve(0, 4);
-        mbar_expect_tx(f0, 4 * B2_SLOT);
-        load(0, &tk, 0, f0); load(1, &tv, 0, f0); load(2, &tq, 0, f0); load(3, &tdo, 0, f0);
-        if (nhq > 1) {
-          reserve(4, 2);
-          mbar_expect_tx(f0 + 1, 2 * B2_SLOT);
-          load(4, &tq, 128, f0 + 1); load(5, &tdo, 128, f0 + 1);
+        // the order the issuer first touches them: K0 V0, Q0 dO0, Q1 dO1, ..., then K1 V1
+        load((int)(gkv & 3), gkv >> 2, &tk, c0, 0, b); ++gkv;
+        load((int)(gkv & 3), gkv >> 2, &tv, c0, 0, b); ++gkv;
+        for (int hq = 0; hq < nhq; ++hq) {
+          load_q(&tq, c0, hq * 128, b);
+          load_q(&tdo, c0, hq * 128, b);
         }
         if (nkt > 1) {
-          reserve(ord_k1, 2);
-          mbar_expect_tx(f0 + 2, 2 * B2_SLOT);
-          load(ord_k1, &tk, 128, f0 + 2); load(ord_k1 + 1, &tv, 128, f0 + 2);
+          load((int)(gkv & 3), gkv >> 2, &tk, c0, 128, b); ++gkv;
+          load((int)(gkv & 3), gkv >> 2, &tv, c0, 128, b); ++gkv;
         }
-        base += tpp;
-        if (base >= ns) base -= ns;
       }
     }
   } else if (warp == 15) {
@@ -1235,26 +1247,39 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dV, dK: A = P^T / dS^T in TMEM, B MN-major
       const uint32_t idesc_q = umma_idesc_bf16(128, DH, 1, 1);   // dQ   : A MN-major (dS^T as dS), B MN-major
       const uint32_t sa = smem_u32(sdS), s0 = smem_u32(smem);
-      // tile order inside a problem: K_kt, V_kt, Q_hq, dO_hq
-      auto ord_k = [&](int kt) { return kt ? ord_k1 : 0; };
-      auto ord_q = [&](int hq) { return hq ? 4 : 2; };
-      auto tile_addr = [&](const B2Iter& c, int ord) { return s0 + (uint32_t)c.slot(ord) * B2_SLOT; };
       auto nk_tile = [&](int kt) { return min(128, ((nkv - kt * 128) + 15) & ~15); };
 
-      auto issue_scores = [&](const B2Iter& c, uint32_t cc) {
-        const int par = c.k & 1;
-        const uint32_t use = (uint32_t)((c.k >> 1) & 1);
-        if (c.part == 0) {   // first touch of a tile group by this problem
-          if (c.kt == 0 && c.hq == 0) mbar_wait(bars + BB_FULL + par * 3, use);
-          if (c.kt == 0 && c.hq == 1) mbar_wait(bars + BB_FULL + par * 3 + 1, use);
-          if (c.kt == 1 && c.hq == 0) mbar_wait(bars + BB_FULL + par * 3 + 2, use);
-          tc_fence_after();
-          B2_TRACE(16);
+      // tiles a chunk touches first: K_kt / V_kt at the first chunk of a key tile, Q_hq / dO_hq at the first chunk of a
+      // query tile in key tile 0
+      auto scores_ready = [&](const B2Iter& c) {
+        bool ok = true;
+        if (c.first_in_kt()) {
+          const B2Tile t = c.tile_k();
+          ok = mbar_try_wait(bars + BB_FULL + t.slot, t.use & 1) && mbar_try_wait(bars + BB_FULL + t.slot + 1, t.use & 1);
         }
+        if (ok && c.kt == 0 && c.part == 0) {
+          const B2Tile tq_ = c.tile_q(), to_ = c.tile_do();
+          ok = mbar_try_wait(bars + BB_FULL + tq_.slot, tq_.use & 1) && mbar_try_wait(bars + BB_FULL + to_.slot, to_.use & 1);
+        }
+        return ok;
+      };
+
+      auto issue_scores = [&](const B2Iter& c, uint32_t cc) {
+        const B2Tile tk_ = c.tile_k(), tq_ = c.tile_q(), to_ = c.tile_do();
+        if (c.first_in_kt()) {
+          mbar_wait(bars + BB_FULL + tk_.slot, tk_.use & 1);
+          mbar_wait(bars + BB_FULL + tk_.slot + 1, tk_.use & 1);
+        }
+        if (c.kt == 0 && c.part == 0) {
+          mbar_wait(bars + BB_FULL + tq_.slot, tq_.use & 1);
+          mbar_wait(bars + BB_FULL + to_.slot, to_.use & 1);
+        }
+        tc_fence_after();
+        B2_TRACE(16);
         const uint32_t buf = tmem_base + (cc & 1) * 128;
-        const uint32_t ka = tile_addr(c, ord_k(c.kt)), va = tile_addr(c, ord_k(c.kt) + 1);
-        const uint32_t qa = tile_addr(c, ord_q(c.hq)) + (uint32_t)c.qo() * 128u;
-        const uint32_t oa = tile_addr(c, ord_q(c.hq) + 1) + (uint32_t)c.qo() * 128u;
+        const uint32_t ka = s0 + (uint32_t)tk_.slot * B2_SLOT, va = ka + B2_SLOT;
+        const uint32_t qa = s0 + (uint32_t)tq_.slot * B2_SLOT + (uint32_t)c.qo() * 128u;
+        const uint32_t oa = s0 + (uint32_t)to_.slot * B2_SLOT + (uint32_t)c.qo() * 128u;
         const uint32_t idesc_s = umma_idesc_bf16(128, c.len(), 0, 0);
         const uint64_t dk = umma_desc_sw128(ka, 0, 1024), dq = umma_desc_sw128(qa, 0, 1024);
         const uint64_t dv = umma_desc_sw128(va, 0, 1024), dd = umma_desc_sw128(oa, 0, 1024);
@@ -1269,29 +1294,32 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         B2_TRACE(13);
       };
 
-      uint32_t n_kt_done = 0;   // key-tile iterations whose dV / dK are complete (drain counter)
-      uint32_t n_half = 0;      // half-iterations whose dQ product has been issued (dS^T buffer = n_half & 1)
+      uint32_t n_kt_done = 0;        // key-tile iterations whose dV / dK are complete (drain counter)
+      uint32_t n_half = 0;           // half-iterations whose dQ product has been issued (dS^T buffer = n_half & 1)
+      uint32_t n_dq[2] = {0, 0};     // completed uses of each dQ accumulator
       auto issue_grads = [&](const B2Iter& c, uint32_t cc) {
-        const int par = c.k & 1;
         const uint32_t buf = tmem_base + (cc & 1) * 128;
+        const B2Tile tk_ = c.tile_k(), tq_ = c.tile_q(), to_ = c.tile_do();
+        const int qb = c.hq & 1;
         B2_TRACE(10);
         mbar_wait(bars + BB_MATH + (cc & 1), (cc >> 1) & 1);
         B2_TRACE(11);
         if (c.first_in_kt() && n_kt_done > 0) { mbar_wait(bars + BB_DKVFREE, (n_kt_done - 1) & 1); B2_TRACE(14); }
         const bool dq_now = c.last_in_half();
-        if (dq_now && c.kt == 0 && c.hq == 0 && c.k > 0)   // the previous problem's dQ has been read out?
-          { mbar_wait(bars + BB_DQFREE, (uint32_t)((c.k - 1) & 1)); B2_TRACE(15); }
+        const uint32_t ndq = qb ? n_dq[1] : n_dq[0];
+        if (dq_now && c.kt == 0 && ndq > 0)   // the accumulator's previous query tile has been read out?
+          { mbar_wait(bars + BB_DQFREE + qb, (ndq - 1) & 1); B2_TRACE(15); }
         tc_fence_after();
-        const int st0 = c.qo() >> 4;   // first 16-query step of the chunk inside its half
+        const int st0 = c.qo() >> 4;   // first 16-query step of the chunk inside its tile
         const int nst = c.len() >> 4;
         // MN-major B tiles advance 2048 B (= 128 in descriptor units) per 16-row step
-        const uint64_t d_o = umma_desc_sw128(tile_addr(c, ord_q(c.hq) + 1), 0, 1024) + (uint64_t)(st0 * 128);
-        const uint64_t d_q = umma_desc_sw128(tile_addr(c, ord_q(c.hq)), 0, 1024) + (uint64_t)(st0 * 128);
+        const uint64_t d_o = umma_desc_sw128(s0 + (uint32_t)to_.slot * B2_SLOT, 0, 1024) + (uint64_t)(st0 * 128);
+        const uint64_t d_q = umma_desc_sw128(s0 + (uint32_t)tq_.slot * B2_SLOT, 0, 1024) + (uint64_t)(st0 * 128);
         const uint64_t d_sq = umma_desc_sw128(sa + (n_half & 1) * 2 * B2_SLOT, 16384, 1024);   // dS^T read MN-major: +2048 B per key step
-        const uint64_t d_k = umma_desc_sw128(tile_addr(c, ord_k(c.kt)), 0, 1024);
+        const uint64_t d_k = umma_desc_sw128(s0 + (uint32_t)tk_.slot * B2_SLOT, 0, 1024);
         const int nks = nk_tile(c.kt) >> 4;
         const uint32_t first = c.first_in_kt() ? 0u : 1u;
-        const bool rel_q = dq_now && c.kt == nkt - 1, rel_k = c.last_in_kt(), fin = c.last_in_problem();
+        const bool rel_q = c.dq_final(), rel_k = c.last_in_kt();
         if (elect_one()) {
           // straight-line issue (uniform predicates instead of loops): the issuing thread, not the tensor pipe, is what
           // bounds a run of small MMAs (tools/probes/mma_probe.cu: 36 - 53 cycles each at N = 64)
@@ -1308,42 +1336,34 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll
             for (int st = 0; st < 8; ++st)   // contraction over the keys of this tile
               if (st < nks)
-                umma_bf16(tmem_base + C_DQ + c.hq * 64, d_sq + (uint64_t)(st * 128), d_k + (uint64_t)(st * 128), idesc_q,
+                umma_bf16(tmem_base + C_DQ + qb * 64, d_sq + (uint64_t)(st * 128), d_k + (uint64_t)(st * 128), idesc_q,
                           st > 0 ? 1u : dq_acc);
             umma_commit(bars + BB_DSFREE + (n_half & 1));
-            if (rel_q) {   // last use of this half's Q / dO tiles
-              umma_commit(bars + BB_REL + par * 8 + ord_q(c.hq));
-              umma_commit(bars + BB_REL + par * 8 + ord_q(c.hq) + 1);
+            if (rel_q) {   // dQ of this query tile is final; last use of its Q / dO tiles
+              umma_commit(bars + BB_REL + tq_.slot);
+              umma_commit(bars + BB_REL + to_.slot);
+              umma_commit(bars + BB_DQ + qb);
             }
           }
           if (rel_k) {
-            umma_commit(bars + BB_REL + par * 8 + ord_k(c.kt));
-            umma_commit(bars + BB_REL + par * 8 + ord_k(c.kt) + 1);
+            umma_commit(bars + BB_REL + tk_.slot);
+            umma_commit(bars + BB_REL + tk_.slot + 1);
             umma_commit(bars + BB_DKV);
           }
-          if (fin) umma_commit(bars + BB_DQ);
         }
         __syncwarp();
         B2_TRACE(12);
         if (dq_now) ++n_half;
+        if (rel_q) { if (qb) ++n_dq[1]; else ++n_dq[0]; }
         if (rel_k) ++n_kt_done;
       };
 
       // Scores run up to two chunks ahead of the gradient products.  Running ahead must never BLOCK: the tiles a score
       // product waits for may sit in ring slots whose previous occupants are released only by gradient products this warp
-      // has not issued yet (the last chunks of the previous problem).  So a chunk whose tiles have not landed is issued
-      // ahead only if a non-blocking probe says so; the blocking wait happens when there is nothing else left to issue.
-      auto scores_ready = [&](const B2Iter& c) {
-        if (c.part != 0) return true;
-        const int par = c.k & 1;
-        const uint32_t use = (uint32_t)((c.k >> 1) & 1);
-        if (c.kt == 0 && c.hq == 0) return mbar_try_wait(bars + BB_FULL + par * 3, use);
-        if (c.kt == 0 && c.hq == 1) return mbar_try_wait(bars + BB_FULL + par * 3 + 1, use);
-        if (c.kt == 1 && c.hq == 0) return mbar_try_wait(bars + BB_FULL + par * 3 + 2, use);
-        return true;
-      };
+      // has not issued yet.  So a chunk whose tiles have not landed is issued ahead only if a non-blocking probe says so;
+      // the blocking wait happens when there is nothing else left to issue.
       B2Iter sc, gr;
-      sc.init(blockIdx.x, gridDim.x, n_bh, nq, nkv, tpp, ns);
+      sc.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
       gr = sc;
       uint32_t cs = 0, cg = 0;
       while (gr.valid()) {
@@ -1354,59 +1374,82 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------------------------------------ delta / lse2
+    // delta_i = sum_d dO[i,d] O[i,d] and lse_i log2(e) per QUERY TILE, straight from global memory, up to three tiles
+    // ahead of the math warps (4 buffers)
     const int t2 = threadIdx.x - 12 * 32;   // 0..63
-    int k = 0;
-    for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
-      const int par = k & 1;
-      mbar_wait(bars + BB_DEMPTY + par, (uint32_t)(((k >> 1) & 1) ^ 1));
+    uint32_t seq = 0;
+    for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x) {
       const int b = bh / heads, h = bh - b * heads;
-      for (int i = t2; i < 256; i += 64) {
-        float acc = 0.f, l2 = INFINITY;
-        if (i < nq) {
-          const uint4* o4 = reinterpret_cast<const uint4*>(Og + ((long)b * nq + i) * ldo + h * DH);
-          const uint4* g4 = reinterpret_cast<const uint4*>(dOg + ((long)b * nq + i) * lddo + h * DH);
+      for (int hq = 0; hq < nhq; ++hq, ++seq) {
+        const int buf = (int)(seq & 3);
+        mbar_wait(bars + BB_DEMPTY + buf, ((seq >> 2) & 1) ^ 1);
+        for (int r = t2; r < 128; r += 64) {
+          const int i = hq * 128 + r;
+          float acc = 0.f, l2 = INFINITY;
+          if (i < nq) {
+            const uint4* o4 = reinterpret_cast<const uint4*>(Og + ((long)b * nq + i) * ldo + h * DH);
+            const uint4* g4 = reinterpret_cast<const uint4*>(dOg + ((long)b * nq + i) * lddo + h * DH);
 #pragma unroll
-          for (int jj = 0; jj < 8; jj += 4) {
-            uint4 ro[4], rg[4];
+            for (int jj = 0; jj < 8; jj += 4) {
+              uint4 ro[4], rg[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ro[j] = __ldg(o4 + jj + j); rg[j] = __ldg(g4 + jj + j); }
+              for (int j = 0; j < 4; ++j) { ro[j] = __ldg(o4 + jj + j); rg[j] = __ldg(g4 + jj + j); }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t wo[4] = {ro[j].x, ro[j].y, ro[j].z, ro[j].w}, wg[4] = {rg[j].x, rg[j].y, rg[j].z, rg[j].w};
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t wo[4] = {ro[j].x, ro[j].y, ro[j].z, ro[j].w}, wg[4] = {rg[j].x, rg[j].y, rg[j].z, rg[j].w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fo = unpack_bf16(wo[e]), fg = unpack_bf16(wg[e]);
-                acc = fmaf(fo.x, fg.x, acc);
-                acc = fmaf(fo.y, fg.y, acc);
+                for (int e = 0; e < 4; ++e) {
+                  const float2 fo = unpack_bf16(wo[e]), fg = unpack_bf16(wg[e]);
+                  acc = fmaf(fo.x, fg.x, acc);
+                  acc = fmaf(fo.y, fg.y, acc);
+                }
               }
             }
+            l2 = lse[(long)bh * nq + i] * 1.4426950408889634f;
           }
-          l2 = lse[(long)bh * nq + i] * 1.4426950408889634f;
+          sts_f32(smem_u32(sDelta) + (uint32_t)(buf * 128 + r) * 4u, acc);   // padding queries: delta 0, lse2 +inf -> P = 0, dS = 0
+          sts_f32(smem_u32(sLse2) + (uint32_t)(buf * 128 + r) * 4u, l2);
         }
-        sts_f32(smem_u32(sDelta) + (uint32_t)(par * 256 + i) * 4u, acc);   // padding queries: delta 0, lse2 +inf -> P = 0, dS = 0
-        sts_f32(smem_u32(sLse2) + (uint32_t)(par * 256 + i) * 4u, l2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BB_DFULL + buf);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + BB_DFULL + par);
     }
   }
   } else if (warp < 4) {
     // ------------------------------------------------------------------------------------------------ drain warps
-    // dV / dK of every key tile and dQ of every problem: TMEM -> bf16 -> global, one accumulator row (128 B) per thread.
-    // Dedicated warps: the accumulators are handed back to the issuer a few hundred cycles after they complete, and the
-    // math sets never stall on the tensor pipe.
+    // dV / dK of every key tile and dQ of every query tile: TMEM -> bf16 -> global, one accumulator row (128 B) per thread,
+    // in the order the issuer commits them.  Dedicated warps: the accumulators are handed back to the issuer a few hundred
+    // cycles after they complete, and the math sets never stall on the tensor pipe.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_DRAIN));
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t n_kt = 0;
-    int k = 0;
-    for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x, ++k) {
-      const int b = bh / heads, h = bh - b * heads;
-      for (int kt = 0; kt < nkt; ++kt, ++n_kt) {
-        mbar_wait(bars + BB_DKV, n_kt & 1);
+    uint32_t n_kt = 0, n_dq0 = 0, n_dq1 = 0;
+    B2Iter c;
+    c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
+    for (; c.valid(); c.advance()) {
+      const int b = c.bh / heads, h = c.bh - b * heads;
+      if (c.dq_final()) {
+        const int qb = c.hq & 1;
+        const uint32_t n = qb ? n_dq1 : n_dq0;
+        mbar_wait(bars + BB_DQ + qb, n & 1);
         tc_fence_after();
-        const int j = kt * 128 + row;
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(t_row + C_DQ + qb * 64, a0);
+        tmem_ld_32x32(t_row + C_DQ + qb * 64 + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BB_DQFREE + qb);
+        if (qb) ++n_dq1; else ++n_dq0;
+        const int i = c.hq * 128 + row;
+        if (i < nq) b2_store_row(a0, a1, scale, dQ + ((long)b * nq + i) * lddq + h * DH);
+      }
+      if (c.last_in_kt()) {
+        mbar_wait(bars + BB_DKV, n_kt & 1);
+        ++n_kt;
+        tc_fence_after();
+        const int j = c.kt * 128 + row;
         uint32_t a0[32], a1[32];
         tmem_ld_32x32(t_row + C_DV, a0);
         tmem_ld_32x32(t_row + C_DV + 32, a1);
@@ -1420,21 +1463,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         if (lane == 0) mbar_arrive(bars + BB_DKVFREE);
         if (j < nkv) b2_store_row(a0, a1, scale, dK + ((long)b * nkv + j) * lddk + h * DH);
       }
-      mbar_wait(bars + BB_DQ, (uint32_t)(k & 1));
-      tc_fence_after();
-      for (int hq = 0; hq < nhq; ++hq) {
-        const int i = hq * 128 + row;
-        uint32_t a0[32], a1[32];
-        tmem_ld_32x32(t_row + C_DQ + hq * 64, a0);
-        tmem_ld_32x32(t_row + C_DQ + hq * 64 + 32, a1);
-        tmem_ld_wait();
-        if (hq == nhq - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bars + BB_DQFREE);
-        }
-        if (i < nq) b2_store_row(a0, a1, scale, dQ + ((long)b * nq + i) * lddq + h * DH);
-      }
     }
   } else {
     // ------------------------------------------------------------------------------------------------ math sets
@@ -1447,16 +1475,13 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     const float sl2 = scale * 1.4426950408889634f;
 
     B2Iter c;
-    c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv, tpp, ns);
+    c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
     uint32_t cc = 0, n_half = 0;
-    int delta_k = -1;   // problem whose delta / lse2 this warp has acquired
     for (; c.valid(); c.advance(), ++cc) {
+      const uint32_t seq = c.qseq();
+      const int dbuf = (int)(seq & 3);
       if ((int)(cc & 1) == set) {
-        const int par = c.k & 1;
-        if (delta_k != c.k) {
-          mbar_wait(bars + BB_DFULL + par, (uint32_t)((c.k >> 1) & 1));
-          delta_k = c.k;
-        }
+        mbar_wait(bars + BB_DFULL + dbuf, (seq >> 2) & 1);   // delta / lse2 of this query tile (re-waiting a done phase is free)
         B2_TRACE(20);
         mbar_wait(bars + BB_S + set, (cc >> 1) & 1);
         tc_fence_after();
@@ -1464,8 +1489,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         const int nk16 = min(128, ((nkv - c.kt * 128) + 15) & ~15);
         if (quarter * 32 < nk16) {   // warps whose 32 key rows are all padding only keep the barriers moving
           const int len = c.len(), qo = c.qo();
-          const uint32_t l2a = smem_u32(sLse2) + (uint32_t)(par * 256 + c.hq * 128 + qo) * 4u;
-          const uint32_t dla = smem_u32(sDelta) + (uint32_t)(par * 256 + c.hq * 128 + qo) * 4u;
+          const uint32_t l2a = smem_u32(sLse2) + (uint32_t)(dbuf * 128 + qo) * 4u;
+          const uint32_t dla = smem_u32(sDelta) + (uint32_t)(dbuf * 128 + qo) * 4u;
           const uint32_t ds_row = smem_u32(sdS) + (n_half & 1) * 2 * B2_SLOT + (uint32_t)row * 128u;
           // dS^T buffer n_half & 1 was last read by the dQ product of half-iteration n_half - 2
           bool ds_free = (n_half < 2);
@@ -1488,9 +1513,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         B2_TRACE(22);
       }
       if (c.last_in_half()) ++n_half;
-      if (c.last_in_problem()) {
+      if (c.dq_final()) {   // last use of this query tile's delta / lse2 (by either set)
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + BB_DEMPTY + (c.k & 1));   // this warp is done with the problem's delta / lse2
+        if (lane == 0) mbar_arrive(bars + BB_DEMPTY + dbuf);
       }
     }
   }
@@ -1506,7 +1531,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 }  // namespace
 
 bool vtb_attn_tc_bwd_ok(const vtb_attn_params* p) {
-  return g_attn_tc && p->mode == VTB_ATTN_GLOBAL && p->dh == DH && p->nkv <= 256 && p->nq <= 256 &&
+  return g_attn_tc && p->mode == VTB_ATTN_GLOBAL && p->dh == DH && p->nkv <= 256 &&
+         (p->nq <= 256 || (p->nkv <= 128 && g_attn_tc_bwd_version != 1)) &&
          !p->rel_bias && !p->mask && !p->dkv_f32 && p->lddq % 8 == 0 && p->lddk % 8 == 0 && p->lddv % 8 == 0 &&
          p->ldo % 8 == 0 && p->lddo % 8 == 0 &&
          ((((uintptr_t)p->dq) | ((uintptr_t)p->dk) | ((uintptr_t)p->dv) | ((uintptr_t)p->o) | ((uintptr_t)p->dout)) & 15) == 0;
