@@ -279,6 +279,10 @@ def run_default(args):
         args.eager_baseline = True
     line = run_one(args)
     rank = int(os.environ.get("RANK", 0))
+    if args.nvtx_step:   # profiling run: one step between cudaProfilerStart / Stop, no line
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
     if extras:
         _release()
         a2 = copy.copy(args)
@@ -528,6 +532,9 @@ def run_one(args, light=False):
                 "hbm": {"achieved": achieved_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": achieved_gbs / peak_hbm,
                         "algorithmic_bytes_per_launch": (gemm_bytes / len(gemm)) if gemm else None},
                 "traffic": traffic,
+                "traffic_source": "committed ncu capture of this command (not measured in this run)" if tpath else None,
+                "achieved_source": "CUDA events around every GEMM launch of ONE instrumented eager step of this run (the "
+                                   "graph-timed region replays the same launches)",
                 "traffic_unit": "bytes per GEMM launch (ncu dram__bytes_read+write, "
                                 + (("profiles/" + os.path.basename(tpath)) if tpath else "no capture committed") + ")",
                 "flop_per_launch": (gemm_flops / len(gemm)) if gemm else None, "peak_source": peak_src,
@@ -543,7 +550,9 @@ def run_one(args, light=False):
             ppaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_attn_tensor_pipe.json")))
             if ppaths:
                 pipe = json.load(open(ppaths[-1])).get(args.workload)
-            roofline["attention"] = {"tensor_pipe_pct_ncu": pipe}
+            roofline["attention"] = {"tensor_pipe_pct_ncu": pipe,
+                                     "tensor_pipe_source": ("capture profiles/" + os.path.basename(ppaths[-1]) + " (ncu, not measured in "
+                                                            "this run; the ms / GB/s / TFLOP/s below ARE measured in this run)") if ppaths else None}
             for k, rows in att.items():
                 t = sum(r[1] for r in rows)
                 if rows and t > 0:
