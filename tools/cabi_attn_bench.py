@@ -247,8 +247,10 @@ def dump_trace(path):
 def bench(tag, mode, seed, **kw):
     pr = Problem(mode, seed=seed, **kw)
     timer = cu.Timer()
+    dump_trace("/dev/null")
     pr.fwd()
     cu.ck(cu.rt.cudaDeviceSynchronize(), "sync after fwd")
+    dump_trace(os.path.join(ROOT, "gpurun_out", "attn_trace_fwd_" + tag.split()[1] + "_" + str(kw.get("n")) + ".txt"))
     mbar_debug(tag + " fwd")
     dump_trace("/dev/null")
     pr.bwd()

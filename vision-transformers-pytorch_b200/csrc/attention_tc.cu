@@ -236,6 +236,24 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 }
 
 
+#ifdef VTB_ATTN_TRACE
+// timeline of block 0 (debug builds): per warp a private list of {event id, clock} pairs (plain stores, no atomics: the
+// probe must not stall the warp), fetched with vtb_debug_attn_trace
+__device__ unsigned int g_b2_trace[16 * 2 * 1024];
+#define B2_TRACE_DECL unsigned int trace_i__ = 0
+#define B2_TRACE(ev)                                                                              \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_i__ < 1024) {                         \
+      unsigned int* p__ = g_b2_trace + ((threadIdx.x >> 5) * 1024 + trace_i__) * 2;              \
+      p__[0] = (ev); p__[1] = (unsigned int)clock64();                                            \
+      ++trace_i__;                                                                                \
+    }                                                                                             \
+  } while (0)
+#else
+#define B2_TRACE_DECL do { } while (0)
+#define B2_TRACE(ev) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // Forward, version 2: PERSISTENT, one CTA per SM, two query tiles in flight, loads prefetched one work item ahead.
 //
@@ -252,7 +270,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int F2_THREADS = 320;
 constexpr int F2_STAGE = 6 * 16384;
-constexpr int SMEM_F2 = 2 * F2_STAGE + 1024 + 256;
+constexpr int F2_OSTAGE = 8 * 4096;   // per softmax warp: 32 output rows x 128 B, transposed before they are written out
+constexpr int SMEM_F2 = 2 * F2_STAGE + F2_OSTAGE + 1024 + 256;
 
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
@@ -308,7 +327,8 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
                     int heads, int nq, int nkv, int n_bh, int n_items, int ppb, int paired, float scale) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * F2_STAGE);
+  uint8_t* sO = smem + 2 * F2_STAGE;   // [8 warps][32 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * F2_STAGE + F2_OSTAGE);
   uint64_t* bar_full = bars;        // [2] TMA -> issuer: the stage's Q / K / V landed
   uint64_t* bar_empty = bars + 2;   // [2] issuer -> TMA: every MMA reading the stage retired
   uint64_t* bar_s = bars + 4;       // [2] per tile: S complete
@@ -318,6 +338,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  B2_TRACE_DECL;
   const int ns = (nkv + 15) & ~15;  // UMMA N of the score tile / contraction length of P V
 
   // warp roles: 0-3 softmax + epilogue of tile 0, 4-7 of tile 1, 8 TMA producer, 9 UMMA issuer (the arbiter prefers the
@@ -386,6 +407,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           umma_commit(bar_s + t);
         }
         __syncwarp();
+        B2_TRACE(30 + t);
       };
       auto issue_pv = [&](int t, int s, bool release) {
         const uint32_t va = smem_u32(smem + s * F2_STAGE) + 4 * 16384;
@@ -400,6 +422,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           if (release) umma_commit(bar_empty + s);
         }
         __syncwarp();
+        B2_TRACE(32 + t);
       };
       int it0 = 0, it1 = 0, k = 0;   // per-tile iteration counters (tile 1 is absent from some items), local item counter
       int item = blockIdx.x;
@@ -415,19 +438,24 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         const int nxt = item + gridDim.x;
         const bool has_next = nxt < n_items;
         const int ntile_next = has_next ? f2_ntile(nxt, ppb, paired, n_bh, nq) : 0;
+        B2_TRACE(34);
         mbar_wait(bar_p, (uint32_t)(it0 & 1));
         tc_fence_after();
+        B2_TRACE(35);
         issue_pv(0, s, ntile == 1);
         ++it0;
         if (has_next) {
           mbar_wait(bar_full + (s ^ 1), (uint32_t)(((k + 1) >> 1) & 1));
+          B2_TRACE(36);
           mbar_wait(bar_free, (uint32_t)((it0 & 1) ^ 1));
           tc_fence_after();
+          B2_TRACE(37);
           issue_s(0, s ^ 1);
         }
         if (ntile > 1) {
           mbar_wait(bar_p + 1, (uint32_t)(it1 & 1));
           tc_fence_after();
+          B2_TRACE(38);
           issue_pv(1, s, true);
           ++it1;
         }
@@ -454,8 +482,10 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       const int bh = f2_bh(item, t, ppb, paired), q0 = f2_q0(item, t, ppb, paired);
       const int rows_valid = min(128, nq - q0);
       const bool active = quarter * 32 < rows_valid;  // warps whose 32 rows are all padding only keep the barriers moving
+      B2_TRACE(40);
       mbar_wait(bar_s + t, (uint32_t)(it & 1));
       tc_fence_after();
+      B2_TRACE(41);
       float mx = -INFINITY, sum = 0.f;
       if (active) {
         // Both passes keep one TMEM load in flight: chunk c + 1 is requested before chunk c is processed.
@@ -483,6 +513,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
           mx = f2_rowmax<16, true>(h16, nkv - nfull, mx);
         }
         const float mb = mx * sl2;
+        B2_TRACE(42);
         // pass 2: p = exp2(s * sl2 - mb); P (bf16 pairs) overwrites the S columns this thread has already consumed
         // (chunk c's P lands in columns [16 c, 16 c + 16), below every column still to be read)
         if (n32 > 0) tmem_ld_32x32(t_row, a);
@@ -511,10 +542,12 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p + t);
+      B2_TRACE(43);
       if (active) {
         // epilogue: O / l -> bf16 -> global; lse = max * scale + ln(sum)
         mbar_wait(bar_o + t, (uint32_t)(it & 1));
         tc_fence_after();
+        B2_TRACE(44);
         uint32_t a0[32], a1[32];
         tmem_ld_32x32(t_row + O_COL, a0);
         tmem_ld_32x32(t_row + O_COL + 32, a1);
@@ -522,27 +555,43 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + t);   // O is in registers: the tile's TMEM columns are free
-        if (row < rows_valid) {
-          const int i = q0 + row;
-          const int b = bh / heads, h = bh - b * heads;
+        // O / l -> bf16.  A thread owns one 128-byte output row, but rows are 2 * ldo bytes apart in global memory: written
+        // straight from the registers every store instruction would touch 32 different lines with 16 bytes each.  The warp
+        // transposes through its private 4 KB of shared memory instead (16-byte chunks XOR-swizzled by the row: no bank
+        // conflicts either way), so that 8 lanes write one full line and an instruction covers 4 whole rows.
+        {
           const float inv = 1.f / sum;
-          bf16* dst = O + ((long)b * nq + i) * ldo + h * DH;
+          const uint32_t so = smem_u32(sO) + (uint32_t)warp * 4096u;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(
-                pack_bf16(__uint_as_float(a0[j]) * inv, __uint_as_float(a0[j + 1]) * inv),
-                pack_bf16(__uint_as_float(a0[j + 2]) * inv, __uint_as_float(a0[j + 3]) * inv),
-                pack_bf16(__uint_as_float(a0[j + 4]) * inv, __uint_as_float(a0[j + 5]) * inv),
-                pack_bf16(__uint_as_float(a0[j + 6]) * inv, __uint_as_float(a0[j + 7]) * inv));
+          for (int c = 0; c < 4; ++c) {
+            sts_u4(so + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4),
+                   pack_bf16(__uint_as_float(a0[8 * c]) * inv, __uint_as_float(a0[8 * c + 1]) * inv),
+                   pack_bf16(__uint_as_float(a0[8 * c + 2]) * inv, __uint_as_float(a0[8 * c + 3]) * inv),
+                   pack_bf16(__uint_as_float(a0[8 * c + 4]) * inv, __uint_as_float(a0[8 * c + 5]) * inv),
+                   pack_bf16(__uint_as_float(a0[8 * c + 6]) * inv, __uint_as_float(a0[8 * c + 7]) * inv));
+            sts_u4(so + (uint32_t)lane * 128u + (uint32_t)(((c + 4) ^ (lane & 7)) << 4),
+                   pack_bf16(__uint_as_float(a1[8 * c]) * inv, __uint_as_float(a1[8 * c + 1]) * inv),
+                   pack_bf16(__uint_as_float(a1[8 * c + 2]) * inv, __uint_as_float(a1[8 * c + 3]) * inv),
+                   pack_bf16(__uint_as_float(a1[8 * c + 4]) * inv, __uint_as_float(a1[8 * c + 5]) * inv),
+                   pack_bf16(__uint_as_float(a1[8 * c + 6]) * inv, __uint_as_float(a1[8 * c + 7]) * inv));
+          }
+          __syncwarp();
+          const int b = bh / heads, h = bh - b * heads;
+          const int sub = lane >> 3, ch = lane & 7;   // row inside a group of four, 16-byte chunk of the row
+          bf16* base = O + ((long)b * nq + q0 + quarter * 32) * ldo + h * DH + ch * 8;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(dst + 32 + j) = make_uint4(
-                pack_bf16(__uint_as_float(a1[j]) * inv, __uint_as_float(a1[j + 1]) * inv),
-                pack_bf16(__uint_as_float(a1[j + 2]) * inv, __uint_as_float(a1[j + 3]) * inv),
-                pack_bf16(__uint_as_float(a1[j + 4]) * inv, __uint_as_float(a1[j + 5]) * inv),
-                pack_bf16(__uint_as_float(a1[j + 6]) * inv, __uint_as_float(a1[j + 7]) * inv));
-          if (lse) lse[(long)bh * nq + i] = mx * scale + __logf(sum);
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int r = r4 * 4 + sub;
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(so + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)));
+            if (quarter * 32 + r < rows_valid) *reinterpret_cast<uint4*>(base + (long)r * ldo) = v;
+          }
+          __syncwarp();   // the staging rows are rewritten by the next item
+          if (row < rows_valid && lse) lse[(long)bh * nq + q0 + row] = mx * scale + __logf(sum);
         }
+        B2_TRACE(45);
       } else {
         tc_fence_before();
         __syncwarp();
@@ -972,23 +1021,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 // =====================================================================================================================
 namespace {
 
-#ifdef VTB_ATTN_TRACE
-// timeline of block 0 (debug builds): per warp a private list of {event id, clock} pairs (plain stores, no atomics: the
-// probe must not stall the warp), fetched with vtb_debug_attn_trace
-__device__ unsigned int g_b2_trace[16 * 2 * 1024];
-#define B2_TRACE_DECL unsigned int trace_i__ = 0
-#define B2_TRACE(ev)                                                                              \
-  do {                                                                                            \
-    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_i__ < 1024) {                         \
-      unsigned int* p__ = g_b2_trace + ((threadIdx.x >> 5) * 1024 + trace_i__) * 2;              \
-      p__[0] = (ev); p__[1] = (unsigned int)clock64();                                            \
-      ++trace_i__;                                                                                \
-    }                                                                                             \
-  } while (0)
-#else
-#define B2_TRACE_DECL do { } while (0)
-#define B2_TRACE(ev) do { } while (0)
-#endif
 constexpr int B2_THREADS = 512;
 // registers (512 x 128 at launch): producer / issuer / delta warpgroup 88, drain warpgroup 104, the two math warpgroups 160
 // (measured: 272 -> 251 us on ViT-B against 96 / 80 / 168; summing the dqkv columns in the drain warps for the QKV bias
@@ -1004,7 +1036,8 @@ constexpr int B2_OFF_DELTA = B2_OFF_DS + 4 * B2_SLOT;          // float [4][128]
 constexpr int B2_OFF_LSE = B2_OFF_DELTA + 4 * 128 * 4;         // float [4][128]: lse * log2(e)
 constexpr int B2_OFF_BAR = B2_OFF_LSE + 4 * 128 * 4;           // 40 mbarriers
 constexpr int B2_OFF_TMEM = B2_OFF_BAR + 40 * 8;
-constexpr int SMEM_B2 = B2_OFF_TMEM + 16 + 1024;
+constexpr int B2_OFF_OST = B2_OFF_TMEM + 64;                     // [4 drain warps][32 rows][64 B] output transposition
+constexpr int SMEM_B2 = B2_OFF_OST + 4 * 2048 + 1024;
 // barrier indices
 constexpr int BB_FULL = 0;      // [9] per input slot: the tile landed
 constexpr int BB_REL = 9;       // [9] per input slot: every MMA reading the tile retired
@@ -1148,22 +1181,36 @@ __device__ __forceinline__ void b2_step(uint32_t t_s, uint32_t t_p, uint32_t l2a
   }
 }
 
-// 64 fp32 accumulator columns of this thread's TMEM lane -> 64 bf16 (x f) -> one 128-byte row of global memory
-__device__ __forceinline__ void b2_store_row(const uint32_t (&a0)[32], const uint32_t (&a1)[32], float f, bf16* dst) {
+// 32 accumulator rows of a warp (one TMEM lane = one row per thread, 64 fp32 columns in a0 | a1) -> bf16 (x f) -> 32 rows
+// of 128 bytes in global memory, `ld` elements apart, rows >= n_valid skipped.  Written straight from the registers every
+// store instruction would touch 32 different lines with 16 bytes each; the warp transposes through 2 KB of shared memory
+// (one 64-byte half row at a time, chunks XOR-swizzled by the row: no bank conflicts either way) so that 4 lanes write a
+// contiguous 64 bytes and an instruction covers 8 rows.
+__device__ __forceinline__ void b2_store_rows(const uint32_t (&a0)[32], const uint32_t (&a1)[32], float f, bf16* row0, long ld,
+                                              int n_valid, uint32_t so, int lane) {
+  const int sub = lane >> 2, ch = lane & 3;
 #pragma unroll
-  for (int e = 0; e < 32; e += 8)
-    *reinterpret_cast<uint4*>(dst + e) = make_uint4(
-        pack_bf16(__uint_as_float(a0[e]) * f, __uint_as_float(a0[e + 1]) * f),
-        pack_bf16(__uint_as_float(a0[e + 2]) * f, __uint_as_float(a0[e + 3]) * f),
-        pack_bf16(__uint_as_float(a0[e + 4]) * f, __uint_as_float(a0[e + 5]) * f),
-        pack_bf16(__uint_as_float(a0[e + 6]) * f, __uint_as_float(a0[e + 7]) * f));
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t* a = half ? a1 : a0;
 #pragma unroll
-  for (int e = 0; e < 32; e += 8)
-    *reinterpret_cast<uint4*>(dst + 32 + e) = make_uint4(
-        pack_bf16(__uint_as_float(a1[e]) * f, __uint_as_float(a1[e + 1]) * f),
-        pack_bf16(__uint_as_float(a1[e + 2]) * f, __uint_as_float(a1[e + 3]) * f),
-        pack_bf16(__uint_as_float(a1[e + 4]) * f, __uint_as_float(a1[e + 5]) * f),
-        pack_bf16(__uint_as_float(a1[e + 6]) * f, __uint_as_float(a1[e + 7]) * f));
+    for (int c = 0; c < 4; ++c)
+      sts_u4(so + (uint32_t)lane * 64u + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4),
+             pack_bf16(__uint_as_float(a[8 * c]) * f, __uint_as_float(a[8 * c + 1]) * f),
+             pack_bf16(__uint_as_float(a[8 * c + 2]) * f, __uint_as_float(a[8 * c + 3]) * f),
+             pack_bf16(__uint_as_float(a[8 * c + 4]) * f, __uint_as_float(a[8 * c + 5]) * f),
+             pack_bf16(__uint_as_float(a[8 * c + 6]) * f, __uint_as_float(a[8 * c + 7]) * f));
+    __syncwarp();
+#pragma unroll
+    for (int r8 = 0; r8 < 4; ++r8) {
+      const int r = r8 * 8 + sub;
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(so + (uint32_t)r * 64u + (uint32_t)((ch ^ ((r >> 1) & 3)) << 4)));
+      if (r < n_valid) *reinterpret_cast<uint4*>(row0 + (long)r * ld + half * 32 + ch * 8) = v;
+    }
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
@@ -1422,8 +1469,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     // cycles after they complete, and the math sets never stall on the tensor pipe.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_REGS_DRAIN));
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t so = smem_u32(smem + B2_OFF_OST) + (uint32_t)warp * 2048u;
     uint32_t n_kt = 0, n_dq0 = 0, n_dq1 = 0;
     B2Iter c;
     c.init(blockIdx.x, gridDim.x, n_bh, nq, nkv);
@@ -1442,26 +1489,26 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BB_DQFREE + qb);
         if (qb) ++n_dq1; else ++n_dq0;
-        const int i = c.hq * 128 + row;
-        if (i < nq) b2_store_row(a0, a1, scale, dQ + ((long)b * nq + i) * lddq + h * DH);
+        const int i0 = c.hq * 128 + quarter * 32;   // first query row of this warp
+        b2_store_rows(a0, a1, scale, dQ + ((long)b * nq + i0) * lddq + h * DH, lddq, nq - i0, so, lane);
       }
       if (c.last_in_kt()) {
         mbar_wait(bars + BB_DKV, n_kt & 1);
         ++n_kt;
         tc_fence_after();
-        const int j = c.kt * 128 + row;
+        const int j0 = c.kt * 128 + quarter * 32;   // first key row of this warp
         uint32_t a0[32], a1[32];
         tmem_ld_32x32(t_row + C_DV, a0);
         tmem_ld_32x32(t_row + C_DV + 32, a1);
         tmem_ld_wait();
-        if (j < nkv) b2_store_row(a0, a1, 1.f, dV + ((long)b * nkv + j) * lddv + h * DH);
+        b2_store_rows(a0, a1, 1.f, dV + ((long)b * nkv + j0) * lddv + h * DH, lddv, nkv - j0, so, lane);
         tmem_ld_32x32(t_row + C_DK, a0);
         tmem_ld_32x32(t_row + C_DK + 32, a1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + BB_DKVFREE);
-        if (j < nkv) b2_store_row(a0, a1, scale, dK + ((long)b * nkv + j) * lddk + h * DH);
+        b2_store_rows(a0, a1, scale, dK + ((long)b * nkv + j0) * lddk + h * DH, lddk, nkv - j0, so, lane);
       }
     }
   } else {
