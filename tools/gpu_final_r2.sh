@@ -10,8 +10,8 @@ TMO=900 run t_all env VTB_TEST_INPUT_V2=1 python -m pytest tests/ -q -m gpu --no
 run smoke python -c "import __graft_entry__ as g; g.smoke()"
 TAILN=1 run bench_default_n1 python bench.py
 TAILN=1 run bench_reference_arm python bench.py --impl reference --steps 3 --warmup 1
-TAILN=1 run bench_pvt_small_n1 python bench.py --only --workload pvt_small --steps 10
-TAILN=1 run bench_halo_t_n1 python bench.py --only --workload halo_t --steps 10
+TAILN=1 run bench_pvt_small_n1 python bench.py --only --workload pvt_small --steps 60
+TAILN=1 run bench_halo_t_n1 python bench.py --only --workload halo_t --steps 40
 for wl in vit_b16 swin_s pvt_small; do
   timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
      --log-file gpurun_out/launches_${wl}.csv python bench.py --only --workload $wl --warmup 3 --nvtx-step > gpurun_out/ncu_${wl}.log 2>&1
