@@ -184,9 +184,21 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, const uint32_
 
 // Staged epilogue of one warp's share (CW columns) of a sub-tile row: TMEM registers -> fused math ->
 // swizzled smem staging (chunks cb..cb+3 of the 128-byte row).  ob/ab point at this thread's row.
+// Explicit shared-space accesses for the staging slabs: `ob` / `ab` are carved out of the dynamic shared block after an
+// integer round-up, which makes them GENERIC pointers to the compiler — their loads / stores were LD.E / ST.E through the
+// L1TEX path (long-scoreboard latency) instead of LDS / STS.
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int CW>
 __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&acc)[CW], float bias_lane, float rs,
-                                           uint8_t* ob, uint8_t* ab, uint32_t cb, uint32_t swz, bool dual,
+                                           uint32_t ob, uint32_t ab, uint32_t cb, uint32_t swz, bool dual,
                                            bool f32out) {
   float v[CW];
   if (e.alpha != 1.f) {
@@ -212,15 +224,15 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
         ph[t] = pack_bf16(silu_f(ur.x), silu_f(ur.y));
       }
       const uint32_t off = ((cb + j / 8) ^ swz) << 4;
-      *reinterpret_cast<uint4*>(ob + off) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
-      *reinterpret_cast<uint4*>(ab + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      sts_u4(ob + off, pu[0], pu[1], pu[2], pu[3]);
+      sts_u4(ab + off, ph[0], ph[1], ph[2], ph[3]);
     }
     return;
   }
   if (e.epilogue == VTB_EPI_SILU_GRAD) {
 #pragma unroll
     for (int j = 0; j < CW; j += 8) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(ab + (((cb + j / 8) ^ swz) << 4));
+      const uint4 raw = lds_u4(ab + (((cb + j / 8) ^ swz) << 4));
       const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -238,19 +250,18 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
     if (e.resid) {  // f32 residual sub-tile prefetched by TMA
 #pragma unroll
       for (int j = 0; j < CW; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(ab + (((cb + j / 4) ^ swz) << 4));
+        const float4 t = lds_f4(ab + (((cb + j / 4) ^ swz) << 4));
         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
       }
     }
 #pragma unroll
     for (int j = 0; j < CW; j += 4)
-      *reinterpret_cast<float4*>(ob + (((cb + j / 4) ^ swz) << 4)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      sts_f4(ob + (((cb + j / 4) ^ swz) << 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
   } else {
 #pragma unroll
     for (int j = 0; j < CW; j += 8)
-      *reinterpret_cast<uint4*>(ob + (((cb + j / 8) ^ swz) << 4)) =
-          make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                     pack_bf16(v[j + 6], v[j + 7]));
+      sts_u4(ob + (((cb + j / 8) ^ swz) << 4), pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+             pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
   }
 }
 
@@ -523,10 +534,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[rd_stage], rd_phase);
         if (mine) {
-          const uint8_t* a = sA + rd_stage * A_STAGE_BYTES + off;
+          const uint32_t a = smem_u32(sA) + (uint32_t)(rd_stage * A_STAGE_BYTES) + off;
 #pragma unroll
           for (int r4 = 0; r4 < 4; ++r4) {
-            const uint4 v = *reinterpret_cast<const uint4*>(a + r4 * (16 * 128));
+            const uint4 v = lds_u4(a + r4 * (16 * 128));
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -540,13 +551,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (++rd_stage == C::STAGES) { rd_stage = 0; rd_phase ^= 1; }
       }
       if (mine) {  // 16 row groups -> one value per column of the tile (scratch behind the mbarriers) -> global
-        float* s_col = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);
-        if (t < BM) s_col[t] = 0.f;
+        const uint32_t s_col = smem_u32(bars) + 1024u;   // float [BM]
+        if (t < BM) sts_f32(s_col + t * 4, 0.f);
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&s_col[box * 64 + cc * 8 + j], acc[j]);
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_col + (uint32_t)(box * 64 + cc * 8 + j) * 4u), "f"(acc[j]) : "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (t < BM && m_blk * BM + t < epi.M) atomicAdd(epi.a_colsum + m_blk * BM + t, s_col[t]);
+        if (t < BM && m_blk * BM + t < epi.M) {
+          float sv;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(s_col + t * 4));
+          atomicAdd(epi.a_colsum + m_blk * BM + t, sv);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     };
@@ -625,8 +641,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int n0 = n_blk * BN + sidx * SUBC;
             const bool live = n0 < epi.N;            // CTA-uniform
             const bool last = (sidx == NSUB - 1);
-            uint8_t* ob = sOut + qb * EPI_BUF_BYTES + row * 128;
-            uint8_t* ab = sAux + (q % N_AUX) * EPI_BUF_BYTES + row * 128;
+            const uint32_t ob = smem_u32(sOut) + (uint32_t)(qb * EPI_BUF_BYTES + row * 128);
+            const uint32_t ab = smem_u32(sAux) + (uint32_t)((q % N_AUX) * EPI_BUF_BYTES + row * 128);
             const float b_nxt = last ? 0.f : bias_at(sidx + 1);
             TRACE_T(0);
             TRACE_T(1);
