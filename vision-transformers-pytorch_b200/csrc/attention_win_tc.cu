@@ -123,6 +123,11 @@ struct WtWatchdog {
     if ((++spins & 4095u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 };
+__device__ __forceinline__ unsigned long long wt_lds_u64(uint32_t saddr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
   return (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
 }
@@ -334,7 +339,9 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
     const int r = quarter * 32 + lane, w = r >> 6, i = r & 63;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sl2 = p.scale * WT_L2E;
-    const uint8_t* brow = sBias + i * 256;
+    // explicit shared-space addresses: pointers carved out of the dynamic block are generic to the compiler and their
+    // loads would go through the L1TEX path (LD.E) instead of LDS
+    const uint32_t brow = smem_u32(sBias) + (uint32_t)i * 256u;
     const int sx = i & 7;
     bf16* O = reinterpret_cast<bf16*>(p.o);
     for (int n = grpi; n < my_tiles; n += 2) {
@@ -343,7 +350,7 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       const int tok = wt_row_token(g, wt_origin(g, tile * 2 + w), i);
       mbar_wait(&full[stage], (n / F_STAGES) & 1);
       const unsigned long long mb =
-          (p.mask_bits && tok >= 0) ? reinterpret_cast<const unsigned long long*>(sSide + stage * F_SIDE_BYTES)[r] : 0ull;
+          (p.mask_bits && tok >= 0) ? wt_lds_u64(smem_u32(sSide) + (uint32_t)(stage * F_SIDE_BYTES + r * 8)) : 0ull;
       mbar_wait(&s_full[b], (n >> 2) & 1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
@@ -354,7 +361,7 @@ attn_wt_fwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        const float4 bb = *reinterpret_cast<const float4*>(brow + ((c ^ sx) << 4));
+        const float4 bb = lds_f4(brow + (uint32_t)((c ^ sx) << 4));
         const uint32_t* src = (c < 8) ? &s0[c * 4] : &s1[(c - 8) * 4];
         x[c * 4 + 0] = fmaf(__uint_as_float(src[0]), sl2, bb.x);
         x[c * 4 + 1] = fmaf(__uint_as_float(src[1]), sl2, bb.y);
@@ -628,7 +635,7 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
     const int r = quarter * 32 + lane, w = r >> 6, j = r & 63;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sl2 = p.scale * WT_L2E;
-    const uint8_t* brow = sBias + j * 256;
+    const uint32_t brow = smem_u32(sBias) + (uint32_t)j * 256u;   // shared-space addresses (see the forward kernel)
     const int sx = j & 7;
     bf16* dQ = reinterpret_cast<bf16*>(p.dq);
     bf16* dK = reinterpret_cast<bf16*>(p.dk);
@@ -657,12 +664,12 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
     for (int n = 0; n < my_tiles; ++n) {
       const int stage = n % 3, b = n & 1;
       mbar_wait(&full[stage], (n / 3) & 1);
-      const uint8_t* side = sSide + stage * B_SIDE_BYTES;
-      const int tok_r = reinterpret_cast<const int*>(side)[r];
-      const int tok_q = reinterpret_cast<const int*>(side)[half * 64 + j];  // dQ row (query j of window `half`)
-      const float* lrow = reinterpret_cast<const float*>(side + 512) + w * 64 + half * 32;
-      const float* drow = reinterpret_cast<const float*>(side + 1024) + w * 64 + half * 32;
-      const unsigned long long mb64 = reinterpret_cast<const unsigned long long*>(side + 1536)[r];
+      const uint32_t side = smem_u32(sSide) + (uint32_t)(stage * B_SIDE_BYTES);
+      const int tok_r = (int)lds_u32(side + r * 4);
+      const int tok_q = (int)lds_u32(side + (half * 64 + j) * 4);  // dQ row (query j of window `half`)
+      const uint32_t lrow = side + 512 + (uint32_t)(w * 64 + half * 32) * 4u;
+      const uint32_t drow = side + 1024 + (uint32_t)(w * 64 + half * 32) * 4u;
+      const unsigned long long mb64 = wt_lds_u64(side + 1536 + r * 8);
       const uint32_t mb = half ? (uint32_t)(mb64 >> 32) : (uint32_t)mb64;
       mbar_wait(&s_full[b], (n >> 1) & 1);
       tc_fence_after();
@@ -676,9 +683,9 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
       uint32_t pp[16], dd[16];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 bb = *reinterpret_cast<const float4*>(brow + (((half * 8 + c) ^ sx) << 4));
-        const float4 ll = *reinterpret_cast<const float4*>(lrow + c * 4);
-        const float4 dl = *reinterpret_cast<const float4*>(drow + c * 4);
+        const float4 bb = lds_f4(brow + (uint32_t)(((half * 8 + c) ^ sx) << 4));
+        const float4 ll = lds_f4(lrow + c * 16);
+        const float4 dl = lds_f4(drow + c * 16);
         const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, lv[4] = {ll.x, ll.y, ll.z, ll.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
         float pv[4], sv[4];
 #pragma unroll
@@ -696,8 +703,8 @@ attn_wt_bwd_kernel(vtb_attn_params p, WtGeom g, int ntiles, int nchunks) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const uint32_t off = sw128(r, half * 4 + q4);
-        *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
-        *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
+        sts_u4(smem_u32(sP) + off, pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+        sts_u4(smem_u32(sdS) + off, dd[q4 * 4], dd[q4 * 4 + 1], dd[q4 * 4 + 2], dd[q4 * 4 + 3]);
       }
       wt_proxy_fence();
       wt_warp_arrive(pds_full, lane);

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvtb200.so")
+# VTB_LIB=<file name next to this module>: A/B of two builds of the library on the same box (tools/gpu_ab_lib.sh)
+LIB_PATH = os.path.join(_HERE, os.environ.get("VTB_LIB", "libvtb200.so"))
 
 EPI_NONE, EPI_SILU_DUAL, EPI_SILU_GRAD = 0, 1, 2
 ATTN_GLOBAL, ATTN_WINDOW, ATTN_HALO = 0, 1, 2
