@@ -156,7 +156,15 @@ typedef struct {
    * [n_mask][2][64] uint64: word [m][0][i] has bit j set where mask[m, i, j] != 0 (query rows, forward),
    * word [m][1][j] has bit i set where mask[m, i, j] != 0 (key rows, backward).  NULL with mask != NULL -> mma.sync path. */
   const void* mask_bits;
+  /* optional, backward only: scratch for the tcgen05 HALO kernels — per-block partial dK / dV rows that a second kernel sums
+   * per token in a fixed order (no atomics).  Size from vtb_attention_bwd_workspace_bytes(); NULL / too small -> the
+   * mma.sync halo kernels run instead.  16-byte aligned. */
+  void* ws;
+  int64_t ws_bytes;
 } vtb_attn_params;
+
+/* Bytes of vtb_attn_params.ws that vtb_attention_bwd can use for this geometry (0: none needed). */
+int64_t vtb_attention_bwd_workspace_bytes(const vtb_attn_params* p);
 
 int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream);
 int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream);

@@ -427,13 +427,26 @@ def test_attention_window_plain_twins(ops):
     _window_case(ops, 14, 7, False, H=2, dh=64, B=2, seed=77, use_bias=False)
 
 
-@pytest.mark.parametrize("Hs,W,hl", [(14, 7, 3), (7, 7, 3), (8, 2, 1)])
-def test_attention_halo(ops, Hs, W, hl):
+@pytest.mark.parametrize("Hs,W,hl,B", [(14, 7, 3, 2), (7, 7, 3, 2), (8, 2, 1, 2), (21, 7, 3, 1), (28, 7, 3, 5), (12, 4, 2, 3)])
+@pytest.mark.parametrize("ht", [1, 0])
+def test_attention_halo(ops, Hs, W, hl, B, ht):
+    """ht=1: tcgen05 halo tiles (forward; backward with per-block partial dK / dV rows + the per-token sum);
+    ht=0: the mma.sync kernels.  B=1 x 9 blocks: an odd number of blocks (the last tile holds one)."""
+    from vtb200 import lib
+
+    lib.set_option("attn_ht", ht)
+    try:
+        _halo_case(ops, Hs, W, hl, B)
+    finally:
+        lib.set_option("attn_ht", 1)
+
+
+def _halo_case(ops, Hs, W, hl, B):
     from oracle import restate as R
     from vtb200 import lib
 
     g = torch.Generator(device="cuda").manual_seed(Hs * 31 + W)
-    B, H, dh = 2, 3, 32
+    H, dh = 3, 32
     HD, T, K = H * dh, B * Hs * Hs, W + 2 * hl
     qkv = bf(torch.randn(T, 3 * HD, device="cuda", generator=g))
     pos = R.halo_pos_table(W, hl)

@@ -647,6 +647,10 @@ int vtb_attn_tc_bwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_wt_ok(const vtb_attn_params* p, bool bwd);
 int vtb_attn_wt_fwd(const vtb_attn_params* p, cudaStream_t stream);
 int vtb_attn_wt_bwd(const vtb_attn_params* p, cudaStream_t stream);
+bool vtb_attn_ht_ok(const vtb_attn_params* p, bool bwd);
+size_t vtb_attn_ht_ws_bytes(const vtb_attn_params* p);
+int vtb_attn_ht_fwd(const vtb_attn_params* p, cudaStream_t stream);
+int vtb_attn_ht_bwd(const vtb_attn_params* p, cudaStream_t stream);
 bool vtb_attn_resident_ok(const vtb_attn_params* p);
 int vtb_attn_resident_fwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream);
 int vtb_attn_resident_bwd(const vtb_attn_params* p, const Geom& g, long groups, cudaStream_t stream, int skip_dkv = 0);
@@ -660,6 +664,7 @@ extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_)
   VTB_CHECK(p->o && p->ldo % 2 == 0, -1, "vtb_attention_fwd: o");
   if (vtb_attn_tc_fwd_ok(p)) return vtb_attn_tc_fwd(p, stream);  // tcgen05 / TMEM path (global, dh 64, <= 256 keys)
   if (vtb_attn_wt_ok(p, false)) return vtb_attn_wt_fwd(p, stream);  // tcgen05 window tiles (two windows per 128-row tile, dh 32)
+  if (vtb_attn_ht_ok(p, false)) return vtb_attn_ht_fwd(p, stream);  // tcgen05 halo tiles (two blocks per 128-row tile, dh 32)
   if (vtb_attn_wp_ok(p, false)) return vtb_attn_wp_fwd(p, g, groups, stream);  // one warp per (window, head)
   if (vtb_attn_resident_ok(p)) return vtb_attn_resident_fwd(p, g, groups, stream);
   const int q_tiles = (p->nq + BQ - 1) / BQ;
@@ -669,6 +674,16 @@ extern "C" int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream_)
   else             attn_fwd_kernel<32><<<(unsigned)blocks, NTHREADS, 0, stream>>>(*p, g, q_tiles);
   VTB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int64_t vtb_attention_bwd_workspace_bytes(const vtb_attn_params* p) {
+  if (p == nullptr || p->mode != VTB_ATTN_HALO || p->dh != 32 || p->window <= 0 || p->dkv_f32) return 0;
+  vtb_attn_params q = *p;  // would the tcgen05 halo kernels take this problem if it had a workspace?
+  q.ws = reinterpret_cast<void*>(16);
+  q.ws_bytes = INT64_MAX;
+  q.dout = q.o; q.dq = q.o; q.dk = q.o; q.dv = q.o;  // alignment of the gradient buffers is checked at the call
+  q.lddo = q.lddq = q.lddk = q.lddv = 8;
+  return vtb_attn_ht_ok(&q, true) ? (int64_t)vtb_attn_ht_ws_bytes(p) : 0;
 }
 
 extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_) {
@@ -686,6 +701,7 @@ extern "C" int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream_)
   const vtb_attn_params& q = *p;
   if (vtb_attn_tc_bwd_ok(p)) return vtb_attn_tc_bwd(p, stream);  // tcgen05 / TMEM path
   if (vtb_attn_wt_ok(p, true)) return vtb_attn_wt_bwd(p, stream);
+  if (vtb_attn_ht_ok(p, true)) return vtb_attn_ht_bwd(p, stream);
   if (vtb_attn_wp_ok(p, true)) return vtb_attn_wp_bwd(p, g, groups, stream);
   if (vtb_attn_resident_ok(p) && vtb_attn_halo_dkv_ok(p)) {
     // halo: dQ + bias gradient query-centric (resident kernel, phase A only), dK / dV key-centric without atomics

@@ -1,0 +1,831 @@
+// tcgen05 / TMEM blocked local attention with a zero-padded halo (HaloNet: W^2 <= 64 queries per block, (W + 2 halo)^2
+// <= 176 key slots, dh = 32), forward and backward.  halo_transformer.py:57-114 (F.unfold gather, rel_pos bias, softmax).
+//
+// Same tile algebra as the window kernels (attention_win_tc.cu): TWO blocks share every 128-row tile and are kept apart by
+// stacking them along the contraction axis (A rows of block w hold their 32 features in K columns [32 w, 32 w + 32), B rows
+// hold [block 0 | block 1]), so the products come out block-diagonal with nothing to mask.  What is different:
+//   * the keys / values of a block are the (W + 2 halo)^2 slots of its halo window: the loaders resolve slot -> token
+//     (or "outside the image" -> cp.async zero fill: the reference pads with zeros, the slot still takes part in the softmax
+//     with score = bias) — the unfold never exists in memory;
+//   * forward: S is 128 x 176 in TMEM (N = 176 in one UMMA), the softmax makes two passes over TMEM (row max, then
+//     probabilities written back over S as bf16 pairs), O = P V takes P straight from TMEM (11 K-steps);
+//   * backward: keys sit on the tile rows as in the window kernel, so a block pair is cut into 64-slot key chunks; every chunk
+//     is one window-style tile (S^T, dP^T, dV, dK complete per chunk; dQ accumulates in TMEM over the chunks of a pair).
+//     Key / value tokens belong to up to four halos, so dK / dV leave as PER-BLOCK partial rows (bf16, plain coalesced
+//     stores, workspace [2][block][head][slot][32]) and a second small kernel sums, for every token, the <= 4 partial rows that
+//     cover it in a fixed order (fp32) — no atomics, run-to-run deterministic.
+//     The bias gradient stays in registers (one accumulator set per key chunk) until the CTA's last tile.
+// One persistent CTA per SM with a fixed head; 4 loader warps (16-byte cp.async gathers whose completion fires the stage
+// barriers), one UMMA issuer thread, 8 math warps (thread = TMEM lane = tile row); registers re-balanced with setmaxnreg.
+#include "attn_win_common.cuh"
+#include "../../include/vtb200.h"
+#include <math.h>
+
+namespace {
+
+constexpr int HT_MAXK = 176;  // key slots per block, padded to a multiple of 16 ((7 + 2 * 3)^2 = 169)
+
+struct HtGeom {
+  int heads, nq, nkv, Hs, Ws, window, halo, kw, nbx, nb, groups;
+  int nkc;  // 16-slot steps covering nkv
+  int nch;  // 64-slot chunks covering nkv (backward tiles per block pair)
+  float inv_nb, inv_nbx, inv_kw, inv_w;
+};
+struct HtOrigin { int img, y0, x0; };  // top-left token of the block (without halo); img < 0: no such block
+
+__device__ __forceinline__ HtOrigin ht_origin(const HtGeom& g, int grp) {
+  HtOrigin o;
+  if (grp >= g.groups) { o.img = -1; o.y0 = o.x0 = 0; return o; }
+  const int b = wt_div(grp, g.nb, g.inv_nb), bi = grp - b * g.nb;
+  const int by = wt_div(bi, g.nbx, g.inv_nbx), bx = bi - by * g.nbx;
+  o.img = b; o.y0 = by * g.window; o.x0 = bx * g.window;
+  return o;
+}
+// token of query t of the block, -1 for padding
+__device__ __forceinline__ int ht_q_token(const HtGeom& g, const HtOrigin& o, int t) {
+  if (t >= g.nq || o.img < 0) return -1;
+  const int ty = wt_div(t, g.window, g.inv_w), tx = t - ty * g.window;
+  return (o.img * g.Hs + o.y0 + ty) * g.Ws + o.x0 + tx;
+}
+// token of key slot j of the block's halo window, -1 where the slot is zero padding (halo_transformer.py:74-80)
+__device__ __forceinline__ int ht_k_token(const HtGeom& g, const HtOrigin& o, int j) {
+  if (j >= g.nkv || o.img < 0) return -1;
+  const int ky = wt_div(j, g.kw, g.inv_kw), kx = j - ky * g.kw;
+  const int y = o.y0 - g.halo + ky, x = o.x0 - g.halo + kx;
+  if (y < 0 || y >= g.Hs || x < 0 || x >= g.Ws) return -1;
+  return (o.img * g.Hs + y) * g.Ws + x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+//   S[(w,i), j] = Qpad . Kcat^T  (M 128, N = 16 nkc <= 176, K 64)  -> two-pass softmax per row -> P (bf16) over S in TMEM
+//   O[(w,i), (w',d)] = P . Vcat  (A from TMEM, B MN-major, nkc K-steps); columns w' = w are the output.
+//   3 operand stages (Qpad 16 KB | Kcat 22 KB | Vcat 22 KB), 2 TMEM buffers (S 176 | O 64), the two math groups take
+//   alternate tiles.  Bias tile: fp32 [64 queries][16 nkc slots] x log2 e, -inf on slot padding, 16-byte chunks XOR-swizzled.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HF_STAGES = 3;
+constexpr int HF_OFF_K = 16384, HF_OFF_V = 16384 + HT_MAXK * 128;
+constexpr int HF_STAGE_BYTES = 16384 + 2 * HT_MAXK * 128;  // 61440
+constexpr int HF_BIAS_BYTES = 64 * HT_MAXK * 4;            // 45056
+constexpr int HF_SMEM = HF_STAGES * HF_STAGE_BYTES + HF_BIAS_BYTES + 256 + 1024;
+constexpr uint32_t HF_TBUF = 256, HF_TO = 192;
+static_assert(HF_SMEM <= 232448, "forward shared memory");
+static_assert(HF_OFF_V % 1024 == 0 && HF_STAGE_BYTES % 1024 == 0, "operand tiles must be 1024-byte aligned");
+
+// physical 16-byte chunk of logical chunk ch in a bias row of `nchunk` chunks: XOR with the row inside whole groups of 8,
+// with the row's low two bits inside a trailing group of 4 (conflict-free float4 reads down a column for both row pitches)
+__device__ __forceinline__ int ht_bias_chunk(int ch, int full, int s7, int s3) {
+  return ch < full ? (ch ^ s7) : full + ((ch - full) ^ s3);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sStage = smem;
+  uint8_t* sBias = smem + HF_STAGES * HF_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + HF_BIAS_BYTES);
+  uint64_t* full = bars;         // [3] 128 cp.async arrivals (loader threads) -> issuer
+  uint64_t* empty = bars + 3;    // [3] PV retired -> loaders
+  uint64_t* s_full = bars + 6;   // [2] S complete
+  uint64_t* p_full = bars + 8;   // [2] P written (4 warps)
+  uint64_t* o_full = bars + 10;  // [2] O complete
+  uint64_t* o_free = bars + 12;  // [2] O drained (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % g.heads;
+  const int chunk = blockIdx.x / g.heads;
+  const int my_tiles = (ntiles - chunk + nchunks - 1) / nchunks;
+  const int nkc = g.nkc;
+  const int pitch = nkc * 64;            // bias row pitch in bytes
+  const int full8 = (nkc * 4) & ~7;      // chunks in whole groups of 8
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HF_STAGES; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  // zero the operand ring once: the zero halves of Qpad, the query rows >= nq and the slot rows >= nkv never change
+  for (int e = threadIdx.x; e < HF_STAGES * HF_STAGE_BYTES / 16; e += WT_THREADS)
+    reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    float* tab = reinterpret_cast<float*>(sStage);  // scratch: the head's column of rel_pos.weight
+    if (p.rel_bias)
+      for (int t = threadIdx.x; t < p.n_pos; t += WT_THREADS) tab[t] = __ldg(p.rel_bias + (long)t * g.heads + h) * WT_L2E;
+    __syncthreads();
+    const int ncol = nkc * 16;
+    for (int e = threadIdx.x; e < 64 * ncol; e += WT_THREADS) {
+      const int row = e / ncol, col = e - row * ncol;
+      float v = 0.f;
+      if (col >= g.nkv) v = -INFINITY;
+      else if (row < g.nq && p.rel_bias) v = tab[__ldg(p.pos + row * g.nkv + col)];
+      *reinterpret_cast<float*>(sBias + row * pitch + ht_bias_chunk(col >> 2, full8, row & 7, row & 3) * 16 + (col & 3) * 4) = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2048 / 16; e += WT_THREADS) reinterpret_cast<uint4*>(sStage)[e] = make_uint4(0, 0, 0, 0);
+  }
+  wt_proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ loaders (128 threads)
+    // thread = (block w of the tile, 16-byte chunk cc, row r4 + 16 it): four lanes cover one 64-byte token row
+    wt_reg_dec<80>();
+    const int tt = threadIdx.x, w = tt >> 6, tl = tt & 63, cc = tl & 3, r4 = tl >> 2;
+    const uint32_t ch = (uint32_t)(((w * 4 + cc) ^ (r4 & 7)) << 4);
+    const uint32_t st0 = smem_u32(sStage) + (uint32_t)r4 * 128u + ch;
+    const char* qb = reinterpret_cast<const char*>(p.q) + (h * 32 + cc * 8) * 2;
+    const char* kb = reinterpret_cast<const char*>(p.k) + (h * 32 + cc * 8) * 2;
+    const char* vb = reinterpret_cast<const char*>(p.v) + (h * 32 + cc * 8) * 2;
+    const long ldq2 = (long)p.ldq * 2, ldk2 = (long)p.ldk * 2, ldv2 = (long)p.ldv * 2;
+    for (int n = 0; n < my_tiles; ++n) {
+      const int tile = chunk + n * nchunks;
+      const int stage = n % HF_STAGES;
+      mbar_wait(&empty[stage], ((n / HF_STAGES) & 1) ^ 1);
+      const uint32_t st = st0 + stage * HF_STAGE_BYTES;
+      const HtOrigin org = ht_origin(g, tile * 2 + w);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 16 + r4;
+        if (row < g.nq) {
+          const int tok = ht_q_token(g, org, row);
+          cp_async16(st + (uint32_t)(w * 64 + it * 16) * 128u, qb + (long)(tok < 0 ? 0 : tok) * ldq2, tok >= 0);
+        }
+      }
+      for (int it = 0; it < nkc; ++it) {
+        const int j = it * 16 + r4;
+        if (j < g.nkv) {
+          const int tok = ht_k_token(g, org, j);
+          const long gr = tok < 0 ? 0 : tok;
+          const uint32_t ro = (uint32_t)(it * 16) * 128u;
+          cp_async16(st + HF_OFF_K + ro, kb + gr * ldk2, tok >= 0);
+          cp_async16(st + HF_OFF_V + ro, vb + gr * ldv2, tok >= 0);
+        }
+      }
+      cp_async_arrive_noinc(&full[stage]);
+    }
+    cp_async_wait<0>();  // nothing may still be in flight towards this CTA's shared memory at exit
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ UMMA issuer (warp 12, one thread)
+    wt_reg_dec<40>();
+    if (warp == 12 && lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, nkc * 16, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      int ns = 0, np = 0;  // event-driven: whichever of "next score tile" / "next P.V" has its inputs ready is issued
+      WtWatchdog dog;
+      dog.reset();
+      while (np < my_tiles) {
+        bool did = false;
+        if (ns < my_tiles && ns < np + 2) {
+          const int b = ns & 1, stage = ns % HF_STAGES;
+          if (mbar_test(&full[stage], (ns / HF_STAGES) & 1) && mbar_test(&o_free[b], ((ns >> 1) & 1) ^ 1)) {
+            wt_proxy_fence();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sStage + stage * HF_STAGE_BYTES), ka = qa + HF_OFF_K;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + b * HF_TBUF, umma_desc_sw128(qa + k * 32, 0, 1024),
+                        umma_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[b]);
+            ++ns;
+            did = true;
+          }
+        }
+        if (np < ns) {
+          const int b = np & 1, stage = np % HF_STAGES;
+          if (mbar_test(&p_full[b], (np >> 1) & 1)) {
+            tc_fence_after();
+            const uint32_t va = smem_u32(sStage + stage * HF_STAGE_BYTES) + HF_OFF_V;
+            for (int k = 0; k < nkc; ++k)
+              wt_umma_ts(tmem_base + b * HF_TBUF + HF_TO, tmem_base + b * HF_TBUF + k * 8,
+                         umma_desc_sw128(va + k * 2048, 0, 1024), idesc_o, k > 0 ? 1u : 0u);
+            umma_commit(&o_full[b]);
+            umma_commit(&empty[stage]);
+            ++np;
+            did = true;
+          }
+        }
+        if (did) dog.reset(); else dog.idle();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ math: thread = query row (w, i)
+    wt_reg_inc<192>();
+    const int grpi = (warp - 4) >> 2;  // math group = TMEM buffer: tiles n = grpi, grpi + 2, ...
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane, w = r >> 6, i = r & 63;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + grpi * HF_TBUF;
+    const float sl2 = p.scale * WT_L2E;
+    const uint32_t brow = smem_u32(sBias) + (uint32_t)(i * pitch);
+    const int s7 = i & 7, s3 = i & 3;
+    bf16* O = reinterpret_cast<bf16*>(p.o);
+    // one 16-slot unit of the row: x = s * sl2 + bias
+    auto unit_max = [&](const uint32_t (&s)[16], int u, float mx) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bb = lds_f4(brow + (uint32_t)(ht_bias_chunk(u * 4 + q, full8, s7, s3) << 4));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(s[q * 4 + 0]), sl2, bb.x), fmaf(__uint_as_float(s[q * 4 + 1]), sl2, bb.y)),
+                             fmaxf(fmaf(__uint_as_float(s[q * 4 + 2]), sl2, bb.z), fmaf(__uint_as_float(s[q * 4 + 3]), sl2, bb.w))));
+      }
+      return mx;
+    };
+    auto unit_prob = [&](const uint32_t (&s)[16], int u, float m, float sum) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bb = lds_f4(brow + (uint32_t)(ht_bias_chunk(u * 4 + q, full8, s7, s3) << 4));
+        const float p0 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 0]), sl2, bb.x - m));
+        const float p1 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 1]), sl2, bb.y - m));
+        const float p2 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 2]), sl2, bb.z - m));
+        const float p3 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 3]), sl2, bb.w - m));
+        sum += (p0 + p1) + (p2 + p3);
+        pk[q * 2] = pack_bf16(p0, p1);
+        pk[q * 2 + 1] = pack_bf16(p2, p3);
+      }
+      wt_tmem_st8(t_lane + u * 8, pk);  // P unit u lands in 32-bit columns [8 u, 8 u + 8): below every S column still to be read
+      return sum;
+    };
+    for (int n = grpi; n < my_tiles; n += 2) {
+      const int tile = chunk + n * nchunks;
+      const int grp = tile * 2 + w;
+      const int tok = ht_q_token(g, ht_origin(g, grp), i);
+      mbar_wait(&s_full[grpi], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t sa[16], sb[16];
+      // pass 1: row maximum (one TMEM load kept in flight)
+      float mx = -INFINITY;
+      tmem_ld_32x16(t_lane, sa);
+      for (int u = 0; u < nkc; u += 2) {
+        tmem_ld_wait();
+        if (u + 1 < nkc) tmem_ld_32x16(t_lane + (u + 1) * 16, sb);
+        mx = unit_max(sa, u, mx);
+        if (u + 1 < nkc) {
+          tmem_ld_wait();
+          if (u + 2 < nkc) tmem_ld_32x16(t_lane + (u + 2) * 16, sa);
+          mx = unit_max(sb, u + 1, mx);
+        }
+      }
+      const float m_use = (mx == -INFINITY) ? 0.f : mx;
+      // pass 2: probabilities
+      float sum = 0.f;
+      tmem_ld_32x16(t_lane, sa);
+      for (int u = 0; u < nkc; u += 2) {
+        tmem_ld_wait();
+        if (u + 1 < nkc) tmem_ld_32x16(t_lane + (u + 1) * 16, sb);
+        sum = unit_prob(sa, u, m_use, sum);
+        if (u + 1 < nkc) {
+          tmem_ld_wait();
+          if (u + 2 < nkc) tmem_ld_32x16(t_lane + (u + 2) * 16, sa);
+          sum = unit_prob(sb, u + 1, m_use, sum);
+        }
+      }
+      wt_tmem_st_wait();
+      tc_fence_before();
+      wt_warp_arrive(&p_full[grpi], lane);
+      // epilogue: O / l -> bf16 -> global; lse = ln 2 * (max + log2(sum))
+      mbar_wait(&o_full[grpi], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld_32x32(t_lane + HF_TO + w * 32, a);
+      tmem_ld_wait();
+      tc_fence_before();
+      wt_warp_arrive(&o_free[grpi], lane);
+      if (tok >= 0) {
+        wt_store_row32(O + (long)tok * p.ldo + h * 32, a, 1.f / sum);
+        if (p.lse) p.lse[((long)grp * g.heads + h) * g.nq + i] = (mx + log2f(sum)) * WT_LN2;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward: tile = (block pair, 64-slot key chunk c); keys on the tile rows
+//   S^T[(w,jj), i] = Kpad . Qcat^T      dP^T[(w,jj), i] = Vpad . dOcat^T             (M 128, N 64, K 64)
+//   P^T = exp2(S^T sl2 + bias - lse2[i]),  dS^T = P^T (dP^T - delta[i])   -> bf16 tiles in shared memory
+//   dV[(w,jj), (w',d)] = P^T . dOcat    dK = dS^T . Qcat   (complete per chunk -> per-block partial rows)
+//   dQ[i, (w,d)]      += dS . Kpad      (accumulates over the chunks of the pair, drained after the last one)
+// TMEM: S^T 2 x 64 | dP^T 2 x 64 | dV 64 | dK 64 | dQ 64.   Rings: 3 key/value chunk stages (Kpad 16 KB | Vpad 16 KB),
+// 2 query stages (Qcat 8 KB | dOcat 8 KB | O rows 8 KB for delta) loaded once per pair.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HB_KV_STAGES = 3, HB_KV_BYTES = 32768;
+constexpr int HB_Q_BYTES = 24576, HB_OFF_DO = 8192, HB_OFF_O = 16384;
+constexpr int HB_BIAS_ROWS = HT_MAXK + 8;  // slots, plus a guard row that is -inf whatever nkv is
+constexpr int HB_SIDE_BYTES = 128 * 4 * 3;  // query token, lse * log2 e, delta per tile row (w, i)
+constexpr int HB_OFF_Q = HB_KV_STAGES * HB_KV_BYTES;
+constexpr int HB_OFF_DS = HB_OFF_Q + 2 * HB_Q_BYTES;
+constexpr int HB_OFF_P = HB_OFF_DS + 16384;
+constexpr int HB_OFF_BIAS = HB_OFF_P + 16384;
+constexpr int HB_OFF_SIDE = HB_OFF_BIAS + HB_BIAS_ROWS * 256;
+constexpr int HB_OFF_BARS = HB_OFF_SIDE + 2 * HB_SIDE_BYTES;
+constexpr int HB_SMEM = HB_OFF_BARS + 256 + 1024;
+static_assert(HB_SMEM <= 232448, "backward shared memory");
+constexpr uint32_t HC_ST = 0, HC_DP = 128, HC_DV = 256, HC_DK = 320, HC_DQ = 384;
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* part_k, bf16* part_v) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sKV = smem;
+  uint8_t* sQ = smem + HB_OFF_Q;
+  uint8_t* sdS = smem + HB_OFF_DS;   // [128 key rows][64 queries] bf16, 128B-swizzled
+  uint8_t* sP = smem + HB_OFF_P;     // directly behind dS^T: the dQ product's second M atom lands here
+  uint8_t* sBias = smem + HB_OFF_BIAS;
+  uint8_t* sSide = smem + HB_OFF_SIDE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HB_OFF_BARS);
+  uint64_t* kv_land = bars;         // [3] 128 cp.async arrivals
+  uint64_t* kv_empty = bars + 3;    // [3] gradient MMAs of the chunk retired
+  uint64_t* q_land = bars + 6;      // [2] 128 cp.async arrivals
+  uint64_t* q_full = bars + 8;      // [2] count 4: delta / lse of the landed pair in place
+  uint64_t* q_empty = bars + 10;    // [2] gradient MMAs of the pair's last chunk retired
+  uint64_t* s_full = bars + 12;     // [2] S^T / dP^T complete
+  uint64_t* s_free = bars + 14;     // [2] read out of TMEM (8 warps)
+  uint64_t* pds_full = bars + 16;   // P^T / dS^T tiles written (8 warps)
+  uint64_t* pds_free = bars + 17;   // ... and consumed by the gradient MMAs
+  uint64_t* g_full = bars + 18;     // dV / dK (/ dQ) complete
+  uint64_t* g_free = bars + 19;     // ... and drained (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % g.heads;
+  const int chunk = blockIdx.x / g.heads;
+  const int my_pairs = (npairs - chunk + nchunks - 1) / nchunks;
+  const int nch = g.nch;
+  const int my_tiles = my_pairs * nch;
+  const bool has_tab = p.rel_bias != nullptr && p.drel_bias != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&kv_land[i], 128); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_land[i], 128); mbar_init(&q_full[i], 4); mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
+    }
+    mbar_init(pds_full, 8); mbar_init(pds_free, 1); mbar_init(g_full, 1); mbar_init(g_free, 8);
+    mbar_fence_init();
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  for (int e = threadIdx.x; e < HB_OFF_BIAS / 16; e += WT_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    // bias tile, keys on the rows: tile[j][i] = rel_bias[pos[i, j], h] * log2 e; -inf rows for j >= nkv (incl. the guard row)
+    float* tab = reinterpret_cast<float*>(sP);
+    if (p.rel_bias)
+      for (int t = threadIdx.x; t < p.n_pos; t += WT_THREADS) tab[t] = __ldg(p.rel_bias + (long)t * g.heads + h) * WT_L2E;
+    __syncthreads();
+    for (int e = threadIdx.x; e < HB_BIAS_ROWS * 64; e += WT_THREADS) {
+      const int row = e >> 6, col = e & 63;
+      float v = 0.f;
+      if (row >= g.nkv) v = -INFINITY;
+      else if (col < g.nq && p.rel_bias) v = tab[__ldg(p.pos + col * g.nkv + row)];
+      *reinterpret_cast<float*>(sBias + row * 256 + ((((col >> 2) ^ (row & 7))) << 4) + (col & 3) * 4) = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2048 / 16; e += WT_THREADS) reinterpret_cast<uint4*>(sP)[e] = make_uint4(0, 0, 0, 0);
+  }
+  wt_proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ loaders (128 threads)
+    wt_reg_dec<80>();
+    const int tt = threadIdx.x, w = tt >> 6, tl = tt & 63, cc = tl & 3, r4 = tl >> 2;
+    const uint32_t ch = (uint32_t)(((w * 4 + cc) ^ (r4 & 7)) << 4);
+    const uint32_t kv0 = smem_u32(sKV) + (uint32_t)(w * 64 + r4) * 128u + ch;  // Kpad row (w, r4 + 16 it)
+    const uint32_t q0 = smem_u32(sQ) + (uint32_t)r4 * 128u + ch;               // Qcat / dOcat row r4 + 16 it
+    const uint32_t o0 = smem_u32(sQ) + HB_OFF_O + (uint32_t)(w * 64 + r4) * 64u + cc * 16;
+    const int colb = (h * 32 + cc * 8) * 2;
+    const char* qb = reinterpret_cast<const char*>(p.q) + colb;
+    const char* kb = reinterpret_cast<const char*>(p.k) + colb;
+    const char* vb = reinterpret_cast<const char*>(p.v) + colb;
+    const char* dob = reinterpret_cast<const char*>(p.dout) + colb;
+    const char* ob = reinterpret_cast<const char*>(p.o) + colb;
+    const long ldq2 = (long)p.ldq * 2, ldk2 = (long)p.ldk * 2, ldv2 = (long)p.ldv * 2, lddo2 = (long)p.lddo * 2,
+               ldo2 = (long)p.ldo * 2;
+    // queries of pair pi: rows, lse, token ids
+    auto issue_q = [&](int pi) {
+      const int qs = pi & 1;
+      const int grp = (chunk + pi * nchunks) * 2 + w;
+      const HtOrigin org = ht_origin(g, grp);
+      const uint32_t side = smem_u32(sSide) + (uint32_t)(qs * HB_SIDE_BYTES);
+      const int tok_side = ht_q_token(g, org, tl);
+      sts_u32(side + tt * 4, (uint32_t)tok_side);
+      if (tok_side >= 0) cp_async4(side + 512 + tt * 4, p.lse + ((long)grp * g.heads + h) * g.nq + tl);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 16 + r4;
+        if (row < g.nq) {  // rows >= nq stay zero from the prologue
+          const int tok = ht_q_token(g, org, row);
+          const long gr = tok < 0 ? 0 : tok;
+          const uint32_t ro = (uint32_t)(qs * HB_Q_BYTES) + (uint32_t)(it * 16) * 128u;
+          cp_async16(q0 + ro, qb + gr * ldq2, tok >= 0);
+          cp_async16(q0 + HB_OFF_DO + ro, dob + gr * lddo2, tok >= 0);
+          cp_async16(o0 + (uint32_t)(qs * HB_Q_BYTES) + (uint32_t)(it * 16) * 64u, ob + gr * ldo2, tok >= 0);
+        }
+      }
+      cp_async_arrive_noinc(&q_land[qs]);
+    };
+    // the pair's rows have landed: delta = dO . O and lse * log2 e, then release
+    auto finish_q = [&](int qs) {
+      const uint32_t st = smem_u32(sQ) + (uint32_t)(qs * HB_Q_BYTES);
+      const uint32_t side = smem_u32(sSide) + (uint32_t)(qs * HB_SIDE_BYTES);
+      float acc = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const uint4 ra = wt_lds_u4(st + HB_OFF_DO + sw128(tl, w * 4 + c4));
+        const uint4 rb = wt_lds_u4(st + HB_OFF_O + tt * 64 + c4 * 16);
+        const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fa = unpack_bf16(wa[q]), fb = unpack_bf16(wb[q]);
+          acc += fa.x * fb.x + fa.y * fb.y;
+        }
+      }
+      const int tok = (int)lds_u32(side + tt * 4);
+      const float l = __uint_as_float(lds_u32(side + 512 + tt * 4));
+      sts_f32(side + 512 + tt * 4, tok >= 0 ? l * WT_L2E : INFINITY);
+      sts_f32(side + 1024 + tt * 4, acc);
+      wt_warp_arrive(&q_full[qs], lane);
+    };
+    // key chunk of tile n: slots [64 c, 64 c + 64) of both blocks; slots outside the image / past nkv are zero-filled
+    auto issue_kv = [&](int n) {
+      const int pi = n / nch, c = n - pi * nch;
+      const int stage = n % HB_KV_STAGES;
+      const HtOrigin org = ht_origin(g, (chunk + pi * nchunks) * 2 + w);
+      const uint32_t st = kv0 + stage * HB_KV_BYTES;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int tok = ht_k_token(g, org, c * 64 + it * 16 + r4);
+        const long gr = tok < 0 ? 0 : tok;
+        const uint32_t ro = (uint32_t)(it * 16) * 128u;
+        cp_async16(st + ro, kb + gr * ldk2, tok >= 0);
+        cp_async16(st + 16384 + ro, vb + gr * ldv2, tok >= 0);
+      }
+      cp_async_arrive_noinc(&kv_land[stage]);
+    };
+    // event-driven (warp-uniform votes): the loaders never block on a load
+    int nk = 0, nqi = 0, nqf = 0;
+    WtWatchdog dog;
+    dog.reset();
+    while (nk < my_tiles || nqf < my_pairs) {
+      bool did = false;
+      if (nqi < my_pairs && __all_sync(0xffffffffu, mbar_test(&q_empty[nqi & 1], ((nqi >> 1) & 1) ^ 1))) {
+        issue_q(nqi);
+        ++nqi;
+        did = true;
+      }
+      if (nqf < nqi && __all_sync(0xffffffffu, mbar_test(&q_land[nqf & 1], (nqf >> 1) & 1))) {
+        finish_q(nqf & 1);
+        ++nqf;
+        did = true;
+      }
+      if (nk < my_tiles && __all_sync(0xffffffffu, mbar_test(&kv_empty[nk % 3], ((nk / 3) & 1) ^ 1))) {
+        issue_kv(nk);
+        ++nk;
+        did = true;
+      }
+      if (did) dog.reset(); else dog.idle();
+    }
+    cp_async_wait<0>();
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ UMMA issuer (warp 12, one thread)
+    wt_reg_dec<40>();
+    if (warp == 12 && lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
+      int ns = 0, ng = 0;          // next score tile / next gradient tile
+      int ns_pi = 0, ns_c = 0;     // (pair, chunk) of ns
+      int ng_pi = 0, ng_c = 0;
+      WtWatchdog dog;
+      dog.reset();
+      while (ng < my_tiles) {
+        bool did = false;
+        if (ns < my_tiles && ns < ng + 2) {
+          const int stage = ns % 3, b = ns & 1, qs = ns_pi & 1;
+          if (mbar_test(&kv_land[stage], (ns / 3) & 1) && mbar_test(&q_full[qs], (ns_pi >> 1) & 1) &&
+              mbar_test(&s_free[b], ((ns >> 1) & 1) ^ 1)) {
+            wt_proxy_fence();  // cp.async / st.shared (generic proxy) writes -> visible to the tensor core's async-proxy reads
+            tc_fence_after();
+            const uint32_t ka = smem_u32(sKV + stage * HB_KV_BYTES), qa = smem_u32(sQ + qs * HB_Q_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + HC_ST + b * 64, umma_desc_sw128(ka + k * 32, 0, 1024),
+                        umma_desc_sw128(qa + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + HC_DP + b * 64, umma_desc_sw128(ka + 16384 + k * 32, 0, 1024),
+                        umma_desc_sw128(qa + HB_OFF_DO + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[b]);
+            ++ns;
+            if (++ns_c == nch) { ns_c = 0; ++ns_pi; }
+            did = true;
+          }
+        }
+        if (ng < ns) {
+          if (mbar_test(pds_full, ng & 1) && mbar_test(g_free, (ng & 1) ^ 1)) {
+            tc_fence_after();
+            const int stage = ng % 3, qs = ng_pi & 1;
+            const uint32_t ka = smem_u32(sKV + stage * HB_KV_BYTES), qa = smem_u32(sQ + qs * HB_Q_BYTES);
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2)
+              umma_bf16(tmem_base + HC_DV, umma_desc_sw128(pa + s2 * 32, 0, 1024),
+                        umma_desc_sw128(qa + HB_OFF_DO + s2 * 2048, 0, 1024), idesc_g, s2 > 0 ? 1u : 0u);
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2)
+              umma_bf16(tmem_base + HC_DK, umma_desc_sw128(sa + s2 * 32, 0, 1024),
+                        umma_desc_sw128(qa + s2 * 2048, 0, 1024), idesc_g, s2 > 0 ? 1u : 0u);
+#pragma unroll
+            for (int s2 = 0; s2 < 8; ++s2)
+              umma_bf16(tmem_base + HC_DQ, umma_desc_sw128(sa + s2 * 2048, 16384, 1024),
+                        umma_desc_sw128(ka + s2 * 2048, 0, 1024), idesc_q, (ng_c > 0 || s2 > 0) ? 1u : 0u);
+            umma_commit(g_full);
+            umma_commit(pds_free);
+            umma_commit(&kv_empty[stage]);
+            ++ng;
+            if (++ng_c == nch) {
+              ng_c = 0;
+              umma_commit(&q_empty[qs]);
+              ++ng_pi;
+            }
+            did = true;
+          }
+        }
+        if (did) dog.reset(); else dog.idle();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ math: thread = key row (w, jj), 32 of the 64 queries
+    wt_reg_inc<192>();
+    const int half = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane, w = r >> 6, jj = r & 63;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * WT_L2E;
+    bf16* dQ = reinterpret_cast<bf16*>(p.dq);
+    bf16* part = half ? part_k : part_v;
+    float acc[3][32];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[c][e] = 0.f;
+    long prow = -1;     // partial row of the previous tile (dV / dK drain is deferred by one tile), -1: nothing to store
+    int ptok_q = -1;    // dQ row of the previous tile if it closed its pair
+    int n = 0;
+
+    auto epilogue = [&](int np, long row, int tok_q, bool last) {
+      mbar_wait(g_full, np & 1);
+      tc_fence_after();
+      uint32_t a[32], bq[32];
+      tmem_ld_32x32(t_lane + (half ? HC_DK : HC_DV) + w * 32, a);
+      if (last && quarter < 2) tmem_ld_32x32(t_lane + HC_DQ + half * 32, bq);
+      tmem_ld_wait();
+      tc_fence_before();
+      wt_warp_arrive(g_free, lane);
+      if (row >= 0) wt_store_row32(part + row * 32, a, half ? p.scale : 1.f);
+      if (last && quarter < 2 && tok_q >= 0) wt_store_row32(dQ + (long)tok_q * p.lddq + h * 32, bq, p.scale);
+    };
+
+    for (int pi = 0; pi < my_pairs; ++pi) {
+      const int qs = pi & 1;
+      const int grp = (chunk + pi * nchunks) * 2 + w;
+      const uint32_t side = smem_u32(sSide) + (uint32_t)(qs * HB_SIDE_BYTES);
+      const uint32_t lrow = side + 512 + (uint32_t)(w * 64 + half * 32) * 4u;
+      const uint32_t drow = side + 1024 + (uint32_t)(w * 64 + half * 32) * 4u;
+      mbar_wait(&q_full[qs], (pi >> 1) & 1);
+      const int tok_q = (int)lds_u32(side + (half * 64 + jj) * 4);  // dQ row (query jj of block `half`)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c < nch) {
+          const int b = n & 1;
+          const int j = c * 64 + jj;
+          const int jb = j < HB_BIAS_ROWS - 1 ? j : HB_BIAS_ROWS - 1;   // rows past the tile read the -inf guard row
+          const uint32_t brow = smem_u32(sBias) + (uint32_t)jb * 256u;
+          const int sx = jb & 7;
+          mbar_wait(&s_full[b], (n >> 1) & 1);
+          tc_fence_after();
+          // two passes of 16 queries (the three bias-gradient accumulator sets leave no room for 32-wide register tiles)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t st[16], dp[16];
+            tmem_ld_32x16(t_lane + HC_ST + b * 64 + half * 32 + hh * 16, st);
+            tmem_ld_32x16(t_lane + HC_DP + b * 64 + half * 32 + hh * 16, dp);
+            tmem_ld_wait();
+            if (hh == 1) {
+              tc_fence_before();
+              wt_warp_arrive(&s_free[b], lane);
+            }
+            uint32_t pp[8], dd[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int c8 = hh * 4 + c4;
+              const float4 bb = lds_f4(brow + (uint32_t)(((half * 8 + c8) ^ sx) << 4));
+              const float4 ll = lds_f4(lrow + c8 * 16);
+              const float4 dl = lds_f4(drow + c8 * 16);
+              const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, lv[4] = {ll.x, ll.y, ll.z, ll.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
+              float pv[4], sv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pv[e] = wt_ex2(fmaf(__uint_as_float(st[c4 * 4 + e]), sl2, bv[e]) - lv[e]);
+                sv[e] = pv[e] * (__uint_as_float(dp[c4 * 4 + e]) - dv[e]);
+                acc[c][c8 * 4 + e] += sv[e];
+              }
+              pp[c4 * 2] = pack_bf16(pv[0], pv[1]); pp[c4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
+              dd[c4 * 2] = pack_bf16(sv[0], sv[1]); dd[c4 * 2 + 1] = pack_bf16(sv[2], sv[3]);
+            }
+            if (hh == 0) mbar_wait(pds_free, (n & 1) ^ 1);  // the previous tile's gradient MMAs no longer read the tiles
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+              const uint32_t off = sw128(r, half * 4 + hh * 2 + q2);
+              sts_u4(smem_u32(sP) + off, pp[q2 * 4], pp[q2 * 4 + 1], pp[q2 * 4 + 2], pp[q2 * 4 + 3]);
+              sts_u4(smem_u32(sdS) + off, dd[q2 * 4], dd[q2 * 4 + 1], dd[q2 * 4 + 2], dd[q2 * 4 + 3]);
+            }
+          }
+          wt_proxy_fence();
+          wt_warp_arrive(pds_full, lane);
+          if (n > 0) epilogue(n - 1, prow, ptok_q, ptok_q != -2);
+          prow = (j < g.nkv && grp < g.groups) ? (((long)grp * g.heads + h) * g.nkv + j) : -1;
+          ptok_q = (c == nch - 1) ? tok_q : -2;  // -2: the pair is not finished, dQ keeps accumulating
+          ++n;
+        }
+      }
+    }
+    if (n > 0) epilogue(n - 1, prow, ptok_q, ptok_q != -2);
+
+    // bias gradient: registers -> per-CTA table in shared memory (over the retired P^T tile) -> global atomics
+    if (has_tab) {
+      float* dtab = reinterpret_cast<float*>(sP);
+      const int mt = threadIdx.x - 128;  // 0..255
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = mt; e < p.n_pos; e += 256) dtab[e] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int j = c * 64 + jj;
+        if (c < nch && j < g.nkv) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int i = half * 32 + e;
+            if (i < g.nq && acc[c][e] != 0.f) atomicAdd(&dtab[__ldg(p.pos + i * g.nkv + j)], acc[c][e]);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = mt; e < p.n_pos; e += 256) {
+        const float v = dtab[e];
+        if (v != 0.f) atomicAdd(p.drel_bias + (long)e * g.heads + h, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dK / dV of a token = sum of the partial rows of the blocks whose halo covers it, in block order (fp32, rounded once)
+__global__ void __launch_bounds__(256)
+attn_ht_dkv_reduce_kernel(vtb_attn_params p, HtGeom g, const bf16* __restrict__ part_k, const bf16* __restrict__ part_v,
+                          long total) {
+  const int W = g.window, HL = g.halo, nby = g.Hs / W;
+  const long T = (long)p.batch * g.Hs * g.Ws;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int cc = (int)(e & 3);
+    long t2 = e >> 2;
+    const int h = (int)(t2 % g.heads);
+    t2 /= g.heads;
+    const long tok = t2 % T;
+    const int kv = (int)(t2 / T);
+    const int b = (int)(tok / (g.Hs * g.Ws));
+    const int rem = (int)(tok - (long)b * g.Hs * g.Ws);
+    const int y = rem / g.Ws, x = rem - y * g.Ws;
+    const int ay = y - W - HL + 1, ax = x - W - HL + 1;
+    const int by_lo = ay > 0 ? (ay + W - 1) / W : 0, bx_lo = ax > 0 ? (ax + W - 1) / W : 0;
+    int by_hi = (y + HL) / W, bx_hi = (x + HL) / W;
+    if (by_hi > nby - 1) by_hi = nby - 1;
+    if (bx_hi > g.nbx - 1) bx_hi = g.nbx - 1;
+    const bf16* part = kv ? part_v : part_k;
+    float s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = 0.f;
+    for (int by = by_lo; by <= by_hi; ++by)
+      for (int bx = bx_lo; bx <= bx_hi; ++bx) {
+        const long grp = (long)b * g.nb + by * g.nbx + bx;
+        const int j = (y - by * W + HL) * g.kw + (x - bx * W + HL);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(part + ((grp * g.heads + h) * g.nkv + j) * 32 + cc * 8));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16(wv[q]);
+          s[q * 2] += f.x;
+          s[q * 2 + 1] += f.y;
+        }
+      }
+    bf16* dst = kv ? reinterpret_cast<bf16*>(p.dv) + tok * p.lddv : reinterpret_cast<bf16*>(p.dk) + tok * p.lddk;
+    *reinterpret_cast<uint4*>(dst + h * 32 + cc * 8) =
+        make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+  }
+}
+
+bool g_attn_ht = true;
+
+int ht_geom(const vtb_attn_params* p, HtGeom* g) {
+  g->heads = p->heads; g->nq = p->nq; g->nkv = p->nkv; g->Hs = p->Hs; g->Ws = p->Ws;
+  g->window = p->window; g->halo = p->halo; g->kw = p->window + 2 * p->halo;
+  g->nbx = p->Ws / p->window;
+  g->nb = (p->Hs / p->window) * g->nbx;
+  const long groups = (long)p->batch * g->nb;
+  VTB_CHECK(groups < (1L << 22) && (long)p->batch * p->Hs * p->Ws < (1L << 31), -1,
+            "vtb_attention(halo tcgen05): problem too large for 32-bit token indices");
+  g->groups = (int)groups;
+  g->nkc = (p->nkv + 15) / 16;
+  g->nch = (p->nkv + 63) / 64;
+  g->inv_nb = 1.f / (float)g->nb; g->inv_nbx = 1.f / (float)g->nbx;
+  g->inv_kw = 1.f / (float)g->kw; g->inv_w = 1.f / (float)g->window;
+  return 0;
+}
+
+}  // namespace
+
+void vtb_attn_ht_set(bool on) { g_attn_ht = on; }
+
+size_t vtb_attn_ht_ws_bytes(const vtb_attn_params* p) {
+  const long groups = (long)p->batch * (p->Hs / p->window) * (p->Ws / p->window);
+  return (size_t)2 * groups * p->heads * p->nkv * 32 * sizeof(bf16);
+}
+
+bool vtb_attn_ht_ok(const vtb_attn_params* p, bool bwd) {
+  if (!g_attn_ht || p->mode != VTB_ATTN_HALO || p->dh != 32 || p->nq > 64 || p->nkv > HT_MAXK || p->mask) return false;
+  if (p->rel_bias && p->n_pos > 512) return false;
+  if (p->heads > 148) return false;
+  uintptr_t al = (uintptr_t)p->q | (uintptr_t)p->k | (uintptr_t)p->v | (uintptr_t)p->o;
+  int ld = p->ldq | p->ldk | p->ldv | p->ldo;
+  if (bwd) {
+    if (p->dkv_f32 || !p->ws || p->ws_bytes < (int64_t)vtb_attn_ht_ws_bytes(p)) return false;
+    al |= (uintptr_t)p->dout | (uintptr_t)p->dq | (uintptr_t)p->dk | (uintptr_t)p->dv | (uintptr_t)p->ws;
+    ld |= p->lddo | p->lddq | p->lddk | p->lddv;
+  }
+  return (al & 15) == 0 && (ld & 7) == 0;
+}
+
+int vtb_attn_ht_fwd(const vtb_attn_params* p, cudaStream_t stream) {
+  static bool attr = false;
+  HtGeom g;
+  if (int rc = ht_geom(p, &g)) return rc;
+  if (!attr) {
+    VTB_CUDA(cudaFuncSetAttribute(attn_ht_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM));
+    attr = true;
+  }
+  const int ntiles = (g.groups + 1) / 2;
+  int nchunks = vtb_num_sms() / p->heads;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > ntiles) nchunks = ntiles;
+  attn_ht_fwd_kernel<<<(unsigned)(nchunks * p->heads), WT_THREADS, HF_SMEM, stream>>>(*p, g, ntiles, nchunks);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
+int vtb_attn_ht_bwd(const vtb_attn_params* p, cudaStream_t stream) {
+  static bool attr = false;
+  HtGeom g;
+  if (int rc = ht_geom(p, &g)) return rc;
+  if (!attr) {
+    VTB_CUDA(cudaFuncSetAttribute(attn_ht_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
+    attr = true;
+  }
+  const int npairs = (g.groups + 1) / 2;
+  int nchunks = vtb_num_sms() / p->heads;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > npairs) nchunks = npairs;
+  bf16* part_k = reinterpret_cast<bf16*>(p->ws);
+  bf16* part_v = part_k + (size_t)g.groups * p->heads * p->nkv * 32;
+  attn_ht_bwd_kernel<<<(unsigned)(nchunks * p->heads), WT_THREADS, HB_SMEM, stream>>>(*p, g, npairs, nchunks, part_k, part_v);
+  VTB_LAUNCH_CHECK();
+  const long total = 2L * p->batch * p->Hs * p->Ws * p->heads * 4;
+  long blocks = (total + 255) / 256;
+  const long cap = (long)vtb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  attn_ht_dkv_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*p, g, part_k, part_v, total);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}

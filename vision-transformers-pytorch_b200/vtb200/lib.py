@@ -17,7 +17,7 @@ ATTN_GLOBAL, ATTN_WINDOW, ATTN_HALO = 0, 1, 2
 # every symbol include/vtb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "vtb_last_error", "vtb_version", "vtb_init", "vtb_set_option", "vtb_gemm_bf16", "vtb_layernorm_fwd",
-    "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_cast_f32_bf16",
+    "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_attention_bwd_workspace_bytes", "vtb_cast_f32_bf16",
     "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_scale_cast_colsum_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
     "vtb_patch_scatter", "vtb_transpose_hw", "vtb_dwconv3x3_fwd", "vtb_dwconv3x3_bwd", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
     "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss", "vtb_mt_num_chunks", "vtb_mt_cast_f32_bf16", "vtb_mt_ema",
@@ -65,6 +65,7 @@ class AttnParams(C.Structure):
         ("delta", C.c_void_p),
         ("drel_bias", C.c_void_p),
         ("mask_bits", C.c_void_p),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
     ]
 
 
@@ -95,6 +96,8 @@ def load():
                                       i32, vp, vp, vp, vp]
     lib.vtb_attention_fwd.argtypes = [C.POINTER(AttnParams), vp]
     lib.vtb_attention_bwd.argtypes = [C.POINTER(AttnParams), vp]
+    lib.vtb_attention_bwd_workspace_bytes.argtypes = [C.POINTER(AttnParams)]
+    lib.vtb_attention_bwd_workspace_bytes.restype = i64
     lib.vtb_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
     lib.vtb_cast_f32_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i32, vp]
     lib.vtb_scale_cast_bf16.argtypes = [vp, vp, i32, i64, i32, vp, vp]

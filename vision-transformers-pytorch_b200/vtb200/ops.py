@@ -328,6 +328,10 @@ def attention_bwd(spec, q, k, v, o, lse, dout, dq, dk, dv, drel_bias=None, dkv_f
     p.delta = delta.data_ptr()
     if drel_bias is not None:
         p.drel_bias = drel_bias.data_ptr()
+    ws_bytes = lib.vtb_attention_bwd_workspace_bytes(C.byref(p))
+    if ws_bytes > 0:  # tcgen05 halo kernels: per-block partial dK / dV rows, summed per token by a second kernel
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+        p.ws, p.ws_bytes = ws.data_ptr(), ws_bytes
     hd = spec.heads * spec.dh
     with _prof("attention_bwd", 10.0 * spec.groups * spec.heads * spec.nq * spec.nkv * spec.dh,
                2.0 * hd * (4 * q.shape[0] + 4 * k.shape[0])):  # q, k, v, o, do read; dq, dk, dv written (bf16)
