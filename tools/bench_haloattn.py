@@ -9,7 +9,8 @@ from vtb200 import lib, ops
 
 B, W, hl, dh = int(os.environ.get("HB", 128)), 7, 3, 32
 K = W + 2 * hl
-SHAPES = ((14, 12),) if os.environ.get("HT_ONLY") else ((56, 3), (28, 6), (14, 12), (7, 24))
+ALL = ((56, 3), (28, 6), (14, 12), (7, 24))
+SHAPES = tuple(s for s in ALL if str(s[0]) == os.environ["HT_ONLY"]) if os.environ.get("HT_ONLY") else ALL  # HT_ONLY=56: one shape, tcgen05 only
 
 
 def rel(a, b):

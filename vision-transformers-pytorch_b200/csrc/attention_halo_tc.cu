@@ -16,7 +16,7 @@
 //     cover it in a fixed order (fp32) — no atomics, run-to-run deterministic.
 //     The bias gradient stays in registers (one accumulator set per key chunk) until the CTA's last tile.
 // One persistent CTA per SM with a fixed head; 4 loader warps (16-byte cp.async gathers whose completion fires the stage
-// barriers), one UMMA issuer thread, 8 math warps (thread = TMEM lane = tile row); registers re-balanced with setmaxnreg.
+// barriers), one UMMA issuer warp, 8 math warps (thread = TMEM lane = tile row); registers re-balanced with setmaxnreg.
 #include "attn_win_common.cuh"
 #include "../../include/vtb200.h"
 #include <math.h>
@@ -56,6 +56,55 @@ __device__ __forceinline__ int ht_k_token(const HtGeom& g, const HtOrigin& o, in
   return (o.img * g.Hs + y) * g.Ws + x;
 }
 
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work — the math warps are issue-bound)
+__device__ __forceinline__ uint64_t ht_pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t ht_pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void ht_upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ht_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t ht_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ht_mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// Tile-invariant part of ht_k_token / ht_q_token for a loader thread: slot -> (dy, dx) relative to the block origin, packed
+// as two signed 16-bit fields (0x7fff7fff: no such slot).  Per tile only the bounds test and one multiply-add remain.
+__device__ __forceinline__ int ht_slot_pack(const HtGeom& g, int j) {
+  if (j >= g.nkv) return 0x7fff7fff;
+  const int ky = j / g.kw, kx = j - ky * g.kw;
+  return ((ky - g.halo) & 0xffff) | ((kx - g.halo) << 16);
+}
+__device__ __forceinline__ int ht_query_pack(const HtGeom& g, int t) {
+  if (t >= g.nq) return 0x7fff7fff;
+  const int ty = t / g.window, tx = t - ty * g.window;
+  return ty | (tx << 16);
+}
+// token of a packed slot for the block at `o` (base = token of the block origin), -1 outside the image / no slot / no block
+__device__ __forceinline__ int ht_pack_token(const HtGeom& g, const HtOrigin& o, int base, int pk) {
+  const int dy = (int)(short)(pk & 0xffff), dx = pk >> 16;
+  const int y = o.y0 + dy, x = o.x0 + dx;
+  const bool ok = o.img >= 0 && (unsigned)y < (unsigned)g.Hs && (unsigned)x < (unsigned)g.Ws;
+  return ok ? base + dy * g.Ws + dx : -1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 //   S[(w,i), j] = Qpad . Kcat^T  (M 128, N = 16 nkc <= 176, K 64)  -> two-pass softmax per row -> P (bf16) over S in TMEM
@@ -78,6 +127,7 @@ __device__ __forceinline__ int ht_bias_chunk(int ch, int full, int s7, int s3) {
   return ch < full ? (ch ^ s7) : full + ((ch - full) ^ s3);
 }
 
+template <int NKC>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
   extern __shared__ uint8_t smem_raw[];
@@ -97,9 +147,9 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
   const int h = blockIdx.x % g.heads;
   const int chunk = blockIdx.x / g.heads;
   const int my_tiles = (ntiles - chunk + nchunks - 1) / nchunks;
-  const int nkc = g.nkc;
-  const int pitch = nkc * 64;            // bias row pitch in bytes
-  const int full8 = (nkc * 4) & ~7;      // chunks in whole groups of 8
+  constexpr int nkc = NKC;              // 16-slot steps (compile time: the unit loops unroll, bias addresses become immediates)
+  constexpr int pitch = nkc * 64;        // bias row pitch in bytes
+  constexpr int full8 = (nkc * 4) & ~7;  // chunks in whole groups of 8
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < HF_STAGES; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
@@ -146,24 +196,29 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
     const char* kb = reinterpret_cast<const char*>(p.k) + (h * 32 + cc * 8) * 2;
     const char* vb = reinterpret_cast<const char*>(p.v) + (h * 32 + cc * 8) * 2;
     const long ldq2 = (long)p.ldq * 2, ldk2 = (long)p.ldk * 2, ldv2 = (long)p.ldv * 2;
+    int qpk[4], kpk[nkc];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) qpk[it] = ht_query_pack(g, it * 16 + r4);
+#pragma unroll
+    for (int it = 0; it < nkc; ++it) kpk[it] = ht_slot_pack(g, it * 16 + r4);
     for (int n = 0; n < my_tiles; ++n) {
       const int tile = chunk + n * nchunks;
       const int stage = n % HF_STAGES;
       mbar_wait(&empty[stage], ((n / HF_STAGES) & 1) ^ 1);
       const uint32_t st = st0 + stage * HF_STAGE_BYTES;
       const HtOrigin org = ht_origin(g, tile * 2 + w);
+      const int base = (org.img * g.Hs + org.y0) * g.Ws + org.x0;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int row = it * 16 + r4;
-        if (row < g.nq) {
-          const int tok = ht_q_token(g, org, row);
+        if (qpk[it] != 0x7fff7fff) {  // rows >= nq stay zero from the prologue
+          const int tok = ht_pack_token(g, org, base, qpk[it]);
           cp_async16(st + (uint32_t)(w * 64 + it * 16) * 128u, qb + (long)(tok < 0 ? 0 : tok) * ldq2, tok >= 0);
         }
       }
+#pragma unroll
       for (int it = 0; it < nkc; ++it) {
-        const int j = it * 16 + r4;
-        if (j < g.nkv) {
-          const int tok = ht_k_token(g, org, j);
+        if (kpk[it] != 0x7fff7fff) {  // slots >= nkv stay zero from the prologue
+          const int tok = ht_pack_token(g, org, base, kpk[it]);
           const long gr = tok < 0 ? 0 : tok;
           const uint32_t ro = (uint32_t)(it * 16) * 128u;
           cp_async16(st + HF_OFF_K + ro, kb + gr * ldk2, tok >= 0);
@@ -174,11 +229,15 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
     }
     cp_async_wait<0>();  // nothing may still be in flight towards this CTA's shared memory at exit
   } else if (warp >= 12) {
-    // ------------------------------------------------------------------ UMMA issuer (warp 12, one thread)
+    // ------------------------------------------------------------------ UMMA issuer (warp 12)
+    // All 32 lanes run the warp-uniform loop; only tcgen05.mma / commit sit under elect.sync, so descriptors live in uniform
+    // registers and a K-step is "previous descriptor + constant" (a single-thread issuer spends ~15 instructions per MMA on
+    // descriptor arithmetic and vector -> uniform moves: the issuer's instruction stream is the critical path of a tile).
     wt_reg_dec<40>();
-    if (warp == 12 && lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, nkc * 16, 0, 0);
+    if (warp == 12) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, nkc * 16, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      const uint64_t dq0 = umma_desc_sw128(smem_u32(sStage), 0, 1024);  // + (byte offset >> 4) addresses any other tile
       int ns = 0, np = 0;  // event-driven: whichever of "next score tile" / "next P.V" has its inputs ready is issued
       WtWatchdog dog;
       dog.reset();
@@ -186,34 +245,41 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
         bool did = false;
         if (ns < my_tiles && ns < np + 2) {
           const int b = ns & 1, stage = ns % HF_STAGES;
-          if (mbar_test(&full[stage], (ns / HF_STAGES) & 1) && mbar_test(&o_free[b], ((ns >> 1) & 1) ^ 1)) {
+          // S(ns) overwrites the S / P columns of tile ns - 2: free once that tile's P.V has completed (its O may still drain)
+          if (mbar_test(&full[stage], (ns / HF_STAGES) & 1) && mbar_test(&o_full[b], ((ns >> 1) & 1) ^ 1)) {
             wt_proxy_fence();  // cp.async (generic proxy) writes -> visible to the tensor core's async-proxy reads
             tc_fence_after();
-            const uint32_t qa = smem_u32(sStage + stage * HF_STAGE_BYTES), ka = qa + HF_OFF_K;
+            const uint64_t dq = dq0 + (uint64_t)((stage * HF_STAGE_BYTES) >> 4), dk = dq + (uint64_t)(HF_OFF_K >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + b * HF_TBUF, umma_desc_sw128(qa + k * 32, 0, 1024),
-                        umma_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-            umma_commit(&s_full[b]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + b * HF_TBUF, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+              umma_commit(&s_full[b]);
+            }
+            __syncwarp();
             ++ns;
             did = true;
           }
         }
         if (np < ns) {
           const int b = np & 1, stage = np % HF_STAGES;
-          if (mbar_test(&p_full[b], (np >> 1) & 1)) {
+          if (mbar_test(&p_full[b], (np >> 1) & 1) && mbar_test(&o_free[b], ((np >> 1) & 1) ^ 1)) {
             tc_fence_after();
-            const uint32_t va = smem_u32(sStage + stage * HF_STAGE_BYTES) + HF_OFF_V;
-            for (int k = 0; k < nkc; ++k)
-              wt_umma_ts(tmem_base + b * HF_TBUF + HF_TO, tmem_base + b * HF_TBUF + k * 8,
-                         umma_desc_sw128(va + k * 2048, 0, 1024), idesc_o, k > 0 ? 1u : 0u);
-            umma_commit(&o_full[b]);
-            umma_commit(&empty[stage]);
+            const uint64_t dv = dq0 + (uint64_t)((stage * HF_STAGE_BYTES + HF_OFF_V) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < nkc; ++k)
+                wt_umma_ts(tmem_base + b * HF_TBUF + HF_TO, tmem_base + b * HF_TBUF + k * 8, dv + (uint64_t)(k * 128), idesc_o,
+                           k > 0 ? 1u : 0u);
+              umma_commit(&o_full[b]);
+              umma_commit(&empty[stage]);
+            }
+            __syncwarp();
             ++np;
             did = true;
           }
         }
-        if (did) dog.reset(); else dog.idle();
+        if (did) dog.reset(); else { dog.idle(); __nanosleep(20); }
       }
     }
   } else {
@@ -224,35 +290,15 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
     const int r = quarter * 32 + lane, w = r >> 6, i = r & 63;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + grpi * HF_TBUF;
     const float sl2 = p.scale * WT_L2E;
-    const uint32_t brow = smem_u32(sBias) + (uint32_t)(i * pitch);
-    const int s7 = i & 7, s3 = i & 3;
+    // bias row of this thread: the address of logical 16-byte chunk c is bx[c & 7] + (c & ~7) * 16 inside whole groups of 8
+    // and bt[c - full8] in a trailing group of 4 (the XOR swizzle folded into per-thread bases, the rest is an immediate)
+    uint32_t bx[8], bt[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bx[k] = smem_u32(sBias) + (uint32_t)(i * pitch) + (uint32_t)((k ^ (i & 7)) << 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bt[k] = smem_u32(sBias) + (uint32_t)(i * pitch) + (uint32_t)((full8 + (k ^ (i & 3))) << 4);
+    const uint64_t sl22 = ht_pk2(sl2, sl2);
     bf16* O = reinterpret_cast<bf16*>(p.o);
-    // one 16-slot unit of the row: x = s * sl2 + bias
-    auto unit_max = [&](const uint32_t (&s)[16], int u, float mx) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 bb = lds_f4(brow + (uint32_t)(ht_bias_chunk(u * 4 + q, full8, s7, s3) << 4));
-        mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(s[q * 4 + 0]), sl2, bb.x), fmaf(__uint_as_float(s[q * 4 + 1]), sl2, bb.y)),
-                             fmaxf(fmaf(__uint_as_float(s[q * 4 + 2]), sl2, bb.z), fmaf(__uint_as_float(s[q * 4 + 3]), sl2, bb.w))));
-      }
-      return mx;
-    };
-    auto unit_prob = [&](const uint32_t (&s)[16], int u, float m, float sum) {
-      uint32_t pk[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 bb = lds_f4(brow + (uint32_t)(ht_bias_chunk(u * 4 + q, full8, s7, s3) << 4));
-        const float p0 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 0]), sl2, bb.x - m));
-        const float p1 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 1]), sl2, bb.y - m));
-        const float p2 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 2]), sl2, bb.z - m));
-        const float p3 = wt_ex2(fmaf(__uint_as_float(s[q * 4 + 3]), sl2, bb.w - m));
-        sum += (p0 + p1) + (p2 + p3);
-        pk[q * 2] = pack_bf16(p0, p1);
-        pk[q * 2 + 1] = pack_bf16(p2, p3);
-      }
-      wt_tmem_st8(t_lane + u * 8, pk);  // P unit u lands in 32-bit columns [8 u, 8 u + 8): below every S column still to be read
-      return sum;
-    };
     for (int n = grpi; n < my_tiles; n += 2) {
       const int tile = chunk + n * nchunks;
       const int grp = tile * 2 + w;
@@ -260,32 +306,59 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
       mbar_wait(&s_full[grpi], (n >> 1) & 1);
       tc_fence_after();
       uint32_t sa[16], sb[16];
-      // pass 1: row maximum (one TMEM load kept in flight)
-      float mx = -INFINITY;
+      // pass 1: row maximum of x = s * sl2 + bias (one TMEM load kept in flight)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
       tmem_ld_32x16(t_lane, sa);
-      for (int u = 0; u < nkc; u += 2) {
+#pragma unroll
+      for (int u = 0; u < nkc; ++u) {
+        uint32_t (&cur)[16] = (u & 1) ? sb : sa;
+        uint32_t (&nxt)[16] = (u & 1) ? sa : sb;
         tmem_ld_wait();
-        if (u + 1 < nkc) tmem_ld_32x16(t_lane + (u + 1) * 16, sb);
-        mx = unit_max(sa, u, mx);
-        if (u + 1 < nkc) {
-          tmem_ld_wait();
-          if (u + 2 < nkc) tmem_ld_32x16(t_lane + (u + 2) * 16, sa);
-          mx = unit_max(sb, u + 1, mx);
+        if (u + 1 < nkc) tmem_ld_32x16(t_lane + (u + 1) * 16, nxt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = u * 4 + q;
+          const float4 bb = lds_f4(c < full8 ? bx[c & 7] + (uint32_t)((c & ~7) << 4) : bt[(c - full8) & 3]);
+          float x0, x1, x2, x3;
+          ht_upk2(ht_fma2(ht_pk2u(cur[q * 4 + 0], cur[q * 4 + 1]), sl22, ht_pk2(bb.x, bb.y)), x0, x1);
+          ht_upk2(ht_fma2(ht_pk2u(cur[q * 4 + 2], cur[q * 4 + 3]), sl22, ht_pk2(bb.z, bb.w)), x2, x3);
+          mx0 = fmaxf(mx0, fmaxf(x0, x1));
+          mx1 = fmaxf(mx1, fmaxf(x2, x3));
         }
       }
+      const float mx = fmaxf(mx0, mx1);
       const float m_use = (mx == -INFINITY) ? 0.f : mx;
-      // pass 2: probabilities
-      float sum = 0.f;
+      const uint64_t nm2 = ht_pk2(-m_use, -m_use);
+      // pass 2: probabilities; P unit u lands in 32-bit columns [8 u, 8 u + 8): below every S column still to be read
+      uint64_t sum2a = 0ull, sum2b = 0ull;
       tmem_ld_32x16(t_lane, sa);
-      for (int u = 0; u < nkc; u += 2) {
+#pragma unroll
+      for (int u = 0; u < nkc; ++u) {
+        uint32_t (&cur)[16] = (u & 1) ? sb : sa;
+        uint32_t (&nxt)[16] = (u & 1) ? sa : sb;
         tmem_ld_wait();
-        if (u + 1 < nkc) tmem_ld_32x16(t_lane + (u + 1) * 16, sb);
-        sum = unit_prob(sa, u, m_use, sum);
-        if (u + 1 < nkc) {
-          tmem_ld_wait();
-          if (u + 2 < nkc) tmem_ld_32x16(t_lane + (u + 2) * 16, sa);
-          sum = unit_prob(sb, u + 1, m_use, sum);
+        if (u + 1 < nkc) tmem_ld_32x16(t_lane + (u + 1) * 16, nxt);
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = u * 4 + q;
+          const float4 bb = lds_f4(c < full8 ? bx[c & 7] + (uint32_t)((c & ~7) << 4) : bt[(c - full8) & 3]);
+          float x0, x1, x2, x3;
+          ht_upk2(ht_fma2(ht_pk2u(cur[q * 4 + 0], cur[q * 4 + 1]), sl22, ht_add2(ht_pk2(bb.x, bb.y), nm2)), x0, x1);
+          ht_upk2(ht_fma2(ht_pk2u(cur[q * 4 + 2], cur[q * 4 + 3]), sl22, ht_add2(ht_pk2(bb.z, bb.w), nm2)), x2, x3);
+          const float p0 = wt_ex2(x0), p1 = wt_ex2(x1), p2 = wt_ex2(x2), p3 = wt_ex2(x3);
+          sum2a = ht_add2(sum2a, ht_pk2(p0, p1));
+          sum2b = ht_add2(sum2b, ht_pk2(p2, p3));
+          pk[q * 2] = pack_bf16(p0, p1);
+          pk[q * 2 + 1] = pack_bf16(p2, p3);
         }
+        wt_tmem_st8(t_lane + u * 8, pk);
+      }
+      float sum;
+      {
+        float a0, a1;
+        ht_upk2(ht_add2(sum2a, sum2b), a0, a1);
+        sum = a0 + a1;
       }
       wt_tmem_st_wait();
       tc_fence_before();
@@ -404,7 +477,7 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
 
   if (warp < 4) {
     // ------------------------------------------------------------------ loaders (128 threads)
-    wt_reg_dec<80>();
+    wt_reg_dec<72>();
     const int tt = threadIdx.x, w = tt >> 6, tl = tt & 63, cc = tl & 3, r4 = tl >> 2;
     const uint32_t ch = (uint32_t)(((w * 4 + cc) ^ (r4 & 7)) << 4);
     const uint32_t kv0 = smem_u32(sKV) + (uint32_t)(w * 64 + r4) * 128u + ch;  // Kpad row (w, r4 + 16 it)
@@ -418,20 +491,28 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
     const char* ob = reinterpret_cast<const char*>(p.o) + colb;
     const long ldq2 = (long)p.ldq * 2, ldk2 = (long)p.ldk * 2, ldv2 = (long)p.ldv * 2, lddo2 = (long)p.lddo * 2,
                ldo2 = (long)p.ldo * 2;
+    int qpk[4], kpk[3][4];
+    const int qpk_side = ht_query_pack(g, tl);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) qpk[it] = ht_query_pack(g, it * 16 + r4);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int it = 0; it < 4; ++it) kpk[c][it] = ht_slot_pack(g, c * 64 + it * 16 + r4);
     // queries of pair pi: rows, lse, token ids
     auto issue_q = [&](int pi) {
       const int qs = pi & 1;
       const int grp = (chunk + pi * nchunks) * 2 + w;
       const HtOrigin org = ht_origin(g, grp);
+      const int base = (org.img * g.Hs + org.y0) * g.Ws + org.x0;
       const uint32_t side = smem_u32(sSide) + (uint32_t)(qs * HB_SIDE_BYTES);
-      const int tok_side = ht_q_token(g, org, tl);
+      const int tok_side = qpk_side != 0x7fff7fff ? ht_pack_token(g, org, base, qpk_side) : -1;
       sts_u32(side + tt * 4, (uint32_t)tok_side);
       if (tok_side >= 0) cp_async4(side + 512 + tt * 4, p.lse + ((long)grp * g.heads + h) * g.nq + tl);
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int row = it * 16 + r4;
-        if (row < g.nq) {  // rows >= nq stay zero from the prologue
-          const int tok = ht_q_token(g, org, row);
+        if (qpk[it] != 0x7fff7fff) {  // rows >= nq stay zero from the prologue
+          const int tok = ht_pack_token(g, org, base, qpk[it]);
           const long gr = tok < 0 ? 0 : tok;
           const uint32_t ro = (uint32_t)(qs * HB_Q_BYTES) + (uint32_t)(it * 16) * 128u;
           cp_async16(q0 + ro, qb + gr * ldq2, tok >= 0);
@@ -459,19 +540,19 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
       }
       const int tok = (int)lds_u32(side + tt * 4);
       const float l = __uint_as_float(lds_u32(side + 512 + tt * 4));
-      sts_f32(side + 512 + tt * 4, tok >= 0 ? l * WT_L2E : INFINITY);
-      sts_f32(side + 1024 + tt * 4, acc);
+      sts_f32(side + 512 + tt * 4, tok >= 0 ? -l * WT_L2E : -INFINITY);  // stored negated: the math warps add
+      sts_f32(side + 1024 + tt * 4, -acc);
       wt_warp_arrive(&q_full[qs], lane);
     };
     // key chunk of tile n: slots [64 c, 64 c + 64) of both blocks; slots outside the image / past nkv are zero-filled
-    auto issue_kv = [&](int n) {
-      const int pi = n / nch, c = n - pi * nch;
-      const int stage = n % HB_KV_STAGES;
+    auto issue_kv = [&](int pi, int c, int stage) {
       const HtOrigin org = ht_origin(g, (chunk + pi * nchunks) * 2 + w);
+      const int base = (org.img * g.Hs + org.y0) * g.Ws + org.x0;
       const uint32_t st = kv0 + stage * HB_KV_BYTES;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int tok = ht_k_token(g, org, c * 64 + it * 16 + r4);
+        const int pk = c == 0 ? kpk[0][it] : (c == 1 ? kpk[1][it] : kpk[2][it]);
+        const int tok = pk != 0x7fff7fff ? ht_pack_token(g, org, base, pk) : -1;
         const long gr = tok < 0 ? 0 : tok;
         const uint32_t ro = (uint32_t)(it * 16) * 128u;
         cp_async16(st + ro, kb + gr * ldk2, tok >= 0);
@@ -480,7 +561,7 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
       cp_async_arrive_noinc(&kv_land[stage]);
     };
     // event-driven (warp-uniform votes): the loaders never block on a load
-    int nk = 0, nqi = 0, nqf = 0;
+    int nk = 0, nk_pi = 0, nk_c = 0, nqi = 0, nqf = 0;
     WtWatchdog dog;
     dog.reset();
     while (nk < my_tiles || nqf < my_pairs) {
@@ -496,21 +577,24 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
         did = true;
       }
       if (nk < my_tiles && __all_sync(0xffffffffu, mbar_test(&kv_empty[nk % 3], ((nk / 3) & 1) ^ 1))) {
-        issue_kv(nk);
+        issue_kv(nk_pi, nk_c, nk % 3);
         ++nk;
+        if (++nk_c == nch) { nk_c = 0; ++nk_pi; }
         did = true;
       }
-      if (did) dog.reset(); else dog.idle();
+      if (did) dog.reset(); else { dog.idle(); __nanosleep(32); }
     }
     cp_async_wait<0>();
   } else if (warp >= 12) {
-    // ------------------------------------------------------------------ UMMA issuer (warp 12, one thread)
-    wt_reg_dec<40>();
-    if (warp == 12 && lane == 0) {
+    // ------------------------------------------------------------------ UMMA issuer (warp 12; warp-uniform, see the forward)
+    wt_reg_dec<56>();
+    if (warp == 12) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 1, 1);
-      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
+      const uint64_t d0 = umma_desc_sw128(smem_u32(smem), 0, 1024);            // + (byte offset >> 4): any tile of the block
+      const uint64_t dsq0 = umma_desc_sw128(smem_u32(sdS), 16384, 1024);       // dS^T read MN-major as the dQ product's A
+      const uint64_t dpa = d0 + (uint64_t)(HB_OFF_P >> 4), dsa = d0 + (uint64_t)(HB_OFF_DS >> 4);
       int ns = 0, ng = 0;          // next score tile / next gradient tile
       int ns_pi = 0, ns_c = 0;     // (pair, chunk) of ns
       int ng_pi = 0, ng_c = 0;
@@ -524,16 +608,18 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
               mbar_test(&s_free[b], ((ns >> 1) & 1) ^ 1)) {
             wt_proxy_fence();  // cp.async / st.shared (generic proxy) writes -> visible to the tensor core's async-proxy reads
             tc_fence_after();
-            const uint32_t ka = smem_u32(sKV + stage * HB_KV_BYTES), qa = smem_u32(sQ + qs * HB_Q_BYTES);
+            const uint64_t dk = d0 + (uint64_t)((stage * HB_KV_BYTES) >> 4), dv = dk + (uint64_t)(16384 >> 4);
+            const uint64_t dq = d0 + (uint64_t)((HB_OFF_Q + qs * HB_Q_BYTES) >> 4), ddo = dq + (uint64_t)(HB_OFF_DO >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + HC_ST + b * 64, umma_desc_sw128(ka + k * 32, 0, 1024),
-                        umma_desc_sw128(qa + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + HC_ST + b * 64, dk + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + HC_DP + b * 64, umma_desc_sw128(ka + 16384 + k * 32, 0, 1024),
-                        umma_desc_sw128(qa + HB_OFF_DO + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-            umma_commit(&s_full[b]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + HC_DP + b * 64, dv + (uint64_t)(k * 2), ddo + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+              umma_commit(&s_full[b]);
+            }
+            __syncwarp();
             ++ns;
             if (++ns_c == nch) { ns_c = 0; ++ns_pi; }
             did = true;
@@ -543,32 +629,32 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
           if (mbar_test(pds_full, ng & 1) && mbar_test(g_free, (ng & 1) ^ 1)) {
             tc_fence_after();
             const int stage = ng % 3, qs = ng_pi & 1;
-            const uint32_t ka = smem_u32(sKV + stage * HB_KV_BYTES), qa = smem_u32(sQ + qs * HB_Q_BYTES);
+            const uint64_t dk = d0 + (uint64_t)((stage * HB_KV_BYTES) >> 4);
+            const uint64_t dq = d0 + (uint64_t)((HB_OFF_Q + qs * HB_Q_BYTES) >> 4), ddo = dq + (uint64_t)(HB_OFF_DO >> 4);
+            const bool last = ng_c == nch - 1;
+            if (elect_one()) {
 #pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2)
-              umma_bf16(tmem_base + HC_DV, umma_desc_sw128(pa + s2 * 32, 0, 1024),
-                        umma_desc_sw128(qa + HB_OFF_DO + s2 * 2048, 0, 1024), idesc_g, s2 > 0 ? 1u : 0u);
+              for (int s2 = 0; s2 < 4; ++s2)
+                umma_bf16(tmem_base + HC_DV, dpa + (uint64_t)(s2 * 2), ddo + (uint64_t)(s2 * 128), idesc_g, s2 > 0 ? 1u : 0u);
 #pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2)
-              umma_bf16(tmem_base + HC_DK, umma_desc_sw128(sa + s2 * 32, 0, 1024),
-                        umma_desc_sw128(qa + s2 * 2048, 0, 1024), idesc_g, s2 > 0 ? 1u : 0u);
+              for (int s2 = 0; s2 < 4; ++s2)
+                umma_bf16(tmem_base + HC_DK, dsa + (uint64_t)(s2 * 2), dq + (uint64_t)(s2 * 128), idesc_g, s2 > 0 ? 1u : 0u);
 #pragma unroll
-            for (int s2 = 0; s2 < 8; ++s2)
-              umma_bf16(tmem_base + HC_DQ, umma_desc_sw128(sa + s2 * 2048, 16384, 1024),
-                        umma_desc_sw128(ka + s2 * 2048, 0, 1024), idesc_q, (ng_c > 0 || s2 > 0) ? 1u : 0u);
-            umma_commit(g_full);
-            umma_commit(pds_free);
-            umma_commit(&kv_empty[stage]);
-            ++ng;
-            if (++ng_c == nch) {
-              ng_c = 0;
-              umma_commit(&q_empty[qs]);
-              ++ng_pi;
+              for (int s2 = 0; s2 < 8; ++s2)
+                umma_bf16(tmem_base + HC_DQ, dsq0 + (uint64_t)(s2 * 128), dk + (uint64_t)(s2 * 128), idesc_q,
+                          (ng_c > 0 || s2 > 0) ? 1u : 0u);
+              umma_commit(g_full);
+              umma_commit(pds_free);
+              umma_commit(&kv_empty[stage]);
+              if (last) umma_commit(&q_empty[qs]);
             }
+            __syncwarp();
+            ++ng;
+            if (++ng_c == nch) { ng_c = 0; ++ng_pi; }
             did = true;
           }
         }
-        if (did) dog.reset(); else dog.idle();
+        if (did) dog.reset(); else { dog.idle(); __nanosleep(20); }
       }
     }
   } else {
@@ -581,11 +667,12 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
     const float sl2 = p.scale * WT_L2E;
     bf16* dQ = reinterpret_cast<bf16*>(p.dq);
     bf16* part = half ? part_k : part_v;
-    float acc[3][32];
+    const uint64_t sl22 = ht_pk2(sl2, sl2);
+    uint64_t acc[3][16];  // bias gradient, packed pairs: [key chunk][query pair of this half]
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int e = 0; e < 32; ++e) acc[c][e] = 0.f;
+      for (int e = 0; e < 16; ++e) acc[c][e] = 0ull;
     long prow = -1;     // partial row of the previous tile (dV / dK drain is deferred by one tile), -1: nothing to store
     int ptok_q = -1;    // dQ row of the previous tile if it closed its pair
     int n = 0;
@@ -637,18 +724,23 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
             for (int c4 = 0; c4 < 4; ++c4) {
               const int c8 = hh * 4 + c4;
               const float4 bb = lds_f4(brow + (uint32_t)(((half * 8 + c8) ^ sx) << 4));
-              const float4 ll = lds_f4(lrow + c8 * 16);
-              const float4 dl = lds_f4(drow + c8 * 16);
-              const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, lv[4] = {ll.x, ll.y, ll.z, ll.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
-              float pv[4], sv[4];
+              const float4 ll = lds_f4(lrow + c8 * 16);   // -lse * log2 e of the four queries
+              const float4 dl = lds_f4(drow + c8 * 16);   // -delta
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                pv[e] = wt_ex2(fmaf(__uint_as_float(st[c4 * 4 + e]), sl2, bv[e]) - lv[e]);
-                sv[e] = pv[e] * (__uint_as_float(dp[c4 * 4 + e]) - dv[e]);
-                acc[c][c8 * 4 + e] += sv[e];
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const uint64_t b2 = e2 ? ht_pk2(bb.z, bb.w) : ht_pk2(bb.x, bb.y);
+                const uint64_t l2 = e2 ? ht_pk2(ll.z, ll.w) : ht_pk2(ll.x, ll.y);
+                const uint64_t d2 = e2 ? ht_pk2(dl.z, dl.w) : ht_pk2(dl.x, dl.y);
+                float x0, x1;
+                ht_upk2(ht_fma2(ht_pk2u(st[c4 * 4 + e2 * 2], st[c4 * 4 + e2 * 2 + 1]), sl22, ht_add2(b2, l2)), x0, x1);
+                const float p0 = wt_ex2(x0), p1 = wt_ex2(x1);
+                const uint64_t sv = ht_mul2(ht_pk2(p0, p1), ht_add2(ht_pk2u(dp[c4 * 4 + e2 * 2], dp[c4 * 4 + e2 * 2 + 1]), d2));
+                acc[c][c8 * 2 + e2] = ht_add2(acc[c][c8 * 2 + e2], sv);
+                float s0, s1;
+                ht_upk2(sv, s0, s1);
+                pp[c4 * 2 + e2] = pack_bf16(p0, p1);
+                dd[c4 * 2 + e2] = pack_bf16(s0, s1);
               }
-              pp[c4 * 2] = pack_bf16(pv[0], pv[1]); pp[c4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
-              dd[c4 * 2] = pack_bf16(sv[0], sv[1]); dd[c4 * 2 + 1] = pack_bf16(sv[2], sv[3]);
             }
             if (hh == 0) mbar_wait(pds_free, (n & 1) ^ 1);  // the previous tile's gradient MMAs no longer read the tiles
 #pragma unroll
@@ -683,7 +775,10 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int i = half * 32 + e;
-            if (i < g.nq && acc[c][e] != 0.f) atomicAdd(&dtab[__ldg(p.pos + i * g.nkv + j)], acc[c][e]);
+            float a0, a1;
+            ht_upk2(acc[c][e >> 1], a0, a1);
+            const float a = (e & 1) ? a1 : a0;
+            if (i < g.nq && a != 0.f) atomicAdd(&dtab[__ldg(p.pos + i * g.nkv + j)], a);
           }
         }
       }
@@ -792,15 +887,20 @@ int vtb_attn_ht_fwd(const vtb_attn_params* p, cudaStream_t stream) {
   static bool attr = false;
   HtGeom g;
   if (int rc = ht_geom(p, &g)) return rc;
+  using Kern = void (*)(vtb_attn_params, HtGeom, int, int);
+  static const Kern kerns[11] = {attn_ht_fwd_kernel<1>, attn_ht_fwd_kernel<2>,  attn_ht_fwd_kernel<3>, attn_ht_fwd_kernel<4>,
+                                 attn_ht_fwd_kernel<5>, attn_ht_fwd_kernel<6>,  attn_ht_fwd_kernel<7>, attn_ht_fwd_kernel<8>,
+                                 attn_ht_fwd_kernel<9>, attn_ht_fwd_kernel<10>, attn_ht_fwd_kernel<11>};
   if (!attr) {
-    VTB_CUDA(cudaFuncSetAttribute(attn_ht_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM));
+    for (int i = 0; i < 11; ++i)
+      VTB_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM));
     attr = true;
   }
   const int ntiles = (g.groups + 1) / 2;
   int nchunks = vtb_num_sms() / p->heads;
   if (nchunks < 1) nchunks = 1;
   if (nchunks > ntiles) nchunks = ntiles;
-  attn_ht_fwd_kernel<<<(unsigned)(nchunks * p->heads), WT_THREADS, HF_SMEM, stream>>>(*p, g, ntiles, nchunks);
+  kerns[g.nkc - 1]<<<(unsigned)(nchunks * p->heads), WT_THREADS, HF_SMEM, stream>>>(*p, g, ntiles, nchunks);
   VTB_LAUNCH_CHECK();
   return 0;
 }
