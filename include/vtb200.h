@@ -170,6 +170,26 @@ int vtb_attention_fwd(const vtb_attn_params* p, vtb_stream_t stream);
 int vtb_attention_bwd(const vtb_attn_params* p, vtb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Validation mode (vtb200.ops.validation_mode(), forward only): the same host path and the same tcgen05 GEMM / LayerNorm
+ * kernels, fed so that a whole-model forward meets the north star's "logits within rtol 1e-3 of the reference's fp32
+ * forward", which bf16 operands cannot (the reference's own autocast run does not either: tests/golden/autocast_levels.json).
+ *   - activations and weights stay fp32 between kernels (vtb_layernorm_fwd with y_f32, fp32 GEMM outputs);
+ *   - vtb_split3_bf16 turns an fp32 operand [rows, K] into bf16 [rows, 3K] = [hi | lo | hi] (A side) or [hi | hi | lo]
+ *     (B side), hi = bf16(x), lo = bf16(x - hi): one vtb_gemm_bf16 call with K' = 3K then accumulates
+ *     a_hi b_hi + a_lo b_hi + a_hi b_lo in fp32 (error ~2^-16 relative per product instead of 2^-8);
+ *   - vtb_attention_fwd_f32: exact-softmax attention on the CUDA cores for every geometry of vtb_attn_params;
+ *     q / k / v / o are FLOAT buffers (leading dimensions in elements), lse optional;
+ *   - vtb_silu_fwd_exact: x / (1 + exp(-x)) without the tanh.approx shortcut; vtb_patch_gather_f32: the patch gather of
+ *     vtb_patch_gather with a float destination.
+ * ---------------------------------------------------------------------------------------------- */
+int vtb_split3_bf16(const float* src, int64_t lds, int64_t rows, int32_t cols, int32_t b_side, void* dst,
+                    vtb_stream_t stream);
+int vtb_attention_fwd_f32(const vtb_attn_params* p, vtb_stream_t stream);
+int vtb_silu_fwd_exact(const float* x, float* y, int64_t n, vtb_stream_t stream);
+int vtb_patch_gather_f32(const float* src, int32_t src_nchw, int32_t c_major, int32_t B, int32_t C, int32_t H,
+                         int32_t W, int32_t p, float* dst, vtb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Small memory-bound helpers.
  * ---------------------------------------------------------------------------------------------- */
 /* fp32 -> bf16 cast (autocast's weight cast, torch.cuda.amp.autocast at train.py:273). */

@@ -105,6 +105,50 @@ def test_full_size_models_match_oracle(family):
     assert worst[1] < 6e-2, worst
 
 
+@pytest.mark.parametrize("family", ["vit_b16", "swin_s", "pvt_small", "halo_t"])
+def test_full_size_validation_mode_logits_within_rtol_1e3(family):
+    """BASELINE.json's full-size models, forward logits at the north star's tolerance: vtb200.ops.validation_mode() (fp32
+    activations between kernels, split-operand tcgen05 GEMMs, exact fp32 attention) against the oracle's fp32 forward
+    (TF32 off), rtol 1e-3 per logit with atol = 1e-4 of the largest logit."""
+    import models
+    from oracle import restate as R
+    from vtb200 import ops
+
+    torch.manual_seed(4)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    if family == "vit_b16":
+        model = _vit_b()
+        fwd = lambda sd, x: R.vit_forward(sd, x, patch=16, depth=12, heads=12,  # noqa: E731
+                                          head_fn=lambda f: R.linear(f, sd["head.weight"], sd["head.bias"]))
+    elif family == "swin_s":
+        kw = dict(image_size=(224, 224), n_class=1000, depths=(2, 2, 18, 2), dims=(96, 192, 384, 768), dim_head=32,
+                  n_heads=(3, 6, 12, 24), dim_ffs=(384, 768, 1536, 3072), window_size=7)
+        model = models.SwinTransformer(**kw)
+        fwd = lambda sd, x: R.swin_forward(sd, x, depths=kw["depths"], n_heads=kw["n_heads"], dim_head=32, window=7)  # noqa: E731
+    elif family == "pvt_small":
+        model = models.PyramidVisionTransformer(224, 1000, 3, (3, 4, 6, 3), (64, 128, 320, 512), (1, 2, 5, 8),
+                                                (512, 1024, 1280, 2048), (8, 4, 2, 1))
+        fwd = lambda sd, x: R.pvt_forward(sd, x, depths=(3, 4, 6, 3), n_heads=(1, 2, 5, 8), reductions=(8, 4, 2, 1))  # noqa: E731
+    else:
+        model = models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
+                                       (384, 768, 1536, 3072), window_size=7, halo_size=3)
+        fwd = lambda sd, x: R.halo_forward(sd, x, depths=(2, 2, 6, 2), n_heads=(3, 6, 12, 24), dim_head=32, window=7,  # noqa: E731
+                                           halo=3)
+    model = R.randomize_(model, 21).cuda().eval()
+    x = torch.randn(2, 3, 224, 224, device="cuda")
+    sd = dict(model.state_dict())
+    with torch.no_grad():
+        want = fwd(sd, x)
+        with ops.validation_mode():
+            out = model(x)
+        bf = model(x)  # the production bf16 path on the same input, for the record
+    err, err_bf = rel(out, want), rel(bf, want)
+    print(f"{family}: validation mode rel-L2 {err:.2e} (bf16 production path {err_bf:.2e})")
+    torch.testing.assert_close(out, want, rtol=1e-3, atol=1e-4 * want.abs().max().item())
+    assert err < 1e-4 and err < err_bf
+
+
 def test_vit_b16_full_size_gradients_match_oracle():
     """Every parameter gradient of the full-size ViT-B/16 (85.8 M parameters, 12 layers, N = 197)
     at B = 8 against fp32 autograd through the oracle restatement on the same device — the full-size gradient check the

@@ -64,6 +64,30 @@ def test_model_matches_reference_golden(name):
     assert worst[1] < GRAD_TOL, worst
 
 
+@pytest.mark.parametrize("name", ["vit_tiny", "vit_multicrop", "swin_w2", "swin_w7", "pvt_tiny", "halo_w2", "halo_w7",
+                                  "twins_w2", "twins_w7"])
+def test_validation_mode_logits_within_rtol_1e3_of_reference(name):
+    """The north star's stated tolerance — forward logits within rtol 1e-3 of the reference's fp32 forward — through
+    vtb200.ops.validation_mode(): same modules / host path / tcgen05 GEMM and LayerNorm kernels, fp32 activations between
+    kernels, 3-way split bf16 GEMM operands (K' = 3K), exact-softmax fp32 attention.  The golden logits come from the
+    unmodified reference (oracle/make_golden.py).  atol covers logits that are themselves ~0: 1e-4 of the largest logit."""
+    from vtb200 import ops
+
+    fx = load_golden(name)
+    model = build(fx).eval()
+    xs = [x.cuda() for x in fx["inputs"]]
+    with torch.no_grad(), ops.validation_mode():
+        out = model(xs if len(xs) > 1 else xs[0])
+    want = fx["output"].cuda()
+    assert out.shape == want.shape and out.dtype == torch.float32
+    torch.testing.assert_close(out, want, rtol=1e-3, atol=1e-4 * want.abs().max().item())
+    assert rel(out, want) < 1e-4, rel(out, want)
+    assert not ops.PRECISE  # the switch does not leak
+    with pytest.raises(RuntimeError):  # forward-only
+        with ops.validation_mode():
+            pass
+
+
 def test_vit_train_mode_droppath_matches_oracle_with_shared_masks(monkeypatch):
     """DropPath masks are drawn by the product (torch RNG, reference call order) and replayed in the oracle."""
     import models

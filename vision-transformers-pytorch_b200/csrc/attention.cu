@@ -2048,6 +2048,76 @@ attn_halo_dkv_kernel(vtb_attn_params p, Geom g, int groups, int nchunks) {
 
 }  // namespace
 
+// =====================================================================================================
+// Validation mode (vtb_attention_fwd_f32): exact-softmax attention in fp32 on the CUDA cores, every geometry of
+// vtb_attn_params (global / shifted window with bias + mask / halo with zero-padded slots).  One warp per (group, head,
+// query): online softmax over the keys, lanes hold the head dimension.  q / k / v / o are FLOAT buffers here (leading
+// dimensions in elements).  Not a fallback of the bf16 kernels: it exists so that the forward of a whole model can be
+// checked against the reference at the north star's rtol 1e-3, which bf16 operands cannot meet.
+// =====================================================================================================
+namespace {
+__global__ void __launch_bounds__(256)
+attn_f32_fwd_kernel(vtb_attn_params p, Geom g, long n_rows) {
+  const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_rows) return;
+  const int i = (int)(wid % g.nq);
+  const long gh = wid / g.nq;
+  const int h = (int)(gh % g.heads);
+  const int grp = (int)(gh / g.heads);
+  const long tq = q_token(g, grp, i);
+  const float* Q = reinterpret_cast<const float*>(p.q);
+  const float* K = reinterpret_cast<const float*>(p.k);
+  const float* V = reinterpret_cast<const float*>(p.v);
+  float* O = reinterpret_cast<float*>(p.o);
+  const bool two = g.dh > 32;
+  const float q0 = Q[tq * p.ldq + h * g.dh + lane];
+  const float q1 = two ? Q[tq * p.ldq + h * g.dh + 32 + lane] : 0.f;
+  const uint8_t* mrow = p.mask ? p.mask + ((long)(grp % p.n_mask) * g.nq + i) * (p.mask_ld ? p.mask_ld : g.nkv) : nullptr;
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < g.nkv; ++j) {
+    if (mrow && mrow[j]) continue;  // masked_fill(-inf): the key drops out of the softmax
+    const long tk = kv_token(g, grp, j);
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;  // zero-padded halo slot: score = bias, value = 0
+    if (tk >= 0) {
+      k0 = K[tk * p.ldk + h * g.dh + lane];
+      v0 = V[tk * p.ldv + h * g.dh + lane];
+      if (two) {
+        k1 = K[tk * p.ldk + h * g.dh + 32 + lane];
+        v1 = V[tk * p.ldv + h * g.dh + 32 + lane];
+      }
+    }
+    float sdot = warp_sum(fmaf(q0, k0, q1 * k1)) * p.scale;
+    if (p.rel_bias) sdot += p.rel_bias[(long)p.pos[(long)i * g.nkv + j] * g.heads + h];
+    const float mn = fmaxf(m, sdot);
+    const float corr = expf(m - mn), pj = expf(sdot - mn);  // m = -inf on the first key: corr = 0
+    l = l * corr + pj;
+    a0 = a0 * corr + pj * v0;
+    a1 = a1 * corr + pj * v1;
+    m = mn;
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  O[tq * p.ldo + h * g.dh + lane] = a0 * inv;
+  if (two) O[tq * p.ldo + h * g.dh + 32 + lane] = a1 * inv;
+  if (p.lse && lane == 0) p.lse[((long)grp * g.heads + h) * g.nq + i] = m + logf(l);
+}
+}  // namespace
+
+extern "C" int vtb_attention_fwd_f32(const vtb_attn_params* p, vtb_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Geom g;
+  long groups;
+  VTB_CHECK(p != nullptr && p->q && p->k && p->v && p->o, -1, "vtb_attention_fwd_f32: null pointer");
+  int rc = make_geom(p, &g, &groups, "vtb_attention_fwd_f32");  // the bf16 layout rules (rows of 8 elements) hold for float rows too
+  if (rc) return rc;
+  const long n_rows = groups * p->heads * p->nq;
+  const long blocks = (n_rows * 32 + 255) / 256;
+  VTB_CHECK(blocks < (1L << 31), -1, "vtb_attention_fwd_f32: grid too large");
+  attn_f32_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*p, g, n_rows);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
 bool vtb_attn_halo_dkv_ok(const vtb_attn_params* p) {
   return p->mode == VTB_ATTN_HALO && !p->dkv_f32 && p->nq <= 64 && p->rel_bias != nullptr && p->n_pos <= MAX_POS &&
          p->delta != nullptr;

@@ -530,6 +530,78 @@ extern "C" int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- validation mode
+// fp32 -> three bf16 column blocks of one GEMM operand row, so that ONE tcgen05 GEMM with K' = 3K accumulates
+//   a_hi b_hi + a_lo b_hi + a_hi b_lo   (hi = bf16(x), lo = bf16(x - hi): ~16 mantissa bits per operand, fp32 accumulation)
+// A side: [hi | lo | hi], B side: [hi | hi | lo].
+namespace {
+__global__ void split3_kernel(const float* __restrict__ src, long lds, long rows, int cols, int b_side,
+                              bf16* __restrict__ dst) {
+  const long total = rows * cols;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / cols;
+    const int c = (int)(e - r * cols);
+    const float x = src[r * lds + c];
+    const bf16 hi = __float2bfloat16_rn(x);
+    const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    bf16* d = dst + r * 3 * cols + c;
+    d[0] = hi;
+    d[cols] = b_side ? hi : lo;
+    d[2 * cols] = b_side ? lo : hi;
+  }
+}
+__global__ void silu_exact_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    const float v = x[e];
+    y[e] = v / (1.f + expf(-v));
+  }
+}
+template <typename T>
+__global__ void patch_gather_f32_kernel(const T* __restrict__ src, int src_nchw, int c_major, PatchGeom g,
+                                        float* __restrict__ dst) {
+  const long total = (long)g.B * g.Ho * g.Wo * g.F;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ff = (int)(i % g.F);
+    const long row = i / g.F;
+    const int bx = (int)(row % g.Wo);
+    const long t = row / g.Wo;
+    const int by = (int)(t % g.Ho);
+    const int b = (int)(t / g.Ho);
+    int c, py, px;
+    if (c_major) { c = ff / (g.p * g.p); const int r = ff - c * g.p * g.p; py = r / g.p; px = r - py * g.p; }
+    else { const int s = ff / g.C; c = ff - s * g.C; py = s / g.p; px = s - py * g.p; }
+    const int y = by * g.p + py, x = bx * g.p + px;
+    const long off = src_nchw ? (((long)b * g.C + c) * g.H + y) * g.W + x : (((long)b * g.H + y) * g.W + x) * g.C + c;
+    dst[i] = src[off];
+  }
+}
+}  // namespace
+
+extern "C" int vtb_split3_bf16(const float* src, int64_t lds, int64_t rows, int32_t cols, int32_t b_side, void* dst,
+                               vtb_stream_t s) {
+  VTB_CHECK(src && dst && rows > 0 && cols > 0 && lds >= cols, -1, "vtb_split3_bf16: bad args");
+  split3_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)s>>>(src, lds, rows, cols, b_side, (bf16*)dst);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_silu_fwd_exact(const float* x, float* y, int64_t n, vtb_stream_t s) {
+  VTB_CHECK(x && y && n > 0, -1, "vtb_silu_fwd_exact: bad args");
+  silu_exact_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)s>>>(x, y, n);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vtb_patch_gather_f32(const float* src, int32_t src_nchw, int32_t c_major, int32_t B, int32_t C, int32_t H,
+                                    int32_t W, int32_t p, float* dst, vtb_stream_t s) {
+  PatchGeom g;
+  int rc = patch_geom("vtb_patch_gather_f32", B, C, H, W, p, &g);
+  if (rc) return rc;
+  VTB_CHECK(src && dst, -1, "vtb_patch_gather_f32: null pointer");
+  const long total = (long)B * g.Ho * g.Wo * g.F;
+  patch_gather_f32_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(src, src_nchw, c_major, g, dst);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int vtb_colsum_bf16(const void* X, int64_t M, int32_t N, int32_t ld, float* out, vtb_stream_t s) {
   VTB_CHECK(X && out && M > 0 && N > 0, -1, "vtb_colsum_bf16: bad args");
   VTB_CHECK(ld % 8 == 0 && ((uintptr_t)X & 15) == 0, -1, "vtb_colsum_bf16: rows must be 16-byte aligned");

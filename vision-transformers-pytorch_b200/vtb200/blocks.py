@@ -125,8 +125,8 @@ class FFNBranchFn(Function):
         y, mean, rstd = ops.layernorm_fwd(x2, ln_w, ln_b, eps)
         w1b, w2b = ops.cast_bf16(_c(w1)), ops.cast_bf16(_c(w2))
         T, FF = x2.shape[0], w1.shape[0]
-        u = torch.empty((T, FF), dtype=BF16, device=x.device)
-        h = torch.empty((T, FF), dtype=BF16, device=x.device)
+        u = torch.empty((T, FF), dtype=ops.act_dtype(), device=x.device)
+        h = torch.empty((T, FF), dtype=ops.act_dtype(), device=x.device)
         ops.gemm(y, w1b, out=u, out2=h, bias=b1, epilogue=_l.EPI_SILU_DUAL)
         out = ops.gemm(h, w2b, out_dtype=F32, bias=b2, resid=x2, row_scale=dp_scale,
                        rows_per_scale=rows_per_sample)

@@ -23,6 +23,7 @@ SYMBOLS = [
     "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss", "vtb_mt_num_chunks", "vtb_mt_cast_f32_bf16", "vtb_mt_ema",
     "vtb_mt_grad_norm", "vtb_mt_scale", "vtb_mt_agc", "vtb_mt_adamw", "vtb_mix_loss", "vtb_l2norm_fwd", "vtb_l2norm_bwd",
     "vtb_weight_norm_fwd", "vtb_weight_norm_bwd", "vtb_gelu_fwd", "vtb_gelu_bwd", "vtb_input_batch",
+    "vtb_split3_bf16", "vtb_attention_fwd_f32", "vtb_silu_fwd_exact", "vtb_patch_gather_f32",
 ]
 
 
@@ -98,6 +99,10 @@ def load():
     lib.vtb_attention_bwd.argtypes = [C.POINTER(AttnParams), vp]
     lib.vtb_attention_bwd_workspace_bytes.argtypes = [C.POINTER(AttnParams)]
     lib.vtb_attention_bwd_workspace_bytes.restype = i64
+    lib.vtb_attention_fwd_f32.argtypes = [C.POINTER(AttnParams), vp]
+    lib.vtb_split3_bf16.argtypes = [vp, i64, i64, i32, i32, vp, vp]
+    lib.vtb_silu_fwd_exact.argtypes = [vp, vp, i64, vp]
+    lib.vtb_patch_gather_f32.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.vtb_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
     lib.vtb_cast_f32_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i32, vp]
     lib.vtb_scale_cast_bf16.argtypes = [vp, vp, i32, i64, i32, vp, vp]

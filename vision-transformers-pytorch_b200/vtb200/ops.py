@@ -110,6 +110,64 @@ def _chk2d(t, dtype, name):
                          f"{t.dtype} {tuple(t.shape)} strides {t.stride()} on {t.device}")
 
 
+# ------------------------------------------------------------------------------------------------ validation mode
+# Forward-only switch for parity checks at the north star's tolerance (logits within rtol 1e-3 of the reference's fp32
+# forward): activations and weights stay fp32 between kernels, every GEMM runs on the same tcgen05 kernel with 3-way split
+# bf16 operands (K' = 3K: a_hi b_hi + a_lo b_hi + a_hi b_lo accumulated in fp32), attention runs the exact-softmax fp32
+# kernel, SiLU without the tanh.approx shortcut.  See include/vtb200.h ("Validation mode").
+PRECISE = False
+
+
+class validation_mode:
+    """with vtb200.ops.validation_mode(): logits = model(x)   — requires torch.no_grad()."""
+
+    def __enter__(self):
+        global PRECISE
+        if torch.is_grad_enabled():
+            raise RuntimeError("vtb200 validation mode is forward-only: enter it under torch.no_grad()")
+        self._prev, PRECISE = PRECISE, True
+        return self
+
+    def __exit__(self, *exc):
+        global PRECISE
+        PRECISE = self._prev
+        return False
+
+
+def act_dtype():
+    """dtype of the activations that travel between kernels (GEMM operands, attention inputs)."""
+    return F32 if PRECISE else BF16
+
+
+def split3(x, b_side):
+    """fp32 [rows, K] (row-strided view allowed) -> bf16 [rows, 3K]: [hi | lo | hi] (A side) or [hi | hi | lo] (B side)."""
+    lib = _l.get()
+    _chk2d(x, F32, "split3")
+    rows, K = x.shape
+    dst = torch.empty((rows, 3 * K), dtype=BF16, device=x.device)
+    with _prof("split3_bf16"):
+        _l.check(lib.vtb_split3_bf16(_p(x), x.stride(0), rows, K, int(b_side), _p(dst), _stream()), lib)
+    _count()
+    return dst
+
+
+def _gemm_precise(a, b, *, out, bias, resid, row_scale, rows_per_scale, epilogue, out2):
+    """C = A B^T (+ epilogue) with fp32 operands through the split-operand tcgen05 GEMM; C is fp32."""
+    if a.dtype != F32 or b.dtype != F32:
+        raise ValueError("vtb200.gemm (validation mode): fp32 operands expected")
+    if out is not None and out.dtype != F32:
+        raise ValueError("vtb200.gemm (validation mode): fp32 output expected")
+    a3, b3 = split3(a, False), split3(b, True)
+    if epilogue == _l.EPI_SILU_DUAL:  # out = pre-activation, out2 = SiLU(out): exact SiLU as its own pass
+        pre = gemm(a3, b3, out=out, out_dtype=F32, bias=bias)
+        if out2 is not None:
+            silu_fwd(pre, out=out2)
+        return pre
+    if epilogue != _l.EPI_NONE:
+        raise ValueError("vtb200.gemm (validation mode): forward epilogues only")
+    return gemm(a3, b3, out=out, out_dtype=F32, bias=bias, resid=resid, row_scale=row_scale, rows_per_scale=rows_per_scale)
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, resid=None,
          row_scale=None, rows_per_scale=0, epilogue=_l.EPI_NONE, aux=None, out2=None, accumulate=False,
          splits=0, alpha=1.0, a_colsum=None):
@@ -119,6 +177,11 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
     (leading stride may exceed the row length: views into wider buffers are fine).
     """
     lib = _l.get()
+    if PRECISE and (a.dtype == F32 or b.dtype == F32):
+        if a_mn or b_mn or aux is not None or accumulate or a_colsum is not None or alpha != 1.0:
+            raise ValueError("vtb200.gemm (validation mode): forward products only")
+        return _gemm_precise(a, b, out=out, bias=bias, resid=resid, row_scale=row_scale, rows_per_scale=rows_per_scale,
+                             epilogue=epilogue, out2=out2)
     _chk2d(a, BF16, "gemm(a)")
     _chk2d(b, BF16, "gemm(b)")
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -189,6 +252,8 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, patchify=None, rowmod_
         Cc = x.shape[-1]
         cols = s * s * Cc
         rows = x.numel() // cols
+    if PRECISE:
+        out_dtype = F32
     y = torch.empty((rows, cols), dtype=out_dtype, device=x.device)
     mean = torch.empty(rows, dtype=F32, device=x.device)
     rstd = torch.empty(rows, dtype=F32, device=x.device)
@@ -293,9 +358,31 @@ def _qkv_fill(p, q, k, v):
     p.v, p.ldv = v.data_ptr(), v.stride(0)
 
 
+def _attention_fwd_precise(spec, q, k, v):
+    """Validation mode: fp32 q / k / v views -> fp32 o (exact softmax on the CUDA cores, same geometry descriptor)."""
+    lib = _l.get()
+    p = _l.AttnParams()
+    spec.fill(p)
+    p.mask_bits = None
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk2d(t, F32, f"attention({nm}, validation mode)")
+    p.q, p.ldq = q.data_ptr(), q.stride(0)
+    p.k, p.ldk = k.data_ptr(), k.stride(0)
+    p.v, p.ldv = v.data_ptr(), v.stride(0)
+    o = torch.empty((q.shape[0], spec.heads * spec.dh), dtype=F32, device=q.device)
+    lse = torch.empty((spec.groups, spec.heads, spec.nq), dtype=F32, device=q.device)
+    p.o, p.ldo, p.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
+    with _prof("attention_fwd_f32"):
+        _l.check(lib.vtb_attention_fwd_f32(C.byref(p), _stream()), lib)
+    _count()
+    return o, lse
+
+
 def attention_fwd(spec, q, k, v):
     """q [Tq, >=H*dh], k/v [Tkv, >=H*dh] bf16 views (row-major). Returns o [Tq, H*dh] bf16, lse."""
     lib = _l.get()
+    if PRECISE:
+        return _attention_fwd_precise(spec, q, k, v)
     p = _l.AttnParams()
     spec.fill(p)
     _qkv_fill(p, q, k, v)
@@ -350,6 +437,8 @@ def cast_bf16(src):
     lib = _l.get()
     if src.dtype != F32 or not src.is_contiguous():
         raise ValueError("vtb200.cast_bf16: contiguous f32 expected")
+    if PRECISE:
+        return src  # validation mode: weights reach the GEMM in fp32 and are split there
     if WEIGHT_LOOKUP is not None:
         hit = WEIGHT_LOOKUP(src)
         if hit is not None:
@@ -383,6 +472,8 @@ def scale_cast_bf16(src, row_scale=None, rows_per_scale=0):
         raise ValueError("vtb200.scale_cast_bf16: contiguous f32 expected")
     cols = src.shape[-1]
     rows = src.numel() // cols
+    if PRECISE and row_scale is None:
+        return src.view(rows, cols)  # validation mode: the operand stays fp32
     dst = torch.empty((rows, cols), dtype=BF16, device=src.device)
     with _prof("scale_cast_bf16"):
         _l.check(lib.vtb_scale_cast_bf16(_p(src), _p(row_scale), rows_per_scale, rows, cols, _p(dst),
@@ -424,6 +515,14 @@ def patch_gather(src, *, nchw, c_major, B, Cc, H, W, p):
     if not src.is_contiguous() or src.dtype not in (F32, BF16):
         raise ValueError("vtb200.patch_gather: contiguous f32/bf16 expected")
     rows = B * (H // p) * (W // p)
+    if PRECISE:
+        if src.dtype != F32:
+            raise ValueError("vtb200.patch_gather (validation mode): f32 source expected")
+        dst = torch.empty((rows, p * p * Cc), dtype=F32, device=src.device)
+        with _prof("patch_gather_f32"):
+            _l.check(lib.vtb_patch_gather_f32(_p(src), int(nchw), int(c_major), B, Cc, H, W, p, _p(dst), _stream()), lib)
+        _count()
+        return dst
     dst = torch.empty((rows, p * p * Cc), dtype=BF16, device=src.device)
     with _prof("patch_gather"):
         _l.check(lib.vtb_patch_gather(_p(src), int(src.dtype == BF16), int(nchw), int(c_major), B, Cc, H, W,
@@ -487,11 +586,14 @@ def mean_rows_bwd(dy, groups, n, cols):
     return dx
 
 
-def silu_fwd(x):
+def silu_fwd(x, out=None):
     lib = _l.get()
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
+    if y.dtype != F32 or x.dtype != F32 or not y.is_contiguous() or not x.is_contiguous() or y.numel() != x.numel():
+        raise ValueError("vtb200.silu_fwd: contiguous f32 tensors of one size expected")
     with _prof("silu_fwd"):
-        _l.check(lib.vtb_silu_fwd(_p(x), _p(y), x.numel(), _stream()), lib)
+        fn = lib.vtb_silu_fwd_exact if PRECISE else lib.vtb_silu_fwd
+        _l.check(fn(_p(x), _p(y), x.numel(), _stream()), lib)
     _count()
     return y
 
