@@ -392,6 +392,8 @@ attn_ht_fwd_kernel(vtb_attn_params p, HtGeom g, int ntiles, int nchunks) {
 //   P^T = exp2(S^T sl2 + bias - lse2[i]),  dS^T = P^T (dP^T - delta[i])   -> bf16 tiles in shared memory
 //   dV[(w,jj), (w',d)] = P^T . dOcat    dK = dS^T . Qcat   (complete per chunk -> per-block partial rows)
 //   dQ[i, (w,d)]      += dS . Kpad      (accumulates over the chunks of the pair, drained after the last one)
+//   P^T and dS^T go back into TMEM (bf16 pairs over S^T / dP^T) and feed dV / dK as TMEM A operands; dS^T is also written
+//   to one of two shared-memory buffers for dQ — so the math of tile n + 1 never waits for the gradient MMAs of tile n.
 // TMEM: S^T 2 x 64 | dP^T 2 x 64 | dV 64 | dK 64 | dQ 64.   Rings: 3 key/value chunk stages (Kpad 16 KB | Vpad 16 KB),
 // 2 query stages (Qcat 8 KB | dOcat 8 KB | O rows 8 KB for delta) loaded once per pair.
 // ---------------------------------------------------------------------------------------------------------------
@@ -410,13 +412,14 @@ static_assert(HB_SMEM <= 232448, "backward shared memory");
 constexpr uint32_t HC_ST = 0, HC_DP = 128, HC_DV = 256, HC_DK = 320, HC_DQ = 384;
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
-attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* part_k, bf16* part_v) {
+attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* part_k, bf16* part_v, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sKV = smem;
   uint8_t* sQ = smem + HB_OFF_Q;
-  uint8_t* sdS = smem + HB_OFF_DS;   // [128 key rows][64 queries] bf16, 128B-swizzled
-  uint8_t* sP = smem + HB_OFF_P;     // directly behind dS^T: the dQ product's second M atom lands here
+  uint8_t* sdS = smem + HB_OFF_DS;   // [2][128 key rows][64 queries] bf16, 128B-swizzled: dS^T of tile n in buffer n & 1 (the
+                                     // dQ product reads it MN-major; its don't-care second M atom lands 16 KB further on)
+  uint8_t* sP = smem + HB_OFF_P;     // = buffer 1 of sdS; scratch for the bias tables before / after the tile loop
   uint8_t* sBias = smem + HB_OFF_BIAS;
   uint8_t* sSide = smem + HB_OFF_SIDE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HB_OFF_BARS);
@@ -426,9 +429,8 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
   uint64_t* q_full = bars + 8;      // [2] count 4: delta / lse of the landed pair in place
   uint64_t* q_empty = bars + 10;    // [2] gradient MMAs of the pair's last chunk retired
   uint64_t* s_full = bars + 12;     // [2] S^T / dP^T complete
-  uint64_t* s_free = bars + 14;     // [2] read out of TMEM (8 warps)
-  uint64_t* pds_full = bars + 16;   // P^T / dS^T tiles written (8 warps)
-  uint64_t* pds_free = bars + 17;   // ... and consumed by the gradient MMAs
+  uint64_t* s_free = bars + 14;     // [2] the gradient MMAs of the tile have consumed P^T / dS^T (TMEM columns + sdS buffer)
+  uint64_t* pds_full = bars + 16;   // [2] P^T / dS^T of the tile written (8 warps)
   uint64_t* g_full = bars + 18;     // dV / dK (/ dQ) complete
   uint64_t* g_free = bars + 19;     // ... and drained (8 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
@@ -445,9 +447,9 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
     for (int i = 0; i < 3; ++i) { mbar_init(&kv_land[i], 128); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_land[i], 128); mbar_init(&q_full[i], 4); mbar_init(&q_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 1); mbar_init(&pds_full[i], 8);
     }
-    mbar_init(pds_full, 8); mbar_init(pds_free, 1); mbar_init(g_full, 1); mbar_init(g_free, 8);
+    mbar_init(g_full, 1); mbar_init(g_free, 8);
     mbar_fence_init();
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
@@ -555,6 +557,7 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
         const int tok = pk != 0x7fff7fff ? ht_pack_token(g, org, base, pk) : -1;
         const long gr = tok < 0 ? 0 : tok;
         const uint32_t ro = (uint32_t)(it * 16) * 128u;
+        if (dbg & 2) continue;
         cp_async16(st + ro, kb + gr * ldk2, tok >= 0);
         cp_async16(st + 16384 + ro, vb + gr * ldv2, tok >= 0);
       }
@@ -594,7 +597,6 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 1, 1);
       const uint64_t d0 = umma_desc_sw128(smem_u32(smem), 0, 1024);            // + (byte offset >> 4): any tile of the block
       const uint64_t dsq0 = umma_desc_sw128(smem_u32(sdS), 16384, 1024);       // dS^T read MN-major as the dQ product's A
-      const uint64_t dpa = d0 + (uint64_t)(HB_OFF_P >> 4), dsa = d0 + (uint64_t)(HB_OFF_DS >> 4);
       int ns = 0, ng = 0;          // next score tile / next gradient tile
       int ns_pi = 0, ns_c = 0;     // (pair, chunk) of ns
       int ng_pi = 0, ng_c = 0;
@@ -611,9 +613,11 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
             const uint64_t dk = d0 + (uint64_t)((stage * HB_KV_BYTES) >> 4), dv = dk + (uint64_t)(16384 >> 4);
             const uint64_t dq = d0 + (uint64_t)((HB_OFF_Q + qs * HB_Q_BYTES) >> 4), ddo = dq + (uint64_t)(HB_OFF_DO >> 4);
             if (elect_one()) {
+              if (!(dbg & 16))
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(tmem_base + HC_ST + b * 64, dk + (uint64_t)(k * 2), dq + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+              if (!(dbg & 16))
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(tmem_base + HC_DP + b * 64, dv + (uint64_t)(k * 2), ddo + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
@@ -626,25 +630,32 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
           }
         }
         if (ng < ns) {
-          if (mbar_test(pds_full, ng & 1) && mbar_test(g_free, (ng & 1) ^ 1)) {
+          const int b = ng & 1;
+          if (mbar_test(&pds_full[b], (ng >> 1) & 1) && mbar_test(g_free, (ng & 1) ^ 1)) {
             tc_fence_after();
             const int stage = ng % 3, qs = ng_pi & 1;
             const uint64_t dk = d0 + (uint64_t)((stage * HB_KV_BYTES) >> 4);
             const uint64_t dq = d0 + (uint64_t)((HB_OFF_Q + qs * HB_Q_BYTES) >> 4), ddo = dq + (uint64_t)(HB_OFF_DO >> 4);
             const bool last = ng_c == nch - 1;
             if (elect_one()) {
+              if (!(dbg & 8)) {
+#pragma unroll
+              // dV = P^T dO, dK = dS^T Q: A straight from TMEM (bf16 pairs over the S^T / dP^T columns each math thread has
+              // read: queries [32 half + 16 hh, +16) sit in columns 32 half + 8 hh), dQ += dS K from the shared-memory copy
+              for (int s2 = 0; s2 < 4; ++s2)
+                wt_umma_ts(tmem_base + HC_DV, tmem_base + HC_ST + b * 64 + (s2 >> 1) * 32 + (s2 & 1) * 8,
+                           ddo + (uint64_t)(s2 * 128), idesc_g, s2 > 0 ? 1u : 0u);
 #pragma unroll
               for (int s2 = 0; s2 < 4; ++s2)
-                umma_bf16(tmem_base + HC_DV, dpa + (uint64_t)(s2 * 2), ddo + (uint64_t)(s2 * 128), idesc_g, s2 > 0 ? 1u : 0u);
-#pragma unroll
-              for (int s2 = 0; s2 < 4; ++s2)
-                umma_bf16(tmem_base + HC_DK, dsa + (uint64_t)(s2 * 2), dq + (uint64_t)(s2 * 128), idesc_g, s2 > 0 ? 1u : 0u);
+                wt_umma_ts(tmem_base + HC_DK, tmem_base + HC_DP + b * 64 + (s2 >> 1) * 32 + (s2 & 1) * 8,
+                           dq + (uint64_t)(s2 * 128), idesc_g, s2 > 0 ? 1u : 0u);
 #pragma unroll
               for (int s2 = 0; s2 < 8; ++s2)
-                umma_bf16(tmem_base + HC_DQ, dsq0 + (uint64_t)(s2 * 128), dk + (uint64_t)(s2 * 128), idesc_q,
+                umma_bf16(tmem_base + HC_DQ, dsq0 + (uint64_t)(b * 1024 + s2 * 128), dk + (uint64_t)(s2 * 128), idesc_q,
                           (ng_c > 0 || s2 > 0) ? 1u : 0u);
+              }
               umma_commit(g_full);
-              umma_commit(pds_free);
+              umma_commit(&s_free[b]);
               umma_commit(&kv_empty[stage]);
               if (last) umma_commit(&q_empty[qs]);
             }
@@ -686,7 +697,8 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
       tmem_ld_wait();
       tc_fence_before();
       wt_warp_arrive(g_free, lane);
-      if (row >= 0) wt_store_row32(part + row * 32, a, half ? p.scale : 1.f);
+      if (dbg & 1) return;
+      if (row >= 0) wt_store_row32_raw(part + row * 32, a);  // dK partials leave unscaled: the per-token sum applies the softmax scale
       if (last && quarter < 2 && tok_q >= 0) wt_store_row32(dQ + (long)tok_q * p.lddq + h * 32, bq, p.scale);
     };
 
@@ -715,11 +727,11 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
             tmem_ld_32x16(t_lane + HC_ST + b * 64 + half * 32 + hh * 16, st);
             tmem_ld_32x16(t_lane + HC_DP + b * 64 + half * 32 + hh * 16, dp);
             tmem_ld_wait();
-            if (hh == 1) {
-              tc_fence_before();
-              wt_warp_arrive(&s_free[b], lane);
-            }
             uint32_t pp[8], dd[8];
+            if (dbg & 4) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { pp[e] = st[e]; dd[e] = dp[e]; }
+            } else
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const int c8 = hh * 4 + c4;
@@ -742,16 +754,20 @@ attn_ht_bwd_kernel(vtb_attn_params p, HtGeom g, int npairs, int nchunks, bf16* p
                 dd[c4 * 2 + e2] = pack_bf16(s0, s1);
               }
             }
-            if (hh == 0) mbar_wait(pds_free, (n & 1) ^ 1);  // the previous tile's gradient MMAs no longer read the tiles
+            // P^T / dS^T (bf16 pairs) back into TMEM over the columns just read; dS^T also into this tile's shared buffer.
+            // Both were last read by the gradient MMAs of tile n - 2, which completed before scores(n) were issued.
+            wt_tmem_st8(t_lane + HC_ST + b * 64 + half * 32 + hh * 8, pp);
+            wt_tmem_st8(t_lane + HC_DP + b * 64 + half * 32 + hh * 8, dd);
 #pragma unroll
             for (int q2 = 0; q2 < 2; ++q2) {
-              const uint32_t off = sw128(r, half * 4 + hh * 2 + q2);
-              sts_u4(smem_u32(sP) + off, pp[q2 * 4], pp[q2 * 4 + 1], pp[q2 * 4 + 2], pp[q2 * 4 + 3]);
+              const uint32_t off = (uint32_t)(b * 16384) + sw128(r, half * 4 + hh * 2 + q2);
               sts_u4(smem_u32(sdS) + off, dd[q2 * 4], dd[q2 * 4 + 1], dd[q2 * 4 + 2], dd[q2 * 4 + 3]);
             }
           }
+          wt_tmem_st_wait();
+          tc_fence_before();
           wt_proxy_fence();
-          wt_warp_arrive(pds_full, lane);
+          wt_warp_arrive(&pds_full[b], lane);
           if (n > 0) epilogue(n - 1, prow, ptok_q, ptok_q != -2);
           prow = (j < g.nkv && grp < g.groups) ? (((long)grp * g.heads + h) * g.nkv + j) : -1;
           ptok_q = (c == nch - 1) ? tok_q : -2;  // -2: the pair is not finished, dQ keeps accumulating
@@ -823,19 +839,37 @@ attn_ht_dkv_reduce_kernel(vtb_attn_params p, HtGeom g, const bf16* __restrict__ 
     float s[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) s[q] = 0.f;
-    for (int by = by_lo; by <= by_hi; ++by)
-      for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-        const long grp = (long)b * g.nb + by * g.nbx + bx;
-        const int j = (y - by * W + HL) * g.kw + (x - bx * W + HL);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(part + ((grp * g.heads + h) * g.nkv + j) * 32 + cc * 8));
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    auto row_of = [&](int by, int bx) {
+      const long grp = (long)b * g.nb + by * g.nbx + bx;
+      const int j = (y - by * W + HL) * g.kw + (x - bx * W + HL);
+      return reinterpret_cast<const uint4*>(part + ((grp * g.heads + h) * g.nkv + j) * 32 + cc * 8);
+    };
+    auto add = [&](const uint4& v) {
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = unpack_bf16(wv[q]);
-          s[q * 2] += f.x;
-          s[q * 2 + 1] += f.y;
-        }
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16(wv[q]);
+        s[q * 2] += f.x;
+        s[q * 2 + 1] += f.y;
       }
+    };
+    if (by_hi - by_lo <= 1 && bx_hi - bx_lo <= 1) {
+      // the usual case (halo <= window): at most 2 x 2 covering blocks — all loads in flight before the first add
+      const bool y2 = by_hi > by_lo, x2 = bx_hi > bx_lo;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      const uint4 v00 = __ldg(row_of(by_lo, bx_lo));
+      const uint4 v01 = x2 ? __ldg(row_of(by_lo, bx_hi)) : z;
+      const uint4 v10 = y2 ? __ldg(row_of(by_hi, bx_lo)) : z;
+      const uint4 v11 = (y2 && x2) ? __ldg(row_of(by_hi, bx_hi)) : z;
+      add(v00); add(v01); add(v10); add(v11);
+    } else {
+      for (int by = by_lo; by <= by_hi; ++by)
+        for (int bx = bx_lo; bx <= bx_hi; ++bx) add(__ldg(row_of(by, bx)));
+    }
+    if (!kv) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] *= p.scale;
+    }
     bf16* dst = kv ? reinterpret_cast<bf16*>(p.dv) + tok * p.lddv : reinterpret_cast<bf16*>(p.dk) + tok * p.lddk;
     *reinterpret_cast<uint4*>(dst + h * 32 + cc * 8) =
         make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
@@ -843,6 +877,8 @@ attn_ht_dkv_reduce_kernel(vtb_attn_params p, HtGeom g, const bf16* __restrict__ 
 }
 
 bool g_attn_ht = true;
+int g_ht_dbg = 0;  // vtb_set_option("attn_ht_dbg", bits): timing experiments on the backward kernel (results are garbage):
+                  // 1 no global stores, 2 no K/V copies, 4 no softmax math, 8 no gradient MMAs, 16 no score MMAs, 32 no reduce kernel
 
 int ht_geom(const vtb_attn_params* p, HtGeom* g) {
   g->heads = p->heads; g->nq = p->nq; g->nkv = p->nkv; g->Hs = p->Hs; g->Ws = p->Ws;
@@ -863,6 +899,7 @@ int ht_geom(const vtb_attn_params* p, HtGeom* g) {
 }  // namespace
 
 void vtb_attn_ht_set(bool on) { g_attn_ht = on; }
+void vtb_attn_ht_dbg_set(int bits) { g_ht_dbg = bits; }
 
 size_t vtb_attn_ht_ws_bytes(const vtb_attn_params* p) {
   const long groups = (long)p->batch * (p->Hs / p->window) * (p->Ws / p->window);
@@ -919,11 +956,12 @@ int vtb_attn_ht_bwd(const vtb_attn_params* p, cudaStream_t stream) {
   if (nchunks > npairs) nchunks = npairs;
   bf16* part_k = reinterpret_cast<bf16*>(p->ws);
   bf16* part_v = part_k + (size_t)g.groups * p->heads * p->nkv * 32;
-  attn_ht_bwd_kernel<<<(unsigned)(nchunks * p->heads), WT_THREADS, HB_SMEM, stream>>>(*p, g, npairs, nchunks, part_k, part_v);
+  attn_ht_bwd_kernel<<<(unsigned)(nchunks * p->heads), WT_THREADS, HB_SMEM, stream>>>(*p, g, npairs, nchunks, part_k, part_v, g_ht_dbg);
   VTB_LAUNCH_CHECK();
+  if (g_ht_dbg & 32) return 0;
   const long total = 2L * p->batch * p->Hs * p->Ws * p->heads * 4;
   long blocks = (total + 255) / 256;
-  const long cap = (long)vtb_num_sms() * 16;
+  const long cap = (long)vtb_num_sms() * 32;
   if (blocks > cap) blocks = cap;
   attn_ht_dkv_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*p, g, part_k, part_v, total);
   VTB_LAUNCH_CHECK();

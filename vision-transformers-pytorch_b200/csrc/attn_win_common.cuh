@@ -95,6 +95,16 @@ __device__ __forceinline__ void wt_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 template <int N> __device__ __forceinline__ void wt_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void wt_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void wt_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 32 fp32 -> bf16 -> 64 contiguous bytes of global memory (no scaling)
+__device__ __forceinline__ void wt_store_row32_raw(bf16* dst, const uint32_t (&a)[32]) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 8)
+    *reinterpret_cast<uint4*>(dst + e) =
+        make_uint4(pack_bf16(__uint_as_float(a[e]), __uint_as_float(a[e + 1])),
+                   pack_bf16(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3])),
+                   pack_bf16(__uint_as_float(a[e + 4]), __uint_as_float(a[e + 5])),
+                   pack_bf16(__uint_as_float(a[e + 6]), __uint_as_float(a[e + 7])));
+}
 // release a barrier once per warp after every lane is done
 __device__ __forceinline__ void wt_warp_arrive(uint64_t* bar, int lane) {
   __syncwarp();

@@ -808,6 +808,7 @@ void vtb_attn_tc_version_set(int fwd, int bwd);
 void vtb_attn_wp_set(bool on);
 void vtb_attn_wt_set(bool on);
 void vtb_attn_ht_set(bool on);
+void vtb_attn_ht_dbg_set(int bits);
 void vtb_ln_stream_set(bool on);
 void vtb_input_variant_set(int v);
 
@@ -821,6 +822,7 @@ extern "C" int vtb_set_option(const char* name, int32_t value) {
   if (strcmp(name, "attn_wp") == 0) { vtb_attn_wp_set(value != 0); return 0; }
   if (strcmp(name, "attn_wt") == 0) { vtb_attn_wt_set(value != 0); return 0; }
   if (strcmp(name, "attn_ht") == 0) { vtb_attn_ht_set(value != 0); return 0; }
+  if (strcmp(name, "attn_ht_dbg") == 0) { vtb_attn_ht_dbg_set(value); return 0; }
   if (strcmp(name, "ln_stream") == 0) { vtb_ln_stream_set(value != 0); return 0; }
   vtb_set_error("vtb_set_option: unknown option '%s'", name);
   return -1;
