@@ -361,7 +361,7 @@ input_batch_kernel2(const uint8_t* __restrict__ src, int n_src, const int32_t* _
   }
 }
 
-int g_input_variant = 1;  // 1: first kernel; 2: the lean one; 3: lean, 8 pixels per thread (vtb_set_option("input_variant", v))
+int g_input_variant = 2;  // 1: first kernel; 2: the lean one (default: 5-17 % faster on the B200, profiles/r02_input_variants.log); 3: lean, 8 pixels per thread (vtb_set_option("input_variant", v))
 
 }  // namespace
 
