@@ -183,6 +183,53 @@ def test_autocast_and_grad_dtype_contract():
     assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in model.parameters())
 
 
+def test_fp16_autocast_with_grad_scaler_steps_like_the_unscaled_run():
+    """The reference's mixed-precision step (train.py:169, 273-298): fp16 autocast + amp.GradScaler + clip_grad_norm_ +
+    scaler.step / update.  The drop-in modules compute in bf16 / fp32 whatever the autocast dtype is, so the scaled step
+    must (a) keep fp32 outputs and gradients, (b) never produce inf / nan that would make the scaler skip the step, and
+    (c) land on the same weights as an unscaled step from the same start (gradients are linear in the loss scale)."""
+    import copy
+
+    import torch.nn.functional as F
+
+    fx = load_golden("swin_w7")
+    base = build(fx).train()
+    x = fx["inputs"][0].cuda()
+    target = torch.tensor([3], device="cuda")
+
+    def one_step(model, scaler):
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=scaler is not None):
+            out = model(x)
+            loss = F.cross_entropy(out, target)
+        assert out.dtype == torch.float32
+        if scaler is None:
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            opt.step()
+        else:
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            scaler.step(opt)
+            scaler.update()
+        return loss.item()
+
+    plain, scaled = copy.deepcopy(base), copy.deepcopy(base)
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 12)
+    l0, l1 = one_step(plain, None), one_step(scaled, scaler)
+    assert abs(l0 - l1) <= 1e-6 * max(1.0, abs(l0))  # same forward
+    assert scaler.get_scale() == 2.0 ** 12  # no overflow: the step was taken, the scale was not backed off
+    moved = 0
+    for (k, a), b, c in zip(plain.named_parameters(), scaled.parameters(), base.parameters()):
+        assert torch.isfinite(b).all() and b.dtype == torch.float32, k
+        if (a - c).norm() > 0:
+            moved += 1
+            # bf16 gradient operands: the x4096 scale is exact in bf16 / fp32, only reduction order differs
+            assert rel(b - c, a - c) < 1e-3, (k, rel(b - c, a - c))
+    assert moved > 10
+
+
 def test_dropout_is_rejected_loudly():
     import models
 

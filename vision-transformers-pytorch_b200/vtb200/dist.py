@@ -177,11 +177,15 @@ class FlatGradReducer:
                     self._flat[i].mul_(1.0 / world)
                 return
             main = torch.cuda.current_stream(self._flat[0].device)
+            avg = dist.get_backend() == "nccl"   # NCCL averages inside the collective: no extra pass over the bucket
             for i in order:
                 self.comm_stream.wait_event(self._events[i])
                 with torch.cuda.stream(self.comm_stream):
-                    dist.all_reduce(self._flat[i], async_op=True).wait()
-                    self._flat[i].mul_(1.0 / world)
+                    if avg:
+                        dist.all_reduce(self._flat[i], op=dist.ReduceOp.AVG, async_op=True).wait()
+                    else:
+                        dist.all_reduce(self._flat[i], async_op=True).wait()
+                        self._flat[i].mul_(1.0 / world)
             main.wait_stream(self.comm_stream)   # the next step's zero() / the optimizer see reduced gradients
             return
         if self.attached:
