@@ -483,6 +483,31 @@ def test_run_to_run_determinism_contract():
 
 
 @pytest.mark.gpu
+def test_weight_arena_refuses_a_backward_across_a_weight_update():
+    """The arena is one shared buffer: forward, optimizer step, forward again, THEN backward of the first graph would read
+    the new weights in dgrad.  That raises; two forwards without a weight change in between (gradient accumulation) do not."""
+    from models.vit import VisionTransformer
+    from vtb200 import multi
+
+    torch.manual_seed(2)
+    net = VisionTransformer(torch.nn.Linear(64, 10), 32, 16, 2, 64, 2, 128, 0.0, 0.0, 0.0, 0.0).cuda()
+    x = torch.randn(4, 3, 32, 32, device="cuda")
+    multi.enable_weight_arena(net)
+    try:
+        y1 = net(x)
+        y2 = net(x * 0.5)                       # same weights: the generation does not move
+        (y1.sum() + y2.sum()).backward()        # legal
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        y_old = net(x)
+        opt.step()                              # weights change ...
+        net(x)                                  # ... and the next forward re-casts the arena
+        with pytest.raises(RuntimeError, match="weight arena"):
+            y_old.sum().backward()
+    finally:
+        multi.disable_weight_arena(net)
+
+
+@pytest.mark.gpu
 def test_weight_arena_matches_per_call_casts_and_tracks_updates():
     """enable_weight_arena: same logits and gradients as the per-Linear casts, fewer launches, and weights rewritten
     between forwards (optimizer step, multi-tensor EMA, load_state_dict) are picked up."""

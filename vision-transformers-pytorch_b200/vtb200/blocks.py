@@ -39,6 +39,7 @@ def _wgrad(g, x, bias_grad=False):
 
 def _dgrad(g, w_bf16, **kw):
     """dx[T,K] = g[T,N] W[N,K]."""
+    ops.assert_weight_fresh(w_bf16)
     return ops.gemm(g, w_bf16, b_mn=True, **kw)
 
 

@@ -166,7 +166,14 @@ class WeightArena:
     Opt-in (`enable_weight_arena(model)`): the contract is that parameters only change BETWEEN top-level forward
     calls (optimizer step, EMA, load_state_dict), which is how train.py / train_dino.py use the models.  Lookups are
     guarded: an entry is used only if the parameter object is still alive, still owns the same storage address and its
-    autograd version is the one that was cast; anything else falls back to a per-call cast."""
+    autograd version is the one that was cast; anything else falls back to a per-call cast.
+
+    The arena is ONE shared buffer that every refresh overwrites in place, and the branch Functions keep the views they were
+    handed for their backward (dgrad reads the bf16 weight).  A graph whose forward ran BEFORE a weight update and whose backward
+    runs AFTER the next forward would therefore differentiate against the new weights.  That misuse is detected, not silently
+    computed: every view carries the arena's content generation (bumped by a refresh that follows a parameter change), and
+    `ops.assert_weight_fresh` — called by every dgrad — raises if the generation moved on.  Two forwards with unchanged weights
+    (gradient accumulation, the DINO crops) keep the generation and stay legal."""
 
     def __init__(self, module):
         # weight-normed layers (`weight_v` / `weight_g`, vit.py:244) are excluded: their operand is built by vtb_weight_norm_fwd
@@ -185,16 +192,20 @@ class WeightArena:
         self.versions = [-1] * len(self.params)
         self.epoch = -1
         self.index = {}
+        self.generation = 0  # content generation: bumped when a refresh follows a change of any parameter
 
     def refresh(self):
         ptrs = tuple(p.data_ptr() for p in self.params)
+        versions = [p._version for p in self.params]
+        if ptrs != self.ptrs or versions != self.versions or self.epoch != _ops.WEIGHT_EPOCH:
+            self.generation += 1
         if ptrs != self.ptrs:  # first call, or a parameter's storage was swapped (load_state_dict(assign=True), .to())
             self.src = TensorList([p.detach() for p in self.params], F32, "weights")
             self.dst = TensorList(self.views, BF16, "arena")
             self.ptrs = ptrs
             self.index = {ptr: i for i, ptr in enumerate(ptrs)}
         cast_bf16(self.src, self.dst)
-        self.versions = [p._version for p in self.params]
+        self.versions = versions
         self.epoch = _ops.WEIGHT_EPOCH
 
     def lookup(self, t):
@@ -204,7 +215,9 @@ class WeightArena:
         p = self.params[i]
         if p.data_ptr() != t.data_ptr() or p._version != self.versions[i] or t.numel() != p.numel():
             return None
-        return self.views[i].view(t.shape)
+        v = self.views[i].view(t.shape)
+        v._vtb_arena_gen = (self, self.generation)  # checked by ops.assert_weight_fresh in the backward pass
+        return v
 
 
 _ARENAS = []

@@ -433,6 +433,16 @@ WEIGHT_LOOKUP = None
 WEIGHT_EPOCH = 0
 
 
+def assert_weight_fresh(w):
+    """Backward-side guard of the weight arena (vtb200.multi.WeightArena): a bf16 weight view saved by a forward must still
+    hold the weights of that forward when the backward reads it."""
+    tag = getattr(w, "_vtb_arena_gen", None)
+    if tag is not None and tag[0].generation != tag[1]:
+        raise RuntimeError("vtb200: this graph's forward ran before a weight update and its backward runs after a later "
+                           "forward re-cast the weight arena; the saved bf16 weights are gone.  Run backward before the next "
+                           "forward of the updated model, or disable_weight_arena(model).")
+
+
 def cast_bf16(src):
     lib = _l.get()
     if src.dtype != F32 or not src.is_contiguous():
