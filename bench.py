@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — images/sec, fwd+bwd, on the BASELINE.json configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vit_b16|swin_s|pvt_small|halo_t] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vit_b16|swin_s|pvt_small|halo_t|twins_s|dino_deit_s] [--impl reference]
 
 One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1); rank 0 prints ONE JSON line.
 A step = forward + cross-entropy + backward of the whole model on one synthetic batch (256 images/GPU, weak
@@ -35,6 +35,9 @@ WORKLOADS = {
     "pvt_small": dict(gflop=22.875, batch=128, desc="PVT-Small 224x224 fwd+bwd, batch 128/GPU"),
     "halo_t": dict(gflop=29.36, batch=128, desc="Halo-T* 224x224 fwd+bwd, batch 128/GPU"),
     "vit_tiny": dict(gflop=7.463, batch=64, desc="ViT-Tiny/16 224x224 fwd+bwd (plumbing)"),
+    # not a BASELINE config: Twins-SVT with the paper's "S" widths through the reference's own ctor; FLOPs counted
+    # with FlopCounterMode on the reference module like the others
+    "twins_s": dict(gflop=34.486, batch=128, desc="Twins-SVT-S* 224x224 fwd+bwd, batch 128/GPU"),
     # BASELINE config 5: per source image 2x224^2 + 8x96^2 student fwd+bwd, 2x224^2 teacher fwd, + head
     "dino_deit_s": dict(gflop=113.4, batch=128, desc="DINO DeiT-S/16 multi-crop (2x224^2 + 8x96^2), 128 source images/GPU: "
                                                       "teacher fwd + student fwd/bwd + DINO loss + EMA"),
@@ -61,6 +64,11 @@ def build_model(workload, drop_path=None):
                            drop_attn=0., drop_ff=0., drop_path=0.1 if drop_path is None else drop_path,
                            dim_head_out=65536, use_bn=False, norm_last_layer=False, depth_head=3, dim_head_ff=2048,
                            dim_head_bottleneck=256)
+    if workload == "twins_s":
+        import models.twins
+
+        return models.twins.TwinsSVT(1000, (2, 2, 10, 4), (64, 128, 256, 512), 32, (2, 4, 8, 16), (256, 512, 1024, 2048), 7,
+                                     drop_path=0.1 if drop_path is None else drop_path)
     if workload == "halo_t":
         return models.HaloTransformer((224, 224), 1000, (2, 2, 6, 2), (96, 192, 384, 768), 32, (3, 6, 12, 24),
                                       (384, 768, 1536, 3072), window_size=7, halo_size=3, drop_path=0.1)
@@ -172,6 +180,8 @@ def cpu_reference_step(workload, batch, threads, device="cpu", autocast=False):
             return R.swin_forward(sd, x, depths=(2, 2, 18, 2), n_heads=(3, 6, 12, 24), dim_head=32, window=7)
         if workload == "pvt_small":
             return R.pvt_forward(sd, x, depths=(3, 4, 6, 3), n_heads=(1, 2, 5, 8), reductions=(8, 4, 2, 1))
+        if workload == "twins_s":
+            return R.twins_forward(sd, x, depths=(2, 2, 10, 4), n_heads=(2, 4, 8, 16), dim_head=32, window=7)
         return R.halo_forward(sd, x, depths=(2, 2, 6, 2), n_heads=(3, 6, 12, 24), dim_head=32, window=7, halo=3)
 
     def step():

@@ -490,7 +490,9 @@ def test_weight_arena_refuses_a_backward_across_a_weight_update():
     from vtb200 import multi
 
     torch.manual_seed(2)
-    net = VisionTransformer(torch.nn.Linear(64, 10), 32, 16, 2, 64, 2, 128, 0.0, 0.0, 0.0, 0.0).cuda()
+    # head=None: every weight goes through the library's Functions, whose saved operands are bf16 copies that torch's own
+    # in-place version check cannot see (a plain nn.Linear head would make torch raise first)
+    net = VisionTransformer(None, 32, 16, 2, 64, 2, 128, 0.0, 0.0, 0.0, 0.0).cuda()
     x = torch.randn(4, 3, 32, 32, device="cuda")
     multi.enable_weight_arena(net)
     try:
