@@ -427,11 +427,13 @@ def test_attention_window_plain_twins(ops):
     _window_case(ops, 14, 7, False, H=2, dh=64, B=2, seed=77, use_bias=False)
 
 
-@pytest.mark.parametrize("Hs,W,hl,B", [(14, 7, 3, 2), (7, 7, 3, 2), (8, 2, 1, 2), (21, 7, 3, 1), (28, 7, 3, 5), (12, 4, 2, 3)])
+@pytest.mark.parametrize("Hs,W,hl,B", [(14, 7, 3, 2), (7, 7, 3, 2), (8, 2, 1, 2), (21, 7, 3, 1), (28, 7, 3, 5), (12, 4, 2, 3),
+                                       ((14, 35), 7, 3, 3), ((6, 2), 2, 1, 1)])
 @pytest.mark.parametrize("ht", [1, 0])
 def test_attention_halo(ops, Hs, W, hl, B, ht):
     """ht=1: tcgen05 halo tiles (forward; backward with per-block partial dK / dV rows + the per-token sum);
-    ht=0: the mma.sync kernels.  B=1 x 9 blocks: an odd number of blocks (the last tile holds one)."""
+    ht=0: the mma.sync kernels.  B=1 x 9 blocks: an odd number of blocks (the last tile holds one); (14, 35) / (6, 2):
+    non-square token maps (blocks per row != blocks per column, a map narrower than the halo window)."""
     from vtb200 import lib
 
     lib.set_option("attn_ht", ht)
@@ -445,24 +447,25 @@ def _halo_case(ops, Hs, W, hl, B):
     from oracle import restate as R
     from vtb200 import lib
 
-    g = torch.Generator(device="cuda").manual_seed(Hs * 31 + W)
+    Hs, Ws = Hs if isinstance(Hs, tuple) else (Hs, Hs)
+    g = torch.Generator(device="cuda").manual_seed(Hs * 31 + W + Ws)
     H, dh = 3, 32
-    HD, T, K = H * dh, B * Hs * Hs, W + 2 * hl
+    HD, T, K = H * dh, B * Hs * Ws, W + 2 * hl
     qkv = bf(torch.randn(T, 3 * HD, device="cuda", generator=g))
     pos = R.halo_pos_table(W, hl)
     table = 0.5 * torch.randn(int(pos.max()) + 1, H, device="cuda", generator=g)
-    spec = ops.AttnSpec(lib.ATTN_HALO, B, H, dh, W * W, K * K, Hs=Hs, Ws=Hs, window=W, halo=hl, rel_bias=table,
+    spec = ops.AttnSpec(lib.ATTN_HALO, B, H, dh, W * W, K * K, Hs=Hs, Ws=Ws, window=W, halo=hl, rel_bias=table,
                         pos=pos.to(torch.int32).cuda())
     o, lse = ops.attention_fwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:])
     C3 = 3 * HD
-    x = qkv.float().view(B, Hs, Hs, C3).requires_grad_(True)
+    x = qkv.float().view(B, Hs, Ws, C3).requires_grad_(True)
     tab = table.clone().requires_grad_(True)
     sd = {"a.weight.weight": torch.eye(C3, device="cuda"), "a.linear.weight": torch.eye(HD, device="cuda"),
           "a.linear.bias": torch.zeros(HD, device="cuda"), "a.rel_pos.weight": tab, "a.pos": pos.cuda()}
     want = R.halo_attention(x, sd, "a.", H, dh, W, hl)
-    assert rel(o.float().view(B, Hs, Hs, HD), want) < 6e-3
+    assert rel(o.float().view(B, Hs, Ws, HD), want) < 6e-3
     do = bf(torch.randn(T, HD, device="cuda", generator=g))
-    want.backward(do.float().view(B, Hs, Hs, HD))
+    want.backward(do.float().view(B, Hs, Ws, HD))
     dq = torch.empty(T, HD, dtype=BF16, device="cuda")
     dkv = torch.zeros(T, 2 * HD, dtype=F32, device="cuda")
     drel = torch.zeros_like(table)
