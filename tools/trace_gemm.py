@@ -7,17 +7,25 @@ import torch
 from vtb200 import lib, ops
 L = lib.get()
 F32, BF16 = torch.float32, torch.bfloat16
-names = ["wait_group.read", "bar#1", "tmem_ld_wait", "issue ld/aux wait", "math+STS", "fence.proxy", "bar#2", "TMA issue"]
+names = ["-", "-", "tmem_ld_wait", "next ld / aux + free-buffer wait", "math+STS", "fence.proxy", "syncwarp+arrive", "bookkeeping"]
 def run(tag, fn, subtiles_per_cta):
     fn(); torch.cuda.synchronize()
     L.vtb_debug_gemm_trace(None, 1)
     n = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(n): fn()
+    e1.record()
     torch.cuda.synchronize()
-    buf = (C.c_ulonglong * 16)()
+    us = e0.elapsed_time(e1) / n * 1e3
+    buf = (C.c_ulonglong * 32)()
     L.vtb_debug_gemm_trace(buf, 1)
     v = list(buf)
-    tot_i, tot_o = sum(v[:8]), sum(v[8:])
+    tot_i, tot_o = sum(v[:8]), sum(v[8:16])
+    tiles_e, tiles_i = max(v[18], 1), max(v[22], 1)
+    print(f"== {tag}: {us:.1f} us per launch with the trace build")
+    print(f"== {tag}: per tile (CTA 7; {tiles_e / n:.1f} tiles / launch): epilogue warp waits {v[16] / tiles_e:.0f} cycles for the accumulator of "
+          f"{v[17] / tiles_e:.0f}; MMA issuer waits {v[20] / tiles_i:.0f} for a TMEM stage + {v[19] / tiles_i:.0f} for operands of {v[21] / tiles_i:.0f}")
     print(f"== {tag}: issuer-lane cycles/sub-tile (4 quarters summed / 4): " + ", ".join(f"{names[i]}={v[i]/n/4/subtiles_per_cta:.0f}" for i in range(8)) + f" | total {tot_i/n/4/subtiles_per_cta:.0f}")
     print(f"   non-issuer warp: " + ", ".join(f"{names[i]}={v[8+i]/n/4/subtiles_per_cta:.0f}" for i in range(8)) + f" | total {tot_o/n/4/subtiles_per_cta:.0f}")
 T, Cc, FF = 50176, 384, 1536

@@ -66,6 +66,57 @@ __device__ __forceinline__ float silu_grad_f(float x) {
   const float s = sigmoid_f(x);
   return s * fmaf(x, 1.f - s, 1.f);
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 — one issue slot for two lanes of work)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+// silu of a pair: x sigmoid(x) = t + t tanh(t) with t = x / 2  (FMUL2, 2 x MUFU, FFMA2)
+__device__ __forceinline__ void silu_pair(float x0, float x1, float& y0, float& y1) {
+  const uint64_t t = f2_mul(f2_pack(x0, x1), f2_pack(0.5f, 0.5f));
+  float t0, t1;
+  f2_unpack(t, t0, t1);
+  f2_unpack(f2_fma(t, f2_pack(tanh_approx_f(t0), tanh_approx_f(t1)), t), y0, y1);
+}
+// d silu / dx of a pair: 0.5 (1 + th + t (1 - th^2)), t = x / 2, th = tanh(t)
+__device__ __forceinline__ void silu_grad_pair(float x0, float x1, float& g0, float& g1) {
+  const uint64_t one = f2_pack(1.f, 1.f), half = f2_pack(0.5f, 0.5f);
+  const uint64_t t = f2_mul(f2_pack(x0, x1), half);
+  float t0, t1;
+  f2_unpack(t, t0, t1);
+  const uint64_t th = f2_pack(tanh_approx_f(t0), tanh_approx_f(t1));
+  const uint64_t nth = f2_mul(th, f2_pack(-1.f, -1.f));
+  const uint64_t a = f2_fma(nth, th, one);          // 1 - th^2
+  const uint64_t b = f2_fma(t, a, th);              // th + t (1 - th^2)
+  f2_unpack(f2_fma(half, b, half), g0, g1);
+}
+// the two bf16 halves of a packed pair as fp32 (exact): one shift, one mask
+__device__ __forceinline__ float bf16lo_f(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // explicit shared-space accesses (a pointer carved out of the dynamic smem block after integer rounding is "generic" to
 // the compiler: its loads / stores become LD.E / ST.E through the L1TEX path instead of LDS / STS)

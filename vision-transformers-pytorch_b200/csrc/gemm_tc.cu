@@ -33,10 +33,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 #ifdef VTB_GEMM_TRACE
-__device__ unsigned long long g_trace[16];
+__device__ unsigned long long g_trace[32];   // [0,16): epilogue phases per sub-tile; [16,32): tile-level waits (see tools/trace_gemm.py)
 #define TRACE_T(i) const long long tr##i = clock64()
+#define TRACE_ADD(slot, expr) do { if (blockIdx.x == 7) atomicAdd(&g_trace[slot], (unsigned long long)(expr)); } while (0)
 #else
 #define TRACE_T(i)
+#define TRACE_ADD(slot, expr)
 #endif
 int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces 1-CTA tiles,
                               // 2 forces pairs wherever legal (tests)
@@ -196,21 +198,35 @@ __device__ __forceinline__ void sts_f4(uint32_t saddr, float a, float b, float c
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// bias_vec: this warp's CW bias values as 16-byte read-only loads at a warp-uniform address (L1 broadcast; the line was
+// prefetched a sub-tile ahead) instead of CW shuffles — or nullptr (ragged N / unaligned bias): lane j of the warp then holds
+// the bias of column j in bias_lane.  All element-wise math runs on packed fp32 pairs (FFMA2 / FADD2 / FMUL2).
 template <int CW>
-__device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&acc)[CW], float bias_lane, float rs,
+__device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&acc)[CW], float bias_lane,
+                                           const float* __restrict__ bias_vec, float rs,
                                            uint32_t ob, uint32_t ab, uint32_t cb, uint32_t swz, bool dual,
                                            bool f32out) {
-  float v[CW];
+  uint64_t v[CW / 2];
+#pragma unroll
+  for (int j = 0; j < CW / 2; ++j) v[j] = f2_pack(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
   if (e.alpha != 1.f) {
+    const uint64_t al = f2_pack(e.alpha, e.alpha);
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-  } else {
-#pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]);
+    for (int j = 0; j < CW / 2; ++j) v[j] = f2_mul(v[j], al);
   }
-  if (e.bias) {  // lane j of the warp holds the bias of this warp's column j (prefetched one sub-tile ahead)
+  if (e.bias) {
+    if (bias_vec) {
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+      for (int j = 0; j < CW; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_vec + j));
+        v[j / 2] = f2_add(v[j / 2], f2_pack(b4.x, b4.y));
+        v[j / 2 + 1] = f2_add(v[j / 2 + 1], f2_pack(b4.z, b4.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; j += 2)
+        v[j / 2] = f2_add(v[j / 2], f2_pack(__shfl_sync(0xffffffffu, bias_lane, j), __shfl_sync(0xffffffffu, bias_lane, j + 1)));
+    }
   }
   if (dual) {
     // out <- bf16(u) ; out2 <- bf16(silu(float(bf16(u))))     (layer.py:191-193 under autocast)
@@ -219,9 +235,11 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
       uint32_t pu[4], ph[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        pu[t] = pack_bf16(v[j + 2 * t], v[j + 2 * t + 1]);
-        const float2 ur = unpack_bf16(pu[t]);
-        ph[t] = pack_bf16(silu_f(ur.x), silu_f(ur.y));
+        float u0, u1, h0, h1;
+        f2_unpack(v[j / 2 + t], u0, u1);
+        pu[t] = pack_bf16(u0, u1);
+        silu_pair(bf16lo_f(pu[t]), bf16hi_f(pu[t]), h0, h1);
+        ph[t] = pack_bf16(h0, h1);
       }
       const uint32_t off = ((cb + j / 8) ^ swz) << 4;
       sts_u4(ob + off, pu[0], pu[1], pu[2], pu[3]);
@@ -236,32 +254,45 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
       const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 u = unpack_bf16(w[t]);
-        v[j + 2 * t] *= silu_grad_f(u.x);
-        v[j + 2 * t + 1] *= silu_grad_f(u.y);
+        float g0, g1;
+        silu_grad_pair(bf16lo_f(w[t]), bf16hi_f(w[t]), g0, g1);
+        v[j / 2 + t] = f2_mul(v[j / 2 + t], f2_pack(g0, g1));
       }
     }
   }
   if (e.row_scale) {
+    const uint64_t r2 = f2_pack(rs, rs);
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] *= rs;
+    for (int j = 0; j < CW / 2; ++j) v[j] = f2_mul(v[j], r2);
   }
   if (f32out) {
     if (e.resid) {  // f32 residual sub-tile prefetched by TMA
 #pragma unroll
       for (int j = 0; j < CW; j += 4) {
         const float4 t = lds_f4(ab + (((cb + j / 4) ^ swz) << 4));
-        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+        v[j / 2] = f2_add(v[j / 2], f2_pack(t.x, t.y));
+        v[j / 2 + 1] = f2_add(v[j / 2 + 1], f2_pack(t.z, t.w));
       }
     }
 #pragma unroll
-    for (int j = 0; j < CW; j += 4)
-      sts_f4(ob + (((cb + j / 4) ^ swz) << 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < CW; j += 4) {
+      float a0, a1, a2, a3;
+      f2_unpack(v[j / 2], a0, a1);
+      f2_unpack(v[j / 2 + 1], a2, a3);
+      sts_f4(ob + (((cb + j / 4) ^ swz) << 4), a0, a1, a2, a3);
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < CW; j += 8)
-      sts_u4(ob + (((cb + j / 8) ^ swz) << 4), pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-             pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+    for (int j = 0; j < CW; j += 8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float a0, a1;
+        f2_unpack(v[j / 2 + t], a0, a1);
+        pk[t] = pack_bf16(a0, a1);
+      }
+      sts_u4(ob + (((cb + j / 8) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+    }
   }
 }
 
@@ -400,11 +431,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int ks = tile % splits;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(k_blocks, kb0 + kb_per_split);
+#ifdef VTB_GEMM_TRACE
+        const long long ti0 = clock64();
+#endif
         mbar_wait(&tmem_empty[as], aphase ^ 1);
+        TRACE_ADD(20, clock64() - ti0);   // MMA issuer waiting for a free accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
+#ifdef VTB_GEMM_TRACE
+          const long long ti1 = clock64();
+#endif
           mbar_wait(&full_bar[stage], phase);
+          TRACE_ADD(19, clock64() - ti1);  // ... for operands
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
           const uint32_t b_base = smem_u32(sB + stage * C::B_STAGE_BYTES);
@@ -426,6 +465,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         // accumulator complete -> epilogue (of both CTAs in pair mode)
         if (CL == 1) umma_commit(&tmem_full[as]); else umma_commit_pair(&tmem_full[as], (uint16_t)0x3);
+        TRACE_ADD(21, clock64() - ti0);   // issuer: whole tile
+        TRACE_ADD(22, 1);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -626,13 +667,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int n_blk = mn % n_tiles;
           const int m_blk = (mn / n_tiles) * CL + rank;
           const int m = m_blk * BM + row;
+#ifdef VTB_GEMM_TRACE
+          const long long te0 = clock64();
+#endif
           mbar_wait(&tmem_full[as], aphase);
+          if (warp == 4 && lane == 0) { TRACE_ADD(16, clock64() - te0); TRACE_ADD(18, 1); }  // epilogue waiting for the accumulator
           tc_fence_after();
           const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + ehalf * CW;
           const float rs = (epi.row_scale && m < epi.M) ? __ldg(epi.row_scale + m / epi.rows_per_scale) : 1.f;
+          // vector bias path: N a multiple of 4 and a 16-byte aligned bias -> every in-range group of 4 columns is a legal float4
+          const bool bias_v = epi.bias && (epi.N & 3) == 0 && (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0;
           auto bias_at = [&](int sidx) -> float {
             const int col = n_blk * BN + sidx * SUBC + ehalf * CW + lane;
-            return (epi.bias && lane < CW && col < epi.N) ? __ldg(epi.bias + col) : 0.f;
+            return (epi.bias && lane < CW && col < epi.N) ? __ldg(epi.bias + col) : 0.f;   // also warms L1 for the vector path
           };
           uint32_t accA[CW], accB[CW];
           tmem_ld_cols<CW>(t_row, accA);
@@ -660,7 +707,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             // staging buffer qb was handed to TMA `nob` sub-tiles ago: wait until it has been read out
             mbar_wait(&free_q[qb], qph ^ 1);
             TRACE_T(4);
-            if (live) staged_row<CW>(epi, cur, b_cur, rs, ob, ab, cb, swz, dual, CW == 16);
+            const int ncol0 = n0 + ehalf * CW;   // this warp's first column; the vector path needs all CW of them inside N
+            const float* bvec = (bias_v && ncol0 + CW <= epi.N) ? epi.bias + ncol0 : nullptr;
+            if (live) staged_row<CW>(epi, cur, b_cur, bvec, rs, ob, ab, cb, swz, dual, CW == 16);
             b_cur = b_nxt;
             TRACE_T(5);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
@@ -683,6 +732,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             step(accA, accB, sidx);
             if (NSUB > 1) step(accB, accA, sidx + 1);  // NSUB is 1 (BN 64, bf16 out) or even
           }
+          if (warp == 4 && lane == 0) TRACE_ADD(17, clock64() - te0);   // epilogue: whole tile
           if (++as == 2) { as = 0; aphase ^= 1; }
         }
       };
@@ -929,8 +979,8 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
 
 #ifdef VTB_GEMM_TRACE
 extern "C" int vtb_debug_gemm_trace(unsigned long long* out, int reset) {
-  if (out) VTB_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 16));
-  if (reset) { unsigned long long z[16] = {0}; VTB_CUDA(cudaMemcpyToSymbol(g_trace, z, sizeof(z))); }
+  if (out) VTB_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 32));
+  if (reset) { unsigned long long z[32] = {0}; VTB_CUDA(cudaMemcpyToSymbol(g_trace, z, sizeof(z))); }
   return 0;
 }
 #endif
