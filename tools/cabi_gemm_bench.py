@@ -98,6 +98,7 @@ def block(T, Cc, FF, tag, seed):
     qkv, u, h, du = rb((T, QKV)), rb((T, FF)), rb((T, FF)), cu.Buf((T, FF), BF16)
     out, dyb = cu.Buf((T, Cc), F32), cu.Buf((T, Cc), BF16)
     dw1, dw2, dwq = cu.Buf((FF, Cc), F32).zero(), cu.Buf((Cc, FF), F32).zero(), cu.Buf((QKV, Cc), F32).zero()
+    db1, dbq = cu.Buf(FF, F32).zero(), cu.Buf(QKV, F32).zero()
     scale = cu.Buf(T // 196 + 1, F32).upload(np.ones(T // 196 + 1, F32))
     SILU_DUAL, SILU_GRAD = L.EPI_SILU_DUAL, L.EPI_SILU_GRAD
     cases = [
@@ -118,11 +119,17 @@ def block(T, Cc, FF, tag, seed):
          lambda: gemm(du, y, FF, Cc, T, a_mn=True, b_mn=True, out=dw1, accumulate=True)),
         ("qkv wgrad         ", 2 * T * QKV * Cc, T * QKV * 2 + T * Cc * 2,
          lambda: gemm(qkv, y, QKV, Cc, T, a_mn=True, b_mn=True, out=dwq, accumulate=True)),
+        ("fc1 wgrad + colsum", 2 * T * FF * Cc, T * FF * 2 + T * Cc * 2,
+         lambda: gemm(du, y, FF, Cc, T, a_mn=True, b_mn=True, out=dw1, accumulate=True, a_colsum=db1)),
+        ("qkv wgrad + colsum", 2 * T * QKV * Cc, T * QKV * 2 + T * Cc * 2,
+         lambda: gemm(qkv, y, QKV, Cc, T, a_mn=True, b_mn=True, out=dwq, accumulate=True, a_colsum=dbq)),
+        ("fc1 colsum pass   ", 0, T * FF * 2, lambda: L.check(lib.vtb_colsum_bf16(du.addr, T, FF, FF, db1.addr, None), lib)),
+        ("qkv colsum pass   ", 0, T * QKV * 2, lambda: L.check(lib.vtb_colsum_bf16(qkv.addr, T, QKV, QKV, dbq.addr, None), lib)),
     ]
     only = os.environ.get("GEMM_ONLY")
     tot = 0.0
     for name, fl, by, fn in cases:
-        if only and only not in name:
+        if only and not any(o in name for o in only.split(",")):
             continue
         us = timer.time(fn)
         tot += us
@@ -133,6 +140,9 @@ def block(T, Cc, FF, tag, seed):
         buf.free()
 
 
+for kv in filter(None, os.environ.get("GEMM_OPTS", "").split(",")):  # e.g. GEMM_OPTS=gemm_colsum_pair=0
+    k, v = kv.split("=")
+    L.check(lib.vtb_set_option(k.encode(), int(v)), lib)
 self_check()
 rng = np.random.default_rng(1)
 n_seed = 16 << 20

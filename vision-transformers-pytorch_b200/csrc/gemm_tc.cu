@@ -40,6 +40,7 @@ __device__ unsigned long long g_trace[32];   // [0,16): epilogue phases per sub-
 #define TRACE_T(i)
 #define TRACE_ADD(slot, expr)
 #endif
+int g_colsum_pair = 1;      // a_colsum launches may use CTA pairs (vtb_set_option("gemm_colsum_pair", 0): 1-CTA tiles as in round 1)
 int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces 1-CTA tiles,
                               // 2 forces pairs wherever legal (tests)
 
@@ -327,6 +328,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* staged_bar = aux_full + 4 * N_AUX;                // [4 quarters][MAXOB]: sub-tile written + fenced (2 warps)
   uint64_t* free_bar = staged_bar + 4 * MAXOB;                // [4 quarters][MAXOB]: TMA has read the staging buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(free_bar + 4 * MAXOB);
+  uint64_t* mma_done = free_bar + 4 * MAXOB + 1;              // [STAGES], pair-mode a_colsum only (ends below the scratch at +1024)
+  // Pair-mode bias gradient (`a_colsum` on cta_group::2 tiles): the operand bytes of both CTAs are credited to the
+  // LEADER's full barrier, so the peer's readers have no local "tile landed" event.  The issuer's commit therefore goes to
+  // `mma_done` (multicast to both CTAs), the readers add up the stage AFTER the tensor cores are through with it and
+  // release it themselves (`empty` = 8 reader warps).  Six ring stages hide the later release; the k-blocks are dealt
+  // round-robin over the n-tiles of a row of tiles, so every CTA reads 1 / n_tiles of its stages instead of one CTA in
+  // n_tiles reading all of them.  (Tried and not kept: warp 2 as the only reader, so that the epilogue warps can drain
+  // tile i while the ring serves tile i+1 — one warp has too few shared-memory loads in flight next to the tensor
+  // cores' operand reads: ViT-B fc1 wgrad 237 us against 190 us with the 8 warps, profiles/r02_cabi_gemm_colsum_*.log.)
+  const bool cs_post = (CL > 1) && A_MN && (epi.a_colsum != nullptr);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -338,7 +349,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], (A_MN && epi.a_colsum) ? 9 : 1);  // + the 8 epilogue warps that read the A tiles
+      mbar_init(&empty_bar[i], (A_MN && epi.a_colsum) ? (CL > 1 ? 8 : 9) : 1);  // + the 8 epilogue warps that read the A tiles
+      if (CL > 1) mbar_init(&mma_done[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -460,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             else umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CL == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          else umma_commit_pair(&empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
+          else umma_commit_pair(cs_post ? &mma_done[stage] : &empty_bar[stage], (uint16_t)0x3);  // ... in both CTAs of the pair
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs in pair mode)
@@ -573,8 +585,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[rd_stage], rd_phase);
-        if (mine) {
+        mbar_wait(cs_post ? &mma_done[rd_stage] : &full_bar[rd_stage], rd_phase);
+        if (cs_post ? (kb % n_tiles == mn % n_tiles) : mine) {
           const uint32_t a = smem_u32(sA) + (uint32_t)(rd_stage * A_STAGE_BYTES) + off;
 #pragma unroll
           for (int r4 = 0; r4 < 4; ++r4) {
@@ -591,7 +603,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) mbar_arrive(&empty_bar[rd_stage]);
         if (++rd_stage == C::STAGES) { rd_stage = 0; rd_phase ^= 1; }
       }
-      if (mine) {  // 16 row groups -> one value per column of the tile (scratch behind the mbarriers) -> global
+      if (mine || cs_post) {  // 16 row groups -> one value per column of the tile (scratch behind the mbarriers) -> global
         const uint32_t s_col = smem_u32(bars) + 1024u;   // float [BM]
         if (t < BM) sts_f32(s_col + t * 4, 0.f);
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -865,6 +877,7 @@ void vtb_input_variant_set(int v);
 extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
+  if (strcmp(name, "gemm_colsum_pair") == 0) { g_colsum_pair = value; return 0; }
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
   if (strcmp(name, "attn_tc_fwd_version") == 0) { vtb_attn_tc_version_set(value, 0); return 0; }
   if (strcmp(name, "attn_tc_bwd_version") == 0) { vtb_attn_tc_version_set(0, value); return 0; }
@@ -941,7 +954,7 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   // CTA pairs (256 x bn tiles, cta_group::2) whenever there are at least two row tiles and the pairs can fill the
   // machine; an MN-major B tile of 64 columns is one TMA box and cannot be halved
   bool pair = g_use_clusters && m_tiles >= 2 && !(p->b_mn_major && bn < 128);
-  if (p->a_colsum) pair = false;  // the readers of the A tiles wait on their own CTA's `full` barrier (leader-only in pairs)
+  if (p->a_colsum && !g_colsum_pair) pair = false;  // A/B switch: 1-CTA tiles, the readers wait on their own CTA's `full` barrier
   const long units = (long)(pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;  // work items before split-K
   const int slots = pair ? g_num_sms / 2 : g_num_sms;                        // concurrently resident work items
   int splits = p->splits;

@@ -8,6 +8,7 @@ the reference-named modules (models/*.py); bf16 operand copies are made per call
 Reference call sites: vit.py:59-63, swin_transformer.py:193-197, pvt.py:97-101,
 halo_transformer.py:146-150 (restated out-of-place), twins.py:191-197, layer.py:166-196.
 """
+import os
 import threading
 import weakref
 
@@ -22,16 +23,21 @@ _fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = torch.amp.custom_bwd(device_type="cuda")
 
 
+WGRAD_COLSUM = os.environ.get("VTB_WGRAD_COLSUM", "always")  # "always" | "narrow" (round-2 rule) | "never": A/B switch
+
+
 def _wgrad(g, x, bias_grad=False):
     """dW[N,K] = g[T,N]^T x[T,K]  (both operands MN-major views of the forward buffers; split-K).  With bias_grad also
-    returns db[N] = column sums of g.  Where the weight gradient is bandwidth-bound (narrow layers: N K / (N + K) below
-    ~450 flop/byte, measured: Swin stages 1-3 yes, ViT-B no) the sums ride on the same launch — the idle epilogue warps
-    add up the operand tiles while they sit in shared memory; on tensor-bound shapes that slows the GEMM by more than
-    the separate pass costs, so the bias gradient takes its own column-sum kernel there."""
+    returns db[N] = column sums of g, which ride on the same launch: the epilogue warps, idle during the mainloop, add
+    up the operand tiles while they sit in the shared-memory ring (`a_colsum`).  On bandwidth-bound weight gradients
+    (narrow layers) that was always a win; on tensor-bound shapes (ViT-B) it only became one when the CTA-pair tiles
+    learnt to carry it (the k-blocks of a row of tiles are dealt over its n-tiles, read after the MMAs retire) — until
+    then the 1-CTA tiles it forced cost more than the separate column-sum pass it saved."""
     if not bias_grad:
         return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True)
     n, k = g.shape[1], x.shape[1]
-    if n * k >= 450 * (n + k) or g.stride(0) % 8 or x.stride(0) % 8:
+    separate = WGRAD_COLSUM == "never" or (WGRAD_COLSUM == "narrow" and n * k >= 450 * (n + k))
+    if separate or g.stride(0) % 8 or x.stride(0) % 8:
         return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True), ops.colsum(g)
     db = ops.zeros(n, F32, g.device)
     return ops.gemm(g, x, a_mn=True, b_mn=True, out_dtype=F32, accumulate=True, a_colsum=db), db
