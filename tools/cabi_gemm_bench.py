@@ -84,6 +84,28 @@ def self_check():
         raise SystemExit("FAIL: dgrad / wgrad operand flags")
 
 
+def trace_report(name, fn):
+    """Cycle counters of CTA 7 (library built with -DVTB_GEMM_TRACE, VTB_LIB=libvtb200_trace.so): per tile and per sub-tile step."""
+    lib.vtb_debug_gemm_trace.argtypes = [C.c_void_p, C.c_int]
+    buf = (C.c_ulonglong * 32)()
+    lib.vtb_debug_gemm_trace(None, 1)
+    n = 3
+    for _ in range(n):
+        fn()
+    cu.ck(cu.rt.cudaDeviceSynchronize(), "sync")
+    lib.vtb_debug_gemm_trace(buf, 1)
+    v = list(buf)
+    te, ti = max(v[18], 1), max(v[22], 1)
+    names = ["t0", "t1", "tmem_ld_wait", "issue next ld + aux wait + free-buffer wait", "math+STS", "fence.proxy", "syncwarp+arrive", "bookkeeping"]
+    print(f"   trace {name.strip()}: {te / n:.1f} tiles per launch on CTA 7; per tile: epilogue {v[17] / te:.0f} cycles of which "
+          f"{v[16] / te:.0f} waiting for the accumulator; issuer {v[21] / ti:.0f} of which {v[20] / ti:.0f} waiting for a TMEM stage, "
+          f"{v[19] / ti:.0f} for operands")
+    for half in (0, 1):
+        tot = sum(v[8 * half:8 * half + 8])
+        print(f"     warp-half {half} (4 quarters summed / 4, per tile): " + ", ".join(
+            f"{names[i]}={v[8 * half + i] / 4 / te:.0f}" for i in range(2, 8)) + f" | total {tot / 4 / te:.0f}")
+
+
 def block(T, Cc, FF, tag, seed):
     QKV = 3 * Cc
     timer = cu.Timer()
@@ -133,6 +155,8 @@ def block(T, Cc, FF, tag, seed):
             continue
         us = timer.time(fn)
         tot += us
+        if os.environ.get("GEMM_TRACE"):
+            trace_report(name, fn)
         print(f"{tag} {name}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s  "
               f"(floor: {fl / PEAK_TF / 1e6:6.1f} us tensor, {by / PEAK_GB / 1e3:6.1f} us hbm)", flush=True)
     print(f"{tag} total {tot:.1f} us", flush=True)
@@ -140,10 +164,11 @@ def block(T, Cc, FF, tag, seed):
         buf.free()
 
 
-for kv in filter(None, os.environ.get("GEMM_OPTS", "").split(",")):  # e.g. GEMM_OPTS=gemm_colsum_pair=0
+for kv in filter(None, (os.environ.get("GEMM_OPTS") or os.environ.get("VTB_OPTS", "")).split(",")):  # e.g. GEMM_OPTS=gemm_colsum_pair=0
     k, v = kv.split("=")
     L.check(lib.vtb_set_option(k.encode(), int(v)), lib)
-self_check()
+if not os.environ.get("GEMM_NOCHECK"):  # the knock-out probes of the debug build produce wrong results on purpose
+    self_check()
 rng = np.random.default_rng(1)
 n_seed = 16 << 20
 seed = {BF16: cu.Buf(n_seed, BF16).upload(cu.to_bf16_bits(rng.standard_normal(n_seed, F32))),

@@ -40,6 +40,14 @@ __device__ unsigned long long g_trace[32];   // [0,16): epilogue phases per sub-
 #define TRACE_T(i)
 #define TRACE_ADD(slot, expr)
 #endif
+#ifdef VTB_GEMM_DBG
+int g_gemm_dbg = 0;         // knock-out probes of the staged epilogue (debug build only): 1 no bias loads, 2 no staging stores,
+                              // 4 no TMA stores, 8 no epilogue math at all, 16 no tcgen05.ld of the next sub-tile
+#define GDBG(e, bit) (((e).dbg & (bit)) != 0)
+#else
+#define GDBG(e, bit) false
+#endif
+int g_helpers = 2;          // warps issuing the staged epilogue's TMA stores (vtb_set_option("gemm_helpers", 1 | 2))
 int g_colsum_pair = 1;      // a_colsum launches may use CTA pairs (vtb_set_option("gemm_colsum_pair", 0): 1-CTA tiles as in round 1)
 int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces 1-CTA tiles,
                               // 2 forces pairs wherever legal (tests)
@@ -62,6 +70,8 @@ struct EpiParams {
   float alpha;
   int vec;  // all epilogue pointers / leading dims allow 16-byte vector access (direct path)
   int tma;  // 1: staged TMA-store epilogue (tensor maps valid)
+  int dbg;          // VTB_GEMM_DBG builds only
+  int helpers;      // 1 | 2: warps that issue the epilogue's bulk-tensor instructions (see the helper role)
   float* a_colsum;  // MN-major A only: += column sums of the A operand (bias gradient riding on a wgrad)
 };
 
@@ -215,7 +225,7 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < CW / 2; ++j) v[j] = f2_mul(v[j], al);
   }
-  if (e.bias) {
+  if (e.bias && !GDBG(e, 1)) {
     if (bias_vec) {
 #pragma unroll
       for (int j = 0; j < CW; j += 4) {
@@ -243,8 +253,10 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
         ph[t] = pack_bf16(h0, h1);
       }
       const uint32_t off = ((cb + j / 8) ^ swz) << 4;
-      sts_u4(ob + off, pu[0], pu[1], pu[2], pu[3]);
-      sts_u4(ab + off, ph[0], ph[1], ph[2], ph[3]);
+      if (!GDBG(e, 2)) {
+        sts_u4(ob + off, pu[0], pu[1], pu[2], pu[3]);
+        sts_u4(ab + off, ph[0], ph[1], ph[2], ph[3]);
+      }
     }
     return;
   }
@@ -280,7 +292,7 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
       float a0, a1, a2, a3;
       f2_unpack(v[j / 2], a0, a1);
       f2_unpack(v[j / 2 + 1], a2, a3);
-      sts_f4(ob + (((cb + j / 4) ^ swz) << 4), a0, a1, a2, a3);
+      if (!GDBG(e, 2)) sts_f4(ob + (((cb + j / 4) ^ swz) << 4), a0, a1, a2, a3);
     }
   } else {
 #pragma unroll
@@ -292,7 +304,8 @@ __device__ __forceinline__ void staged_row(const EpiParams& e, const uint32_t (&
         f2_unpack(v[j / 2 + t], a0, a1);
         pk[t] = pack_bf16(a0, a1);
       }
-      sts_u4(ob + (((cb + j / 8) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+      if (!GDBG(e, 2)) sts_u4(ob + (((cb + j / 8) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+      else if (pk[0] == 0x12345678u && pk[3] == 0x9abcdef0u) sts_u4(ob, pk[0], pk[1], pk[2], pk[3]);  // keep the math alive
     }
   }
 }
@@ -482,10 +495,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == 3 || (warp == 2 && epi.helpers == 2)) {
     // ------------------------------------------------------------ epilogue TMA helper (staged path only)
-    if (epi.tma && lane < 4) {
-      const int k = lane;                            // TMEM lane quarter served by this lane
+    // helpers == 1: lanes 0-3 of warp 3 serve the four quarters (ONE instruction stream: the lanes' waits and their
+    // 250-800 cycle bulk-tensor issues serialise); helpers == 2: lanes 0-1 of warps 3 and 2 (warp 2 is idle after the
+    // TMEM allocation), two quarters per instruction stream
+    if (epi.tma && lane < (epi.helpers == 2 ? 2 : 4)) {
+      const int k = (epi.helpers == 2 && warp == 2) ? lane + 2 : lane;   // TMEM lane quarter served by this lane
       const bool f32out = epi.out_f32 != 0;
       const int SUBN = f32out ? 32 : 64;
       const int n_sub = BN / SUBN;
@@ -530,7 +546,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         int m0, n0;
         q_coords(q, m0, n0);
-        if (n0 < epi.N) {
+        if (n0 < epi.N && !GDBG(epi, 4)) {
           const uint32_t so = smem_u32(sOut + qb * EPI_BUF_BYTES) + qoff;
           if (epi.accumulate) {
             asm volatile(
@@ -709,7 +725,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tmem_ld_wait();
             TRACE_T(3);
             if (!last) {
-              tmem_ld_cols<CW>(t_row + (sidx + 1) * SUBC, nxt);
+              if (!GDBG(epi, 16)) tmem_ld_cols<CW>(t_row + (sidx + 1) * SUBC, nxt);
             } else {  // accumulator drained into registers: hand the TMEM stage back to the MMA warp
               tc_fence_before();
               __syncwarp();
@@ -721,7 +737,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             TRACE_T(4);
             const int ncol0 = n0 + ehalf * CW;   // this warp's first column; the vector path needs all CW of them inside N
             const float* bvec = (bias_v && ncol0 + CW <= epi.N) ? epi.bias + ncol0 : nullptr;
-            if (live) staged_row<CW>(epi, cur, b_cur, bvec, rs, ob, ab, cb, swz, dual, CW == 16);
+            if (live && !GDBG(epi, 8)) staged_row<CW>(epi, cur, b_cur, bvec, rs, ob, ab, cb, swz, dual, CW == 16);
             b_cur = b_nxt;
             TRACE_T(5);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to TMA
@@ -878,6 +894,10 @@ extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
   if (strcmp(name, "gemm_colsum_pair") == 0) { g_colsum_pair = value; return 0; }
+  if (strcmp(name, "gemm_helpers") == 0) { g_helpers = value == 2 ? 2 : 1; return 0; }
+#ifdef VTB_GEMM_DBG
+  if (strcmp(name, "gemm_dbg") == 0) { g_gemm_dbg = value; return 0; }
+#endif
   if (strcmp(name, "attn_tc") == 0) { vtb_attn_tc_set(value != 0); return 0; }
   if (strcmp(name, "attn_tc_fwd_version") == 0) { vtb_attn_tc_version_set(value, 0); return 0; }
   if (strcmp(name, "attn_tc_bwd_version") == 0) { vtb_attn_tc_version_set(0, value); return 0; }
@@ -928,6 +948,12 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   e.accumulate = p->accumulate;
   e.alpha = p->alpha;
   e.a_colsum = p->a_colsum;
+  e.helpers = g_helpers;
+#ifdef VTB_GEMM_DBG
+  e.dbg = g_gemm_dbg;
+#else
+  e.dbg = 0;
+#endif
   {  // 16-byte vector epilogue only when every touched row start is 16-byte aligned; scalar path otherwise
     const int oalign = p->out_f32 ? 4 : 8;
     bool v = (p->ldo % oalign == 0) && (((uintptr_t)p->out & 15) == 0);
