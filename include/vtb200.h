@@ -205,6 +205,14 @@ int vtb_scale_cast_bf16(const float* src, const float* row_scale, int32_t rows_p
  * the scaled gradient IS that Linear's output gradient).  colsum f32 [cols], accumulated with atomicAdd. */
 int vtb_scale_cast_colsum_bf16(const float* src, const float* row_scale, int32_t rows_per_scale, int64_t rows,
                                int32_t cols, void* dst, float* colsum, vtb_stream_t stream);
+/* Element dropout with a caller-drawn keep mask (uint8, one byte per element; the host draws it with torch's generator in the
+ * reference's call order so that a shared seed gives the reference's masks):
+ *   out[i] = resid[i] + row_scale[i / elems_per_scale] * (keep[i] ? x[i] * scale : 0)      (resid / row_scale NULL => 0 / 1)
+ * x / out are f32 (is_f32) or bf16; out may alias x.  Replaces nn.Dropout in PositionwiseFeedForward (layer.py:194), on the
+ * branch outputs and the token embedding of ViT (vit.py:57-61,102,146) and on PVT's patch embedding (pvt.py:127,141); the
+ * residual form is the DropPath + residual step of a ViT branch (vit.py:60-61).  The adjoint is the same call on the gradient. */
+int vtb_dropout(const void* x, const uint8_t* keep, float scale, int64_t n, int32_t is_f32, const float* resid,
+                const float* row_scale, int64_t elems_per_scale, void* out, vtb_stream_t stream);
 /* SiLU on f32 (halo_transformer.py:218) and its adjoint. */
 int vtb_silu_fwd(const float* x, float* y, int64_t n, vtb_stream_t stream);
 int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, vtb_stream_t stream);

@@ -12,6 +12,7 @@ oracle/ref_loader.py and (b) the golden fixtures.  The reference itself ships no
 
 Each function cites the reference lines it restates (paths relative to the reference root).
 """
+import contextlib
 import math
 
 import torch
@@ -36,9 +37,38 @@ def linear(x, w, b=None):
     return y if b is None else y + b
 
 
+class _ElementDropout:
+    masks, sites, i = None, frozenset(), 0
+
+
+_ED = _ElementDropout()
+
+
+@contextlib.contextmanager
+def element_dropout(masks, sites):
+    """Replays nn.Dropout keep masks — (keep, 1 / (1 - p)) pairs in the reference's call order — at the named sites:
+    "ffn" (layer.py:194), "branch" (vit.py:60-61), "pos" (vit.py:146), "patch" (pvt.py:141).  Outside this context every
+    Dropout is the identity (p = 0 / eval mode)."""
+    _ED.masks, _ED.sites, _ED.i = list(masks), frozenset(sites), 0
+    try:
+        yield
+        assert _ED.i == len(_ED.masks), f"{len(_ED.masks) - _ED.i} dropout masks were never consumed"
+    finally:
+        _ED.masks, _ED.sites, _ED.i = None, frozenset(), 0
+
+
+def _drop(x, site):
+    if _ED.masks is None or site not in _ED.sites:
+        return x
+    keep, scale = _ED.masks[_ED.i]
+    _ED.i += 1
+    return x * keep.reshape(x.shape).to(x.dtype) * scale
+
+
 def ffn(x, sd, pre):
-    """PositionwiseFeedForward: Linear(idx 0) - SiLU - Dropout(p=0) - Linear(idx 3)  (layer.py:186-196)."""
-    return linear(silu(linear(x, sd[pre + "0.weight"], sd[pre + "0.bias"])), sd[pre + "3.weight"], sd[pre + "3.bias"])
+    """PositionwiseFeedForward: Linear(idx 0) - SiLU - Dropout - Linear(idx 3)  (layer.py:186-196)."""
+    hidden = _drop(silu(linear(x, sd[pre + "0.weight"], sd[pre + "0.bias"])), "ffn")
+    return linear(hidden, sd[pre + "3.weight"], sd[pre + "3.bias"])
 
 
 def _dp(branch, scale):
@@ -106,10 +136,10 @@ def mhsa_global(x, sd, pre, heads):
 
 def vit_layer(x, sd, pre, heads, dps):
     """vit.py:59-63."""
-    x = x + _dp(mhsa_global(layer_norm(x, sd[pre + "norm_attn.weight"], sd[pre + "norm_attn.bias"], 1e-6), sd,
-                            pre + "attn.", heads), dps.next())
-    x = x + _dp(ffn(layer_norm(x, sd[pre + "norm_ff.weight"], sd[pre + "norm_ff.bias"], 1e-6), sd, pre + "ff."),
-                dps.next())
+    x = x + _dp(_drop(mhsa_global(layer_norm(x, sd[pre + "norm_attn.weight"], sd[pre + "norm_attn.bias"], 1e-6), sd,
+                                  pre + "attn.", heads), "branch"), dps.next())
+    x = x + _dp(_drop(ffn(layer_norm(x, sd[pre + "norm_ff.weight"], sd[pre + "norm_ff.bias"], 1e-6), sd, pre + "ff."),
+                      "branch"), dps.next())
     return x
 
 
@@ -118,7 +148,7 @@ def vit_features(sd, img, *, patch, depth, heads, dp_scales=None):
     dps = DropPathScales(dp_scales)
     tok = vit_patch_tokens(img, sd["patch_embedding.linear.weight"], sd["patch_embedding.linear.bias"], patch)
     x = torch.cat((sd["cls_token"].expand(tok.shape[0], -1, -1), tok), 1)
-    x = x + vit_pos_embed(sd["pos_embed"], tok.shape[1])
+    x = _drop(x + vit_pos_embed(sd["pos_embed"], tok.shape[1]), "pos")
     for i in range(depth):
         x = vit_layer(x, sd, f"layers.{i}.", heads, dps)
     x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], 1e-6)
@@ -291,7 +321,7 @@ def pvt_forward(sd, img, *, depths, n_heads, reductions, dp_scales=None):
         x = layer_norm(x.reshape(B, Hs * Ws, -1), sd[pe + "norm.weight"], sd[pe + "norm.bias"], 1e-6)
         if pe + "cls_token" in sd:
             x = torch.cat((sd[pe + "cls_token"].view(1, 1, -1).expand(B, -1, -1), x), 1)
-        x = x + sd[pe + "pos"][None]
+        x = _drop(x + sd[pe + "pos"][None], "patch")
         for i in range(depths[st]):
             pre = f"block{st + 1}.{i}."
             x = x + _dp(pvt_attention(layer_norm(x, sd[pre + "norm_attn.weight"], sd[pre + "norm_attn.bias"], 1e-6),

@@ -180,6 +180,29 @@ def test_gemm_wgrad_with_fused_bias_gradient(ops, gemm_mode, T, N, K):
     assert rel(db, 2 * g.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_kernel(ops, dtype):
+    """vtb_dropout: out = resid + row_scale[row] * (keep ? x * scale : 0), in place or not, f32 / bf16."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    rows, cols, rps = 6 * 17, 40, 17
+    x = torch.randn(rows, cols, device="cuda", generator=g).to(dtype)
+    keep = torch.rand(rows, cols, device="cuda", generator=g) > 0.3
+    scale = 1 / 0.7
+    want = torch.where(keep, x.float() * scale, torch.zeros((), device="cuda")).to(dtype)
+    assert torch.equal(ops.dropout(x, keep, scale), want)
+    y = x.clone()
+    assert ops.dropout(y, keep, scale, out=y) is y and torch.equal(y, want)
+    if dtype == torch.float32:
+        resid = torch.randn(rows, cols, device="cuda", generator=g)
+        rs = torch.tensor([0., 2., 2., 0., 2., 2.], device="cuda")
+        got = ops.dropout(x, keep, scale, resid=resid, row_scale=rs, rows_per_scale=rps)
+        ref = resid + rs.repeat_interleave(rps)[:, None] * torch.where(keep, x * scale, torch.zeros((), device="cuda"))
+        assert rel(got, ref) < 1e-6
+    else:
+        with pytest.raises(ValueError):
+            ops.dropout(x, keep, scale, resid=x)
+
+
 def test_gemm_unaligned_output_falls_back_to_direct_path(ops, gemm_mode):
     """N=10 / N=50 heads: rows are not 16-byte multiples -> per-thread epilogue instead of TMA stores."""
     g = torch.Generator(device="cuda").manual_seed(8)

@@ -123,6 +123,104 @@ def test_vit_train_mode_droppath_matches_oracle_with_shared_masks(monkeypatch):
             assert rel(p.grad, sd[k].grad) < GRAD_TOL, k
 
 
+@pytest.mark.parametrize("name", ["vit", "vit_ff_only", "swin", "pvt"])
+def test_element_dropout_matches_reference_golden(name, monkeypatch):
+    """nn.Dropout p > 0 in train mode (layer.py:194, vit.py:56-61,102,146, pvt.py:127,141): the UNMODIFIED reference ran
+    with these keep masks (oracle/make_dropout_golden.py records them call by call); the product replays them in its own
+    call order — which therefore has to be the reference's — and must give the reference's output and gradients."""
+    from vtb200 import blocks
+
+    fx = load_golden("dropout_ops")[name]
+    model = build(fx).train()
+    queue = [(m.cuda(), s) for m, s in fx["masks"]]
+    calls = []
+
+    def replay(training, p, shape, dtype, device):
+        if not training or float(p) == 0:
+            return None
+        keep, scale = queue[len(calls)]
+        assert tuple(keep.shape) == tuple(shape) and abs(scale - 1 / (1 - float(p))) < 1e-6, (len(calls), keep.shape, shape)
+        calls.append(p)
+        return keep.contiguous(), scale
+
+    monkeypatch.setattr(blocks, "make_dropout_keep", replay)
+    out = model(fx["input"].cuda())
+    assert len(calls) == len(queue), (len(calls), len(queue))
+    want = fx["output"].cuda()
+    assert rel(out, want) < OUT_TOL, rel(out, want)
+    assert cos(out, want) > 0.999
+    (out * fx["probe"].cuda()).sum().backward()
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        g = fx["grads"][k].cuda()
+        assert p.grad is not None, k
+        if g.norm() < 1e-6 * max(1.0, g.numel() ** 0.5):
+            continue
+        worst = max(worst, (k, rel(p.grad, g)), key=lambda t: t[1])
+    assert worst[1] < GRAD_TOL, worst
+    # eval mode draws nothing and is the plain forward
+    n = len(calls)
+    with torch.no_grad():
+        model.eval()(fx["input"].cuda())
+    assert len(calls) == n
+
+
+def test_element_dropout_own_draws_match_oracle_replay(monkeypatch):
+    """The product's own mask draws (torch generator, F.dropout on ones) recorded and replayed in the oracle: ViT with
+    dropout, drop_ff AND drop_path active, so the interleaving with the DropPath draws is covered too."""
+    import models
+    from oracle import restate as R
+    from vtb200 import blocks
+
+    torch.manual_seed(3)
+    cfg = dict(head=None, image_size=64, window_size=16, depth=2, dim=128, n_head=2, dim_ff=256, dropout=0.1, drop_attn=0.,
+               drop_ff=0.3, drop_path=0.4)
+    model = R.randomize_(models.VisionTransformer(**cfg), 5).cuda().train()
+    masks, scales = [], []
+    orig_keep, orig_dp = blocks.make_dropout_keep, blocks.make_drop_path_scale
+
+    def spy_keep(*a):
+        km = orig_keep(*a)
+        if km is not None:
+            masks.append(km)
+        return km
+
+    def spy_dp(*a):
+        sc = orig_dp(*a)
+        scales.append(sc)
+        return sc
+
+    monkeypatch.setattr(blocks, "make_dropout_keep", spy_keep)
+    monkeypatch.setattr(blocks, "make_drop_path_scale", spy_dp)
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    out = model(x)
+    assert len(masks) == 1 + 3 * 2 and len(scales) == 4
+    fracs = [m.float().mean().item() for m, _ in masks]
+    assert all(0.5 < f < 0.98 for f in fracs), fracs
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    dps = [s if s is not None else torch.ones(8, device="cuda") for s in scales]
+    with R.element_dropout(masks, ("pos", "branch", "ffn")):
+        want = R.vit_forward(sd, x, patch=16, depth=2, heads=2, dp_scales=dps)
+    assert rel(out, want) < OUT_TOL
+    probe = torch.randn_like(out)
+    (out * probe).sum().backward()
+    (want * probe).sum().backward()
+    for k, p in model.named_parameters():
+        if sd[k].grad.norm() > 1e-6:
+            assert rel(p.grad, sd[k].grad) < GRAD_TOL, k
+
+
+def test_attention_probability_dropout_is_rejected_loudly():
+    import models
+
+    cfg = dict(head=None, image_size=64, window_size=16, depth=1, dim=128, n_head=2, dim_ff=256, dropout=0., drop_attn=0.1,
+               drop_ff=0., drop_path=0.)
+    model = models.VisionTransformer(**cfg).cuda().train()
+    with pytest.raises(NotImplementedError, match="drop_attn"):
+        model(torch.randn(2, 3, 64, 64, device="cuda"))
+    model.eval()(torch.randn(2, 3, 64, 64, device="cuda"))  # eval mode never drops
+
+
 @pytest.mark.parametrize("drop_path", [0.0, 0.5])
 def test_backward_handoff_is_used_and_changes_nothing(drop_path):
     """The LayerNorm backward hands bf16(dx * scale) + its column sums to the next branch backward
@@ -229,10 +327,3 @@ def test_fp16_autocast_with_grad_scaler_steps_like_the_unscaled_run():
             assert rel(b - c, a - c) < 1e-3, (k, rel(b - c, a - c))
     assert moved > 10
 
-
-def test_dropout_is_rejected_loudly():
-    import models
-
-    m = models.VisionTransformer(None, 32, 8, 1, 64, 2, 128, 0.1, 0., 0., 0.).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(2, 3, 32, 32, device="cuda"))

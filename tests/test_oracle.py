@@ -152,3 +152,63 @@ def test_dino_golden_reproduces_from_reference():
         head = ref.vit.DINOHead(**h["ctor"])
         head.load_state_dict(h["state_dict"])
         assert rel(head(h["x"]), h["output"]) < 1e-6, name
+
+
+# ------------------------------------------------------------------------------------------- element dropout (train mode)
+DROPOUT_CASES = ["vit", "vit_ff_only", "swin", "pvt"]
+
+
+@pytest.mark.parametrize("name", DROPOUT_CASES)
+def test_oracle_element_dropout_sites_match_reference_golden(name):
+    """The restatement's nn.Dropout sites (layer.py:194, vit.py:60-61,146, pvt.py:141), replaying the keep masks the
+    UNMODIFIED reference ran with in train mode (oracle/make_dropout_golden.py): same output, same gradients."""
+    fx = load_golden("dropout_ops")[name]
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in fx["state_dict"].items()}
+    with R.element_dropout(fx["masks"], fx["sites"]):
+        out = FWD[fx["family"]](sd, fx["input"], **fx["oracle_kwargs"])
+    assert rel(out, fx["output"]) < 5e-6
+    (out * fx["probe"]).sum().backward()
+    for k, g in fx["grads"].items():
+        assert rel(sd[k].grad, g) < 2e-4, (k, rel(sd[k].grad, g))
+    # without the masks the oracle is the eval-mode forward: a different result (the fixture really dropped something)
+    assert rel(FWD[fx["family"]](sd, fx["input"], **fx["oracle_kwargs"]), fx["output"]) > 1e-2
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("name", DROPOUT_CASES)
+def test_dropout_golden_reproduces_from_reference_with_its_own_masks(name):
+    """The fixture equals the unmodified reference in train mode with nn.Dropout's OWN masks under the recorded generator
+    state — i.e. the recorded masks are the masks torch draws, in the order the reference draws them."""
+    from oracle.make_golden import build
+
+    fx = load_golden("dropout_ops")[name]
+    ref = ref_loader.load()
+    model = build(ref, fx["family"], fx["ctor"]).train()
+    model.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(fx["seed"] + 7)
+    out = model(fx["input"].clone())
+    assert torch.equal(out.detach(), fx["output"])
+
+
+def test_make_dropout_keep_draws_what_nn_dropout_draws():
+    """vtb200.blocks.make_dropout_keep (the product's mask source) = the mask of nn.Dropout on a tensor of that shape /
+    dtype under the same generator state; nothing is drawn in eval mode or at p = 0."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vision-transformers-pytorch_b200"))
+    from vtb200.blocks import make_dropout_keep
+
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(3, 17, 40).to(dtype) + 3  # no exact zeros
+        torch.manual_seed(11)
+        want = torch.nn.Dropout(0.3).train()(x).ne(0)
+        torch.manual_seed(11)
+        keep, scale = make_dropout_keep(True, 0.3, x.shape, dtype, "cpu")
+        assert keep.dtype == torch.bool and torch.equal(keep, want) and abs(scale - 1 / 0.7) < 1e-12
+    state = torch.get_rng_state()
+    assert make_dropout_keep(False, 0.3, (4, 4), torch.float32, "cpu") is None
+    assert make_dropout_keep(True, 0.0, (4, 4), torch.float32, "cpu") is None
+    assert torch.equal(torch.get_rng_state(), state)
+    keep, scale = make_dropout_keep(True, 1.0, (4, 4), torch.float32, "cpu")
+    assert not keep.any() and scale == 0.0

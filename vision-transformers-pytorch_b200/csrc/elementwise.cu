@@ -530,6 +530,41 @@ extern "C" int vtb_silu_bwd(const float* x, const float* dy, float* dx, int64_t 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- element dropout
+// out = resid + row_scale[row] * (keep ? x * scale : 0): nn.Dropout applied to an activation (layer.py:194, vit.py:57-61,
+// pvt.py:141) with the keep mask drawn by torch's own generator (vtb200.blocks.make_dropout_keep), its adjoint (same
+// call on the gradient), and — with resid / row_scale — the DropPath + residual step of a ViT branch whose output
+// Linear can no longer fuse them once a per-element mask sits in between.  No reference config uses p > 0.
+namespace {
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, const uint8_t* __restrict__ keep, float scale,
+                               const float* __restrict__ resid, const float* __restrict__ row_scale,
+                               long elems_per_scale, long n, T* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = keep[i] ? (float)x[i] * scale : 0.f;
+    if (row_scale) v *= __ldg(row_scale + i / elems_per_scale);
+    if (resid) v += resid[i];
+    out[i] = (T)v;
+  }
+}
+}  // namespace
+
+extern "C" int vtb_dropout(const void* x, const uint8_t* keep, float scale, int64_t n, int32_t is_f32,
+                           const float* resid, const float* row_scale, int64_t elems_per_scale, void* out,
+                           vtb_stream_t s) {
+  VTB_CHECK(x && keep && out && n > 0, -1, "vtb_dropout: bad args");
+  VTB_CHECK(!row_scale || elems_per_scale > 0, -1, "vtb_dropout: elems_per_scale");
+  VTB_CHECK(!resid || is_f32, -1, "vtb_dropout: the residual form is fp32 only");
+  if (is_f32)
+    dropout_kernel<float><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)s>>>((const float*)x, keep, scale, resid, row_scale,
+                                                                            elems_per_scale, n, (float*)out);
+  else
+    dropout_kernel<bf16><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)s>>>((const bf16*)x, keep, scale, resid, row_scale,
+                                                                           elems_per_scale, n, (bf16*)out);
+  VTB_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- validation mode
 // fp32 -> three bf16 column blocks of one GEMM operand row, so that ONE tcgen05 GEMM with K' = 3K accumulates
 //   a_hi b_hi + a_lo b_hi + a_hi b_lo   (hi = bf16(x), lo = bf16(x - hi): ~16 mantissa bits per operand, fp32 accumulation)

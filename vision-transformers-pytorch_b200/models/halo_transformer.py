@@ -71,7 +71,7 @@ class TransformerLayer(nn.Module):
         from vtb200.blocks import AttnBranchFn
 
         a = self.attn
-        check_no_dropout(self, a.dropout, self.ff[2].p)
+        check_no_dropout(self, a.dropout)
         B, H, W, _ = input.shape
         w, hl = a.window_size, a.halo_size
         geom = dict(mode=_l.ATTN_HALO, batch=B, heads=a.n_head, dh=a.dim_head, nq=w * w,

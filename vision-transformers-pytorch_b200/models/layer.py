@@ -68,18 +68,33 @@ class PositionwiseFeedForward(nn.Sequential):
 
 
 def check_no_dropout(module, *ps):
-    """nn.Dropout with p > 0 in training mode is not fused (every BASELINE config uses 0)."""
+    """Dropout on the attention PROBABILITIES (vit.py:39, swin:144, pvt.py:62, halo:101, twins) with p > 0 in training mode
+    is rejected: the probabilities never leave the attention kernels' tensor memory, a mask there would have to be drawn
+    inside every kernel (every reference config uses drop_attn = 0).  The other nn.Dropout sites — FFN hidden, ViT branch
+    outputs / token embedding, PVT patch embedding — are implemented (vtb200.blocks.make_dropout_keep / vtb_dropout)."""
     if module.training and any(float(p) > 0 for p in ps):
-        raise NotImplementedError("vtb200: element dropout p > 0 is not implemented in the fused blocks "
-                                  "(all reference configs use dropout = drop_attn = drop_ff = 0)")
+        raise NotImplementedError("vtb200: dropout on the attention probabilities (drop_attn > 0) is not implemented in the "
+                                  "tcgen05 attention kernels (all reference configs use drop_attn = 0); dropout / drop_ff "
+                                  "are supported")
 
 
-def ffn_branch(x, drop_path, norm, ff, rows_per_sample):
-    from vtb200.blocks import FFNBranchFn
+def autocast_dtype(x):
+    """dtype an activation has at this point of the reference's forward: the autocast dtype inside torch.autocast
+    (train.py:273), the input's own dtype otherwise — torch's dropout kernel draws its mask per dtype-sized vector."""
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+
+
+def ffn_branch(x, drop_path, norm, ff, rows_per_sample, out_dropout=None):
+    """x + drop_path(out_dropout(ff(norm(x)))).  RNG draws in the reference's order: the Dropout inside the FFN
+    (layer.py:194), the Dropout on the branch output (ViT only, vit.py:61), then the DropPath mask."""
+    from vtb200.blocks import FFNBranchFn, make_dropout_keep
 
     w1, b1, w2, b2 = ff.params()
+    dt = autocast_dtype(x)
+    ff_drop = make_dropout_keep(ff.training, ff[2].p, (*x.shape[:-1], w1.shape[0]), dt, x.device)
+    out_drop = None if out_dropout is None else make_dropout_keep(out_dropout.training, out_dropout.p, x.shape, dt, x.device)
     return FFNBranchFn.apply(x, drop_path.scale(x.shape[0]), norm.eps, rows_per_sample, norm.weight,
-                             norm.bias, w1, b1, w2, b2)
+                             norm.bias, w1, b1, w2, b2, ff_drop, out_drop)
 
 
 def init_transformer_weights(module, std=0.02):

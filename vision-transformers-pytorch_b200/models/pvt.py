@@ -45,7 +45,7 @@ class TransformerLayer(nn.Module):
         from vtb200.blocks import SRABranchFn
 
         a = self.attn
-        check_no_dropout(self, a.dropout, self.ff[2].p)
+        check_no_dropout(self, a.dropout)
         B, N, _ = input.shape
         cfg = dict(heads=a.n_head, reduction=a.reduction, height=height, width=width)
         red = a.reduction > 1
@@ -79,13 +79,12 @@ class PatchEmbedding(nn.Module):
         self.patch = size[0]
 
     def forward(self, input):
-        from vtb200.blocks import PVTPatchEmbedFn
+        from vtb200.blocks import PVTPatchEmbedFn, dropout
 
-        check_no_dropout(self, self.dropout.p)
         height, width = input.shape[2] // self.patch, input.shape[3] // self.patch
         out = PVTPatchEmbedFn.apply(input, self.patch, self.norm.eps, self.conv.weight, self.conv.bias,
                                     self.norm.weight, self.norm.bias, self.pos, self.cls_token)
-        return out, (height, width)
+        return dropout(out, self.dropout), (height, width)  # pvt.py:141
 
 
 class PyramidVisionTransformer(nn.Module):

@@ -106,7 +106,7 @@ class TransformerLayer(nn.Module):
         from vtb200.blocks import AttnBranchFn
 
         a = self.attn
-        check_no_dropout(self, a.dropout, self.ff[2].p)
+        check_no_dropout(self, a.dropout)
         B, H, W, _ = input.shape
         w = a.window_size
         pos, mask = a.tables()

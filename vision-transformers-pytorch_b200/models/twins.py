@@ -80,7 +80,7 @@ class TransformerLayer(nn.Module):
         from vtb200.blocks import AttnBranchFn, SRABranchFn
 
         la, ga = self.attn_local, self.attn_global
-        check_no_dropout(self, la.dropout, ga.dropout, self.ff_local[2].p, self.ff_global[2].p)
+        check_no_dropout(self, la.dropout, ga.dropout)
         B, H, W, _ = input.shape
         w = la.window_size
         geom = dict(mode=_l.ATTN_WINDOW, batch=B, heads=la.n_head, dh=la.dim_head, nq=w * w, nkv=w * w, Hs=H, Ws=W,

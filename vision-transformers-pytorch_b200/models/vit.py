@@ -9,7 +9,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .dino import DINOHead, dino  # noqa: F401  (vit.py:206-307 of the reference)
-from .layer import (DropPath, PositionwiseFeedForward, assign_drop_path, check_no_dropout, ffn_branch,
+from .layer import (DropPath, PositionwiseFeedForward, assign_drop_path, autocast_dtype, check_no_dropout, ffn_branch,
                     init_transformer_weights, linspace_rates, tuple2)
 
 LN_EPS = 1e-6  # vit.py:13
@@ -47,15 +47,18 @@ class TransformerLayer(nn.Module):
 
     def forward(self, input):
         from vtb200 import lib as _l
-        from vtb200.blocks import AttnBranchFn
+        from vtb200.blocks import AttnBranchFn, make_dropout_keep
 
-        check_no_dropout(self, self.dropout.p, self.attn.dropout.p, self.ff[2].p)
+        check_no_dropout(self, self.attn.dropout.p)
         batch, tokens = input.shape[0], input.shape[1]
         att, ln = self.attn, self.norm_attn
         geom = dict(mode=_l.ATTN_GLOBAL, batch=batch, heads=att.n_head, dh=att.dim_head, nq=tokens, nkv=tokens)
+        # vit.py:60: drop_path(dropout(attn(...))) — the Dropout mask is drawn before the DropPath mask
+        out_drop = make_dropout_keep(self.dropout.training, self.dropout.p, input.shape, autocast_dtype(input), input.device)
         hidden = AttnBranchFn.apply(input, self.drop_path.scale(batch), ln.eps, tokens, geom, None, None, ln.weight,
-                                    ln.bias, att.qkv.weight, att.qkv.bias, att.linear.weight, att.linear.bias, None)
-        return ffn_branch(hidden, self.drop_path, self.norm_ff, self.ff, tokens)
+                                    ln.bias, att.qkv.weight, att.qkv.bias, att.linear.weight, att.linear.bias, None,
+                                    out_drop)
+        return ffn_branch(hidden, self.drop_path, self.norm_ff, self.ff, tokens, out_dropout=self.dropout)
 
 
 class PatchEmbedding(nn.Module):
@@ -106,14 +109,14 @@ class VisionTransformer(nn.Module):
         return torch.cat((pos_embed[:, :1], grid.permute(0, 2, 3, 1).reshape(1, -1, dim)), 1)
 
     def forward_feature(self, input):
-        from vtb200.blocks import LayerNormFn, ViTPatchEmbedFn
+        from vtb200.blocks import LayerNormFn, ViTPatchEmbedFn, dropout
 
-        check_no_dropout(self, self.pos_drop.p)
         patch = self.patch_embedding.window_size
         n_patch = (input.shape[-2] // patch) * (input.shape[-1] // patch)
         conv = self.patch_embedding.linear
         tokens = ViTPatchEmbedFn.apply(input, conv.weight, conv.bias, self.cls_token,
                                        self.interpolate_pos_embedding(n_patch, self.pos_embed), patch)
+        tokens = dropout(tokens, self.pos_drop)  # vit.py:146
         for layer in self.layers:
             tokens = layer(tokens)
         # the final LayerNorm is row-wise, so only the cls rows that are returned need it (vit.py:149-151)

@@ -119,13 +119,71 @@ def make_drop_path_scale(module_training, p, batch, like):
     return (mask.to(F32) / keep).reshape(batch).contiguous()
 
 
+def make_dropout_keep(module_training, p, shape, dtype, device):
+    """Keep mask of an nn.Dropout(p) applied to a tensor of this shape / dtype (layer.py:194, vit.py:56,102, pvt.py:127),
+    drawn from torch's global generator by the very call nn.Dropout makes (F.dropout on a dense tensor), so that under a
+    shared seed — and with the draws made in the reference's order — the masks are the reference's.  Returns
+    (bool tensor, 1 / (1 - p)) or None when the module is in eval mode or p == 0 (F.dropout draws nothing then)."""
+    p = float(p)
+    if not module_training or p == 0:
+        return None
+    if p >= 1:
+        return torch.zeros(shape, dtype=torch.bool, device=device), 0.0
+    kept = torch.nn.functional.dropout(torch.ones(shape, dtype=dtype, device=device), p, True)
+    return kept.ne_(0).to(torch.bool), 1.0 / (1.0 - p)
+
+
+class DropoutFn(Function):
+    """Stand-alone element dropout (ViT pos_drop vit.py:146, PVT patch embedding pvt.py:141): y = keep ? x / (1-p) : 0."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, keep, scale):
+        ctx.keep, ctx.scale = keep, scale
+        return ops.dropout(_c(x), keep, scale)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        return ops.dropout(_c(dy), ctx.keep, ctx.scale), None, None
+
+
+def dropout(x, module):
+    """nn.Dropout `module` applied to x through the library (identity in eval mode / at p = 0)."""
+    km = make_dropout_keep(module.training, module.p, x.shape, x.dtype, x.device)
+    return x if km is None else DropoutFn.apply(x, km[0], km[1])
+
+
+def _branch_output(a, w_bf16, bias, x2, dp_scale, rows_per_sample, out_drop):
+    """x + dp * Dropout(a W^T + b): bias, DropPath scale and residual ride in the GEMM epilogue; with an element mask in
+    between (ViT `dropout` > 0, vit.py:60-61) the Linear writes fp32 and one elementwise pass applies mask, scale and
+    residual."""
+    if out_drop is None:
+        return ops.gemm(a, w_bf16, out_dtype=F32, bias=bias, resid=x2, row_scale=dp_scale, rows_per_scale=rows_per_sample)
+    lin = ops.gemm(a, w_bf16, out_dtype=F32, bias=bias)
+    return ops.dropout(lin, out_drop[0], out_drop[1], out=lin, resid=x2, row_scale=dp_scale,
+                       rows_per_scale=rows_per_sample)
+
+
+def _branch_grad_operand(d2, dp_scale, rps, out_drop):
+    """Gradient operand of the Linear that closes a branch and that Linear's bias gradient (see _grad_operand); with an
+    output Dropout the mask is applied to the bf16 operand and the column sums are taken again."""
+    g, db = _grad_operand(d2, dp_scale, rps)
+    if out_drop is not None:
+        ops.dropout(g, out_drop[0], out_drop[1], out=g)
+        db = ops.colsum(g)
+    return g, db
+
+
 # ----------------------------------------------------------------------------------------- FFN branch
 class FFNBranchFn(Function):
     """x + dp * (W2 silu(W1 LN(x) + b1) + b2)      (layer.py:186-196 inside vit.py:61 etc.)"""
 
     @staticmethod
     @_fwd
-    def forward(ctx, x, dp_scale, eps, rows_per_sample, ln_w, ln_b, w1, b1, w2, b2):
+    def forward(ctx, x, dp_scale, eps, rows_per_sample, ln_w, ln_b, w1, b1, w2, b2, ff_drop=None, out_drop=None):
+        # ff_drop / out_drop: (keep, scale) of the Dropout between SiLU and the second Linear (layer.py:194) and of the
+        # Dropout on the branch output (ViT only, vit.py:61), or None
         shape = x.shape
         C = shape[-1]
         x2 = _c(x).view(-1, C)
@@ -135,26 +193,29 @@ class FFNBranchFn(Function):
         u = torch.empty((T, FF), dtype=ops.act_dtype(), device=x.device)
         h = torch.empty((T, FF), dtype=ops.act_dtype(), device=x.device)
         ops.gemm(y, w1b, out=u, out2=h, bias=b1, epilogue=_l.EPI_SILU_DUAL)
-        out = ops.gemm(h, w2b, out_dtype=F32, bias=b2, resid=x2, row_scale=dp_scale,
-                       rows_per_scale=rows_per_sample)
+        if ff_drop is not None:
+            ops.dropout(h, ff_drop[0], ff_drop[1], out=h)  # backward only ever needs the dropped activation
+        out = _branch_output(h, w2b, b2, x2, dp_scale, rows_per_sample, out_drop)
         ctx.save_for_backward(x2, ln_w, mean, rstd)
-        ctx.stash = (y, u, h, w1b, w2b, dp_scale, rows_per_sample, _producer_of(x))
+        ctx.stash = (y, u, h, w1b, w2b, dp_scale, rows_per_sample, _producer_of(x), ff_drop, out_drop)
         return _register_output(out.view(shape), dp_scale, rows_per_sample)
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         x2, ln_w, mean, rstd = ctx.saved_tensors
-        y, u, h, w1b, w2b, dp_scale, rps, up = ctx.stash
+        y, u, h, w1b, w2b, dp_scale, rps, up, ff_drop, out_drop = ctx.stash
         C = x2.shape[1]
         d2 = _c(dout).view(-1, C)
-        g, db2 = _grad_operand(d2, dp_scale, rps)
+        g, db2 = _branch_grad_operand(d2, dp_scale, rps, out_drop)
         dw2 = _wgrad(g, h)
         du = _dgrad(g, w2b, epilogue=_l.EPI_SILU_GRAD, aux=u)
+        if ff_drop is not None:
+            ops.dropout(du, ff_drop[0], ff_drop[1], out=du)
         dw1, db1 = _wgrad(du, y, bias_grad=True)
         dy = _dgrad(du, w1b)
         dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
-        return dx.view(dout.shape), None, None, None, dg, dbeta, dw1, db1, dw2, db2
+        return dx.view(dout.shape), None, None, None, dg, dbeta, dw1, db1, dw2, db2, None, None
 
 
 # ------------------------------------------------------------------------------ fused-QKV attention branch
@@ -167,7 +228,7 @@ class AttnBranchFn(Function):
     @staticmethod
     @_fwd
     def forward(ctx, x, dp_scale, eps, rows_per_sample, geom, pos, mask, ln_w, ln_b, w_qkv, b_qkv, w_o,
-                b_o, rel_pos):
+                b_o, rel_pos, out_drop=None):
         shape = x.shape
         C = shape[-1]
         x2 = _c(x).view(-1, C)
@@ -178,21 +239,21 @@ class AttnBranchFn(Function):
         rel = _c(rel_pos) if rel_pos is not None else None
         spec = ops.AttnSpec(rel_bias=rel, pos=pos if rel is not None else None, mask=mask, **geom)
         o, lse = ops.attention_fwd(spec, qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:])
-        out = ops.gemm(o, wob, out_dtype=F32, bias=b_o, resid=x2, row_scale=dp_scale,
-                       rows_per_scale=rows_per_sample)
+        out = _branch_output(o, wob, b_o, x2, dp_scale, rows_per_sample, out_drop)
         ctx.save_for_backward(x2, ln_w, mean, rstd)
-        ctx.stash = (y, qkv, o, lse, wqb, wob, dp_scale, rows_per_sample, spec, b_qkv is not None, _producer_of(x))
+        ctx.stash = (y, qkv, o, lse, wqb, wob, dp_scale, rows_per_sample, spec, b_qkv is not None, _producer_of(x),
+                     out_drop)
         return _register_output(out.view(shape), dp_scale, rows_per_sample)
 
     @staticmethod
     @_bwd
     def backward(ctx, dout):
         x2, ln_w, mean, rstd = ctx.saved_tensors
-        y, qkv, o, lse, wqb, wob, dp_scale, rps, spec, has_bqkv, up = ctx.stash
+        y, qkv, o, lse, wqb, wob, dp_scale, rps, spec, has_bqkv, up, out_drop = ctx.stash
         C = x2.shape[1]
         HD = spec.heads * spec.dh
         d2 = _c(dout).view(-1, C)
-        g, db_o = _grad_operand(d2, dp_scale, rps)
+        g, db_o = _branch_grad_operand(d2, dp_scale, rps, out_drop)
         dw_o = _wgrad(g, o)
         do = _dgrad(g, wob)
         dqkv = torch.empty_like(qkv)
@@ -214,7 +275,7 @@ class AttnBranchFn(Function):
         dy = _dgrad(dqkv, wqb)
         dx, dg, dbeta = _ln_bwd_handoff(dy, x2, ln_w, mean, rstd, d2, up)
         return (dx.view(dout.shape), None, None, None, None, None, None, dg, dbeta, dw_qkv, db_qkv, dw_o,
-                db_o, drel)
+                db_o, drel, None)
 
 
 # ------------------------------------------------------------------- spatial-reduction attention branch

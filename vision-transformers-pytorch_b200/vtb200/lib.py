@@ -18,7 +18,7 @@ ATTN_GLOBAL, ATTN_WINDOW, ATTN_HALO = 0, 1, 2
 SYMBOLS = [
     "vtb_last_error", "vtb_version", "vtb_init", "vtb_set_option", "vtb_gemm_bf16", "vtb_layernorm_fwd",
     "vtb_layernorm_bwd", "vtb_attention_fwd", "vtb_attention_bwd", "vtb_attention_bwd_workspace_bytes", "vtb_cast_f32_bf16",
-    "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_scale_cast_colsum_bf16", "vtb_colsum_bf16", "vtb_patch_gather",
+    "vtb_cast_f32_bf16_2d", "vtb_scale_cast_bf16", "vtb_scale_cast_colsum_bf16", "vtb_colsum_bf16", "vtb_dropout", "vtb_patch_gather",
     "vtb_patch_scatter", "vtb_transpose_hw", "vtb_dwconv3x3_fwd", "vtb_dwconv3x3_bwd", "vtb_vit_assemble_tokens", "vtb_fill_rows", "vtb_rowgroup_sum", "vtb_mean_rows_fwd", "vtb_mean_rows_bwd",
     "vtb_silu_fwd", "vtb_silu_bwd", "vtb_dino_loss", "vtb_mt_num_chunks", "vtb_mt_cast_f32_bf16", "vtb_mt_ema",
     "vtb_mt_grad_norm", "vtb_mt_scale", "vtb_mt_agc", "vtb_mt_adamw", "vtb_mix_loss", "vtb_l2norm_fwd", "vtb_l2norm_bwd",
@@ -108,6 +108,7 @@ def load():
     lib.vtb_scale_cast_bf16.argtypes = [vp, vp, i32, i64, i32, vp, vp]
     lib.vtb_scale_cast_colsum_bf16.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
     lib.vtb_colsum_bf16.argtypes = [vp, i64, i32, i32, vp, vp]
+    lib.vtb_dropout.argtypes = [vp, vp, f32, i64, i32, vp, vp, i64, vp, vp]
     lib.vtb_patch_gather.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.vtb_patch_scatter.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.vtb_transpose_hw.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]

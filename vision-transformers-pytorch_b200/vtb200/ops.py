@@ -520,6 +520,31 @@ def colsum(x, out=None):
     return out
 
 
+def dropout(x, keep, scale, *, out=None, resid=None, row_scale=None, rows_per_scale=0):
+    """out = resid + row_scale[row] * (keep ? x * scale : 0) for contiguous f32 / bf16 x and a bool / uint8 keep mask of the
+    same shape (nn.Dropout with a caller-drawn mask; its adjoint is the same call on the gradient).  out may be x."""
+    lib = _l.get()
+    if x.dtype not in (F32, BF16) or not x.is_contiguous() or not keep.is_contiguous() or keep.numel() != x.numel() \
+            or keep.element_size() != 1:
+        raise ValueError("vtb200.dropout: contiguous f32 / bf16 input and a one-byte keep mask of the same size expected")
+    if out is None:
+        out = torch.empty_like(x)
+    if out.dtype != x.dtype or not out.is_contiguous() or out.numel() != x.numel():
+        raise ValueError("vtb200.dropout: out must match x")
+    if resid is not None and (x.dtype != F32 or resid.dtype != F32 or not resid.is_contiguous() or resid.numel() != x.numel()):
+        raise ValueError("vtb200.dropout: resid needs contiguous f32 operands of the same size")
+    eps = 0
+    if row_scale is not None:
+        if rows_per_scale <= 0 or row_scale.dtype != F32:
+            raise ValueError("vtb200.dropout: row_scale needs rows_per_scale > 0 and f32 scales")
+        eps = rows_per_scale * x.shape[-1]
+    with _prof("dropout"):
+        _l.check(lib.vtb_dropout(_p(x), _p(keep), float(scale), x.numel(), int(x.dtype == F32), _p(resid), _p(row_scale),
+                                 eps, _p(out), _stream()), lib)
+    _count()
+    return out
+
+
 def patch_gather(src, *, nchw, c_major, B, Cc, H, W, p):
     lib = _l.get()
     if not src.is_contiguous() or src.dtype not in (F32, BF16):
