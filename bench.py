@@ -764,7 +764,8 @@ def run_one(args, light=False):
                            "timed": "forward + cross-entropy + backward (+ gradient all-reduce); optimizer excluded per metric",
                            "execution": "CUDA graph replay of the captured step" if use_graph else "eager launches",
                            "weight_cast": "per Linear" if args.no_weight_arena else "one multi-tensor launch per forward",
-                           "host_issue_ms_per_step": host_ms},
+                           "host_issue_ms_per_step": host_ms,
+                           "nccl_registered_buckets": bool(reducer is not None and getattr(reducer, "nccl_registered", False))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "with_optimizer": with_opt}
         if e2e_u8 is not None:

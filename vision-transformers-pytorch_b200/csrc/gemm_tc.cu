@@ -42,7 +42,8 @@ __device__ unsigned long long g_trace[32];   // [0,16): epilogue phases per sub-
 #endif
 #ifdef VTB_GEMM_DBG
 int g_gemm_dbg = 0;         // knock-out probes of the staged epilogue (debug build only): 1 no bias loads, 2 no staging stores,
-                              // 4 no TMA stores, 8 no epilogue math at all, 16 no tcgen05.ld of the next sub-tile
+                              // 4 no TMA stores, 8 no epilogue math at all, 16 no tcgen05.ld of the next sub-tile,
+                              // 32 / 64 no B / A operand loads on CTA-pair tiles (stale smem: timing only)
 #define GDBG(e, bit) (((e).dbg & (bit)) != 0)
 #else
 #define GDBG(e, bit) false
@@ -422,8 +423,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else {
             // the leader's barrier collects the bytes of BOTH CTAs (its expect_tx may race with the peer's
             // complete_tx: the phase cannot complete before the leader's own arrive)
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES * CL);
-            if (!A_MN) {
+            const bool no_b = GDBG(epi, 32), no_a = GDBG(epi, 64);   // operand-traffic probes (debug build)
+            if (rank == 0)
+              mbar_expect_tx(&full_bar[stage], ((no_a ? 0 : A_STAGE_BYTES) + (no_b ? 0 : C::B_STAGE_BYTES)) * CL);
+            if (no_a) {
+            } else if (!A_MN) {
               tma_load_2d_pair(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
             } else {
 #pragma unroll
@@ -431,7 +435,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 tma_load_2d_pair(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
             }
             // this CTA's half of the B tile's N range
-            if (!B_MN) {
+            if (no_b) {
+            } else if (!B_MN) {
               tma_load_2d_pair(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN + rank * (BN / CL));
             } else {
 #pragma unroll
