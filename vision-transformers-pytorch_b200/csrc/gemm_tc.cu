@@ -590,55 +590,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // k-blocks the epilogue warps have nothing to do, so they add up the columns of the A tiles sitting in the ring
     // (A stage = two boxes of 64 k-rows x 64 m, 128B-swizzled: thread = one 16-byte chunk column of 4 k-rows) and hand
     // each stage back themselves (its `empty` barrier counts 1 commit + 8 warps).  Only CTAs on the first n-tile add.
+    // The service of the ring is a small state machine (tile, k-block, stage, phase, partial sums) instead of a phase of
+    // the tile loop: a tile's remaining k-blocks are served blocking BEFORE its drain, and during the drain every sub-tile
+    // step polls the barriers and serves whatever k-blocks of the NEXT tile have become ready — a CTA with several tiles
+    // (ViT-B QKV weight gradient: 3 per CTA) no longer stalls its ring for the length of a drain.
+    const bool cs_on = A_MN && (epi.a_colsum != nullptr);
     int rd_stage = 0;
     uint32_t rd_phase = 0;
-    auto a_colsum_phase = [&](int tile) {
-      if (!(A_MN && epi.a_colsum)) return;
-      const int ks = tile % splits;
-      const int mn = tile / splits;
-      const bool mine = (mn % n_tiles) == 0;
-      const int m_blk = (mn / n_tiles) * CL + rank;
-      const int kb0 = ks * kb_per_split, kb1 = min(k_blocks, kb0 + kb_per_split);
-      const int t = threadIdx.x - 128;                  // 0..255
-      const int cc = t & 7, box = (t >> 3) & 1, rg = t >> 4;
-      const uint32_t off = (uint32_t)box * (BK * 128) + (uint32_t)rg * 128u + (uint32_t)((cc ^ (rg & 7)) << 4);
-      float acc[8];
+    int r_tile = cta, r_kb = 0, r_kb1 = 0, r_nmod = 0;
+    float cacc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(cs_post ? &mma_done[rd_stage] : &full_bar[rd_stage], rd_phase);
-        if (cs_post ? (kb % n_tiles == mn % n_tiles) : mine) {
-          const uint32_t a = smem_u32(sA) + (uint32_t)(rd_stage * A_STAGE_BYTES) + off;
+    for (int j = 0; j < 8; ++j) cacc[j] = 0.f;
+    const int ct = threadIdx.x - 128;                  // 0..255
+    const int ccc = ct & 7, cbox = (ct >> 3) & 1, crg = ct >> 4;
+    const uint32_t coff = (uint32_t)cbox * (BK * 128) + (uint32_t)crg * 128u + (uint32_t)((ccc ^ (crg & 7)) << 4);
+    auto ring_begin = [&]() {
+      if (r_tile < total_tiles) {
+        const int ks = r_tile % splits;
+        r_nmod = (r_tile / splits) % n_tiles;
+        r_kb = ks * kb_per_split;
+        r_kb1 = min(k_blocks, r_kb + kb_per_split);
+      } else {
+        r_kb = r_kb1 = 0;
+      }
+    };
+    if (cs_on) ring_begin();
+    auto serve_one = [&](bool blocking) -> bool {
+      if (r_kb >= r_kb1) return false;
+      uint64_t* bar = cs_post ? &mma_done[rd_stage] : &full_bar[rd_stage];
+      if (blocking) mbar_wait(bar, rd_phase);
+      else if (!__any_sync(0xffffffffu, mbar_try_wait(bar, rd_phase))) return false;  // a completed phase stays completed
+      if (cs_post ? (r_kb % n_tiles == r_nmod) : (r_nmod == 0)) {
+        const uint32_t a = smem_u32(sA) + (uint32_t)(rd_stage * A_STAGE_BYTES) + coff;
 #pragma unroll
-          for (int r4 = 0; r4 < 4; ++r4) {
-            const uint4 v = lds_u4(a + r4 * (16 * 128));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const uint4 v = lds_u4(a + r4 * (16 * 128));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = unpack_bf16(w[q]);
-              acc[2 * q] += f.x; acc[2 * q + 1] += f.y;
-            }
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_bf16(w[q]);
+            cacc[2 * q] += f.x; cacc[2 * q + 1] += f.y;
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[rd_stage]);
-        if (++rd_stage == C::STAGES) { rd_stage = 0; rd_phase ^= 1; }
       }
-      if (mine || cs_post) {  // 16 row groups -> one value per column of the tile (scratch behind the mbarriers) -> global
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[rd_stage]);
+      if (++rd_stage == C::STAGES) { rd_stage = 0; rd_phase ^= 1; }
+      ++r_kb;
+      return true;
+    };
+    auto ring_poll = [&]() {
+      if (cs_on) while (serve_one(false)) {}
+    };
+    auto a_colsum_phase = [&](int tile) {   // top of the tile loop, all 8 epilogue warps: finish `tile`'s k-blocks, flush its sums
+      if (!cs_on) return;
+      while (serve_one(true)) {}
+      const int mn = tile / splits;
+      const int m_blk = (mn / n_tiles) * CL + rank;
+      if (cs_post || (mn % n_tiles) == 0) {  // 16 row groups -> one value per column of the tile (scratch behind the mbarriers) -> global
         const uint32_t s_col = smem_u32(bars) + 1024u;   // float [BM]
-        if (t < BM) sts_f32(s_col + t * 4, 0.f);
+        if (ct < BM) sts_f32(s_col + ct * 4, 0.f);
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_col + (uint32_t)(box * 64 + cc * 8 + j) * 4u), "f"(acc[j]) : "memory");
+        for (int j = 0; j < 8; ++j) {   // lanes l and l ^ 16 hold the same columns (row groups 2 w and 2 w + 1)
+          const float v = cacc[j] + __shfl_xor_sync(0xffffffffu, cacc[j], 16);
+          if (lane < 16)
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_col + (uint32_t)(cbox * 64 + ccc * 8 + j) * 4u), "f"(v) : "memory");
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (t < BM && m_blk * BM + t < epi.M) {
+        if (ct < BM && m_blk * BM + ct < epi.M) {
           float sv;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(s_col + t * 4));
-          atomicAdd(epi.a_colsum + m_blk * BM + t, sv);
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(s_col + ct * 4));
+          atomicAdd(epi.a_colsum + m_blk * BM + ct, sv);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cacc[j] = 0.f;
+      r_tile += ncl;
+      ring_begin();
     };
     if (!epi.tma) {
       // direct path (unaligned outputs): per-thread row stores; the two warps of a lane quarter alternate chunks
@@ -656,6 +686,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int c = ehalf; c < BN / 32; c += 2) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= epi.N) break;  // warp-uniform
+          ring_poll();
           uint32_t acc[32];
           tmem_ld_32x32(t_row + c * 32, acc);
           tmem_ld_wait();
@@ -724,6 +755,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t ob = smem_u32(sOut) + (uint32_t)(qb * EPI_BUF_BYTES + row * 128);
             const uint32_t ab = smem_u32(sAux) + (uint32_t)((q % N_AUX) * EPI_BUF_BYTES + row * 128);
             const float b_nxt = last ? 0.f : bias_at(sidx + 1);
+            ring_poll();   // a_colsum launches: serve the next tile's ready k-blocks (no-op otherwise)
             TRACE_T(0);
             TRACE_T(1);
             TRACE_T(2);
