@@ -48,7 +48,7 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out2=None, bias=Non
         p.row_scale, p.rows_per_scale = row_scale.addr, rows_per_scale
     if aux is not None:
         p.aux, p.ldaux = aux.addr, N
-    p.epilogue, p.splits, p.accumulate, p.alpha = epilogue, 0, int(accumulate), 1.0
+    p.epilogue, p.splits, p.accumulate, p.alpha = epilogue, (int(os.environ.get("GEMM_SPLITS", 0)) if accumulate else 0), int(accumulate), 1.0
     if a_colsum is not None:
         p.a_colsum = a_colsum.addr
     L.check(lib.vtb_gemm_bf16(C.byref(p), None), lib)

@@ -50,8 +50,8 @@ int g_gemm_dbg = 0;         // knock-out probes of the staged epilogue (debug bu
 #endif
 int g_helpers = 2;          // warps issuing the staged epilogue's TMA stores (vtb_set_option("gemm_helpers", 1 | 2))
 int g_colsum_pair = 1;      // a_colsum launches may use CTA pairs (vtb_set_option("gemm_colsum_pair", 0): 1-CTA tiles as in round 1)
-int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces 1-CTA tiles,
-                              // 2 forces pairs wherever legal (tests)
+int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles wherever legal; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces
+                              // 1-CTA tiles, 2 = 1 (kept for the tests' parametrisation), 3 = pairs only when pairs x splits fill the slots (round 1)
 
 struct EpiParams {
   int M, N;
@@ -1045,7 +1045,12 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
     int per = (k_blocks + splits - 1) / splits;
     splits = (k_blocks + per - 1) / per;
   }
-  if (pair && g_use_clusters != 2 && units * splits < slots) pair = false;  // too little work for pairs: independent 128-row tiles spread wider
+  // Round 1 dropped the pairs when pairs x splits did not fill the pair slots ("independent 128-row tiles spread wider").  They do not:
+  // the split factor is kept, so 1-CTA tiles occupy exactly the SMs the pairs would, with a third more operand traffic per SM
+  // and a shallower ring — the ViT-B fc1 / fc2 weight gradients (36 pair tiles x 2 splits = 72 of 74 slots) ran 16-20 % slower for it
+  // (profiles/r02_cabi_gemm_wgrad_splits_pairs.log; whole steps: ViT-B 34.13 -> 33.44 ms, Swin-S 35.25 -> 34.88, r02_ab_pairs_rule.log).
+  // gemm_cluster = 3 keeps the old rule for A/B.
+  if (pair && g_use_clusters == 3 && units * splits < slots) pair = false;
   switch (bn) {
     case 256: return pair ? dispatch_major<256, 2>(p, e, splits, stream) : dispatch_major<256, 1>(p, e, splits, stream);
     case 128: return pair ? dispatch_major<128, 2>(p, e, splits, stream) : dispatch_major<128, 1>(p, e, splits, stream);
