@@ -48,6 +48,7 @@ int g_gemm_dbg = 0;         // knock-out probes of the staged epilogue (debug bu
 #else
 #define GDBG(e, bit) false
 #endif
+int g_bn_waste_pct = 120;   // tile-N choice: a wider tile may waste this much more of the MMA columns than the next narrower one
 int g_helpers = 2;          // warps issuing the staged epilogue's TMA stores (vtb_set_option("gemm_helpers", 1 | 2))
 int g_colsum_pair = 1;      // a_colsum launches may use CTA pairs (vtb_set_option("gemm_colsum_pair", 0): 1-CTA tiles as in round 1)
 int g_use_clusters = 1;     // CTA-pair (cta_group::2) tiles wherever legal; vtb_set_option("gemm_cluster", 0) / VTB_GEMM_CLUSTER=0 forces
@@ -931,6 +932,7 @@ extern "C" int vtb_set_option(const char* name, int32_t value) {
   VTB_CHECK(name != nullptr, -1, "vtb_set_option: null name");
   if (strcmp(name, "gemm_cluster") == 0) { g_use_clusters = value; return 0; }
   if (strcmp(name, "gemm_colsum_pair") == 0) { g_colsum_pair = value; return 0; }
+  if (strcmp(name, "gemm_bn_waste_pct") == 0) { g_bn_waste_pct = value; return 0; }
   if (strcmp(name, "gemm_helpers") == 0) { g_helpers = value == 2 ? 2 : 1; return 0; }
 #ifdef VTB_GEMM_DBG
   if (strcmp(name, "gemm_dbg") == 0) { g_gemm_dbg = value; return 0; }
@@ -1008,8 +1010,9 @@ extern "C" int vtb_gemm_bf16(const vtb_gemm_params* p, vtb_stream_t stream_) {
   else if (p->N <= 128) bn = 128;
   else {
     auto waste = [&](int b) { return (double)(((p->N + b - 1) / b) * b) / p->N; };
-    if (waste(256) > 1.2 * waste(128)) bn = 128;
-    if (bn == 128 && waste(128) > 1.2 * waste(64)) bn = 64;
+    const double tol = g_bn_waste_pct / 100.0;
+    if (waste(256) > tol * waste(128)) bn = 128;
+    if (bn == 128 && waste(128) > tol * waste(64)) bn = 64;
   }
   const int m_tiles = (p->M + BM - 1) / BM;
   const int n_tiles = (p->N + bn - 1) / bn;
