@@ -25,17 +25,24 @@ const char* vtb_last_error(void);
 int vtb_version(void);
 /* Resolve cuTensorMapEncodeTiled through the runtime, query SM count.  Idempotent. */
 int vtb_init(void);
-/* Runtime switches.  "gemm_cluster" (0/1): run the GEMM as CTA pairs (thread-block clusters of 2) that
- * TMA-multicast the shared B tile into both CTAs' shared memory.  Default 0: measured neutral on B200.
- * "attn_tc" (0/1, default 1): use the tcgen05/TMEM attention kernels where they apply (global attention,
- * dh = 64, <= 256 keys); 0 forces the mma.sync kernels (A/B measurements, cross-checks).
- * "attn_wp" (0/1, default 1): one warp per (window, head) problem when nq, nkv <= 64; 0 = one CTA per problem.
+/* Runtime switches (A/B measurements, cross-checks; also settable from the environment: VTB_OPTS=name=value,... is applied by the
+ * Python loader).  Defaults are the measured-best settings.
+ * "gemm_cluster" (default 1): GEMM tiles as CTA pairs (tcgen05 cta_group::2, 256 x BN tiles, each CTA stages its 128 rows of A and
+ *   half of B) wherever legal; 0 = 1-CTA tiles; 3 = the round-1 rule (pairs only when pairs x splits fill the pair slots).
+ * "gemm_colsum_pair" (default 1): a_colsum launches may use CTA pairs; 0 = 1-CTA tiles for them.
+ * "gemm_helpers" (1/2, default 2): warps that issue the staged epilogue's TMA stores.
+ * "gemm_bn_waste_pct" (default 120): a wider tile-N may waste this much more of the MMA columns than the next narrower one.
+ * "attn_tc" (0/1, default 1): tcgen05/TMEM attention kernels where they apply (global attention, dh = 64, <= 256 keys);
+ *   0 forces the mma.sync kernels.  "attn_tc_fwd_version" / "attn_tc_bwd_version" (1/2, default 2): persistent round-2 kernels or
+ *   the round-1 ones.
+ * "attn_wp" (0/1, default 1): one warp per (window, head) problem when nq, nkv <= 64 on the mma.sync path; 0 = one CTA per problem.
  * "attn_wt" (0/1, default 1): tcgen05 window kernels (two windows per 128-row tile) for WINDOW problems with dh = 32 and
- * <= 64 tokens per window; 0 forces the mma.sync kernels (A/B measurements, cross-checks).
+ *   <= 64 tokens per window; 0 forces the mma.sync kernels.
+ * "attn_ht" (0/1, default 1): tcgen05 halo kernels (dh = 32, <= 64 queries, <= 176 halo slots); 0 forces the mma.sync kernels.
+ *   "attn_ht_dbg": timing knock-outs of the halo backward (results are wrong on purpose).
  * "ln_stream" (0/1, default 1): streaming (bulk-copy staged) LayerNorm kernels; 0 = register-resident kernels.
- * "input_variant" (1/2/3, default 1): vtb_input_batch kernel; 2 = the leaner variant written after the first ncu capture,
- *   3 = the same with 8 pixels per thread when W % 8 == 0 (same results; checked on the host build only so far; both need
- *   a 16-byte aligned table, else variant 1 runs). */
+ * "input_variant" (1/2/3, default 2): vtb_input_batch kernel; 2 = the leaner variant (bit-identical, 5-17 % faster on the B200),
+ *   3 = the same with 8 pixels per thread when W % 8 == 0; both need a 16-byte aligned table, else variant 1 runs. */
 int vtb_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------
