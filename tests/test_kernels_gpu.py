@@ -165,9 +165,11 @@ def test_gemm_splitk_accumulate_and_group_rows(ops, gemm_mode):
     assert rel(got2, 2 * want) < 1e-5
 
 
-@pytest.mark.parametrize("T,N,K", [(1000, 384, 96), (50432 // 8, 3072, 768), (197 * 3, 200, 64)])
+@pytest.mark.parametrize("T,N,K", [(1000, 384, 96), (50432 // 8, 3072, 768), (197 * 3, 200, 64), (4096, 2304, 768)])
 def test_gemm_wgrad_with_fused_bias_gradient(ops, gemm_mode, T, N, K):
-    """dW = g^T x and db = column sums of g from ONE launch (a_colsum: the epilogue warps add up the A tiles in smem)."""
+    """dW = g^T x and db = column sums of g from ONE launch (a_colsum: the epilogue warps add up the A tiles in smem).
+    The last shape gives every CTA several (tile, k-split) work items: the ring is then served between the sub-tile steps
+    of a drain (non-blocking state machine) and the partial sums are flushed per tile."""
     gen = torch.Generator(device="cuda").manual_seed(T + N)
     g = bf(torch.randn(T, N, device="cuda", generator=gen))
     x = bf(torch.randn(T, K, device="cuda", generator=gen))
